@@ -1,0 +1,132 @@
+/* rustpde_b200.h -- C ABI of librustpde_b200.so
+ *
+ * Drop-in boundary for the Navier2D time-step path of preiter93/rustpde
+ * (SURVEY.md section 8b).  The reference is pure Rust with no FFI boundary of
+ * its own; these are the entry points a thin Rust shim (see INTEGRATION.md and
+ * rust/src/lib.rs) binds so that the reference's public API keeps its
+ * signatures while the arithmetic runs in hand-written sm_100a CUDA kernels.
+ *
+ * Conventions
+ *   - every function returns an int status (RP_OK == 0); on failure
+ *     rp_last_error() holds a message.  The Rust shim turns a non-zero status
+ *     into panic!(), the reference's error convention on this path
+ *     (funspace/src/utils.rs:49-76, src/solver/fdma_tensor.rs:201-209).
+ *   - arrays crossing the ABI are caller-owned HOST buffers, dense row-major
+ *     [n0, n1] (ndarray's default layout, funspace/src/space2.rs:75-83), f64;
+ *     complex data is interleaved (re, im) like num_complex::Complex<f64>.
+ *     `len` arguments count doubles and are checked (RP_ERR_SHAPE).
+ *   - device memory, streams and CUDA graphs are owned by the handles.
+ *     A handle is not thread-safe (the reference API is &mut self).
+ *   - there is no CPU fallback: every call below runs on the GPU.
+ */
+#ifndef RUSTPDE_B200_H
+#define RUSTPDE_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+  RP_OK = 0,
+  RP_ERR_INVALID = 1,  /* bad argument / unsupported combination */
+  RP_ERR_SHAPE = 2,    /* size mismatch (reference: panic!)       */
+  RP_ERR_CUDA = 3,
+  RP_ERR_LAPACK = 4,   /* set-up eigendecomposition unavailable/failed */
+  RP_ERR_INTERNAL = 5
+};
+
+/* funspace constructors (funspace/src/lib.rs:230-345) */
+enum {
+  RP_BASE_CHEBYSHEV = 0,         /* chebyshev(n)          */
+  RP_BASE_CHEB_DIRICHLET = 1,    /* cheb_dirichlet(n)     */
+  RP_BASE_CHEB_NEUMANN = 2,      /* cheb_neumann(n)       */
+  RP_BASE_CHEB_DIRICHLET_BC = 3, /* cheb_dirichlet_bc(n)  (set-up helper, host side) */
+  RP_BASE_CHEB_NEUMANN_BC = 4,   /* cheb_neumann_bc(n)    (set-up helper, host side) */
+  RP_BASE_FOURIER_R2C = 5        /* fourier_r2c(n)        */
+};
+
+/* Navier2D pub fields (src/navier/navier.rs:153-195) */
+enum { RP_FIELD_TEMP = 0, RP_FIELD_UX = 1, RP_FIELD_UY = 2, RP_FIELD_PRES = 3, RP_FIELD_PSEUDO_PRES = 4, RP_FIELD_WORK = 5 };
+
+typedef struct rp_field rp_field_t;
+typedef struct rp_solver rp_solver_t;
+typedef struct rp_navier rp_navier_t;
+
+/* ---- library ----------------------------------------------------------- */
+int rp_init(int device);                 /* selects the CUDA device, sets kernel attributes */
+const char* rp_last_error(void);
+int rp_version(void);
+int rp_is_emulated(void);                /* 0 in the product library */
+int rp_set_lapack_library(const char* path); /* dgeev/dgetri provider for solver set-up (utils.rs:66-106) */
+
+/* ---- Field2 (src/field.rs:66-129) --------------------------------------- */
+/* Field2::new(&Space2::new(&base_x, &base_y)) */
+int rp_field_create(int kind_x, int nx, int kind_y, int ny, rp_field_t** out);
+int rp_field_destroy(rp_field_t* f);
+/* shapes: physical, spectral, ortho-spectral; is_complex = spectral type is Complex<f64> */
+int rp_field_shape(rp_field_t* f, int phys[2], int spec[2], int ortho[2], int* is_complex);
+int rp_field_coords(rp_field_t* f, int axis, double* x, size_t len);   /* pub x  */
+int rp_field_dx(rp_field_t* f, int axis, double* dx, size_t len);      /* pub dx */
+int rp_field_upload_v(rp_field_t* f, const double* v, size_t len);      /* pub v    */
+int rp_field_download_v(rp_field_t* f, double* v, size_t len);
+int rp_field_upload_vhat(rp_field_t* f, const double* vhat, size_t len);/* pub vhat */
+int rp_field_download_vhat(rp_field_t* f, double* vhat, size_t len);
+int rp_field_forward(rp_field_t* f);                                    /* field.rs:103-105 */
+int rp_field_backward(rp_field_t* f);                                   /* field.rs:108-110 */
+int rp_field_to_ortho(rp_field_t* f, double* out, size_t len);          /* field.rs:113-115 */
+int rp_field_from_ortho(rp_field_t* f, const double* in, size_t len);   /* field.rs:118-123 */
+/* field.rs:127-129; scale may be NULL (None) or point to [sx, sy] */
+int rp_field_gradient(rp_field_t* f, int dx, int dy, const double* scale, double* out, size_t len);
+int rp_field_average(rp_field_t* f, double* out);                       /* average.rs:51-57 */
+int rp_field_average_axis(rp_field_t* f, int axis, double* out, size_t len); /* average.rs:25-33 (axis 0) */
+
+/* ---- solvers (src/solver.rs:56-155) -------------------------------------- */
+int rp_hholtz_create(rp_field_t* f, double cx, double cy, double alpha, rp_solver_t** out); /* Hholtz::new (alpha=1) / new2, hholtz.rs:42,81 */
+int rp_hholtz_adi_create(rp_field_t* f, double cx, double cy, rp_solver_t** out);          /* HholtzAdi::new, hholtz_adi.rs:44 */
+int rp_poisson_create(rp_field_t* f, double cx, double cy, rp_solver_t** out);             /* Poisson::new, poisson.rs:50 */
+/* Same, with the eigen set-up data (lam[m], Q[m*m], P = Q^-1 Cx^-1 [m*m], row-major,
+ * m = nx-2) supplied by the caller instead of LAPACK -- this is what makes
+ * <=1e-10 parity of the fast-diagonalisation solve well defined. */
+int rp_hholtz_create_with_eig(rp_field_t* f, double cx, double cy, double alpha, const double* lam, const double* q,
+                              const double* p, rp_solver_t** out);
+int rp_poisson_create_with_eig(rp_field_t* f, double cx, double cy, const double* lam, const double* q, const double* p,
+                               rp_solver_t** out);
+int rp_solver_eig_size(rp_solver_t* s, int* m, int* has_matrices);
+int rp_solver_export_eig(rp_solver_t* s, double* lam, double* q, double* p);
+/* Solve::solve(&self, input, output, axis) ; input [n0,n1] ortho, output composite */
+int rp_solver_solve(rp_solver_t* s, const double* in, size_t in_len, double* out, size_t out_len, int is_complex);
+int rp_solver_destroy(rp_solver_t* s);
+
+/* ---- Navier2D (src/navier/navier.rs) -------------------------------------- */
+/* Navier2D::new (219-307) when periodic == 0, Navier2D::new_periodic (384-467) otherwise.
+ * Unlike the reference constructors, which add an UNSEEDED random disturbance
+ * (navier.rs:304,464), all fields start at zero: set deterministic ICs. */
+int rp_navier_create(int nx, int ny, double ra, double pr, double dt, double aspect, int adiabatic, int periodic,
+                     rp_navier_t** out);
+int rp_navier_create_with_eig(int nx, int ny, double ra, double pr, double dt, double aspect, int adiabatic,
+                              const double* lam, const double* q, const double* p, rp_navier_t** out);
+int rp_navier_destroy(rp_navier_t* h);
+int rp_navier_set_velocity(rp_navier_t* h, double amp, double m, double n);    /* 927-930 */
+int rp_navier_set_temperature(rp_navier_t* h, double amp, double m, double n); /* 934-936 */
+int rp_navier_set_tempbc_ortho(rp_navier_t* h, const double* that_bc, size_t len); /* set_temp_bc, 517-519 (ortho coefficients) */
+int rp_navier_set_dealias(rp_navier_t* h, int on);                             /* pub dealias */
+int rp_navier_update(rp_navier_t* h, int nsteps);                              /* Integrate::update, 737-765 (x nsteps, asynchronous) */
+int rp_navier_sync(rp_navier_t* h);
+int rp_navier_get_time(rp_navier_t* h, double* time);                          /* get_time */
+int rp_navier_get_dt(rp_navier_t* h, double* dt);                              /* get_dt */
+int rp_navier_reset_time(rp_navier_t* h);                                      /* 951-953 */
+int rp_navier_params(rp_navier_t* h, double* nu, double* ka, double scale[2]); /* pub nu, ka, scale */
+/* eval_nu / eval_nuvol / eval_re (890-921), |div|_2 (exit(), 855-879) and <(ux^2+uy^2)/2>;
+ * any pointer may be NULL */
+int rp_navier_eval(rp_navier_t* h, double* nu, double* nuvol, double* re, double* div_norm, double* ekin);
+int rp_navier_field(rp_navier_t* h, int which, rp_field_t** out);              /* borrowed handle */
+int rp_navier_export_eig(rp_navier_t* h, double* lam, double* q, double* p);   /* pressure Poisson set-up data */
+int rp_navier_launches_per_step(rp_navier_t* h, int* n);
+int rp_navier_set_graph(rp_navier_t* h, int on);                               /* CUDA-graph replay of update() (default on) */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RUSTPDE_B200_H */

@@ -1,0 +1,29 @@
+"""rustpde_b200 -- B200-native Navier2D time step of preiter93/rustpde.
+
+Hand-written sm_100a CUDA kernels behind a C ABI (include/rustpde_b200.h,
+librustpde_b200.so) with a host-side mirror of the reference API (api.py).
+Importing the package does not touch the GPU; the first object created loads
+the CUDA library and raises if it (or a GPU) is missing -- no CPU fallback.
+"""
+from .api import (  # noqa: F401
+    Base,
+    Field2,
+    Hholtz,
+    HholtzAdi,
+    Navier2D,
+    Poisson,
+    RustpdeError,
+    Space2,
+    cheb_dirichlet,
+    cheb_dirichlet_bc,
+    cheb_neumann,
+    cheb_neumann_bc,
+    chebyshev,
+    fourier_r2c,
+    integrate,
+)
+
+__all__ = [
+    "Base", "Field2", "Hholtz", "HholtzAdi", "Navier2D", "Poisson", "RustpdeError", "Space2",
+    "cheb_dirichlet", "cheb_dirichlet_bc", "cheb_neumann", "cheb_neumann_bc", "chebyshev", "fourier_r2c", "integrate",
+]

@@ -1,0 +1,461 @@
+"""Host-side mirror of the reference's public API on the Navier2D path, over
+the C ABI of librustpde_b200.so (same names, argument meaning and error
+behaviour as rustpde; citations are reference file:line).
+
+    funspace:  chebyshev, cheb_dirichlet, cheb_neumann, fourier_r2c, Space2
+    field:     Field2 (v, vhat, x, dx, forward, backward, to_ortho, from_ortho, gradient)
+    solver:    Hholtz (new / new2), HholtzAdi, Poisson  -- .solve(input, output, axis)
+    navier:    Navier2D.new / new_periodic, set_velocity, set_temperature,
+               update, callback, exit, eval_nu / eval_nuvol / eval_re; integrate()
+
+Every object takes an optional keyword `lib=`; the default is the CUDA
+library (`_ffi.product_lib()`), which raises if it cannot be loaded.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _ffi
+from ._ffi import RustpdeError  # noqa: F401
+
+BASE_CHEBYSHEV, BASE_CHEB_DIRICHLET, BASE_CHEB_NEUMANN, BASE_CHEB_DIRICHLET_BC, BASE_CHEB_NEUMANN_BC, BASE_FOURIER_R2C = range(6)
+MAX_TIMESTEP = 10_000_000  # src/lib.rs:132
+
+
+def _dp(a):
+    return a.ctypes.data_as(_ffi.c_double_p)
+
+
+def _as_f64(a, cplx):
+    a = np.ascontiguousarray(a, dtype=np.complex128 if cplx else np.float64)
+    return a, a.view(np.float64).reshape(-1)
+
+
+class Base:
+    """One funspace base (funspace/src/lib.rs:230-345)."""
+
+    def __init__(self, kind, n):
+        self.kind, self.n = kind, n
+
+    def len_phys(self):
+        return self.n
+
+    def len_spec(self):
+        if self.kind == BASE_CHEBYSHEV:
+            return self.n
+        if self.kind in (BASE_CHEB_DIRICHLET, BASE_CHEB_NEUMANN):
+            return self.n - 2
+        if self.kind == BASE_FOURIER_R2C:
+            return self.n // 2 + 1
+        return 2
+
+
+def chebyshev(n):
+    return Base(BASE_CHEBYSHEV, n)
+
+
+def cheb_dirichlet(n):
+    return Base(BASE_CHEB_DIRICHLET, n)
+
+
+def cheb_neumann(n):
+    return Base(BASE_CHEB_NEUMANN, n)
+
+
+def cheb_dirichlet_bc(n):
+    return Base(BASE_CHEB_DIRICHLET_BC, n)
+
+
+def cheb_neumann_bc(n):
+    return Base(BASE_CHEB_NEUMANN_BC, n)
+
+
+def fourier_r2c(n):
+    return Base(BASE_FOURIER_R2C, n)
+
+
+class Space2:
+    """funspace/src/space2.rs:42-53."""
+
+    def __init__(self, base0, base1):
+        self.base0, self.base1 = base0, base1
+
+
+class Field2:
+    """src/field.rs:66-129.  `v` / `vhat` are host mirrors of the device arrays:
+    reading downloads, assigning uploads."""
+
+    def __init__(self, space=None, lib=None, _handle=None, _owner=None):
+        self._lib = lib or _ffi.product_lib()
+        self._owner = _owner
+        if _handle is None:
+            h = C.c_void_p()
+            self._lib.call("rp_field_create", space.base0.kind, space.base0.n, space.base1.kind, space.base1.n, C.byref(h))
+            self._h, self._owned = h, True
+        else:
+            self._h, self._owned = _handle, False
+        ph, sp, ort, cx = (C.c_int * 2)(), (C.c_int * 2)(), (C.c_int * 2)(), C.c_int()
+        self._lib.call("rp_field_shape", self._h, ph, sp, ort, C.byref(cx))
+        self.shape_physical, self.shape_spectral, self.shape_ortho = tuple(ph), tuple(sp), tuple(ort)
+        self.is_complex = bool(cx.value)
+        self.ndim = 2
+        self.space = space
+
+    def __del__(self):
+        try:
+            if getattr(self, "_owned", False):
+                self._lib.c.rp_field_destroy(self._h)
+        except Exception:
+            pass
+
+    @property
+    def spectral_dtype(self):
+        return np.complex128 if self.is_complex else np.float64
+
+    def _coords(self, fn):
+        out = []
+        for axis in range(2):
+            # the Fourier grid may have n or (rarely) n+1 points: ask with the physical size first
+            n = self.shape_physical[axis]
+            for trial in (n, n + 1):
+                a = np.zeros(trial)
+                if self._lib.c.__getattr__(fn)(self._h, axis, _dp(a), trial) == 0:
+                    out.append(a)
+                    break
+            else:
+                raise RuntimeError("coords query failed")
+        return out
+
+    @property
+    def x(self):
+        return self._coords("rp_field_coords")
+
+    @property
+    def dx(self):
+        return self._coords("rp_field_dx")
+
+    @property
+    def v(self):
+        a = np.zeros(self.shape_physical)
+        self._lib.call("rp_field_download_v", self._h, _dp(a), a.size)
+        return a
+
+    @v.setter
+    def v(self, val):
+        a, flat = _as_f64(val, False)
+        if a.shape != self.shape_physical:
+            raise RustpdeError(2, "v: shape mismatch %s vs %s" % (a.shape, self.shape_physical))
+        self._lib.call("rp_field_upload_v", self._h, _dp(flat), flat.size)
+
+    @property
+    def vhat(self):
+        a = np.zeros(self.shape_spectral, dtype=self.spectral_dtype)
+        flat = a.view(np.float64).reshape(-1)
+        self._lib.call("rp_field_download_vhat", self._h, _dp(flat), flat.size)
+        return a
+
+    @vhat.setter
+    def vhat(self, val):
+        a, flat = _as_f64(val, self.is_complex)
+        if a.shape != self.shape_spectral:
+            raise RustpdeError(2, "vhat: shape mismatch %s vs %s" % (a.shape, self.shape_spectral))
+        self._lib.call("rp_field_upload_vhat", self._h, _dp(flat), flat.size)
+
+    def forward(self):  # field.rs:103-105
+        self._lib.call("rp_field_forward", self._h)
+
+    def backward(self):  # field.rs:108-110
+        self._lib.call("rp_field_backward", self._h)
+
+    def to_ortho(self):  # field.rs:113-115
+        a = np.zeros(self.shape_ortho, dtype=self.spectral_dtype)
+        flat = a.view(np.float64).reshape(-1)
+        self._lib.call("rp_field_to_ortho", self._h, _dp(flat), flat.size)
+        return a
+
+    def from_ortho(self, inp):  # field.rs:118-123
+        a, flat = _as_f64(inp, self.is_complex)
+        if a.shape != self.shape_ortho:
+            raise RustpdeError(2, "from_ortho: shape mismatch %s vs %s" % (a.shape, self.shape_ortho))
+        self._lib.call("rp_field_from_ortho", self._h, _dp(flat), flat.size)
+
+    def gradient(self, deriv, scale=None):  # field.rs:127-129
+        a = np.zeros(self.shape_ortho, dtype=self.spectral_dtype)
+        flat = a.view(np.float64).reshape(-1)
+        sc = None if scale is None else _dp(np.asarray(scale, dtype=np.float64))
+        self._lib.call("rp_field_gradient", self._h, int(deriv[0]), int(deriv[1]), sc, _dp(flat), flat.size)
+        return a
+
+    def average(self):  # average.rs:51-57
+        out = C.c_double()
+        self._lib.call("rp_field_average", self._h, C.byref(out))
+        return out.value
+
+    def average_axis(self, axis):  # average.rs:25-33
+        a = np.zeros(self.shape_physical[1])
+        self._lib.call("rp_field_average_axis", self._h, axis, _dp(a), a.size)
+        return a
+
+
+class _Solver:
+    def __init__(self):
+        self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            if self._h:
+                self._lib.c.rp_solver_destroy(self._h)
+        except Exception:
+            pass
+
+    def _shapes(self, field):
+        b0, b1 = field.space.base0, field.space.base1
+        four = b0.kind == BASE_FOURIER_R2C
+        self.shape_in = ((b0.n // 2 + 1) if four else b0.n, b1.n)
+        self.shape_out = ((b0.n // 2 + 1) if four else b0.n - 2, b1.n - 2)
+
+    def solve(self, inp, output=None, axis=0):
+        """Solve::solve (src/solver.rs:60-66); shape mismatch raises (reference: panic!)."""
+        cplx = np.iscomplexobj(inp)
+        a, flat = _as_f64(inp, cplx)
+        if a.shape != self.shape_in:
+            raise RustpdeError(2, "Dimension mismatch in solver input: %s vs %s" % (a.shape, self.shape_in))
+        out = np.zeros(self.shape_out, dtype=a.dtype)
+        oflat = out.view(np.float64).reshape(-1)
+        self._lib.call("rp_solver_solve", self._h, _dp(flat), flat.size, _dp(oflat), oflat.size, int(cplx))
+        if output is not None:
+            output[...] = out
+        return out
+
+    def export_eig(self):
+        m, has = C.c_int(), C.c_int()
+        self._lib.call("rp_solver_eig_size", self._h, C.byref(m), C.byref(has))
+        lam = np.zeros(m.value)
+        q = np.zeros((m.value, m.value)) if has.value else None
+        p = np.zeros((m.value, m.value)) if has.value else None
+        self._lib.call("rp_solver_export_eig", self._h, _dp(lam), _dp(q) if has.value else None, _dp(p) if has.value else None)
+        return lam, q, p
+
+
+def _eig_args(eig):
+    lam, q, p = (np.ascontiguousarray(e, dtype=np.float64) for e in eig)
+    return lam, q, p
+
+
+class Hholtz(_Solver):
+    """src/solver/hholtz.rs:42 (new) / :81 (new2): (alpha I - c D2) vhat = A f."""
+
+    def __init__(self, field, c, alpha=1.0, eig=None, lib=None):
+        super().__init__()
+        self._lib = lib or field._lib
+        self._shapes(field)
+        if eig is None:
+            self._lib.call("rp_hholtz_create", field._h, float(c[0]), float(c[1]), float(alpha), C.byref(self._h))
+        else:
+            lam, q, p = _eig_args(eig)
+            self._lib.call("rp_hholtz_create_with_eig", field._h, float(c[0]), float(c[1]), float(alpha), _dp(lam), _dp(q), _dp(p), C.byref(self._h))
+
+    @classmethod
+    def new2(cls, field, c, alpha, **kw):
+        return cls(field, c, alpha, **kw)
+
+
+class HholtzAdi(_Solver):
+    """src/solver/hholtz_adi.rs:44."""
+
+    def __init__(self, field, c, lib=None):
+        super().__init__()
+        self._lib = lib or field._lib
+        self._shapes(field)
+        self._lib.call("rp_hholtz_adi_create", field._h, float(c[0]), float(c[1]), C.byref(self._h))
+
+
+class Poisson(_Solver):
+    """src/solver/poisson.rs:50."""
+
+    def __init__(self, field, c, eig=None, lib=None):
+        super().__init__()
+        self._lib = lib or field._lib
+        self._shapes(field)
+        if eig is None:
+            self._lib.call("rp_poisson_create", field._h, float(c[0]), float(c[1]), C.byref(self._h))
+        else:
+            lam, q, p = _eig_args(eig)
+            self._lib.call("rp_poisson_create_with_eig", field._h, float(c[0]), float(c[1]), _dp(lam), _dp(q), _dp(p), C.byref(self._h))
+
+
+class Navier2D:
+    """src/navier/navier.rs:153-195.  Use Navier2D.new(...) / Navier2D.new_periodic(...)."""
+
+    def __init__(self):
+        raise TypeError("use Navier2D.new(...) or Navier2D.new_periodic(...)")
+
+    @classmethod
+    def _make(cls, nx, ny, ra, pr, dt, aspect, adiabatic, periodic, eig, lib):
+        s = object.__new__(cls)
+        s._lib = lib or _ffi.product_lib()
+        s._h = C.c_void_p()
+        if eig is not None and not periodic:
+            lam, q, p = _eig_args(eig)
+            s._lib.call("rp_navier_create_with_eig", nx, ny, ra, pr, dt, aspect, int(adiabatic), _dp(lam), _dp(q), _dp(p), C.byref(s._h))
+        else:
+            s._lib.call("rp_navier_create", nx, ny, ra, pr, dt, aspect, int(adiabatic), int(periodic), C.byref(s._h))
+        s.nx, s.ny, s.ra, s.pr, s.dt, s.periodic = nx, ny, ra, pr, dt, bool(periodic)
+        nu, ka, sc = C.c_double(), C.c_double(), (C.c_double * 2)()
+        s._lib.call("rp_navier_params", s._h, C.byref(nu), C.byref(ka), sc)
+        s.nu, s.ka, s.scale = nu.value, ka.value, [sc[0], sc[1]]
+        kx = fourier_r2c if periodic else None
+        spaces = {
+            0: Space2((kx or (cheb_neumann if adiabatic else cheb_dirichlet))(nx), cheb_dirichlet(ny)),
+            1: Space2((kx or cheb_dirichlet)(nx), cheb_dirichlet(ny)),
+            2: Space2((kx or cheb_dirichlet)(nx), cheb_dirichlet(ny)),
+            3: Space2((kx or chebyshev)(nx), chebyshev(ny)),
+            4: Space2((kx or cheb_neumann)(nx), cheb_neumann(ny)),
+            5: Space2((kx or chebyshev)(nx), chebyshev(ny)),
+        }
+        flds = []
+        for i in range(6):
+            fh = C.c_void_p()
+            s._lib.call("rp_navier_field", s._h, i, C.byref(fh))
+            flds.append(Field2(spaces[i], lib=s._lib, _handle=fh, _owner=s))
+        s.temp, s.ux, s.uy = flds[0], flds[1], flds[2]
+        s.pres = [flds[3], flds[4]]
+        s.field = flds[5]
+        s.diagnostics = {"time": [], "Nu": [], "Nuvol": [], "Re": []}
+        s.write_intervall = None
+        s.solid = None
+        s.statistics = None
+        s._dealias = True
+        return s
+
+    @classmethod
+    def new(cls, nx, ny, ra, pr, dt, aspect, adiabatic, eig=None, lib=None):  # navier.rs:219-307
+        return cls._make(nx, ny, ra, pr, dt, aspect, adiabatic, False, eig, lib)
+
+    @classmethod
+    def new_periodic(cls, nx, ny, ra, pr, dt, aspect, lib=None):  # navier.rs:384-467
+        return cls._make(nx, ny, ra, pr, dt, aspect, True, True, None, lib)
+
+    def __del__(self):
+        try:
+            if self._h:
+                self._lib.c.rp_navier_destroy(self._h)
+        except Exception:
+            pass
+
+    @property
+    def dealias(self):
+        return self._dealias
+
+    @dealias.setter
+    def dealias(self, on):
+        self._lib.call("rp_navier_set_dealias", self._h, int(bool(on)))
+        self._dealias = bool(on)
+
+    @property
+    def time(self):
+        t = C.c_double()
+        self._lib.call("rp_navier_get_time", self._h, C.byref(t))
+        return t.value
+
+    def set_velocity(self, amp, m, n):  # navier.rs:927-930
+        self._lib.call("rp_navier_set_velocity", self._h, float(amp), float(m), float(n))
+
+    def set_temperature(self, amp, m, n):  # navier.rs:934-936
+        self._lib.call("rp_navier_set_temperature", self._h, float(amp), float(m), float(n))
+
+    def set_temp_bc_ortho(self, that_bc):  # set_temp_bc, navier.rs:517-519 (ortho coefficients)
+        a, flat = _as_f64(that_bc, self.periodic)
+        self._lib.call("rp_navier_set_tempbc_ortho", self._h, _dp(flat), flat.size)
+
+    def reset_time(self):  # navier.rs:951-953
+        self._lib.call("rp_navier_reset_time", self._h)
+
+    def set_graph(self, on):
+        self._lib.call("rp_navier_set_graph", self._h, int(bool(on)))
+
+    # ---- Integrate (src/lib.rs:135-146, navier.rs:737-862) ----------------
+    def update(self, nsteps=1):
+        """Integrate::update; nsteps > 1 queues several steps without a host sync."""
+        self._lib.call("rp_navier_update", self._h, int(nsteps))
+
+    def sync(self):
+        self._lib.call("rp_navier_sync", self._h)
+
+    def get_time(self):
+        return self.time
+
+    def get_dt(self):
+        return self.dt
+
+    def eval(self, nu=True, nuvol=True, re=True, div=True, ekin=True):
+        vals = [C.c_double() for _ in range(5)]
+        want = [nu, nuvol, re, div, ekin]
+        args = [C.byref(v) if w else None for v, w in zip(vals, want)]
+        self._lib.call("rp_navier_eval", self._h, *args)
+        return [v.value if w else None for v, w in zip(vals, want)]
+
+    def eval_nu(self):  # navier.rs:890-893
+        return self.eval(True, False, False, False, False)[0]
+
+    def eval_nuvol(self):  # navier.rs:899-909
+        return self.eval(False, True, False, False, False)[1]
+
+    def eval_re(self):  # navier.rs:912-921
+        return self.eval(False, False, True, False, False)[2]
+
+    def eval_ekin(self):
+        return self.eval(False, False, False, False, True)[4]
+
+    def div_norm(self):
+        return self.eval(False, False, False, True, False)[3]
+
+    def callback(self):  # navier.rs:775-853 (diagnostics; HDF5 output is out of scope)
+        nu, nuvol, re, div, _ = self.eval(True, True, True, True, False)
+        t = self.time
+        print("time = %4.2f      |div| = %4.2e     Nu = %5.3e     Nuv = %5.3e    Re = %5.3e" % (t, div, nu, nuvol, re))
+        self.diagnostics["time"].append(t)
+        self.diagnostics["Nu"].append(nu)
+        self.diagnostics["Nuvol"].append(nuvol)
+        self.diagnostics["Re"].append(re)
+
+    def exit(self):  # navier.rs:855-862: stop when |div| is NaN
+        return math.isnan(self.div_norm())
+
+    def export_eig(self):
+        m = self.nx - 2
+        lam, q, p = np.zeros(m), np.zeros((m, m)), np.zeros((m, m))
+        if self.periodic:
+            raise RustpdeError(1, "periodic Navier2D has no eigen set-up data")
+        self._lib.call("rp_navier_export_eig", self._h, _dp(lam), _dp(q), _dp(p))
+        return lam, q, p
+
+    def launches_per_step(self):
+        n = C.c_int()
+        self._lib.call("rp_navier_launches_per_step", self._h, C.byref(n))
+        return n.value
+
+
+def integrate(pde, max_time, save_intervall=None, exit_every=1):
+    """src/lib.rs:155-187.  `exit_every` > 1 checks the NaN break criterion less
+    often (the reference checks every step, which costs a device sync)."""
+    timestep = 0
+    eps_dt = pde.get_dt() * 1e-4
+    while True:
+        pde.update()
+        timestep += 1
+        if save_intervall is not None:
+            t, dt = pde.get_time(), pde.get_dt()
+            if (t % save_intervall) < dt / 2.0 or (t % save_intervall) > save_intervall - dt / 2.0:
+                pde.callback()
+        if pde.get_time() + eps_dt >= max_time:
+            print("time limit reached: %r" % pde.get_time())
+            break
+        if timestep >= MAX_TIMESTEP:
+            print("timestep limit reached: %r" % timestep)
+            break
+        if timestep % exit_every == 0 and pde.exit():
+            print("break criteria triggered")
+            break
+    return timestep

@@ -1,0 +1,360 @@
+// capi.cu -- extern "C" boundary (include/rustpde_b200.h).
+#include <cstring>
+#include <string>
+
+#include "../../include/rustpde_b200.h"
+#include "model.h"
+
+using namespace rp;
+
+struct rp_field {
+  Field2* f;
+  bool owned;
+};
+struct rp_solver {
+  Solver2* s;
+};
+struct rp_navier {
+  Navier2D* n;
+  rp_field views[6];
+};
+
+static thread_local std::string g_last_error;
+
+template <class F>
+static int guard(F&& fn) {
+  try {
+    fn();
+    return RP_OK;
+  } catch (const rp::Error& e) {
+    g_last_error = e.what();
+    return e.code;
+  } catch (const std::exception& e) {
+    g_last_error = e.what();
+    return RP_ERR_INTERNAL;
+  } catch (...) {
+    g_last_error = "unknown error";
+    return RP_ERR_INTERNAL;
+  }
+}
+
+static void need(bool c, int code, const char* msg) {
+  if (!c) throw rp::Error(code, msg);
+}
+
+#pragma GCC visibility push(default)
+extern "C" {
+
+int rp_init(int device) {
+  return guard([&] {
+#ifndef RP_EMU
+    RP_CUDA_CHECK(cudaSetDevice(device));
+    RP_CUDA_CHECK(cudaFree(0));
+#else
+    (void)device;
+#endif
+    init_kernels();
+  });
+}
+const char* rp_last_error(void) { return g_last_error.c_str(); }
+int rp_version(void) { return 100; }
+int rp_is_emulated(void) {
+#ifdef RP_EMU
+  return 1;
+#else
+  return 0;
+#endif
+}
+int rp_set_lapack_library(const char* path) {
+  return guard([&] { lapack_set_library(path); });
+}
+
+// ---- Field2 ---------------------------------------------------------------
+int rp_field_create(int kind_x, int nx, int kind_y, int ny, rp_field_t** out) {
+  return guard([&] {
+    need(out != nullptr, RP_ERR_INVALID, "null out pointer");
+    Space2 sp{get_base(kind_x, nx), get_base(kind_y, ny)};
+    *out = new rp_field{new Field2(sp), true};
+  });
+}
+int rp_field_destroy(rp_field_t* f) {
+  return guard([&] {
+    if (!f) return;
+    if (f->owned) {
+      delete f->f;
+      delete f;
+    }
+  });
+}
+int rp_field_shape(rp_field_t* f, int phys[2], int spec[2], int ortho[2], int* is_complex) {
+  return guard([&] {
+    need(f, RP_ERR_INVALID, "null field");
+    if (phys) phys[0] = f->f->n0, phys[1] = f->f->n1;
+    if (spec) spec[0] = f->f->m0, spec[1] = f->f->m1;
+    if (ortho) ortho[0] = f->f->o0, ortho[1] = f->f->o1;
+    if (is_complex) *is_complex = f->f->cplx ? 1 : 0;
+  });
+}
+static int copy_vec(const std::vector<double>& v, double* out, size_t len) {
+  return guard([&] {
+    need(len == v.size(), RP_ERR_SHAPE, "coordinate length mismatch");
+    std::copy(v.begin(), v.end(), out);
+  });
+}
+int rp_field_coords(rp_field_t* f, int axis, double* x, size_t len) {
+  if (!f || axis < 0 || axis > 1) return RP_ERR_INVALID;
+  return copy_vec(f->f->x[axis], x, len);
+}
+int rp_field_dx(rp_field_t* f, int axis, double* dx, size_t len) {
+  if (!f || axis < 0 || axis > 1) return RP_ERR_INVALID;
+  return copy_vec(f->f->dx[axis], dx, len);
+}
+static size_t arr_len(const Arr& a) { return (size_t)a.rows * a.cols * (a.cplx ? 2 : 1); }
+
+int rp_field_upload_v(rp_field_t* f, const double* v, size_t len) {
+  return guard([&] {
+    need(f && v, RP_ERR_INVALID, "null argument");
+    need(len == arr_len(f->f->v), RP_ERR_SHAPE, "v: size mismatch");
+    f->f->v.upload(v, f->f->stream);
+    rt::sync(f->f->stream);
+  });
+}
+int rp_field_download_v(rp_field_t* f, double* v, size_t len) {
+  return guard([&] {
+    need(f && v, RP_ERR_INVALID, "null argument");
+    need(len == arr_len(f->f->v), RP_ERR_SHAPE, "v: size mismatch");
+    f->f->v.download(v, f->f->stream);
+    rt::sync(f->f->stream);
+  });
+}
+int rp_field_upload_vhat(rp_field_t* f, const double* v, size_t len) {
+  return guard([&] {
+    need(f && v, RP_ERR_INVALID, "null argument");
+    need(len == arr_len(f->f->vhat), RP_ERR_SHAPE, "vhat: size mismatch");
+    f->f->vhat.upload(v, f->f->stream);
+    rt::sync(f->f->stream);
+  });
+}
+int rp_field_download_vhat(rp_field_t* f, double* v, size_t len) {
+  return guard([&] {
+    need(f && v, RP_ERR_INVALID, "null argument");
+    need(len == arr_len(f->f->vhat), RP_ERR_SHAPE, "vhat: size mismatch");
+    f->f->vhat.download(v, f->f->stream);
+    rt::sync(f->f->stream);
+  });
+}
+int rp_field_forward(rp_field_t* f) {
+  return guard([&] {
+    need(f, RP_ERR_INVALID, "null field");
+    f->f->forward();
+  });
+}
+int rp_field_backward(rp_field_t* f) {
+  return guard([&] {
+    need(f, RP_ERR_INVALID, "null field");
+    f->f->backward();
+  });
+}
+int rp_field_to_ortho(rp_field_t* f, double* out, size_t len) {
+  return guard([&] {
+    need(f && out, RP_ERR_INVALID, "null argument");
+    need(len == arr_len(f->f->ortho), RP_ERR_SHAPE, "to_ortho: output size mismatch");
+    f->f->to_ortho();
+    f->f->ortho.download(out, f->f->stream);
+    rt::sync(f->f->stream);
+  });
+}
+int rp_field_from_ortho(rp_field_t* f, const double* in, size_t len) {
+  return guard([&] {
+    need(f && in, RP_ERR_INVALID, "null argument");
+    need(len == arr_len(f->f->ortho), RP_ERR_SHAPE, "from_ortho: input size mismatch");
+    f->f->ortho.upload(in, f->f->stream);
+    f->f->from_ortho();
+    rt::sync(f->f->stream);
+  });
+}
+int rp_field_gradient(rp_field_t* f, int dx, int dy, const double* scale, double* out, size_t len) {
+  return guard([&] {
+    need(f && out, RP_ERR_INVALID, "null argument");
+    need(dx >= 0 && dy >= 0 && dx <= 4 && dy <= 4, RP_ERR_INVALID, "derivative order out of range");
+    need(len == arr_len(f->f->ortho), RP_ERR_SHAPE, "gradient: output size mismatch");
+    f->f->gradient(dx, dy, scale);
+    f->f->ortho.download(out, f->f->stream);
+    rt::sync(f->f->stream);
+  });
+}
+int rp_field_average(rp_field_t* f, double* out) {
+  return guard([&] {
+    need(f && out, RP_ERR_INVALID, "null argument");
+    *out = f->f->average();
+  });
+}
+int rp_field_average_axis(rp_field_t* f, int axis, double* out, size_t len) {
+  return guard([&] {
+    need(f && out, RP_ERR_INVALID, "null argument");
+    need(axis == 0, RP_ERR_INVALID, "average_axis: only axis 0 is on the Navier2D path");
+    need(len == (size_t)f->f->n1, RP_ERR_SHAPE, "average_axis: output size mismatch");
+    std::vector<double> v;
+    f->f->average_axis0(v);
+    std::copy(v.begin(), v.end(), out);
+  });
+}
+
+// ---- solvers --------------------------------------------------------------
+static int make_solver(int kind, rp_field_t* f, double cx, double cy, double alpha, const double* lam, const double* q,
+                       const double* p, rp_solver_t** out) {
+  return guard([&] {
+    need(f && out, RP_ERR_INVALID, "null argument");
+    EigData e;
+    e.lam = lam, e.q = q, e.p = p;
+    *out = new rp_solver{new Solver2(kind, f->f->sp, cx, cy, alpha, (lam && q && p) ? &e : nullptr)};
+  });
+}
+int rp_hholtz_create(rp_field_t* f, double cx, double cy, double alpha, rp_solver_t** out) {
+  return make_solver(SOLVER_HHOLTZ, f, cx, cy, alpha, nullptr, nullptr, nullptr, out);
+}
+int rp_hholtz_adi_create(rp_field_t* f, double cx, double cy, rp_solver_t** out) {
+  return make_solver(SOLVER_HHOLTZ_ADI, f, cx, cy, 1.0, nullptr, nullptr, nullptr, out);
+}
+int rp_poisson_create(rp_field_t* f, double cx, double cy, rp_solver_t** out) {
+  return make_solver(SOLVER_POISSON, f, cx, cy, 0.0, nullptr, nullptr, nullptr, out);
+}
+int rp_hholtz_create_with_eig(rp_field_t* f, double cx, double cy, double alpha, const double* lam, const double* q,
+                              const double* p, rp_solver_t** out) {
+  return make_solver(SOLVER_HHOLTZ, f, cx, cy, alpha, lam, q, p, out);
+}
+int rp_poisson_create_with_eig(rp_field_t* f, double cx, double cy, const double* lam, const double* q, const double* p,
+                               rp_solver_t** out) {
+  return make_solver(SOLVER_POISSON, f, cx, cy, 0.0, lam, q, p, out);
+}
+int rp_solver_eig_size(rp_solver_t* s, int* m, int* has_matrices) {
+  return guard([&] {
+    need(s, RP_ERR_INVALID, "null solver");
+    if (m) *m = s->s->m0;
+    if (has_matrices) *has_matrices = (s->s->kind != SOLVER_HHOLTZ_ADI && !s->s->x_fourier) ? 1 : 0;
+  });
+}
+int rp_solver_export_eig(rp_solver_t* s, double* lam, double* q, double* p) {
+  return guard([&] {
+    need(s, RP_ERR_INVALID, "null solver");
+    s->s->export_eig(lam, q, p);
+  });
+}
+int rp_solver_solve(rp_solver_t* s, const double* in, size_t in_len, double* out, size_t out_len, int is_complex) {
+  return guard([&] {
+    need(s && in && out, RP_ERR_INVALID, "null argument");
+    Solver2& S = *s->s;
+    const bool cd = is_complex != 0;
+    need(!S.x_fourier || cd, RP_ERR_INVALID, "a Fourier axis needs complex data");
+    const size_t w = cd ? 2 : 1;
+    // reference: panic!("Dimension mismatch in Tensor! ...")  (fdma_tensor.rs:201-209)
+    need(in_len == (size_t)S.n0 * S.n1 * w, RP_ERR_SHAPE, "Dimension mismatch in solver input");
+    need(out_len == (size_t)S.m0 * S.m1 * w, RP_ERR_SHAPE, "Dimension mismatch in solver output");
+    const bool lanes_c = cd || S.x_fourier;
+    Arr& ain = lanes_c ? S.in_c : S.in_r;
+    Arr& aout = lanes_c ? S.out_c : S.out_r;
+    if (!ain.buf.p) {
+      ain.alloc(S.n0, S.n1, lanes_c);
+      aout.alloc(S.m0, S.m1, lanes_c);
+    }
+    ain.upload(in, S.stream);
+    S.solve(cd);
+    aout.download(out, S.stream);
+    rt::sync(S.stream);
+  });
+}
+int rp_solver_destroy(rp_solver_t* s) {
+  return guard([&] {
+    if (!s) return;
+    delete s->s;
+    delete s;
+  });
+}
+
+// ---- Navier2D ---------------------------------------------------------------
+static int make_navier(int nx, int ny, double ra, double pr, double dt, double aspect, int adiabatic, int periodic,
+                       const double* lam, const double* q, const double* p, rp_navier_t** out) {
+  return guard([&] {
+    need(out != nullptr, RP_ERR_INVALID, "null out pointer");
+    need(nx >= 8 && ny >= 8, RP_ERR_INVALID, "grid too small");
+    need(ra > 0 && pr > 0 && dt > 0 && aspect > 0, RP_ERR_INVALID, "ra, pr, dt, aspect must be positive");
+    EigData e;
+    e.lam = lam, e.q = q, e.p = p;
+    init_kernels();
+    auto* h = new rp_navier;
+    h->n = new Navier2D(nx, ny, ra, pr, dt, aspect, adiabatic != 0, periodic != 0, (lam && q && p) ? &e : nullptr);
+    for (int i = 0; i < 6; ++i) h->views[i] = rp_field{h->n->field_by_index(i), false};
+    *out = h;
+  });
+}
+int rp_navier_create(int nx, int ny, double ra, double pr, double dt, double aspect, int adiabatic, int periodic,
+                     rp_navier_t** out) {
+  return make_navier(nx, ny, ra, pr, dt, aspect, adiabatic, periodic, nullptr, nullptr, nullptr, out);
+}
+int rp_navier_create_with_eig(int nx, int ny, double ra, double pr, double dt, double aspect, int adiabatic,
+                              const double* lam, const double* q, const double* p, rp_navier_t** out) {
+  return make_navier(nx, ny, ra, pr, dt, aspect, adiabatic, 0, lam, q, p, out);
+}
+int rp_navier_destroy(rp_navier_t* h) {
+  return guard([&] {
+    if (!h) return;
+    delete h->n;
+    delete h;
+  });
+}
+#define NAV_GUARD(...)                       \
+  return guard([&] {                         \
+    need(h, RP_ERR_INVALID, "null handle");  \
+    Navier2D& N = *h->n;                     \
+    (void)N;                                 \
+    __VA_ARGS__;                             \
+  })
+int rp_navier_set_velocity(rp_navier_t* h, double amp, double m, double n) { NAV_GUARD(N.set_velocity(amp, m, n)); }
+int rp_navier_set_temperature(rp_navier_t* h, double amp, double m, double n) { NAV_GUARD(N.set_temperature(amp, m, n)); }
+int rp_navier_set_tempbc_ortho(rp_navier_t* h, const double* tb, size_t len) {
+  NAV_GUARD({
+    need(tb, RP_ERR_INVALID, "null argument");
+    need(len == arr_len(N.field->ortho), RP_ERR_SHAPE, "set_tempbc_ortho: size mismatch");
+    N.set_tempbc_ortho(tb);
+  });
+}
+int rp_navier_set_dealias(rp_navier_t* h, int on) {
+  NAV_GUARD({
+    need(N.launches_per_step() == 0, RP_ERR_INVALID, "set_dealias must be called before the first update()");
+    N.dealias = on != 0;
+  });
+}
+int rp_navier_update(rp_navier_t* h, int nsteps) {
+  NAV_GUARD({
+    need(nsteps >= 0, RP_ERR_INVALID, "nsteps < 0");
+    N.update(nsteps);
+  });
+}
+int rp_navier_sync(rp_navier_t* h) { NAV_GUARD(N.sync()); }
+int rp_navier_get_time(rp_navier_t* h, double* t) { NAV_GUARD(if (t) *t = N.time); }
+int rp_navier_get_dt(rp_navier_t* h, double* dt) { NAV_GUARD(if (dt) *dt = N.dt); }
+int rp_navier_reset_time(rp_navier_t* h) { NAV_GUARD(N.time = 0.0); }
+int rp_navier_params(rp_navier_t* h, double* nu, double* ka, double scale[2]) {
+  NAV_GUARD({
+    if (nu) *nu = N.nu;
+    if (ka) *ka = N.ka;
+    if (scale) scale[0] = N.scale[0], scale[1] = N.scale[1];
+  });
+}
+int rp_navier_eval(rp_navier_t* h, double* nu, double* nuvol, double* re, double* div_norm, double* ekin) {
+  NAV_GUARD(N.eval(nu, nuvol, re, div_norm, ekin));
+}
+int rp_navier_field(rp_navier_t* h, int which, rp_field_t** out) {
+  NAV_GUARD({
+    need(out && which >= 0 && which < 6, RP_ERR_INVALID, "bad field index");
+    *out = &h->views[which];
+  });
+}
+int rp_navier_export_eig(rp_navier_t* h, double* lam, double* q, double* p) {
+  NAV_GUARD(N.solver[3]->export_eig(lam, q, p));
+}
+int rp_navier_launches_per_step(rp_navier_t* h, int* n) { NAV_GUARD(if (n) *n = N.launches_per_step()); }
+int rp_navier_set_graph(rp_navier_t* h, int on) { NAV_GUARD(N.set_graph(on != 0)); }
+
+}  // extern "C"
+#pragma GCC visibility pop

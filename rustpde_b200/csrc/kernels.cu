@@ -1,0 +1,213 @@
+// kernels.cu -- __global__ entry points and their launch wrappers:
+//   * lane_vm_kernel : the lane-program interpreter (lane_vm.cuh)
+//   * dgemm_dmma     : FP64 tensor-core GEMM (mma.sync m8n8k4) for the
+//                      fast-diagonalisation contractions (fdma_tensor.rs:212-233)
+//   * small elementwise / reduction kernels for the diagnostics
+#include "kernels.h"
+#include "lane_vm.cuh"
+
+namespace rp {
+
+__global__ void __launch_bounds__(512) lane_vm_kernel(const Program* __restrict__ progs) { lane_vm_body(progs); }
+
+__global__ void __launch_bounds__(256) dgemm_dmma_kernel(GemmArgs g);
+enum { GBM = 128, GBN = 128, GBK = 16, GPAD = 8, GLD = GBM + GPAD };
+static const int kGemmSmem = 4 * GBK * GLD * (int)sizeof(double);
+
+void init_kernels() {
+#ifndef RP_EMU
+  static bool done = false;
+  if (done) return;
+  RP_CUDA_CHECK(cudaFuncSetAttribute(lane_vm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RP_MAX_SMEM));
+  RP_CUDA_CHECK(cudaFuncSetAttribute(dgemm_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
+  done = true;
+#endif
+}
+
+void launch_lane_programs(const Program* d_progs, int nprogs, int nblocks, int nthreads, int smem_bytes, cudaStream_t s) {
+  if (nblocks <= 0 || nprogs <= 0) return;
+  init_kernels();
+  if (smem_bytes > RP_MAX_SMEM) throw Error(RP_ERR_INTERNAL, "lane program needs too much shared memory");
+  RP_LAUNCH(lane_vm_kernel, dim3(nblocks, nprogs), dim3(nthreads), (size_t)smem_bytes, s, d_progs);
+}
+
+// ===========================================================================
+// FP64 DMMA GEMM:  C[m, n] = sum_k A[m, k] * B[k, n]      (row-major)
+//   B element (k, n) at B[(b_r0 + k*b_rs)*ldb + n], C likewise with c_r0/c_rs
+//   so the even/odd parity-split solves can address interleaved rows.
+// Block tile 128 x 128 x 16, 8 warps (2 x 4), warp tile 64 x 32.
+// ===========================================================================
+RP_DEV void dmma(double& d0, double& d1, double a, double b) {
+#ifdef RP_EMU
+  cuemu::mma_m8n8k4(d0, d1, a, b, d0, d1);
+#else
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+#endif
+}
+
+__global__ void __launch_bounds__(256) dgemm_dmma_kernel(GemmArgs g) {
+  RP_DYN_SMEM(double, sm);
+  double* As = sm;                       // [2][GBK][GLD]  (k-major)
+  double* Bs = sm + 2 * GBK * GLD;       // [2][GBK][GLD]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int m0 = blockIdx.y * GBM, n0 = blockIdx.x * GBN;
+  const int wm = (warp >> 2) * 64, wn = (warp & 3) * 32;
+  const int lr = lane >> 2, lc = lane & 3;
+  double acc[8][4][2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+  // global -> register staging
+  const int arow = tid >> 1, acol = (tid & 1) * 8;   // A tile: 128 rows x 16 k
+  const int brow = tid >> 4, bcol = (tid & 15) * 8;  // B tile: 16 k x 128 cols
+  double ra[8], rb[8];
+  const int nk = (g.K + GBK - 1) / GBK;
+  auto gload = [&](int kt) {
+    const int k0 = kt * GBK;
+    const int gm = m0 + arow;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int gk = k0 + acol + q;
+      ra[q] = (gm < g.M && gk < g.K) ? g.A[(size_t)gm * g.lda + gk] : 0.0;
+    }
+    const int gk = k0 + brow;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int gn = n0 + bcol + q;
+      rb[q] = (gk < g.K && gn < g.N) ? g.B[(size_t)(g.b_r0 + (long long)gk * g.b_rs) * g.ldb + gn] : 0.0;
+    }
+  };
+  auto sstore = [&](int buf) {
+    double* a = As + buf * GBK * GLD;
+    double* b = Bs + buf * GBK * GLD;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) a[(acol + q) * GLD + arow] = ra[q];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) b[brow * GLD + bcol + q] = rb[q];
+  };
+  gload(0);
+  sstore(0);
+  __syncthreads();
+  for (int kt = 0; kt < nk; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < nk) gload(kt + 1);
+    const double* a = As + buf * GBK * GLD;
+    const double* b = Bs + buf * GBK * GLD;
+#pragma unroll
+    for (int kk = 0; kk < GBK; kk += 4) {
+      double af[8], bf[4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) af[i] = a[(kk + lc) * GLD + wm + 8 * i + lr];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bf[j] = b[(kk + lc) * GLD + wn + 8 * j + lr];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+    }
+    if (kt + 1 < nk) sstore(buf ^ 1);
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int gm = m0 + wm + 8 * i + lr;
+    if (gm >= g.M) continue;
+    double* crow = g.C + (size_t)(g.c_r0 + (long long)gm * g.c_rs) * g.ldc;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gn = n0 + wn + 8 * j + 2 * lc;
+      if (gn < g.N) crow[gn] = acc[i][j][0];
+      if (gn + 1 < g.N) crow[gn + 1] = acc[i][j][1];
+    }
+  }
+}
+
+void launch_dgemm(const GemmArgs& g, cudaStream_t s) {
+  if (g.M <= 0 || g.N <= 0) return;
+  const int smem = kGemmSmem;
+  init_kernels();
+  dim3 grid((g.N + GBN - 1) / GBN, (g.M + GBM - 1) / GBM);
+  RP_LAUNCH(dgemm_dmma_kernel, grid, dim3(256), (size_t)smem, s, g);
+}
+
+// ===========================================================================
+// small helpers
+// ===========================================================================
+__global__ void zero_elems_kernel(double* p, int count) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) p[i] = 0.0;
+}
+void launch_zero_elems(double* p, int count, cudaStream_t s) {
+  RP_LAUNCH(zero_elems_kernel, dim3(1), dim3(32), (size_t)0, s, p, count);
+}
+
+RP_DEV double block_sum(double v, double* red) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  double tot = 0.0;
+  if (threadIdx.x == 0)
+    for (int i = 0; i < (int)((blockDim.x + 31) >> 5); ++i) tot += red[i];
+  __syncthreads();
+  return tot;  // valid on thread 0
+}
+
+// out[0] += sum_ij wx[i] wy[j] g(a, b, c)[i, j];  mode selects g
+//   0: a    1: sqrt(a^2+b^2)    2: 0.5 (a^2+b^2)    3: a^2 (sum of squares, weights ignored)
+__global__ void __launch_bounds__(256) wsum_kernel(const double* a, const double* b, long long ld, int rows, int cols,
+                                                    const double* wx, const double* wy, int mode, double* out) {
+  __shared__ double red[32];
+  double acc = 0.0;
+  const long long total = (long long)rows * cols;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(idx / cols), j = (int)(idx % cols);
+    const double va = a[(size_t)i * ld + j];
+    double gval;
+    if (mode == 0)
+      gval = va;
+    else if (mode == 3)
+      gval = va * va;
+    else {
+      const double vb = b[(size_t)i * ld + j];
+      const double e = va * va + vb * vb;
+      gval = (mode == 1) ? sqrt(e) : 0.5 * e;
+    }
+    const double w = (mode == 3) ? 1.0 : wx[i] * wy[j];
+    acc = fma(w, gval, acc);
+  }
+  const double tot = block_sum(acc, red);
+  if (threadIdx.x == 0) atomicAdd(out, tot);
+}
+void launch_wsum(const double* a, const double* b, long long ld, int rows, int cols, const double* wx, const double* wy,
+                 int mode, double* out, cudaStream_t s) {
+  long long total = (long long)rows * cols;
+  int blocks = (int)std::min<long long>((total + 255) / 256, 592);
+  if (blocks < 1) blocks = 1;
+  RP_LAUNCH(wsum_kernel, dim3(blocks), dim3(256), (size_t)0, s, a, b, ld, rows, cols, wx, wy, mode, out);
+}
+
+// out = (a + b*c*s1) * s0   elementwise on pitched arrays (eval_nuvol, functions.rs:60-72)
+__global__ void combine_kernel(double* out, const double* a, const double* b, const double* c, long long ld, int rows,
+                               int cols, double s0, double s1) {
+  const long long total = (long long)rows * cols;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(idx / cols), j = (int)(idx % cols);
+    const size_t o = (size_t)i * ld + j;
+    double r = a[o];
+    if (b) r += (c ? b[o] * c[o] : b[o]) * s1;
+    out[o] = r * s0;
+  }
+}
+void launch_combine(double* out, const double* a, const double* b, const double* c, long long ld, int rows, int cols,
+                    double s0, double s1, cudaStream_t s) {
+  long long total = (long long)rows * cols;
+  int blocks = (int)std::min<long long>((total + 255) / 256, 1184);
+  if (blocks < 1) blocks = 1;
+  RP_LAUNCH(combine_kernel, dim3(blocks), dim3(256), (size_t)0, s, out, a, b, c, ld, rows, cols, s0, s1);
+}
+
+}  // namespace rp

@@ -1,0 +1,232 @@
+// model.h -- host-side mirror of the reference's objects on the Navier2D path
+// (Space2 / Field2: src/field.rs, funspace/src/space2.rs; HholtzAdi / Hholtz /
+// Poisson: src/solver/*.rs; Navier2D: src/navier/navier.rs), each one a thin
+// owner of device arrays plus the lane programs / GEMMs that implement it.
+#pragma once
+#include <array>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "kernels.h"
+#include "tables.h"
+
+namespace rp {
+
+// pitched device 2-D array, row-major; complex arrays hold interleaved (re, im)
+struct Arr {
+  DevBuf buf;
+  int rows = 0, cols = 0;
+  long long ld = 0;  // in elements of its own type (double or double2)
+  bool cplx = false;
+  void alloc(int r, int c, bool cx);
+  double* d() const { return buf.as<double>(); }
+  size_t elem_bytes() const { return cplx ? 16 : 8; }
+  void upload(const double* host, cudaStream_t s);        // dense row-major host array
+  void download(double* host, cudaStream_t s) const;
+  void zero(cudaStream_t s);
+};
+
+// non-owning view of a pitched device array (what lane-program loads/stores take)
+struct ArrRef {
+  const void* p;
+  long long ld;
+  int rows, cols;
+  bool cplx;
+  ArrRef(const void* p_, long long ld_, int r, int c, bool cx) : p(p_), ld(ld_), rows(r), cols(c), cplx(cx) {}
+  ArrRef(const Arr& a) : p(a.buf.p), ld(a.ld), rows(a.rows), cols(a.cols), cplx(a.cplx) {}
+};
+
+// A finalised lane program on the device
+struct Built {
+  DevBuf dprog;
+  int nblocks = 0, nthreads = 0, smem = 0;
+  bool valid = false;
+  void launch(cudaStream_t s) const;
+};
+
+class ProgBuilder {
+ public:
+  ProgBuilder(int axis, int nunits);
+  void ld(int r, ArrRef a, int n, Lay lay, double s = 1.0, int flags = 0, int shift = 0,
+          const double* lanecoef = nullptr, int zfill = 0, int lane2 = -1);
+  void st(int r, ArrRef a, int n, Lay lay, double s = 1.0, int flags = 0, int cut_i = -1, int cut_lane = -1,
+          int lane2 = -1);
+  void toortho(int r, const Base& b, Lay lay);
+  void fromortho(int r, const Base& b, Lay lay);
+  Lay diff(int r, int n, Lay lay, int times, double scale);
+  Lay dct(int r, const Base& b, Lay lay, bool backward);
+  void bandmv(int r, const Base& b, Lay lay);
+  void fdma(int r, const FdmaDev& f, Lay lay);
+  void fdmamode(int r, int rinv, const FdmaModeDev& f, Lay lay, bool complex_lanes);
+  void copy(int rd, int rs, int n, Lay ld, Lay ls);
+  void axpy(int rd, int rs, int n, double a, Lay ld, Lay ls);
+  void scale(int r, int n, double a, Lay lay);
+  void mulpw(int rd, int ra, int rb, int n, Lay ld, Lay lab, bool acc);
+  void cut(int r, int n, int from, Lay lay);
+  void mulik(int r, int n, double a, Lay lay, bool elem_k = false);
+  void zero(int r, int n, Lay lay);
+  void setzero00(int r, Lay lay, bool complex_lanes);
+  void rfft(int r0, int r1, int r2, const Base& b);
+  void irfft(int r0, int r1, int r2, const Base& b);
+  Built build();
+  int default_anchor = 0;  // set by callers: SPLIT anchor large enough for the program
+
+ private:
+  Instr& add(int op);
+  void touch(int r, Lay lay, int n);
+  Program p_;
+  int fftlen_ = 0, wbcap_ = 0;
+};
+
+struct Space2 {
+  std::shared_ptr<Base> b0, b1;
+};
+
+// FieldBase<f64, f64, T2, S, 2>  (src/field.rs:66-129)
+class Field2 {
+ public:
+  explicit Field2(const Space2& sp);
+  Space2 sp;
+  int n0, n1, m0, m1, o0, o1;  // physical, spectral, ortho-spectral shapes
+  bool cplx;
+  Arr v, vhat, ortho;  // ortho: staging for to_ortho / from_ortho / gradient results
+  std::vector<double> x[2], dx[2];
+  cudaStream_t stream = 0;
+
+  void forward();
+  void backward();
+  void to_ortho();    // vhat -> ortho
+  void from_ortho();  // ortho -> vhat
+  void gradient(int dx, int dy, const double* scale);  // vhat -> ortho
+  // weighted averages (src/field/average.rs:25-57)
+  double average();
+  void average_axis0(std::vector<double>& out);
+  const double* weights_x() const { return wx_.as<double>(); }
+  const double* weights_y() const { return wy_.as<double>(); }
+
+ private:
+  Arr ta_, tb_;
+  Built fwd_y_, fwd_x_, bwd_x_, bwd_y_, to_x_, to_y_, from_x_, from_y_;
+  std::map<std::array<long long, 4>, std::pair<Built, Built>> grad_;
+  DevBuf wx_, wy_, red_;
+  void build_transforms();
+};
+
+// HholtzAdi (src/solver/hholtz_adi.rs:32-130)
+struct AxisAdi {
+  FdmaDev fdma;
+};
+// Hholtz / Poisson through FdmaTensor (src/solver/{hholtz,poisson,fdma_tensor}.rs)
+struct TensorSolver {
+  FdmaModeDev mode;     // per-lane banded solve along y
+  Arr P, Q;             // fwd = Q^-1 Cx^-1, bwd = Q  (only when x is Chebyshev)
+  std::vector<double> lam;
+  bool x_diag = false;  // Fourier axis: no GEMM
+};
+
+enum SolverKind { SOLVER_HHOLTZ = 0, SOLVER_HHOLTZ_ADI = 1, SOLVER_POISSON = 2 };
+
+struct EigData {  // optional externally supplied set-up data (lam, Q, P = Q^-1 Cx^-1), row-major m x m
+  const double* lam = nullptr;
+  const double* q = nullptr;
+  const double* p = nullptr;
+};
+
+class Solver2 {
+ public:
+  Solver2(int kind, const Space2& sp, double cx, double cy, double alpha, const EigData* eig);
+  int kind;
+  Space2 sp;
+  int n0, n1, m0, m1;  // rhs is (n0 x n1) ortho, solution (m0 x m1) composite
+  bool x_fourier;
+  AxisAdi adi[2];
+  TensorSolver ts;
+  cudaStream_t stream = 0;
+  // generic entry: in_/out_ are solver-owned staging arrays
+  Arr in_r, out_r, in_c, out_c;
+  void solve(bool complex_data);
+  void export_eig(double* lam, double* q, double* p) const;
+  // building blocks used by Navier2D's fused programs
+  void emit_x(ProgBuilder& pb, int r, Lay lay) const;        // bandmv_x (+ fdma_x for ADI)
+  void emit_y(ProgBuilder& pb, int r, int rinv, Lay lay, bool complex_lanes) const;  // bandmv_y + solve_y
+  void gemm_fwd(const Arr& in, Arr& out, int ncols_real) const;
+  void gemm_bwd(const Arr& in, Arr& out, int ncols_real) const;
+
+ private:
+  Arr t1_[2], t2_[2], t3_[2];
+  Built px_[2], py_[2];
+  std::vector<double> hq_, hp_;
+  void build_programs(bool complex_data);
+};
+
+// Navier2D (src/navier/navier.rs:153-195)
+class Navier2D {
+ public:
+  Navier2D(int nx, int ny, double ra, double pr, double dt, double aspect, bool adiabatic, bool periodic,
+           const EigData* eig);
+  ~Navier2D();
+  int nx, ny;
+  bool periodic, adiabatic;
+  double ra, pr, nu, ka, dt, time, scale[2];
+  bool dealias = true;
+  std::unique_ptr<Field2> temp, ux, uy, pres0, pres1, field;
+  std::unique_ptr<Solver2> solver[4];
+  cudaStream_t stream = 0;
+
+  void set_velocity(double amp, double m, double n);
+  void set_temperature(double amp, double m, double n);
+  void set_tempbc_ortho(const double* that_bc);  // ortho coefficients of the BC field (o0 x o1 [x2])
+  void update(int nsteps);
+  void eval(double* nu, double* nuvol, double* re, double* div_norm, double* ekin);
+  void sync();
+  Field2* field_by_index(int which);
+  int launches_per_step() const { return launches_per_step_; }
+  void set_graph(bool on) {
+    use_graph_ = on;
+    graph_dirty_ = true;
+  }
+
+ private:
+  void build_step();
+  void build_step_confined();
+  void build_step_periodic();
+  void build_y_phase();
+  void add_prog(ProgBuilder& pb);
+  void rebuild_bc();
+  void apply_ic(Field2& f, double amp, double m, double n, bool sin_cos);
+  void run_step();
+  double div_norm();
+  Arr a1_, a2_;
+  bool graph_dirty_ = true;
+  bool use_graph_ = true;
+  // work arrays
+  Arr ax_[3], adx_[3];           // x-backward results: value and d/dx   [nx x my]
+  Arr phys_[8];                  // ux, uy, dxu, dyu, dxv, dyv, dxT, dyT   [nx x ny]
+  Arr bconv_[3];                 // conv after y-forward                   [nx x ny]
+  Arr chat_[3];                  // conv after x-forward (periodic: complex (mk x ny))
+  Arr w_[3];                     // after x-part of the implicit solve     [mx x ny]
+  Arr vx_, ey_, div_, r1_, g_, h_, dyp_;
+  Arr tbc_ortho_, dxtbc_, dytbc_, bcdiff_;
+  std::vector<Built> step_;      // programs of one update() in launch order
+  struct StepOp {
+    int kind;  // 0 lane program, 1 gemm fwd, 2 gemm bwd, 3 zero elem
+    int idx;
+  };
+  std::vector<StepOp> ops_;
+  int launches_per_step_ = 0;
+  DevBuf red_;
+#ifndef RP_EMU
+  cudaGraphExec_t graph_ = nullptr;
+  bool graph_ok_ = false;
+#endif
+};
+
+// LAPACK access for the set-up eigendecomposition (src/solver/utils.rs:66-106)
+void lapack_set_library(const char* path);
+bool lapack_available(std::string* why);
+void lapack_eig_setup(int m, const std::vector<double>& Cx, const std::vector<double>& Ax, std::vector<double>& lam,
+                      std::vector<double>& Q, std::vector<double>& P);
+
+}  // namespace rp

@@ -1,0 +1,616 @@
+// navier.cu -- Navier2D::update (src/navier/navier.rs:737-765) on the device.
+//
+// One IMEX-Euler step of 2-D Rayleigh-Benard convection:
+//   explicit: convection (conv_term.rs:22-42, navier.rs:538-616), buoyancy, grad p
+//   implicit: diffusion, HholtzAdi (confined) / Hholtz (periodic)  (navier.rs:622-674)
+//   projection: Poisson for the pseudo pressure, u -= grad phi, p update (683-721)
+// All explicit terms depend on start-of-step state only, so the three
+// convection terms are evaluated up-front in one batch:
+//   x-backward (value and d/dx of ux, uy, T) -> y-backward / products /
+//   y-forward -> x-forward fused with the x half of the implicit solves
+//   -> y half of the solves -> divergence -> Poisson -> projection.
+// Operators on different axes commute, which is what lets every pass be a
+// single sweep of strided (x) or contiguous (y) lanes.
+#include <cmath>
+
+#include "model.h"
+
+namespace rp {
+
+static int half_up(int n) { return (n + 1) / 2; }
+
+static double get_nu(double ra, double pr, double h) { return std::sqrt(pr / (ra / std::pow(h, 3.0))); }   // navier.rs:46-49
+static double get_ka(double ra, double pr, double h) { return std::sqrt(1.0 / ((ra / std::pow(h, 3.0)) * pr)); }  // :52-55
+
+Navier2D::Navier2D(int nx_, int ny_, double ra_, double pr_, double dt_, double aspect, bool adiabatic_, bool periodic_,
+                   const EigData* eig)
+    : nx(nx_), ny(ny_), periodic(periodic_), adiabatic(adiabatic_), ra(ra_), pr(pr_), dt(dt_), time(0.0) {
+  scale[0] = aspect;
+  scale[1] = 1.0;
+  nu = get_nu(ra, pr, scale[1] * 2.0);
+  ka = get_ka(ra, pr, scale[1] * 2.0);
+  auto B = [&](int kind, int n) { return get_base(kind, n); };
+  const int kx_u = periodic ? BASE_FOURIER_R2C : BASE_CHEB_DIRICHLET;
+  const int kx_t = periodic ? BASE_FOURIER_R2C : (adiabatic ? BASE_CHEB_NEUMANN : BASE_CHEB_DIRICHLET);
+  const int kx_o = periodic ? BASE_FOURIER_R2C : BASE_CHEBYSHEV;
+  const int kx_n = periodic ? BASE_FOURIER_R2C : BASE_CHEB_NEUMANN;
+  // navier.rs:234-248 / 398-408
+  ux.reset(new Field2(Space2{B(kx_u, nx), B(BASE_CHEB_DIRICHLET, ny)}));
+  uy.reset(new Field2(Space2{B(kx_u, nx), B(BASE_CHEB_DIRICHLET, ny)}));
+  temp.reset(new Field2(Space2{B(kx_t, nx), B(BASE_CHEB_DIRICHLET, ny)}));
+  pres0.reset(new Field2(Space2{B(kx_o, nx), B(BASE_CHEBYSHEV, ny)}));
+  pres1.reset(new Field2(Space2{B(kx_n, nx), B(BASE_CHEB_NEUMANN, ny)}));
+  field.reset(new Field2(Space2{B(kx_o, nx), B(BASE_CHEBYSHEV, ny)}));
+  // navier.rs:250-266 / 410-426
+  const double sx2 = std::pow(scale[0], 2.0), sy2 = std::pow(scale[1], 2.0);
+  const int hk = periodic ? SOLVER_HHOLTZ : SOLVER_HHOLTZ_ADI;
+  solver[0].reset(new Solver2(hk, ux->sp, dt * nu / sx2, dt * nu / sy2, 1.0, nullptr));
+  solver[1].reset(new Solver2(hk, uy->sp, dt * nu / sx2, dt * nu / sy2, 1.0, nullptr));
+  solver[2].reset(new Solver2(hk, temp->sp, dt * ka / sx2, dt * ka / sy2, 1.0, nullptr));
+  solver[3].reset(new Solver2(SOLVER_POISSON, pres1->sp, 1.0 / sx2, 1.0 / sy2, 0.0, eig));
+  // navier.rs:502-514 _scale
+  for (Field2* f : {temp.get(), ux.get(), uy.get(), pres0.get()})
+    for (int a = 0; a < 2; ++a) {
+      for (auto& v : f->x[a]) v *= scale[a];
+      for (auto& v : f->dx[a]) v *= scale[a];
+    }
+  // work arrays
+  const int mx = periodic ? nx / 2 + 1 : nx - 2, my = ny - 2;
+  const int ox = periodic ? mx : nx;
+  for (int f = 0; f < 3; ++f) {
+    ax_[f].alloc(nx, my, false);
+    adx_[f].alloc(nx, my, false);
+    bconv_[f].alloc(nx, ny, false);
+    chat_[f].alloc(ox, ny, periodic);
+    w_[f].alloc(mx, ny, periodic);
+  }
+  for (int i = 0; i < 8; ++i) phys_[i].alloc(nx, ny, false);
+  vx_.alloc(mx, ny, periodic);
+  ey_.alloc(mx, ny, periodic);
+  div_.alloc(ox, ny, periodic);
+  r1_.alloc(mx, ny, periodic);
+  g_.alloc(mx, ny, periodic);
+  h_.alloc(mx, my, periodic);
+  a1_.alloc(mx, my, periodic);
+  a2_.alloc(mx, my, periodic);
+  dyp_.alloc(ox, ny, periodic);
+  tbc_ortho_.alloc(ox, ny, periodic);
+  dxtbc_.alloc(nx, ny, false);
+  dytbc_.alloc(nx, ny, false);
+  bcdiff_.alloc(ox, ny, periodic);
+  red_ = DevBuf(64);
+  // navier.rs:301 / 461: Rayleigh-Benard boundary field, T = +0.5 at y=-1, -0.5 at y=+1
+  // (bc_rbc 314-332, bc_rbc_periodic 474-492): in the ortho basis only T_1(y) is present.
+  std::vector<double> tb((size_t)ox * ny * (periodic ? 2 : 1), 0.0);
+  const double amp = periodic ? -0.5 * (double)nx : -0.5;  // r2c forward is unnormalised
+  tb[(size_t)1 * (periodic ? 2 : 1)] = amp;
+  set_tempbc_ortho(tb.data());
+  // navier.rs:304 random_disturbance(0.1) uses an unseeded RNG -> fields start at
+  // zero here; callers set deterministic ICs (set_velocity / set_temperature / upload).
+}
+
+Navier2D::~Navier2D() {
+#ifndef RP_EMU
+  if (graph_) cudaGraphExecDestroy(graph_);
+#endif
+}
+
+Field2* Navier2D::field_by_index(int which) {
+  switch (which) {
+    case 0: return temp.get();
+    case 1: return ux.get();
+    case 2: return uy.get();
+    case 3: return pres0.get();
+    case 4: return pres1.get();
+    case 5: return field.get();
+    default: throw Error(RP_ERR_INVALID, "field index out of range");
+  }
+}
+
+void Navier2D::sync() { rt::sync(stream); }
+
+static void copy_arr(Arr& dst, const Arr& src, cudaStream_t s) {
+  if (dst.buf.bytes != src.buf.bytes) throw Error(RP_ERR_INTERNAL, "copy_arr: shape mismatch");
+  rt::d2d(dst.buf.p, src.buf.p, src.buf.bytes, s);
+}
+
+void Navier2D::set_tempbc_ortho(const double* that_bc) {
+  tbc_ortho_.upload(that_bc, stream);
+  rebuild_bc();
+}
+
+// Time-invariant pieces of the boundary field (navier.rs:547-550, 665-668)
+void Navier2D::rebuild_bc() {
+  Field2& f = *field;
+  auto grad_to = [&](int ddx, int ddy) {
+    copy_arr(f.vhat, tbc_ortho_, stream);
+    f.gradient(ddx, ddy, scale);
+  };
+  grad_to(1, 0);
+  copy_arr(f.vhat, f.ortho, stream);
+  f.backward();
+  copy_arr(dxtbc_, f.v, stream);
+  grad_to(0, 1);
+  copy_arr(f.vhat, f.ortho, stream);
+  f.backward();
+  copy_arr(dytbc_, f.v, stream);
+  const int rc = f.cplx ? 2 : 1;
+  grad_to(2, 0);
+  launch_combine(bcdiff_.d(), f.ortho.d(), nullptr, nullptr, f.ortho.ld * rc, f.o0, f.o1 * rc, dt * ka, 0.0, stream);
+  grad_to(0, 2);
+  launch_combine(bcdiff_.d(), bcdiff_.d(), f.ortho.d(), nullptr, f.ortho.ld * rc, f.o0, f.o1 * rc, 1.0, dt * ka, stream);
+  rt::sync(stream);
+  graph_dirty_ = true;
+}
+
+// navier.rs:1035-1076: amp * sin(pi m x~) cos(pi n y~) (or cos/sin) on normalised coords, then forward()
+void Navier2D::apply_ic(Field2& f, double amp, double m, double n, bool sin_cos) {
+  const std::vector<double>&x = f.x[0], &y = f.x[1];
+  const int nxp = f.n0, nyp = f.n1;
+  std::vector<double> xs(x.size()), ys(y.size());
+  for (size_t i = 0; i < x.size(); ++i) xs[i] = (x[i] - x[0]) / (x[x.size() - 1] - x[0]);
+  for (size_t j = 0; j < y.size(); ++j) ys[j] = (y[j] - y[0]) / (y[y.size() - 1] - y[0]);
+  const double ax = M_PI * m, ay = M_PI * n;
+  std::vector<double> v((size_t)nxp * nyp);
+  for (int i = 0; i < nxp; ++i)
+    for (int j = 0; j < nyp; ++j)
+      v[(size_t)i * nyp + j] = sin_cos ? amp * std::sin(ax * xs[i]) * std::cos(ay * ys[j])
+                                       : amp * std::cos(ax * xs[i]) * std::sin(ay * ys[j]);
+  f.stream = stream;
+  f.v.upload(v.data(), stream);
+  f.forward();
+  rt::sync(stream);
+}
+
+void Navier2D::set_velocity(double amp, double m, double n) {  // navier.rs:927-930
+  apply_ic(*ux, amp, m, n, true);
+  apply_ic(*uy, -amp, m, n, false);
+}
+void Navier2D::set_temperature(double amp, double m, double n) {  // navier.rs:934-936
+  apply_ic(*temp, -amp, m, n, false);
+}
+
+// --------------------------------------------------------------------------
+void Navier2D::build_step() {
+  if (!ops_.empty()) return;
+  if (periodic)
+    build_step_periodic();
+  else
+    build_step_confined();
+  launches_per_step_ = (int)ops_.size();
+}
+
+void Navier2D::add_prog(ProgBuilder& pb) {
+  step_.push_back(pb.build());
+  ops_.push_back(StepOp{0, (int)step_.size() - 1});
+}
+
+// y phase shared by both geometries: physical-space products (conv_term.rs:41)
+// between y-backward and y-forward transforms.  Real arrays, rows = physical x.
+void Navier2D::build_y_phase() {
+  const Base& byu = *ux->sp.b1;
+  const Base& byt = *temp->sp.b1;
+  const Base& byo = *field->sp.b1;
+  const int my = ny - 2;
+  const Lay nat = lay_natural();
+  const double isy = 1.0 / scale[1];
+  Field2* flds[3] = {ux.get(), uy.get(), temp.get()};
+  // phys_: 0 ux, 1 uy, 2 dxu, 3 dyu, 4 dxv, 5 dyv, 6 dxT, 7 dyT
+  const int val_idx[3] = {0, 1, -1}, dx_idx[3] = {2, 4, 6}, dy_idx[3] = {3, 5, 7};
+  for (int f = 0; f < 3; ++f) {
+    const Base& by = (f == 2) ? byt : byu;
+    (void)flds;
+    ProgBuilder pb(AXIS_Y, half_up(nx));
+    Lay l = lay_split(ny);
+    pb.ld(0, ax_[f], my, l, 1.0, 0, 0, nullptr, ny);
+    pb.toortho(0, by, l);
+    Lay lv = l;
+    if (val_idx[f] >= 0) {
+      pb.copy(1, 0, ny, l, l);
+      lv = pb.dct(1, byo, l, true);
+      pb.st(1, phys_[val_idx[f]], ny, lv);
+    }
+    Lay ld = pb.diff(0, ny, l, 1, isy);
+    ld = pb.dct(0, byo, ld, true);
+    pb.st(0, phys_[dy_idx[f]], ny, ld);
+    pb.ld(0, adx_[f], my, l, 1.0, 0, 0, nullptr, ny);
+    pb.toortho(0, by, l);
+    Lay lx = pb.dct(0, byo, l, true);
+    pb.st(0, phys_[dx_idx[f]], ny, lx);
+    add_prog(pb);
+  }
+  const int ny_cut = dealias ? (ny * 2) / 3 : -1;  // navier.rs:1029
+  for (int f = 0; f < 3; ++f) {
+    ProgBuilder pb(AXIS_Y, half_up(nx));
+    pb.ld(0, phys_[0], ny, nat);
+    pb.ld(1, phys_[dx_idx[f]], ny, nat);
+    if (f == 2) pb.ld(1, dxtbc_, ny, nat, 1.0, LF_ACC);
+    pb.mulpw(2, 0, 1, ny, nat, nat, false);
+    pb.ld(0, phys_[1], ny, nat);
+    pb.ld(1, phys_[dy_idx[f]], ny, nat);
+    if (f == 2) pb.ld(1, dytbc_, ny, nat, 1.0, LF_ACC);
+    pb.mulpw(2, 0, 1, ny, nat, nat, true);
+    Lay l = pb.dct(2, byo, nat, false);
+    pb.st(2, bconv_[f], ny, l, 1.0, 0, ny_cut, -1);
+    add_prog(pb);
+  }
+}
+
+void Navier2D::build_step_confined() {
+  const Base &bxu = *ux->sp.b0, &byu = *ux->sp.b1;
+  const Base &bxt = *temp->sp.b0, &byt = *temp->sp.b1;
+  const Base &bxn = *pres1->sp.b0, &byn = *pres1->sp.b1;
+  const Base &bxo = *field->sp.b0, &byo = *field->sp.b1;
+  const int mx = nx - 2, my = ny - 2;
+  const double isx = 1.0 / scale[0], isy = 1.0 / scale[1];
+  Field2* flds[3] = {ux.get(), uy.get(), temp.get()};
+  const Base* bxs[3] = {&bxu, &bxu, &bxt};
+  const Base* bys[3] = {&byu, &byu, &byt};
+  // ---- 1. x-backward: value and d/dx of ux, uy, T ------------------------
+  for (int f = 0; f < 3; ++f) {
+    ProgBuilder pb(AXIS_X, half_up(my));
+    Lay l = lay_split(nx);
+    pb.ld(0, flds[f]->vhat, mx, l, 1.0, 0, 0, nullptr, nx);
+    pb.toortho(0, *bxs[f], l);
+    pb.copy(1, 0, nx, l, l);
+    Lay l1 = pb.diff(1, nx, l, 1, isx);
+    Lay l0 = pb.dct(0, bxo, l, true);
+    l1 = pb.dct(1, bxo, l1, true);
+    pb.st(0, ax_[f], nx, l0);
+    pb.st(1, adx_[f], nx, l1);
+    add_prog(pb);
+  }
+  // ---- 2. y phase ----------------------------------------------------------
+  build_y_phase();
+  // ---- 3. x-forward + dealias + rhs assembly + x half of HholtzAdi ---------
+  const int nx_cut = dealias ? (nx * 2) / 3 : -1;  // navier.rs:1028
+  for (int f = 0; f < 3; ++f) {
+    ProgBuilder pb(AXIS_X, half_up(ny));
+    pb.ld(0, bconv_[f], nx, lay_natural());
+    Lay l0 = pb.dct(0, bxo, lay_natural(), false);
+    if (nx_cut >= 0) pb.cut(0, nx, nx_cut, l0);
+    pb.scale(0, nx, -dt, l0);                                  // - dt * conv       (navier.rs:630, 651, 671)
+    Lay l = lay_split(nx);
+    // + to_ortho(field): S_y across lanes (coefficients d_j, l_{j-2}), S_x in the lane
+    pb.ld(1, flds[f]->vhat, mx, l, 1.0, 0, 0, bys[f]->d_sd.as<double>(), nx);
+    pb.ld(1, flds[f]->vhat, mx, l, 1.0, LF_ACC, -2, bys[f]->d_sl.as<double>());
+    pb.toortho(1, *bxs[f], l);
+    pb.axpy(0, 1, nx, 1.0, l0, l);
+    if (f == 0) {  // - dt * d/dx pres / sx            (navier.rs:627)
+      pb.ld(1, pres0->vhat, nx, l);
+      Lay lp = pb.diff(1, nx, l, 1, -dt * isx);
+      pb.axpy(0, 1, nx, 1.0, l0, lp);
+    } else if (f == 1) {  // - dt * d/dy pres / sy, + dt * buoyancy  (navier.rs:646-648)
+      pb.ld(0, dyp_, nx, l0, -dt, LF_ACC);
+      pb.ld(1, temp->vhat, mx, l, 1.0, 0, 0, byt.d_sd.as<double>(), nx);
+      pb.ld(1, temp->vhat, mx, l, 1.0, LF_ACC, -2, byt.d_sl.as<double>());
+      pb.toortho(1, bxt, l);
+      pb.axpy(0, 1, nx, dt, l0, l);
+      pb.ld(0, tbc_ortho_, nx, l0, dt, LF_ACC);
+    } else {  // + dt * ka * (dxx + dyy) fieldbc          (navier.rs:665-668)
+      pb.ld(0, bcdiff_, nx, l0, 1.0, LF_ACC);
+    }
+    solver[f]->emit_x(pb, 0, l0);
+    pb.st(0, w_[f], mx, l0);
+    add_prog(pb);
+  }
+  // ---- 4. y half of HholtzAdi (+ pieces of the divergence) -----------------
+  for (int f = 0; f < 3; ++f) {
+    ProgBuilder pb(AXIS_Y, half_up(mx));
+    Lay l = lay_split(ny);
+    pb.ld(0, w_[f], ny, l);
+    solver[f]->emit_y(pb, 0, 1, l, false);
+    pb.st(0, flds[f]->vhat, my, l);
+    if (f == 0) {
+      pb.toortho(0, byu, l);
+      pb.st(0, vx_, ny, l);
+    } else if (f == 1) {
+      pb.toortho(0, byu, l);
+      Lay ld = pb.diff(0, ny, l, 1, isy);
+      pb.st(0, ey_, ny, ld);
+    }
+    add_prog(pb);
+  }
+  // ---- 5. divergence (navier.rs:698-703) + B2x of the Poisson rhs ----------
+  {
+    ProgBuilder pb(AXIS_X, half_up(ny));
+    Lay l = lay_split(nx);
+    pb.ld(0, vx_, mx, l, 1.0, 0, 0, nullptr, nx);
+    pb.toortho(0, bxu, l);
+    Lay ld = pb.diff(0, nx, l, 1, isx);
+    pb.ld(1, ey_, mx, l, 1.0, 0, 0, nullptr, nx);
+    pb.toortho(1, bxu, l);
+    pb.axpy(0, 1, nx, 1.0, ld, l);
+    pb.st(0, div_, nx, ld);
+    solver[3]->emit_x(pb, 0, ld);
+    pb.st(0, r1_, mx, ld);
+    add_prog(pb);
+  }
+  // ---- 6-8. fast diagonalisation: P., per-mode Fdma_y, Q. (poisson.rs:131-149)
+  ops_.push_back(StepOp{1, 0});
+  {
+    ProgBuilder pb(AXIS_Y, half_up(mx));
+    Lay l = lay_split(ny);
+    pb.ld(0, g_, ny, l);
+    const FdmaModeDev& md = solver[3]->ts.mode;
+    pb.ld(1, ArrRef(md.inv.p, md.inv_ld, md.nlanes, md.n, false), my, l);
+    solver[3]->emit_y(pb, 0, 1, l, false);
+    pb.st(0, h_, my, l);
+    add_prog(pb);
+  }
+  ops_.push_back(StepOp{2, 0});
+  ops_.push_back(StepOp{3, 0});  // pres[1].vhat[[0,0]] = 0   (navier.rs:714)
+  // ---- 9. projection (navier.rs:683-695): x part -----------------------------
+  {
+    ProgBuilder pb(AXIS_X, half_up(my));
+    Lay l = lay_split(nx);
+    pb.ld(0, pres1->vhat, mx, l, 1.0, 0, 0, nullptr, nx);
+    pb.toortho(0, bxn, l);
+    pb.copy(1, 0, nx, l, l);
+    Lay ld = pb.diff(0, nx, l, 1, isx);
+    pb.fromortho(0, bxu, ld);
+    pb.fromortho(1, bxu, l);
+    pb.st(0, a1_, mx, ld);
+    pb.st(1, a2_, mx, l);
+    add_prog(pb);
+  }
+  // ---- 10. projection: y part; u -= from_ortho(grad phi) ---------------------
+  {
+    ProgBuilder pb(AXIS_Y, half_up(mx));
+    Lay l = lay_split(ny);
+    pb.ld(0, a1_, my, l, 1.0, 0, 0, nullptr, ny);
+    pb.toortho(0, byn, l);
+    pb.fromortho(0, byu, l);
+    pb.st(0, ux->vhat, my, l, -1.0, LF_ACC);
+    pb.ld(0, a2_, my, l, 1.0, 0, 0, nullptr, ny);
+    pb.toortho(0, byn, l);
+    Lay ld = pb.diff(0, ny, l, 1, isy);
+    pb.fromortho(0, byu, ld);
+    pb.st(0, uy->vhat, my, ld, -1.0, LF_ACC);
+    add_prog(pb);
+  }
+  // ---- 11. pressure update (navier.rs:717-721) + d/dy pres for the next step --
+  {
+    ProgBuilder pb(AXIS_Y, half_up(nx));
+    Lay l = lay_split(ny);
+    pb.ld(0, pres1->vhat, my, l, 1.0, 0, 0, bxn.d_sd.as<double>(), ny);
+    pb.ld(0, pres1->vhat, my, l, 1.0, LF_ACC, -2, bxn.d_sl.as<double>());
+    pb.toortho(0, byn, l);
+    pb.scale(0, ny, 1.0 / dt, l);
+    pb.ld(0, div_, ny, l, -nu, LF_ACC);
+    pb.ld(0, pres0->vhat, ny, l, 1.0, LF_ACC);
+    pb.st(0, pres0->vhat, ny, l);
+    Lay ld = pb.diff(0, ny, l, 1, isy);
+    pb.st(0, dyp_, ny, ld);
+    add_prog(pb);
+  }
+  (void)byo;
+  (void)byt;
+}
+
+void Navier2D::build_step_periodic() {
+  const Base &bx = *ux->sp.b0, &byu = *ux->sp.b1, &byt = *temp->sp.b1, &byn = *pres1->sp.b1;
+  const int mk = nx / 2 + 1, my = ny - 2;
+  const double isx = 1.0 / scale[0], isy = 1.0 / scale[1];
+  Field2* flds[3] = {ux.get(), uy.get(), temp.get()};
+  const Base* bys[3] = {&byu, &byu, &byt};
+  const Lay nat = lay_natural();
+  // ---- 1. x-backward (c2r): value and (ik/sx) derivative -------------------
+  for (int f = 0; f < 3; ++f) {
+    ProgBuilder pb(AXIS_X, half_up(my));
+    pb.ld(1, flds[f]->vhat, mk, nat, 1.0, 0, 0, nullptr, 0, 0);
+    pb.ld(2, flds[f]->vhat, mk, nat, 1.0, 0, 0, nullptr, 0, 1);
+    pb.irfft(0, 1, 2, bx);
+    pb.st(0, ax_[f], nx, nat);
+    pb.mulik(1, mk, isx, nat, true);
+    pb.mulik(2, mk, isx, nat, true);
+    pb.irfft(0, 1, 2, bx);
+    pb.st(0, adx_[f], nx, nat);
+    add_prog(pb);
+  }
+  // ---- 2. y phase ------------------------------------------------------------
+  build_y_phase();
+  // ---- 3. x-forward (r2c) + dealias ------------------------------------------
+  const int kx_cut = dealias ? (mk * 2) / 3 : -1;
+  for (int f = 0; f < 3; ++f) {
+    ProgBuilder pb(AXIS_X, half_up(ny));
+    pb.ld(0, bconv_[f], nx, nat);
+    pb.rfft(0, 1, 2, bx);
+    pb.st(1, chat_[f], mk, nat, 1.0, 0, kx_cut, -1, 0);
+    pb.st(2, chat_[f], mk, nat, 1.0, 0, kx_cut, -1, 1);
+    add_prog(pb);
+  }
+  // ---- 4. rhs assembly + per-mode Helmholtz solves (hholtz.rs:156-197) ------
+  auto inv_of = [&](int s) {
+    const FdmaModeDev& md = solver[s]->ts.mode;
+    return ArrRef(md.inv.p, md.inv_ld, md.nlanes, md.n, false);
+  };
+  for (int f = 0; f < 3; ++f) {
+    ProgBuilder pb(AXIS_Y, mk);
+    Lay l = lay_split(ny);
+    pb.ld(0, chat_[f], ny, l, -dt);
+    if (f == 0) {
+      pb.ld(0, pres0->vhat, ny, l, -dt * isx, LF_ACC | LF_MULIK);
+    } else if (f == 1) {
+      pb.ld(1, pres0->vhat, ny, l);
+      Lay lp = pb.diff(1, ny, l, 1, -dt * isy);
+      pb.axpy(0, 1, ny, 1.0, l, lp);
+      pb.ld(1, temp->vhat, my, l, 1.0, 0, 0, nullptr, ny);
+      pb.toortho(1, byt, l);
+      pb.axpy(0, 1, ny, dt, l, l);
+      pb.ld(0, tbc_ortho_, ny, l, dt, LF_ACC);
+    } else {
+      pb.ld(0, bcdiff_, ny, l, 1.0, LF_ACC);
+    }
+    pb.ld(1, flds[f]->vhat, my, l, 1.0, 0, 0, nullptr, ny);
+    pb.toortho(1, *bys[f], l);
+    pb.axpy(0, 1, ny, 1.0, l, l);
+    pb.ld(1, inv_of(f), my, l, 1.0, LF_BCAST);
+    solver[f]->emit_y(pb, 0, 1, l, true);
+    pb.st(0, flds[f]->vhat, my, l);
+    add_prog(pb);
+  }
+  // ---- 5. divergence + Poisson (per-mode) -------------------------------------
+  {
+    ProgBuilder pb(AXIS_Y, mk);
+    Lay l = lay_split(ny);
+    pb.ld(0, ux->vhat, my, l, isx, LF_MULIK, 0, nullptr, ny);
+    pb.toortho(0, byu, l);
+    pb.ld(1, uy->vhat, my, l, 1.0, 0, 0, nullptr, ny);
+    pb.toortho(1, byu, l);
+    Lay ld = pb.diff(1, ny, l, 1, isy);
+    pb.axpy(0, 1, ny, 1.0, l, ld);
+    pb.st(0, div_, ny, l);
+    pb.ld(1, inv_of(3), my, l, 1.0, LF_BCAST);
+    solver[3]->emit_y(pb, 0, 1, l, true);
+    pb.setzero00(0, l, true);
+    pb.st(0, pres1->vhat, my, l);
+    add_prog(pb);
+  }
+  // ---- 6. projection + pressure update ------------------------------------------
+  {
+    ProgBuilder pb(AXIS_Y, mk);
+    Lay l = lay_split(ny);
+    pb.ld(0, pres1->vhat, my, l, isx, LF_MULIK, 0, nullptr, ny);
+    pb.toortho(0, byn, l);
+    pb.fromortho(0, byu, l);
+    pb.st(0, ux->vhat, my, l, -1.0, LF_ACC);
+    pb.ld(0, pres1->vhat, my, l, 1.0, 0, 0, nullptr, ny);
+    pb.toortho(0, byn, l);
+    pb.copy(1, 0, ny, l, l);
+    Lay ld = pb.diff(0, ny, l, 1, isy);
+    pb.fromortho(0, byu, ld);
+    pb.st(0, uy->vhat, my, ld, -1.0, LF_ACC);
+    pb.scale(1, ny, 1.0 / dt, l);
+    pb.ld(1, div_, ny, l, -nu, LF_ACC);
+    pb.ld(1, pres0->vhat, ny, l, 1.0, LF_ACC);
+    pb.st(1, pres0->vhat, ny, l);
+    add_prog(pb);
+  }
+}
+
+void Navier2D::run_step() {
+  for (const StepOp& op : ops_) {
+    switch (op.kind) {
+      case 0: step_[op.idx].launch(stream); break;
+      case 1: solver[3]->gemm_fwd(r1_, g_, ny); break;
+      case 2: solver[3]->gemm_bwd(h_, pres1->vhat, ny - 2); break;
+      case 3: launch_zero_elems(pres1->vhat.d(), 1, stream); break;
+    }
+  }
+}
+
+void Navier2D::update(int nsteps) {
+  build_step();
+  for (Field2* f : {temp.get(), ux.get(), uy.get(), pres0.get(), pres1.get(), field.get()}) f->stream = stream;
+  for (auto& s : solver) s->stream = stream;
+  if (!periodic) {  // d/dy pres of the current pressure (it may have been uploaded since the last step)
+    pres0->gradient(0, 1, scale);
+    copy_arr(dyp_, pres0->ortho, stream);
+  }
+#ifndef RP_EMU
+  if (use_graph_) {
+    if (!graph_ || graph_dirty_) {
+      if (graph_) {
+        cudaGraphExecDestroy(graph_);
+        graph_ = nullptr;
+      }
+      cudaStream_t cs;
+      RP_CUDA_CHECK(cudaStreamCreate(&cs));
+      cudaStream_t saved = stream;
+      stream = cs;
+      for (auto& s : solver) s->stream = cs;
+      cudaGraph_t g = nullptr;
+      RP_CUDA_CHECK(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+      run_step();
+      RP_CUDA_CHECK(cudaStreamEndCapture(cs, &g));
+      RP_CUDA_CHECK(cudaGraphInstantiate(&graph_, g, 0));
+      cudaGraphDestroy(g);
+      stream = saved;
+      for (auto& s : solver) s->stream = saved;
+      cudaStreamDestroy(cs);
+      graph_dirty_ = false;
+    }
+    for (int i = 0; i < nsteps; ++i) {
+      RP_CUDA_CHECK(cudaGraphLaunch(graph_, stream));
+      time += dt;
+    }
+    return;
+  }
+#endif
+  for (int i = 0; i < nsteps; ++i) {
+    run_step();
+    time += dt;  // navier.rs:764
+  }
+}
+
+// --------------------------------------------------------------------------
+// Diagnostics (src/navier/functions.rs, navier.rs:855-879)
+// --------------------------------------------------------------------------
+double Navier2D::div_norm() {
+  ux->gradient(1, 0, scale);
+  uy->gradient(0, 1, scale);
+  const int rc = ux->cplx ? 2 : 1;
+  Arr& o = ux->ortho;
+  launch_combine(o.d(), o.d(), uy->ortho.d(), nullptr, o.ld * rc, o.rows, o.cols * rc, 1.0, 1.0, stream);
+  rt::dzero(red_.p, 8, stream);
+  launch_wsum(o.d(), nullptr, o.ld * rc, o.rows, o.cols * rc, nullptr, nullptr, 3, red_.as<double>(), stream);
+  double r = 0.0;
+  rt::d2h(&r, red_.p, 8, stream);
+  rt::sync(stream);
+  return std::sqrt(r);
+}
+
+void Navier2D::eval(double* o_nu, double* o_nuvol, double* o_re, double* o_div, double* o_ekin) {
+  for (Field2* f : {temp.get(), ux.get(), uy.get(), pres0.get(), pres1.get(), field.get()}) f->stream = stream;
+  Field2& F = *field;
+  const int rc = F.cplx ? 2 : 1;
+  auto set_that = [&]() {  // field.vhat = temp.to_ortho() + fieldbc.to_ortho()
+    temp->to_ortho();
+    launch_combine(F.vhat.d(), temp->ortho.d(), tbc_ortho_.d(), nullptr, F.vhat.ld * rc, F.o0, F.o1 * rc, 1.0, 1.0, stream);
+  };
+  if (o_div) *o_div = div_norm();
+  if (o_nu) {  // functions.rs:12-36
+    set_that();
+    F.gradient(0, 1, nullptr);
+    launch_combine(F.vhat.d(), F.ortho.d(), nullptr, nullptr, F.vhat.ld * rc, F.o0, F.o1 * rc,
+                   -1.0 * (1.0 / (scale[1] / 2.0)), 0.0, stream);
+    F.backward();
+    std::vector<double> xa;
+    F.average_axis0(xa);
+    *o_nu = (xa[xa.size() - 1] + xa[0]) / 2.0;
+  }
+  if (o_nuvol) {  // functions.rs:42-75
+    set_that();
+    F.backward();
+    uy->backward();
+    Arr& tmp = phys_[7];
+    launch_combine(tmp.d(), F.v.d(), nullptr, nullptr, tmp.ld, nx, ny, 1.0, 0.0, stream);  // T physical
+    F.gradient(0, 1, nullptr);
+    launch_combine(F.vhat.d(), F.ortho.d(), nullptr, nullptr, F.vhat.ld * rc, F.o0, F.o1 * rc, 1.0 / (scale[1] * -1.0), 0.0,
+                   stream);
+    F.backward();
+    // field.v = (dtdz + uy*T/kappa) * 2 * scale[1]
+    launch_combine(F.v.d(), F.v.d(), tmp.d(), uy->v.d(), F.v.ld, nx, ny, 2.0 * scale[1], 1.0 / ka, stream);
+    *o_nuvol = F.average();
+  }
+  if (o_re || o_ekin) {  // functions.rs:82-101
+    ux->backward();
+    uy->backward();
+    for (int mode = 1; mode <= 2; ++mode) {
+      if ((mode == 1 && !o_re) || (mode == 2 && !o_ekin)) continue;
+      rt::dzero(red_.p, 8, stream);
+      // averaging weights of `field` (unscaled coords; the ratio dx/L is scale invariant)
+      launch_wsum(ux->v.d(), uy->v.d(), ux->v.ld, nx, ny, F.weights_x(), F.weights_y(), mode, red_.as<double>(), stream);
+      double r = 0.0;
+      rt::d2h(&r, red_.p, 8, stream);
+      rt::sync(stream);
+      if (mode == 1)
+        *o_re = r * (2.0 * scale[1] / nu);
+      else
+        *o_ekin = r;
+    }
+  }
+}
+
+}  // namespace rp
