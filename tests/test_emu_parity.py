@@ -1,0 +1,113 @@
+"""CPU-side check of the CUDA kernels' arithmetic: the same kernel sources,
+compiled against the cuemu emulator, versus the numpy oracle.  (The parity
+tests proper are test_gpu_parity.py; these keep index arithmetic, layouts and
+numerics honest on a box without a GPU.)"""
+import numpy as np
+import pytest
+
+import parity_cases as pc
+
+
+@pytest.mark.parametrize(
+    "kx,nx,ky,ny",
+    [
+        ("chebyshev", 17, "chebyshev", 33),          # pow2 DCT lengths (N = 16, 32)
+        ("cheb_dirichlet", 16, "cheb_dirichlet", 17),  # Bluestein x (N = 15), pow2 y
+        ("cheb_neumann", 33, "cheb_dirichlet", 20),    # pow2 x, Bluestein y (N = 19)
+        ("cheb_dirichlet", 64, "cheb_neumann", 64),    # config-1 shape: N = 63 both
+        ("fourier_r2c", 16, "cheb_dirichlet", 17),
+        ("fourier_r2c", 24, "chebyshev", 21),          # Bluestein r2c (n = 24)
+        ("fourier_r2c", 64, "cheb_neumann", 65),
+        ("chebyshev", 7, "cheb_dirichlet", 9),         # tiny, odd/ragged pairs
+    ],
+)
+def test_field_ops(emu, kx, nx, ky, ny):
+    pc.check_field_ops(emu, kx, nx, ky, ny)
+
+
+@pytest.mark.parametrize("nx,ny", [(7, 7), (16, 7), (33, 40), (129, 66)])
+def test_hholtz_adi(emu, nx, ny):
+    pc.check_adi(emu, nx, ny)
+
+
+def test_hholtz_adi_kat(emu):  # hholtz_adi.rs:176-207 through the device path
+    import rustpde_b200 as R
+    f = R.Field2(R.Space2(R.cheb_dirichlet(7), R.cheb_dirichlet(7)), lib=emu)
+    x = R.HholtzAdi(f, [1.0, 1.0]).solve(np.tile(np.arange(1.0, 8.0), (7, 1)))
+    y = np.array(
+        [
+            [-7.083e-03, -9.025e-03, -5.210e-03, 4.146e-03, 3.520e-03],
+            [5.809e-04, 7.402e-04, 4.273e-04, -3.401e-04, -2.887e-04],
+            [1.699e-04, 2.165e-04, 1.250e-04, -9.951e-05, -8.447e-05],
+            [-1.007e-03, -1.283e-03, -7.406e-04, 5.895e-04, 5.004e-04],
+            [-6.775e-04, -8.632e-04, -4.983e-04, 3.966e-04, 3.366e-04],
+        ]
+    )
+    assert np.abs(x - y).max() < 1e-6
+
+
+@pytest.mark.parametrize("which,kx,ky,nx,ny", [
+    ("poisson", "cheb_neumann", "cheb_neumann", 16, 19),
+    ("poisson", "cheb_dirichlet", "cheb_dirichlet", 8, 7),
+    ("hholtz", "cheb_dirichlet", "cheb_dirichlet", 40, 33),
+    ("poisson", "cheb_neumann", "cheb_neumann", 140, 34),   # more than one 128-row GEMM tile
+])
+def test_fast_diag_shared_eig(emu, which, kx, ky, nx, ny):
+    e1, e2, _, _ = pc.check_tensor_shared_eig(emu, which, kx, ky, nx, ny)
+    assert e1 <= pc.TOL and e2 <= pc.TOL, (e1, e2)
+
+
+def test_poisson_kat_own_lapack(emu):  # poisson.rs:208-243, set-up through the library's own dgeev
+    import rustpde_b200 as R
+    from test_oracle_kat import POISSON_2D
+    f = R.Field2(R.Space2(R.cheb_dirichlet(8), R.cheb_dirichlet(7)), lib=emu)
+    b = np.tile(np.arange(1.0, 8.0), (8, 1))
+    x = R.Poisson(f, [1.0, 1.0]).solve(b)
+    assert np.abs(x - POISSON_2D).max() < 2e-6
+    xc = R.Poisson(f, [1.0, 1.0]).solve(b * (1 + 1j))
+    assert np.abs(xc - POISSON_2D * (1 + 1j)).max() < 2e-6
+
+
+@pytest.mark.parametrize("nx,ny", [(16, 7), (32, 33)])
+def test_fast_diag_fourier(emu, nx, ny):
+    pc.check_tensor_fourier(emu, nx, ny)
+
+
+@pytest.mark.parametrize("nx,ny,adiabatic", [(16, 17, True), (24, 20, False), (33, 33, True)])
+def test_navier_confined(emu, nx, ny, adiabatic):
+    err, derr, dn, do = pc.check_navier_steps(emu, False, nx, ny, 4, adiabatic=adiabatic, batch=2)
+    assert max(derr) < 1e-9, (derr, dn, do)
+
+
+@pytest.mark.parametrize("nx,ny", [(16, 17), (24, 20)])
+def test_navier_periodic(emu, nx, ny):
+    err, derr, dn, do = pc.check_navier_steps(emu, True, nx, ny, 4, batch=2)
+    assert max(derr) < 1e-9, (derr, dn, do)
+
+
+def test_navier_aspect_and_no_dealias(emu):
+    import oracle as O
+    import rustpde_b200 as R
+    o = O.Navier2D.new_periodic(16, 17, 1e4, 0.7, 0.02, 1.5, banded=True)
+    n = R.Navier2D.new_periodic(16, 17, 1e4, 0.7, 0.02, 1.5, lib=emu)
+    o.dealias = False
+    n.dealias = False
+    for x in (n, o):
+        x.set_velocity(0.1, 2.0, 1.0)
+        x.set_temperature(0.3, 1.0, 2.0)
+    n.update(3)
+    for _ in range(3):
+        o.update()
+    err = pc.navier_field_errors(n, o)
+    assert max(err.values()) < 1e-9, err
+
+
+def test_shape_errors(emu):
+    import rustpde_b200 as R
+    f = R.Field2(R.Space2(R.cheb_dirichlet(8), R.cheb_dirichlet(9)), lib=emu)
+    with pytest.raises(R.RustpdeError):
+        f.v = np.zeros((8, 8))
+    with pytest.raises(R.RustpdeError):
+        R.HholtzAdi(f, [1.0, 1.0]).solve(np.zeros((9, 9)))
+    with pytest.raises(R.RustpdeError):
+        f.from_ortho(np.zeros((6, 7)))

