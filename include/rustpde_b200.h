@@ -125,6 +125,11 @@ int rp_navier_field(rp_navier_t* h, int which, rp_field_t** out);              /
 int rp_navier_export_eig(rp_navier_t* h, double* lam, double* q, double* p);   /* pressure Poisson set-up data */
 int rp_navier_launches_per_step(rp_navier_t* h, int* n);
 int rp_navier_set_graph(rp_navier_t* h, int on);                               /* CUDA-graph replay of update() (default on) */
+/* Measurement aids (no reference counterpart): per-launch device time of update(), averaged over
+ * `reps` eagerly launched steps (CUDA events on the launching stream; advances the solution), and
+ * the name / algorithmic bytes / flops of launch i. */
+int rp_navier_profile(rp_navier_t* h, int reps, double* ms, size_t cap, int* nops);
+int rp_navier_op_info(rp_navier_t* h, int i, char* name, size_t name_len, double* bytes, double* flops);
 
 #ifdef __cplusplus
 }

@@ -436,6 +436,20 @@ class Navier2D:
         self._lib.call("rp_navier_launches_per_step", self._h, C.byref(n))
         return n.value
 
+    def profile(self, reps=5):
+        """Per-launch device time of update() (ms, mean of `reps` eager steps) with the
+        launch's name and algorithmic bytes / flops.  Advances the solution by `reps` steps."""
+        ms = np.zeros(128)
+        nops = C.c_int()
+        self._lib.call("rp_navier_profile", self._h, int(reps), _dp(ms), ms.size, C.byref(nops))
+        out = []
+        for i in range(nops.value):
+            name = C.create_string_buffer(64)
+            by, fl = C.c_double(), C.c_double()
+            self._lib.call("rp_navier_op_info", self._h, i, name, 64, C.byref(by), C.byref(fl))
+            out.append({"name": name.value.decode(), "ms": float(ms[i]), "bytes": by.value, "flops": fl.value})
+        return out
+
 
 def integrate(pde, max_time, save_intervall=None, exit_every=1):
     """src/lib.rs:155-187.  `exit_every` > 1 checks the NaN break criterion less

@@ -355,6 +355,27 @@ int rp_navier_export_eig(rp_navier_t* h, double* lam, double* q, double* p) {
 }
 int rp_navier_launches_per_step(rp_navier_t* h, int* n) { NAV_GUARD(if (n) *n = N.launches_per_step()); }
 int rp_navier_set_graph(rp_navier_t* h, int on) { NAV_GUARD(N.set_graph(on != 0)); }
+int rp_navier_profile(rp_navier_t* h, int reps, double* ms, size_t cap, int* nops) {
+  NAV_GUARD({
+    need(reps > 0 && ms, RP_ERR_INVALID, "bad profile arguments");
+    std::vector<double> v;
+    N.profile(reps, v);
+    if (nops) *nops = (int)v.size();
+    for (size_t i = 0; i < v.size() && i < cap; ++i) ms[i] = v[i];
+  });
+}
+int rp_navier_op_info(rp_navier_t* h, int i, char* name, size_t name_len, double* bytes, double* flops) {
+  NAV_GUARD({
+    const auto& info = N.op_info();
+    need(i >= 0 && i < (int)info.size(), RP_ERR_INVALID, "op index out of range");
+    if (name && name_len) {
+      strncpy(name, info[i].name.c_str(), name_len - 1);
+      name[name_len - 1] = 0;
+    }
+    if (bytes) *bytes = info[i].bytes;
+    if (flops) *flops = info[i].flops;
+  });
+}
 
 }  // extern "C"
 #pragma GCC visibility pop

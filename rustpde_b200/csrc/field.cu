@@ -70,9 +70,7 @@ void Field2::build_transforms() {
       pb.st(0, vhat, m0, l);
     } else {
       pb.ld(0, ta_, n0, nat);
-      pb.rfft(0, 1, 2, b0);
-      pb.st(1, vhat, m0, nat, 1.0, 0, -1, -1, 0);
-      pb.st(2, vhat, m0, nat, 1.0, 0, -1, -1, 1);
+      pb.rfft_st(0, vhat, b0);
     }
     fwd_x_ = pb.build();
   }
@@ -85,9 +83,7 @@ void Field2::build_transforms() {
       l = pb.dct(0, b0, l, true);
       pb.st(0, ta_, n0, l);
     } else {
-      pb.ld(1, vhat, m0, nat, 1.0, 0, 0, nullptr, 0, 0);
-      pb.ld(2, vhat, m0, nat, 1.0, 0, 0, nullptr, 0, 1);
-      pb.irfft(0, 1, 2, b0);
+      pb.irfft_ld(0, vhat, b0);
       pb.st(0, ta_, n0, nat);
     }
     bwd_x_ = pb.build();

@@ -911,33 +911,50 @@ RP_DEVNI void op_dct(const Blk& b, const Instr& I) {
 }
 
 // ===========================================================================
-// Real FFT along x (r2c.rs:250-303) on a packed pair of real lanes.
-//   RFFT : r0 (natural, n reals per component) -> r1 = X_a, r2 = X_b (n/2+1)
-//   IRFFT: r1, r2 -> r0; Im of the DC and Nyquist bins is ignored (c2r).
+// Real FFT along x (r2c.rs:250-303) on a packed pair of real lanes (columns
+// 2P, 2P+1), fused with the global-memory side so only one register is needed:
+//   RFFT : r0 (natural, n reals per component) -> FFT -> X_a, X_b stored to the
+//          complex array's columns 2P, 2P+1 (n/2+1 rows), scale s0, dealias cut i0
+//   IRFFT: complex columns 2P, 2P+1 (optionally times i k s0) -> packed spectrum
+//          -> inverse FFT -> r0.  Im of the DC and Nyquist bins is ignored (c2r).
 // ===========================================================================
 RP_DEVNI void op_rfft(const Blk& b, const Instr& I) {
-  const FftPlan P = *(const FftPlan*)I.p0;
+  const FftPlan P = *(const FftPlan*)I.p1;
   const int n = P.L, m = n / 2 + 1;
   dft_any(b, lane_ptr(b, I.r0, 0), b.capP, b.T, P, false, 1.0);
+  cplx* dst = (cplx*)I.p0;
   for (int idx = b.tid; idx < b.T * m; idx += b.nthr) {
-    const int t = idx / m, k = idx % m;
+    const int k = idx / b.T, t = idx % b.T;
+    const int ca = 2 * (b.unit0 + t), cb = ca + 1;
     const cplx* z = lane_ptr(b, I.r0, t);
     const cplx zk = z[padi(k)];
     const cplx zm = cconj(z[padi((n - k) % n)]);
     const cplx s = cadd(zk, zm), d = csub(zk, zm);
-    lane_ptr(b, I.r1, t)[padi(k)] = mk(0.5 * s.x, 0.5 * s.y);
-    lane_ptr(b, I.r2, t)[padi(k)] = mk(0.5 * d.y, -0.5 * d.x);
+    double h = 0.5 * I.s0;
+    if ((I.flags & LF_CUT) && k >= I.i0) h = 0.0;
+    if (ca < I.nlanes) dst[(size_t)k * I.ld + ca] = mk(h * s.x, h * s.y);
+    if (cb < I.nlanes) dst[(size_t)k * I.ld + cb] = mk(h * d.y, -h * d.x);
   }
   __syncthreads();
 }
 
 RP_DEVNI void op_irfft(const Blk& b, const Instr& I) {
-  const FftPlan P = *(const FftPlan*)I.p0;
+  const FftPlan P = *(const FftPlan*)I.p1;
   const int n = P.L, m = n / 2 + 1;
+  const cplx* src = (const cplx*)I.p0;
   for (int idx = b.tid; idx < b.T * m; idx += b.nthr) {
-    const int t = idx / m, k = idx % m;
-    cplx xa = lane_ptr(b, I.r1, t)[padi(k)];
-    cplx xb = lane_ptr(b, I.r2, t)[padi(k)];
+    const int k = idx / b.T, t = idx % b.T;
+    const int ca = 2 * (b.unit0 + t), cb = ca + 1;
+    cplx xa = (ca < I.nlanes) ? src[(size_t)k * I.ld + ca] : mk(0, 0);
+    cplx xb = (cb < I.nlanes) ? src[(size_t)k * I.ld + cb] : mk(0, 0);
+    if (I.flags & LF_MULIK) {
+      const double kk = (double)k * I.s0;
+      xa = mk(-kk * xa.y, kk * xa.x);
+      xb = mk(-kk * xb.y, kk * xb.x);
+    } else {
+      xa = cscale(xa, I.s0);
+      xb = cscale(xb, I.s0);
+    }
     if (k == 0 || 2 * k == n) {
       xa.y = 0.0;
       xb.y = 0.0;

@@ -42,6 +42,7 @@ struct ArrRef {
 struct Built {
   DevBuf dprog;
   int nblocks = 0, nthreads = 0, smem = 0;
+  double bytes = 0.0;  // algorithmic global-memory bytes of one launch (loads + stores)
   bool valid = false;
   void launch(cudaStream_t s) const;
 };
@@ -68,8 +69,8 @@ class ProgBuilder {
   void mulik(int r, int n, double a, Lay lay, bool elem_k = false);
   void zero(int r, int n, Lay lay);
   void setzero00(int r, Lay lay, bool complex_lanes);
-  void rfft(int r0, int r1, int r2, const Base& b);
-  void irfft(int r0, int r1, int r2, const Base& b);
+  void rfft_st(int r0, ArrRef dst, const Base& b, double s = 1.0, int cut_k = -1);   // r2c + store
+  void irfft_ld(int r0, ArrRef src, const Base& b, double s = 1.0, bool mulik = false);  // load + c2r
   Built build();
   int default_anchor = 0;  // set by callers: SPLIT anchor large enough for the program
 
@@ -78,6 +79,7 @@ class ProgBuilder {
   void touch(int r, Lay lay, int n);
   Program p_;
   int fftlen_ = 0, wbcap_ = 0;
+  double bytes_unit_ = 0.0;  // bytes moved per slot unit
 };
 
 struct Space2 {
@@ -183,6 +185,15 @@ class Navier2D {
   void sync();
   Field2* field_by_index(int which);
   int launches_per_step() const { return launches_per_step_; }
+  struct OpInfo {
+    std::string name;
+    double bytes, flops;  // algorithmic bytes / flops of one launch
+  };
+  const std::vector<OpInfo>& op_info() {
+    build_step();
+    return opinfo_;
+  }
+  void profile(int reps, std::vector<double>& ms);
   void set_graph(bool on) {
     use_graph_ = on;
     graph_dirty_ = true;
@@ -193,7 +204,7 @@ class Navier2D {
   void build_step_confined();
   void build_step_periodic();
   void build_y_phase();
-  void add_prog(ProgBuilder& pb);
+  void add_prog(ProgBuilder& pb, const char* name);
   void rebuild_bc();
   void apply_ic(Field2& f, double amp, double m, double n, bool sin_cos);
   void run_step();
@@ -215,6 +226,8 @@ class Navier2D {
     int idx;
   };
   std::vector<StepOp> ops_;
+  std::vector<OpInfo> opinfo_;
+  void run_op(const StepOp& op);
   int launches_per_step_ = 0;
   DevBuf red_;
 #ifndef RP_EMU

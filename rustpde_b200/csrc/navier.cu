@@ -180,9 +180,10 @@ void Navier2D::build_step() {
   launches_per_step_ = (int)ops_.size();
 }
 
-void Navier2D::add_prog(ProgBuilder& pb) {
+void Navier2D::add_prog(ProgBuilder& pb, const char* name) {
   step_.push_back(pb.build());
   ops_.push_back(StepOp{0, (int)step_.size() - 1});
+  opinfo_.push_back(OpInfo{name, step_.back().bytes, 0.0});
 }
 
 // y phase shared by both geometries: physical-space products (conv_term.rs:41)
@@ -217,7 +218,7 @@ void Navier2D::build_y_phase() {
     pb.toortho(0, by, l);
     Lay lx = pb.dct(0, byo, l, true);
     pb.st(0, phys_[dx_idx[f]], ny, lx);
-    add_prog(pb);
+    add_prog(pb, "y_backward");
   }
   const int ny_cut = dealias ? (ny * 2) / 3 : -1;  // navier.rs:1029
   for (int f = 0; f < 3; ++f) {
@@ -232,7 +233,7 @@ void Navier2D::build_y_phase() {
     pb.mulpw(2, 0, 1, ny, nat, nat, true);
     Lay l = pb.dct(2, byo, nat, false);
     pb.st(2, bconv_[f], ny, l, 1.0, 0, ny_cut, -1);
-    add_prog(pb);
+    add_prog(pb, "conv_y_forward");
   }
 }
 
@@ -258,7 +259,7 @@ void Navier2D::build_step_confined() {
     l1 = pb.dct(1, bxo, l1, true);
     pb.st(0, ax_[f], nx, l0);
     pb.st(1, adx_[f], nx, l1);
-    add_prog(pb);
+    add_prog(pb, "x_backward_dct");
   }
   // ---- 2. y phase ----------------------------------------------------------
   build_y_phase();
@@ -292,7 +293,7 @@ void Navier2D::build_step_confined() {
     }
     solver[f]->emit_x(pb, 0, l0);
     pb.st(0, w_[f], mx, l0);
-    add_prog(pb);
+    add_prog(pb, "x_forward_rhs_adi_x");
   }
   // ---- 4. y half of HholtzAdi (+ pieces of the divergence) -----------------
   for (int f = 0; f < 3; ++f) {
@@ -309,7 +310,7 @@ void Navier2D::build_step_confined() {
       Lay ld = pb.diff(0, ny, l, 1, isy);
       pb.st(0, ey_, ny, ld);
     }
-    add_prog(pb);
+    add_prog(pb, "adi_y");
   }
   // ---- 5. divergence (navier.rs:698-703) + B2x of the Poisson rhs ----------
   {
@@ -324,10 +325,11 @@ void Navier2D::build_step_confined() {
     pb.st(0, div_, nx, ld);
     solver[3]->emit_x(pb, 0, ld);
     pb.st(0, r1_, mx, ld);
-    add_prog(pb);
+    add_prog(pb, "divergence_b2x");
   }
   // ---- 6-8. fast diagonalisation: P., per-mode Fdma_y, Q. (poisson.rs:131-149)
   ops_.push_back(StepOp{1, 0});
+  opinfo_.push_back(OpInfo{"poisson_gemm_fwd", 8.0 * ((double)mx * mx + 2.0 * mx * ny), 2.0 * mx * (double)mx * ny});
   {
     ProgBuilder pb(AXIS_Y, half_up(mx));
     Lay l = lay_split(ny);
@@ -336,10 +338,12 @@ void Navier2D::build_step_confined() {
     pb.ld(1, ArrRef(md.inv.p, md.inv_ld, md.nlanes, md.n, false), my, l);
     solver[3]->emit_y(pb, 0, 1, l, false);
     pb.st(0, h_, my, l);
-    add_prog(pb);
+    add_prog(pb, "poisson_mode_y");
   }
   ops_.push_back(StepOp{2, 0});
+  opinfo_.push_back(OpInfo{"poisson_gemm_bwd", 8.0 * ((double)mx * mx + 2.0 * mx * my), 2.0 * mx * (double)mx * my});
   ops_.push_back(StepOp{3, 0});  // pres[1].vhat[[0,0]] = 0   (navier.rs:714)
+  opinfo_.push_back(OpInfo{"zero_mode00", 8.0, 0.0});
   // ---- 9. projection (navier.rs:683-695): x part -----------------------------
   {
     ProgBuilder pb(AXIS_X, half_up(my));
@@ -352,7 +356,7 @@ void Navier2D::build_step_confined() {
     pb.fromortho(1, bxu, l);
     pb.st(0, a1_, mx, ld);
     pb.st(1, a2_, mx, l);
-    add_prog(pb);
+    add_prog(pb, "project_x");
   }
   // ---- 10. projection: y part; u -= from_ortho(grad phi) ---------------------
   {
@@ -367,7 +371,7 @@ void Navier2D::build_step_confined() {
     Lay ld = pb.diff(0, ny, l, 1, isy);
     pb.fromortho(0, byu, ld);
     pb.st(0, uy->vhat, my, ld, -1.0, LF_ACC);
-    add_prog(pb);
+    add_prog(pb, "project_y");
   }
   // ---- 11. pressure update (navier.rs:717-721) + d/dy pres for the next step --
   {
@@ -382,7 +386,7 @@ void Navier2D::build_step_confined() {
     pb.st(0, pres0->vhat, ny, l);
     Lay ld = pb.diff(0, ny, l, 1, isy);
     pb.st(0, dyp_, ny, ld);
-    add_prog(pb);
+    add_prog(pb, "pressure_update");
   }
   (void)byo;
   (void)byt;
@@ -398,15 +402,11 @@ void Navier2D::build_step_periodic() {
   // ---- 1. x-backward (c2r): value and (ik/sx) derivative -------------------
   for (int f = 0; f < 3; ++f) {
     ProgBuilder pb(AXIS_X, half_up(my));
-    pb.ld(1, flds[f]->vhat, mk, nat, 1.0, 0, 0, nullptr, 0, 0);
-    pb.ld(2, flds[f]->vhat, mk, nat, 1.0, 0, 0, nullptr, 0, 1);
-    pb.irfft(0, 1, 2, bx);
+    pb.irfft_ld(0, flds[f]->vhat, bx);
     pb.st(0, ax_[f], nx, nat);
-    pb.mulik(1, mk, isx, nat, true);
-    pb.mulik(2, mk, isx, nat, true);
-    pb.irfft(0, 1, 2, bx);
+    pb.irfft_ld(0, flds[f]->vhat, bx, isx, true);
     pb.st(0, adx_[f], nx, nat);
-    add_prog(pb);
+    add_prog(pb, "x_backward_c2r");
   }
   // ---- 2. y phase ------------------------------------------------------------
   build_y_phase();
@@ -415,10 +415,8 @@ void Navier2D::build_step_periodic() {
   for (int f = 0; f < 3; ++f) {
     ProgBuilder pb(AXIS_X, half_up(ny));
     pb.ld(0, bconv_[f], nx, nat);
-    pb.rfft(0, 1, 2, bx);
-    pb.st(1, chat_[f], mk, nat, 1.0, 0, kx_cut, -1, 0);
-    pb.st(2, chat_[f], mk, nat, 1.0, 0, kx_cut, -1, 1);
-    add_prog(pb);
+    pb.rfft_st(0, chat_[f], bx, 1.0, kx_cut);
+    add_prog(pb, "x_forward_r2c");
   }
   // ---- 4. rhs assembly + per-mode Helmholtz solves (hholtz.rs:156-197) ------
   auto inv_of = [&](int s) {
@@ -448,7 +446,7 @@ void Navier2D::build_step_periodic() {
     pb.ld(1, inv_of(f), my, l, 1.0, LF_BCAST);
     solver[f]->emit_y(pb, 0, 1, l, true);
     pb.st(0, flds[f]->vhat, my, l);
-    add_prog(pb);
+    add_prog(pb, "rhs_hholtz_mode_y");
   }
   // ---- 5. divergence + Poisson (per-mode) -------------------------------------
   {
@@ -465,7 +463,7 @@ void Navier2D::build_step_periodic() {
     solver[3]->emit_y(pb, 0, 1, l, true);
     pb.setzero00(0, l, true);
     pb.st(0, pres1->vhat, my, l);
-    add_prog(pb);
+    add_prog(pb, "divergence_poisson_mode_y");
   }
   // ---- 6. projection + pressure update ------------------------------------------
   {
@@ -485,19 +483,53 @@ void Navier2D::build_step_periodic() {
     pb.ld(1, div_, ny, l, -nu, LF_ACC);
     pb.ld(1, pres0->vhat, ny, l, 1.0, LF_ACC);
     pb.st(1, pres0->vhat, ny, l);
-    add_prog(pb);
+    add_prog(pb, "project_pressure_update");
+  }
+}
+
+void Navier2D::run_op(const StepOp& op) {
+  switch (op.kind) {
+    case 0: step_[op.idx].launch(stream); break;
+    case 1: solver[3]->gemm_fwd(r1_, g_, ny); break;
+    case 2: solver[3]->gemm_bwd(h_, pres1->vhat, ny - 2); break;
+    case 3: launch_zero_elems(pres1->vhat.d(), 1, stream); break;
   }
 }
 
 void Navier2D::run_step() {
-  for (const StepOp& op : ops_) {
-    switch (op.kind) {
-      case 0: step_[op.idx].launch(stream); break;
-      case 1: solver[3]->gemm_fwd(r1_, g_, ny); break;
-      case 2: solver[3]->gemm_bwd(h_, pres1->vhat, ny - 2); break;
-      case 3: launch_zero_elems(pres1->vhat.d(), 1, stream); break;
+  for (const StepOp& op : ops_) run_op(op);
+}
+
+// Per-launch device times of one update(), averaged over `reps` eager steps
+// (CUDA events on the launching stream).  Advances the solution by `reps` steps.
+void Navier2D::profile(int reps, std::vector<double>& ms) {
+  build_step();
+  for (auto& s : solver) s->stream = stream;
+  ms.assign(ops_.size(), 0.0);
+#ifndef RP_EMU
+  std::vector<cudaEvent_t> ev(ops_.size() + 1);
+  for (auto& e : ev) RP_CUDA_CHECK(cudaEventCreate(&e));
+  for (int r = 0; r < reps; ++r) {
+    RP_CUDA_CHECK(cudaEventRecord(ev[0], stream));
+    for (size_t i = 0; i < ops_.size(); ++i) {
+      run_op(ops_[i]);
+      RP_CUDA_CHECK(cudaEventRecord(ev[i + 1], stream));
     }
+    RP_CUDA_CHECK(cudaStreamSynchronize(stream));
+    for (size_t i = 0; i < ops_.size(); ++i) {
+      float t = 0.f;
+      RP_CUDA_CHECK(cudaEventElapsedTime(&t, ev[i], ev[i + 1]));
+      ms[i] += (double)t / reps;
+    }
+    time += dt;
   }
+  for (auto& e : ev) cudaEventDestroy(e);
+#else
+  for (int r = 0; r < reps; ++r) {
+    run_step();
+    time += dt;
+  }
+#endif
 }
 
 void Navier2D::update(int nsteps) {

@@ -81,6 +81,7 @@ void ProgBuilder::ld(int r, ArrRef a, int n, Lay lay, double s, int flags, int s
   I.ld = a.ld;
   I.nlanes = (p_.axis == AXIS_Y) ? a.rows : a.cols;
   I.s0 = s;
+  bytes_unit_ += (double)n * ((flags & LF_BCAST) ? 8.0 : 16.0);
   touch(r, lay, std::max(n, zfill));
 }
 
@@ -103,6 +104,7 @@ void ProgBuilder::st(int r, ArrRef a, int n, Lay lay, double s, int flags, int c
   I.ld = a.ld;
   I.nlanes = (p_.axis == AXIS_Y) ? a.rows : a.cols;
   I.s0 = s;
+  bytes_unit_ += (double)n * 16.0 * ((flags & LF_ACC) ? 2.0 : 1.0);
   touch(r, lay, n);
 }
 
@@ -270,29 +272,36 @@ void ProgBuilder::setzero00(int r, Lay lay, bool complex_lanes) {
   I.lay = lay;
   I.flags = complex_lanes ? LF_COMPLEX : 0;
 }
-void ProgBuilder::rfft(int r0, int r1, int r2, const Base& b) {
+void ProgBuilder::rfft_st(int r0, ArrRef dst, const Base& b, double s, int cut_k) {
   Instr& I = add(OP_RFFT);
   I.r0 = r0;
-  I.r1 = r1;
-  I.r2 = r2;
   I.n = b.n;
-  I.p0 = b.d_fft.p;
+  I.p0 = dst.p;
+  I.p1 = b.d_fft.p;
+  I.ld = dst.ld;
+  I.nlanes = dst.cols;
+  I.s0 = s;
+  if (cut_k >= 0) {
+    I.flags |= LF_CUT;
+    I.i0 = cut_k;
+  }
+  bytes_unit_ += (double)b.m * 32.0;
   touch(r0, lay_natural(), b.n);
-  touch(r1, lay_natural(), b.m);
-  touch(r2, lay_natural(), b.m);
   fftlen_ = std::max(fftlen_, b.fft_len());
   if (!b.fft.plan.pow2) wbcap_ = std::max(wbcap_, b.fft.plan.Lb);
 }
-void ProgBuilder::irfft(int r0, int r1, int r2, const Base& b) {
+void ProgBuilder::irfft_ld(int r0, ArrRef src, const Base& b, double s, bool mulik) {
   Instr& I = add(OP_IRFFT);
   I.r0 = r0;
-  I.r1 = r1;
-  I.r2 = r2;
   I.n = b.n;
-  I.p0 = b.d_fft.p;
+  I.p0 = src.p;
+  I.p1 = b.d_fft.p;
+  I.ld = src.ld;
+  I.nlanes = src.cols;
+  I.s0 = s;
+  if (mulik) I.flags |= LF_MULIK;
+  bytes_unit_ += (double)b.m * 32.0;
   touch(r0, lay_natural(), b.n);
-  touch(r1, lay_natural(), b.m);
-  touch(r2, lay_natural(), b.m);
   fftlen_ = std::max(fftlen_, b.fft_len());
   if (!b.fft.plan.pow2) wbcap_ = std::max(wbcap_, b.fft.plan.Lb);
 }
@@ -346,6 +355,7 @@ Built ProgBuilder::build() {
   b.nblocks = (p.nunits + p.T - 1) / p.T;
   b.nthreads = nthr;
   b.smem = bestSmem;
+  b.bytes = bytes_unit_ * (double)p.nunits;
   b.valid = true;
   return b;
 }
