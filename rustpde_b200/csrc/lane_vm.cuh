@@ -31,15 +31,47 @@ RP_DEV int slot_of(const Lay& L, int i) {
   return (i & 1) ? L.o0 + L.so * h : L.e0 + L.se * h;
 }
 
+// Dynamic shared memory base.  Every shared-memory pointer below is derived
+// from this symbol inside the function that uses it, so the compiler emits
+// LDS/STS (not generic loads) and never has to assume aliasing with global
+// or local memory.
+#ifdef RP_EMU
+#define RP_SMEM ((cplx*)cuemu::dyn_smem())
+#else
+extern __shared__ __align__(16) unsigned char rp_dyn_smem_raw_[];
+#define RP_SMEM ((cplx*)rp_dyn_smem_raw_)
+#endif
+
+// Block context.  Built by value inside each (noinline) op from the program
+// header; it is never passed by reference across a call, so it stays in registers.
 struct Blk {
   cplx* regs;
   cplx* wb;
   cplx* scr;
+  int wb_off;  // offset of wb from RP_SMEM in cplx units
   int T, capP, wbP, wbT;
   int tid, nthr;
   int unit0, nunits, axis;
 };
-RP_DEV cplx* lane_ptr(const Blk& b, int r, int t) { return b.regs + (size_t)(r * b.T + t) * b.capP; }
+RP_DEV cplx* lane_ptr(const Blk& b, int r, int t) { return b.regs + (r * b.T + t) * b.capP; }
+RP_DEV Blk make_blk(const Program* __restrict__ pg) {
+  Blk b;
+  b.T = pg->T;
+  b.capP = padi(pg->cap) + 1;
+  const int wbcap = pg->wb_cap;
+  b.wbP = wbcap ? padi(wbcap) + 1 : 0;
+  b.wbT = pg->wb_T;
+  b.regs = RP_SMEM;
+  b.wb_off = pg->nreg * b.T * b.capP;
+  b.wb = RP_SMEM + b.wb_off;
+  b.scr = b.wb + b.wbT * b.wbP;
+  b.tid = threadIdx.x;
+  b.nthr = blockDim.x;
+  b.unit0 = blockIdx.x * b.T;
+  b.nunits = pg->nunits;
+  b.axis = pg->axis;
+  return b;
+}
 
 // ===========================================================================
 // Radix-R DFT in registers (forward, e^{-2 pi i / R}); in-order output.
@@ -114,20 +146,25 @@ struct Dft {
 
 // One Stockham radix-R pass, in place through registers.  Each thread owns K
 // butterflies of one FFT; `per` = (L/R)/K threads serve one FFT.
+// Arguments are scalars (offsets, not pointers): the buffers are addressed from
+// RP_SMEM so the accesses compile to LDS/STS.
+enum { FF_CONJ_IN = 1, FF_CONJ_OUT = 2, FF_LIN = 4 };
 template <int R, int K>
-RP_DEVNI void fft_pass(const Blk& b, cplx* base, int stride, int nslots, int L, int Ns, const cplx* __restrict__ tw,
-                       bool conj_in, bool conj_out, double oscale, const Lay* lin) {
+RP_DEVNI void fft_pass(int tid, int nthr, int base_off, int stride, int nslots, int L, int Ns,
+                       const cplx* __restrict__ tw, int fl, double oscale, Lay lin) {
   const int nb = L / R;
   const int per = nb / K;
-  const int fpr = b.nthr / per;  // FFTs per round
+  const int fpr = nthr / per;  // FFTs per round
   const int twstep = L / (Ns * R);
+  const bool conj_in = fl & FF_CONJ_IN, conj_out = fl & FF_CONJ_OUT, use_lin = fl & FF_LIN;
+  cplx* const base = RP_SMEM + base_off;
   for (int s0 = 0; s0 < nslots; s0 += fpr) {
-    const int t = s0 + b.tid / per;
-    const int q = b.tid % per;
-    const bool act = (t < nslots) && (b.tid < fpr * per);
+    const int t = s0 + tid / per;
+    const int q = tid % per;
+    const bool act = (t < nslots) && (tid < fpr * per);
     cplx v[K][R];
     if (act) {
-      const cplx* x = base + (size_t)t * stride;
+      const cplx* x = base + t * stride;
 #pragma unroll
       for (int kk = 0; kk < K; ++kk) {
         const int j = q + per * kk;
@@ -135,9 +172,9 @@ RP_DEVNI void fft_pass(const Blk& b, cplx* base, int stride, int nslots, int L, 
 #pragma unroll
         for (int r = 0; r < R; ++r) {
           const int src = j + r * nb;
-          cplx c = x[padi(lin ? slot_of(*lin, src) : src)];
+          cplx c = x[padi(use_lin ? slot_of(lin, src) : src)];
           if (conj_in) c.y = -c.y;
-          if (r > 0 && Ns > 1) c = cmul(c, __ldg(&tw[(size_t)r * k * twstep]));
+          if (r > 0 && Ns > 1) c = cmul(c, __ldg(&tw[r * k * twstep]));
           v[kk][r] = c;
         }
         Dft<R>::run(v[kk]);
@@ -145,7 +182,7 @@ RP_DEVNI void fft_pass(const Blk& b, cplx* base, int stride, int nslots, int L, 
     }
     __syncthreads();
     if (act) {
-      cplx* x = base + (size_t)t * stride;
+      cplx* x = base + t * stride;
 #pragma unroll
       for (int kk = 0; kk < K; ++kk) {
         const int j = q + per * kk;
@@ -166,91 +203,98 @@ RP_DEVNI void fft_pass(const Blk& b, cplx* base, int stride, int nslots, int L, 
 }
 
 template <int R>
-RP_DEV void fft_pass_k(const Blk& b, int K, cplx* base, int stride, int nslots, int L, int Ns, const cplx* tw, bool ci,
-                       bool co, double os, const Lay* lin) {
+RP_DEV void fft_pass_k(int tid, int nthr, int K, int base_off, int stride, int nslots, int L, int Ns, const cplx* tw,
+                       int fl, double os, Lay lin) {
   if (K == 1) {
-    fft_pass<R, 1>(b, base, stride, nslots, L, Ns, tw, ci, co, os, lin);
+    fft_pass<R, 1>(tid, nthr, base_off, stride, nslots, L, Ns, tw, fl, os, lin);
     return;
   }
   if constexpr (R <= 8) {
     if (K == 2) {
-      fft_pass<R, 2>(b, base, stride, nslots, L, Ns, tw, ci, co, os, lin);
+      fft_pass<R, 2>(tid, nthr, base_off, stride, nslots, L, Ns, tw, fl, os, lin);
       return;
     }
   }
   if constexpr (R <= 4) {
     if (K == 4) {
-      fft_pass<R, 4>(b, base, stride, nslots, L, Ns, tw, ci, co, os, lin);
+      fft_pass<R, 4>(tid, nthr, base_off, stride, nslots, L, Ns, tw, fl, os, lin);
       return;
     }
   }
   if constexpr (R <= 2) {
     if (K == 8) {
-      fft_pass<R, 8>(b, base, stride, nslots, L, Ns, tw, ci, co, os, lin);
+      fft_pass<R, 8>(tid, nthr, base_off, stride, nslots, L, Ns, tw, fl, os, lin);
       return;
     }
   }
 }
 
-// Complex FFT of pow2 length L on nslots buffers (base + t*stride), natural
-// order in and out.  inverse: conj-in / conj-out around the forward kernel.
-// Requires b.nthr >= L/16 (host planner guarantees it).
-RP_DEVNI void fft_run(const Blk& b, cplx* base, int stride, int nslots, int L, const cplx* tw, bool inverse, double scale,
-                      const Lay* lin0 = nullptr) {
+// Complex FFT of pow2 length L on nslots buffers (RP_SMEM + base_off + t*stride),
+// natural order in and out.  inverse: conj-in / conj-out around the forward kernel.
+// Requires nthr >= L/16 (host planner guarantees it).  use_lin: the first pass
+// reads element j from slot_of(lin, j) (absorbs an input permutation for free).
+RP_DEVNI void fft_run(int tid, int nthr, int base_off, int stride, int nslots, int L, const cplx* tw, bool inverse,
+                      double scale, Lay lin, bool use_lin) {
   int rem = L, Ns = 1;
   while (rem > 1) {
     const int R = rem >= 16 ? 16 : rem;
     const bool first = (Ns == 1), last = (rem == R);
-    int K = (L / R) / b.nthr;  // butterflies per thread; R*K = L/nthr <= 16 when K > 1
+    int K = (L / R) / nthr;  // butterflies per thread; R*K = L/nthr <= 16 when K > 1
     if (K < 1) K = 1;
-    const bool ci = inverse && first, co = inverse && last;
+    const int fl = ((inverse && first) ? FF_CONJ_IN : 0) | ((inverse && last) ? FF_CONJ_OUT : 0) |
+                   ((use_lin && first) ? FF_LIN : 0);
     const double os = last ? scale : 1.0;
-    const Lay* lin = first ? lin0 : nullptr;
     switch (R) {
-      case 16: fft_pass_k<16>(b, K, base, stride, nslots, L, Ns, tw, ci, co, os, lin); break;
-      case 8: fft_pass_k<8>(b, K, base, stride, nslots, L, Ns, tw, ci, co, os, lin); break;
-      case 4: fft_pass_k<4>(b, K, base, stride, nslots, L, Ns, tw, ci, co, os, lin); break;
-      default: fft_pass_k<2>(b, K, base, stride, nslots, L, Ns, tw, ci, co, os, lin); break;
+      case 16: fft_pass_k<16>(tid, nthr, K, base_off, stride, nslots, L, Ns, tw, fl, os, lin); break;
+      case 8: fft_pass_k<8>(tid, nthr, K, base_off, stride, nslots, L, Ns, tw, fl, os, lin); break;
+      case 4: fft_pass_k<4>(tid, nthr, K, base_off, stride, nslots, L, Ns, tw, fl, os, lin); break;
+      default: fft_pass_k<2>(tid, nthr, K, base_off, stride, nslots, L, Ns, tw, fl, os, lin); break;
     }
     Ns *= R;
     rem /= R;
   }
 }
+RP_DEV void fft_run(const Blk& b, int base_off, int stride, int nslots, int L, const cplx* tw, bool inverse, double scale) {
+  fft_run(b.tid, b.nthr, base_off, stride, nslots, L, tw, inverse, scale, lay_natural(), false);
+}
 
 // Complex DFT of arbitrary length on lane slots [0, L) of register buffers
 // (natural order), in place.  pow2 -> fft_run; else Bluestein through b.wb.
-RP_DEVNI void dft_any(const Blk& b, cplx* base, int stride, int nslots, const FftPlan& P, bool inverse, double scale) {
+RP_DEV void dft_any(const Blk& b, int base_off, int stride, int nslots, const FftPlan& P, bool inverse, double scale) {
   if (P.pow2) {
-    fft_run(b, base, stride, nslots, P.L, P.tw, inverse, scale);
+    fft_run(b, base_off, stride, nslots, P.L, P.tw, inverse, scale);
     return;
   }
   const int L = P.L, Lb = P.Lb;
+  cplx* const base = RP_SMEM + base_off;
+  const cplx* __restrict__ chirp = P.chirp;
+  const cplx* __restrict__ bhat = P.bhat;
   for (int g = 0; g < nslots; g += b.wbT) {
     const int ns = min(b.wbT, nslots - g);
     for (int idx = b.tid; idx < ns * Lb; idx += b.nthr) {
       const int t = idx / Lb, j = idx % Lb;
       cplx v = mk(0.0, 0.0);
       if (j < L) {
-        v = base[(size_t)(g + t) * stride + padi(j)];
+        v = base[(g + t) * stride + padi(j)];
         if (inverse) v.y = -v.y;
-        v = cmul(v, __ldg(&P.chirp[j]));
+        v = cmul(v, __ldg(&chirp[j]));
       }
-      b.wb[(size_t)t * b.wbP + padi(j)] = v;
+      b.wb[t * b.wbP + padi(j)] = v;
     }
     __syncthreads();
-    fft_run(b, b.wb, b.wbP, ns, Lb, P.tw, false, 1.0);
+    fft_run(b, b.wb_off, b.wbP, ns, Lb, P.tw, false, 1.0);
     for (int idx = b.tid; idx < ns * Lb; idx += b.nthr) {
       const int t = idx / Lb, j = idx % Lb;
-      cplx* w = &b.wb[(size_t)t * b.wbP + padi(j)];
-      *w = cmul(*w, __ldg(&P.bhat[j]));
+      cplx* w = &b.wb[t * b.wbP + padi(j)];
+      *w = cmul(*w, __ldg(&bhat[j]));
     }
     __syncthreads();
-    fft_run(b, b.wb, b.wbP, ns, Lb, P.tw, true, 1.0);
+    fft_run(b, b.wb_off, b.wbP, ns, Lb, P.tw, true, 1.0);
     for (int idx = b.tid; idx < ns * L; idx += b.nthr) {
       const int t = idx / L, j = idx % L;
-      cplx v = cmul(b.wb[(size_t)t * b.wbP + padi(j)], __ldg(&P.chirp[j]));
+      cplx v = cmul(b.wb[t * b.wbP + padi(j)], __ldg(&chirp[j]));
       if (inverse) v.y = -v.y;
-      base[(size_t)(g + t) * stride + padi(j)] = cscale(v, scale);
+      base[(g + t) * stride + padi(j)] = cscale(v, scale);
     }
     __syncthreads();
   }
@@ -452,7 +496,9 @@ RP_DEV LaneSel lane_sel(const Blk& b, const Instr& I, int t) {
   return s;
 }
 
-RP_DEVNI void op_ld(const Blk& b, const Instr& I) {
+RP_DEVNI void op_ld(const Program* __restrict__ pg, int pc) {
+  const Blk b = make_blk(pg);
+  const Instr I = pg->ins[pc];
   const int n = I.n, nz = (I.n2 > n && !(I.flags & LF_ACC)) ? I.n2 : n;
   const int total = b.T * nz;
   const double* lc = (const double*)I.p1;
@@ -511,7 +557,9 @@ RP_DEVNI void op_ld(const Blk& b, const Instr& I) {
   __syncthreads();
 }
 
-RP_DEVNI void op_st(const Blk& b, const Instr& I) {
+RP_DEVNI void op_st(const Program* __restrict__ pg, int pc) {
+  const Blk b = make_blk(pg);
+  const Instr I = pg->ins[pc];
   const int n = I.n;
   const int total = b.T * n;
   for (int idx = b.tid; idx < total; idx += b.nthr) {
@@ -556,7 +604,9 @@ RP_DEVNI void op_st(const Blk& b, const Instr& I) {
 }
 
 // elementwise two/three-register ops; mode: 0 copy, 1 axpy, 2 scale, 3 mulpw, 4 mulpw-acc, 5 zero, 6 cut
-RP_DEVNI void op_elem(const Blk& b, const Instr& I, int mode) {
+RP_DEVNI void op_elem(const Program* __restrict__ pg, int pc, int mode) {
+  const Blk b = make_blk(pg);
+  const Instr I = pg->ins[pc];
   const int n = I.n;
   for (int idx = b.tid; idx < b.T * n; idx += b.nthr) {
     const int t = idx / n, i = idx % n;
@@ -583,7 +633,9 @@ RP_DEVNI void op_elem(const Blk& b, const Instr& I, int mode) {
   __syncthreads();
 }
 
-RP_DEVNI void op_mulik(const Blk& b, const Instr& I) {
+RP_DEVNI void op_mulik(const Program* __restrict__ pg, int pc) {
+  const Blk b = make_blk(pg);
+  const Instr I = pg->ins[pc];
   const int n = I.n;
   for (int idx = b.tid; idx < b.T * n; idx += b.nthr) {
     const int t = idx / n, i = idx % n;
@@ -595,7 +647,9 @@ RP_DEVNI void op_mulik(const Blk& b, const Instr& I) {
   __syncthreads();
 }
 
-RP_DEVNI void op_setzero00(const Blk& b, const Instr& I) {
+RP_DEVNI void op_setzero00(const Program* __restrict__ pg, int pc) {
+  const Blk b = make_blk(pg);
+  const Instr I = pg->ins[pc];
   if (b.unit0 == 0 && b.tid == 0) {
     cplx* x0 = lane_ptr(b, I.r0, 0) + padi(slot_of(I.lay, 0));
     if (I.flags & LF_COMPLEX)
@@ -608,7 +662,9 @@ RP_DEVNI void op_setzero00(const Blk& b, const Instr& I) {
 
 // ---- Galerkin stencils ------------------------------------------------------
 // to_ortho (composite_stencil.rs:207-229): p_i = d_i c_i + l_{i-2} c_{i-2}
-RP_DEVNI void op_toortho(const Blk& b, const Instr& I) {
+RP_DEVNI void op_toortho(const Program* __restrict__ pg, int pc) {
+  const Blk b = make_blk(pg);
+  const Instr I = pg->ins[pc];
   const int n = I.n, m = n - 2;
   const double* d = (const double*)I.p0;
   const double* l = (const double*)I.p1;
@@ -620,7 +676,9 @@ RP_DEVNI void op_toortho(const Blk& b, const Instr& I) {
 }
 
 // from_ortho (composite_stencil.rs:250-276): c = S^T p, then (S^T S) solve.
-RP_DEVNI void op_fromortho(const Blk& b, const Instr& I) {
+RP_DEVNI void op_fromortho(const Program* __restrict__ pg, int pc) {
+  const Blk b = make_blk(pg);
+  const Instr I = pg->ins[pc];
   const int n = I.n, m = n - 2;
   const double* d = (const double*)I.p0;
   const double* l = (const double*)I.p1;
@@ -652,7 +710,9 @@ RP_DEVNI void op_fromortho(const Blk& b, const Instr& I) {
 }
 
 // B2 preconditioner (matvec.rs:172-193): out_r = lo_r x_r + di_r x_{r+2} + up_r x_{r+4}
-RP_DEVNI void op_bandmv(const Blk& b, const Instr& I) {
+RP_DEVNI void op_bandmv(const Program* __restrict__ pg, int pc) {
+  const Blk b = make_blk(pg);
+  const Instr I = pg->ins[pc];
   const int n = I.n, m = n - 2;
   const double* lo = (const double*)I.p0;
   const double* di = (const double*)I.p1;
@@ -668,7 +728,9 @@ RP_DEVNI void op_bandmv(const Blk& b, const Instr& I) {
 //   b_k = sum_{p>k, p-k odd} 2 p a_p  (k>=1),  b_0 = half of that.
 // Run in place on the chain of p; b_{p-1} ends up in the slot of a_p, so the
 // layout becomes lay_after_diff(lay).
-RP_DEVNI void op_diff(const Blk& b, const Instr& I) {
+RP_DEVNI void op_diff(const Program* __restrict__ pg, int pc) {
+  const Blk b = make_blk(pg);
+  const Instr I = pg->ins[pc];
   Lay L = I.lay;
   const int n = I.n;
   for (int rep = 0; rep < I.i0; ++rep) {
@@ -695,7 +757,9 @@ RP_DEVNI void op_diff(const Blk& b, const Instr& I) {
 }
 
 // Pre-swept banded solve (fdma.rs:101-118)
-RP_DEVNI void op_fdma(const Blk& b, const Instr& I) {
+RP_DEVNI void op_fdma(const Program* __restrict__ pg, int pc) {
+  const Blk b = make_blk(pg);
+  const Instr I = pg->ins[pc];
   const FdmaTab ft = *(const FdmaTab*)I.p0;
   const Chains ch = chains_of(I.lay, I.n);
   chain_solve(b, I.r0, ch, true, [=](int, int c, int mm) -> Coef {
@@ -721,7 +785,9 @@ RP_DEVNI void op_fdma(const Blk& b, const Instr& I) {
 // Per-lane banded solve (A + (lam+alpha) C) x = b  (fdma_tensor.rs:219-227).
 // Register r1 holds the lane of swept-pivot reciprocals 1/dia'_i (set-up data),
 // everything else of the sweep is recomputed from the raw diagonals.
-RP_DEVNI void op_fdmamode(const Blk& b, const Instr& I) {
+RP_DEVNI void op_fdmamode(const Program* __restrict__ pg, int pc) {
+  const Blk b = make_blk(pg);
+  const Instr I = pg->ins[pc];
   const FdmaModeTab mt = *(const FdmaModeTab*)I.p0;
   const int n = I.n;
   const Chains ch = chains_of(I.lay, n);
@@ -788,7 +854,9 @@ RP_DEVNI void op_fdmamode(const Blk& b, const Instr& I) {
 // one complex DFT of length N, recombine; odd outputs by a prefix sum.
 // Output layout: SPLIT(N).
 // ===========================================================================
-RP_DEVNI void op_dct(const Blk& b, const Instr& I) {
+RP_DEVNI void op_dct(const Program* __restrict__ pg, int pc) {
+  const Blk b = make_blk(pg);
+  const Instr I = pg->ins[pc];
   const DctPlan P = *(const DctPlan*)I.p0;
   const int n = P.n, N = n - 1;
   const bool backward = I.i0 != 0;
@@ -840,7 +908,7 @@ RP_DEVNI void op_dct(const Blk& b, const Instr& I) {
     __syncthreads();
     // ---- complex DFT of length N ----------------------------------------
     if (P.fft.pow2) {
-      fft_run(b, lane_ptr(b, I.r0, g), b.capP, ns, N, P.fft.tw, false, 1.0, &lin);
+      fft_run(b.tid, b.nthr, (I.r0 * b.T + g) * b.capP, b.capP, ns, N, P.fft.tw, false, 1.0, lin, true);
     } else {
       const int Lb = P.fft.Lb;
       for (int idx = b.tid; idx < ns * (Lb - N); idx += b.nthr) {
@@ -848,14 +916,14 @@ RP_DEVNI void op_dct(const Blk& b, const Instr& I) {
         b.wb[(size_t)t * b.wbP + padi(j)] = mk(0, 0);
       }
       __syncthreads();
-      fft_run(b, b.wb, b.wbP, ns, Lb, P.fft.tw, false, 1.0);
+      fft_run(b, b.wb_off, b.wbP, ns, Lb, P.fft.tw, false, 1.0);
       for (int idx = b.tid; idx < ns * Lb; idx += b.nthr) {
         const int t = idx / Lb, j = idx % Lb;
         cplx* w = &b.wb[(size_t)t * b.wbP + padi(j)];
         *w = cmul(*w, __ldg(&P.fft.bhat[j]));
       }
       __syncthreads();
-      fft_run(b, b.wb, b.wbP, ns, Lb, P.fft.tw, true, 1.0);
+      fft_run(b, b.wb_off, b.wbP, ns, Lb, P.fft.tw, true, 1.0);
       for (int idx = b.tid; idx < ns * N; idx += b.nthr) {
         const int t = idx / N, j = idx % N;
         lane_ptr(b, I.r0, g + t)[padi(j)] = cmul(b.wb[(size_t)t * b.wbP + padi(j)], __ldg(&P.fft.chirp[j]));
@@ -918,10 +986,12 @@ RP_DEVNI void op_dct(const Blk& b, const Instr& I) {
 //   IRFFT: complex columns 2P, 2P+1 (optionally times i k s0) -> packed spectrum
 //          -> inverse FFT -> r0.  Im of the DC and Nyquist bins is ignored (c2r).
 // ===========================================================================
-RP_DEVNI void op_rfft(const Blk& b, const Instr& I) {
+RP_DEVNI void op_rfft(const Program* __restrict__ pg, int pc) {
+  const Blk b = make_blk(pg);
+  const Instr I = pg->ins[pc];
   const FftPlan P = *(const FftPlan*)I.p1;
   const int n = P.L, m = n / 2 + 1;
-  dft_any(b, lane_ptr(b, I.r0, 0), b.capP, b.T, P, false, 1.0);
+  dft_any(b, I.r0 * b.T * b.capP, b.capP, b.T, P, false, 1.0);
   cplx* dst = (cplx*)I.p0;
   for (int idx = b.tid; idx < b.T * m; idx += b.nthr) {
     const int k = idx / b.T, t = idx % b.T;
@@ -938,7 +1008,9 @@ RP_DEVNI void op_rfft(const Blk& b, const Instr& I) {
   __syncthreads();
 }
 
-RP_DEVNI void op_irfft(const Blk& b, const Instr& I) {
+RP_DEVNI void op_irfft(const Program* __restrict__ pg, int pc) {
+  const Blk b = make_blk(pg);
+  const Instr I = pg->ins[pc];
   const FftPlan P = *(const FftPlan*)I.p1;
   const int n = P.L, m = n / 2 + 1;
   const cplx* src = (const cplx*)I.p0;
@@ -964,51 +1036,38 @@ RP_DEVNI void op_irfft(const Blk& b, const Instr& I) {
     if (k > 0 && 2 * k != n) z[padi(n - k)] = mk(xa.x + xb.y, -xa.y + xb.x);  // conj(X_a) + i conj(X_b)
   }
   __syncthreads();
-  dft_any(b, lane_ptr(b, I.r0, 0), b.capP, b.T, P, true, 1.0 / (double)n);
+  dft_any(b, I.r0 * b.T * b.capP, b.capP, b.T, P, true, 1.0 / (double)n);
 }
 
 // ===========================================================================
 // The interpreter
 // ===========================================================================
 RP_DEV void lane_vm_body(const Program* __restrict__ progs) {
-  const Program& pg = progs[blockIdx.y];
-  RP_DYN_SMEM(cplx, smem);
-  Blk b;
-  b.T = pg.T;
-  b.capP = padi(pg.cap) + 1;
-  b.wbP = pg.wb_cap ? padi(pg.wb_cap) + 1 : 0;
-  b.wbT = pg.wb_T;
-  b.regs = smem;
-  b.wb = smem + (size_t)pg.nreg * pg.T * b.capP;
-  b.scr = b.wb + (size_t)b.wbT * b.wbP;
-  b.tid = threadIdx.x;
-  b.nthr = blockDim.x;
-  b.unit0 = blockIdx.x * pg.T;
-  b.nunits = pg.nunits;
-  b.axis = pg.axis;
-  if (b.unit0 >= pg.nunits) return;
-  for (int pc = 0; pc < pg.ninstr; ++pc) {
-    const Instr I = pg.ins[pc];
-    switch (I.op) {
-      case OP_LD: op_ld(b, I); break;
-      case OP_ST: op_st(b, I); break;
-      case OP_ZERO: op_elem(b, I, 5); break;
-      case OP_COPY: op_elem(b, I, 0); break;
-      case OP_AXPY: op_elem(b, I, 1); break;
-      case OP_SCALE: op_elem(b, I, 2); break;
-      case OP_MULPW: op_elem(b, I, (I.flags & LF_ACC) ? 4 : 3); break;
-      case OP_CUT: op_elem(b, I, 6); break;
-      case OP_MULIK: op_mulik(b, I); break;
-      case OP_TOORTHO: op_toortho(b, I); break;
-      case OP_FROMORTHO: op_fromortho(b, I); break;
-      case OP_DIFF: op_diff(b, I); break;
-      case OP_DCT: op_dct(b, I); break;
-      case OP_RFFT: op_rfft(b, I); break;
-      case OP_IRFFT: op_irfft(b, I); break;
-      case OP_BANDMV: op_bandmv(b, I); break;
-      case OP_FDMA: op_fdma(b, I); break;
-      case OP_FDMAMODE: op_fdmamode(b, I); break;
-      case OP_SETZERO00: op_setzero00(b, I); break;
+  const Program* __restrict__ pg = progs + blockIdx.y;
+  if ((int)(blockIdx.x * pg->T) >= pg->nunits) return;
+  const int ninstr = pg->ninstr;
+  for (int pc = 0; pc < ninstr; ++pc) {
+    const int op = pg->ins[pc].op;
+    switch (op) {
+      case OP_LD: op_ld(pg, pc); break;
+      case OP_ST: op_st(pg, pc); break;
+      case OP_ZERO: op_elem(pg, pc, 5); break;
+      case OP_COPY: op_elem(pg, pc, 0); break;
+      case OP_AXPY: op_elem(pg, pc, 1); break;
+      case OP_SCALE: op_elem(pg, pc, 2); break;
+      case OP_MULPW: op_elem(pg, pc, (pg->ins[pc].flags & LF_ACC) ? 4 : 3); break;
+      case OP_CUT: op_elem(pg, pc, 6); break;
+      case OP_MULIK: op_mulik(pg, pc); break;
+      case OP_TOORTHO: op_toortho(pg, pc); break;
+      case OP_FROMORTHO: op_fromortho(pg, pc); break;
+      case OP_DIFF: op_diff(pg, pc); break;
+      case OP_DCT: op_dct(pg, pc); break;
+      case OP_RFFT: op_rfft(pg, pc); break;
+      case OP_IRFFT: op_irfft(pg, pc); break;
+      case OP_BANDMV: op_bandmv(pg, pc); break;
+      case OP_FDMA: op_fdma(pg, pc); break;
+      case OP_FDMAMODE: op_fdmamode(pg, pc); break;
+      case OP_SETZERO00: op_setzero00(pg, pc); break;
       default: break;
     }
   }
