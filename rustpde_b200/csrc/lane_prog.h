@@ -95,6 +95,7 @@ struct Program {
   int nunits; // number of slot units to process (pairs of real lanes / complex lanes)
   int nthreads;
   int smem_bytes;
+  long long* prof;  // development aid: per-opcode cycle counters of block 0 (NULL = off)
   Instr ins[RP_MAX_INSTR];
 };
 

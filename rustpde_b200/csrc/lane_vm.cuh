@@ -4,8 +4,17 @@
 // short program of block-parallel stages over them: strided/contiguous loads
 // and stores, Galerkin stencils, Chebyshev derivative, DCT-I / real FFT,
 // banded matvec and banded solves.  All sequential recurrences of the
-// reference (ortho.rs:107-125, linalg.rs:14-57, fdma.rs:101-118) are run as
-// chunked two-pass recurrences so that the whole block works on them.
+// reference (ortho.rs:107-125, linalg.rs:14-57, fdma.rs:101-118) run as
+// block-wide scans: every thread walks a short chunk, the chunk summaries are
+// combined with warp shuffles, and the chunk is re-walked with its carry.
+//
+// Performance rules followed throughout (B200: FP64 and HBM are roughly
+// balanced for these transforms, so latency hiding is what matters):
+//   * shared-memory pointers are derived from the smem symbol in the function
+//     that uses them (LDS/STS, no generic or local traffic);
+//   * loops are written in explicit batches (load B values, then compute,
+//     then store) so several independent memory operations are in flight;
+//   * no integer division in inner loops (all strides are powers of two).
 #pragma once
 #include "lane_prog.h"
 
@@ -19,6 +28,7 @@ RP_DEV cplx mk(double x, double y) { return make_double2(x, y); }
 RP_DEV cplx cadd(cplx a, cplx b) { return mk(a.x + b.x, a.y + b.y); }
 RP_DEV cplx csub(cplx a, cplx b) { return mk(a.x - b.x, a.y - b.y); }
 RP_DEV cplx cmul(cplx a, cplx b) { return mk(fma(a.x, b.x, -a.y * b.y), fma(a.x, b.y, a.y * b.x)); }
+RP_DEV cplx csqr(cplx a) { return mk(fma(a.x, a.x, -a.y * a.y), 2.0 * a.x * a.y); }
 RP_DEV cplx cscale(cplx a, double s) { return mk(a.x * s, a.y * s); }
 RP_DEV cplx cconj(cplx a) { return mk(a.x, -a.y); }
 // componentwise (the two packed real lanes are independent)
@@ -30,11 +40,9 @@ RP_DEV int slot_of(const Lay& L, int i) {
   int h = i >> 1;
   return (i & 1) ? L.o0 + L.so * h : L.e0 + L.se * h;
 }
+RP_DEV int ilog2(int v) { return 31 - __clz(v); }
 
-// Dynamic shared memory base.  Every shared-memory pointer below is derived
-// from this symbol inside the function that uses it, so the compiler emits
-// LDS/STS (not generic loads) and never has to assume aliasing with global
-// or local memory.
+// Dynamic shared memory base (see header comment).
 #ifdef RP_EMU
 #define RP_SMEM ((cplx*)cuemu::dyn_smem())
 #else
@@ -43,13 +51,13 @@ extern __shared__ __align__(16) unsigned char rp_dyn_smem_raw_[];
 #endif
 
 // Block context.  Built by value inside each (noinline) op from the program
-// header; it is never passed by reference across a call, so it stays in registers.
+// header; never passed by reference across a call, so it stays in registers.
 struct Blk {
   cplx* regs;
   cplx* wb;
   cplx* scr;
   int wb_off;  // offset of wb from RP_SMEM in cplx units
-  int T, capP, wbP, wbT;
+  int T, logT, capP, wbP, wbT;
   int tid, nthr;
   int unit0, nunits, axis;
 };
@@ -57,6 +65,7 @@ RP_DEV cplx* lane_ptr(const Blk& b, int r, int t) { return b.regs + (r * b.T + t
 RP_DEV Blk make_blk(const Program* __restrict__ pg) {
   Blk b;
   b.T = pg->T;
+  b.logT = ilog2(b.T);
   b.capP = padi(pg->cap) + 1;
   const int wbcap = pg->wb_cap;
   b.wbP = wbcap ? padi(wbcap) + 1 : 0;
@@ -144,39 +153,76 @@ struct Dft {
   }
 };
 
+// v[r] *= w^r, r = 1..R-1, from the single table value w (log-depth products,
+// error ~ 4 ulp), applied as soon as each power is known to bound live registers.
+template <int R>
+RP_DEV void apply_twiddles(cplx* v, cplx w1) {
+  v[1] = cmul(v[1], w1);
+  if constexpr (R > 2) {
+    const cplx w2 = csqr(w1);
+    v[2] = cmul(v[2], w2);
+    const cplx w3 = cmul(w2, w1);
+    v[3] = cmul(v[3], w3);
+    if constexpr (R > 4) {
+      const cplx w4 = csqr(w2);
+      v[4] = cmul(v[4], w4);
+      const cplx w5 = cmul(w4, w1);
+      v[5] = cmul(v[5], w5);
+      const cplx w6 = cmul(w4, w2);
+      v[6] = cmul(v[6], w6);
+      const cplx w7 = cmul(w4, w3);
+      v[7] = cmul(v[7], w7);
+      if constexpr (R > 8) {
+        const cplx w8 = csqr(w4);
+        v[8] = cmul(v[8], w8);
+        v[9] = cmul(v[9], cmul(w8, w1));
+        v[10] = cmul(v[10], cmul(w8, w2));
+        v[11] = cmul(v[11], cmul(w8, w3));
+        v[12] = cmul(v[12], cmul(w8, w4));
+        v[13] = cmul(v[13], cmul(w8, w5));
+        v[14] = cmul(v[14], cmul(w8, w6));
+        v[15] = cmul(v[15], cmul(w8, w7));
+      }
+    }
+  }
+}
+
 // One Stockham radix-R pass, in place through registers.  Each thread owns K
-// butterflies of one FFT; `per` = (L/R)/K threads serve one FFT.
-// Arguments are scalars (offsets, not pointers): the buffers are addressed from
-// RP_SMEM so the accesses compile to LDS/STS.
+// butterflies of one FFT; `per` = (L/R)/K threads serve one FFT.  Arguments
+// are scalars (offsets, not pointers).  All of L, R, K, Ns, nthr are powers of 2.
 enum { FF_CONJ_IN = 1, FF_CONJ_OUT = 2, FF_LIN = 4 };
 template <int R, int K>
 RP_DEVNI void fft_pass(int tid, int nthr, int base_off, int stride, int nslots, int L, int Ns,
                        const cplx* __restrict__ tw, int fl, double oscale, Lay lin) {
   const int nb = L / R;
-  const int per = nb / K;
-  const int fpr = nthr / per;  // FFTs per round
+  const int per = nb / K, lper = ilog2(per);
+  const int fpr = nthr >> lper;  // FFTs per round
   const int twstep = L / (Ns * R);
   const bool conj_in = fl & FF_CONJ_IN, conj_out = fl & FF_CONJ_OUT, use_lin = fl & FF_LIN;
   cplx* const base = RP_SMEM + base_off;
+  const int q = tid & (per - 1), tq = tid >> lper;
   for (int s0 = 0; s0 < nslots; s0 += fpr) {
-    const int t = s0 + tid / per;
-    const int q = tid % per;
-    const bool act = (t < nslots) && (tid < fpr * per);
+    const int t = s0 + tq;
+    const bool act = (t < nslots);
     cplx v[K][R];
     if (act) {
       const cplx* x = base + t * stride;
+      cplx w1[K];
 #pragma unroll
       for (int kk = 0; kk < K; ++kk) {
         const int j = q + per * kk;
-        const int k = j % Ns;
+        w1[kk] = (Ns > 1) ? __ldg(&tw[(j & (Ns - 1)) * twstep]) : mk(1.0, 0.0);
 #pragma unroll
         for (int r = 0; r < R; ++r) {
           const int src = j + r * nb;
           cplx c = x[padi(use_lin ? slot_of(lin, src) : src)];
           if (conj_in) c.y = -c.y;
-          if (r > 0 && Ns > 1) c = cmul(c, __ldg(&tw[r * k * twstep]));
           v[kk][r] = c;
         }
+      }
+#pragma unroll
+      for (int kk = 0; kk < K; ++kk) {
+        if (Ns > 1) apply_twiddles<R>(v[kk], w1[kk]);
         Dft<R>::run(v[kk]);
       }
     }
@@ -186,7 +232,7 @@ RP_DEVNI void fft_pass(int tid, int nthr, int base_off, int stride, int nslots, 
 #pragma unroll
       for (int kk = 0; kk < K; ++kk) {
         const int j = q + per * kk;
-        const int k = j % Ns;
+        const int k = j & (Ns - 1);
         const int o = (j - k) * R + k;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
@@ -258,6 +304,24 @@ RP_DEV void fft_run(const Blk& b, int base_off, int stride, int nslots, int L, c
   fft_run(b.tid, b.nthr, base_off, stride, nslots, L, tw, inverse, scale, lay_natural(), false);
 }
 
+// Batched grid-stride loop over i = tid, tid+nthr, ... < n: `ldf(u, i)` for a
+// batch of B indices first (independent loads in flight), then `stf(u, i)`.
+template <int B, class LF, class SF>
+RP_DEV void batched(int tid, int nthr, int n, LF ldf, SF stf) {
+  for (int i0 = tid; i0 < n; i0 += B * nthr) {
+#pragma unroll
+    for (int u = 0; u < B; ++u) {
+      const int i = i0 + u * nthr;
+      if (i < n) ldf(u, i);
+    }
+#pragma unroll
+    for (int u = 0; u < B; ++u) {
+      const int i = i0 + u * nthr;
+      if (i < n) stf(u, i);
+    }
+  }
+}
+
 // Complex DFT of arbitrary length on lane slots [0, L) of register buffers
 // (natural order), in place.  pow2 -> fft_run; else Bluestein through b.wb.
 RP_DEV void dft_any(const Blk& b, int base_off, int stride, int nslots, const FftPlan& P, bool inverse, double scale) {
@@ -271,117 +335,243 @@ RP_DEV void dft_any(const Blk& b, int base_off, int stride, int nslots, const Ff
   const cplx* __restrict__ bhat = P.bhat;
   for (int g = 0; g < nslots; g += b.wbT) {
     const int ns = min(b.wbT, nslots - g);
-    for (int idx = b.tid; idx < ns * Lb; idx += b.nthr) {
-      const int t = idx / Lb, j = idx % Lb;
-      cplx v = mk(0.0, 0.0);
-      if (j < L) {
-        v = base[(g + t) * stride + padi(j)];
-        if (inverse) v.y = -v.y;
-        v = cmul(v, __ldg(&chirp[j]));
-      }
-      b.wb[t * b.wbP + padi(j)] = v;
+    for (int t = 0; t < ns; ++t) {
+      const cplx* x = base + (g + t) * stride;
+      cplx* w = b.wb + t * b.wbP;
+      cplx v[4];
+      batched<4>(
+          b.tid, b.nthr, Lb,
+          [&](int u, int j) {
+            v[u] = mk(0.0, 0.0);
+            if (j < L) {
+              cplx a = x[padi(j)];
+              if (inverse) a.y = -a.y;
+              v[u] = cmul(a, __ldg(&chirp[j]));
+            }
+          },
+          [&](int u, int j) { w[padi(j)] = v[u]; });
     }
     __syncthreads();
     fft_run(b, b.wb_off, b.wbP, ns, Lb, P.tw, false, 1.0);
-    for (int idx = b.tid; idx < ns * Lb; idx += b.nthr) {
-      const int t = idx / Lb, j = idx % Lb;
-      cplx* w = &b.wb[t * b.wbP + padi(j)];
-      *w = cmul(*w, __ldg(&bhat[j]));
+    for (int t = 0; t < ns; ++t) {
+      cplx* w = b.wb + t * b.wbP;
+      cplx v[4];
+      batched<4>(
+          b.tid, b.nthr, Lb, [&](int u, int j) { v[u] = cmul(w[padi(j)], __ldg(&bhat[j])); },
+          [&](int u, int j) { w[padi(j)] = v[u]; });
     }
     __syncthreads();
     fft_run(b, b.wb_off, b.wbP, ns, Lb, P.tw, true, 1.0);
-    for (int idx = b.tid; idx < ns * L; idx += b.nthr) {
-      const int t = idx / L, j = idx % L;
-      cplx v = cmul(b.wb[t * b.wbP + padi(j)], __ldg(&chirp[j]));
-      if (inverse) v.y = -v.y;
-      base[(g + t) * stride + padi(j)] = cscale(v, scale);
+    for (int t = 0; t < ns; ++t) {
+      cplx* x = base + (g + t) * stride;
+      const cplx* w = b.wb + t * b.wbP;
+      cplx v[4];
+      batched<4>(
+          b.tid, b.nthr, L,
+          [&](int u, int j) {
+            cplx a = cmul(w[padi(j)], __ldg(&chirp[j]));
+            if (inverse) a.y = -a.y;
+            v[u] = cscale(a, scale);
+          },
+          [&](int u, int j) { x[padi(j)] = v[u]; });
     }
     __syncthreads();
   }
 }
 
 // ===========================================================================
-// Chunked two-pass linear recurrences along parity chains.
-//   y_k = s*q_k + p*y_{k-1} + r*y_{k-2}      (k in dependency order)
+// Linear recurrences along parity chains as block-wide scans.
+//   y_k = s*q_k + p*y_{k-1} [+ r*y_{k-2}]      (k in dependency order)
 // Chain c of slot t: element k at slot c0[c] + cs[c]*m, m = fwd ? k : M-1-k.
 // F(t, c, m) -> coefficients (componentwise double2).
+// tpc = nthr / (T*nch) threads serve one chain (a multiple of 32); each walks
+// a chunk of ceil(M/tpc) elements, the chunk maps  y -> A y + b  are combined
+// by an inclusive warp scan (shuffles) and a short cross-warp fix-up through
+// shared memory, and the chunk is re-walked with its carry-in.
 // ===========================================================================
 struct Coef {
   cplx s, p, r;
 };
 struct Chains {
-  int nch;       // chains per slot (1 or 2)
+  int nch;  // chains per slot (1 or 2)
   int c0[2], cs[2], M[2];
 };
-enum { RP_CHUNK = RP_CHUNK_HOST };
+struct Aff {  // [y1; y2] -> A [y1; y2] + b, all entries componentwise
+  cplx a11, a12, a21, a22, b1, b2;
+};
+template <bool SECOND>
+RP_DEV Aff aff_combine(const Aff& p, const Aff& c) {  // apply p first, then c
+  Aff r;
+  if (SECOND) {
+    r.a11 = pfma(c.a11, p.a11, pmul(c.a12, p.a21));
+    r.a12 = pfma(c.a11, p.a12, pmul(c.a12, p.a22));
+    r.a21 = pfma(c.a21, p.a11, pmul(c.a22, p.a21));
+    r.a22 = pfma(c.a21, p.a12, pmul(c.a22, p.a22));
+    r.b1 = pfma(c.a11, p.b1, pfma(c.a12, p.b2, c.b1));
+    r.b2 = pfma(c.a21, p.b1, pfma(c.a22, p.b2, c.b2));
+  } else {
+    r.a11 = pmul(c.a11, p.a11);
+    r.b1 = pfma(c.a11, p.b1, c.b1);
+    r.a12 = r.a21 = r.a22 = r.b2 = mk(0, 0);
+  }
+  return r;
+}
+RP_DEV cplx shfl_up_c(cplx v, int d) {
+  return mk(__shfl_up_sync(0xffffffffu, v.x, d), __shfl_up_sync(0xffffffffu, v.y, d));
+}
+template <bool SECOND>
+RP_DEV Aff aff_shfl_up(const Aff& a, int d) {
+  Aff r;
+  r.a11 = shfl_up_c(a.a11, d);
+  r.b1 = shfl_up_c(a.b1, d);
+  if (SECOND) {
+    r.a12 = shfl_up_c(a.a12, d);
+    r.a21 = shfl_up_c(a.a21, d);
+    r.a22 = shfl_up_c(a.a22, d);
+    r.b2 = shfl_up_c(a.b2, d);
+  } else {
+    r.a12 = r.a21 = r.a22 = r.b2 = mk(0, 0);
+  }
+  return r;
+}
 
-template <class F>
+template <bool SECOND, class F>
 RP_DEV void chain_solve(const Blk& b, int reg, const Chains& ch, bool fwd, F coef) {
+  const int nchains = b.T * ch.nch;
+  const int ltpc = ilog2(b.nthr) - ilog2(nchains);  // threads per chain (pow2, >= 32)
+  const int tpc = 1 << ltpc;
+  const int cid = b.tid >> ltpc, j = b.tid & (tpc - 1);
+  const int t = (ch.nch == 2) ? (cid >> 1) : cid, c = (ch.nch == 2) ? (cid & 1) : 0;
   int Mmax = ch.M[0];
   if (ch.nch > 1 && ch.M[1] > Mmax) Mmax = ch.M[1];
-  const int nck = (Mmax + RP_CHUNK - 1) / RP_CHUNK;
-  const int nitems = b.T * ch.nch * nck;
-  // pass 1: zero-carry chunk summaries + homogeneous responses
-  for (int it = b.tid; it < nitems; it += b.nthr) {
-    const int ck = it % nck, c = (it / nck) % ch.nch, t = it / (nck * ch.nch);
-    const int M = ch.M[c];
-    const cplx* x = lane_ptr(b, reg, t);
-    cplx y1 = mk(0, 0), y2 = mk(0, 0), u1 = mk(1, 1), u2 = mk(0, 0), v1 = mk(0, 0), v2 = mk(1, 1);
-    const int k0 = ck * RP_CHUNK, k1 = min(M, k0 + RP_CHUNK);
-    for (int k = k0; k < k1; ++k) {
-      const int m = fwd ? k : M - 1 - k;
-      const Coef cf = coef(t, c, m);
-      const cplx q = x[padi(ch.c0[c] + ch.cs[c] * m)];
-      cplx y = pfma(cf.p, y1, pfma(cf.r, y2, pmul(cf.s, q)));
-      y2 = y1;
-      y1 = y;
-      cplx u = pfma(cf.p, u1, pmul(cf.r, u2));
-      u2 = u1;
-      u1 = u;
-      cplx v = pfma(cf.p, v1, pmul(cf.r, v2));
-      v2 = v1;
-      v1 = v;
-    }
-    cplx* s = b.scr + (size_t)it * 8;
-    s[0] = y1;
-    s[1] = y2;
-    s[2] = u1;
-    s[3] = u2;
-    s[4] = v1;
-    s[5] = v2;
+  const int Cs = (Mmax + tpc - 1) >> ltpc;
+  const int M = ch.M[c];
+  const int c0 = ch.c0[c], cs = ch.cs[c];
+  cplx* const x = lane_ptr(b, reg, t);
+  const int k0 = min(M, j * Cs), k1 = min(M, k0 + Cs);
+  const int lane = b.tid & 31, wic = j >> 5, wpc = tpc >> 5;  // warp in chain, warps per chain
+  // ---- pass A: chunk map (zero-carry result and homogeneous responses) ----
+  cplx y1 = mk(0, 0), y2 = mk(0, 0), u1 = mk(1, 1), u2 = mk(0, 0), v1 = mk(0, 0), v2 = mk(1, 1);
+  for (int kb = k0; kb < k1; kb += 4) {
+    Coef cf[4];
+    cplx q[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (kb + u < k1) {
+        const int m = fwd ? kb + u : M - 1 - (kb + u);
+        cf[u] = coef(t, c, m);
+        q[u] = x[padi(c0 + cs * m)];
+      }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (kb + u < k1) {
+        if (SECOND) {
+          const cplx y = pfma(cf[u].p, y1, pfma(cf[u].r, y2, pmul(cf[u].s, q[u])));
+          y2 = y1;
+          y1 = y;
+          const cplx uu = pfma(cf[u].p, u1, pmul(cf[u].r, u2));
+          u2 = u1;
+          u1 = uu;
+          const cplx vv = pfma(cf[u].p, v1, pmul(cf[u].r, v2));
+          v2 = v1;
+          v1 = vv;
+        } else {
+          y1 = pfma(cf[u].p, y1, pmul(cf[u].s, q[u]));
+          u1 = pmul(cf[u].p, u1);
+        }
+      }
   }
-  __syncthreads();
-  // pass 2: carry chain over chunks (one thread per chain)
-  for (int cid = b.tid; cid < b.T * ch.nch; cid += b.nthr) {
-    cplx c1 = mk(0, 0), c2 = mk(0, 0);
-    for (int ck = 0; ck < nck; ++ck) {
-      cplx* s = b.scr + (size_t)(cid * nck + ck) * 8;
-      s[6] = c1;
-      s[7] = c2;
-      cplx n1 = pfma(s[2], c1, pfma(s[4], c2, s[0]));
-      cplx n2 = pfma(s[3], c1, pfma(s[5], c2, s[1]));
-      c1 = n1;
-      c2 = n2;
-    }
+  Aff me;
+  me.a11 = u1;
+  me.b1 = y1;
+  if (SECOND) {
+    me.a12 = v1;
+    me.a21 = u2;
+    me.a22 = v2;
+    me.b2 = y2;
+  } else {
+    me.a12 = me.a21 = me.a22 = me.b2 = mk(0, 0);
   }
-  __syncthreads();
-  // pass 3: re-run with the true carries, in place
-  for (int it = b.tid; it < nitems; it += b.nthr) {
-    const int ck = it % nck, c = (it / nck) % ch.nch, t = it / (nck * ch.nch);
-    const int M = ch.M[c];
-    cplx* x = lane_ptr(b, reg, t);
-    const cplx* s = b.scr + (size_t)it * 8;
-    cplx y1 = s[6], y2 = s[7];
-    const int k0 = ck * RP_CHUNK, k1 = min(M, k0 + RP_CHUNK);
-    for (int k = k0; k < k1; ++k) {
-      const int m = fwd ? k : M - 1 - k;
-      const Coef cf = coef(t, c, m);
-      cplx* px = &x[padi(ch.c0[c] + ch.cs[c] * m)];
-      cplx y = pfma(cf.p, y1, pfma(cf.r, y2, pmul(cf.s, *px)));
-      y2 = y1;
-      y1 = y;
-      *px = y;
+  // ---- inclusive warp scan of the chunk maps --------------------------------
+  Aff inc = me;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const Aff prev = aff_shfl_up<SECOND>(inc, d);
+    if (lane >= d) inc = aff_combine<SECOND>(prev, inc);
+  }
+  Aff exc = aff_shfl_up<SECOND>(inc, 1);  // map of the chunks before mine inside the warp
+  if (lane == 0) {
+    exc.a11 = mk(1, 1);
+    exc.a22 = mk(1, 1);
+    exc.a12 = exc.a21 = exc.b1 = exc.b2 = mk(0, 0);
+  }
+  cplx ci1, ci2;  // carry-in: y_{k0-1}, y_{k0-2}
+  if (wpc > 1) {
+    cplx* tot = b.scr + (cid * wpc + wic) * 6;
+    if (lane == 31) {
+      tot[0] = inc.a11;
+      tot[1] = inc.a12;
+      tot[2] = inc.a21;
+      tot[3] = inc.a22;
+      tot[4] = inc.b1;
+      tot[5] = inc.b2;
     }
+    __syncthreads();
+    cplx p1 = mk(0, 0), p2 = mk(0, 0);  // state entering my warp
+    for (int w = 0; w < wic; ++w) {
+      const cplx* s = b.scr + (cid * wpc + w) * 6;
+      if (SECOND) {
+        const cplx n1 = pfma(s[0], p1, pfma(s[1], p2, s[4]));
+        const cplx n2 = pfma(s[2], p1, pfma(s[3], p2, s[5]));
+        p1 = n1;
+        p2 = n2;
+      } else {
+        p1 = pfma(s[0], p1, s[4]);
+      }
+    }
+    if (SECOND) {
+      ci1 = pfma(exc.a11, p1, pfma(exc.a12, p2, exc.b1));
+      ci2 = pfma(exc.a21, p1, pfma(exc.a22, p2, exc.b2));
+    } else {
+      ci1 = pfma(exc.a11, p1, exc.b1);
+      ci2 = mk(0, 0);
+    }
+  } else {
+    ci1 = exc.b1;
+    ci2 = exc.b2;
+  }
+  // ---- pass C: re-walk with the carry, in place ------------------------------
+  y1 = ci1;
+  y2 = ci2;
+  for (int kb = k0; kb < k1; kb += 4) {
+    Coef cf[4];
+    cplx q[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (kb + u < k1) {
+        const int m = fwd ? kb + u : M - 1 - (kb + u);
+        cf[u] = coef(t, c, m);
+        q[u] = x[padi(c0 + cs * m)];
+      }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (kb + u < k1) {
+        cplx y;
+        if (SECOND) {
+          y = pfma(cf[u].p, y1, pfma(cf[u].r, y2, pmul(cf[u].s, q[u])));
+          y2 = y1;
+        } else {
+          y = pfma(cf[u].p, y1, pmul(cf[u].s, q[u]));
+        }
+        y1 = y;
+        q[u] = y;
+      }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (kb + u < k1) {
+        const int m = fwd ? kb + u : M - 1 - (kb + u);
+        x[padi(c0 + cs * m)] = q[u];
+      }
   }
   __syncthreads();
 }
@@ -398,75 +588,45 @@ RP_DEV Chains chains_of(const Lay& L, int n) {
   return ch;
 }
 
-// Chain stencil: out_m = sum_{d=0..2} w_d(i) * in_{m + dir*d} walking the chain
-// so that in-place is safe (halo elements are fetched before the barrier).
-//   dir = -1: out_i uses in_i, in_{i-2}          (to_ortho)
-//   dir = +1: out_i uses in_i, in_{i+2}, in_{i+4} (S^T, B2 matvec)
-// nin = number of valid input elements (others read as 0), nout = outputs.
+// Stencil along the lane, elementwise and in place:
+//   dir = -1: out_i = w(i, in_i, in_{i-2})                 (to_ortho)
+//   dir = +1: out_i = w(i, in_i, in_{i+2}, in_{i+4})        (S^T, B2 matvec)
+// Elements are processed in rounds of E per thread, walking against `dir`, so
+// a round only ever reads slots that no earlier round has written; results are
+// held in registers across the round's single barrier.
+// nin = number of valid inputs (others read as 0), nout = outputs written.
 template <class W>
-RP_DEV void chain_stencil(const Blk& b, int reg, const Lay& L, int nin, int nout, int dir, W wfun) {
+RP_DEV void lane_stencil(const Blk& b, int reg, const Lay& L, int nin, int nout, int dir, W wfun) {
+  enum { E = 4 };
   const int nmax = nin > nout ? nin : nout;
-  const Chains ch = chains_of(L, nmax);
-  int Mmax = ch.M[0];
-  const int nck = (Mmax + RP_CHUNK - 1) / RP_CHUNK;
-  const int nitems = b.T * 2 * nck;
-  // every thread handles at most RP_SI items so halos can sit in registers
-  enum { RP_SI = 4 };
-  cplx h1[RP_SI], h2[RP_SI];
-  int cnt = 0;
-  for (int it = b.tid; it < nitems && cnt < RP_SI; it += b.nthr, ++cnt) {
-    const int ck = it % nck, c = (it / nck) % 2, t = it / (nck * 2);
-    const cplx* x = lane_ptr(b, reg, t);
-    // halo = the two chain elements just beyond the chunk in direction dir
-    const int mh = (dir > 0) ? (ck + 1) * RP_CHUNK : ck * RP_CHUNK - 1;
-    const int mh2 = mh + dir;
-    const int i1 = 2 * mh + c, i2 = 2 * mh2 + c;
-    h1[cnt] = (mh >= 0 && i1 < nin) ? x[padi(ch.c0[c] + ch.cs[c] * mh)] : mk(0, 0);
-    h2[cnt] = (mh2 >= 0 && i2 < nin) ? x[padi(ch.c0[c] + ch.cs[c] * mh2)] : mk(0, 0);
-  }
-  __syncthreads();
-  cnt = 0;
-  for (int it = b.tid; it < nitems && cnt < RP_SI; it += b.nthr, ++cnt) {
-    const int ck = it % nck, c = (it / nck) % 2, t = it / (nck * 2);
-    cplx* x = lane_ptr(b, reg, t);
-    const int M = ch.M[c];
-    const int m0 = ck * RP_CHUNK, m1 = min(M, m0 + RP_CHUNK);
-    if (m0 >= m1) continue;
-    if (dir > 0) {
-      // ascending: window (in_m, in_{m+1}, in_{m+2})
-      cplx a0, a1, a2;
-      auto ld = [&](int m) -> cplx {
-        if (m >= m1) {
-          return (m == m1) ? h1[cnt] : h2[cnt];
+  const int span = E * b.nthr;
+  const int nrounds = (nmax + span - 1) / span;
+  for (int t = 0; t < b.T; ++t) {
+    cplx* const x = lane_ptr(b, reg, t);
+    auto in = [&](int i) -> cplx { return (i >= 0 && i < nin) ? x[padi(slot_of(L, i))] : mk(0, 0); };
+    for (int r = 0; r < nrounds; ++r) {
+      const int base = (dir > 0) ? r * span : (nrounds - 1 - r) * span;
+      cplx a0[E], a1[E], a2[E];
+#pragma unroll
+      for (int u = 0; u < E; ++u) {
+        const int i = base + b.tid + u * b.nthr;
+        if (i < nmax) {
+          a0[u] = in(i);
+          a1[u] = in(i + 2 * dir);
+          a2[u] = (dir > 0) ? in(i + 4) : mk(0, 0);
         }
-        const int i = 2 * m + c;
-        return (i < nin) ? x[padi(ch.c0[c] + ch.cs[c] * m)] : mk(0, 0);
-      };
-      a0 = ld(m0);
-      a1 = ld(m0 + 1);
-      a2 = ld(m0 + 2);
-      for (int m = m0; m < m1; ++m) {
-        const int i = 2 * m + c;
-        cplx o = wfun(i, a0, a1, a2);
-        if (i < nout) x[padi(ch.c0[c] + ch.cs[c] * m)] = o;
-        a0 = a1;
-        a1 = a2;
-        a2 = ld(m + 3);
       }
-    } else {
-      // descending: window (in_m, in_{m-1})
-      auto ld = [&](int m) -> cplx {
-        if (m < m0) return (m == m0 - 1) ? h1[cnt] : h2[cnt];
-        const int i = 2 * m + c;
-        return (i < nin) ? x[padi(ch.c0[c] + ch.cs[c] * m)] : mk(0, 0);
-      };
-      cplx a0 = ld(m1 - 1), a1 = ld(m1 - 2);
-      for (int m = m1 - 1; m >= m0; --m) {
-        const int i = 2 * m + c;
-        cplx o = wfun(i, a0, a1, mk(0, 0));
-        if (i < nout) x[padi(ch.c0[c] + ch.cs[c] * m)] = o;
-        a0 = a1;
-        a1 = ld(m - 2);
+      cplx res[E];
+#pragma unroll
+      for (int u = 0; u < E; ++u) {
+        const int i = base + b.tid + u * b.nthr;
+        if (i < nmax) res[u] = wfun(i, a0[u], a1[u], a2[u]);
+      }
+      __syncthreads();
+#pragma unroll
+      for (int u = 0; u < E; ++u) {
+        const int i = base + b.tid + u * b.nthr;
+        if (i < nout) x[padi(slot_of(L, i))] = res[u];
       }
     }
   }
@@ -474,7 +634,7 @@ RP_DEV void chain_stencil(const Blk& b, int reg, const Lay& L, int nin, int nout
 }
 
 // ===========================================================================
-// Lane index helpers
+// Loads / stores between global arrays and lanes
 // ===========================================================================
 struct LaneSel {
   int la, lb;   // lane indices of the .x / .y component (complex: la == lb)
@@ -496,63 +656,67 @@ RP_DEV LaneSel lane_sel(const Blk& b, const Instr& I, int t) {
   return s;
 }
 
+// Per-thread iteration space of a load/store: AXIS_Y walks one slot at a time
+// with i = tid + k*nthr (coalesced along the row); AXIS_X gives every thread a
+// fixed slot t = tid % T and i = tid / T + k * nthr / T (the T slots of one row
+// are adjacent in memory).
 RP_DEVNI void op_ld(const Program* __restrict__ pg, int pc) {
   const Blk b = make_blk(pg);
   const Instr I = pg->ins[pc];
   const int n = I.n, nz = (I.n2 > n && !(I.flags & LF_ACC)) ? I.n2 : n;
-  const int total = b.T * nz;
-  const double* lc = (const double*)I.p1;
-  for (int idx = b.tid; idx < total; idx += b.nthr) {
-    int t, i;
-    if (b.axis == AXIS_Y) {
-      t = idx / nz;
-      i = idx % nz;
-    } else {
-      i = idx / b.T;
-      t = idx % b.T;
-    }
+  const bool acc = I.flags & LF_ACC, isc = I.flags & LF_COMPLEX, isb = I.flags & LF_BCAST, mik = I.flags & LF_MULIK;
+  const double* __restrict__ lc = (const double*)I.p1;
+  const double* __restrict__ srd = (const double*)I.p0;
+  const cplx* __restrict__ src = (const cplx*)I.p0;
+  const long long ld = I.ld;
+  const Lay L = I.lay;
+  const bool ydir = (b.axis == AXIS_Y);
+  const int nt = ydir ? b.T : 1;
+  for (int tt = 0; tt < nt; ++tt) {
+    const int t = ydir ? tt : (b.tid & (b.T - 1));
+    const int istart = ydir ? b.tid : (b.tid >> b.logT);
+    const int istep = ydir ? b.nthr : (b.nthr >> b.logT);
     const LaneSel s = lane_sel(b, I, t);
-    cplx v = mk(0, 0);
-    if (i < n) {
-      if (I.flags & LF_COMPLEX) {
-        if (s.va) {
-          const cplx* src = (const cplx*)I.p0;
-          v = (b.axis == AXIS_Y) ? src[(size_t)s.la * I.ld + i] : src[(size_t)i * I.ld + s.la];
-        }
-      } else if (I.flags & LF_BCAST) {
-        if (s.va) {
-          const double* src = (const double*)I.p0;
-          double d = (b.axis == AXIS_Y) ? src[(size_t)s.la * I.ld + i] : src[(size_t)i * I.ld + s.la];
-          v = mk(d, d);
-        }
-      } else {
-        const double* src = (const double*)I.p0;
-        if (b.axis == AXIS_Y) {
-          if (s.va) v.x = src[(size_t)s.la * I.ld + i];
-          if (s.vb) v.y = src[(size_t)s.lb * I.ld + i];
-        } else {
-          if (s.va) v.x = src[(size_t)i * I.ld + s.la];
-          if (s.vb) v.y = src[(size_t)i * I.ld + s.lb];
-        }
-      }
-      double ca = I.s0, cb = I.s0;
-      if (I.flags & LF_LANECOEF) {
-        ca *= s.va ? __ldg(&lc[s.la]) : 0.0;
-        cb *= s.vb ? __ldg(&lc[s.lb]) : 0.0;
-      }
-      if (I.flags & LF_MULIK) {
-        const double k = (double)s.la * ca;
-        v = mk(-k * v.y, k * v.x);
-      } else {
-        v = mk(v.x * ca, v.y * cb);
-      }
+    double ca = I.s0, cb = I.s0;
+    if (I.flags & LF_LANECOEF) {
+      ca *= s.va ? __ldg(&lc[s.la]) : 0.0;
+      cb *= s.vb ? __ldg(&lc[s.lb]) : 0.0;
     }
-    cplx* x = lane_ptr(b, I.r0, t) + padi(slot_of(I.lay, i));
-    if (I.flags & LF_ACC) {
-      if (i < n) *x = cadd(*x, v);
-    } else {
-      *x = v;
-    }
+    const double kfac = (double)s.la * ca;
+    // element (lane l, index i) lives at l*sl + i*si
+    const long long sl = ydir ? ld : 1, si = ydir ? 1 : ld;
+    const long long oa = (long long)s.la * sl, ob = (long long)s.lb * sl;
+    cplx* const x = lane_ptr(b, I.r0, t);
+    cplx v[4];
+    batched<4>(
+        istart, istep, nz,
+        [&](int u, int i) {
+          cplx a = mk(0, 0);
+          if (i < n) {
+            if (isc) {
+              if (s.va) a = src[oa + i * si];
+            } else if (isb) {
+              if (s.va) {
+                const double d = srd[oa + i * si];
+                a = mk(d, d);
+              }
+            } else {
+              if (s.va) a.x = srd[oa + i * si];
+              if (s.vb) a.y = srd[ob + i * si];
+            }
+          }
+          v[u] = a;
+        },
+        [&](int u, int i) {
+          cplx a = v[u];
+          a = mik ? mk(-kfac * a.y, kfac * a.x) : mk(a.x * ca, a.y * cb);
+          cplx* px = x + padi(slot_of(L, i));
+          if (acc) {
+            if (i < n) *px = cadd(*px, a);
+          } else {
+            *px = a;
+          }
+        });
   }
   __syncthreads();
 }
@@ -561,44 +725,51 @@ RP_DEVNI void op_st(const Program* __restrict__ pg, int pc) {
   const Blk b = make_blk(pg);
   const Instr I = pg->ins[pc];
   const int n = I.n;
-  const int total = b.T * n;
-  for (int idx = b.tid; idx < total; idx += b.nthr) {
-    int t, i;
-    if (b.axis == AXIS_Y) {
-      t = idx / n;
-      i = idx % n;
-    } else {
-      i = idx / b.T;
-      t = idx % b.T;
-    }
+  const bool acc = I.flags & LF_ACC, isc = I.flags & LF_COMPLEX, cut = I.flags & LF_CUT;
+  double* __restrict__ drd = (double*)I.p0;
+  cplx* __restrict__ dst = (cplx*)I.p0;
+  const long long ld = I.ld;
+  const Lay L = I.lay;
+  const bool ydir = (b.axis == AXIS_Y);
+  const int nt = ydir ? b.T : 1;
+  for (int tt = 0; tt < nt; ++tt) {
+    const int t = ydir ? tt : (b.tid & (b.T - 1));
+    const int istart = ydir ? b.tid : (b.tid >> b.logT);
+    const int istep = ydir ? b.nthr : (b.nthr >> b.logT);
     const LaneSel s = lane_sel(b, I, t);
-    cplx v = lane_ptr(b, I.r0, t)[padi(slot_of(I.lay, i))];
-    v = cscale(v, I.s0);
-    bool cuta = false, cutb = false;
-    if (I.flags & LF_CUT) {
-      cuta = (i >= I.i0) || (I.i1 >= 0 && s.la >= I.i1);
-      cutb = (i >= I.i0) || (I.i1 >= 0 && s.lb >= I.i1);
-      if (cuta) v.x = 0.0;
-      if (cutb) v.y = 0.0;
-      if ((I.flags & LF_COMPLEX) && cuta) v = mk(0, 0);
-    }
-    if (I.flags & LF_COMPLEX) {
-      if (s.va) {
-        cplx* dst = (cplx*)I.p0;
-        cplx* d = (b.axis == AXIS_Y) ? &dst[(size_t)s.la * I.ld + i] : &dst[(size_t)i * I.ld + s.la];
-        *d = (I.flags & LF_ACC) ? cadd(*d, v) : v;
-      }
-    } else {
-      double* dst = (double*)I.p0;
-      if (s.va) {
-        double* d = (b.axis == AXIS_Y) ? &dst[(size_t)s.la * I.ld + i] : &dst[(size_t)i * I.ld + s.la];
-        *d = (I.flags & LF_ACC) ? *d + v.x : v.x;
-      }
-      if (s.vb) {
-        double* d = (b.axis == AXIS_Y) ? &dst[(size_t)s.lb * I.ld + i] : &dst[(size_t)i * I.ld + s.lb];
-        *d = (I.flags & LF_ACC) ? *d + v.y : v.y;
-      }
-    }
+    const long long sl = ydir ? ld : 1, si = ydir ? 1 : ld;
+    const long long oa = (long long)s.la * sl, ob = (long long)s.lb * sl;
+    const bool lcuta = cut && I.i1 >= 0 && s.la >= I.i1, lcutb = cut && I.i1 >= 0 && s.lb >= I.i1;
+    const cplx* const x = lane_ptr(b, I.r0, t);
+    cplx v[4], old[4];
+    batched<4>(
+        istart, istep, n,
+        [&](int u, int i) {
+          v[u] = x[padi(slot_of(L, i))];
+          if (acc) {
+            old[u] = mk(0, 0);
+            if (isc) {
+              if (s.va) old[u] = dst[oa + i * si];
+            } else {
+              if (s.va) old[u].x = drd[oa + i * si];
+              if (s.vb) old[u].y = drd[ob + i * si];
+            }
+          }
+        },
+        [&](int u, int i) {
+          cplx a = cscale(v[u], I.s0);
+          const bool ecut = cut && i >= I.i0;
+          if (ecut || lcuta) a.x = 0.0;
+          if (ecut || lcutb) a.y = 0.0;
+          if (isc && (ecut || lcuta)) a = mk(0, 0);
+          if (acc) a = cadd(a, old[u]);
+          if (isc) {
+            if (s.va) dst[oa + i * si] = a;
+          } else {
+            if (s.va) drd[oa + i * si] = a.x;
+            if (s.vb) drd[ob + i * si] = a.y;
+          }
+        });
   }
   __syncthreads();
 }
@@ -608,27 +779,35 @@ RP_DEVNI void op_elem(const Program* __restrict__ pg, int pc, int mode) {
   const Blk b = make_blk(pg);
   const Instr I = pg->ins[pc];
   const int n = I.n;
-  for (int idx = b.tid; idx < b.T * n; idx += b.nthr) {
-    const int t = idx / n, i = idx % n;
-    cplx* x0 = lane_ptr(b, I.r0, t) + padi(slot_of(I.lay, i));
-    switch (mode) {
-      case 0: *x0 = lane_ptr(b, I.r1, t)[padi(slot_of(I.lay2, i))]; break;
-      case 1: {
-        cplx a = lane_ptr(b, I.r1, t)[padi(slot_of(I.lay2, i))];
-        *x0 = mk(fma(I.s0, a.x, x0->x), fma(I.s0, a.y, x0->y));
-      } break;
-      case 2: *x0 = cscale(*x0, I.s0); break;
-      case 3:
-      case 4: {
-        cplx a = lane_ptr(b, I.r1, t)[padi(slot_of(I.lay2, i))];
-        cplx c = lane_ptr(b, I.r2, t)[padi(slot_of(I.lay2, i))];
-        *x0 = (mode == 4) ? pfma(a, c, *x0) : pmul(a, c);
-      } break;
-      case 5: *x0 = mk(0, 0); break;
-      case 6:
-        if (i >= I.i0) *x0 = mk(0, 0);
-        break;
-    }
+  const Lay L0 = I.lay, L1 = I.lay2;
+  for (int t = 0; t < b.T; ++t) {
+    cplx* const x0 = lane_ptr(b, I.r0, t);
+    const cplx* const x1 = lane_ptr(b, I.r1, t);
+    const cplx* const x2 = lane_ptr(b, I.r2, t);
+    cplx va[4], vb[4], vc[4];
+    batched<4>(
+        b.tid, b.nthr, n,
+        [&](int u, int i) {
+          if (mode == 1 || mode == 2 || mode == 4) va[u] = x0[padi(slot_of(L0, i))];
+          if (mode == 0 || mode == 1 || mode == 3 || mode == 4) vb[u] = x1[padi(slot_of(L1, i))];
+          if (mode == 3 || mode == 4) vc[u] = x2[padi(slot_of(L1, i))];
+        },
+        [&](int u, int i) {
+          cplx r;
+          switch (mode) {
+            case 0: r = vb[u]; break;
+            case 1: r = mk(fma(I.s0, vb[u].x, va[u].x), fma(I.s0, vb[u].y, va[u].y)); break;
+            case 2: r = cscale(va[u], I.s0); break;
+            case 3: r = pmul(vb[u], vc[u]); break;
+            case 4: r = pfma(vb[u], vc[u], va[u]); break;
+            case 5: r = mk(0, 0); break;
+            default:
+              if (i < I.i0) return;
+              r = mk(0, 0);
+              break;
+          }
+          x0[padi(slot_of(L0, i))] = r;
+        });
   }
   __syncthreads();
 }
@@ -637,12 +816,17 @@ RP_DEVNI void op_mulik(const Program* __restrict__ pg, int pc) {
   const Blk b = make_blk(pg);
   const Instr I = pg->ins[pc];
   const int n = I.n;
-  for (int idx = b.tid; idx < b.T * n; idx += b.nthr) {
-    const int t = idx / n, i = idx % n;
-    const double k = (double)((I.flags & LF_ELEMK) ? i : (b.unit0 + t)) * I.s0;
-    cplx* x0 = lane_ptr(b, I.r0, t) + padi(slot_of(I.lay, i));
-    cplx v = *x0;
-    *x0 = mk(-k * v.y, k * v.x);
+  const Lay L = I.lay;
+  const bool ek = I.flags & LF_ELEMK;
+  for (int t = 0; t < b.T; ++t) {
+    cplx* const x = lane_ptr(b, I.r0, t);
+    const double kl = (double)(b.unit0 + t) * I.s0;
+    for (int i = b.tid; i < n; i += b.nthr) {
+      const double k = ek ? (double)i * I.s0 : kl;
+      cplx* px = x + padi(slot_of(L, i));
+      const cplx v = *px;
+      *px = mk(-k * v.y, k * v.x);
+    }
   }
   __syncthreads();
 }
@@ -666,9 +850,9 @@ RP_DEVNI void op_toortho(const Program* __restrict__ pg, int pc) {
   const Blk b = make_blk(pg);
   const Instr I = pg->ins[pc];
   const int n = I.n, m = n - 2;
-  const double* d = (const double*)I.p0;
-  const double* l = (const double*)I.p1;
-  chain_stencil(b, I.r0, I.lay, m, n, -1, [=](int i, cplx a0, cplx a1, cplx) -> cplx {
+  const double* __restrict__ d = (const double*)I.p0;
+  const double* __restrict__ l = (const double*)I.p1;
+  lane_stencil(b, I.r0, I.lay, m, n, -1, [=](int i, cplx a0, cplx a1, cplx) -> cplx {
     const double di = (i < m) ? __ldg(&d[i]) : 0.0;
     const double li = (i >= 2) ? __ldg(&l[i - 2]) : 0.0;
     return mk(fma(di, a0.x, li * a1.x), fma(di, a0.y, li * a1.y));
@@ -680,27 +864,30 @@ RP_DEVNI void op_fromortho(const Program* __restrict__ pg, int pc) {
   const Blk b = make_blk(pg);
   const Instr I = pg->ins[pc];
   const int n = I.n, m = n - 2;
-  const double* d = (const double*)I.p0;
-  const double* l = (const double*)I.p1;
+  const double* __restrict__ d = (const double*)I.p0;
+  const double* __restrict__ l = (const double*)I.p1;
   const TdmaTab tt = *(const TdmaTab*)I.p2;
-  chain_stencil(b, I.r0, I.lay, n, m, +1, [=](int i, cplx a0, cplx a1, cplx) -> cplx {
+  lane_stencil(b, I.r0, I.lay, n, m, +1, [=](int i, cplx a0, cplx a1, cplx) -> cplx {
     if (i >= m) return mk(0, 0);
     const double di = __ldg(&d[i]), li = __ldg(&l[i]);
     return mk(fma(di, a0.x, li * a1.x), fma(di, a0.y, li * a1.y));
   });
   const Chains ch = chains_of(I.lay, m);
-  chain_solve(b, I.r0, ch, true, [=](int, int c, int mm) -> Coef {
+  const double* __restrict__ fs = tt.fs;
+  const double* __restrict__ fp = tt.fp;
+  const double* __restrict__ bp = tt.bp;
+  chain_solve<false>(b, I.r0, ch, true, [=](int, int c, int mm) -> Coef {
     const int i = 2 * mm + c;
-    const double s = __ldg(&tt.fs[i]), p = __ldg(&tt.fp[i]);
+    const double s = __ldg(&fs[i]), p = __ldg(&fp[i]);
     Coef cf;
     cf.s = mk(s, s);
     cf.p = mk(p, p);
     cf.r = mk(0, 0);
     return cf;
   });
-  chain_solve(b, I.r0, ch, false, [=](int, int c, int mm) -> Coef {
+  chain_solve<false>(b, I.r0, ch, false, [=](int, int c, int mm) -> Coef {
     const int i = 2 * mm + c;
-    const double p = __ldg(&tt.bp[i]);
+    const double p = __ldg(&bp[i]);
     Coef cf;
     cf.s = mk(1, 1);
     cf.p = mk(p, p);
@@ -714,10 +901,10 @@ RP_DEVNI void op_bandmv(const Program* __restrict__ pg, int pc) {
   const Blk b = make_blk(pg);
   const Instr I = pg->ins[pc];
   const int n = I.n, m = n - 2;
-  const double* lo = (const double*)I.p0;
-  const double* di = (const double*)I.p1;
-  const double* up = (const double*)I.p2;
-  chain_stencil(b, I.r0, I.lay, n, m, +1, [=](int i, cplx a0, cplx a1, cplx a2) -> cplx {
+  const double* __restrict__ lo = (const double*)I.p0;
+  const double* __restrict__ di = (const double*)I.p1;
+  const double* __restrict__ up = (const double*)I.p2;
+  lane_stencil(b, I.r0, I.lay, n, m, +1, [=](int i, cplx a0, cplx a1, cplx a2) -> cplx {
     if (i >= m) return mk(0, 0);
     const double w0 = __ldg(&lo[i]), w1 = __ldg(&di[i]), w2 = __ldg(&up[i]);
     return mk(fma(w0, a0.x, fma(w1, a1.x, w2 * a2.x)), fma(w0, a0.y, fma(w1, a1.y, w2 * a2.y)));
@@ -736,7 +923,7 @@ RP_DEVNI void op_diff(const Program* __restrict__ pg, int pc) {
   for (int rep = 0; rep < I.i0; ++rep) {
     const double sc = (rep == 0) ? I.s0 : 1.0;
     const Chains ch = chains_of(L, n);
-    chain_solve(b, I.r0, ch, false, [=](int, int c, int mm) -> Coef {
+    chain_solve<false>(b, I.r0, ch, false, [=](int, int c, int mm) -> Coef {
       const double s = 2.0 * (double)(2 * mm + c) * sc;
       Coef cf;
       cf.s = mk(s, s);
@@ -762,18 +949,22 @@ RP_DEVNI void op_fdma(const Program* __restrict__ pg, int pc) {
   const Instr I = pg->ins[pc];
   const FdmaTab ft = *(const FdmaTab*)I.p0;
   const Chains ch = chains_of(I.lay, I.n);
-  chain_solve(b, I.r0, ch, true, [=](int, int c, int mm) -> Coef {
+  const double* __restrict__ fp = ft.fp;
+  const double* __restrict__ bs = ft.bs;
+  const double* __restrict__ bp1 = ft.bp1;
+  const double* __restrict__ bp2 = ft.bp2;
+  chain_solve<false>(b, I.r0, ch, true, [=](int, int c, int mm) -> Coef {
     const int i = 2 * mm + c;
-    const double p = __ldg(&ft.fp[i]);
+    const double p = __ldg(&fp[i]);
     Coef cf;
     cf.s = mk(1, 1);
     cf.p = mk(p, p);
     cf.r = mk(0, 0);
     return cf;
   });
-  chain_solve(b, I.r0, ch, false, [=](int, int c, int mm) -> Coef {
+  chain_solve<true>(b, I.r0, ch, false, [=](int, int c, int mm) -> Coef {
     const int i = 2 * mm + c;
-    const double s = __ldg(&ft.bs[i]), p = __ldg(&ft.bp1[i]), r = __ldg(&ft.bp2[i]);
+    const double s = __ldg(&bs[i]), p = __ldg(&bp1[i]), r = __ldg(&bp2[i]);
     Coef cf;
     cf.s = mk(s, s);
     cf.p = mk(p, p);
@@ -794,15 +985,24 @@ RP_DEVNI void op_fdmamode(const Program* __restrict__ pg, int pc) {
   const Lay L = I.lay;
   const int r1 = I.r1;
   const bool cplxl = (I.flags & LF_COMPLEX) != 0;
+  const int nlanes = I.nlanes;
+  const double* __restrict__ a_low = mt.a_low;
+  const double* __restrict__ a_up1 = mt.a_up1;
+  const double* __restrict__ a_up2 = mt.a_up2;
+  const double* __restrict__ c_low = mt.c_low;
+  const double* __restrict__ c_up1 = mt.c_up1;
+  const double* __restrict__ c_up2 = mt.c_up2;
+  const double* __restrict__ lam = mt.lam;
+  const double alpha = mt.alpha;
   auto mu_of = [=](int t) -> cplx {
     const int P = b.unit0 + t;
     int la = cplxl ? P : 2 * P, lb = cplxl ? P : 2 * P + 1;
-    if (la >= I.nlanes) la = I.nlanes - 1;
-    if (lb >= I.nlanes) lb = I.nlanes - 1;
-    return mk(__ldg(&mt.lam[la]) + mt.alpha, __ldg(&mt.lam[lb]) + mt.alpha);
+    if (la >= nlanes) la = nlanes - 1;
+    if (lb >= nlanes) lb = nlanes - 1;
+    return mk(__ldg(&lam[la]) + alpha, __ldg(&lam[lb]) + alpha);
   };
   // forward: x_i -= l_{i-2} x_{i-2},  l_j = low_j / dia'_j
-  chain_solve(b, I.r0, ch, true, [=](int t, int c, int mm) -> Coef {
+  chain_solve<false>(b, I.r0, ch, true, [=](int t, int c, int mm) -> Coef {
     const int i = 2 * mm + c;
     Coef cf;
     cf.s = mk(1, 1);
@@ -810,34 +1010,32 @@ RP_DEVNI void op_fdmamode(const Program* __restrict__ pg, int pc) {
     cf.p = mk(0, 0);
     if (i >= 2) {
       const cplx mu = mu_of(t);
-      const double al = __ldg(&mt.a_low[i - 2]), cl = __ldg(&mt.c_low[i - 2]);
+      const double al = __ldg(&a_low[i - 2]), cl = __ldg(&c_low[i - 2]);
       const cplx inv = lane_ptr(b, r1, t)[padi(slot_of(L, i - 2))];
       cf.p = mk(-fma(mu.x, cl, al) * inv.x, -fma(mu.y, cl, al) * inv.y);
     }
     return cf;
   });
   // backward: x_i = (x_i - up1'_i x_{i+2} - up2_i x_{i+4}) / dia'_i
-  chain_solve(b, I.r0, ch, false, [=](int t, int c, int mm) -> Coef {
+  chain_solve<true>(b, I.r0, ch, false, [=](int t, int c, int mm) -> Coef {
     const int i = 2 * mm + c;
     const cplx mu = mu_of(t);
     const cplx inv = lane_ptr(b, r1, t)[padi(slot_of(L, i))];
     cplx u1 = mk(0, 0), u2 = mk(0, 0);
     if (i < n - 2) {
-      const double a = __ldg(&mt.a_up1[i]), cc = __ldg(&mt.c_up1[i]);
+      const double a = __ldg(&a_up1[i]), cc = __ldg(&c_up1[i]);
       u1 = mk(fma(mu.x, cc, a), fma(mu.y, cc, a));
       if (i >= 2) {
-        const double al = __ldg(&mt.a_low[i - 2]), cl = __ldg(&mt.c_low[i - 2]);
-        const double a2 = __ldg(&mt.a_up2[i - 2]), c2 = __ldg(&mt.c_up2[i - 2]);
+        const double al = __ldg(&a_low[i - 2]), cl = __ldg(&c_low[i - 2]);
+        const double a2 = __ldg(&a_up2[i - 2]), c2 = __ldg(&c_up2[i - 2]);
         const cplx invm = lane_ptr(b, r1, t)[padi(slot_of(L, i - 2))];
         const cplx lw = mk(fma(mu.x, cl, al) * invm.x, fma(mu.y, cl, al) * invm.y);
-        if (i - 2 < n - 4) {
-          u1.x = fma(-lw.x, fma(mu.x, c2, a2), u1.x);
-          u1.y = fma(-lw.y, fma(mu.y, c2, a2), u1.y);
-        }
+        u1.x = fma(-lw.x, fma(mu.x, c2, a2), u1.x);
+        u1.y = fma(-lw.y, fma(mu.y, c2, a2), u1.y);
       }
     }
     if (i < n - 4) {
-      const double a = __ldg(&mt.a_up2[i]), cc = __ldg(&mt.c_up2[i]);
+      const double a = __ldg(&a_up2[i]), cc = __ldg(&c_up2[i]);
       u2 = mk(fma(mu.x, cc, a), fma(mu.y, cc, a));
     }
     Coef cf;
@@ -863,42 +1061,53 @@ RP_DEVNI void op_dct(const Program* __restrict__ pg, int pc) {
   const Lay lin = I.lay;
   const int npairs = N / 2 + 1;
   const int nwarp = (b.nthr + 31) >> 5;
-  const int group = P.fft.pow2 ? b.T : b.wbT;
+  const bool pow2 = P.fft.pow2;
+  const int group = pow2 ? b.T : b.wbT;
+  const cplx* __restrict__ sctab = P.sc;
+  const cplx* __restrict__ chirp = P.fft.chirp;
+  const cplx* __restrict__ bhat = P.fft.bhat;
   for (int g = 0; g < b.T; g += group) {
     const int ns = min(group, b.T - g);
     // ---- pre-combine, in place at the source slots (the first FFT pass
     //      reads through the layout map; Bluestein writes to the work buffer)
     for (int tt = 0; tt < ns; ++tt) {
       const int t = g + tt;
-      cplx* x = lane_ptr(b, I.r0, t);
+      cplx* const x = lane_ptr(b, I.r0, t);
+      cplx* const wbuf = b.wb + tt * b.wbP;
       cplx f1 = mk(0, 0);
-      for (int j = b.tid; j < npairs; j += b.nthr) {
-        const int jm = N - j;
-        const int sj = padi(slot_of(lin, j)), sm = padi(slot_of(lin, jm));
-        cplx a = x[sj], c = x[sm];
-        if (backward) {  // c_k * (-1)^k / 2, ends doubled
-          double ga = (j & 1) ? -0.5 : 0.5, gc = (jm & 1) ? -0.5 : 0.5;
-          if (j == 0) ga *= 2.0;
-          if (jm == N) gc *= 2.0;
-          a = cscale(a, ga);
-          c = cscale(c, gc);
-        }
-        const cplx sc = __ldg(&P.sc[j]);
-        const cplx sum = cadd(a, c), dif = csub(a, c);
-        const cplx za = mk(fma(-sc.x, dif.x, 0.5 * sum.x), fma(-sc.x, dif.y, 0.5 * sum.y));
-        const cplx zb = mk(fma(sc.x, dif.x, 0.5 * sum.x), fma(sc.x, dif.y, 0.5 * sum.y));
-        const double w = (j == 0) ? 0.5 * sc.y : sc.y;
-        f1.x = fma(w, dif.x, f1.x);
-        f1.y = fma(w, dif.y, f1.y);
-        if (P.fft.pow2) {
-          x[sj] = za;
-          if (jm != j && j != 0) x[sm] = zb;
-        } else {
-          cplx* wbuf = b.wb + (size_t)tt * b.wbP;
-          wbuf[padi(j)] = cmul(za, __ldg(&P.fft.chirp[j]));
-          if (jm != j && j != 0) wbuf[padi(jm)] = cmul(zb, __ldg(&P.fft.chirp[jm]));
-        }
-      }
+      cplx va[4], vc[4], vs[4];
+      batched<4>(
+          b.tid, b.nthr, npairs,
+          [&](int u, int j) {
+            va[u] = x[padi(slot_of(lin, j))];
+            vc[u] = x[padi(slot_of(lin, N - j))];
+            vs[u] = __ldg(&sctab[j]);
+          },
+          [&](int u, int j) {
+            const int jm = N - j;
+            cplx a = va[u], c = vc[u];
+            if (backward) {  // c_k * (-1)^k / 2, ends doubled
+              double ga = (j & 1) ? -0.5 : 0.5, gc = (jm & 1) ? -0.5 : 0.5;
+              if (j == 0) ga *= 2.0;
+              if (jm == N) gc *= 2.0;
+              a = cscale(a, ga);
+              c = cscale(c, gc);
+            }
+            const cplx sc = vs[u];
+            const cplx sum = cadd(a, c), dif = csub(a, c);
+            const cplx za = mk(fma(-sc.x, dif.x, 0.5 * sum.x), fma(-sc.x, dif.y, 0.5 * sum.y));
+            const cplx zb = mk(fma(sc.x, dif.x, 0.5 * sum.x), fma(sc.x, dif.y, 0.5 * sum.y));
+            const double w = (j == 0) ? 0.5 * sc.y : sc.y;
+            f1.x = fma(w, dif.x, f1.x);
+            f1.y = fma(w, dif.y, f1.y);
+            if (pow2) {
+              x[padi(slot_of(lin, j))] = za;
+              if (jm != j && j != 0) x[padi(slot_of(lin, jm))] = zb;
+            } else {
+              wbuf[padi(j)] = cmul(za, __ldg(&chirp[j]));
+              if (jm != j && j != 0) wbuf[padi(jm)] = cmul(zb, __ldg(&chirp[jm]));
+            }
+          });
       for (int o = 16; o > 0; o >>= 1) {
         f1.x += __shfl_down_sync(0xffffffffu, f1.x, o);
         f1.y += __shfl_down_sync(0xffffffffu, f1.y, o);
@@ -907,26 +1116,32 @@ RP_DEVNI void op_dct(const Program* __restrict__ pg, int pc) {
     }
     __syncthreads();
     // ---- complex DFT of length N ----------------------------------------
-    if (P.fft.pow2) {
+    if (pow2) {
       fft_run(b.tid, b.nthr, (I.r0 * b.T + g) * b.capP, b.capP, ns, N, P.fft.tw, false, 1.0, lin, true);
     } else {
       const int Lb = P.fft.Lb;
-      for (int idx = b.tid; idx < ns * (Lb - N); idx += b.nthr) {
-        const int t = idx / (Lb - N), j = N + idx % (Lb - N);
-        b.wb[(size_t)t * b.wbP + padi(j)] = mk(0, 0);
+      for (int t = 0; t < ns; ++t) {
+        cplx* w = b.wb + t * b.wbP;
+        for (int j = N + b.tid; j < Lb; j += b.nthr) w[padi(j)] = mk(0, 0);
       }
       __syncthreads();
       fft_run(b, b.wb_off, b.wbP, ns, Lb, P.fft.tw, false, 1.0);
-      for (int idx = b.tid; idx < ns * Lb; idx += b.nthr) {
-        const int t = idx / Lb, j = idx % Lb;
-        cplx* w = &b.wb[(size_t)t * b.wbP + padi(j)];
-        *w = cmul(*w, __ldg(&P.fft.bhat[j]));
+      for (int t = 0; t < ns; ++t) {
+        cplx* w = b.wb + t * b.wbP;
+        cplx v[4];
+        batched<4>(
+            b.tid, b.nthr, Lb, [&](int u, int j) { v[u] = cmul(w[padi(j)], __ldg(&bhat[j])); },
+            [&](int u, int j) { w[padi(j)] = v[u]; });
       }
       __syncthreads();
       fft_run(b, b.wb_off, b.wbP, ns, Lb, P.fft.tw, true, 1.0);
-      for (int idx = b.tid; idx < ns * N; idx += b.nthr) {
-        const int t = idx / N, j = idx % N;
-        lane_ptr(b, I.r0, g + t)[padi(j)] = cmul(b.wb[(size_t)t * b.wbP + padi(j)], __ldg(&P.fft.chirp[j]));
+      for (int t = 0; t < ns; ++t) {
+        const cplx* w = b.wb + t * b.wbP;
+        cplx* x = lane_ptr(b, I.r0, g + t);
+        cplx v[4];
+        batched<4>(
+            b.tid, b.nthr, N, [&](int u, int j) { v[u] = cmul(w[padi(j)], __ldg(&chirp[j])); },
+            [&](int u, int j) { x[padi(j)] = v[u]; });
       }
       __syncthreads();
     }
@@ -934,21 +1149,27 @@ RP_DEVNI void op_dct(const Program* __restrict__ pg, int pc) {
   // ---- recombine: X_{2k} = Z_k + Z_{N-k};  D_k = i (Z_k - Z_{N-k}) -------
   const double he = backward ? 1.0 : 1.0 / (double)N;  // even outputs: (+1)/N
   const int Ko = (N - 1) / 2;                           // odd outputs O_0..O_Ko
-  for (int idx = b.tid; idx < b.T * npairs; idx += b.nthr) {
-    const int t = idx / npairs, k = idx % npairs;
-    cplx* x = lane_ptr(b, I.r0, t);
-    const cplx zk = x[padi(k)];
-    const cplx zm = (k == 0) ? zk : x[padi(N - k)];
-    cplx e = cadd(zk, zm);
-    double h = he;
-    if (!backward && (k == 0 || 2 * k == N)) h *= 0.5;
-    x[padi(k)] = cscale(e, h);
-    if (k >= 1 && k <= Ko) x[padi(N - k)] = mk(-(zk.y - zm.y), zk.x - zm.x);
-    if (k == 0) {
-      cplx f1 = mk(0, 0);
-      for (int w = 0; w < nwarp; ++w) f1 = cadd(f1, b.scr[t * 32 + w]);
-      x[padi(N)] = cscale(f1, 2.0);
-    }
+  for (int t = 0; t < b.T; ++t) {
+    cplx* const x = lane_ptr(b, I.r0, t);
+    cplx vk[4], vm[4];
+    batched<4>(
+        b.tid, b.nthr, npairs,
+        [&](int u, int k) {
+          vk[u] = x[padi(k)];
+          vm[u] = (k == 0) ? vk[u] : x[padi(N - k)];
+        },
+        [&](int u, int k) {
+          const cplx zk = vk[u], zm = vm[u];
+          double h = he;
+          if (!backward && (k == 0 || 2 * k == N)) h *= 0.5;
+          x[padi(k)] = cscale(cadd(zk, zm), h);
+          if (k >= 1 && k <= Ko) x[padi(N - k)] = mk(-(zk.y - zm.y), zk.x - zm.x);
+          if (k == 0) {
+            cplx f1 = mk(0, 0);
+            for (int w = 0; w < nwarp; ++w) f1 = cadd(f1, b.scr[t * 32 + w]);
+            x[padi(N)] = cscale(f1, 2.0);
+          }
+        });
   }
   __syncthreads();
   // ---- odd outputs: prefix sum along slots N, N-1, ... -------------------
@@ -960,7 +1181,7 @@ RP_DEVNI void op_dct(const Program* __restrict__ pg, int pc) {
   ch.c0[1] = 0;
   ch.cs[1] = 0;
   ch.M[1] = 0;
-  chain_solve(b, I.r0, ch, true, [=](int, int, int) -> Coef {
+  chain_solve<false>(b, I.r0, ch, true, [=](int, int, int) -> Coef {
     Coef cf;
     cf.s = mk(1, 1);
     cf.p = mk(1, 1);
@@ -969,10 +1190,12 @@ RP_DEVNI void op_dct(const Program* __restrict__ pg, int pc) {
   });
   if (!backward) {  // odd outputs: (-1)/N, last one halved when N is odd
     const double ho = -1.0 / (double)N;
-    for (int idx = b.tid; idx < b.T * (Ko + 1); idx += b.nthr) {
-      const int t = idx / (Ko + 1), k = idx % (Ko + 1);
-      cplx* x = &lane_ptr(b, I.r0, t)[padi(N - k)];
-      *x = cscale(*x, (2 * k + 1 == N) ? 0.5 * ho : ho);
+    for (int t = 0; t < b.T; ++t) {
+      cplx* const x = lane_ptr(b, I.r0, t);
+      for (int k = b.tid; k <= Ko; k += b.nthr) {
+        cplx* px = &x[padi(N - k)];
+        *px = cscale(*px, (2 * k + 1 == N) ? 0.5 * ho : ho);
+      }
     }
     __syncthreads();
   }
@@ -992,19 +1215,28 @@ RP_DEVNI void op_rfft(const Program* __restrict__ pg, int pc) {
   const FftPlan P = *(const FftPlan*)I.p1;
   const int n = P.L, m = n / 2 + 1;
   dft_any(b, I.r0 * b.T * b.capP, b.capP, b.T, P, false, 1.0);
-  cplx* dst = (cplx*)I.p0;
-  for (int idx = b.tid; idx < b.T * m; idx += b.nthr) {
-    const int k = idx / b.T, t = idx % b.T;
-    const int ca = 2 * (b.unit0 + t), cb = ca + 1;
-    const cplx* z = lane_ptr(b, I.r0, t);
-    const cplx zk = z[padi(k)];
-    const cplx zm = cconj(z[padi((n - k) % n)]);
-    const cplx s = cadd(zk, zm), d = csub(zk, zm);
-    double h = 0.5 * I.s0;
-    if ((I.flags & LF_CUT) && k >= I.i0) h = 0.0;
-    if (ca < I.nlanes) dst[(size_t)k * I.ld + ca] = mk(h * s.x, h * s.y);
-    if (cb < I.nlanes) dst[(size_t)k * I.ld + cb] = mk(h * d.y, -h * d.x);
-  }
+  cplx* __restrict__ dst = (cplx*)I.p0;
+  const long long ld = I.ld;
+  const int t = b.tid & (b.T - 1);
+  const int ca = 2 * (b.unit0 + t), cb = ca + 1;
+  const bool va = ca < I.nlanes, vb = cb < I.nlanes;
+  const cplx* const z = lane_ptr(b, I.r0, t);
+  const bool cut = I.flags & LF_CUT;
+  cplx vk[4], vm[4];
+  batched<4>(
+      b.tid >> b.logT, b.nthr >> b.logT, m,
+      [&](int u, int k) {
+        vk[u] = z[padi(k)];
+        vm[u] = z[padi(k == 0 ? 0 : n - k)];
+      },
+      [&](int u, int k) {
+        const cplx zk = vk[u], zm = cconj(vm[u]);
+        const cplx s = cadd(zk, zm), d = csub(zk, zm);
+        double h = 0.5 * I.s0;
+        if (cut && k >= I.i0) h = 0.0;
+        if (va) dst[k * ld + ca] = mk(h * s.x, h * s.y);
+        if (vb) dst[k * ld + cb] = mk(h * d.y, -h * d.x);
+      });
   __syncthreads();
 }
 
@@ -1013,28 +1245,37 @@ RP_DEVNI void op_irfft(const Program* __restrict__ pg, int pc) {
   const Instr I = pg->ins[pc];
   const FftPlan P = *(const FftPlan*)I.p1;
   const int n = P.L, m = n / 2 + 1;
-  const cplx* src = (const cplx*)I.p0;
-  for (int idx = b.tid; idx < b.T * m; idx += b.nthr) {
-    const int k = idx / b.T, t = idx % b.T;
-    const int ca = 2 * (b.unit0 + t), cb = ca + 1;
-    cplx xa = (ca < I.nlanes) ? src[(size_t)k * I.ld + ca] : mk(0, 0);
-    cplx xb = (cb < I.nlanes) ? src[(size_t)k * I.ld + cb] : mk(0, 0);
-    if (I.flags & LF_MULIK) {
-      const double kk = (double)k * I.s0;
-      xa = mk(-kk * xa.y, kk * xa.x);
-      xb = mk(-kk * xb.y, kk * xb.x);
-    } else {
-      xa = cscale(xa, I.s0);
-      xb = cscale(xb, I.s0);
-    }
-    if (k == 0 || 2 * k == n) {
-      xa.y = 0.0;
-      xb.y = 0.0;
-    }
-    cplx* z = lane_ptr(b, I.r0, t);
-    z[padi(k)] = mk(xa.x - xb.y, xa.y + xb.x);  // X_a + i X_b
-    if (k > 0 && 2 * k != n) z[padi(n - k)] = mk(xa.x + xb.y, -xa.y + xb.x);  // conj(X_a) + i conj(X_b)
-  }
+  const cplx* __restrict__ src = (const cplx*)I.p0;
+  const long long ld = I.ld;
+  const int t = b.tid & (b.T - 1);
+  const int ca = 2 * (b.unit0 + t), cb = ca + 1;
+  const bool va = ca < I.nlanes, vb = cb < I.nlanes;
+  const bool mik = I.flags & LF_MULIK;
+  cplx* const z = lane_ptr(b, I.r0, t);
+  cplx xa4[4], xb4[4];
+  batched<4>(
+      b.tid >> b.logT, b.nthr >> b.logT, m,
+      [&](int u, int k) {
+        xa4[u] = va ? src[k * ld + ca] : mk(0, 0);
+        xb4[u] = vb ? src[k * ld + cb] : mk(0, 0);
+      },
+      [&](int u, int k) {
+        cplx xa = xa4[u], xb = xb4[u];
+        if (mik) {
+          const double kk = (double)k * I.s0;
+          xa = mk(-kk * xa.y, kk * xa.x);
+          xb = mk(-kk * xb.y, kk * xb.x);
+        } else {
+          xa = cscale(xa, I.s0);
+          xb = cscale(xb, I.s0);
+        }
+        if (k == 0 || 2 * k == n) {
+          xa.y = 0.0;
+          xb.y = 0.0;
+        }
+        z[padi(k)] = mk(xa.x - xb.y, xa.y + xb.x);  // X_a + i X_b
+        if (k > 0 && 2 * k != n) z[padi(n - k)] = mk(xa.x + xb.y, -xa.y + xb.x);  // conj(X_a) + i conj(X_b)
+      });
   __syncthreads();
   dft_any(b, I.r0 * b.T * b.capP, b.capP, b.T, P, true, 1.0 / (double)n);
 }
@@ -1046,8 +1287,15 @@ RP_DEV void lane_vm_body(const Program* __restrict__ progs) {
   const Program* __restrict__ pg = progs + blockIdx.y;
   if ((int)(blockIdx.x * pg->T) >= pg->nunits) return;
   const int ninstr = pg->ninstr;
+#ifndef RP_EMU
+  long long* const prof = (blockIdx.x == 0 && threadIdx.x == 0) ? pg->prof : nullptr;
+#endif
   for (int pc = 0; pc < ninstr; ++pc) {
     const int op = pg->ins[pc].op;
+#ifndef RP_EMU
+    long long t0 = 0;
+    if (prof) t0 = clock64();
+#endif
     switch (op) {
       case OP_LD: op_ld(pg, pc); break;
       case OP_ST: op_st(pg, pc); break;
@@ -1070,6 +1318,9 @@ RP_DEV void lane_vm_body(const Program* __restrict__ progs) {
       case OP_SETZERO00: op_setzero00(pg, pc); break;
       default: break;
     }
+#ifndef RP_EMU
+    if (prof) prof[op] += clock64() - t0;
+#endif
   }
 }
 

@@ -40,8 +40,9 @@ struct ArrRef {
 
 // A finalised lane program on the device
 struct Built {
-  DevBuf dprog;
+  DevBuf dprog, dprof;
   int nblocks = 0, nthreads = 0, smem = 0;
+  void dump_prof(const char* name) const;  // development aid (RUSTPDE_B200_OPPROF=1)
   double bytes = 0.0;  // algorithmic global-memory bytes of one launch (loads + stores)
   bool valid = false;
   void launch(cudaStream_t s) const;

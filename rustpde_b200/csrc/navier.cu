@@ -524,6 +524,8 @@ void Navier2D::profile(int reps, std::vector<double>& ms) {
     time += dt;
   }
   for (auto& e : ev) cudaEventDestroy(e);
+  for (size_t i = 0; i < ops_.size(); ++i)
+    if (ops_[i].kind == 0) step_[ops_[i].idx].dump_prof(opinfo_[i].name.c_str());
 #else
   for (int r = 0; r < reps; ++r) {
     run_step();

@@ -22,6 +22,21 @@ void Arr::download(double* host, cudaStream_t s) const {
 }
 void Arr::zero(cudaStream_t s) { rt::dzero(buf.p, buf.bytes, s); }
 
+void Built::dump_prof(const char* name) const {
+  if (!dprof.p) return;
+  static const char* names[] = {"end", "ld", "st", "zero", "copy", "axpy", "scale", "mulpw", "cut", "mulik", "toortho",
+                                "fromortho", "diff", "dct", "rfft", "irfft", "bandmv", "fdma", "fdmamode", "setzero00"};
+  long long c[64];
+  rt::d2h(c, dprof.p, sizeof(c), 0);
+  rt::sync(0);
+  long long tot = 0;
+  for (int i = 0; i < 20; ++i) tot += c[i];
+  fprintf(stderr, "  [opprof] %-26s blocks %d thr %d smem %d: total %lld cyc:", name, nblocks, nthreads, smem, tot);
+  for (int i = 0; i < 20; ++i)
+    if (c[i]) fprintf(stderr, " %s=%.1f%%", names[i], 100.0 * c[i] / (double)tot);
+  fprintf(stderr, "\n");
+}
+
 void Built::launch(cudaStream_t s) const {
   if (!valid) throw Error(RP_ERR_INTERNAL, "launch of an unbuilt lane program");
   launch_lane_programs(dprog.as<Program>(), 1, nblocks, nthreads, smem, s);
@@ -328,7 +343,7 @@ Built ProgBuilder::build() {
       const int T = cand[c];
       if (T > 1 && (p.nunits + T - 1) / T < 1) continue;
       for (int wbT = wbcap_ ? T : 0; wbT >= (wbcap_ ? 1 : 0); wbT = (wbT > 1 ? wbT / 2 : wbT - 1)) {
-        const long long scr = std::max<long long>((long long)T * 32, (long long)T * 2 * nck * 8) + 64;
+        const long long scr = (long long)T * 32 + 160;  // DCT partial sums + warp totals of the scans
         const long long bytes = 16LL * ((long long)p.nreg * T * capP + (long long)wbT * wbP + scr);
         if (bytes <= (pass == 0 ? soft : budget)) {
           bestT = T;
@@ -347,10 +362,16 @@ Built ProgBuilder::build() {
   int nthr = std::max(64, pow2_ceil((fftlen_ + 15) / 16));
   const int want = pow2_ceil(std::max(1, bestT * p.cap / 8));
   while (nthr < 256 && nthr < want) nthr <<= 1;
-  while (nthr * 4 < bestT * 2 * nck) nthr <<= 1;  // chain_stencil: <= 4 items per thread
+  while (nthr < 64 * bestT) nthr <<= 1;  // scans: >= one warp per parity chain
+  (void)nck;
   if (nthr > 512) throw Error(RP_ERR_SHAPE, "lane too long for a 512-thread block");
   p.nthreads = nthr;
   Built b;
+  p.prof = nullptr;
+  if (getenv("RUSTPDE_B200_OPPROF")) {
+    b.dprof = DevBuf(64 * sizeof(long long));
+    p.prof = b.dprof.as<long long>();
+  }
   b.dprog = upload_struct(p);
   b.nblocks = (p.nunits + p.T - 1) / p.T;
   b.nthreads = nthr;

@@ -256,6 +256,7 @@ static inline int atomicAdd(int* p, int v) {
   *p = o + v;
   return o;
 }
+static inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
 static inline double __dmul_rn(double a, double b) { return a * b; }
 static inline double __dadd_rn(double a, double b) { return a + b; }
 static inline double __fma_rn(double a, double b, double c) { return std::fma(a, b, c); }
