@@ -8,7 +8,8 @@
 
 namespace rp {
 
-__global__ void __launch_bounds__(512) lane_vm_kernel(const Program* __restrict__ progs) { lane_vm_body(progs); }
+// (512, 1): without the explicit min-blocks ptxas squeezed the whole call tree into 32 registers
+__global__ void __launch_bounds__(512, 1) lane_vm_kernel(const Program* __restrict__ progs) { lane_vm_body(progs); }
 
 __global__ void __launch_bounds__(256) dgemm_dmma_kernel(GemmArgs g);
 enum { GBM = 128, GBN = 128, GBK = 16, GPAD = 8, GLD = GBM + GPAD };
