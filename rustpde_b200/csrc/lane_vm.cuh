@@ -50,6 +50,22 @@ extern __shared__ __align__(16) unsigned char rp_dyn_smem_raw_[];
 #define RP_SMEM ((cplx*)rp_dyn_smem_raw_)
 #endif
 
+// development aid: sub-op cycle marks of thread 0 / block 0 (RUSTPDE_B200_OPPROF=1)
+#ifndef RP_EMU
+#define RP_MARK_INIT long long mark_t_ = clock64()
+#define RP_MARK(slot)                                                   \
+  do {                                                                  \
+    if (blockIdx.x == 0 && threadIdx.x == 0 && pg->prof) {              \
+      const long long c_ = clock64();                                   \
+      pg->prof[slot] += c_ - mark_t_;                                   \
+      mark_t_ = c_;                                                     \
+    }                                                                   \
+  } while (0)
+#else
+#define RP_MARK_INIT
+#define RP_MARK(slot)
+#endif
+
 // Block context.  Built by value inside each (noinline) op from the program
 // header; never passed by reference across a call, so it stays in registers.
 struct Blk {
@@ -304,23 +320,11 @@ RP_DEV void fft_run(const Blk& b, int base_off, int stride, int nslots, int L, c
   fft_run(b.tid, b.nthr, base_off, stride, nslots, L, tw, inverse, scale, lay_natural(), false);
 }
 
-// Batched grid-stride loop over i = tid, tid+nthr, ... < n: `ldf(u, i)` for a
-// batch of B indices first (independent loads in flight), then `stf(u, i)`.
-template <int B, class LF, class SF>
-RP_DEV void batched(int tid, int nthr, int n, LF ldf, SF stf) {
-  for (int i0 = tid; i0 < n; i0 += B * nthr) {
-#pragma unroll
-    for (int u = 0; u < B; ++u) {
-      const int i = i0 + u * nthr;
-      if (i < n) ldf(u, i);
-    }
-#pragma unroll
-    for (int u = 0; u < B; ++u) {
-      const int i = i0 + u * nthr;
-      if (i < n) stf(u, i);
-    }
-  }
-}
+// Batched grid-stride loops are written out explicitly at each site:
+//   for (i0 = start; i0 < n; i0 += 4*step) { load 4 -> registers; compute/store 4 }
+// (register arrays with compile-time indices only -- lambdas capturing arrays by
+// reference ended up in local memory and dominated the run time).
+#define RP_B4 _Pragma("unroll") for (int u = 0; u < 4; ++u)
 
 // Complex DFT of arbitrary length on lane slots [0, L) of register buffers
 // (natural order), in place.  pow2 -> fft_run; else Bluestein through b.wb.
@@ -338,42 +342,69 @@ RP_DEV void dft_any(const Blk& b, int base_off, int stride, int nslots, const Ff
     for (int t = 0; t < ns; ++t) {
       const cplx* x = base + (g + t) * stride;
       cplx* w = b.wb + t * b.wbP;
-      cplx v[4];
-      batched<4>(
-          b.tid, b.nthr, Lb,
-          [&](int u, int j) {
-            v[u] = mk(0.0, 0.0);
-            if (j < L) {
-              cplx a = x[padi(j)];
-              if (inverse) a.y = -a.y;
-              v[u] = cmul(a, __ldg(&chirp[j]));
-            }
-          },
-          [&](int u, int j) { w[padi(j)] = v[u]; });
+      for (int j0 = b.tid; j0 < Lb; j0 += 4 * b.nthr) {
+        cplx v[4], c[4];
+        RP_B4 {
+          const int j = j0 + u * b.nthr;
+          v[u] = mk(0.0, 0.0);
+          c[u] = mk(0.0, 0.0);
+          if (j < L) {
+            v[u] = x[padi(j)];
+            c[u] = __ldg(&chirp[j]);
+          }
+        }
+        RP_B4 {
+          const int j = j0 + u * b.nthr;
+          if (j < Lb) {
+            cplx a = v[u];
+            if (inverse) a.y = -a.y;
+            w[padi(j)] = cmul(a, c[u]);
+          }
+        }
+      }
     }
     __syncthreads();
     fft_run(b, b.wb_off, b.wbP, ns, Lb, P.tw, false, 1.0);
     for (int t = 0; t < ns; ++t) {
       cplx* w = b.wb + t * b.wbP;
-      cplx v[4];
-      batched<4>(
-          b.tid, b.nthr, Lb, [&](int u, int j) { v[u] = cmul(w[padi(j)], __ldg(&bhat[j])); },
-          [&](int u, int j) { w[padi(j)] = v[u]; });
+      for (int j0 = b.tid; j0 < Lb; j0 += 4 * b.nthr) {
+        cplx v[4], c[4];
+        RP_B4 {
+          const int j = j0 + u * b.nthr;
+          if (j < Lb) {
+            v[u] = w[padi(j)];
+            c[u] = __ldg(&bhat[j]);
+          }
+        }
+        RP_B4 {
+          const int j = j0 + u * b.nthr;
+          if (j < Lb) w[padi(j)] = cmul(v[u], c[u]);
+        }
+      }
     }
     __syncthreads();
     fft_run(b, b.wb_off, b.wbP, ns, Lb, P.tw, true, 1.0);
     for (int t = 0; t < ns; ++t) {
       cplx* x = base + (g + t) * stride;
       const cplx* w = b.wb + t * b.wbP;
-      cplx v[4];
-      batched<4>(
-          b.tid, b.nthr, L,
-          [&](int u, int j) {
-            cplx a = cmul(w[padi(j)], __ldg(&chirp[j]));
+      for (int j0 = b.tid; j0 < L; j0 += 4 * b.nthr) {
+        cplx v[4], c[4];
+        RP_B4 {
+          const int j = j0 + u * b.nthr;
+          if (j < L) {
+            v[u] = w[padi(j)];
+            c[u] = __ldg(&chirp[j]);
+          }
+        }
+        RP_B4 {
+          const int j = j0 + u * b.nthr;
+          if (j < L) {
+            cplx a = cmul(v[u], c[u]);
             if (inverse) a.y = -a.y;
-            v[u] = cscale(a, scale);
-          },
-          [&](int u, int j) { x[padi(j)] = v[u]; });
+            x[padi(j)] = cscale(a, scale);
+          }
+        }
+      }
     }
     __syncthreads();
   }
@@ -661,6 +692,7 @@ RP_DEV LaneSel lane_sel(const Blk& b, const Instr& I, int t) {
 // fixed slot t = tid % T and i = tid / T + k * nthr / T (the T slots of one row
 // are adjacent in memory).
 RP_DEVNI void op_ld(const Program* __restrict__ pg, int pc) {
+  RP_MARK_INIT;
   const Blk b = make_blk(pg);
   const Instr I = pg->ins[pc];
   const int n = I.n, nz = (I.n2 > n && !(I.flags & LF_ACC)) ? I.n2 : n;
@@ -671,6 +703,7 @@ RP_DEVNI void op_ld(const Program* __restrict__ pg, int pc) {
   const long long ld = I.ld;
   const Lay L = I.lay;
   const bool ydir = (b.axis == AXIS_Y);
+  RP_MARK(40);
   const int nt = ydir ? b.T : 1;
   for (int tt = 0; tt < nt; ++tt) {
     const int t = ydir ? tt : (b.tid & (b.T - 1));
@@ -687,38 +720,45 @@ RP_DEVNI void op_ld(const Program* __restrict__ pg, int pc) {
     const long long sl = ydir ? ld : 1, si = ydir ? 1 : ld;
     const long long oa = (long long)s.la * sl, ob = (long long)s.lb * sl;
     cplx* const x = lane_ptr(b, I.r0, t);
-    cplx v[4];
-    batched<4>(
-        istart, istep, nz,
-        [&](int u, int i) {
-          cplx a = mk(0, 0);
-          if (i < n) {
-            if (isc) {
-              if (s.va) a = src[oa + i * si];
-            } else if (isb) {
-              if (s.va) {
-                const double d = srd[oa + i * si];
-                a = mk(d, d);
-              }
-            } else {
-              if (s.va) a.x = srd[oa + i * si];
-              if (s.vb) a.y = srd[ob + i * si];
+    for (int i0 = istart; i0 < nz; i0 += 4 * istep) {
+      cplx v[4], o[4];
+      RP_B4 {
+        const int i = i0 + u * istep;
+        cplx a = mk(0, 0);
+        if (i < n) {
+          if (isc) {
+            if (s.va) a = src[oa + i * si];
+          } else if (isb) {
+            if (s.va) {
+              const double d = srd[oa + i * si];
+              a = mk(d, d);
             }
+          } else {
+            if (s.va) a.x = srd[oa + i * si];
+            if (s.vb) a.y = srd[ob + i * si];
           }
-          v[u] = a;
-        },
-        [&](int u, int i) {
+          if (acc) o[u] = x[padi(slot_of(L, i))];
+        }
+        v[u] = a;
+      }
+      RP_B4 {
+        const int i = i0 + u * istep;
+        if (i < nz) {
           cplx a = v[u];
           a = mik ? mk(-kfac * a.y, kfac * a.x) : mk(a.x * ca, a.y * cb);
           cplx* px = x + padi(slot_of(L, i));
           if (acc) {
-            if (i < n) *px = cadd(*px, a);
+            if (i < n) *px = cadd(o[u], a);
           } else {
             *px = a;
           }
-        });
+        }
+      }
+    }
   }
+  RP_MARK(41);
   __syncthreads();
+  RP_MARK(42);
 }
 
 RP_DEVNI void op_st(const Program* __restrict__ pg, int pc) {
@@ -741,10 +781,13 @@ RP_DEVNI void op_st(const Program* __restrict__ pg, int pc) {
     const long long oa = (long long)s.la * sl, ob = (long long)s.lb * sl;
     const bool lcuta = cut && I.i1 >= 0 && s.la >= I.i1, lcutb = cut && I.i1 >= 0 && s.lb >= I.i1;
     const cplx* const x = lane_ptr(b, I.r0, t);
-    cplx v[4], old[4];
-    batched<4>(
-        istart, istep, n,
-        [&](int u, int i) {
+    const double s0 = I.s0;
+    const int cut_i = I.i0;
+    for (int i0 = istart; i0 < n; i0 += 4 * istep) {
+      cplx v[4], old[4];
+      RP_B4 {
+        const int i = i0 + u * istep;
+        if (i < n) {
           v[u] = x[padi(slot_of(L, i))];
           if (acc) {
             old[u] = mk(0, 0);
@@ -755,10 +798,13 @@ RP_DEVNI void op_st(const Program* __restrict__ pg, int pc) {
               if (s.vb) old[u].y = drd[ob + i * si];
             }
           }
-        },
-        [&](int u, int i) {
-          cplx a = cscale(v[u], I.s0);
-          const bool ecut = cut && i >= I.i0;
+        }
+      }
+      RP_B4 {
+        const int i = i0 + u * istep;
+        if (i < n) {
+          cplx a = cscale(v[u], s0);
+          const bool ecut = cut && i >= cut_i;
           if (ecut || lcuta) a.x = 0.0;
           if (ecut || lcutb) a.y = 0.0;
           if (isc && (ecut || lcuta)) a = mk(0, 0);
@@ -769,7 +815,9 @@ RP_DEVNI void op_st(const Program* __restrict__ pg, int pc) {
             if (s.va) drd[oa + i * si] = a.x;
             if (s.vb) drd[ob + i * si] = a.y;
           }
-        });
+        }
+      }
+    }
   }
   __syncthreads();
 }
@@ -784,30 +832,34 @@ RP_DEVNI void op_elem(const Program* __restrict__ pg, int pc, int mode) {
     cplx* const x0 = lane_ptr(b, I.r0, t);
     const cplx* const x1 = lane_ptr(b, I.r1, t);
     const cplx* const x2 = lane_ptr(b, I.r2, t);
-    cplx va[4], vb[4], vc[4];
-    batched<4>(
-        b.tid, b.nthr, n,
-        [&](int u, int i) {
+    const double s0 = I.s0;
+    const int cut_i = I.i0;
+    for (int i0 = b.tid; i0 < n; i0 += 4 * b.nthr) {
+      cplx va[4], vb[4], vc[4];
+      RP_B4 {
+        const int i = i0 + u * b.nthr;
+        if (i < n) {
           if (mode == 1 || mode == 2 || mode == 4) va[u] = x0[padi(slot_of(L0, i))];
           if (mode == 0 || mode == 1 || mode == 3 || mode == 4) vb[u] = x1[padi(slot_of(L1, i))];
           if (mode == 3 || mode == 4) vc[u] = x2[padi(slot_of(L1, i))];
-        },
-        [&](int u, int i) {
+        }
+      }
+      RP_B4 {
+        const int i = i0 + u * b.nthr;
+        if (i < n && !(mode == 6 && i < cut_i)) {
           cplx r;
           switch (mode) {
             case 0: r = vb[u]; break;
-            case 1: r = mk(fma(I.s0, vb[u].x, va[u].x), fma(I.s0, vb[u].y, va[u].y)); break;
-            case 2: r = cscale(va[u], I.s0); break;
+            case 1: r = mk(fma(s0, vb[u].x, va[u].x), fma(s0, vb[u].y, va[u].y)); break;
+            case 2: r = cscale(va[u], s0); break;
             case 3: r = pmul(vb[u], vc[u]); break;
             case 4: r = pfma(vb[u], vc[u], va[u]); break;
-            case 5: r = mk(0, 0); break;
-            default:
-              if (i < I.i0) return;
-              r = mk(0, 0);
-              break;
+            default: r = mk(0, 0); break;
           }
           x0[padi(slot_of(L0, i))] = r;
-        });
+        }
+      }
+    }
   }
   __syncthreads();
 }
@@ -1053,6 +1105,7 @@ RP_DEVNI void op_fdmamode(const Program* __restrict__ pg, int pc) {
 // Output layout: SPLIT(N).
 // ===========================================================================
 RP_DEVNI void op_dct(const Program* __restrict__ pg, int pc) {
+  RP_MARK_INIT;
   const Blk b = make_blk(pg);
   const Instr I = pg->ins[pc];
   const DctPlan P = *(const DctPlan*)I.p0;
@@ -1066,6 +1119,7 @@ RP_DEVNI void op_dct(const Program* __restrict__ pg, int pc) {
   const cplx* __restrict__ sctab = P.sc;
   const cplx* __restrict__ chirp = P.fft.chirp;
   const cplx* __restrict__ bhat = P.fft.bhat;
+  const int tid = b.tid, nthr = b.nthr;
   for (int g = 0; g < b.T; g += group) {
     const int ns = min(group, b.T - g);
     // ---- pre-combine, in place at the source slots (the first FFT pass
@@ -1075,15 +1129,23 @@ RP_DEVNI void op_dct(const Program* __restrict__ pg, int pc) {
       cplx* const x = lane_ptr(b, I.r0, t);
       cplx* const wbuf = b.wb + tt * b.wbP;
       cplx f1 = mk(0, 0);
-      cplx va[4], vc[4], vs[4];
-      batched<4>(
-          b.tid, b.nthr, npairs,
-          [&](int u, int j) {
+      for (int j0 = tid; j0 < npairs; j0 += 4 * nthr) {
+        cplx va[4], vc[4], vs[4], ca[4], cc[4];
+        RP_B4 {
+          const int j = j0 + u * nthr;
+          if (j < npairs) {
             va[u] = x[padi(slot_of(lin, j))];
             vc[u] = x[padi(slot_of(lin, N - j))];
             vs[u] = __ldg(&sctab[j]);
-          },
-          [&](int u, int j) {
+            if (!pow2) {
+              ca[u] = __ldg(&chirp[j]);
+              cc[u] = __ldg(&chirp[(N - j) % N]);
+            }
+          }
+        }
+        RP_B4 {
+          const int j = j0 + u * nthr;
+          if (j < npairs) {
             const int jm = N - j;
             cplx a = va[u], c = vc[u];
             if (backward) {  // c_k * (-1)^k / 2, ends doubled
@@ -1104,61 +1166,89 @@ RP_DEVNI void op_dct(const Program* __restrict__ pg, int pc) {
               x[padi(slot_of(lin, j))] = za;
               if (jm != j && j != 0) x[padi(slot_of(lin, jm))] = zb;
             } else {
-              wbuf[padi(j)] = cmul(za, __ldg(&chirp[j]));
-              if (jm != j && j != 0) wbuf[padi(jm)] = cmul(zb, __ldg(&chirp[jm]));
+              wbuf[padi(j)] = cmul(za, ca[u]);
+              if (jm != j && j != 0) wbuf[padi(jm)] = cmul(zb, cc[u]);
             }
-          });
+          }
+        }
+      }
       for (int o = 16; o > 0; o >>= 1) {
         f1.x += __shfl_down_sync(0xffffffffu, f1.x, o);
         f1.y += __shfl_down_sync(0xffffffffu, f1.y, o);
       }
-      if ((b.tid & 31) == 0) b.scr[t * 32 + (b.tid >> 5)] = f1;
+      if ((tid & 31) == 0) b.scr[t * 32 + (tid >> 5)] = f1;
     }
     __syncthreads();
+    RP_MARK(32);
     // ---- complex DFT of length N ----------------------------------------
     if (pow2) {
-      fft_run(b.tid, b.nthr, (I.r0 * b.T + g) * b.capP, b.capP, ns, N, P.fft.tw, false, 1.0, lin, true);
+      fft_run(tid, nthr, (I.r0 * b.T + g) * b.capP, b.capP, ns, N, P.fft.tw, false, 1.0, lin, true);
     } else {
       const int Lb = P.fft.Lb;
       for (int t = 0; t < ns; ++t) {
         cplx* w = b.wb + t * b.wbP;
-        for (int j = N + b.tid; j < Lb; j += b.nthr) w[padi(j)] = mk(0, 0);
+        for (int j = N + tid; j < Lb; j += nthr) w[padi(j)] = mk(0, 0);
       }
       __syncthreads();
       fft_run(b, b.wb_off, b.wbP, ns, Lb, P.fft.tw, false, 1.0);
       for (int t = 0; t < ns; ++t) {
         cplx* w = b.wb + t * b.wbP;
-        cplx v[4];
-        batched<4>(
-            b.tid, b.nthr, Lb, [&](int u, int j) { v[u] = cmul(w[padi(j)], __ldg(&bhat[j])); },
-            [&](int u, int j) { w[padi(j)] = v[u]; });
+        for (int j0 = tid; j0 < Lb; j0 += 4 * nthr) {
+          cplx v[4], c[4];
+          RP_B4 {
+            const int j = j0 + u * nthr;
+            if (j < Lb) {
+              v[u] = w[padi(j)];
+              c[u] = __ldg(&bhat[j]);
+            }
+          }
+          RP_B4 {
+            const int j = j0 + u * nthr;
+            if (j < Lb) w[padi(j)] = cmul(v[u], c[u]);
+          }
+        }
       }
       __syncthreads();
       fft_run(b, b.wb_off, b.wbP, ns, Lb, P.fft.tw, true, 1.0);
       for (int t = 0; t < ns; ++t) {
         const cplx* w = b.wb + t * b.wbP;
         cplx* x = lane_ptr(b, I.r0, g + t);
-        cplx v[4];
-        batched<4>(
-            b.tid, b.nthr, N, [&](int u, int j) { v[u] = cmul(w[padi(j)], __ldg(&chirp[j])); },
-            [&](int u, int j) { x[padi(j)] = v[u]; });
+        for (int j0 = tid; j0 < N; j0 += 4 * nthr) {
+          cplx v[4], c[4];
+          RP_B4 {
+            const int j = j0 + u * nthr;
+            if (j < N) {
+              v[u] = w[padi(j)];
+              c[u] = __ldg(&chirp[j]);
+            }
+          }
+          RP_B4 {
+            const int j = j0 + u * nthr;
+            if (j < N) x[padi(j)] = cmul(v[u], c[u]);
+          }
+        }
       }
       __syncthreads();
     }
   }
+  RP_MARK(33);
   // ---- recombine: X_{2k} = Z_k + Z_{N-k};  D_k = i (Z_k - Z_{N-k}) -------
   const double he = backward ? 1.0 : 1.0 / (double)N;  // even outputs: (+1)/N
   const int Ko = (N - 1) / 2;                           // odd outputs O_0..O_Ko
   for (int t = 0; t < b.T; ++t) {
     cplx* const x = lane_ptr(b, I.r0, t);
-    cplx vk[4], vm[4];
-    batched<4>(
-        b.tid, b.nthr, npairs,
-        [&](int u, int k) {
+    for (int k0 = tid; k0 < npairs; k0 += 4 * nthr) {
+      cplx vk[4], vm[4];
+      RP_B4 {
+        const int k = k0 + u * nthr;
+        if (k < npairs) {
           vk[u] = x[padi(k)];
-          vm[u] = (k == 0) ? vk[u] : x[padi(N - k)];
-        },
-        [&](int u, int k) {
+          vm[u] = x[padi(k == 0 ? 0 : N - k)];
+        }
+      }
+      RP_B4 {
+        const int k = k0 + u * nthr;
+        if (k < npairs) {
           const cplx zk = vk[u], zm = vm[u];
           double h = he;
           if (!backward && (k == 0 || 2 * k == N)) h *= 0.5;
@@ -1169,9 +1259,12 @@ RP_DEVNI void op_dct(const Program* __restrict__ pg, int pc) {
             for (int w = 0; w < nwarp; ++w) f1 = cadd(f1, b.scr[t * 32 + w]);
             x[padi(N)] = cscale(f1, 2.0);
           }
-        });
+        }
+      }
+    }
   }
   __syncthreads();
+  RP_MARK(34);
   // ---- odd outputs: prefix sum along slots N, N-1, ... -------------------
   Chains ch;
   ch.nch = 1;
@@ -1188,11 +1281,12 @@ RP_DEVNI void op_dct(const Program* __restrict__ pg, int pc) {
     cf.r = mk(0, 0);
     return cf;
   });
+  RP_MARK(35);
   if (!backward) {  // odd outputs: (-1)/N, last one halved when N is odd
     const double ho = -1.0 / (double)N;
     for (int t = 0; t < b.T; ++t) {
       cplx* const x = lane_ptr(b, I.r0, t);
-      for (int k = b.tid; k <= Ko; k += b.nthr) {
+      for (int k = tid; k <= Ko; k += nthr) {
         cplx* px = &x[padi(N - k)];
         *px = cscale(*px, (2 * k + 1 == N) ? 0.5 * ho : ho);
       }
@@ -1222,21 +1316,30 @@ RP_DEVNI void op_rfft(const Program* __restrict__ pg, int pc) {
   const bool va = ca < I.nlanes, vb = cb < I.nlanes;
   const cplx* const z = lane_ptr(b, I.r0, t);
   const bool cut = I.flags & LF_CUT;
-  cplx vk[4], vm[4];
-  batched<4>(
-      b.tid >> b.logT, b.nthr >> b.logT, m,
-      [&](int u, int k) {
+  const int cut_k = I.i0;
+  const double s0 = I.s0;
+  const int kstart = b.tid >> b.logT, kstep = b.nthr >> b.logT;
+  for (int k0 = kstart; k0 < m; k0 += 4 * kstep) {
+    cplx vk[4], vm[4];
+    RP_B4 {
+      const int k = k0 + u * kstep;
+      if (k < m) {
         vk[u] = z[padi(k)];
         vm[u] = z[padi(k == 0 ? 0 : n - k)];
-      },
-      [&](int u, int k) {
+      }
+    }
+    RP_B4 {
+      const int k = k0 + u * kstep;
+      if (k < m) {
         const cplx zk = vk[u], zm = cconj(vm[u]);
         const cplx s = cadd(zk, zm), d = csub(zk, zm);
-        double h = 0.5 * I.s0;
-        if (cut && k >= I.i0) h = 0.0;
+        double h = 0.5 * s0;
+        if (cut && k >= cut_k) h = 0.0;
         if (va) dst[k * ld + ca] = mk(h * s.x, h * s.y);
         if (vb) dst[k * ld + cb] = mk(h * d.y, -h * d.x);
-      });
+      }
+    }
+  }
   __syncthreads();
 }
 
@@ -1251,23 +1354,29 @@ RP_DEVNI void op_irfft(const Program* __restrict__ pg, int pc) {
   const int ca = 2 * (b.unit0 + t), cb = ca + 1;
   const bool va = ca < I.nlanes, vb = cb < I.nlanes;
   const bool mik = I.flags & LF_MULIK;
+  const double s0 = I.s0;
   cplx* const z = lane_ptr(b, I.r0, t);
-  cplx xa4[4], xb4[4];
-  batched<4>(
-      b.tid >> b.logT, b.nthr >> b.logT, m,
-      [&](int u, int k) {
+  const int kstart = b.tid >> b.logT, kstep = b.nthr >> b.logT;
+  for (int k0 = kstart; k0 < m; k0 += 4 * kstep) {
+    cplx xa4[4], xb4[4];
+    RP_B4 {
+      const int k = k0 + u * kstep;
+      if (k < m) {
         xa4[u] = va ? src[k * ld + ca] : mk(0, 0);
         xb4[u] = vb ? src[k * ld + cb] : mk(0, 0);
-      },
-      [&](int u, int k) {
+      }
+    }
+    RP_B4 {
+      const int k = k0 + u * kstep;
+      if (k < m) {
         cplx xa = xa4[u], xb = xb4[u];
         if (mik) {
-          const double kk = (double)k * I.s0;
+          const double kk = (double)k * s0;
           xa = mk(-kk * xa.y, kk * xa.x);
           xb = mk(-kk * xb.y, kk * xb.x);
         } else {
-          xa = cscale(xa, I.s0);
-          xb = cscale(xb, I.s0);
+          xa = cscale(xa, s0);
+          xb = cscale(xb, s0);
         }
         if (k == 0 || 2 * k == n) {
           xa.y = 0.0;
@@ -1275,7 +1384,9 @@ RP_DEVNI void op_irfft(const Program* __restrict__ pg, int pc) {
         }
         z[padi(k)] = mk(xa.x - xb.y, xa.y + xb.x);  // X_a + i X_b
         if (k > 0 && 2 * k != n) z[padi(n - k)] = mk(xa.x + xb.y, -xa.y + xb.x);  // conj(X_a) + i conj(X_b)
-      });
+      }
+    }
+  }
   __syncthreads();
   dft_any(b, I.r0 * b.T * b.capP, b.capP, b.T, P, true, 1.0 / (double)n);
 }

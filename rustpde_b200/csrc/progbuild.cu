@@ -34,6 +34,9 @@ void Built::dump_prof(const char* name) const {
   fprintf(stderr, "  [opprof] %-26s blocks %d thr %d smem %d: total %lld cyc:", name, nblocks, nthreads, smem, tot);
   for (int i = 0; i < 20; ++i)
     if (c[i]) fprintf(stderr, " %s=%.1f%%", names[i], 100.0 * c[i] / (double)tot);
+  if (c[32] + c[40])
+    fprintf(stderr, " | dct: pre=%lld fft=%lld recomb=%lld scan=%lld | ld: prologue=%lld loop=%lld bar=%lld", c[32], c[33], c[34],
+            c[35], c[40], c[41], c[42]);
   fprintf(stderr, "\n");
 }
 
