@@ -299,7 +299,7 @@ RP_DEVNI void fft_run(int tid, int nthr, int base_off, int stride, int nslots, i
                       double scale, Lay lin, bool use_lin) {
   int rem = L, Ns = 1;
   while (rem > 1) {
-    const int R = rem >= 16 ? 16 : rem;
+    const int R = rem >= 8 ? 8 : rem;  // radix 8: L/8 butterflies keep every thread busy at nthr = L/8
     const bool first = (Ns == 1), last = (rem == R);
     int K = (L / R) / nthr;  // butterflies per thread; R*K = L/nthr <= 16 when K > 1
     if (K < 1) K = 1;
@@ -420,53 +420,80 @@ RP_DEV void dft_any(const Blk& b, int base_off, int stride, int nslots, const Ff
 // by an inclusive warp scan (shuffles) and a short cross-warp fix-up through
 // shared memory, and the chunk is re-walked with its carry-in.
 // ===========================================================================
-struct Coef {
-  cplx s, p, r;
+// coefficient type CT: double (same coefficient for both packed components)
+// or cplx (componentwise, e.g. two real rows with different eigenvalues)
+RP_DEV cplx kmulv(double k, cplx v) { return mk(k * v.x, k * v.y); }
+RP_DEV cplx kmulv(cplx k, cplx v) { return pmul(k, v); }
+RP_DEV cplx kfmav(double k, cplx v, cplx c) { return mk(fma(k, v.x, c.x), fma(k, v.y, c.y)); }
+RP_DEV cplx kfmav(cplx k, cplx v, cplx c) { return pfma(k, v, c); }
+RP_DEV double kmul(double a, double b) { return a * b; }
+RP_DEV cplx kmul(cplx a, cplx b) { return pmul(a, b); }
+RP_DEV double kfma(double a, double b, double c) { return fma(a, b, c); }
+RP_DEV cplx kfma(cplx a, cplx b, cplx c) { return pfma(a, b, c); }
+template <class CT>
+RP_DEV CT kconst(double v);
+template <>
+RP_DEV double kconst<double>(double v) {
+  return v;
+}
+template <>
+RP_DEV cplx kconst<cplx>(double v) {
+  return mk(v, v);
+}
+RP_DEV double shfl_up_k(double v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
+RP_DEV cplx shfl_up_k(cplx v, int d) {
+  return mk(__shfl_up_sync(0xffffffffu, v.x, d), __shfl_up_sync(0xffffffffu, v.y, d));
+}
+
+template <class CT>
+struct CoefT {
+  CT s, p, r;
 };
 struct Chains {
   int nch;  // chains per slot (1 or 2)
   int c0[2], cs[2], M[2];
 };
-struct Aff {  // [y1; y2] -> A [y1; y2] + b, all entries componentwise
-  cplx a11, a12, a21, a22, b1, b2;
+template <class CT>
+struct AffT {  // [y1; y2] -> A [y1; y2] + b
+  CT a11, a12, a21, a22;
+  cplx b1, b2;
 };
-template <bool SECOND>
-RP_DEV Aff aff_combine(const Aff& p, const Aff& c) {  // apply p first, then c
-  Aff r;
+template <class CT, bool SECOND>
+RP_DEV AffT<CT> aff_combine(const AffT<CT>& p, const AffT<CT>& c) {  // apply p first, then c
+  AffT<CT> r;
   if (SECOND) {
-    r.a11 = pfma(c.a11, p.a11, pmul(c.a12, p.a21));
-    r.a12 = pfma(c.a11, p.a12, pmul(c.a12, p.a22));
-    r.a21 = pfma(c.a21, p.a11, pmul(c.a22, p.a21));
-    r.a22 = pfma(c.a21, p.a12, pmul(c.a22, p.a22));
-    r.b1 = pfma(c.a11, p.b1, pfma(c.a12, p.b2, c.b1));
-    r.b2 = pfma(c.a21, p.b1, pfma(c.a22, p.b2, c.b2));
+    r.a11 = kfma(c.a11, p.a11, kmul(c.a12, p.a21));
+    r.a12 = kfma(c.a11, p.a12, kmul(c.a12, p.a22));
+    r.a21 = kfma(c.a21, p.a11, kmul(c.a22, p.a21));
+    r.a22 = kfma(c.a21, p.a12, kmul(c.a22, p.a22));
+    r.b1 = kfmav(c.a11, p.b1, kfmav(c.a12, p.b2, c.b1));
+    r.b2 = kfmav(c.a21, p.b1, kfmav(c.a22, p.b2, c.b2));
   } else {
-    r.a11 = pmul(c.a11, p.a11);
-    r.b1 = pfma(c.a11, p.b1, c.b1);
-    r.a12 = r.a21 = r.a22 = r.b2 = mk(0, 0);
+    r.a11 = kmul(c.a11, p.a11);
+    r.b1 = kfmav(c.a11, p.b1, c.b1);
+    r.a12 = r.a21 = r.a22 = kconst<CT>(0.0);
+    r.b2 = mk(0, 0);
   }
   return r;
 }
-RP_DEV cplx shfl_up_c(cplx v, int d) {
-  return mk(__shfl_up_sync(0xffffffffu, v.x, d), __shfl_up_sync(0xffffffffu, v.y, d));
-}
-template <bool SECOND>
-RP_DEV Aff aff_shfl_up(const Aff& a, int d) {
-  Aff r;
-  r.a11 = shfl_up_c(a.a11, d);
-  r.b1 = shfl_up_c(a.b1, d);
+template <class CT, bool SECOND>
+RP_DEV AffT<CT> aff_shfl_up(const AffT<CT>& a, int d) {
+  AffT<CT> r;
+  r.a11 = shfl_up_k(a.a11, d);
+  r.b1 = shfl_up_k(a.b1, d);
   if (SECOND) {
-    r.a12 = shfl_up_c(a.a12, d);
-    r.a21 = shfl_up_c(a.a21, d);
-    r.a22 = shfl_up_c(a.a22, d);
-    r.b2 = shfl_up_c(a.b2, d);
+    r.a12 = shfl_up_k(a.a12, d);
+    r.a21 = shfl_up_k(a.a21, d);
+    r.a22 = shfl_up_k(a.a22, d);
+    r.b2 = shfl_up_k(a.b2, d);
   } else {
-    r.a12 = r.a21 = r.a22 = r.b2 = mk(0, 0);
+    r.a12 = r.a21 = r.a22 = kconst<CT>(0.0);
+    r.b2 = mk(0, 0);
   }
   return r;
 }
 
-template <bool SECOND, class F>
+template <class CT, bool SECOND, class F>
 RP_DEV void chain_solve(const Blk& b, int reg, const Chains& ch, bool fwd, F coef) {
   const int nchains = b.T * ch.nch;
   const int ltpc = ilog2(b.nthr) - ilog2(nchains);  // threads per chain (pow2, >= 32)
@@ -481,71 +508,77 @@ RP_DEV void chain_solve(const Blk& b, int reg, const Chains& ch, bool fwd, F coe
   cplx* const x = lane_ptr(b, reg, t);
   const int k0 = min(M, j * Cs), k1 = min(M, k0 + Cs);
   const int lane = b.tid & 31, wic = j >> 5, wpc = tpc >> 5;  // warp in chain, warps per chain
+  const CT one = kconst<CT>(1.0), zero = kconst<CT>(0.0);
   // ---- pass A: chunk map (zero-carry result and homogeneous responses) ----
-  cplx y1 = mk(0, 0), y2 = mk(0, 0), u1 = mk(1, 1), u2 = mk(0, 0), v1 = mk(0, 0), v2 = mk(1, 1);
-  for (int kb = k0; kb < k1; kb += 4) {
-    Coef cf[4];
-    cplx q[4];
+  cplx y1 = mk(0, 0), y2 = mk(0, 0);
+  CT u1 = one, u2 = zero, v1 = zero, v2 = one;
+  for (int kb = k0; kb < k1; kb += 2) {
+    CoefT<CT> cf[2];
+    cplx q[2];
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
+    for (int u = 0; u < 2; ++u)
       if (kb + u < k1) {
         const int m = fwd ? kb + u : M - 1 - (kb + u);
         cf[u] = coef(t, c, m);
         q[u] = x[padi(c0 + cs * m)];
       }
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
+    for (int u = 0; u < 2; ++u)
       if (kb + u < k1) {
         if (SECOND) {
-          const cplx y = pfma(cf[u].p, y1, pfma(cf[u].r, y2, pmul(cf[u].s, q[u])));
+          const cplx y = kfmav(cf[u].p, y1, kfmav(cf[u].r, y2, kmulv(cf[u].s, q[u])));
           y2 = y1;
           y1 = y;
-          const cplx uu = pfma(cf[u].p, u1, pmul(cf[u].r, u2));
+          const CT uu = kfma(cf[u].p, u1, kmul(cf[u].r, u2));
           u2 = u1;
           u1 = uu;
-          const cplx vv = pfma(cf[u].p, v1, pmul(cf[u].r, v2));
+          const CT vv = kfma(cf[u].p, v1, kmul(cf[u].r, v2));
           v2 = v1;
           v1 = vv;
         } else {
-          y1 = pfma(cf[u].p, y1, pmul(cf[u].s, q[u]));
-          u1 = pmul(cf[u].p, u1);
+          y1 = kfmav(cf[u].p, y1, kmulv(cf[u].s, q[u]));
+          u1 = kmul(cf[u].p, u1);
         }
       }
   }
-  Aff me;
-  me.a11 = u1;
-  me.b1 = y1;
+  AffT<CT> inc;
+  inc.a11 = u1;
+  inc.b1 = y1;
   if (SECOND) {
-    me.a12 = v1;
-    me.a21 = u2;
-    me.a22 = v2;
-    me.b2 = y2;
+    inc.a12 = v1;
+    inc.a21 = u2;
+    inc.a22 = v2;
+    inc.b2 = y2;
   } else {
-    me.a12 = me.a21 = me.a22 = me.b2 = mk(0, 0);
+    inc.a12 = inc.a21 = inc.a22 = zero;
+    inc.b2 = mk(0, 0);
   }
   // ---- inclusive warp scan of the chunk maps --------------------------------
-  Aff inc = me;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
-    const Aff prev = aff_shfl_up<SECOND>(inc, d);
-    if (lane >= d) inc = aff_combine<SECOND>(prev, inc);
+    const AffT<CT> prev = aff_shfl_up<CT, SECOND>(inc, d);
+    if (lane >= d) inc = aff_combine<CT, SECOND>(prev, inc);
   }
-  Aff exc = aff_shfl_up<SECOND>(inc, 1);  // map of the chunks before mine inside the warp
+  AffT<CT> exc = aff_shfl_up<CT, SECOND>(inc, 1);  // map of the chunks before mine inside the warp
   if (lane == 0) {
-    exc.a11 = mk(1, 1);
-    exc.a22 = mk(1, 1);
-    exc.a12 = exc.a21 = exc.b1 = exc.b2 = mk(0, 0);
+    exc.a11 = one;
+    exc.a22 = one;
+    exc.a12 = exc.a21 = zero;
+    exc.b1 = exc.b2 = mk(0, 0);
   }
   cplx ci1, ci2;  // carry-in: y_{k0-1}, y_{k0-2}
   if (wpc > 1) {
+    // warp totals through shared memory: 4 coefficient slots (as cplx) + 2 vectors
     cplx* tot = b.scr + (cid * wpc + wic) * 6;
     if (lane == 31) {
-      tot[0] = inc.a11;
-      tot[1] = inc.a12;
-      tot[2] = inc.a21;
-      tot[3] = inc.a22;
+      tot[0] = kmulv(inc.a11, mk(1, 1));
       tot[4] = inc.b1;
-      tot[5] = inc.b2;
+      if (SECOND) {
+        tot[1] = kmulv(inc.a12, mk(1, 1));
+        tot[2] = kmulv(inc.a21, mk(1, 1));
+        tot[3] = kmulv(inc.a22, mk(1, 1));
+        tot[5] = inc.b2;
+      }
     }
     __syncthreads();
     cplx p1 = mk(0, 0), p2 = mk(0, 0);  // state entering my warp
@@ -561,10 +594,10 @@ RP_DEV void chain_solve(const Blk& b, int reg, const Chains& ch, bool fwd, F coe
       }
     }
     if (SECOND) {
-      ci1 = pfma(exc.a11, p1, pfma(exc.a12, p2, exc.b1));
-      ci2 = pfma(exc.a21, p1, pfma(exc.a22, p2, exc.b2));
+      ci1 = kfmav(exc.a11, p1, kfmav(exc.a12, p2, exc.b1));
+      ci2 = kfmav(exc.a21, p1, kfmav(exc.a22, p2, exc.b2));
     } else {
-      ci1 = pfma(exc.a11, p1, exc.b1);
+      ci1 = kfmav(exc.a11, p1, exc.b1);
       ci2 = mk(0, 0);
     }
   } else {
@@ -574,31 +607,31 @@ RP_DEV void chain_solve(const Blk& b, int reg, const Chains& ch, bool fwd, F coe
   // ---- pass C: re-walk with the carry, in place ------------------------------
   y1 = ci1;
   y2 = ci2;
-  for (int kb = k0; kb < k1; kb += 4) {
-    Coef cf[4];
-    cplx q[4];
+  for (int kb = k0; kb < k1; kb += 2) {
+    CoefT<CT> cf[2];
+    cplx q[2];
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
+    for (int u = 0; u < 2; ++u)
       if (kb + u < k1) {
         const int m = fwd ? kb + u : M - 1 - (kb + u);
         cf[u] = coef(t, c, m);
         q[u] = x[padi(c0 + cs * m)];
       }
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
+    for (int u = 0; u < 2; ++u)
       if (kb + u < k1) {
         cplx y;
         if (SECOND) {
-          y = pfma(cf[u].p, y1, pfma(cf[u].r, y2, pmul(cf[u].s, q[u])));
+          y = kfmav(cf[u].p, y1, kfmav(cf[u].r, y2, kmulv(cf[u].s, q[u])));
           y2 = y1;
         } else {
-          y = pfma(cf[u].p, y1, pmul(cf[u].s, q[u]));
+          y = kfmav(cf[u].p, y1, kmulv(cf[u].s, q[u]));
         }
         y1 = y;
         q[u] = y;
       }
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
+    for (int u = 0; u < 2; ++u)
       if (kb + u < k1) {
         const int m = fwd ? kb + u : M - 1 - (kb + u);
         x[padi(c0 + cs * m)] = q[u];
@@ -928,22 +961,20 @@ RP_DEVNI void op_fromortho(const Program* __restrict__ pg, int pc) {
   const double* __restrict__ fs = tt.fs;
   const double* __restrict__ fp = tt.fp;
   const double* __restrict__ bp = tt.bp;
-  chain_solve<false>(b, I.r0, ch, true, [=](int, int c, int mm) -> Coef {
+  chain_solve<double, false>(b, I.r0, ch, true, [=](int, int c, int mm) -> CoefT<double> {
     const int i = 2 * mm + c;
-    const double s = __ldg(&fs[i]), p = __ldg(&fp[i]);
-    Coef cf;
-    cf.s = mk(s, s);
-    cf.p = mk(p, p);
-    cf.r = mk(0, 0);
+    CoefT<double> cf;
+    cf.s = __ldg(&fs[i]);
+    cf.p = __ldg(&fp[i]);
+    cf.r = 0.0;
     return cf;
   });
-  chain_solve<false>(b, I.r0, ch, false, [=](int, int c, int mm) -> Coef {
+  chain_solve<double, false>(b, I.r0, ch, false, [=](int, int c, int mm) -> CoefT<double> {
     const int i = 2 * mm + c;
-    const double p = __ldg(&bp[i]);
-    Coef cf;
-    cf.s = mk(1, 1);
-    cf.p = mk(p, p);
-    cf.r = mk(0, 0);
+    CoefT<double> cf;
+    cf.s = 1.0;
+    cf.p = __ldg(&bp[i]);
+    cf.r = 0.0;
     return cf;
   });
 }
@@ -975,12 +1006,11 @@ RP_DEVNI void op_diff(const Program* __restrict__ pg, int pc) {
   for (int rep = 0; rep < I.i0; ++rep) {
     const double sc = (rep == 0) ? I.s0 : 1.0;
     const Chains ch = chains_of(L, n);
-    chain_solve<false>(b, I.r0, ch, false, [=](int, int c, int mm) -> Coef {
-      const double s = 2.0 * (double)(2 * mm + c) * sc;
-      Coef cf;
-      cf.s = mk(s, s);
-      cf.p = mk(1, 1);
-      cf.r = mk(0, 0);
+    chain_solve<double, false>(b, I.r0, ch, false, [=](int, int c, int mm) -> CoefT<double> {
+      CoefT<double> cf;
+      cf.s = 2.0 * (double)(2 * mm + c) * sc;
+      cf.p = 1.0;
+      cf.r = 0.0;
       return cf;
     });
     const Lay Ln = lay_after_diff(L);
@@ -1005,22 +1035,20 @@ RP_DEVNI void op_fdma(const Program* __restrict__ pg, int pc) {
   const double* __restrict__ bs = ft.bs;
   const double* __restrict__ bp1 = ft.bp1;
   const double* __restrict__ bp2 = ft.bp2;
-  chain_solve<false>(b, I.r0, ch, true, [=](int, int c, int mm) -> Coef {
+  chain_solve<double, false>(b, I.r0, ch, true, [=](int, int c, int mm) -> CoefT<double> {
     const int i = 2 * mm + c;
-    const double p = __ldg(&fp[i]);
-    Coef cf;
-    cf.s = mk(1, 1);
-    cf.p = mk(p, p);
-    cf.r = mk(0, 0);
+    CoefT<double> cf;
+    cf.s = 1.0;
+    cf.p = __ldg(&fp[i]);
+    cf.r = 0.0;
     return cf;
   });
-  chain_solve<true>(b, I.r0, ch, false, [=](int, int c, int mm) -> Coef {
+  chain_solve<double, true>(b, I.r0, ch, false, [=](int, int c, int mm) -> CoefT<double> {
     const int i = 2 * mm + c;
-    const double s = __ldg(&bs[i]), p = __ldg(&bp1[i]), r = __ldg(&bp2[i]);
-    Coef cf;
-    cf.s = mk(s, s);
-    cf.p = mk(p, p);
-    cf.r = mk(r, r);
+    CoefT<double> cf;
+    cf.s = __ldg(&bs[i]);
+    cf.p = __ldg(&bp1[i]);
+    cf.r = __ldg(&bp2[i]);
     return cf;
   });
 }
@@ -1054,9 +1082,9 @@ RP_DEVNI void op_fdmamode(const Program* __restrict__ pg, int pc) {
     return mk(__ldg(&lam[la]) + alpha, __ldg(&lam[lb]) + alpha);
   };
   // forward: x_i -= l_{i-2} x_{i-2},  l_j = low_j / dia'_j
-  chain_solve<false>(b, I.r0, ch, true, [=](int t, int c, int mm) -> Coef {
+  chain_solve<cplx, false>(b, I.r0, ch, true, [=](int t, int c, int mm) -> CoefT<cplx> {
     const int i = 2 * mm + c;
-    Coef cf;
+    CoefT<cplx> cf;
     cf.s = mk(1, 1);
     cf.r = mk(0, 0);
     cf.p = mk(0, 0);
@@ -1069,7 +1097,7 @@ RP_DEVNI void op_fdmamode(const Program* __restrict__ pg, int pc) {
     return cf;
   });
   // backward: x_i = (x_i - up1'_i x_{i+2} - up2_i x_{i+4}) / dia'_i
-  chain_solve<true>(b, I.r0, ch, false, [=](int t, int c, int mm) -> Coef {
+  chain_solve<cplx, true>(b, I.r0, ch, false, [=](int t, int c, int mm) -> CoefT<cplx> {
     const int i = 2 * mm + c;
     const cplx mu = mu_of(t);
     const cplx inv = lane_ptr(b, r1, t)[padi(slot_of(L, i))];
@@ -1090,7 +1118,7 @@ RP_DEVNI void op_fdmamode(const Program* __restrict__ pg, int pc) {
       const double a = __ldg(&a_up2[i]), cc = __ldg(&c_up2[i]);
       u2 = mk(fma(mu.x, cc, a), fma(mu.y, cc, a));
     }
-    Coef cf;
+    CoefT<cplx> cf;
     cf.s = inv;
     cf.p = mk(-u1.x * inv.x, -u1.y * inv.y);
     cf.r = mk(-u2.x * inv.x, -u2.y * inv.y);
@@ -1274,11 +1302,11 @@ RP_DEVNI void op_dct(const Program* __restrict__ pg, int pc) {
   ch.c0[1] = 0;
   ch.cs[1] = 0;
   ch.M[1] = 0;
-  chain_solve<false>(b, I.r0, ch, true, [=](int, int, int) -> Coef {
-    Coef cf;
-    cf.s = mk(1, 1);
-    cf.p = mk(1, 1);
-    cf.r = mk(0, 0);
+  chain_solve<double, false>(b, I.r0, ch, true, [=](int, int, int) -> CoefT<double> {
+    CoefT<double> cf;
+    cf.s = 1.0;
+    cf.p = 1.0;
+    cf.r = 0.0;
     return cf;
   });
   RP_MARK(35);

@@ -362,7 +362,7 @@ Built ProgBuilder::build() {
   p.wb_cap = wbcap_;
   p.wb_T = bestWb;
   p.smem_bytes = bestSmem;
-  int nthr = std::max(64, pow2_ceil((fftlen_ + 15) / 16));
+  int nthr = std::min(512, std::max(64, pow2_ceil((fftlen_ + 7) / 8)));
   const int want = pow2_ceil(std::max(1, bestT * p.cap / 8));
   while (nthr < 256 && nthr < want) nthr <<= 1;
   while (nthr < 64 * bestT) nthr <<= 1;  // scans: >= one warp per parity chain
