@@ -503,8 +503,9 @@ RP_DEV void chain_solve(const Blk& b, int reg, const Chains& ch, bool fwd, F coe
   int Mmax = ch.M[0];
   if (ch.nch > 1 && ch.M[1] > Mmax) Mmax = ch.M[1];
   const int Cs = (Mmax + tpc - 1) >> ltpc;
-  const int M = ch.M[c];
-  const int c0 = ch.c0[c], cs = ch.cs[c];
+  // (ternaries, not ch.X[c]: a dynamically indexed struct array would live in local memory)
+  const int M = c ? ch.M[1] : ch.M[0];
+  const int c0 = c ? ch.c0[1] : ch.c0[0], cs = c ? ch.cs[1] : ch.cs[0];
   cplx* const x = lane_ptr(b, reg, t);
   const int k0 = min(M, j * Cs), k1 = min(M, k0 + Cs);
   const int lane = b.tid & 31, wic = j >> 5, wpc = tpc >> 5;  // warp in chain, warps per chain
