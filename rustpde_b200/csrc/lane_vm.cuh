@@ -22,7 +22,12 @@ namespace rp {
 
 typedef double2 cplx;
 #define RP_DEV __device__ __forceinline__
+#ifdef RP_INLINE_OPS
+#define RP_DEVNI __device__ __forceinline__
+#else
 #define RP_DEVNI __device__ __noinline__
+#endif
+#define RP_DEVCALL __device__ __noinline__
 
 RP_DEV cplx mk(double x, double y) { return make_double2(x, y); }
 RP_DEV cplx cadd(cplx a, cplx b) { return mk(a.x + b.x, a.y + b.y); }
@@ -208,7 +213,7 @@ RP_DEV void apply_twiddles(cplx* v, cplx w1) {
 // are scalars (offsets, not pointers).  All of L, R, K, Ns, nthr are powers of 2.
 enum { FF_CONJ_IN = 1, FF_CONJ_OUT = 2, FF_LIN = 4 };
 template <int R, int K>
-RP_DEVNI void fft_pass(int tid, int nthr, int base_off, int stride, int nslots, int L, int Ns,
+RP_DEVCALL void fft_pass(int tid, int nthr, int base_off, int stride, int nslots, int L, int Ns,
                        const cplx* __restrict__ tw, int fl, double oscale, Lay lin) {
   const int nb = L / R;
   const int per = nb / K, lper = ilog2(per);
@@ -295,7 +300,7 @@ RP_DEV void fft_pass_k(int tid, int nthr, int K, int base_off, int stride, int n
 // natural order in and out.  inverse: conj-in / conj-out around the forward kernel.
 // Requires nthr >= L/16 (host planner guarantees it).  use_lin: the first pass
 // reads element j from slot_of(lin, j) (absorbs an input permutation for free).
-RP_DEVNI void fft_run(int tid, int nthr, int base_off, int stride, int nslots, int L, const cplx* tw, bool inverse,
+RP_DEVCALL void fft_run(int tid, int nthr, int base_off, int stride, int nslots, int L, const cplx* tw, bool inverse,
                       double scale, Lay lin, bool use_lin) {
   int rem = L, Ns = 1;
   while (rem > 1) {

@@ -340,7 +340,11 @@ Built ProgBuilder::build() {
   const int candX[] = {4, 2, 1}, candY[] = {2, 1};
   const int* cand = (p.axis == AXIS_X) ? candX : candY;
   const int ncand = (p.axis == AXIS_X) ? 3 : 2;
-  const int soft = (p.axis == AXIS_Y) ? budget / 2 : budget;  // rows: leave room for 2 blocks per SM
+  // tuning knobs (development): RUSTPDE_B200_SOFT = soft smem budget fraction in percent for row programs,
+  // RUSTPDE_B200_TMULT = multiply the thread count by this factor
+  const char* e_soft = getenv("RUSTPDE_B200_SOFT");
+  const int soft_pct = e_soft ? atoi(e_soft) : 50;
+  const int soft = (p.axis == AXIS_Y) ? (int)((long long)budget * soft_pct / 100) : budget;  // rows: room for 2 blocks per SM
   for (int pass = 0; pass < 2 && !bestT; ++pass)
     for (int c = 0; c < ncand && !bestT; ++c) {
       const int T = cand[c];
@@ -365,6 +369,7 @@ Built ProgBuilder::build() {
   int nthr = std::min(512, std::max(64, pow2_ceil((fftlen_ + 7) / 8)));
   const int want = pow2_ceil(std::max(1, bestT * p.cap / 8));
   while (nthr < 256 && nthr < want) nthr <<= 1;
+  if (const char* e_tm = getenv("RUSTPDE_B200_TMULT")) nthr = std::min(512, nthr * atoi(e_tm));
   while (nthr < 64 * bestT) nthr <<= 1;  // scans: >= one warp per parity chain
   (void)nck;
   if (nthr > 512) throw Error(RP_ERR_SHAPE, "lane too long for a 512-thread block");
