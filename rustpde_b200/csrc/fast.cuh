@@ -1,0 +1,487 @@
+// fast.cuh -- device building blocks of the specialised Navier2D kernels
+// (fast_x.cu, fast_y.cu).
+//
+// A thread block owns a *tile* in shared memory: `rows` elements along the
+// transformed axis times 4 real lanes (4 adjacent columns for an x pass, 4
+// adjacent rows for a y pass).  The 4 lanes are the fastest dimension, i.e. the
+// tile is a `double[rows][4]` == `double2[rows][2]` array: two packed complex
+// lanes whose re/im parts are two independent real lanes.  Every operator on the
+// path is real-linear along the lane, so one complex FFT serves two real
+// DCT-I lanes (ortho.rs:337-407 via a real DFT of half length).
+//
+// Because the lanes are the fastest dimension, consecutive threads always touch
+// consecutive shared-memory words in every FFT pass; the only pattern that
+// would collide (first Stockham pass, output stride 8 rows) is removed by the
+// row swizzle prow().
+//
+// Sequential recurrences of the reference (Chebyshev derivative ortho.rs:107-125,
+// TDMA linalg.rs:14-57, FDMA fdma.rs:101-118) run as chunked scans: each thread
+// owns a chunk of one parity chain of one lane, caches it in registers, the
+// chunk maps are chained through a small shared array, and the chunk is
+// re-walked with its carry-in.
+#pragma once
+#include "fast.h"
+
+namespace rp {
+namespace fk {
+
+typedef double2 cplx;
+#define FK_DEV __device__ __forceinline__
+
+FK_DEV cplx mk(double x, double y) { return make_double2(x, y); }
+FK_DEV cplx cadd(cplx a, cplx b) { return mk(a.x + b.x, a.y + b.y); }
+FK_DEV cplx csub(cplx a, cplx b) { return mk(a.x - b.x, a.y - b.y); }
+FK_DEV cplx cmul(cplx a, cplx b) { return mk(fma(a.x, b.x, -a.y * b.y), fma(a.x, b.y, a.y * b.x)); }
+FK_DEV cplx csqr(cplx a) { return mk(fma(a.x, a.x, -a.y * a.y), 2.0 * a.x * a.y); }
+FK_DEV cplx cscale(cplx a, double s) { return mk(a.x * s, a.y * s); }
+
+// ---- tile addressing --------------------------------------------------------
+FK_DEV int prow(int i) { return i ^ ((i >> 3) & 3); }
+FK_DEV int didx(int i, int r) { return prow(i) * 4 + r; }  // as double
+FK_DEV int cidx(int i, int c) { return prow(i) * 2 + c; }  // as double2
+// layout of a lane inside a tile: natural (sn < 0: element i at row i) or
+// split(sn) (even i at row i/2, odd i at row sn - i/2), the output layout of the DCT
+FK_DEV int rowof(int sn, int i) { return sn < 0 ? i : ((i & 1) ? sn - (i >> 1) : (i >> 1)); }
+
+// ---- radix butterflies (forward, e^{-2 pi i / R}), in-order output ----------
+template <int R>
+struct Bfly;
+template <>
+struct Bfly<2> {
+  static FK_DEV void run(cplx* v) {
+    const cplx a = v[0], b = v[1];
+    v[0] = cadd(a, b);
+    v[1] = csub(a, b);
+  }
+};
+FK_DEV void dft4(cplx& x0, cplx& x1, cplx& x2, cplx& x3) {
+  const cplx s0 = cadd(x0, x2), d0 = csub(x0, x2), s1 = cadd(x1, x3), d1 = csub(x1, x3);
+  x0 = cadd(s0, s1);
+  x2 = csub(s0, s1);
+  x1 = mk(d0.x + d1.y, d0.y - d1.x);
+  x3 = mk(d0.x - d1.y, d0.y + d1.x);
+}
+template <>
+struct Bfly<4> {
+  static FK_DEV void run(cplx* v) { dft4(v[0], v[1], v[2], v[3]); }
+};
+template <>
+struct Bfly<8> {
+  static FK_DEV void run(cplx* v) {
+    dft4(v[0], v[2], v[4], v[6]);
+    dft4(v[1], v[3], v[5], v[7]);
+    const double h = 0.70710678118654752440;
+    const cplx b0 = v[1];
+    const cplx b1 = mk(h * (v[3].x + v[3].y), h * (v[3].y - v[3].x));
+    const cplx b2 = mk(v[5].y, -v[5].x);
+    const cplx b3 = mk(h * (v[7].y - v[7].x), -h * (v[7].x + v[7].y));
+    const cplx a0 = v[0], a1 = v[2], a2 = v[4], a3 = v[6];
+    v[0] = cadd(a0, b0);
+    v[4] = csub(a0, b0);
+    v[1] = cadd(a1, b1);
+    v[5] = csub(a1, b1);
+    v[2] = cadd(a2, b2);
+    v[6] = csub(a2, b2);
+    v[3] = cadd(a3, b3);
+    v[7] = csub(a3, b3);
+  }
+};
+
+// v[r] *= w^r from the single table value w (log-depth products)
+template <int R>
+FK_DEV void apply_twiddles(cplx* v, cplx w1) {
+  v[1] = cmul(v[1], w1);
+  if constexpr (R > 2) {
+    const cplx w2 = csqr(w1);
+    v[2] = cmul(v[2], w2);
+    const cplx w3 = cmul(w2, w1);
+    v[3] = cmul(v[3], w3);
+    if constexpr (R > 4) {
+      const cplx w4 = csqr(w2);
+      v[4] = cmul(v[4], w4);
+      v[5] = cmul(v[5], cmul(w4, w1));
+      v[6] = cmul(v[6], cmul(w4, w2));
+      v[7] = cmul(v[7], cmul(w4, w3));
+    }
+  }
+}
+
+// One in-place Stockham pass of radix R over both complex lanes of the tile.
+// L = 1 << LOG2L rows; tw[k] = exp(-2 pi i k / L).
+// MUL: the loaded values are first multiplied by mulv[row] (Bluestein filter).
+template <int LOG2L, int NTHR, int R, int NS, bool CONJ_IN, bool CONJ_OUT, bool MUL>
+FK_DEV void fft_pass(cplx* tc, const cplx* __restrict__ tw, const cplx* __restrict__ mulv) {
+  constexpr int L = 1 << LOG2L;
+  constexpr int NB = L / R;
+  constexpr int TOT = NB * 2;
+  constexpr int KB = (TOT + NTHR - 1) / NTHR;
+  const int tid = threadIdx.x;
+  cplx v[KB][R];
+#pragma unroll
+  for (int kb = 0; kb < KB; ++kb) {
+    const int b = tid + kb * NTHR;
+    if (TOT % NTHR == 0 || b < TOT) {
+      const int q = b >> 1, c = b & 1;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        cplx x = tc[cidx(q + r * NB, c)];
+        if (MUL) x = cmul(x, __ldg(&mulv[q + r * NB]));
+        if (CONJ_IN) x.y = -x.y;
+        v[kb][r] = x;
+      }
+      if (NS > 1) {
+        const int k = q & (NS - 1);
+        apply_twiddles<R>(v[kb], __ldg(&tw[k * (L / (NS * R))]));
+      }
+      Bfly<R>::run(v[kb]);
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int kb = 0; kb < KB; ++kb) {
+    const int b = tid + kb * NTHR;
+    if (TOT % NTHR == 0 || b < TOT) {
+      const int q = b >> 1, c = b & 1;
+      const int k = q & (NS - 1);
+      const int o = (q - k) * R + k;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        cplx x = v[kb][r];
+        if (CONJ_OUT) x.y = -x.y;
+        tc[cidx(o + r * NS, c)] = x;
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// Complex FFT of length L = 1 << LOG2L on rows [0, L) of the tile (both complex
+// lanes), natural order in and out, radix-8 passes plus one radix-2/4 pass.
+// INV: unnormalised inverse (conjugate in / out).  MUL: input multiplied by mulv[row].
+template <int LOG2L, int NTHR, int LOG2NS, bool INV, bool MUL>
+FK_DEV void fft_rec(cplx* tc, const cplx* __restrict__ tw, const cplx* __restrict__ mulv) {
+  constexpr int REM = LOG2L - LOG2NS;  // log2 of what is left
+  if constexpr (REM > 0) {
+    constexpr int LR = REM >= 3 ? 3 : REM;
+    constexpr bool first = (LOG2NS == 0), last = (REM == LR);
+    fft_pass<LOG2L, NTHR, (1 << LR), (1 << LOG2NS), INV && first, INV && last, MUL && first>(tc, tw, mulv);
+    fft_rec<LOG2L, NTHR, LOG2NS + LR, INV, MUL>(tc, tw, mulv);
+  }
+}
+template <int LOG2L, int NTHR, bool INV, bool MUL>
+FK_DEV void fft(cplx* tc, const cplx* __restrict__ tw, const cplx* __restrict__ mulv) {
+  fft_rec<LOG2L, NTHR, 0, INV, MUL>(tc, tw, mulv);
+}
+
+// pre-combine of one pair (j, N-j): Chebyshev scaling of the backward transform
+// (ortho.rs:398-404), reduction of the length-2N even DFT to a length-N real DFT.
+template <bool BWD>
+FK_DEV void precombine_pair(cplx a, cplx c, int j, int N, cplx sc, cplx& za, cplx& zb, cplx& f1) {
+  const int jm = N - j;
+  if (BWD) {  // c_k * (-1)^k / 2, ends doubled
+    double ga = (j & 1) ? -0.5 : 0.5, gc = (jm & 1) ? -0.5 : 0.5;
+    if (j == 0) ga *= 2.0;
+    if (jm == N) gc *= 2.0;
+    a = cscale(a, ga);
+    c = cscale(c, gc);
+  }
+  const cplx sum = cadd(a, c), dif = csub(a, c);
+  za = mk(fma(-sc.x, dif.x, 0.5 * sum.x), fma(-sc.x, dif.y, 0.5 * sum.y));
+  zb = mk(fma(sc.x, dif.x, 0.5 * sum.x), fma(sc.x, dif.y, 0.5 * sum.y));
+  const double w = (j == 0) ? 0.5 * sc.y : sc.y;
+  f1.x = fma(w, dif.x, f1.x);
+  f1.y = fma(w, dif.y, f1.y);
+}
+
+// per-complex-lane block reduction of f1 (threads with equal tid&1 share a lane)
+template <int NTHR>
+FK_DEV void reduce_f1(cplx f1, cplx* f1red) {
+#pragma unroll
+  for (int o = 2; o < 32; o <<= 1) {
+    f1.x += __shfl_xor_sync(0xffffffffu, f1.x, o);
+    f1.y += __shfl_xor_sync(0xffffffffu, f1.y, o);
+  }
+  const int tid = threadIdx.x;
+  if ((tid & 31) < 2) f1red[(tid >> 5) * 2 + (tid & 1)] = f1;
+}
+
+// recombine of one pair: X_{2k} = Z_k + Z_{N-k}, D_k = i (Z_k - Z_{N-k}); forward
+// scaling (-1)^k/(n-1), ends halved (ortho.rs:355-359)
+template <bool BWD>
+FK_DEV void recombine_pair(cplx zk, cplx zm, int k, int N, cplx& xe, cplx& dk) {
+  double h = BWD ? 1.0 : 1.0 / (double)N;
+  if (!BWD && (k == 0 || 2 * k == N)) h *= 0.5;
+  xe = cscale(cadd(zk, zm), h);
+  dk = mk(-(zk.y - zm.y), zk.x - zm.x);
+}
+
+// Odd outputs of the DCT: prefix sum along rows N, N-1, ..., N-Ko of the tile
+// (4 real lanes); forward transform: times -1/N, last one halved when N is odd.
+template <int NTHR, int CLR, bool BWD>
+FK_DEV void dct_odd_scan(double* td, int N, double* red) {
+  constexpr int NG = NTHR / 4;
+  const int tid = threadIdx.x, lane = tid & 3, g = tid >> 2;
+  const int M = (N - 1) / 2 + 1;  // Ko + 1
+  const int cl = (M + NG - 1) / NG;
+  const int t0 = g * cl, t1 = min(t0 + cl, M);
+  double q[CLR];
+  double s = 0.0;
+#pragma unroll
+  for (int u = 0; u < CLR; ++u) {
+    const int t = t0 + u;
+    if (t < t1) {
+      q[u] = td[didx(N - t, lane)];
+      s += q[u];
+    }
+  }
+  red[g * 4 + lane] = s;
+  __syncthreads();
+  double y = 0.0;
+  for (int gg = 0; gg < g; ++gg) y += red[gg * 4 + lane];
+  const double ho = BWD ? 1.0 : -1.0 / (double)N;
+#pragma unroll
+  for (int u = 0; u < CLR; ++u) {
+    const int t = t0 + u;
+    if (t < t1) {
+      y += q[u];
+      double o = y * ho;
+      if (!BWD && 2 * t + 1 == N) o *= 0.5;
+      td[didx(N - t, lane)] = o;
+    }
+  }
+  __syncthreads();
+}
+
+// DCT-I with the Chebyshev scaling, power-of-two N = 1 << LOG2L, in place on a
+// tile of n = N + 1 rows in natural layout.  Result in split(N) layout.
+template <int LOG2L, int NTHR, bool BWD>
+FK_DEV void dct_pow2(double* td, const DctTab& T, double* red) {
+  constexpr int N = 1 << LOG2L;
+  constexpr int NP = N / 2 + 1;
+  cplx* tc = (cplx*)td;
+  cplx* f1red = (cplx*)red;
+  const int tid = threadIdx.x, c = tid & 1;
+  cplx f1 = mk(0.0, 0.0);
+  for (int it = tid; it < NP * 2; it += NTHR) {
+    const int j = it >> 1, jm = N - j;
+    const cplx a = tc[cidx(j, c)], cc = tc[cidx(jm, c)];
+    cplx za, zb;
+    precombine_pair<BWD>(a, cc, j, N, __ldg(&T.sc[j]), za, zb, f1);
+    tc[cidx(j, c)] = za;
+    if (jm != j && j != 0) tc[cidx(jm, c)] = zb;
+  }
+  reduce_f1<NTHR>(f1, f1red);
+  __syncthreads();
+  fft<LOG2L, NTHR, false, false>(tc, T.tw, nullptr);
+  constexpr int Ko = (N - 1) / 2;
+  for (int it = tid; it < NP * 2; it += NTHR) {
+    const int k = it >> 1;
+    const cplx zk = tc[cidx(k, c)], zm = tc[cidx(k == 0 ? 0 : N - k, c)];
+    cplx xe, dk;
+    recombine_pair<BWD>(zk, zm, k, N, xe, dk);
+    tc[cidx(k, c)] = xe;
+    if (k >= 1 && k <= Ko) tc[cidx(N - k, c)] = dk;
+    if (k == 0) {
+      cplx s = mk(0.0, 0.0);
+      for (int w = 0; w < NTHR / 32; ++w) s = cadd(s, f1red[w * 2 + c]);
+      tc[cidx(N, c)] = cscale(s, 2.0);
+    }
+  }
+  __syncthreads();
+  dct_odd_scan<NTHR, (N / 2 + NTHR / 4 - 1) / (NTHR / 4), BWD>(td, N, red);
+}
+
+// DCT-I of arbitrary N = n - 1 through Bluestein (FFT length Lb = 1 << LOG2LB >=
+// 2N - 1): reads tile A (natural layout, n rows), result in tile W (Lb rows),
+// split(N) layout.  A is left untouched.
+template <int LOG2LB, int NTHR, bool BWD>
+FK_DEV void dct_bluestein(const double* ta, double* tw_, const DctTab& T, double* red) {
+  constexpr int LB = 1 << LOG2LB;
+  const int N = T.n - 1;
+  const int NP = N / 2 + 1;
+  const cplx* A = (const cplx*)ta;
+  cplx* W = (cplx*)tw_;
+  cplx* f1red = (cplx*)red;
+  const int tid = threadIdx.x, c = tid & 1;
+  cplx f1 = mk(0.0, 0.0);
+  for (int it = tid; it < NP * 2; it += NTHR) {
+    const int j = it >> 1, jm = N - j;
+    cplx za, zb;
+    precombine_pair<BWD>(A[cidx(j, c)], A[cidx(jm, c)], j, N, __ldg(&T.sc[j]), za, zb, f1);
+    W[cidx(j, c)] = cmul(za, __ldg(&T.chirp[j]));
+    if (jm != j && j != 0) W[cidx(jm, c)] = cmul(zb, __ldg(&T.chirp[jm]));
+  }
+  for (int it = 2 * N + tid; it < 2 * LB; it += NTHR) W[cidx(it >> 1, c)] = mk(0.0, 0.0);
+  reduce_f1<NTHR>(f1, f1red);
+  __syncthreads();
+  fft<LOG2LB, NTHR, false, false>(W, T.tw, nullptr);
+  fft<LOG2LB, NTHR, true, true>(W, T.tw, T.bhat);
+  const int Ko = (N - 1) / 2;
+  for (int it = tid; it < NP * 2; it += NTHR) {
+    const int k = it >> 1;
+    const cplx zk = cmul(W[cidx(k, c)], __ldg(&T.chirp[k]));
+    const cplx zm = (k == 0) ? zk : cmul(W[cidx(N - k, c)], __ldg(&T.chirp[N - k]));
+    cplx xe, dk;
+    recombine_pair<BWD>(zk, zm, k, N, xe, dk);
+    W[cidx(k, c)] = xe;
+    if (k >= 1 && k <= Ko) W[cidx(N - k, c)] = dk;
+    if (k == 0) {
+      cplx s = mk(0.0, 0.0);
+      for (int w = 0; w < NTHR / 32; ++w) s = cadd(s, f1red[w * 2 + c]);
+      W[cidx(N, c)] = cscale(s, 2.0);
+    }
+  }
+  __syncthreads();
+  dct_odd_scan<NTHR, (LB / 4 + NTHR / 4 - 1) / (NTHR / 4), BWD>(tw_, N, red);
+}
+
+// ---- chunked scans over the 8 parity chains of a tile ---------------------------
+// Dependency order t = 0..M-1 of the chain of parity p; element m = FWD ? t : M-1-t,
+// natural index i = 2m + p.
+//   y_t = in(i, lane) + c1(i, lane) * y_{t-1}
+// `out(i, lane, y)` is called after every input of the block has been read, so
+// it may overwrite the tile the inputs came from (any row).
+template <int NTHR, int CL, bool FWD, class In, class C1, class Out>
+FK_DEV void scan1(int n, double* red, In in, C1 c1, Out out) {
+  constexpr int NG = NTHR / 8;
+  const int tid = threadIdx.x, ch = tid & 7, g = tid >> 3;
+  const int lane = ch & 3, p = ch >> 2;
+  const int M = (n - p + 1) >> 1;
+  const int cl = (((n + 1) >> 1) + NG - 1) / NG;
+  const int t0 = g * cl, t1 = min(t0 + cl, M);
+  double q[CL];
+  double A = 1.0, b = 0.0;
+#pragma unroll
+  for (int u = 0; u < CL; ++u) {
+    const int t = t0 + u;
+    if (t < t1) {
+      const int i = 2 * (FWD ? t : M - 1 - t) + p;
+      q[u] = in(i, lane);
+      const double k = c1(i, lane);
+      b = fma(k, b, q[u]);
+      A *= k;
+    }
+  }
+  red[(g * 8 + ch) * 2] = A;
+  red[(g * 8 + ch) * 2 + 1] = b;
+  __syncthreads();
+  double y = 0.0;
+  for (int gg = 0; gg < g; ++gg) y = fma(red[(gg * 8 + ch) * 2], y, red[(gg * 8 + ch) * 2 + 1]);
+#pragma unroll
+  for (int u = 0; u < CL; ++u) {
+    const int t = t0 + u;
+    if (t < t1) {
+      const int i = 2 * (FWD ? t : M - 1 - t) + p;
+      y = fma(c1(i, lane), y, q[u]);
+      out(i, lane, y);
+    }
+  }
+  __syncthreads();
+}
+
+//   y_t = in(i, lane) + c1(i, lane) * y_{t-1} + c2(i, lane) * y_{t-2}
+template <int NTHR, int CL, bool FWD, class In, class C1, class C2, class Out>
+FK_DEV void scan2(int n, double* red, In in, C1 c1, C2 c2, Out out) {
+  constexpr int NG = NTHR / 8;
+  const int tid = threadIdx.x, ch = tid & 7, g = tid >> 3;
+  const int lane = ch & 3, p = ch >> 2;
+  const int M = (n - p + 1) >> 1;
+  const int cl = (((n + 1) >> 1) + NG - 1) / NG;
+  const int t0 = g * cl, t1 = min(t0 + cl, M);
+  double q[CL];
+  // particular solution and the two homogeneous ones, states (y_{t-1}, y_{t-2})
+  double p1 = 0.0, p2 = 0.0, a1 = 1.0, a2 = 0.0, b1 = 0.0, b2 = 1.0;
+#pragma unroll
+  for (int u = 0; u < CL; ++u) {
+    const int t = t0 + u;
+    if (t < t1) {
+      const int i = 2 * (FWD ? t : M - 1 - t) + p;
+      q[u] = in(i, lane);
+      const double k1 = c1(i, lane), k2 = c2(i, lane);
+      const double pn = fma(k1, p1, fma(k2, p2, q[u]));
+      const double an = fma(k1, a1, k2 * a2);
+      const double bn = fma(k1, b1, k2 * b2);
+      p2 = p1, p1 = pn;
+      a2 = a1, a1 = an;
+      b2 = b1, b1 = bn;
+    }
+  }
+  double* r = red + (g * 8 + ch) * 6;
+  r[0] = a1, r[1] = b1, r[2] = p1, r[3] = a2, r[4] = b2, r[5] = p2;
+  __syncthreads();
+  double y1 = 0.0, y2 = 0.0;
+  for (int gg = 0; gg < g; ++gg) {
+    const double* rr = red + (gg * 8 + ch) * 6;
+    const double n1 = fma(rr[0], y1, fma(rr[1], y2, rr[2]));
+    const double n2 = fma(rr[3], y1, fma(rr[4], y2, rr[5]));
+    y1 = n1, y2 = n2;
+  }
+#pragma unroll
+  for (int u = 0; u < CL; ++u) {
+    const int t = t0 + u;
+    if (t < t1) {
+      const int i = 2 * (FWD ? t : M - 1 - t) + p;
+      const double yn = fma(c1(i, lane), y1, fma(c2(i, lane), y2, q[u]));
+      y2 = y1, y1 = yn;
+      out(i, lane, yn);
+    }
+  }
+  __syncthreads();
+}
+
+// chunk length bound for a lane of n elements handled by NTHR threads
+constexpr int chunk_len(int n, int nthr) { return (((n + 1) / 2) + nthr / 8 - 1) / (nthr / 8); }
+
+// Chebyshev derivative (ortho.rs:107-125) of the lane held in tile `src`
+// (layout sn_s, n elements), times `sc`, written to tile `dst` (layout sn_d;
+// may alias src):  b_k = sum_{p > k, p - k odd} 2 p a_p  (k >= 1), b_0 = half of that.
+template <int NTHR, int CL>
+FK_DEV void cheb_diff(const double* src, int sn_s, double* dst, int sn_d, int n, double sc, double* red) {
+  scan1<NTHR, CL, false>(
+      n, red, [&](int i, int l) { return (2.0 * (double)i * sc) * src[didx(rowof(sn_s, i), l)]; },
+      [](int, int) { return 1.0; },
+      [&](int i, int l, double y) {
+        if (i >= 1) dst[didx(rowof(sn_d, i - 1), l)] = (i == 1) ? 0.5 * y : y;
+        if (i == n - 1) dst[didx(rowof(sn_d, n - 1), l)] = 0.0;
+      });
+}
+
+// HholtzAdi half step along the tile axis (hholtz_adi.rs:108-129): B2 matvec
+// (n -> m = n-2) fused into the forward sweep, then the backward sweep
+// (fdma.rs:101-118).  In place on tile t (layout sn); result elements 0..m-1.
+template <int NTHR, int CL>
+FK_DEV void b2_fdma(double* t, int sn, int n, const B2Tabs& B, const FdmaTabs& F, double* red) {
+  const int m = n - 2;
+  scan1<NTHR, CL, true>(
+      m, red,
+      [&](int i, int l) {
+        return fma(__ldg(&B.lo[i]), t[didx(rowof(sn, i), l)],
+                   fma(__ldg(&B.di[i]), t[didx(rowof(sn, i + 2), l)],
+                       (i + 4 < n) ? __ldg(&B.up[i]) * t[didx(rowof(sn, i + 4), l)] : 0.0));
+      },
+      [&](int i, int) { return __ldg(&F.fp[i]); }, [&](int i, int l, double y) { t[didx(rowof(sn, i), l)] = y; });
+  scan2<NTHR, CL, false>(
+      m, red, [&](int i, int l) { return __ldg(&F.bs[i]) * t[didx(rowof(sn, i), l)]; },
+      [&](int i, int) { return __ldg(&F.bp1[i]); }, [&](int i, int) { return __ldg(&F.bp2[i]); },
+      [&](int i, int l, double y) { t[didx(rowof(sn, i), l)] = y; });
+}
+
+// from_ortho (composite_stencil.rs:250-276): c = S^T p, then the (S^T S) solve.
+// In place on tile t (layout sn): n ortho coefficients -> m = n-2 composite ones.
+template <int NTHR, int CL>
+FK_DEV void from_ortho(double* t, int sn, int n, const TdmaTabs& T, double* red) {
+  const int m = n - 2;
+  scan1<NTHR, CL, true>(
+      m, red,
+      [&](int i, int l) {
+        const double c = fma(__ldg(&T.sd[i]), t[didx(rowof(sn, i), l)], __ldg(&T.sl[i]) * t[didx(rowof(sn, i + 2), l)]);
+        return __ldg(&T.fs[i]) * c;
+      },
+      [&](int i, int) { return __ldg(&T.fp[i]); }, [&](int i, int l, double y) { t[didx(rowof(sn, i), l)] = y; });
+  scan1<NTHR, CL, false>(
+      m, red, [&](int i, int l) { return t[didx(rowof(sn, i), l)]; }, [&](int i, int) { return __ldg(&T.bp[i]); },
+      [&](int i, int l, double y) { t[didx(rowof(sn, i), l)] = y; });
+}
+
+}  // namespace fk
+}  // namespace rp

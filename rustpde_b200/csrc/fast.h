@@ -1,0 +1,158 @@
+// fast.h -- host interface of the specialised Navier2D kernels (fast_y.cu, fast_x.cu).
+//
+// "y kernels" own 4 adjacent rows of a row-major [n0, n1] array (lanes are
+// contiguous in memory), "x kernels" own 4 adjacent columns (lanes are strided).
+// Supported sizes: y lanes of n1 = 2^k + 1 points (DCT-I through a power-of-two
+// FFT), x lanes of any n0 whose Bluestein length 2^k >= 2 (n0 - 1) - 1 is
+// instantiated.  Everything else stays on the generic lane programs.
+#pragma once
+#include "lane_prog.h"
+
+namespace rp {
+namespace fk {
+
+struct Mat {  // pitched real matrix in global memory
+  double* p;
+  long long ld;
+  int rows, cols;
+};
+
+struct DctTab {
+  int n;                 // lane length, N = n - 1
+  const double2* sc;     // (sin, cos)(pi j / N), j = 0..N/2
+  const double2* tw;     // exp(-2 pi i k / L), L = N (pow2) or Lb (Bluestein)
+  const double2* chirp;  // Bluestein: exp(-i pi j^2 / N), j < N
+  const double2* bhat;   // Bluestein: FFT_Lb(wrapped conj chirp) / Lb
+};
+struct FdmaTabs {  // pre-swept banded solve (tables.h FdmaDev)
+  const double *fp, *bs, *bp1, *bp2;
+};
+struct B2Tabs {  // B2 preconditioner rows (matvec.rs:172-193)
+  const double *lo, *di, *up;
+};
+struct TdmaTabs {  // from_ortho: S^T then the pre-factored (S^T S) solve
+  const double *sd, *sl, *fs, *fp, *bp;
+};
+struct ModeTabs {  // per-lane A + (lam + alpha) C (fdma_tensor.rs:219-227)
+  const double *a_low, *a_up1, *a_up2, *c_low, *c_up1, *c_up2;
+  const double* lam;
+  double alpha;
+  const double* inv;  // swept pivot reciprocals, [lanes][inv_ld]
+  long long inv_ld;
+};
+
+bool y_supported(int n1);
+bool x_supported(int n0);
+
+// ---- y kernels ------------------------------------------------------------------
+struct YBackwardArgs {  // B_y S_y (value), B_y D_y S_y / sy, and B_y S_y of a second array
+  Mat a, adx;           // [rows, my]
+  Mat val, dy, dx;      // [rows, ny]; val.p may be null
+  const double *sd, *sl;
+  double isy;
+  DctTab t;
+};
+void launch_y_backward(const YBackwardArgs& a, cudaStream_t s);
+
+struct YConvArgs {  // out = cut_y(F_y(u * (du + bcx) + v * (dv + bcy)))   (conv_term.rs:41)
+  Mat u, du, v, dv, bcx, bcy;  // bcx/bcy.p may be null
+  Mat out;
+  int cut;  // first zeroed y mode (navier.rs:1029), >= ny: none
+  DctTab t;
+};
+void launch_y_conv(const YConvArgs& a, cudaStream_t s);
+
+struct YAdiArgs {  // y half of HholtzAdi (hholtz_adi.rs:113,129) + pieces of the divergence
+  Mat w;           // [mx, ny]
+  Mat out;         // [mx, my]
+  Mat aux;         // mode 1: S_y out  [mx, ny];  mode 2: D_y S_y out / sy
+  int mode;
+  const double *sd, *sl;
+  double isy;
+  B2Tabs b2;
+  FdmaTabs f;
+  int ny;
+};
+void launch_y_adi(const YAdiArgs& a, cudaStream_t s);
+
+struct YModeArgs {  // per-mode banded solve of the fast diagonalisation (fdma_tensor.rs:219-227)
+  Mat g;            // [mx, ny]
+  Mat h;            // [mx, my]
+  B2Tabs b2;
+  ModeTabs m;
+  int ny;
+};
+void launch_y_mode(const YModeArgs& a, cudaStream_t s);
+
+struct YProjectArgs {  // u -= from_ortho(grad phi), y part (navier.rs:683-695)
+  Mat a1, a2;          // [mx, my]: from_ortho_x(D_x S_x phi)/sx, from_ortho_x(S_x phi)
+  Mat ux, uy;          // [mx, my], updated in place
+  const double *nsd, *nsl;  // Neumann stencil of phi along y
+  TdmaTabs t;          // Dirichlet from_ortho along y
+  double isy;
+  int ny;
+};
+void launch_y_project(const YProjectArgs& a, cudaStream_t s);
+
+struct YPresArgs {  // p += -nu div + to_ortho(phi)/dt (navier.rs:717-721); dyp = D_y p / sy
+  Mat phi;          // [mx, my] Neumann composite
+  Mat div, pres, dyp;  // [nx, ny]
+  const double *xsd, *xsl;  // Neumann stencil along x (across lanes)
+  const double *ysd, *ysl;  // Neumann stencil along y
+  double inv_dt, nu, isy;
+  int ny;
+};
+void launch_y_pres(const YPresArgs& a, cudaStream_t s);
+
+// ---- x kernels ------------------------------------------------------------------
+struct XBackwardArgs {  // B_x S_x u^ and B_x D_x S_x u^ / sx
+  Mat src;              // [mx, cols]
+  Mat val, dx;          // [nx, cols]
+  const double *sd, *sl;
+  double isx;
+  DctTab t;
+};
+void launch_x_backward(const XBackwardArgs& a, cudaStream_t s);
+
+struct XForwardArgs {  // forward DCT-x + dealias + rhs assembly + x half of HholtzAdi
+  Mat conv;            // [nx, ny] after the y-forward transform
+  Mat out;             // [mx, ny]
+  int cut;             // first zeroed x mode
+  double dt;
+  // + S_x S_y u^_f
+  Mat fld;             // [mx, my]
+  const double *fxsd, *fxsl, *fysd, *fysl;
+  // mode 0: - dt/sx D_x pres ; 1: - dt dyp + dt (S_x S_y T^ + tbc) ; 2: + bcdiff
+  int mode;
+  Mat pres, dyp, tmp, tbc, bcdiff;
+  const double *txsd, *txsl, *tysd, *tysl;
+  double isx;
+  B2Tabs b2;
+  FdmaTabs f;
+  DctTab t;
+};
+void launch_x_forward(const XForwardArgs& a, cudaStream_t s);
+
+struct XDivArgs {  // div = D_x S_x vx / sx + S_x ey ; r1 = B2_x div
+  Mat vx, ey;      // [mx, ny]
+  Mat div;         // [nx, ny]
+  Mat r1;          // [mx, ny]
+  const double *sd, *sl;
+  double isx;
+  B2Tabs b2;
+  int nx;
+};
+void launch_x_div(const XDivArgs& a, cudaStream_t s);
+
+struct XProjectArgs {  // a1 = from_ortho_x(D_x S_x phi)/sx, a2 = from_ortho_x(S_x phi)
+  Mat phi;             // [mx, my]
+  Mat a1, a2;          // [mx, my]
+  const double *nsd, *nsl;  // Neumann stencil along x
+  TdmaTabs t;               // Dirichlet from_ortho along x
+  double isx;
+  int nx;
+};
+void launch_x_project(const XProjectArgs& a, cudaStream_t s);
+
+}  // namespace fk
+}  // namespace rp

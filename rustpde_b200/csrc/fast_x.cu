@@ -1,0 +1,242 @@
+// fast_x.cu -- specialised x-pass kernels of the confined Navier2D::update (lanes
+// strided in memory; a block owns 4 adjacent columns).  The x axis of the
+// confined configurations has n0 = 2^k points, i.e. an odd DCT-I period, so the
+// DCT goes through Bluestein with a power-of-two FFT (fast.cuh dct_bluestein).
+//
+//   xk_backward : B_x S_x u^ and B_x D_x S_x u^ / sx       (composite.rs:480-506, ortho.rs:107-125)
+//   xk_forward  : forward DCT-x + dealias (navier.rs:1022-1032) + rhs assembly
+//                 (navier.rs:622-674) + x half of HholtzAdi (hholtz_adi.rs:108,128)
+//   xk_div      : divergence (navier.rs:698-703) + B2_x of the Poisson rhs
+//   xk_project  : x part of u -= from_ortho(grad phi) (navier.rs:683-695)
+#include "fast.cuh"
+
+namespace rp {
+namespace fk {
+
+template <int LOG2LB>
+struct XCfg {
+  static constexpr int LB = 1 << LOG2LB;
+  static constexpr int NMAX = LB / 2 + 1;  // 2 (n - 1) - 1 <= LB
+  static constexpr int NTHR = (LB / 8) < 64 ? 64 : (LB / 8);
+  static constexpr int AROWS = LB / 2 + 4;
+  static constexpr int CL = chunk_len(NMAX, NTHR);
+  static constexpr int SMEM_A = AROWS * 32 + NTHR * 48;
+  static constexpr int SMEM_AW = (AROWS + LB) * 32 + NTHR * 48;
+};
+
+template <int NTHR, class F>
+FK_DEV void xtile_fill(double* td, int nfill, F f) {
+  for (int it = threadIdx.x; it < nfill * 4; it += NTHR) {
+    const int lane = it & 3, i = it >> 2;
+    td[didx(i, lane)] = f(i, lane);
+  }
+}
+
+// composite -> ortho stencil along x applied while loading column c of `a`
+// (m = n-2 rows): p_i = d_i c_i + l_{i-2} c_{i-2}   (composite_stencil.rs:207-229)
+FK_DEV double ld_stencil_x(const Mat& a, int i, int c, const double* __restrict__ sd, const double* __restrict__ sl) {
+  if (c >= a.cols) return 0.0;
+  double v = 0.0;
+  if (i < a.rows) v = __ldg(&sd[i]) * a.p[(size_t)i * a.ld + c];
+  if (i >= 2) v = fma(__ldg(&sl[i - 2]), a.p[(size_t)(i - 2) * a.ld + c], v);
+  return v;
+}
+// S_x S_y f at ortho index (i, j); f is [mx, my]
+FK_DEV double ld_stencil_xy(const Mat& f, int i, int j, const double* __restrict__ xsd, const double* __restrict__ xsl,
+                            const double* __restrict__ ysd, const double* __restrict__ ysl) {
+  auto ty = [&](int ii) {
+    const double* row = f.p + (size_t)ii * f.ld;
+    double v = 0.0;
+    if (j < f.cols) v = __ldg(&ysd[j]) * row[j];
+    if (j >= 2) v = fma(__ldg(&ysl[j - 2]), row[j - 2], v);
+    return v;
+  };
+  double p = 0.0;
+  if (i < f.rows) p = __ldg(&xsd[i]) * ty(i);
+  if (i >= 2) p = fma(__ldg(&xsl[i - 2]), ty(i - 2), p);
+  return p;
+}
+
+// ---------------------------------------------------------------------------------
+template <int LOG2LB>
+__global__ void __launch_bounds__(XCfg<LOG2LB>::NTHR, 1) xk_backward(XBackwardArgs a) {
+  typedef XCfg<LOG2LB> C;
+  RP_DYN_SMEM(double, ta);
+  double* tw = ta + C::AROWS * 4;
+  double* red = tw + C::LB * 4;
+  const int c0 = blockIdx.x * 4;
+  const int n = a.t.n, N = n - 1;
+  xtile_fill<C::NTHR>(ta, n, [&](int i, int l) { return ld_stencil_x(a.src, i, c0 + l, a.sd, a.sl); });
+  __syncthreads();
+  for (int pass = 0; pass < 2; ++pass) {
+    const Mat& o = pass ? a.dx : a.val;
+    if (pass) cheb_diff<C::NTHR, C::CL>(ta, -1, ta, -1, n, a.isx, red);
+    dct_bluestein<LOG2LB, C::NTHR, true>(ta, tw, a.t, red);
+    for (int it = threadIdx.x; it < n * 4; it += C::NTHR) {
+      const int l = it & 3, i = it >> 2;
+      if (c0 + l < o.cols) o.p[(size_t)i * o.ld + c0 + l] = tw[didx(rowof(N, i), l)];
+    }
+    __syncthreads();
+  }
+}
+
+template <int LOG2LB>
+__global__ void __launch_bounds__(XCfg<LOG2LB>::NTHR, 1) xk_forward(XForwardArgs a) {
+  typedef XCfg<LOG2LB> C;
+  RP_DYN_SMEM(double, ta);
+  double* tw = ta + C::AROWS * 4;
+  double* red = tw + C::LB * 4;
+  const int c0 = blockIdx.x * 4;
+  const int n = a.t.n, N = n - 1;
+  const int ncols = a.conv.cols;
+  xtile_fill<C::NTHR>(ta, n, [&](int i, int l) { return c0 + l < ncols ? a.conv.p[(size_t)i * a.conv.ld + c0 + l] : 0.0; });
+  __syncthreads();
+  dct_bluestein<LOG2LB, C::NTHR, false>(ta, tw, a.t, red);
+  if (a.mode == 0) {  // - dt/sx d/dx pres   (navier.rs:627)
+    xtile_fill<C::NTHR>(ta, n, [&](int i, int l) { return c0 + l < ncols ? a.pres.p[(size_t)i * a.pres.ld + c0 + l] : 0.0; });
+    __syncthreads();
+    cheb_diff<C::NTHR, C::CL>(ta, -1, ta, -1, n, -a.dt * a.isx, red);
+  }
+  for (int it = threadIdx.x; it < n * 4; it += C::NTHR) {
+    const int l = it & 3, i = it >> 2, j = c0 + l;
+    double* w = &tw[didx(rowof(N, i), l)];
+    double v = (i < a.cut) ? -a.dt * (*w) : 0.0;  // - dt * dealiased conv   (navier.rs:630, 651, 671)
+    if (j < ncols) {
+      v += ld_stencil_xy(a.fld, i, j, a.fxsd, a.fxsl, a.fysd, a.fysl);  // + to_ortho(field)
+      if (a.mode == 0) {
+        v += ta[didx(i, l)];
+      } else if (a.mode == 1) {  // - dt/sy d/dy pres + dt * (that + tbc)   (navier.rs:646-648)
+        v = fma(-a.dt, a.dyp.p[(size_t)i * a.dyp.ld + j], v);
+        const double that = ld_stencil_xy(a.tmp, i, j, a.txsd, a.txsl, a.tysd, a.tysl) + a.tbc.p[(size_t)i * a.tbc.ld + j];
+        v = fma(a.dt, that, v);
+      } else {  // + dt ka (dxx + dyy) fieldbc   (navier.rs:665-668)
+        v += a.bcdiff.p[(size_t)i * a.bcdiff.ld + j];
+      }
+    }
+    *w = v;
+  }
+  __syncthreads();
+  b2_fdma<C::NTHR, C::CL>(tw, N, n, a.b2, a.f, red);
+  const int m = n - 2;
+  for (int it = threadIdx.x; it < m * 4; it += C::NTHR) {
+    const int l = it & 3, i = it >> 2;
+    if (c0 + l < ncols) a.out.p[(size_t)i * a.out.ld + c0 + l] = tw[didx(rowof(N, i), l)];
+  }
+}
+
+template <int LOG2LB>
+__global__ void __launch_bounds__(XCfg<LOG2LB>::NTHR, 1) xk_div(XDivArgs a) {
+  typedef XCfg<LOG2LB> C;
+  RP_DYN_SMEM(double, ta);
+  double* red = ta + C::AROWS * 4;
+  const int c0 = blockIdx.x * 4;
+  const int n = a.nx, m = n - 2;
+  const int ncols = a.vx.cols;
+  xtile_fill<C::NTHR>(ta, n, [&](int i, int l) { return ld_stencil_x(a.vx, i, c0 + l, a.sd, a.sl); });
+  __syncthreads();
+  cheb_diff<C::NTHR, C::CL>(ta, -1, ta, -1, n, a.isx, red);
+  for (int it = threadIdx.x; it < n * 4; it += C::NTHR) {
+    const int l = it & 3, i = it >> 2;
+    const double v = ta[didx(i, l)] + ld_stencil_x(a.ey, i, c0 + l, a.sd, a.sl);
+    ta[didx(i, l)] = v;
+    if (c0 + l < ncols) a.div.p[(size_t)i * a.div.ld + c0 + l] = v;
+  }
+  __syncthreads();
+  for (int it = threadIdx.x; it < m * 4; it += C::NTHR) {
+    const int l = it & 3, i = it >> 2;
+    const double v = fma(__ldg(&a.b2.lo[i]), ta[didx(i, l)],
+                         fma(__ldg(&a.b2.di[i]), ta[didx(i + 2, l)], (i + 4 < n) ? __ldg(&a.b2.up[i]) * ta[didx(i + 4, l)] : 0.0));
+    if (c0 + l < ncols) a.r1.p[(size_t)i * a.r1.ld + c0 + l] = v;
+  }
+}
+
+template <int LOG2LB>
+__global__ void __launch_bounds__(XCfg<LOG2LB>::NTHR, 1) xk_project(XProjectArgs a) {
+  typedef XCfg<LOG2LB> C;
+  RP_DYN_SMEM(double, ta);
+  double* tb = ta + C::AROWS * 4;
+  double* red = tb + C::AROWS * 4;
+  const int c0 = blockIdx.x * 4;
+  const int n = a.nx, m = n - 2;
+  const int ncols = a.phi.cols;
+  xtile_fill<C::NTHR>(ta, n, [&](int i, int l) { return ld_stencil_x(a.phi, i, c0 + l, a.nsd, a.nsl); });
+  __syncthreads();
+  cheb_diff<C::NTHR, C::CL>(ta, -1, tb, -1, n, a.isx, red);
+  from_ortho<C::NTHR, C::CL>(tb, -1, n, a.t, red);
+  from_ortho<C::NTHR, C::CL>(ta, -1, n, a.t, red);
+  for (int it = threadIdx.x; it < m * 4; it += C::NTHR) {
+    const int l = it & 3, i = it >> 2;
+    if (c0 + l < ncols) {
+      a.a1.p[(size_t)i * a.a1.ld + c0 + l] = tb[didx(i, l)];
+      a.a2.p[(size_t)i * a.a2.ld + c0 + l] = ta[didx(i, l)];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------
+#define XK_SIZES(X) X(6) X(7) X(11) X(12)
+
+static int bluestein_log2(int n0) {  // tables.cu: Lb = next_pow2(2N - 1)
+  const int need = 2 * (n0 - 1) - 1;
+  int l = 0;
+  while ((1 << l) < need) ++l;
+  return l;
+}
+
+bool x_supported(int n0) {
+  if (n0 < 8) return false;
+  const int N = n0 - 1;
+  if ((N & (N - 1)) == 0) return false;  // power-of-two period: the tables hold no chirp
+  const int l = bluestein_log2(n0);
+#define X(L) \
+  if (l == L) return true;
+  XK_SIZES(X)
+#undef X
+  return false;
+}
+
+template <class K>
+static void set_smem(K kern, int bytes) {
+#ifndef RP_EMU
+  RP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+#else
+  (void)kern;
+  (void)bytes;
+#endif
+}
+
+#define XK_CASE_BODY(kern, L, smem_expr)                                         \
+  if (l_ == L) {                                                                 \
+    typedef XCfg<L> C;                                                           \
+    const int sm_ = (smem_expr);                                                 \
+    static bool init_ = false;                                                   \
+    if (!init_) {                                                                \
+      set_smem(kern<L>, sm_);                                                    \
+      init_ = true;                                                              \
+    }                                                                            \
+    RP_LAUNCH(kern<L>, dim3(nb_), dim3(C::NTHR), (size_t)sm_, s, a);             \
+    ok_ = true;                                                                  \
+  }
+#define XK_CASE_xk_backward(L) XK_CASE_BODY(xk_backward, L, C::SMEM_AW)
+#define XK_CASE_xk_forward(L) XK_CASE_BODY(xk_forward, L, C::SMEM_AW)
+#define XK_CASE_xk_div(L) XK_CASE_BODY(xk_div, L, C::SMEM_A)
+#define XK_CASE_xk_project(L) XK_CASE_BODY(xk_project, L, 2 * C::AROWS * 32 + C::NTHR * 48)
+
+#define XK_LAUNCH(kern, ncols, nx)                                                 \
+  do {                                                                             \
+    const int l_ = bluestein_log2(nx);                                             \
+    const int nb_ = ((ncols) + 3) / 4;                                             \
+    bool ok_ = false;                                                              \
+    XK_SIZES(XK_CASE_##kern)                                                       \
+    if (!ok_) throw Error(RP_ERR_INTERNAL, #kern ": unsupported lane length");     \
+  } while (0)
+
+void launch_x_backward(const XBackwardArgs& a, cudaStream_t s) { XK_LAUNCH(xk_backward, a.src.cols, a.t.n); }
+void launch_x_forward(const XForwardArgs& a, cudaStream_t s) { XK_LAUNCH(xk_forward, a.conv.cols, a.t.n); }
+void launch_x_div(const XDivArgs& a, cudaStream_t s) { XK_LAUNCH(xk_div, a.vx.cols, a.nx); }
+void launch_x_project(const XProjectArgs& a, cudaStream_t s) { XK_LAUNCH(xk_project, a.phi.cols, a.nx); }
+
+}  // namespace fk
+}  // namespace rp

@@ -4,11 +4,13 @@
 // owner of device arrays plus the lane programs / GEMMs that implement it.
 #pragma once
 #include <array>
+#include <functional>
 #include <map>
 #include <memory>
 #include <string>
 #include <vector>
 
+#include "fast.h"
 #include "kernels.h"
 #include "tables.h"
 
@@ -204,6 +206,9 @@ class Navier2D {
   void build_step();
   void build_step_confined();
   void build_step_periodic();
+  void build_step_confined_fast();
+  void add_fast(const char* name, double bytes, std::function<void()> fn);
+  std::vector<std::function<void()>> fast_ops_;  // specialised kernels (fast.h), launched on `stream`
   void build_y_phase();
   void add_prog(ProgBuilder& pb, const char* name);
   void rebuild_bc();
@@ -223,7 +228,7 @@ class Navier2D {
   Arr tbc_ortho_, dxtbc_, dytbc_, bcdiff_;
   std::vector<Built> step_;      // programs of one update() in launch order
   struct StepOp {
-    int kind;  // 0 lane program, 1 gemm fwd, 2 gemm bwd, 3 zero elem
+    int kind;  // 0 lane program, 1 gemm fwd, 2 gemm bwd, 3 zero elem, 4 specialised kernel
     int idx;
   };
   std::vector<StepOp> ops_;

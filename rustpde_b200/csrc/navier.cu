@@ -173,11 +173,18 @@ void Navier2D::set_temperature(double amp, double m, double n) {  // navier.rs:9
 // --------------------------------------------------------------------------
 void Navier2D::build_step() {
   if (!ops_.empty()) return;
+  const char* nf = getenv("RUSTPDE_B200_NO_FAST");
+  const bool fast_ok = !(nf && nf[0] == '1');
   if (periodic)
     build_step_periodic();
+  else if (fast_ok && fk::x_supported(nx) && fk::y_supported(ny))
+    build_step_confined_fast();
   else
     build_step_confined();
   launches_per_step_ = (int)ops_.size();
+  if (getenv("RUSTPDE_B200_VERBOSE"))
+    fprintf(stderr, "[rustpde_b200] Navier2D %dx%d %s: %s kernels, %d launches/step\n", nx, ny,
+            periodic ? "periodic" : "confined", fast_ops_.empty() ? "lane-program" : "specialised", launches_per_step_);
 }
 
 void Navier2D::add_prog(ProgBuilder& pb, const char* name) {
@@ -392,6 +399,197 @@ void Navier2D::build_step_confined() {
   (void)byt;
 }
 
+
+// --------------------------------------------------------------------------
+// Confined step on the specialised kernels (fast_x.cu / fast_y.cu): same
+// schedule and intermediate arrays as build_step_confined, one hand-written
+// kernel per pass instead of a lane program.
+// --------------------------------------------------------------------------
+void Navier2D::add_fast(const char* name, double bytes, std::function<void()> fn) {
+  fast_ops_.push_back(std::move(fn));
+  ops_.push_back(StepOp{4, (int)fast_ops_.size() - 1});
+  opinfo_.push_back(OpInfo{name, bytes, 0.0});
+}
+
+static fk::Mat mat_of(const Arr& a) { return fk::Mat{a.d(), a.ld, a.rows, a.cols}; }
+static fk::DctTab dct_of(const Base& b) {
+  fk::DctTab t;
+  t.n = b.n;
+  t.sc = b.d_sc.as<double2>();
+  t.tw = b.fft.plan.tw;
+  t.chirp = b.fft.plan.chirp;
+  t.bhat = b.fft.plan.bhat;
+  return t;
+}
+static fk::B2Tabs b2_of(const Base& b) {
+  return fk::B2Tabs{b.d_b2lo.as<double>(), b.d_b2di.as<double>(), b.d_b2up.as<double>()};
+}
+static fk::FdmaTabs fdma_of(const FdmaDev& f) {
+  return fk::FdmaTabs{f.fp.as<double>(), f.bs.as<double>(), f.bp1.as<double>(), f.bp2.as<double>()};
+}
+static fk::TdmaTabs tdma_of(const Base& b) {
+  return fk::TdmaTabs{b.d_sd.as<double>(), b.d_sl.as<double>(), b.d_tfs.as<double>(), b.d_tfp.as<double>(),
+                      b.d_tbp.as<double>()};
+}
+static fk::ModeTabs mode_of(const FdmaModeDev& m) {
+  fk::ModeTabs t;
+  t.a_low = m.a_low.as<double>(), t.a_up1 = m.a_up1.as<double>(), t.a_up2 = m.a_up2.as<double>();
+  t.c_low = m.c_low.as<double>(), t.c_up1 = m.c_up1.as<double>(), t.c_up2 = m.c_up2.as<double>();
+  t.lam = m.lam.as<double>();
+  t.alpha = m.alpha;
+  t.inv = m.inv.as<double>();
+  t.inv_ld = m.inv_ld;
+  return t;
+}
+
+void Navier2D::build_step_confined_fast() {
+  const Base &bxu = *ux->sp.b0, &byu = *ux->sp.b1;
+  const Base &bxt = *temp->sp.b0, &byt = *temp->sp.b1;
+  const Base &bxn = *pres1->sp.b0, &byn = *pres1->sp.b1;
+  const Base &bxo = *field->sp.b0, &byo = *field->sp.b1;
+  const int mx = nx - 2, my = ny - 2;
+  const double isx = 1.0 / scale[0], isy = 1.0 / scale[1];
+  Field2* flds[3] = {ux.get(), uy.get(), temp.get()};
+  const Base* bxs[3] = {&bxu, &bxu, &bxt};
+  const Base* bys[3] = {&byu, &byu, &byt};
+  const double fb = 8.0 * (double)nx * (double)ny;  // bytes of one field sweep
+  // phys_: 0 ux, 1 uy, 2 dxu, 3 dyu, 4 dxv, 5 dyv, 6 dxT, 7 dyT
+  const int val_idx[3] = {0, 1, -1}, dx_idx[3] = {2, 4, 6}, dy_idx[3] = {3, 5, 7};
+  // ---- 1. x-backward: value and d/dx of ux, uy, T ------------------------
+  for (int f = 0; f < 3; ++f) {
+    fk::XBackwardArgs a;
+    a.src = mat_of(flds[f]->vhat);
+    a.val = mat_of(ax_[f]);
+    a.dx = mat_of(adx_[f]);
+    a.sd = bxs[f]->d_sd.as<double>();
+    a.sl = bxs[f]->d_sl.as<double>();
+    a.isx = isx;
+    a.t = dct_of(bxo);
+    add_fast("x_backward_dct", 3 * fb, [this, a]() { fk::launch_x_backward(a, stream); });
+  }
+  // ---- 2. y-backward -> physical space ------------------------------------
+  for (int f = 0; f < 3; ++f) {
+    fk::YBackwardArgs a;
+    a.a = mat_of(ax_[f]);
+    a.adx = mat_of(adx_[f]);
+    a.val = val_idx[f] >= 0 ? mat_of(phys_[val_idx[f]]) : fk::Mat{nullptr, 0, 0, 0};
+    a.dy = mat_of(phys_[dy_idx[f]]);
+    a.dx = mat_of(phys_[dx_idx[f]]);
+    a.sd = bys[f]->d_sd.as<double>();
+    a.sl = bys[f]->d_sl.as<double>();
+    a.isy = isy;
+    a.t = dct_of(byo);
+    add_fast("y_backward", (val_idx[f] >= 0 ? 5 : 4) * fb, [this, a]() { fk::launch_y_backward(a, stream); });
+  }
+  // ---- 3. products + forward DCT-y + dealias-y -----------------------------
+  for (int f = 0; f < 3; ++f) {
+    fk::YConvArgs a;
+    a.u = mat_of(phys_[0]);
+    a.du = mat_of(phys_[dx_idx[f]]);
+    a.v = mat_of(phys_[1]);
+    a.dv = mat_of(phys_[dy_idx[f]]);
+    a.bcx = f == 2 ? mat_of(dxtbc_) : fk::Mat{nullptr, 0, 0, 0};
+    a.bcy = f == 2 ? mat_of(dytbc_) : fk::Mat{nullptr, 0, 0, 0};
+    a.out = mat_of(bconv_[f]);
+    a.cut = dealias ? (ny * 2) / 3 : ny;  // navier.rs:1029
+    a.t = dct_of(byo);
+    add_fast("conv_y_forward", (f == 2 ? 7 : 5) * fb, [this, a]() { fk::launch_y_conv(a, stream); });
+  }
+  // ---- 4. x-forward + dealias + rhs assembly + x half of HholtzAdi ---------
+  for (int f = 0; f < 3; ++f) {
+    fk::XForwardArgs a;
+    a.conv = mat_of(bconv_[f]);
+    a.out = mat_of(w_[f]);
+    a.cut = dealias ? (nx * 2) / 3 : nx;  // navier.rs:1028
+    a.dt = dt;
+    a.fld = mat_of(flds[f]->vhat);
+    a.fxsd = bxs[f]->d_sd.as<double>(), a.fxsl = bxs[f]->d_sl.as<double>();
+    a.fysd = bys[f]->d_sd.as<double>(), a.fysl = bys[f]->d_sl.as<double>();
+    a.mode = f;
+    a.pres = mat_of(pres0->vhat);
+    a.dyp = mat_of(dyp_);
+    a.tmp = mat_of(temp->vhat);
+    a.tbc = mat_of(tbc_ortho_);
+    a.bcdiff = mat_of(bcdiff_);
+    a.txsd = bxt.d_sd.as<double>(), a.txsl = bxt.d_sl.as<double>();
+    a.tysd = byt.d_sd.as<double>(), a.tysl = byt.d_sl.as<double>();
+    a.isx = isx;
+    a.b2 = b2_of(bxo);
+    a.f = fdma_of(solver[f]->adi[0].fdma);
+    a.t = dct_of(bxo);
+    add_fast("x_forward_rhs_adi_x", (f == 1 ? 6 : 4) * fb, [this, a]() { fk::launch_x_forward(a, stream); });
+  }
+  // ---- 5. y half of HholtzAdi (+ pieces of the divergence) -----------------
+  for (int f = 0; f < 3; ++f) {
+    fk::YAdiArgs a;
+    a.w = mat_of(w_[f]);
+    a.out = mat_of(flds[f]->vhat);
+    a.aux = f == 0 ? mat_of(vx_) : (f == 1 ? mat_of(ey_) : fk::Mat{nullptr, 0, 0, 0});
+    a.mode = f == 0 ? 1 : (f == 1 ? 2 : 0);
+    a.sd = byu.d_sd.as<double>(), a.sl = byu.d_sl.as<double>();
+    a.isy = isy;
+    a.b2 = b2_of(byo);
+    a.f = fdma_of(solver[f]->adi[1].fdma);
+    a.ny = ny;
+    add_fast("adi_y", (f == 2 ? 2 : 3) * fb, [this, a]() { fk::launch_y_adi(a, stream); });
+  }
+  // ---- 6. divergence (navier.rs:698-703) + B2x of the Poisson rhs ----------
+  {
+    fk::XDivArgs a;
+    a.vx = mat_of(vx_), a.ey = mat_of(ey_), a.div = mat_of(div_), a.r1 = mat_of(r1_);
+    a.sd = bxu.d_sd.as<double>(), a.sl = bxu.d_sl.as<double>();
+    a.isx = isx;
+    a.b2 = b2_of(bxo);
+    a.nx = nx;
+    add_fast("divergence_b2x", 4 * fb, [this, a]() { fk::launch_x_div(a, stream); });
+  }
+  // ---- 7-9. fast diagonalisation: P., per-mode Fdma_y, Q. (poisson.rs:131-149)
+  ops_.push_back(StepOp{1, 0});
+  opinfo_.push_back(OpInfo{"poisson_gemm_fwd", 8.0 * ((double)mx * mx + 2.0 * mx * ny), 2.0 * mx * (double)mx * ny});
+  {
+    fk::YModeArgs a;
+    a.g = mat_of(g_), a.h = mat_of(h_);
+    a.b2 = b2_of(byo);
+    a.m = mode_of(solver[3]->ts.mode);
+    a.ny = ny;
+    add_fast("poisson_mode_y", 3 * fb, [this, a]() { fk::launch_y_mode(a, stream); });
+  }
+  ops_.push_back(StepOp{2, 0});
+  opinfo_.push_back(OpInfo{"poisson_gemm_bwd", 8.0 * ((double)mx * mx + 2.0 * mx * my), 2.0 * mx * (double)mx * my});
+  ops_.push_back(StepOp{3, 0});  // pres[1].vhat[[0,0]] = 0   (navier.rs:714)
+  opinfo_.push_back(OpInfo{"zero_mode00", 8.0, 0.0});
+  // ---- 10-11. projection (navier.rs:683-695) --------------------------------
+  {
+    fk::XProjectArgs a;
+    a.phi = mat_of(pres1->vhat), a.a1 = mat_of(a1_), a.a2 = mat_of(a2_);
+    a.nsd = bxn.d_sd.as<double>(), a.nsl = bxn.d_sl.as<double>();
+    a.t = tdma_of(bxu);
+    a.isx = isx;
+    a.nx = nx;
+    add_fast("project_x", 3 * fb, [this, a]() { fk::launch_x_project(a, stream); });
+  }
+  {
+    fk::YProjectArgs a;
+    a.a1 = mat_of(a1_), a.a2 = mat_of(a2_), a.ux = mat_of(ux->vhat), a.uy = mat_of(uy->vhat);
+    a.nsd = byn.d_sd.as<double>(), a.nsl = byn.d_sl.as<double>();
+    a.t = tdma_of(byu);
+    a.isy = isy;
+    a.ny = ny;
+    add_fast("project_y", 6 * fb, [this, a]() { fk::launch_y_project(a, stream); });
+  }
+  // ---- 12. pressure update (navier.rs:717-721) + d/dy pres for the next step --
+  {
+    fk::YPresArgs a;
+    a.phi = mat_of(pres1->vhat), a.div = mat_of(div_), a.pres = mat_of(pres0->vhat), a.dyp = mat_of(dyp_);
+    a.xsd = bxn.d_sd.as<double>(), a.xsl = bxn.d_sl.as<double>();
+    a.ysd = byn.d_sd.as<double>(), a.ysl = byn.d_sl.as<double>();
+    a.inv_dt = 1.0 / dt, a.nu = nu, a.isy = isy;
+    a.ny = ny;
+    add_fast("pressure_update", 5 * fb, [this, a]() { fk::launch_y_pres(a, stream); });
+  }
+  (void)my;
+}
+
 void Navier2D::build_step_periodic() {
   const Base &bx = *ux->sp.b0, &byu = *ux->sp.b1, &byt = *temp->sp.b1, &byn = *pres1->sp.b1;
   const int mk = nx / 2 + 1, my = ny - 2;
@@ -493,6 +691,7 @@ void Navier2D::run_op(const StepOp& op) {
     case 1: solver[3]->gemm_fwd(r1_, g_, ny); break;
     case 2: solver[3]->gemm_bwd(h_, pres1->vhat, ny - 2); break;
     case 3: launch_zero_elems(pres1->vhat.d(), 1, stream); break;
+    case 4: fast_ops_[op.idx](); break;
   }
 }
 

@@ -277,6 +277,7 @@ void build_fdma_mode_dev(const Diags& A, const Diags& C, const std::vector<doubl
   const int nl = (int)lam.size();
   out.n = n;
   out.nlanes = nl;
+  out.alpha = alpha;
   out.inv_ld = (n + 7) & ~7;
   std::vector<double> inv((size_t)nl * out.inv_ld, 0.0);
   std::vector<double> dia(n), up1(n);

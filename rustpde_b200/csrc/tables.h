@@ -122,6 +122,7 @@ struct FdmaModeDev {
   DevBuf tab, a_low, a_dia, a_up1, a_up2, c_low, c_dia, c_up1, c_up2, lam, inv;
   int n = 0, nlanes = 0;
   long long inv_ld = 0;
+  double alpha = 0.0;
 };
 void build_fdma_mode_dev(const Diags& A, const Diags& C, const std::vector<double>& lam, double alpha, FdmaModeDev& out);
 
