@@ -125,6 +125,9 @@ int rp_navier_field(rp_navier_t* h, int which, rp_field_t** out);              /
 int rp_navier_export_eig(rp_navier_t* h, double* lam, double* q, double* p);   /* pressure Poisson set-up data */
 int rp_navier_launches_per_step(rp_navier_t* h, int* n);
 int rp_navier_set_graph(rp_navier_t* h, int on);                               /* CUDA-graph replay of update() (default on) */
+/* which kernels serve update(): specialised = 1 -> hand-specialised x/y pass kernels (else generic lane programs);
+   split_gemm = 1 -> pressure Poisson runs the even/odd parity-split GEMM pairs (exactly checkerboard set-up data) */
+int rp_navier_kernel_path(rp_navier_t* h, int* specialised, int* split_gemm);
 /* Measurement aids (no reference counterpart): per-launch device time of update(), averaged over
  * `reps` eagerly launched steps (CUDA events on the launching stream; advances the solution), and
  * the name / algorithmic bytes / flops of launch i. */

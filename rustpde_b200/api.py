@@ -431,6 +431,12 @@ class Navier2D:
         self._lib.call("rp_navier_export_eig", self._h, _dp(lam), _dp(q), _dp(p))
         return lam, q, p
 
+    def kernel_path(self):
+        """(specialised, split_gemm): which kernels serve update() (see rp_navier_kernel_path)."""
+        a, b = C.c_int(), C.c_int()
+        self._lib.call("rp_navier_kernel_path", self._h, C.byref(a), C.byref(b))
+        return bool(a.value), bool(b.value)
+
     def launches_per_step(self):
         n = C.c_int()
         self._lib.call("rp_navier_launches_per_step", self._h, C.byref(n))

@@ -355,6 +355,12 @@ int rp_navier_export_eig(rp_navier_t* h, double* lam, double* q, double* p) {
 }
 int rp_navier_launches_per_step(rp_navier_t* h, int* n) { NAV_GUARD(if (n) *n = N.launches_per_step()); }
 int rp_navier_set_graph(rp_navier_t* h, int on) { NAV_GUARD(N.set_graph(on != 0)); }
+int rp_navier_kernel_path(rp_navier_t* h, int* specialised, int* split_gemm) {
+  NAV_GUARD({
+    if (specialised) *specialised = N.uses_specialised_kernels() ? 1 : 0;
+    if (split_gemm) *split_gemm = (!N.periodic && N.solver[3]->ts.split) ? 1 : 0;
+  });
+}
 int rp_navier_profile(rp_navier_t* h, int reps, double* ms, size_t cap, int* nops) {
   NAV_GUARD({
     need(reps > 0 && ms, RP_ERR_INVALID, "bad profile arguments");

@@ -24,11 +24,22 @@ struct XCfg {
   static constexpr int SMEM_AW = (AROWS + LB) * 32 + NTHR * 48;
 };
 
+#define FK_FILL_U 8
 template <int NTHR, class F>
-FK_DEV void xtile_fill(double* td, int nfill, F f) {
-  for (int it = threadIdx.x; it < nfill * 4; it += NTHR) {
-    const int lane = it & 3, i = it >> 2;
-    td[didx(i, lane)] = f(i, lane);
+FK_DEV void xtile_fill(double* td, int nfill, F f) {  // batched like tile_fill (fast_y.cu)
+  const int tot = nfill * 4;
+  for (int it0 = threadIdx.x; it0 < tot; it0 += NTHR * FK_FILL_U) {
+    double v[FK_FILL_U];
+#pragma unroll
+    for (int u = 0; u < FK_FILL_U; ++u) {
+      const int it = it0 + u * NTHR;
+      v[u] = it < tot ? f(it >> 2, it & 3) : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < FK_FILL_U; ++u) {
+      const int it = it0 + u * NTHR;
+      if (it < tot) td[didx(it >> 2, it & 3)] = v[u];
+    }
   }
 }
 

@@ -28,12 +28,24 @@ struct YCfg {
   RP_DYN_SMEM(double, td);        \
   double* red = td + C::ROWS * 4
 
-// tile(j, lane) = f(j, lane) for j < nfill
+// tile(j, lane) = f(j, lane) for j < nfill.  Loads are issued in batches of FK_FILL_U
+// per thread before the first store, so that enough global requests are in flight.
+#define FK_FILL_U 8
 template <int NTHR, class F>
 FK_DEV void tile_fill(double* td, int nfill, F f) {
-  for (int it = threadIdx.x; it < nfill * 4; it += NTHR) {
-    const int lane = it & 3, j = it >> 2;
-    td[didx(j, lane)] = f(j, lane);
+  const int tot = nfill * 4;
+  for (int it0 = threadIdx.x; it0 < tot; it0 += NTHR * FK_FILL_U) {
+    double v[FK_FILL_U];
+#pragma unroll
+    for (int u = 0; u < FK_FILL_U; ++u) {
+      const int it = it0 + u * NTHR;
+      v[u] = it < tot ? f(it >> 2, it & 3) : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < FK_FILL_U; ++u) {
+      const int it = it0 + u * NTHR;
+      if (it < tot) td[didx(it >> 2, it & 3)] = v[u];
+    }
   }
 }
 // g(j, lane, value of natural element j) for j < nout

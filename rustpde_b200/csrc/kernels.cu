@@ -11,7 +11,7 @@ namespace rp {
 // (512, 1): without the explicit min-blocks ptxas squeezed the whole call tree into 32 registers
 __global__ void __launch_bounds__(512, 1) lane_vm_kernel(const Program* __restrict__ progs) { lane_vm_body(progs); }
 
-__global__ void __launch_bounds__(256) dgemm_dmma_kernel(GemmArgs g);
+__global__ void __launch_bounds__(256) dgemm_dmma_kernel(GemmArgs g0, GemmArgs g1);
 enum { GBM = 128, GBN = 128, GBK = 16, GPAD = 8, GLD = GBM + GPAD };
 static const int kGemmSmem = 4 * GBK * GLD * (int)sizeof(double);
 
@@ -48,7 +48,9 @@ RP_DEV void dmma(double& d0, double& d1, double a, double b) {
 #endif
 }
 
-__global__ void __launch_bounds__(256) dgemm_dmma_kernel(GemmArgs g) {
+__global__ void __launch_bounds__(256) dgemm_dmma_kernel(GemmArgs g0, GemmArgs g1) {
+  const GemmArgs& g = blockIdx.z ? g1 : g0;
+  if ((int)(blockIdx.y * GBM) >= g.M) return;
   RP_DYN_SMEM(double, sm);
   double* As = sm;                       // [2][GBK][GLD]  (k-major)
   double* Bs = sm + 2 * GBK * GLD;       // [2][GBK][GLD]
@@ -131,7 +133,14 @@ void launch_dgemm(const GemmArgs& g, cudaStream_t s) {
   const int smem = kGemmSmem;
   init_kernels();
   dim3 grid((g.N + GBN - 1) / GBN, (g.M + GBM - 1) / GBM);
-  RP_LAUNCH(dgemm_dmma_kernel, grid, dim3(256), (size_t)smem, s, g);
+  RP_LAUNCH(dgemm_dmma_kernel, grid, dim3(256), (size_t)smem, s, g, g);
+}
+void launch_dgemm2(const GemmArgs& g0, const GemmArgs& g1, cudaStream_t s) {
+  if (g0.N <= 0 || g0.M <= 0) return;
+  init_kernels();
+  const int mmax = std::max(g0.M, g1.M);
+  dim3 grid((g0.N + GBN - 1) / GBN, (mmax + GBM - 1) / GBM, 2);
+  RP_LAUNCH(dgemm_dmma_kernel, grid, dim3(256), (size_t)kGemmSmem, s, g0, g1);
 }
 
 // ===========================================================================

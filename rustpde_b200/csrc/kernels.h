@@ -18,6 +18,7 @@ struct GemmArgs {
   int b_r0, b_rs, c_r0, c_rs;  // row offset / row stride multiplier of B and C
 };
 void launch_dgemm(const GemmArgs& g, cudaStream_t s);
+void launch_dgemm2(const GemmArgs& g0, const GemmArgs& g1, cudaStream_t s);  // two independent products, one launch
 
 void launch_zero_elems(double* p, int count, cudaStream_t s);
 void launch_wsum(const double* a, const double* b, long long ld, int rows, int cols, const double* wx, const double* wy,

@@ -152,9 +152,8 @@ bool lapack_available(std::string* why) {
   return ok;
 }
 
-void lapack_eig_setup(int m, const std::vector<double>& Cx, const std::vector<double>& Ax, std::vector<double>& lam,
-                      std::vector<double>& Q, std::vector<double>& P) {
-  std::lock_guard<std::mutex> g(g_mu);
+static void eig_setup_locked(int m, const std::vector<double>& Cx, const std::vector<double>& Ax, std::vector<double>& lam,
+                             std::vector<double>& Q, std::vector<double>& P) {
   if (!ensure_loaded())
     throw Error(RP_ERR_LAPACK,
                 "no LAPACK library found for the fast-diagonalisation set-up (set RUSTPDE_B200_LAPACK or call "
@@ -163,6 +162,55 @@ void lapack_eig_setup(int m, const std::vector<double>& Cx, const std::vector<do
     do_eig_setup<int64_t>(m, Cx, Ax, lam, Q, P);
   else
     do_eig_setup<int32_t>(m, Cx, Ax, lam, Q, P);
+}
+
+void lapack_eig_setup(int m, const std::vector<double>& Cx, const std::vector<double>& Ax, std::vector<double>& lam,
+                      std::vector<double>& Q, std::vector<double>& P) {
+  std::lock_guard<std::mutex> g(g_mu);
+  eig_setup_locked(m, Cx, Ax, lam, Q, P);
+}
+
+// The Chebyshev operators only couple modes of equal parity (offsets -2, 0, +2, +4),
+// so inv(Cx).Ax is exactly block diagonal after an even/odd permutation.  This
+// variant diagonalises the two half-size blocks separately and merges the
+// result (eigenvalues sorted descending like utils.rs:80-94): the same
+// decomposition as lapack_eig_setup in exact arithmetic, with Q and P exactly
+// checkerboard (cross-parity entries are 0.0), which is what lets the solve run
+// two half-size GEMM pairs.
+void lapack_eig_setup_parity(int m, const std::vector<double>& Cx, const std::vector<double>& Ax, std::vector<double>& lam,
+                             std::vector<double>& Q, std::vector<double>& P) {
+  std::lock_guard<std::mutex> g(g_mu);
+  std::vector<double> l2[2], q2[2], p2[2];
+  int mp[2];
+  for (int par = 0; par < 2; ++par) {
+    const int mm = (m - par + 1) / 2;
+    mp[par] = mm;
+    std::vector<double> c((size_t)mm * mm), a((size_t)mm * mm);
+    for (int i = 0; i < mm; ++i)
+      for (int j = 0; j < mm; ++j) {
+        c[(size_t)i * mm + j] = Cx[(size_t)(2 * i + par) * m + 2 * j + par];
+        a[(size_t)i * mm + j] = Ax[(size_t)(2 * i + par) * m + 2 * j + par];
+      }
+    eig_setup_locked(mm, c, a, l2[par], q2[par], p2[par]);
+  }
+  // merge, descending (both halves are already sorted descending)
+  lam.assign(m, 0.0);
+  Q.assign((size_t)m * m, 0.0);
+  P.assign((size_t)m * m, 0.0);
+  int i0 = 0, i1 = 0;
+  for (int k = 0; k < m; ++k) {
+    int par;
+    if (i0 >= mp[0]) par = 1;
+    else if (i1 >= mp[1]) par = 0;
+    else par = (l2[0][i0] >= l2[1][i1]) ? 0 : 1;
+    const int kk = par ? i1++ : i0++;
+    const int mm = mp[par];
+    lam[k] = l2[par][kk];
+    for (int a = 0; a < mm; ++a) {
+      Q[(size_t)(2 * a + par) * m + k] = q2[par][(size_t)a * mm + kk];
+      P[(size_t)k * m + 2 * a + par] = p2[par][(size_t)kk * mm + a];
+    }
+  }
 }
 
 }  // namespace rp

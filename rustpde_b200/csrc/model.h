@@ -126,9 +126,15 @@ struct AxisAdi {
 // Hholtz / Poisson through FdmaTensor (src/solver/{hholtz,poisson,fdma_tensor}.rs)
 struct TensorSolver {
   FdmaModeDev mode;     // per-lane banded solve along y
-  Arr P, Q;             // fwd = Q^-1 Cx^-1, bwd = Q  (only when x is Chebyshev)
+  Arr P, Q;             // fwd = Q^-1 Cx^-1, bwd = Q  (only when x is Chebyshev; full matrices, strict mode)
   std::vector<double> lam;
   bool x_diag = false;  // Fourier axis: no GEMM
+  // parity-split mode (Q, P exactly checkerboard): modes are stored grouped by the
+  // parity of their eigenvector (me even ones first), the contractions run on the
+  // even and odd sub-blocks only (half the flops)
+  bool split = false;
+  int me = 0, mo = 0;
+  Arr Pe, Po, Qe, Qo;
 };
 
 enum SolverKind { SOLVER_HHOLTZ = 0, SOLVER_HHOLTZ_ADI = 1, SOLVER_POISSON = 2 };
@@ -162,7 +168,7 @@ class Solver2 {
  private:
   Arr t1_[2], t2_[2], t3_[2];
   Built px_[2], py_[2];
-  std::vector<double> hq_, hp_;
+  std::vector<double> hq_, hp_, lam_export_;
   void build_programs(bool complex_data);
 };
 
@@ -188,6 +194,10 @@ class Navier2D {
   void sync();
   Field2* field_by_index(int which);
   int launches_per_step() const { return launches_per_step_; }
+  bool uses_specialised_kernels() {
+    build_step();
+    return !fast_ops_.empty();
+  }
   struct OpInfo {
     std::string name;
     double bytes, flops;  // algorithmic bytes / flops of one launch
@@ -247,5 +257,7 @@ void lapack_set_library(const char* path);
 bool lapack_available(std::string* why);
 void lapack_eig_setup(int m, const std::vector<double>& Cx, const std::vector<double>& Ax, std::vector<double>& lam,
                       std::vector<double>& Q, std::vector<double>& P);
+void lapack_eig_setup_parity(int m, const std::vector<double>& Cx, const std::vector<double>& Ax, std::vector<double>& lam,
+                             std::vector<double>& Q, std::vector<double>& P);
 
 }  // namespace rp

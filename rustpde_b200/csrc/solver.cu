@@ -73,7 +73,11 @@ Solver2::Solver2(int kind_, const Space2& sp_, double cx, double cy, double alph
       P.assign(eig->p, eig->p + (size_t)m0 * m0);
     } else {
       std::vector<double> Cx = dense_from(b0.C, 1.0), Ax = dense_from(b0.A, sign * cx);
-      lapack_eig_setup(m0, Cx, Ax, ts.lam, Q, P);
+      const char* gm = getenv("RUSTPDE_B200_EIG");
+      if (gm && std::string(gm) == "full")
+        lapack_eig_setup(m0, Cx, Ax, ts.lam, Q, P);  // dgeev on the full matrix, like utils.rs:66-98
+      else
+        lapack_eig_setup_parity(m0, Cx, Ax, ts.lam, Q, P);
     }
     hq_ = Q;
     hp_ = P;
@@ -81,17 +85,61 @@ Solver2::Solver2(int kind_, const Space2& sp_, double cx, double cy, double alph
     ts.Q.alloc(m0, m0, false);
     ts.P.upload(P.data(), 0);
     ts.Q.upload(Q.data(), 0);
+    // parity-split mode: every eigenvector is purely even or purely odd (exact zeros elsewhere)
+    std::vector<int> par(m0, -1);
+    bool cb = true;
+    for (int k = 0; k < m0 && cb; ++k) {
+      bool has[2] = {false, false};
+      for (int i = 0; i < m0; ++i) {
+        if (Q[(size_t)i * m0 + k] != 0.0) has[i & 1] = true;
+        if (P[(size_t)k * m0 + i] != 0.0) has[i & 1] = true;
+      }
+      if (has[0] && has[1]) cb = false;
+      par[k] = has[1] ? 1 : 0;
+    }
+    std::vector<int> ke, ko;
+    for (int k = 0; k < m0; ++k) (par[k] ? ko : ke).push_back(k);
+    const int me = (m0 + 1) / 2, mo = m0 / 2;
+    if (cb && (int)ke.size() == me && (int)ko.size() == mo && m0 >= 4) {
+      ts.split = true;
+      ts.me = me, ts.mo = mo;
+      std::vector<double> pe((size_t)me * me), po((size_t)mo * mo), qe((size_t)me * me), qo((size_t)mo * mo);
+      for (int a = 0; a < me; ++a)
+        for (int b = 0; b < me; ++b) {
+          pe[(size_t)a * me + b] = P[(size_t)ke[a] * m0 + 2 * b];
+          qe[(size_t)b * me + a] = Q[(size_t)(2 * b) * m0 + ke[a]];
+        }
+      for (int a = 0; a < mo; ++a)
+        for (int b = 0; b < mo; ++b) {
+          po[(size_t)a * mo + b] = P[(size_t)ko[a] * m0 + 2 * b + 1];
+          qo[(size_t)b * mo + a] = Q[(size_t)(2 * b + 1) * m0 + ko[a]];
+        }
+      ts.Pe.alloc(me, me, false), ts.Po.alloc(mo, mo, false), ts.Qe.alloc(me, me, false), ts.Qo.alloc(mo, mo, false);
+      ts.Pe.upload(pe.data(), 0), ts.Po.upload(po.data(), 0), ts.Qe.upload(qe.data(), 0), ts.Qo.upload(qo.data(), 0);
+      // internal mode order: even-parity modes first
+      std::vector<double> l2;
+      for (int k : ke) l2.push_back(ts.lam[k]);
+      for (int k : ko) l2.push_back(ts.lam[k]);
+      lam_export_ = ts.lam;
+      ts.lam = l2;
+    }
     rt::sync(0);
   }
-  if (kind == SOLVER_POISSON && std::fabs(ts.lam[0]) < 1e-10)  // poisson.rs:80-83
-    for (auto& l : ts.lam) l -= 1e-10;
+  {
+    const std::vector<double>& l0 = lam_export_.empty() ? ts.lam : lam_export_;  // reference order: descending
+    if (kind == SOLVER_POISSON && std::fabs(l0[0]) < 1e-10) {                   // poisson.rs:80-83
+      for (auto& l : ts.lam) l -= 1e-10;
+      for (auto& l : lam_export_) l -= 1e-10;
+    }
+  }
   Diags Ay = combine(b1.A, sign * cy, b1.A, 0.0);
   build_fdma_mode_dev(Ay, b1.C, ts.lam, al, ts.mode);
 }
 
 void Solver2::export_eig(double* lam, double* q, double* p) const {
   if (kind == SOLVER_HHOLTZ_ADI) throw Error(RP_ERR_INVALID, "HholtzAdi has no eigen set-up data");
-  if (lam) std::copy(ts.lam.begin(), ts.lam.end(), lam);
+  const std::vector<double>& l0 = lam_export_.empty() ? ts.lam : lam_export_;
+  if (lam) std::copy(l0.begin(), l0.end(), lam);
   if (!ts.x_diag) {
     if (q) std::copy(hq_.begin(), hq_.end(), q);
     if (p) std::copy(hp_.begin(), hp_.end(), p);
@@ -113,29 +161,34 @@ void Solver2::emit_y(ProgBuilder& pb, int r, int rinv, Lay lay, bool complex_lan
 }
 
 // C = P . B over `ncols_real` real columns (complex data = interleaved real columns)
-void Solver2::gemm_fwd(const Arr& in, Arr& out, int ncols_real) const {
+static GemmArgs gemm_args(const Arr& A, int M, int K, const Arr& in, int b_r0, int b_rs, Arr& out, int c_r0, int c_rs,
+                          int ncols_real) {
   GemmArgs g;
-  g.A = ts.P.d();
+  g.A = A.d();
   g.B = in.d();
   g.C = out.d();
-  g.M = m0, g.N = ncols_real, g.K = m0;
-  g.lda = ts.P.ld;
+  g.M = M, g.N = ncols_real, g.K = K;
+  g.lda = A.ld;
   g.ldb = in.cplx ? in.ld * 2 : in.ld;
   g.ldc = out.cplx ? out.ld * 2 : out.ld;
-  g.b_r0 = 0, g.b_rs = 1, g.c_r0 = 0, g.c_rs = 1;
-  launch_dgemm(g, stream);
+  g.b_r0 = b_r0, g.b_rs = b_rs, g.c_r0 = c_r0, g.c_rs = c_rs;
+  return g;
+}
+void Solver2::gemm_fwd(const Arr& in, Arr& out, int ncols_real) const {
+  if (ts.split) {  // even rows of `in` -> modes [0, me), odd rows -> modes [me, m0)
+    launch_dgemm2(gemm_args(ts.Pe, ts.me, ts.me, in, 0, 2, out, 0, 1, ncols_real),
+                  gemm_args(ts.Po, ts.mo, ts.mo, in, 1, 2, out, ts.me, 1, ncols_real), stream);
+    return;
+  }
+  launch_dgemm(gemm_args(ts.P, m0, m0, in, 0, 1, out, 0, 1, ncols_real), stream);
 }
 void Solver2::gemm_bwd(const Arr& in, Arr& out, int ncols_real) const {
-  GemmArgs g;
-  g.A = ts.Q.d();
-  g.B = in.d();
-  g.C = out.d();
-  g.M = m0, g.N = ncols_real, g.K = m0;
-  g.lda = ts.Q.ld;
-  g.ldb = in.cplx ? in.ld * 2 : in.ld;
-  g.ldc = out.cplx ? out.ld * 2 : out.ld;
-  g.b_r0 = 0, g.b_rs = 1, g.c_r0 = 0, g.c_rs = 1;
-  launch_dgemm(g, stream);
+  if (ts.split) {
+    launch_dgemm2(gemm_args(ts.Qe, ts.me, ts.me, in, 0, 1, out, 0, 2, ncols_real),
+                  gemm_args(ts.Qo, ts.mo, ts.mo, in, ts.me, 1, out, 1, 2, ncols_real), stream);
+    return;
+  }
+  launch_dgemm(gemm_args(ts.Q, m0, m0, in, 0, 1, out, 0, 1, ncols_real), stream);
 }
 
 void Solver2::build_programs(bool cd) {

@@ -100,6 +100,32 @@ def check_tensor_shared_eig(lib, which, kx, ky, nx, ny, c=(1.0, 0.8), alpha=2.0,
     return e1, e2, sol, osol
 
 
+def check_tensor_own_eig(lib, which, kx, ky, nx, ny, c=(1.0, 0.8), alpha=2.0, seed=13):
+    """Hholtz / Poisson with the library's own set-up (even/odd block diagonalisation ->
+    exactly checkerboard Q, P -> parity-split GEMMs); the oracle consumes the exported (lam, Q, P)."""
+    rng = np.random.default_rng(seed)
+    f, of = make_fields(lib, kx, nx, ky, ny)
+    if which == "poisson":
+        sol, osol = R.Poisson(f, c), O.Poisson(of, c, banded=True)
+    else:
+        sol, osol = R.Hholtz(f, c, alpha=alpha), O.Hholtz(of, c, alpha=alpha, banded=True)
+    lam, q, p = sol.export_eig()
+    m = nx - 2
+    # the exported decomposition is exactly checkerboard and reproduces inv(Cx) Ax
+    for k in range(m):
+        assert not (np.any(q[0::2, k] != 0) and np.any(q[1::2, k] != 0)), "Q not checkerboard"
+        assert not (np.any(p[k, 0::2] != 0) and np.any(p[k, 1::2] != 0)), "P not checkerboard"
+    assert np.all(np.diff(lam) <= 0), "eigenvalues not sorted descending (utils.rs:80-94)"
+    lam_ref = np.sort(osol.solver.lam[0])[::-1]
+    assert np.abs(lam - lam_ref).max() <= 1e-6 * max(1.0, np.abs(lam_ref).max()), "eigenvalues differ from dgeev on the full matrix"
+    osol.solver.lam[0], osol.solver.bwd[0], osol.solver.fwd[0] = lam, q, p
+    b = rng.uniform(-1, 1, (nx, ny))
+    ref = osol.solve(b)
+    e1 = rel(sol.solve(b), ref)
+    e2 = rel(sol.solve(b * (1 + 1j)), ref * (1 + 1j))
+    return e1, e2
+
+
 def check_tensor_fourier(lib, nx, ny, seed=5, tol=TOL):
     rng = np.random.default_rng(seed)
     f, of = make_fields(lib, "fourier_r2c", nx, "cheb_dirichlet", ny)
@@ -110,11 +136,18 @@ def check_tensor_fourier(lib, nx, ny, seed=5, tol=TOL):
     return e1, e2
 
 
-def make_navier_pair(lib, periodic, nx, ny, ra, pr, dt, aspect=1.0, adiabatic=True, ics=True):
-    """Device Navier2D and oracle Navier2D with identical set-up data and deterministic ICs."""
+def make_navier_pair(lib, periodic, nx, ny, ra, pr, dt, aspect=1.0, adiabatic=True, ics=True, own_eig=False):
+    """Device Navier2D and oracle Navier2D with identical set-up data and deterministic ICs.
+    own_eig: the device library does the pressure-Poisson eigen set-up itself (parity-split
+    mode) and the oracle consumes the exported (lam, Q, P); else the oracle's go to the device."""
     if periodic:
         o = O.Navier2D.new_periodic(nx, ny, ra, pr, dt, aspect, banded=True)
         n = R.Navier2D.new_periodic(nx, ny, ra, pr, dt, aspect, lib=lib)
+    elif own_eig:
+        n = R.Navier2D.new(nx, ny, ra, pr, dt, aspect, adiabatic, lib=lib)
+        lam, q, p = n.export_eig()  # lam already carries the poisson.rs:80-83 shift
+        o = O.Navier2D.new(nx, ny, ra, pr, dt, aspect, adiabatic, banded=True, eig_data=(lam, q, p))
+        o.solver[3].solver.lam[0] = lam.copy()
     else:
         o = O.Navier2D.new(nx, ny, ra, pr, dt, aspect, adiabatic, banded=True)
         ts = o.solver[3].solver
@@ -142,8 +175,8 @@ def oracle_diag(o):
     return [o.eval_nu(), o.eval_nuvol(), o.eval_re(), o.div_norm(), o.eval_ekin()]
 
 
-def check_navier_steps(lib, periodic, nx, ny, nsteps, ra=1e5, pr=1.0, dt=0.01, adiabatic=True, tol=1e-9, batch=1):
-    n, o = make_navier_pair(lib, periodic, nx, ny, ra, pr, dt, adiabatic=adiabatic)
+def check_navier_steps(lib, periodic, nx, ny, nsteps, ra=1e5, pr=1.0, dt=0.01, adiabatic=True, tol=1e-9, batch=1, own_eig=False):
+    n, o = make_navier_pair(lib, periodic, nx, ny, ra, pr, dt, adiabatic=adiabatic, own_eig=own_eig)
     e0 = navier_field_errors(n, o)
     assert max(e0.values()) <= TOL, e0
     done = 0

@@ -57,6 +57,19 @@ def test_fast_diag_shared_eig(emu, which, kx, ky, nx, ny):
     assert e1 <= pc.TOL and e2 <= pc.TOL, (e1, e2)
 
 
+@pytest.mark.parametrize("which,kx,ky,nx,ny", [
+    ("poisson", "cheb_neumann", "cheb_neumann", 16, 19),
+    ("poisson", "cheb_dirichlet", "cheb_dirichlet", 9, 7),     # odd number of modes: 4 even + 3 odd
+    ("hholtz", "cheb_dirichlet", "cheb_dirichlet", 40, 33),
+    ("poisson", "cheb_neumann", "cheb_neumann", 141, 34),
+])
+def test_fast_diag_parity_split(emu, which, kx, ky, nx, ny):
+    """Library's own set-up (even/odd block diagonalisation, exactly checkerboard Q and P) ->
+    two half-size GEMM pairs; the oracle consumes the exported set-up data."""
+    e1, e2 = pc.check_tensor_own_eig(emu, which, kx, ky, nx, ny)
+    assert e1 <= pc.TOL and e2 <= pc.TOL, (e1, e2)
+
+
 def test_poisson_kat_own_lapack(emu):  # poisson.rs:208-243, set-up through the library's own dgeev
     import rustpde_b200 as R
     from test_oracle_kat import POISSON_2D
@@ -77,6 +90,31 @@ def test_fast_diag_fourier(emu, nx, ny):
 def test_navier_confined(emu, nx, ny, adiabatic):
     err, derr, dn, do = pc.check_navier_steps(emu, False, nx, ny, 4, adiabatic=adiabatic, batch=2)
     assert max(derr) < 1e-9, (derr, dn, do)
+
+
+@pytest.mark.parametrize("nx,ny,adiabatic,own_eig", [(32, 33, True, False), (24, 33, False, True), (64, 65, True, True), (30, 65, True, False)])
+def test_navier_confined_specialised_kernels(emu, nx, ny, adiabatic, own_eig):
+    """Sizes served by the specialised x/y kernels (fast_x.cu / fast_y.cu): Bluestein DCT along x,
+    power-of-two DCT along y; own_eig also exercises the parity-split GEMMs."""
+    import rustpde_b200 as R
+    assert R.Navier2D.new(nx, ny, 1e5, 1.0, 0.01, 1.0, adiabatic, lib=emu).kernel_path() == (True, True)
+    err, derr, dn, do = pc.check_navier_steps(emu, False, nx, ny, 4, adiabatic=adiabatic, batch=2, own_eig=own_eig)
+    assert max(derr) < 1e-9, (derr, dn, do)
+
+
+def test_lane_program_and_specialised_kernels_agree(emu, monkeypatch):
+    """The generic lane programs and the specialised kernels implement the same step."""
+    import rustpde_b200 as R
+    outs = []
+    for no_fast in ("1", "0"):
+        monkeypatch.setenv("RUSTPDE_B200_NO_FAST", no_fast)
+        n = R.Navier2D.new(32, 33, 1e5, 1.0, 0.01, 1.0, True, lib=emu)
+        n.set_velocity(0.2, 1.0, 1.0)
+        n.set_temperature(0.2, 1.0, 1.0)
+        n.update(3)
+        outs.append((n.temp.vhat, n.ux.vhat, n.uy.vhat, n.pres[0].vhat))
+    for a, b in zip(*outs):
+        assert pc.rel(a, b) < 1e-11
 
 
 @pytest.mark.parametrize("nx,ny", [(16, 17), (24, 20)])

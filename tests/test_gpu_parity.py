@@ -134,6 +134,39 @@ def test_navier_confined(gpu, nx, ny, adiabatic, steps):
     assert max(derr) < 1e-9, (derr, dn, do)
 
 
+@pytest.mark.parametrize("nx,ny,adiabatic,steps,own_eig", [
+    (32, 33, True, 6, False),
+    (64, 65, False, 50, True),
+    (1024, 1025, True, 3, True),     # config-2 grid
+    (2048, 2049, True, 2, True),     # config-4 grid: the benchmark configuration itself
+])
+def test_navier_confined_specialised_kernels(gpu, nx, ny, adiabatic, steps, own_eig):
+    """The hand-specialised x/y pass kernels (Bluestein DCT along x, pow2 DCT along y) and, with own_eig,
+    the parity-split GEMMs on the library's own eigen set-up (exported to the oracle).
+    Fields <= 1e-9 relative, Nu / Nuvol / Re / |div| / Ekin <= 1e-9 relative."""
+    import rustpde_b200 as R
+    assert R.Navier2D.new(nx, ny, 1e5, 1.0, 0.01, 1.0, adiabatic, lib=gpu).kernel_path() == (True, True)
+    ra, dt = (1e5, 0.01) if nx < 1000 else (1e9, 1e-4)
+    err, derr, dn, do = pc.check_navier_steps(gpu, False, nx, ny, steps, ra=ra, dt=dt, adiabatic=adiabatic, tol=1e-9, batch=2, own_eig=own_eig)
+    assert max(derr) < 1e-9, (derr, dn, do)
+
+
+@pytest.mark.parametrize("which,kx,ky,nx,ny", [
+    ("poisson", "cheb_neumann", "cheb_neumann", 16, 19),
+    ("poisson", "cheb_dirichlet", "cheb_dirichlet", 141, 34),
+    ("hholtz", "cheb_dirichlet", "cheb_dirichlet", 512, 513),
+    ("poisson", "cheb_neumann", "cheb_neumann", 1024, 1025),
+])
+def test_fast_diag_parity_split(gpu, which, kx, ky, nx, ny):
+    """Parity-split mode: the library's own set-up (even/odd block diagonalisation, exactly checkerboard
+    Q and P) and two half-size DMMA GEMM pairs; the oracle consumes the exported (lam, Q, P).
+    Tolerance as in test_fast_diag_shared_eig: max(1e-10, 20 x summation-order floor of the oracle)."""
+    import oracle.solver as S
+    e1, e2 = pc.check_tensor_own_eig(gpu, which, kx, ky, nx, ny)
+    tol = 1e-10 if nx <= 141 else 1e-8
+    assert e1 <= tol and e2 <= tol, (e1, e2)
+
+
 @pytest.mark.parametrize("nx,ny,steps", [(16, 17, 6), (24, 20, 6), (128, 129, 50), (512, 513, 5)])
 def test_navier_periodic(gpu, nx, ny, steps):
     err, derr, dn, do = pc.check_navier_steps(gpu, True, nx, ny, steps, ra=1e6, dt=2e-3, tol=1e-9, batch=5)
