@@ -173,6 +173,127 @@ FK_DEV void fft(cplx* tc, const cplx* __restrict__ tw, const cplx* __restrict__ 
   fft_rec<LOG2L, NTHR, 0, INV, MUL>(tc, tw, mulv);
 }
 
+// ---- in-place decimation-in-frequency / decimation-in-time FFT pair ----------------
+// Used for the Bluestein convolution: forward DIF (natural in, digit-reversed out),
+// pointwise filter stored in the same digit-reversed order, inverse DIT (digit-
+// reversed in, natural out).  Every butterfly reads and writes the same rows, so
+// a thread can run its butterflies one after the other (8 values live instead of
+// all of them) and there is one barrier per stage.  Stage radices: 2^(LOG2L % 3)
+// first (span L), then 8 down to span 8 (DIF); mirrored for DIT.
+template <int R>
+FK_DEV void bfly_zero_half(cplx* v) {  // DFT-R of (v[0..R/2), 0, ..., 0)
+  if constexpr (R == 2) {
+    v[1] = v[0];
+  } else if constexpr (R == 4) {
+    const cplx a = v[0], b = v[1];
+    v[0] = cadd(a, b);
+    v[2] = csub(a, b);
+    v[1] = mk(a.x + b.y, a.y - b.x);
+    v[3] = mk(a.x - b.y, a.y + b.x);
+  } else {
+    const double h = 0.70710678118654752440;
+    // even-indexed inputs (v0, v2, 0, 0) and odd-indexed inputs (v1, v3, 0, 0)
+    const cplx e0 = cadd(v[0], v[2]), e2 = csub(v[0], v[2]);
+    const cplx e1 = mk(v[0].x + v[2].y, v[0].y - v[2].x), e3 = mk(v[0].x - v[2].y, v[0].y + v[2].x);
+    const cplx o0 = cadd(v[1], v[3]), o2 = csub(v[1], v[3]);
+    const cplx o1 = mk(v[1].x + v[3].y, v[1].y - v[3].x), o3 = mk(v[1].x - v[3].y, v[1].y + v[3].x);
+    const cplx b1 = mk(h * (o1.x + o1.y), h * (o1.y - o1.x));
+    const cplx b2 = mk(o2.y, -o2.x);
+    const cplx b3 = mk(h * (o3.y - o3.x), -h * (o3.x + o3.y));
+    v[0] = cadd(e0, o0);
+    v[4] = csub(e0, o0);
+    v[1] = cadd(e1, b1);
+    v[5] = csub(e1, b1);
+    v[2] = cadd(e2, b2);
+    v[6] = csub(e2, b2);
+    v[3] = cadd(e3, b3);
+    v[7] = csub(e3, b3);
+  }
+}
+
+// DIF stage of span S = 1 << LOG2S, radix R.  ZERO_HALF: rows >= L/2 hold zeros (not read).
+template <int LOG2L, int NTHR, int LOG2S, int R, bool ZERO_HALF>
+FK_DEV void dif_stage(cplx* tc, const cplx* __restrict__ tw) {
+  constexpr int L = 1 << LOG2L, S = 1 << LOG2S, SR = S / R;
+  constexpr int TOT = (L / R) * 2;
+#pragma unroll 2
+  for (int b = threadIdx.x; b < TOT; b += NTHR) {
+    const int u = b >> 1, c = b & 1;
+    const int q = u & (SR - 1), base = (u - q) * R + q;
+    cplx v[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) v[r] = (ZERO_HALF && r >= R / 2) ? mk(0.0, 0.0) : tc[cidx(base + r * SR, c)];
+    if (ZERO_HALF)
+      bfly_zero_half<R>(v);
+    else
+      Bfly<R>::run(v);
+    if (SR > 1) apply_twiddles<R>(v, __ldg(&tw[q * (L / S)]));
+#pragma unroll
+    for (int r = 0; r < R; ++r) tc[cidx(base + r * SR, c)] = v[r];
+  }
+  __syncthreads();
+}
+// inverse DIT stage (unnormalised): FIRST multiplies the loaded values by mulv[row]
+// and conjugates them, LAST conjugates the results; HALF_OUT: only rows < L/2 are stored.
+template <int LOG2L, int NTHR, int LOG2S, int R, bool FIRST, bool LAST, bool HALF_OUT>
+FK_DEV void dit_stage(cplx* tc, const cplx* __restrict__ tw, const cplx* __restrict__ mulv) {
+  constexpr int L = 1 << LOG2L, S = 1 << LOG2S, SR = S / R;
+  constexpr int TOT = (L / R) * 2;
+#pragma unroll 2
+  for (int b = threadIdx.x; b < TOT; b += NTHR) {
+    const int u = b >> 1, c = b & 1;
+    const int q = u & (SR - 1), base = (u - q) * R + q;
+    cplx v[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      cplx x = tc[cidx(base + r * SR, c)];
+      if (FIRST) {
+        x = cmul(x, __ldg(&mulv[base + r * SR]));
+        x.y = -x.y;
+      }
+      v[r] = x;
+    }
+    if (SR > 1) apply_twiddles<R>(v, __ldg(&tw[q * (L / S)]));
+    Bfly<R>::run(v);
+#pragma unroll
+    for (int r = 0; r < (HALF_OUT ? R / 2 : R); ++r) {
+      cplx x = v[r];
+      if (LAST) x.y = -x.y;
+      tc[cidx(base + r * SR, c)] = x;
+    }
+  }
+  __syncthreads();
+}
+template <int LOG2L, int NTHR, int LOG2S, bool ZERO_HALF>
+FK_DEV void fft_dif_rec(cplx* tc, const cplx* __restrict__ tw) {
+  if constexpr (LOG2S > 0) {
+    constexpr int LR = (LOG2S % 3) ? (LOG2S % 3) : 3;
+    dif_stage<LOG2L, NTHR, LOG2S, (1 << LR), ZERO_HALF && LOG2S == LOG2L>(tc, tw);
+    fft_dif_rec<LOG2L, NTHR, LOG2S - LR, ZERO_HALF>(tc, tw);
+  }
+}
+template <int LOG2L, int NTHR, int LOG2S, bool HALF_OUT>
+FK_DEV void fft_dit_rec(cplx* tc, const cplx* __restrict__ tw, const cplx* __restrict__ mulv) {
+  constexpr int LR = (LOG2S == LOG2L && (LOG2L % 3)) ? (LOG2L % 3) : 3;
+  constexpr bool last = (LOG2S == LOG2L);
+  dit_stage<LOG2L, NTHR, LOG2S, (1 << LR), LOG2S == 3, last, HALF_OUT && last>(tc, tw, mulv);
+  if constexpr (!last) {
+    constexpr int NEXT = (LOG2S + 3 > LOG2L) ? LOG2L : LOG2S + 3;
+    fft_dit_rec<LOG2L, NTHR, NEXT, HALF_OUT>(tc, tw, mulv);
+  }
+}
+// forward: natural order in, digit-reversed out (rows >= L/2 of the input are zero when ZERO_HALF)
+template <int LOG2L, int NTHR, bool ZERO_HALF>
+FK_DEV void fft_dif(cplx* tc, const cplx* __restrict__ tw) {
+  fft_dif_rec<LOG2L, NTHR, LOG2L, ZERO_HALF>(tc, tw);
+}
+// inverse of fft_dif (unnormalised) with the input first multiplied by mulv (digit-reversed order)
+template <int LOG2L, int NTHR, bool HALF_OUT>
+FK_DEV void fft_dit_inv(cplx* tc, const cplx* __restrict__ tw, const cplx* __restrict__ mulv) {
+  static_assert(LOG2L >= 3, "FFT length must be at least 8");
+  fft_dit_rec<LOG2L, NTHR, 3, HALF_OUT>(tc, tw, mulv);
+}
+
 // pre-combine of one pair (j, N-j): Chebyshev scaling of the backward transform
 // (ortho.rs:398-404), reduction of the length-2N even DFT to a length-N real DFT.
 template <bool BWD>
@@ -234,10 +355,21 @@ FK_DEV void dct_odd_scan(double* td, int N, double* red) {
       s += q[u];
     }
   }
+  // two-level carry: sums of groups of 8 chunks, then the chunks inside the group
+  double* red2 = red + NG * 4;
   red[g * 4 + lane] = s;
   __syncthreads();
+  if ((g & 7) == 0) {
+    double t = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (g + k < NG) t += red[(g + k) * 4 + lane];
+    red2[(g >> 3) * 4 + lane] = t;
+  }
+  __syncthreads();
   double y = 0.0;
-  for (int gg = 0; gg < g; ++gg) y += red[gg * 4 + lane];
+  for (int gg = 0; gg < (g >> 3); ++gg) y += red2[gg * 4 + lane];
+  for (int gg = (g & ~7); gg < g; ++gg) y += red[gg * 4 + lane];
   const double ho = BWD ? 1.0 : -1.0 / (double)N;
 #pragma unroll
   for (int u = 0; u < CLR; ++u) {
@@ -311,11 +443,11 @@ FK_DEV void dct_bluestein(const double* ta, double* tw_, const DctTab& T, double
     W[cidx(j, c)] = cmul(za, __ldg(&T.chirp[j]));
     if (jm != j && j != 0) W[cidx(jm, c)] = cmul(zb, __ldg(&T.chirp[jm]));
   }
-  for (int it = 2 * N + tid; it < 2 * LB; it += NTHR) W[cidx(it >> 1, c)] = mk(0.0, 0.0);
+  for (int it = 2 * N + tid; it < LB; it += NTHR) W[cidx(it >> 1, c)] = mk(0.0, 0.0);  // rows [N, LB/2)
   reduce_f1<NTHR>(f1, f1red);
   __syncthreads();
-  fft<LOG2LB, NTHR, false, false>(W, T.tw, nullptr);
-  fft<LOG2LB, NTHR, true, true>(W, T.tw, T.bhat);
+  fft_dif<LOG2LB, NTHR, true>(W, T.tw);
+  fft_dit_inv<LOG2LB, NTHR, true>(W, T.tw, T.bhat);
   const int Ko = (N - 1) / 2;
   for (int it = tid; it < NP * 2; it += NTHR) {
     const int k = it >> 1;
@@ -362,11 +494,27 @@ FK_DEV void scan1(int n, double* red, In in, C1 c1, Out out) {
       A *= k;
     }
   }
+  // two-level carry: maps of groups of 8 chunks, then the chunks inside the group
+  double* red2 = red + NG * 16;
   red[(g * 8 + ch) * 2] = A;
   red[(g * 8 + ch) * 2 + 1] = b;
   __syncthreads();
+  if ((g & 7) == 0) {
+    double Ag = 1.0, bg = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (g + k < NG) {
+        const double Ak = red[((g + k) * 8 + ch) * 2], bk = red[((g + k) * 8 + ch) * 2 + 1];
+        bg = fma(Ak, bg, bk);
+        Ag *= Ak;
+      }
+    red2[((g >> 3) * 8 + ch) * 2] = Ag;
+    red2[((g >> 3) * 8 + ch) * 2 + 1] = bg;
+  }
+  __syncthreads();
   double y = 0.0;
-  for (int gg = 0; gg < g; ++gg) y = fma(red[(gg * 8 + ch) * 2], y, red[(gg * 8 + ch) * 2 + 1]);
+  for (int gg = 0; gg < (g >> 3); ++gg) y = fma(red2[(gg * 8 + ch) * 2], y, red2[(gg * 8 + ch) * 2 + 1]);
+  for (int gg = (g & ~7); gg < g; ++gg) y = fma(red[(gg * 8 + ch) * 2], y, red[(gg * 8 + ch) * 2 + 1]);
 #pragma unroll
   for (int u = 0; u < CL; ++u) {
     const int t = t0 + u;
@@ -409,8 +557,32 @@ FK_DEV void scan2(int n, double* red, In in, C1 c1, C2 c2, Out out) {
   double* r = red + (g * 8 + ch) * 6;
   r[0] = a1, r[1] = b1, r[2] = p1, r[3] = a2, r[4] = b2, r[5] = p2;
   __syncthreads();
+  // two-level carry: maps of groups of 8 chunks, then the chunks inside the group
+  double* red2 = red + NG * 48;
+  if ((g & 7) == 0) {
+    // group map  [y1; y2] -> G [y1; y2] + h,  G = [g11 g12; g21 g22]
+    double g11 = 1.0, g12 = 0.0, g21 = 0.0, g22 = 1.0, h1 = 0.0, h2 = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (g + k < NG) {
+        const double* rr = red + ((g + k) * 8 + ch) * 6;
+        const double n11 = fma(rr[0], g11, rr[1] * g21), n12 = fma(rr[0], g12, rr[1] * g22);
+        const double n21 = fma(rr[3], g11, rr[4] * g21), n22 = fma(rr[3], g12, rr[4] * g22);
+        const double m1 = fma(rr[0], h1, fma(rr[1], h2, rr[2])), m2 = fma(rr[3], h1, fma(rr[4], h2, rr[5]));
+        g11 = n11, g12 = n12, g21 = n21, g22 = n22, h1 = m1, h2 = m2;
+      }
+    double* w = red2 + ((g >> 3) * 8 + ch) * 6;
+    w[0] = g11, w[1] = g12, w[2] = h1, w[3] = g21, w[4] = g22, w[5] = h2;
+  }
+  __syncthreads();
   double y1 = 0.0, y2 = 0.0;
-  for (int gg = 0; gg < g; ++gg) {
+  for (int gg = 0; gg < (g >> 3); ++gg) {
+    const double* rr = red2 + (gg * 8 + ch) * 6;
+    const double n1 = fma(rr[0], y1, fma(rr[1], y2, rr[2]));
+    const double n2 = fma(rr[3], y1, fma(rr[4], y2, rr[5]));
+    y1 = n1, y2 = n2;
+  }
+  for (int gg = (g & ~7); gg < g; ++gg) {
     const double* rr = red + (gg * 8 + ch) * 6;
     const double n1 = fma(rr[0], y1, fma(rr[1], y2, rr[2]));
     const double n2 = fma(rr[3], y1, fma(rr[4], y2, rr[5]));

@@ -22,7 +22,7 @@ struct DctTab {
   const double2* sc;     // (sin, cos)(pi j / N), j = 0..N/2
   const double2* tw;     // exp(-2 pi i k / L), L = N (pow2) or Lb (Bluestein)
   const double2* chirp;  // Bluestein: exp(-i pi j^2 / N), j < N
-  const double2* bhat;   // Bluestein: FFT_Lb(wrapped conj chirp) / Lb
+  const double2* bhat;   // Bluestein: FFT_Lb(wrapped conj chirp) / Lb, in the digit-reversed order of fft_dif (fast.cuh)
 };
 struct FdmaTabs {  // pre-swept banded solve (tables.h FdmaDev)
   const double *fp, *bs, *bp1, *bp2;
@@ -52,7 +52,10 @@ struct YBackwardArgs {  // B_y S_y (value), B_y D_y S_y / sy, and B_y S_y of a s
   double isy;
   DctTab t;
 };
-void launch_y_backward(const YBackwardArgs& a, cudaStream_t s);
+struct YBackwardArgs3 {
+  YBackwardArgs a[3];
+};
+void launch_y_backward(const YBackwardArgs3& a, int nbatch, cudaStream_t s);  // nbatch independent fields, one launch
 
 struct YConvArgs {  // out = cut_y(F_y(u * (du + bcx) + v * (dv + bcy)))   (conv_term.rs:41)
   Mat u, du, v, dv, bcx, bcy;  // bcx/bcy.p may be null
@@ -60,7 +63,10 @@ struct YConvArgs {  // out = cut_y(F_y(u * (du + bcx) + v * (dv + bcy)))   (conv
   int cut;  // first zeroed y mode (navier.rs:1029), >= ny: none
   DctTab t;
 };
-void launch_y_conv(const YConvArgs& a, cudaStream_t s);
+struct YConvArgs3 {
+  YConvArgs a[3];
+};
+void launch_y_conv(const YConvArgs3& a, int nbatch, cudaStream_t s);
 
 struct YAdiArgs {  // y half of HholtzAdi (hholtz_adi.rs:113,129) + pieces of the divergence
   Mat w;           // [mx, ny]
@@ -73,7 +79,10 @@ struct YAdiArgs {  // y half of HholtzAdi (hholtz_adi.rs:113,129) + pieces of th
   FdmaTabs f;
   int ny;
 };
-void launch_y_adi(const YAdiArgs& a, cudaStream_t s);
+struct YAdiArgs3 {
+  YAdiArgs a[3];
+};
+void launch_y_adi(const YAdiArgs3& a, int nbatch, cudaStream_t s);
 
 struct YModeArgs {  // per-mode banded solve of the fast diagonalisation (fdma_tensor.rs:219-227)
   Mat g;            // [mx, ny]
@@ -112,7 +121,10 @@ struct XBackwardArgs {  // B_x S_x u^ and B_x D_x S_x u^ / sx
   double isx;
   DctTab t;
 };
-void launch_x_backward(const XBackwardArgs& a, cudaStream_t s);
+struct XBackwardArgs3 {
+  XBackwardArgs a[3];
+};
+void launch_x_backward(const XBackwardArgs3& a, int nbatch, cudaStream_t s);
 
 struct XForwardArgs {  // forward DCT-x + dealias + rhs assembly + x half of HholtzAdi
   Mat conv;            // [nx, ny] after the y-forward transform
@@ -131,7 +143,10 @@ struct XForwardArgs {  // forward DCT-x + dealias + rhs assembly + x half of Hho
   FdmaTabs f;
   DctTab t;
 };
-void launch_x_forward(const XForwardArgs& a, cudaStream_t s);
+struct XForwardArgs3 {
+  XForwardArgs a[3];
+};
+void launch_x_forward(const XForwardArgs3& a, int nbatch, cudaStream_t s);
 
 struct XDivArgs {  // div = D_x S_x vx / sx + S_x ey ; r1 = B2_x div
   Mat vx, ey;      // [mx, ny]

@@ -20,8 +20,8 @@ struct XCfg {
   static constexpr int NTHR = (LB / 8) < 64 ? 64 : (LB / 8);
   static constexpr int AROWS = LB / 2 + 4;
   static constexpr int CL = chunk_len(NMAX, NTHR);
-  static constexpr int SMEM_A = AROWS * 32 + NTHR * 48;
-  static constexpr int SMEM_AW = (AROWS + LB) * 32 + NTHR * 48;
+  static constexpr int SMEM_A = AROWS * 32 + NTHR * 56 + 512;
+  static constexpr int SMEM_AW = (AROWS + LB) * 32 + NTHR * 56 + 512;
 };
 
 #define FK_FILL_U 8
@@ -70,8 +70,9 @@ FK_DEV double ld_stencil_xy(const Mat& f, int i, int j, const double* __restrict
 
 // ---------------------------------------------------------------------------------
 template <int LOG2LB>
-__global__ void __launch_bounds__(XCfg<LOG2LB>::NTHR, 1) xk_backward(XBackwardArgs a) {
+__global__ void __launch_bounds__(XCfg<LOG2LB>::NTHR, 1) xk_backward(XBackwardArgs3 a3) {
   typedef XCfg<LOG2LB> C;
+  const XBackwardArgs& a = a3.a[blockIdx.y];
   RP_DYN_SMEM(double, ta);
   double* tw = ta + C::AROWS * 4;
   double* red = tw + C::LB * 4;
@@ -92,8 +93,9 @@ __global__ void __launch_bounds__(XCfg<LOG2LB>::NTHR, 1) xk_backward(XBackwardAr
 }
 
 template <int LOG2LB>
-__global__ void __launch_bounds__(XCfg<LOG2LB>::NTHR, 1) xk_forward(XForwardArgs a) {
+__global__ void __launch_bounds__(XCfg<LOG2LB>::NTHR, 1) xk_forward(XForwardArgs3 a3) {
   typedef XCfg<LOG2LB> C;
+  const XForwardArgs& a = a3.a[blockIdx.y];
   RP_DYN_SMEM(double, ta);
   double* tw = ta + C::AROWS * 4;
   double* red = tw + C::LB * 4;
@@ -227,16 +229,17 @@ static void set_smem(K kern, int bytes) {
       set_smem(kern<L>, sm_);                                                    \
       init_ = true;                                                              \
     }                                                                            \
-    RP_LAUNCH(kern<L>, dim3(nb_), dim3(C::NTHR), (size_t)sm_, s, a);             \
+    RP_LAUNCH(kern<L>, dim3(nb_, nby_), dim3(C::NTHR), (size_t)sm_, s, a);             \
     ok_ = true;                                                                  \
   }
 #define XK_CASE_xk_backward(L) XK_CASE_BODY(xk_backward, L, C::SMEM_AW)
 #define XK_CASE_xk_forward(L) XK_CASE_BODY(xk_forward, L, C::SMEM_AW)
 #define XK_CASE_xk_div(L) XK_CASE_BODY(xk_div, L, C::SMEM_A)
-#define XK_CASE_xk_project(L) XK_CASE_BODY(xk_project, L, 2 * C::AROWS * 32 + C::NTHR * 48)
+#define XK_CASE_xk_project(L) XK_CASE_BODY(xk_project, L, 2 * C::AROWS * 32 + C::NTHR * 56 + 512)
 
-#define XK_LAUNCH(kern, ncols, nx)                                                 \
+#define XK_LAUNCH(kern, ncols, nx, nby)                                            \
   do {                                                                             \
+    const int nby_ = (nby);                                                        \
     const int l_ = bluestein_log2(nx);                                             \
     const int nb_ = ((ncols) + 3) / 4;                                             \
     bool ok_ = false;                                                              \
@@ -244,10 +247,10 @@ static void set_smem(K kern, int bytes) {
     if (!ok_) throw Error(RP_ERR_INTERNAL, #kern ": unsupported lane length");     \
   } while (0)
 
-void launch_x_backward(const XBackwardArgs& a, cudaStream_t s) { XK_LAUNCH(xk_backward, a.src.cols, a.t.n); }
-void launch_x_forward(const XForwardArgs& a, cudaStream_t s) { XK_LAUNCH(xk_forward, a.conv.cols, a.t.n); }
-void launch_x_div(const XDivArgs& a, cudaStream_t s) { XK_LAUNCH(xk_div, a.vx.cols, a.nx); }
-void launch_x_project(const XProjectArgs& a, cudaStream_t s) { XK_LAUNCH(xk_project, a.phi.cols, a.nx); }
+void launch_x_backward(const XBackwardArgs3& a, int nb, cudaStream_t s) { XK_LAUNCH(xk_backward, a.a[0].src.cols, a.a[0].t.n, nb); }
+void launch_x_forward(const XForwardArgs3& a, int nb, cudaStream_t s) { XK_LAUNCH(xk_forward, a.a[0].conv.cols, a.a[0].t.n, nb); }
+void launch_x_div(const XDivArgs& a, cudaStream_t s) { XK_LAUNCH(xk_div, a.vx.cols, a.nx, 1); }
+void launch_x_project(const XProjectArgs& a, cudaStream_t s) { XK_LAUNCH(xk_project, a.phi.cols, a.nx, 1); }
 
 }  // namespace fk
 }  // namespace rp

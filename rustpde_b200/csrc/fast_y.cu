@@ -17,11 +17,11 @@ template <int LOG2L>
 struct YCfg {
   static constexpr int N = 1 << LOG2L;
   static constexpr int n = N + 1;
-  static constexpr int NTHR = (N / 8) < 64 ? 64 : (N / 8);
+  static constexpr int NTHR = (N / 4) < 64 ? 64 : (N / 4);
   static constexpr int ROWS = N + 4;
   static constexpr int CL = chunk_len(n, NTHR);
-  static constexpr int SMEM1 = ROWS * 32 + NTHR * 48;      // one tile + scratch
-  static constexpr int SMEM2 = 2 * ROWS * 32 + NTHR * 48;  // two tiles + scratch
+  static constexpr int SMEM1 = ROWS * 32 + NTHR * 56 + 512;      // one tile + scratch
+  static constexpr int SMEM2 = 2 * ROWS * 32 + NTHR * 56 + 512;  // two tiles + scratch
 };
 
 #define YK_SMEM(td, red)          \
@@ -70,8 +70,9 @@ FK_DEV double ld_stencil(const Mat& a, int r, int j, int m, const double* __rest
 
 // ---------------------------------------------------------------------------------
 template <int LOG2L>
-__global__ void __launch_bounds__(YCfg<LOG2L>::NTHR, 2) yk_backward(YBackwardArgs a) {
+__global__ void __launch_bounds__(YCfg<LOG2L>::NTHR, 2) yk_backward(YBackwardArgs3 a3) {
   typedef YCfg<LOG2L> C;
+  const YBackwardArgs& a = a3.a[blockIdx.y];
   YK_SMEM(td, red);
   const int r0 = blockIdx.x * 4;
   constexpr int n = C::n, m = n - 2, N = C::N;
@@ -101,8 +102,9 @@ __global__ void __launch_bounds__(YCfg<LOG2L>::NTHR, 2) yk_backward(YBackwardArg
 }
 
 template <int LOG2L>
-__global__ void __launch_bounds__(YCfg<LOG2L>::NTHR, 2) yk_conv(YConvArgs a) {
+__global__ void __launch_bounds__(YCfg<LOG2L>::NTHR, 2) yk_conv(YConvArgs3 a3) {
   typedef YCfg<LOG2L> C;
+  const YConvArgs& a = a3.a[blockIdx.y];
   YK_SMEM(td, red);
   const int r0 = blockIdx.x * 4;
   constexpr int n = C::n, N = C::N;
@@ -122,8 +124,9 @@ __global__ void __launch_bounds__(YCfg<LOG2L>::NTHR, 2) yk_conv(YConvArgs a) {
 }
 
 template <int LOG2L>
-__global__ void __launch_bounds__(YCfg<LOG2L>::NTHR, 2) yk_adi(YAdiArgs a) {
+__global__ void __launch_bounds__(YCfg<LOG2L>::NTHR, 2) yk_adi(YAdiArgs3 a3) {
   typedef YCfg<LOG2L> C;
+  const YAdiArgs& a = a3.a[blockIdx.y];
   YK_SMEM(td, red);
   const int r0 = blockIdx.x * 4;
   constexpr int n = C::n, m = n - 2;
@@ -295,8 +298,9 @@ static void set_smem(K kern, int bytes) {
 #endif
 }
 
-#define YK_LAUNCH(kern, two_tiles, nrows, ny, args)                                                   \
+#define YK_LAUNCH(kern, two_tiles, nrows, ny, args, nby)                                              \
   do {                                                                                                \
+    const int nby_ = (nby);                                                                           \
     const int l_ = log2_of((ny)-1);                                                                   \
     const int nb_ = ((nrows) + 3) / 4;                                                                \
     bool ok_ = false;                                                                                 \
@@ -313,7 +317,7 @@ static void set_smem(K kern, int bytes) {
       set_smem(kern<L>, sm_);                                                                 \
       init_ = true;                                                                           \
     }                                                                                         \
-    RP_LAUNCH(kern<L>, dim3(nb_), dim3(C::NTHR), (size_t)sm_, s, args);                       \
+    RP_LAUNCH(kern<L>, dim3(nb_, nby_), dim3(C::NTHR), (size_t)sm_, s, args);                       \
     ok_ = true;                                                                               \
   }
 
@@ -324,12 +328,12 @@ static void set_smem(K kern, int bytes) {
 #define YK_CASE_yk_project(L) YK_CASE_BODY(yk_project, L, false, a)
 #define YK_CASE_yk_pres(L) YK_CASE_BODY(yk_pres, L, false, a)
 
-void launch_y_backward(const YBackwardArgs& a, cudaStream_t s) { YK_LAUNCH(yk_backward, false, a.a.rows, a.t.n, a); }
-void launch_y_conv(const YConvArgs& a, cudaStream_t s) { YK_LAUNCH(yk_conv, false, a.u.rows, a.t.n, a); }
-void launch_y_adi(const YAdiArgs& a, cudaStream_t s) { YK_LAUNCH(yk_adi, false, a.w.rows, a.ny, a); }
-void launch_y_mode(const YModeArgs& a, cudaStream_t s) { YK_LAUNCH(yk_mode, true, a.g.rows, a.ny, a); }
-void launch_y_project(const YProjectArgs& a, cudaStream_t s) { YK_LAUNCH(yk_project, false, a.a1.rows, a.ny, a); }
-void launch_y_pres(const YPresArgs& a, cudaStream_t s) { YK_LAUNCH(yk_pres, false, a.pres.rows, a.ny, a); }
+void launch_y_backward(const YBackwardArgs3& a, int nb, cudaStream_t s) { YK_LAUNCH(yk_backward, false, a.a[0].a.rows, a.a[0].t.n, a, nb); }
+void launch_y_conv(const YConvArgs3& a, int nb, cudaStream_t s) { YK_LAUNCH(yk_conv, false, a.a[0].u.rows, a.a[0].t.n, a, nb); }
+void launch_y_adi(const YAdiArgs3& a, int nb, cudaStream_t s) { YK_LAUNCH(yk_adi, false, a.a[0].w.rows, a.a[0].ny, a, nb); }
+void launch_y_mode(const YModeArgs& a, cudaStream_t s) { YK_LAUNCH(yk_mode, true, a.g.rows, a.ny, a, 1); }
+void launch_y_project(const YProjectArgs& a, cudaStream_t s) { YK_LAUNCH(yk_project, false, a.a1.rows, a.ny, a, 1); }
+void launch_y_pres(const YPresArgs& a, cudaStream_t s) { YK_LAUNCH(yk_pres, false, a.pres.rows, a.ny, a, 1); }
 
 }  // namespace fk
 }  // namespace rp

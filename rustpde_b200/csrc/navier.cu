@@ -418,7 +418,7 @@ static fk::DctTab dct_of(const Base& b) {
   t.sc = b.d_sc.as<double2>();
   t.tw = b.fft.plan.tw;
   t.chirp = b.fft.plan.chirp;
-  t.bhat = b.fft.plan.bhat;
+  t.bhat = b.fft.bhat_dr.as<double2>();
   return t;
 }
 static fk::B2Tabs b2_of(const Base& b) {
@@ -455,83 +455,99 @@ void Navier2D::build_step_confined_fast() {
   const double fb = 8.0 * (double)nx * (double)ny;  // bytes of one field sweep
   // phys_: 0 ux, 1 uy, 2 dxu, 3 dyu, 4 dxv, 5 dyv, 6 dxT, 7 dyT
   const int val_idx[3] = {0, 1, -1}, dx_idx[3] = {2, 4, 6}, dy_idx[3] = {3, 5, 7};
+  // Each group of three independent passes (ux, uy, T) is one launch (blockIdx.y = field).
   // ---- 1. x-backward: value and d/dx of ux, uy, T ------------------------
-  for (int f = 0; f < 3; ++f) {
-    fk::XBackwardArgs a;
-    a.src = mat_of(flds[f]->vhat);
-    a.val = mat_of(ax_[f]);
-    a.dx = mat_of(adx_[f]);
-    a.sd = bxs[f]->d_sd.as<double>();
-    a.sl = bxs[f]->d_sl.as<double>();
-    a.isx = isx;
-    a.t = dct_of(bxo);
-    add_fast("x_backward_dct", 3 * fb, [this, a]() { fk::launch_x_backward(a, stream); });
+  {
+    fk::XBackwardArgs3 a3;
+    for (int f = 0; f < 3; ++f) {
+      fk::XBackwardArgs& a = a3.a[f];
+      a.src = mat_of(flds[f]->vhat);
+      a.val = mat_of(ax_[f]);
+      a.dx = mat_of(adx_[f]);
+      a.sd = bxs[f]->d_sd.as<double>();
+      a.sl = bxs[f]->d_sl.as<double>();
+      a.isx = isx;
+      a.t = dct_of(bxo);
+    }
+    add_fast("x_backward_dct", 9 * fb, [this, a3]() { fk::launch_x_backward(a3, 3, stream); });
   }
   // ---- 2. y-backward -> physical space ------------------------------------
-  for (int f = 0; f < 3; ++f) {
-    fk::YBackwardArgs a;
-    a.a = mat_of(ax_[f]);
-    a.adx = mat_of(adx_[f]);
-    a.val = val_idx[f] >= 0 ? mat_of(phys_[val_idx[f]]) : fk::Mat{nullptr, 0, 0, 0};
-    a.dy = mat_of(phys_[dy_idx[f]]);
-    a.dx = mat_of(phys_[dx_idx[f]]);
-    a.sd = bys[f]->d_sd.as<double>();
-    a.sl = bys[f]->d_sl.as<double>();
-    a.isy = isy;
-    a.t = dct_of(byo);
-    add_fast("y_backward", (val_idx[f] >= 0 ? 5 : 4) * fb, [this, a]() { fk::launch_y_backward(a, stream); });
+  {
+    fk::YBackwardArgs3 a3;
+    for (int f = 0; f < 3; ++f) {
+      fk::YBackwardArgs& a = a3.a[f];
+      a.a = mat_of(ax_[f]);
+      a.adx = mat_of(adx_[f]);
+      a.val = val_idx[f] >= 0 ? mat_of(phys_[val_idx[f]]) : fk::Mat{nullptr, 0, 0, 0};
+      a.dy = mat_of(phys_[dy_idx[f]]);
+      a.dx = mat_of(phys_[dx_idx[f]]);
+      a.sd = bys[f]->d_sd.as<double>();
+      a.sl = bys[f]->d_sl.as<double>();
+      a.isy = isy;
+      a.t = dct_of(byo);
+    }
+    add_fast("y_backward", 14 * fb, [this, a3]() { fk::launch_y_backward(a3, 3, stream); });
   }
   // ---- 3. products + forward DCT-y + dealias-y -----------------------------
-  for (int f = 0; f < 3; ++f) {
-    fk::YConvArgs a;
-    a.u = mat_of(phys_[0]);
-    a.du = mat_of(phys_[dx_idx[f]]);
-    a.v = mat_of(phys_[1]);
-    a.dv = mat_of(phys_[dy_idx[f]]);
-    a.bcx = f == 2 ? mat_of(dxtbc_) : fk::Mat{nullptr, 0, 0, 0};
-    a.bcy = f == 2 ? mat_of(dytbc_) : fk::Mat{nullptr, 0, 0, 0};
-    a.out = mat_of(bconv_[f]);
-    a.cut = dealias ? (ny * 2) / 3 : ny;  // navier.rs:1029
-    a.t = dct_of(byo);
-    add_fast("conv_y_forward", (f == 2 ? 7 : 5) * fb, [this, a]() { fk::launch_y_conv(a, stream); });
+  {
+    fk::YConvArgs3 a3;
+    for (int f = 0; f < 3; ++f) {
+      fk::YConvArgs& a = a3.a[f];
+      a.u = mat_of(phys_[0]);
+      a.du = mat_of(phys_[dx_idx[f]]);
+      a.v = mat_of(phys_[1]);
+      a.dv = mat_of(phys_[dy_idx[f]]);
+      a.bcx = f == 2 ? mat_of(dxtbc_) : fk::Mat{nullptr, 0, 0, 0};
+      a.bcy = f == 2 ? mat_of(dytbc_) : fk::Mat{nullptr, 0, 0, 0};
+      a.out = mat_of(bconv_[f]);
+      a.cut = dealias ? (ny * 2) / 3 : ny;  // navier.rs:1029
+      a.t = dct_of(byo);
+    }
+    add_fast("conv_y_forward", 17 * fb, [this, a3]() { fk::launch_y_conv(a3, 3, stream); });
   }
   // ---- 4. x-forward + dealias + rhs assembly + x half of HholtzAdi ---------
-  for (int f = 0; f < 3; ++f) {
-    fk::XForwardArgs a;
-    a.conv = mat_of(bconv_[f]);
-    a.out = mat_of(w_[f]);
-    a.cut = dealias ? (nx * 2) / 3 : nx;  // navier.rs:1028
-    a.dt = dt;
-    a.fld = mat_of(flds[f]->vhat);
-    a.fxsd = bxs[f]->d_sd.as<double>(), a.fxsl = bxs[f]->d_sl.as<double>();
-    a.fysd = bys[f]->d_sd.as<double>(), a.fysl = bys[f]->d_sl.as<double>();
-    a.mode = f;
-    a.pres = mat_of(pres0->vhat);
-    a.dyp = mat_of(dyp_);
-    a.tmp = mat_of(temp->vhat);
-    a.tbc = mat_of(tbc_ortho_);
-    a.bcdiff = mat_of(bcdiff_);
-    a.txsd = bxt.d_sd.as<double>(), a.txsl = bxt.d_sl.as<double>();
-    a.tysd = byt.d_sd.as<double>(), a.tysl = byt.d_sl.as<double>();
-    a.isx = isx;
-    a.b2 = b2_of(bxo);
-    a.f = fdma_of(solver[f]->adi[0].fdma);
-    a.t = dct_of(bxo);
-    add_fast("x_forward_rhs_adi_x", (f == 1 ? 6 : 4) * fb, [this, a]() { fk::launch_x_forward(a, stream); });
+  {
+    fk::XForwardArgs3 a3;
+    for (int f = 0; f < 3; ++f) {
+      fk::XForwardArgs& a = a3.a[f];
+      a.conv = mat_of(bconv_[f]);
+      a.out = mat_of(w_[f]);
+      a.cut = dealias ? (nx * 2) / 3 : nx;  // navier.rs:1028
+      a.dt = dt;
+      a.fld = mat_of(flds[f]->vhat);
+      a.fxsd = bxs[f]->d_sd.as<double>(), a.fxsl = bxs[f]->d_sl.as<double>();
+      a.fysd = bys[f]->d_sd.as<double>(), a.fysl = bys[f]->d_sl.as<double>();
+      a.mode = f;
+      a.pres = mat_of(pres0->vhat);
+      a.dyp = mat_of(dyp_);
+      a.tmp = mat_of(temp->vhat);
+      a.tbc = mat_of(tbc_ortho_);
+      a.bcdiff = mat_of(bcdiff_);
+      a.txsd = bxt.d_sd.as<double>(), a.txsl = bxt.d_sl.as<double>();
+      a.tysd = byt.d_sd.as<double>(), a.tysl = byt.d_sl.as<double>();
+      a.isx = isx;
+      a.b2 = b2_of(bxo);
+      a.f = fdma_of(solver[f]->adi[0].fdma);
+      a.t = dct_of(bxo);
+    }
+    add_fast("x_forward_rhs_adi_x", 14 * fb, [this, a3]() { fk::launch_x_forward(a3, 3, stream); });
   }
   // ---- 5. y half of HholtzAdi (+ pieces of the divergence) -----------------
-  for (int f = 0; f < 3; ++f) {
-    fk::YAdiArgs a;
-    a.w = mat_of(w_[f]);
-    a.out = mat_of(flds[f]->vhat);
-    a.aux = f == 0 ? mat_of(vx_) : (f == 1 ? mat_of(ey_) : fk::Mat{nullptr, 0, 0, 0});
-    a.mode = f == 0 ? 1 : (f == 1 ? 2 : 0);
-    a.sd = byu.d_sd.as<double>(), a.sl = byu.d_sl.as<double>();
-    a.isy = isy;
-    a.b2 = b2_of(byo);
-    a.f = fdma_of(solver[f]->adi[1].fdma);
-    a.ny = ny;
-    add_fast("adi_y", (f == 2 ? 2 : 3) * fb, [this, a]() { fk::launch_y_adi(a, stream); });
+  {
+    fk::YAdiArgs3 a3;
+    for (int f = 0; f < 3; ++f) {
+      fk::YAdiArgs& a = a3.a[f];
+      a.w = mat_of(w_[f]);
+      a.out = mat_of(flds[f]->vhat);
+      a.aux = f == 0 ? mat_of(vx_) : (f == 1 ? mat_of(ey_) : fk::Mat{nullptr, 0, 0, 0});
+      a.mode = f == 0 ? 1 : (f == 1 ? 2 : 0);
+      a.sd = byu.d_sd.as<double>(), a.sl = byu.d_sl.as<double>();
+      a.isy = isy;
+      a.b2 = b2_of(byo);
+      a.f = fdma_of(solver[f]->adi[1].fdma);
+      a.ny = ny;
+    }
+    add_fast("adi_y", 8 * fb, [this, a3]() { fk::launch_y_adi(a3, 3, stream); });
   }
   // ---- 6. divergence (navier.rs:698-703) + B2x of the Poisson rhs ----------
   {

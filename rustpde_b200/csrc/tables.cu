@@ -80,6 +80,22 @@ void build_fft_tables(int L, FftTables& out) {
     }
     out.chirp = upload(chirp);
     out.bhat = upload(bhat);
+    // position of X[k] after the in-place DIF stages (radix 2^(log2 Lb % 3) first, then 8)
+    int lg = 0;
+    while ((1 << lg) < P.Lb) ++lg;
+    std::vector<double2> bdr(P.Lb);
+    for (int k = 0; k < P.Lb; ++k) {
+      int kk = k, span = P.Lb, pos = 0, ls = lg;
+      while (span > 1) {
+        const int lr = (ls % 3) ? (ls % 3) : 3, R = 1 << lr;
+        pos += (kk % R) * (span / R);
+        kk /= R;
+        span /= R;
+        ls -= lr;
+      }
+      bdr[pos] = bhat[k];
+    }
+    out.bhat_dr = upload(bdr);
     P.chirp = out.chirp.as<double2>();
     P.bhat = out.bhat.as<double2>();
   }

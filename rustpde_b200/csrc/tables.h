@@ -76,6 +76,7 @@ struct Diags {
 struct FftTables {
   FftPlan plan;  // pointers into the buffers below
   DevBuf tw, chirp, bhat;
+  DevBuf bhat_dr;  // bhat in the digit-reversed order of the in-place DIF FFT (fast.cuh fft_dif)
   int fft_len() const { return plan.pow2 ? plan.L : plan.Lb; }
 };
 void build_fft_tables(int L, FftTables& out);
