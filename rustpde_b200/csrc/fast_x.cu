@@ -110,23 +110,38 @@ __global__ void __launch_bounds__(XCfg<LOG2LB>::NTHR, 1) xk_forward(XForwardArgs
     __syncthreads();
     cheb_diff<C::NTHR, C::CL>(ta, -1, ta, -1, n, -a.dt * a.isx, red);
   }
-  for (int it = threadIdx.x; it < n * 4; it += C::NTHR) {
-    const int l = it & 3, i = it >> 2, j = c0 + l;
-    double* w = &tw[didx(rowof(N, i), l)];
-    double v = (i < a.cut) ? -a.dt * (*w) : 0.0;  // - dt * dealiased conv   (navier.rs:630, 651, 671)
-    if (j < ncols) {
-      v += ld_stencil_xy(a.fld, i, j, a.fxsd, a.fxsl, a.fysd, a.fysl);  // + to_ortho(field)
-      if (a.mode == 0) {
-        v += ta[didx(i, l)];
-      } else if (a.mode == 1) {  // - dt/sy d/dy pres + dt * (that + tbc)   (navier.rs:646-648)
-        v = fma(-a.dt, a.dyp.p[(size_t)i * a.dyp.ld + j], v);
-        const double that = ld_stencil_xy(a.tmp, i, j, a.txsd, a.txsl, a.tysd, a.tysl) + a.tbc.p[(size_t)i * a.tbc.ld + j];
-        v = fma(a.dt, that, v);
-      } else {  // + dt ka (dxx + dyy) fieldbc   (navier.rs:665-668)
-        v += a.bcdiff.p[(size_t)i * a.bcdiff.ld + j];
+  // rhs terms read from global memory: batches of 4 elements per thread so that the loads overlap
+  auto rhs_terms = [&](int i, int l) -> double {
+    const int j = c0 + l;
+    if (j >= ncols) return 0.0;
+    double v = ld_stencil_xy(a.fld, i, j, a.fxsd, a.fxsl, a.fysd, a.fysl);  // + to_ortho(field)
+    if (a.mode == 1) {  // - dt/sy d/dy pres + dt * (that + tbc)   (navier.rs:646-648)
+      v = fma(-a.dt, a.dyp.p[(size_t)i * a.dyp.ld + j], v);
+      const double that = ld_stencil_xy(a.tmp, i, j, a.txsd, a.txsl, a.tysd, a.tysl) + a.tbc.p[(size_t)i * a.tbc.ld + j];
+      v = fma(a.dt, that, v);
+    } else if (a.mode == 2) {  // + dt ka (dxx + dyy) fieldbc   (navier.rs:665-668)
+      v += a.bcdiff.p[(size_t)i * a.bcdiff.ld + j];
+    }
+    return v;
+  };
+  for (int it0 = threadIdx.x; it0 < n * 4; it0 += C::NTHR * 4) {
+    double add[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int it = it0 + u * C::NTHR;
+      add[u] = it < n * 4 ? rhs_terms(it >> 2, it & 3) : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int it = it0 + u * C::NTHR;
+      if (it < n * 4) {
+        const int l = it & 3, i = it >> 2;
+        double* w = &tw[didx(rowof(N, i), l)];
+        double v = (i < a.cut) ? -a.dt * (*w) : 0.0;  // - dt * dealiased conv   (navier.rs:630, 651, 671)
+        if (a.mode == 0) v += ta[didx(i, l)];         // - dt/sx d/dx pres       (navier.rs:627)
+        *w = v + add[u];
       }
     }
-    *w = v;
   }
   __syncthreads();
   b2_fdma<C::NTHR, C::CL>(tw, N, n, a.b2, a.f, red);

@@ -11,9 +11,12 @@ namespace rp {
 // (512, 1): without the explicit min-blocks ptxas squeezed the whole call tree into 32 registers
 __global__ void __launch_bounds__(512, 1) lane_vm_kernel(const Program* __restrict__ progs) { lane_vm_body(progs); }
 
-__global__ void __launch_bounds__(256) dgemm_dmma_kernel(GemmArgs g0, GemmArgs g1);
-enum { GBM = 128, GBN = 128, GBK = 16, GPAD = 8, GLD = GBM + GPAD };
-static const int kGemmSmem = 4 * GBK * GLD * (int)sizeof(double);
+__global__ void __launch_bounds__(256, 2) dgemm_dmma_kernel(GemmArgs g0, GemmArgs g1);
+// block tile 128 x 64 x 16, 3-stage cp.async pipeline; shared tiles: A [m][k] (row stride GLDK),
+// B [k][n] (row stride GLDN), both padded so that the DMMA fragment loads are conflict-free
+enum { GBM = 128, GBN = 64, GBK = 16, GLDK = GBK + 4, GLDN = GBN + 4, GSTAGES = 3 };
+enum { GA_STAGE = GBM * GLDK, GB_STAGE = GBK * GLDN };
+static const int kGemmSmem = GSTAGES * (GA_STAGE + GB_STAGE) * (int)sizeof(double);
 
 void init_kernels() {
 #ifndef RP_EMU
@@ -36,7 +39,10 @@ void launch_lane_programs(const Program* d_progs, int nprogs, int nblocks, int n
 // FP64 DMMA GEMM:  C[m, n] = sum_k A[m, k] * B[k, n]      (row-major)
 //   B element (k, n) at B[(b_r0 + k*b_rs)*ldb + n], C likewise with c_r0/c_rs
 //   so the even/odd parity-split solves can address interleaved rows.
-// Block tile 128 x 128 x 16, 8 warps (2 x 4), warp tile 64 x 32.
+// Block tile 128 x 64 x 16, 8 warps (4 x 2), warp tile 32 x 32 (16 m8n8k4 DMMAs per
+// k-step of 4), operands staged by cp.async (16-byte chunks, zero-filled at the
+// edges) through a 3-stage ring, two blocks per SM.  blockIdx.z selects one of two
+// independent products (the even and the odd half of a parity-split solve).
 // ===========================================================================
 RP_DEV void dmma(double& d0, double& d1, double a, double b) {
 #ifdef RP_EMU
@@ -47,75 +53,100 @@ RP_DEV void dmma(double& d0, double& d1, double a, double b) {
                : "d"(a), "d"(b));
 #endif
 }
+// 16-byte asynchronous copy global -> shared; only the first `bytes` (0, 8 or 16) are read, the rest is zero
+RP_DEV void cp_async16(double* smem_dst, const double* gsrc, int bytes) {
+#ifdef RP_EMU
+  smem_dst[0] = bytes >= 8 ? gsrc[0] : 0.0;
+  smem_dst[1] = bytes >= 16 ? gsrc[1] : 0.0;
+#else
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(bytes) : "memory");
+#endif
+}
+RP_DEV void cp_async_commit() {
+#ifndef RP_EMU
+  asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+template <int N>
+RP_DEV void cp_async_wait() {
+#ifndef RP_EMU
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+#endif
+}
 
-__global__ void __launch_bounds__(256) dgemm_dmma_kernel(GemmArgs g0, GemmArgs g1) {
+__global__ void __launch_bounds__(256, 2) dgemm_dmma_kernel(GemmArgs g0, GemmArgs g1) {
   const GemmArgs& g = blockIdx.z ? g1 : g0;
   if ((int)(blockIdx.y * GBM) >= g.M) return;
   RP_DYN_SMEM(double, sm);
-  double* As = sm;                       // [2][GBK][GLD]  (k-major)
-  double* Bs = sm + 2 * GBK * GLD;       // [2][GBK][GLD]
+  double* As = sm;                        // [GSTAGES][GBM][GLDK]
+  double* Bs = sm + GSTAGES * GA_STAGE;   // [GSTAGES][GBK][GLDN]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int m0 = blockIdx.y * GBM, n0 = blockIdx.x * GBN;
-  const int wm = (warp >> 2) * 64, wn = (warp & 3) * 32;
+  const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
   const int lr = lane >> 2, lc = lane & 3;
-  double acc[8][4][2];
+  // number of 8-column blocks of this warp that hold valid columns (ragged last tile)
+  int jmax = (g.N - n0 - wn + 7) >> 3;
+  jmax = jmax < 0 ? 0 : (jmax > 4 ? 4 : jmax);
+  double acc[4][4][2];
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-  // global -> register staging
-  const int arow = tid >> 1, acol = (tid & 1) * 8;   // A tile: 128 rows x 16 k
-  const int brow = tid >> 4, bcol = (tid & 15) * 8;  // B tile: 16 k x 128 cols
-  double ra[8], rb[8];
   const int nk = (g.K + GBK - 1) / GBK;
-  auto gload = [&](int kt) {
-    const int k0 = kt * GBK;
-    const int gm = m0 + arow;
+  auto issue = [&](int kt) {
+    if (kt < nk) {
+      const int st = kt % GSTAGES, k0 = kt * GBK;
+      double* a = As + st * GA_STAGE;
+      double* b = Bs + st * GB_STAGE;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const int gk = k0 + acol + q;
-      ra[q] = (gm < g.M && gk < g.K) ? g.A[(size_t)gm * g.lda + gk] : 0.0;
+      for (int q = 0; q < 4; ++q) {  // A: 128 rows x 8 chunks
+        const int ch = tid + q * 256, row = ch >> 3, kc = (ch & 7) * 2;
+        const int gm = m0 + row, gk = k0 + kc;
+        int bytes = (gm < g.M) ? (g.K - gk) * 8 : 0;
+        bytes = bytes < 0 ? 0 : (bytes > 16 ? 16 : bytes);
+        const double* src = bytes ? g.A + (size_t)gm * g.lda + gk : g.A;
+        cp_async16(a + row * GLDK + kc, src, bytes);
+      }
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {  // B: 16 rows x 32 chunks
+        const int ch = tid + q * 256, row = ch >> 5, nc = (ch & 31) * 2;
+        const int gk = k0 + row, gn = n0 + nc;
+        int bytes = (gk < g.K) ? (g.N - gn) * 8 : 0;
+        bytes = bytes < 0 ? 0 : (bytes > 16 ? 16 : bytes);
+        const double* src = bytes ? g.B + (size_t)(g.b_r0 + (long long)gk * g.b_rs) * g.ldb + gn : g.B;
+        cp_async16(b + row * GLDN + nc, src, bytes);
+      }
     }
-    const int gk = k0 + brow;
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const int gn = n0 + bcol + q;
-      rb[q] = (gk < g.K && gn < g.N) ? g.B[(size_t)(g.b_r0 + (long long)gk * g.b_rs) * g.ldb + gn] : 0.0;
-    }
+    cp_async_commit();
   };
-  auto sstore = [&](int buf) {
-    double* a = As + buf * GBK * GLD;
-    double* b = Bs + buf * GBK * GLD;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) a[(acol + q) * GLD + arow] = ra[q];
-#pragma unroll
-    for (int q = 0; q < 8; ++q) b[brow * GLD + bcol + q] = rb[q];
-  };
-  gload(0);
-  sstore(0);
-  __syncthreads();
+  for (int s = 0; s < GSTAGES - 1; ++s) issue(s);
   for (int kt = 0; kt < nk; ++kt) {
-    const int buf = kt & 1;
-    if (kt + 1 < nk) gload(kt + 1);
-    const double* a = As + buf * GBK * GLD;
-    const double* b = Bs + buf * GBK * GLD;
-#pragma unroll
-    for (int kk = 0; kk < GBK; kk += 4) {
-      double af[8], bf[4];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) af[i] = a[(kk + lc) * GLD + wm + 8 * i + lr];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) bf[j] = b[(kk + lc) * GLD + wn + 8 * j + lr];
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
-    }
-    if (kt + 1 < nk) sstore(buf ^ 1);
+    cp_async_wait<GSTAGES - 2>();
     __syncthreads();
+    issue(kt + GSTAGES - 1);
+    const double* a = As + (kt % GSTAGES) * GA_STAGE;
+    const double* b = Bs + (kt % GSTAGES) * GB_STAGE;
+    if (jmax > 0) {
+#pragma unroll
+      for (int kk = 0; kk < GBK; kk += 4) {
+        double af[4], bf[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) af[i] = a[(wm + 8 * i + lr) * GLDK + kk + lc];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) bf[j] = b[(kk + lc) * GLDN + wn + 8 * j + lr];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (j < jmax) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+          }
+      }
+    }
   }
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 0; i < 4; ++i) {
     const int gm = m0 + wm + 8 * i + lr;
     if (gm >= g.M) continue;
     double* crow = g.C + (size_t)(g.c_r0 + (long long)gm * g.c_rs) * g.ldc;
