@@ -32,8 +32,8 @@ FK_DEV void xtile_fill(double* td, int nfill, F f) {  // batched like tile_fill 
     double v[FK_FILL_U];
 #pragma unroll
     for (int u = 0; u < FK_FILL_U; ++u) {
-      const int it = it0 + u * NTHR;
-      v[u] = it < tot ? f(it >> 2, it & 3) : 0.0;
+      const int it = min(it0 + u * NTHR, tot - 1);  // clamped: the loads stay unconditional
+      v[u] = f(it >> 2, it & 3);
     }
 #pragma unroll
     for (int u = 0; u < FK_FILL_U; ++u) {
@@ -45,27 +45,32 @@ FK_DEV void xtile_fill(double* td, int nfill, F f) {  // batched like tile_fill 
 
 // composite -> ortho stencil along x applied while loading column c of `a`
 // (m = n-2 rows): p_i = d_i c_i + l_{i-2} c_{i-2}   (composite_stencil.rs:207-229)
+// All loads are unconditional (clamped indices, zero weights) so that the compiler
+// can issue a whole batch of them before the first use.
 FK_DEV double ld_stencil_x(const Mat& a, int i, int c, const double* __restrict__ sd, const double* __restrict__ sl) {
-  if (c >= a.cols) return 0.0;
-  double v = 0.0;
-  if (i < a.rows) v = __ldg(&sd[i]) * a.p[(size_t)i * a.ld + c];
-  if (i >= 2) v = fma(__ldg(&sl[i - 2]), a.p[(size_t)(i - 2) * a.ld + c], v);
-  return v;
+  const int cc = min(c, a.cols - 1), i0 = min(i, a.rows - 1), i2 = max(i - 2, 0);
+  const double v0 = a.p[(size_t)i0 * a.ld + cc], v2 = a.p[(size_t)i2 * a.ld + cc];
+  const bool ok = c < a.cols;
+  const double d = (ok && i < a.rows) ? __ldg(&sd[i0]) : 0.0;
+  const double l = (ok && i >= 2) ? __ldg(&sl[i2]) : 0.0;
+  return fma(l, v2, d * v0);
+}
+// plain element (i, c) of a, zero outside
+FK_DEV double ld_plain(const Mat& a, int i, int c) {
+  const double v = a.p[(size_t)min(i, a.rows - 1) * a.ld + min(c, a.cols - 1)];
+  return (i < a.rows && c < a.cols) ? v : 0.0;
 }
 // S_x S_y f at ortho index (i, j); f is [mx, my]
 FK_DEV double ld_stencil_xy(const Mat& f, int i, int j, const double* __restrict__ xsd, const double* __restrict__ xsl,
                             const double* __restrict__ ysd, const double* __restrict__ ysl) {
-  auto ty = [&](int ii) {
-    const double* row = f.p + (size_t)ii * f.ld;
-    double v = 0.0;
-    if (j < f.cols) v = __ldg(&ysd[j]) * row[j];
-    if (j >= 2) v = fma(__ldg(&ysl[j - 2]), row[j - 2], v);
-    return v;
-  };
-  double p = 0.0;
-  if (i < f.rows) p = __ldg(&xsd[i]) * ty(i);
-  if (i >= 2) p = fma(__ldg(&xsl[i - 2]), ty(i - 2), p);
-  return p;
+  const int i0 = min(i, f.rows - 1), i2 = max(i - 2, 0), j0 = min(j, f.cols - 1), j2 = max(j - 2, 0);
+  const double* r0 = f.p + (size_t)i0 * f.ld;
+  const double* r2 = f.p + (size_t)i2 * f.ld;
+  const double v00 = r0[j0], v02 = r0[j2], v20 = r2[j0], v22 = r2[j2];
+  const double yd = (j < f.cols) ? __ldg(&ysd[j0]) : 0.0, yl = (j >= 2) ? __ldg(&ysl[j2]) : 0.0;
+  const double xd = (i < f.rows) ? __ldg(&xsd[i0]) : 0.0, xl = (i >= 2) ? __ldg(&xsl[i2]) : 0.0;
+  const double t0 = fma(yl, v02, yd * v00), t2 = fma(yl, v22, yd * v20);
+  return fma(xl, t2, xd * t0);
 }
 
 // ---------------------------------------------------------------------------------
@@ -102,23 +107,22 @@ __global__ void __launch_bounds__(XCfg<LOG2LB>::NTHR, 1) xk_forward(XForwardArgs
   const int c0 = blockIdx.x * 4;
   const int n = a.t.n, N = n - 1;
   const int ncols = a.conv.cols;
-  xtile_fill<C::NTHR>(ta, n, [&](int i, int l) { return c0 + l < ncols ? a.conv.p[(size_t)i * a.conv.ld + c0 + l] : 0.0; });
+  xtile_fill<C::NTHR>(ta, n, [&](int i, int l) { return ld_plain(a.conv, i, c0 + l); });
   __syncthreads();
   dct_bluestein<LOG2LB, C::NTHR, false>(ta, tw, a.t, red);
   if (a.mode == 0) {  // - dt/sx d/dx pres   (navier.rs:627)
-    xtile_fill<C::NTHR>(ta, n, [&](int i, int l) { return c0 + l < ncols ? a.pres.p[(size_t)i * a.pres.ld + c0 + l] : 0.0; });
+    xtile_fill<C::NTHR>(ta, n, [&](int i, int l) { return ld_plain(a.pres, i, c0 + l); });
     __syncthreads();
     cheb_diff<C::NTHR, C::CL>(ta, -1, ta, -1, n, -a.dt * a.isx, red);
   }
   // rhs terms read from global memory: batches of 4 elements per thread so that the loads overlap
   auto rhs_terms = [&](int i, int l) -> double {
-    const int j = c0 + l;
-    if (j >= ncols) return 0.0;
+    const int j = min(c0 + l, ncols - 1);
     double v = ld_stencil_xy(a.fld, i, j, a.fxsd, a.fxsl, a.fysd, a.fysl);  // + to_ortho(field)
     if (a.mode == 1) {  // - dt/sy d/dy pres + dt * (that + tbc)   (navier.rs:646-648)
-      v = fma(-a.dt, a.dyp.p[(size_t)i * a.dyp.ld + j], v);
-      const double that = ld_stencil_xy(a.tmp, i, j, a.txsd, a.txsl, a.tysd, a.tysl) + a.tbc.p[(size_t)i * a.tbc.ld + j];
-      v = fma(a.dt, that, v);
+      const double dyp = a.dyp.p[(size_t)i * a.dyp.ld + j], tbc = a.tbc.p[(size_t)i * a.tbc.ld + j];
+      const double that = ld_stencil_xy(a.tmp, i, j, a.txsd, a.txsl, a.tysd, a.tysl) + tbc;
+      v = fma(a.dt, that, fma(-a.dt, dyp, v));
     } else if (a.mode == 2) {  // + dt ka (dxx + dyy) fieldbc   (navier.rs:665-668)
       v += a.bcdiff.p[(size_t)i * a.bcdiff.ld + j];
     }
@@ -128,8 +132,8 @@ __global__ void __launch_bounds__(XCfg<LOG2LB>::NTHR, 1) xk_forward(XForwardArgs
     double add[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const int it = it0 + u * C::NTHR;
-      add[u] = it < n * 4 ? rhs_terms(it >> 2, it & 3) : 0.0;
+      const int it = min(it0 + u * C::NTHR, n * 4 - 1);
+      add[u] = rhs_terms(it >> 2, it & 3);
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {

@@ -38,8 +38,8 @@ FK_DEV void tile_fill(double* td, int nfill, F f) {
     double v[FK_FILL_U];
 #pragma unroll
     for (int u = 0; u < FK_FILL_U; ++u) {
-      const int it = it0 + u * NTHR;
-      v[u] = it < tot ? f(it >> 2, it & 3) : 0.0;
+      const int it = min(it0 + u * NTHR, tot - 1);  // clamped: the loads stay unconditional
+      v[u] = f(it >> 2, it & 3);
     }
 #pragma unroll
     for (int u = 0; u < FK_FILL_U; ++u) {
@@ -59,13 +59,21 @@ FK_DEV void tile_drain(const double* td, int sn, int nout, G g) {
 
 // composite -> ortho stencil applied while loading row r of `a` (m = n-2 columns):
 // p_j = d_j c_j + l_{j-2} c_{j-2}   (composite_stencil.rs:207-229)
+// All loads are unconditional (clamped indices, zero weights) so that the compiler
+// can issue a whole batch of them before the first use.
 FK_DEV double ld_stencil(const Mat& a, int r, int j, int m, const double* __restrict__ sd, const double* __restrict__ sl) {
-  if (r >= a.rows) return 0.0;
-  const double* row = a.p + (size_t)r * a.ld;
-  double v = 0.0;
-  if (j < m) v = __ldg(&sd[j]) * row[j];
-  if (j >= 2) v = fma(__ldg(&sl[j - 2]), row[j - 2], v);
-  return v;
+  const int rr = min(r, a.rows - 1), j0 = min(j, m - 1), j2 = max(j - 2, 0);
+  const double* row = a.p + (size_t)rr * a.ld;
+  const double v0 = row[j0], v2 = row[j2];
+  const bool ok = r < a.rows;
+  const double d = (ok && j < m) ? __ldg(&sd[j0]) : 0.0;
+  const double l = (ok && j >= 2) ? __ldg(&sl[j2]) : 0.0;
+  return fma(l, v2, d * v0);
+}
+// plain element (r, j) of a, zero for rows outside
+FK_DEV double ld_row(const Mat& a, int r, int j) {
+  const double v = a.p[(size_t)min(r, a.rows - 1) * a.ld + j];
+  return r < a.rows ? v : 0.0;
 }
 
 // ---------------------------------------------------------------------------------
@@ -108,13 +116,16 @@ __global__ void __launch_bounds__(YCfg<LOG2L>::NTHR, 2) yk_conv(YConvArgs3 a3) {
   YK_SMEM(td, red);
   const int r0 = blockIdx.x * 4;
   constexpr int n = C::n, N = C::N;
+  const bool has_bc = a.bcx.p != nullptr;
   tile_fill<C::NTHR>(td, n, [&](int j, int l) {
-    const int r = r0 + l;
-    if (r >= a.u.rows) return 0.0;
+    const int r = min(r0 + l, a.u.rows - 1);
     double gx = a.du.p[(size_t)r * a.du.ld + j], gy = a.dv.p[(size_t)r * a.dv.ld + j];
-    if (a.bcx.p) gx += a.bcx.p[(size_t)r * a.bcx.ld + j];
-    if (a.bcy.p) gy += a.bcy.p[(size_t)r * a.bcy.ld + j];
-    return fma(a.u.p[(size_t)r * a.u.ld + j], gx, a.v.p[(size_t)r * a.v.ld + j] * gy);
+    const double u = a.u.p[(size_t)r * a.u.ld + j], v = a.v.p[(size_t)r * a.v.ld + j];
+    if (has_bc) {
+      gx += a.bcx.p[(size_t)r * a.bcx.ld + j];
+      gy += a.bcy.p[(size_t)r * a.bcy.ld + j];
+    }
+    return (r0 + l < a.u.rows) ? fma(u, gx, v * gy) : 0.0;
   });
   __syncthreads();
   dct_pow2<LOG2L, C::NTHR, false>(td, a.t, red);
@@ -130,10 +141,7 @@ __global__ void __launch_bounds__(YCfg<LOG2L>::NTHR, 2) yk_adi(YAdiArgs3 a3) {
   YK_SMEM(td, red);
   const int r0 = blockIdx.x * 4;
   constexpr int n = C::n, m = n - 2;
-  tile_fill<C::NTHR>(td, n, [&](int j, int l) {
-    const int r = r0 + l;
-    return r < a.w.rows ? a.w.p[(size_t)r * a.w.ld + j] : 0.0;
-  });
+  tile_fill<C::NTHR>(td, n, [&](int j, int l) { return ld_row(a.w, r0 + l, j); });
   __syncthreads();
   b2_fdma<C::NTHR, C::CL>(td, -1, n, a.b2, a.f, red);
   tile_drain<C::NTHR>(td, -1, m, [&](int j, int l, double v) {
@@ -175,14 +183,8 @@ __global__ void __launch_bounds__(YCfg<LOG2L>::NTHR, 1) yk_mode(YModeArgs a) {
   (void)red0;
   const int r0 = blockIdx.x * 4;
   constexpr int n = C::n, m = n - 2;
-  tile_fill<C::NTHR>(td, n, [&](int j, int l) {
-    const int r = r0 + l;
-    return r < a.g.rows ? a.g.p[(size_t)r * a.g.ld + j] : 0.0;
-  });
-  tile_fill<C::NTHR>(ti, m, [&](int j, int l) {
-    const int r = r0 + l;
-    return r < a.g.rows ? a.m.inv[(size_t)r * a.m.inv_ld + j] : 1.0;
-  });
+  tile_fill<C::NTHR>(td, n, [&](int j, int l) { return ld_row(a.g, r0 + l, j); });
+  tile_fill<C::NTHR>(ti, m, [&](int j, int l) { return a.m.inv[(size_t)min(r0 + l, a.g.rows - 1) * a.m.inv_ld + j]; });
   __syncthreads();
   const ModeTabs& M = a.m;
   const B2Tabs& B = a.b2;
@@ -251,15 +253,17 @@ __global__ void __launch_bounds__(YCfg<LOG2L>::NTHR, 2) yk_pres(YPresArgs a) {
   const int mx = a.phi.rows;
   // to_ortho(phi): S_x across lanes (rows i, i-2 of phi), S_y along the lane
   tile_fill<C::NTHR>(td, n, [&](int j, int l) {
-    const int i = r0 + l;
-    if (i >= a.pres.rows) return 0.0;
-    double v = 0.0;
-    if (i < mx) v = __ldg(&a.xsd[i]) * ld_stencil(a.phi, i, j, m, a.ysd, a.ysl);
-    if (i >= 2) v = fma(__ldg(&a.xsl[i - 2]), ld_stencil(a.phi, i - 2, j, m, a.ysd, a.ysl), v);
-    const size_t o = (size_t)i * a.pres.ld + j;
-    const double p = fma(-a.nu, a.div.p[(size_t)i * a.div.ld + j], a.pres.p[o]) + v * a.inv_dt;
-    a.pres.p[o] = p;
-    return p;
+    const int i = min(r0 + l, a.pres.rows - 1);
+    const double s0 = ld_stencil(a.phi, min(i, mx - 1), j, m, a.ysd, a.ysl);
+    const double s2 = ld_stencil(a.phi, max(i - 2, 0), j, m, a.ysd, a.ysl);
+    const double xd = (i < mx) ? __ldg(&a.xsd[min(i, mx - 1)]) : 0.0, xl = (i >= 2) ? __ldg(&a.xsl[max(i - 2, 0)]) : 0.0;
+    const double v = fma(xl, s2, xd * s0);
+    const double p = fma(-a.nu, a.div.p[(size_t)i * a.div.ld + j], a.pres.p[(size_t)i * a.pres.ld + j]) + v * a.inv_dt;
+    return (r0 + l < a.pres.rows) ? p : 0.0;
+  });
+  __syncthreads();
+  tile_drain<C::NTHR>(td, -1, n, [&](int j, int l, double v) {
+    if (r0 + l < a.pres.rows) a.pres.p[(size_t)(r0 + l) * a.pres.ld + j] = v;
   });
   __syncthreads();
   cheb_diff<C::NTHR, C::CL>(td, -1, td, -1, n, a.isy, red);
