@@ -35,6 +35,31 @@ FK_DEV cplx cmul(cplx a, cplx b) { return mk(fma(a.x, b.x, -a.y * b.y), fma(a.x,
 FK_DEV cplx csqr(cplx a) { return mk(fma(a.x, a.x, -a.y * a.y), 2.0 * a.x * a.y); }
 FK_DEV cplx cscale(cplx a, double s) { return mk(a.x * s, a.y * s); }
 
+// L2 prefetch of the 32-byte sector that holds *p (no register or shared-memory cost): used to pull
+// the column strips a later phase (or the block that will run next on this SM) reads out of DRAM
+// while the current phase computes.
+FK_DEV void prefetch_l2(const void* p) {
+#ifndef RP_EMU
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+  (void)p;
+#endif
+}
+// rows [0, nrows) of the 4-column strip of `a` starting at column c0 (and, with HALO, the two columns before it)
+template <int NTHR, bool HALO>
+FK_DEV void prefetch_strip(const Mat& a, int c0, int nrows) {
+  if (a.p == nullptr || c0 >= a.cols) return;
+  for (int i = threadIdx.x; i < nrows; i += NTHR) {
+    const double* row = a.p + (size_t)i * a.ld;
+    prefetch_l2(row + c0);
+    if (HALO && c0 >= 2) prefetch_l2(row + c0 - 2);
+  }
+}
+
+// at most 512 threads of a block take part in the scans (bounds the scratch array); the rest only
+// joins the barriers
+RP_HD constexpr int scan_threads(int nthr) { return nthr > 512 ? 512 : nthr; }
+
 // ---- tile addressing --------------------------------------------------------
 FK_DEV int prow(int i) { return i ^ ((i >> 3) & 3); }
 FK_DEV int didx(int i, int r) { return prow(i) * 4 + r; }  // as double
@@ -340,9 +365,10 @@ FK_DEV void recombine_pair(cplx zk, cplx zm, int k, int N, cplx& xe, cplx& dk) {
 // (4 real lanes); forward transform: times -1/N, last one halved when N is odd.
 template <int NTHR, int CLR, bool BWD>
 FK_DEV void dct_odd_scan(double* td, int N, double* red) {
-  constexpr int NG = NTHR / 4;
+  constexpr int NSC = scan_threads(NTHR), NG = NSC / 4;
   const int tid = threadIdx.x, lane = tid & 3, g = tid >> 2;
-  const int M = (N - 1) / 2 + 1;  // Ko + 1
+  const bool act = tid < NSC;
+  const int M = act ? (N - 1) / 2 + 1 : 0;  // Ko + 1
   const int cl = (M + NG - 1) / NG;
   const int t0 = g * cl, t1 = min(t0 + cl, M);
   double q[CLR];
@@ -357,9 +383,9 @@ FK_DEV void dct_odd_scan(double* td, int N, double* red) {
   }
   // two-level carry: sums of groups of 8 chunks, then the chunks inside the group
   double* red2 = red + NG * 4;
-  red[g * 4 + lane] = s;
+  if (act) red[g * 4 + lane] = s;
   __syncthreads();
-  if ((g & 7) == 0) {
+  if (act && (g & 7) == 0) {
     double t = 0.0;
 #pragma unroll
     for (int k = 0; k < 8; ++k)
@@ -368,8 +394,8 @@ FK_DEV void dct_odd_scan(double* td, int N, double* red) {
   }
   __syncthreads();
   double y = 0.0;
-  for (int gg = 0; gg < (g >> 3); ++gg) y += red2[gg * 4 + lane];
-  for (int gg = (g & ~7); gg < g; ++gg) y += red[gg * 4 + lane];
+  for (int gg = 0; act && gg < (g >> 3); ++gg) y += red2[gg * 4 + lane];
+  for (int gg = (g & ~7); act && gg < g; ++gg) y += red[gg * 4 + lane];
   const double ho = BWD ? 1.0 : -1.0 / (double)N;
 #pragma unroll
   for (int u = 0; u < CLR; ++u) {
@@ -420,7 +446,7 @@ FK_DEV void dct_pow2(double* td, const DctTab& T, double* red) {
     }
   }
   __syncthreads();
-  dct_odd_scan<NTHR, (N / 2 + NTHR / 4 - 1) / (NTHR / 4), BWD>(td, N, red);
+  dct_odd_scan<NTHR, (N / 2 + scan_threads(NTHR) / 4 - 1) / (scan_threads(NTHR) / 4), BWD>(td, N, red);
 }
 
 // DCT-I of arbitrary N = n - 1 through Bluestein (FFT length Lb = 1 << LOG2LB >=
@@ -464,7 +490,7 @@ FK_DEV void dct_bluestein(const double* ta, double* tw_, const DctTab& T, double
     }
   }
   __syncthreads();
-  dct_odd_scan<NTHR, (LB / 4 + NTHR / 4 - 1) / (NTHR / 4), BWD>(tw_, N, red);
+  dct_odd_scan<NTHR, (LB / 4 + scan_threads(NTHR) / 4 - 1) / (scan_threads(NTHR) / 4), BWD>(tw_, N, red);
 }
 
 // ---- chunked scans over the 8 parity chains of a tile ---------------------------
@@ -475,10 +501,10 @@ FK_DEV void dct_bluestein(const double* ta, double* tw_, const DctTab& T, double
 // it may overwrite the tile the inputs came from (any row).
 template <int NTHR, int CL, bool FWD, class In, class C1, class Out>
 FK_DEV void scan1(int n, double* red, In in, C1 c1, Out out) {
-  constexpr int NG = NTHR / 8;
+  constexpr int NSC = scan_threads(NTHR), NG = NSC / 8;
   const int tid = threadIdx.x, ch = tid & 7, g = tid >> 3;
   const int lane = ch & 3, p = ch >> 2;
-  const int M = (n - p + 1) >> 1;
+  const int M = (tid < NSC) ? ((n - p + 1) >> 1) : 0;  // threads beyond NSC own empty chunks
   const int cl = (((n + 1) >> 1) + NG - 1) / NG;
   const int t0 = g * cl, t1 = min(t0 + cl, M);
   double q[CL];
@@ -496,10 +522,13 @@ FK_DEV void scan1(int n, double* red, In in, C1 c1, Out out) {
   }
   // two-level carry: maps of groups of 8 chunks, then the chunks inside the group
   double* red2 = red + NG * 16;
-  red[(g * 8 + ch) * 2] = A;
-  red[(g * 8 + ch) * 2 + 1] = b;
+  const bool act = tid < NSC;
+  if (act) {
+    red[(g * 8 + ch) * 2] = A;
+    red[(g * 8 + ch) * 2 + 1] = b;
+  }
   __syncthreads();
-  if ((g & 7) == 0) {
+  if (act && (g & 7) == 0) {
     double Ag = 1.0, bg = 0.0;
 #pragma unroll
     for (int k = 0; k < 8; ++k)
@@ -513,8 +542,10 @@ FK_DEV void scan1(int n, double* red, In in, C1 c1, Out out) {
   }
   __syncthreads();
   double y = 0.0;
-  for (int gg = 0; gg < (g >> 3); ++gg) y = fma(red2[(gg * 8 + ch) * 2], y, red2[(gg * 8 + ch) * 2 + 1]);
-  for (int gg = (g & ~7); gg < g; ++gg) y = fma(red[(gg * 8 + ch) * 2], y, red[(gg * 8 + ch) * 2 + 1]);
+  if (act) {
+    for (int gg = 0; gg < (g >> 3); ++gg) y = fma(red2[(gg * 8 + ch) * 2], y, red2[(gg * 8 + ch) * 2 + 1]);
+    for (int gg = (g & ~7); gg < g; ++gg) y = fma(red[(gg * 8 + ch) * 2], y, red[(gg * 8 + ch) * 2 + 1]);
+  }
 #pragma unroll
   for (int u = 0; u < CL; ++u) {
     const int t = t0 + u;
@@ -530,10 +561,10 @@ FK_DEV void scan1(int n, double* red, In in, C1 c1, Out out) {
 //   y_t = in(i, lane) + c1(i, lane) * y_{t-1} + c2(i, lane) * y_{t-2}
 template <int NTHR, int CL, bool FWD, class In, class C1, class C2, class Out>
 FK_DEV void scan2(int n, double* red, In in, C1 c1, C2 c2, Out out) {
-  constexpr int NG = NTHR / 8;
+  constexpr int NSC = scan_threads(NTHR), NG = NSC / 8;
   const int tid = threadIdx.x, ch = tid & 7, g = tid >> 3;
   const int lane = ch & 3, p = ch >> 2;
-  const int M = (n - p + 1) >> 1;
+  const int M = (tid < NSC) ? ((n - p + 1) >> 1) : 0;
   const int cl = (((n + 1) >> 1) + NG - 1) / NG;
   const int t0 = g * cl, t1 = min(t0 + cl, M);
   double q[CL];
@@ -554,12 +585,15 @@ FK_DEV void scan2(int n, double* red, In in, C1 c1, C2 c2, Out out) {
       b2 = b1, b1 = bn;
     }
   }
-  double* r = red + (g * 8 + ch) * 6;
-  r[0] = a1, r[1] = b1, r[2] = p1, r[3] = a2, r[4] = b2, r[5] = p2;
+  const bool act = tid < NSC;
+  if (act) {
+    double* r = red + (g * 8 + ch) * 6;
+    r[0] = a1, r[1] = b1, r[2] = p1, r[3] = a2, r[4] = b2, r[5] = p2;
+  }
   __syncthreads();
   // two-level carry: maps of groups of 8 chunks, then the chunks inside the group
   double* red2 = red + NG * 48;
-  if ((g & 7) == 0) {
+  if (act && (g & 7) == 0) {
     // group map  [y1; y2] -> G [y1; y2] + h,  G = [g11 g12; g21 g22]
     double g11 = 1.0, g12 = 0.0, g21 = 0.0, g22 = 1.0, h1 = 0.0, h2 = 0.0;
 #pragma unroll
@@ -576,13 +610,13 @@ FK_DEV void scan2(int n, double* red, In in, C1 c1, C2 c2, Out out) {
   }
   __syncthreads();
   double y1 = 0.0, y2 = 0.0;
-  for (int gg = 0; gg < (g >> 3); ++gg) {
+  for (int gg = 0; act && gg < (g >> 3); ++gg) {
     const double* rr = red2 + (gg * 8 + ch) * 6;
     const double n1 = fma(rr[0], y1, fma(rr[1], y2, rr[2]));
     const double n2 = fma(rr[3], y1, fma(rr[4], y2, rr[5]));
     y1 = n1, y2 = n2;
   }
-  for (int gg = (g & ~7); gg < g; ++gg) {
+  for (int gg = (g & ~7); act && gg < g; ++gg) {
     const double* rr = red + (gg * 8 + ch) * 6;
     const double n1 = fma(rr[0], y1, fma(rr[1], y2, rr[2]));
     const double n2 = fma(rr[3], y1, fma(rr[4], y2, rr[5]));
@@ -602,7 +636,7 @@ FK_DEV void scan2(int n, double* red, In in, C1 c1, C2 c2, Out out) {
 }
 
 // chunk length bound for a lane of n elements handled by NTHR threads
-constexpr int chunk_len(int n, int nthr) { return (((n + 1) / 2) + nthr / 8 - 1) / (nthr / 8); }
+RP_HD constexpr int chunk_len(int n, int nthr) { return (((n + 1) / 2) + scan_threads(nthr) / 8 - 1) / (scan_threads(nthr) / 8); }
 
 // Chebyshev derivative (ortho.rs:107-125) of the lane held in tile `src`
 // (layout sn_s, n elements), times `sc`, written to tile `dst` (layout sn_d;

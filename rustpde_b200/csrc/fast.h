@@ -123,6 +123,7 @@ struct XBackwardArgs {  // B_x S_x u^ and B_x D_x S_x u^ / sx
 };
 struct XBackwardArgs3 {
   XBackwardArgs a[3];
+  int next_wave;  // set by the launcher: linear block distance to prefetch ahead
 };
 void launch_x_backward(const XBackwardArgs3& a, int nbatch, cudaStream_t s);
 
@@ -145,6 +146,7 @@ struct XForwardArgs {  // forward DCT-x + dealias + rhs assembly + x half of Hho
 };
 struct XForwardArgs3 {
   XForwardArgs a[3];
+  int next_wave;
 };
 void launch_x_forward(const XForwardArgs3& a, int nbatch, cudaStream_t s);
 

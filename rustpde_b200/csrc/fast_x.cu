@@ -20,8 +20,8 @@ struct XCfg {
   static constexpr int NTHR = (LB / 8) < 64 ? 64 : (LB / 8);
   static constexpr int AROWS = LB / 2 + 4;
   static constexpr int CL = chunk_len(NMAX, NTHR);
-  static constexpr int SMEM_A = AROWS * 32 + NTHR * 56 + 512;
-  static constexpr int SMEM_AW = (AROWS + LB) * 32 + NTHR * 56 + 512;
+  static constexpr int SMEM_A = AROWS * 32 + scan_threads(NTHR) * 56 + 512;
+  static constexpr int SMEM_AW = (AROWS + LB) * 32 + scan_threads(NTHR) * 56 + 512;
 };
 
 #define FK_FILL_U 8
@@ -73,6 +73,21 @@ FK_DEV double ld_stencil_xy(const Mat& f, int i, int j, const double* __restrict
   return fma(xl, t2, xd * t0);
 }
 
+// dst(i) = d_i src(i) + l_{i-2} src(i-2), i < n: composite (m = n-2 rows of src) -> ortho along the tile axis
+// (composite_stencil.rs:207-229).  A 4-column strip costs one L1 line per row and array, so every
+// array is read from global memory once and the stencil runs on the shared-memory copy.
+template <int NTHR>
+FK_DEV void xstencil_tile(double* dst, const double* src, int n, const double* __restrict__ sd, const double* __restrict__ sl) {
+  const int m = n - 2;
+  for (int it = threadIdx.x; it < n * 4; it += NTHR) {
+    const int l = it & 3, i = it >> 2;
+    double v = 0.0;
+    if (i < m) v = __ldg(&sd[i]) * src[didx(i, l)];
+    if (i >= 2) v = fma(__ldg(&sl[i - 2]), src[didx(i - 2, l)], v);
+    dst[didx(i, l)] = v;
+  }
+}
+
 // ---------------------------------------------------------------------------------
 template <int LOG2LB>
 __global__ void __launch_bounds__(XCfg<LOG2LB>::NTHR, 1) xk_backward(XBackwardArgs3 a3) {
@@ -83,7 +98,13 @@ __global__ void __launch_bounds__(XCfg<LOG2LB>::NTHR, 1) xk_backward(XBackwardAr
   double* red = tw + C::LB * 4;
   const int c0 = blockIdx.x * 4;
   const int n = a.t.n, N = n - 1;
-  xtile_fill<C::NTHR>(ta, n, [&](int i, int l) { return ld_stencil_x(a.src, i, c0 + l, a.sd, a.sl); });
+  xtile_fill<C::NTHR>(tw, n - 2, [&](int i, int l) { return ld_plain(a.src, i, c0 + l); });
+  {  // first strip of the block that runs on this SM next
+    const int nxt = blockIdx.y * gridDim.x + blockIdx.x + a3.next_wave;
+    if (nxt < (int)(gridDim.x * gridDim.y)) prefetch_strip<C::NTHR, false>(a3.a[nxt / gridDim.x].src, (nxt % gridDim.x) * 4, n - 2);
+  }
+  __syncthreads();
+  xstencil_tile<C::NTHR>(ta, tw, n, a.sd, a.sl);
   __syncthreads();
   for (int pass = 0; pass < 2; ++pass) {
     const Mat& o = pass ? a.dx : a.val;
@@ -108,32 +129,37 @@ __global__ void __launch_bounds__(XCfg<LOG2LB>::NTHR, 1) xk_forward(XForwardArgs
   const int n = a.t.n, N = n - 1;
   const int ncols = a.conv.cols;
   xtile_fill<C::NTHR>(ta, n, [&](int i, int l) { return ld_plain(a.conv, i, c0 + l); });
+  {  // first strip of the block that runs on this SM next -> L2
+    const int nxt = blockIdx.y * gridDim.x + blockIdx.x + a3.next_wave;
+    if (nxt < (int)(gridDim.x * gridDim.y)) prefetch_strip<C::NTHR, false>(a3.a[nxt / gridDim.x].conv, (nxt % gridDim.x) * 4, n);
+  }
   __syncthreads();
   dct_bluestein<LOG2LB, C::NTHR, false>(ta, tw, a.t, red);
-  if (a.mode == 0) {  // - dt/sx d/dx pres   (navier.rs:627)
-    xtile_fill<C::NTHR>(ta, n, [&](int i, int l) { return ld_plain(a.pres, i, c0 + l); });
-    __syncthreads();
-    cheb_diff<C::NTHR, C::CL>(ta, -1, ta, -1, n, -a.dt * a.isx, red);
-  }
-  // rhs terms read from global memory: batches of 4 elements per thread so that the loads overlap
-  auto rhs_terms = [&](int i, int l) -> double {
-    const int j = min(c0 + l, ncols - 1);
-    double v = ld_stencil_xy(a.fld, i, j, a.fxsd, a.fxsl, a.fysd, a.fysl);  // + to_ortho(field)
-    if (a.mode == 1) {  // - dt/sy d/dy pres + dt * (that + tbc)   (navier.rs:646-648)
-      const double dyp = a.dyp.p[(size_t)i * a.dyp.ld + j], tbc = a.tbc.p[(size_t)i * a.tbc.ld + j];
-      const double that = ld_stencil_xy(a.tmp, i, j, a.txsd, a.txsl, a.tysd, a.tysl) + tbc;
-      v = fma(a.dt, that, fma(-a.dt, dyp, v));
-    } else if (a.mode == 2) {  // + dt ka (dxx + dyy) fieldbc   (navier.rs:665-668)
-      v += a.bcdiff.p[(size_t)i * a.bcdiff.ld + j];
-    }
+  // rhs assembly in the split(N) layout of W.  Every global array is read once per element:
+  // S_y is applied while loading (columns j, j-2), S_x on the shared-memory copy in A.
+  const int mxr = n - 2;
+  auto ld_sy = [&](const Mat& f, int i, int l, const double* __restrict__ ysd, const double* __restrict__ ysl) {
+    const int j = c0 + l, j0 = min(j, f.cols - 1), j2 = min(max(j - 2, 0), f.cols - 1);
+    const double* row = f.p + (size_t)i * f.ld;
+    const double v0 = row[j0], v2 = row[j2];
+    const double yd = (j < f.cols) ? __ldg(&ysd[j0]) : 0.0, yl = (j >= 2 && j - 2 < f.cols) ? __ldg(&ysl[j2]) : 0.0;
+    return fma(yl, v2, yd * v0);
+  };
+  auto sx_at = [&](int i, int l, const double* __restrict__ xsd, const double* __restrict__ xsl) {
+    double v = 0.0;
+    if (i < mxr) v = __ldg(&xsd[i]) * ta[didx(i, l)];
+    if (i >= 2) v = fma(__ldg(&xsl[i - 2]), ta[didx(i - 2, l)], v);
     return v;
   };
+  // - dt * dealiased conv + to_ortho(field)   (navier.rs:625, 630, 651, 671)
+  xtile_fill<C::NTHR>(ta, mxr, [&](int i, int l) { return ld_sy(a.fld, i, l, a.fysd, a.fysl); });
+  __syncthreads();
   for (int it0 = threadIdx.x; it0 < n * 4; it0 += C::NTHR * 4) {
     double add[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int it = min(it0 + u * C::NTHR, n * 4 - 1);
-      add[u] = rhs_terms(it >> 2, it & 3);
+      add[u] = (a.mode == 2) ? ld_plain(a.bcdiff, it >> 2, c0 + (it & 3)) : 0.0;  // + dt ka (dxx + dyy) fieldbc (665-668)
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
@@ -141,9 +167,40 @@ __global__ void __launch_bounds__(XCfg<LOG2LB>::NTHR, 1) xk_forward(XForwardArgs
       if (it < n * 4) {
         const int l = it & 3, i = it >> 2;
         double* w = &tw[didx(rowof(N, i), l)];
-        double v = (i < a.cut) ? -a.dt * (*w) : 0.0;  // - dt * dealiased conv   (navier.rs:630, 651, 671)
-        if (a.mode == 0) v += ta[didx(i, l)];         // - dt/sx d/dx pres       (navier.rs:627)
-        *w = v + add[u];
+        const double v = (i < a.cut) ? -a.dt * (*w) : 0.0;
+        *w = v + sx_at(i, l, a.fxsd, a.fxsl) + add[u];
+      }
+    }
+  }
+  __syncthreads();
+  if (a.mode == 0) {  // - dt/sx d/dx pres   (navier.rs:627)
+    xtile_fill<C::NTHR>(ta, n, [&](int i, int l) { return ld_plain(a.pres, i, c0 + l); });
+    __syncthreads();
+    cheb_diff<C::NTHR, C::CL>(ta, -1, ta, -1, n, -a.dt * a.isx, red);
+    for (int it = threadIdx.x; it < n * 4; it += C::NTHR) {
+      const int l = it & 3, i = it >> 2;
+      tw[didx(rowof(N, i), l)] += ta[didx(i, l)];
+    }
+  } else if (a.mode == 1) {  // - dt/sy d/dy pres + dt * (that + tbc)   (navier.rs:646-648)
+    xtile_fill<C::NTHR>(ta, mxr, [&](int i, int l) { return ld_sy(a.tmp, i, l, a.tysd, a.tysl); });
+    __syncthreads();
+    for (int it0 = threadIdx.x; it0 < n * 4; it0 += C::NTHR * 4) {
+      double g1[4], g2[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int it = min(it0 + u * C::NTHR, n * 4 - 1);
+        g1[u] = ld_plain(a.dyp, it >> 2, c0 + (it & 3));
+        g2[u] = ld_plain(a.tbc, it >> 2, c0 + (it & 3));
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int it = it0 + u * C::NTHR;
+        if (it < n * 4) {
+          const int l = it & 3, i = it >> 2;
+          const double that = sx_at(i, l, a.txsd, a.txsl) + g2[u];
+          double* w = &tw[didx(rowof(N, i), l)];
+          *w = fma(a.dt, that, fma(-a.dt, g1[u], *w));
+        }
       }
     }
   }
@@ -164,12 +221,19 @@ __global__ void __launch_bounds__(XCfg<LOG2LB>::NTHR, 1) xk_div(XDivArgs a) {
   const int c0 = blockIdx.x * 4;
   const int n = a.nx, m = n - 2;
   const int ncols = a.vx.cols;
-  xtile_fill<C::NTHR>(ta, n, [&](int i, int l) { return ld_stencil_x(a.vx, i, c0 + l, a.sd, a.sl); });
+  double* tb = red + scan_threads(C::NTHR) * 7 + 64;  // second tile (after the scan scratch)
+  xtile_fill<C::NTHR>(tb, m, [&](int i, int l) { return ld_plain(a.vx, i, c0 + l); });
   __syncthreads();
+  xstencil_tile<C::NTHR>(ta, tb, n, a.sd, a.sl);
+  __syncthreads();
+  xtile_fill<C::NTHR>(tb, m, [&](int i, int l) { return ld_plain(a.ey, i, c0 + l); });
   cheb_diff<C::NTHR, C::CL>(ta, -1, ta, -1, n, a.isx, red);
   for (int it = threadIdx.x; it < n * 4; it += C::NTHR) {
     const int l = it & 3, i = it >> 2;
-    const double v = ta[didx(i, l)] + ld_stencil_x(a.ey, i, c0 + l, a.sd, a.sl);
+    double e = 0.0;
+    if (i < m) e = __ldg(&a.sd[i]) * tb[didx(i, l)];
+    if (i >= 2) e = fma(__ldg(&a.sl[i - 2]), tb[didx(i - 2, l)], e);
+    const double v = ta[didx(i, l)] + e;
     ta[didx(i, l)] = v;
     if (c0 + l < ncols) a.div.p[(size_t)i * a.div.ld + c0 + l] = v;
   }
@@ -191,7 +255,9 @@ __global__ void __launch_bounds__(XCfg<LOG2LB>::NTHR, 1) xk_project(XProjectArgs
   const int c0 = blockIdx.x * 4;
   const int n = a.nx, m = n - 2;
   const int ncols = a.phi.cols;
-  xtile_fill<C::NTHR>(ta, n, [&](int i, int l) { return ld_stencil_x(a.phi, i, c0 + l, a.nsd, a.nsl); });
+  xtile_fill<C::NTHR>(tb, m, [&](int i, int l) { return ld_plain(a.phi, i, c0 + l); });
+  __syncthreads();
+  xstencil_tile<C::NTHR>(ta, tb, n, a.nsd, a.nsl);
   __syncthreads();
   cheb_diff<C::NTHR, C::CL>(ta, -1, tb, -1, n, a.isx, red);
   from_ortho<C::NTHR, C::CL>(tb, -1, n, a.t, red);
@@ -253,8 +319,8 @@ static void set_smem(K kern, int bytes) {
   }
 #define XK_CASE_xk_backward(L) XK_CASE_BODY(xk_backward, L, C::SMEM_AW)
 #define XK_CASE_xk_forward(L) XK_CASE_BODY(xk_forward, L, C::SMEM_AW)
-#define XK_CASE_xk_div(L) XK_CASE_BODY(xk_div, L, C::SMEM_A)
-#define XK_CASE_xk_project(L) XK_CASE_BODY(xk_project, L, 2 * C::AROWS * 32 + C::NTHR * 56 + 512)
+#define XK_CASE_xk_div(L) XK_CASE_BODY(xk_div, L, 2 * C::AROWS * 32 + scan_threads(C::NTHR) * 56 + 512)
+#define XK_CASE_xk_project(L) XK_CASE_BODY(xk_project, L, 2 * C::AROWS * 32 + scan_threads(C::NTHR) * 56 + 512)
 
 #define XK_LAUNCH(kern, ncols, nx, nby)                                            \
   do {                                                                             \
@@ -266,8 +332,29 @@ static void set_smem(K kern, int bytes) {
     if (!ok_) throw Error(RP_ERR_INTERNAL, #kern ": unsupported lane length");     \
   } while (0)
 
-void launch_x_backward(const XBackwardArgs3& a, int nb, cudaStream_t s) { XK_LAUNCH(xk_backward, a.a[0].src.cols, a.a[0].t.n, nb); }
-void launch_x_forward(const XForwardArgs3& a, int nb, cudaStream_t s) { XK_LAUNCH(xk_forward, a.a[0].conv.cols, a.a[0].t.n, nb); }
+static int sm_count() {
+#ifndef RP_EMU
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return n;
+#else
+  return 1;
+#endif
+}
+void launch_x_backward(const XBackwardArgs3& a_, int nb, cudaStream_t s) {
+  XBackwardArgs3 a = a_;
+  a.next_wave = sm_count();  // one block per SM: the block that follows on the same SM is about one wave ahead
+  XK_LAUNCH(xk_backward, a.a[0].src.cols, a.a[0].t.n, nb);
+}
+void launch_x_forward(const XForwardArgs3& a_, int nb, cudaStream_t s) {
+  XForwardArgs3 a = a_;
+  a.next_wave = sm_count();
+  XK_LAUNCH(xk_forward, a.a[0].conv.cols, a.a[0].t.n, nb);
+}
 void launch_x_div(const XDivArgs& a, cudaStream_t s) { XK_LAUNCH(xk_div, a.vx.cols, a.nx, 1); }
 void launch_x_project(const XProjectArgs& a, cudaStream_t s) { XK_LAUNCH(xk_project, a.phi.cols, a.nx, 1); }
 

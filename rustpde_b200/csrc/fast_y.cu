@@ -20,8 +20,8 @@ struct YCfg {
   static constexpr int NTHR = (N / 4) < 64 ? 64 : (N / 4);
   static constexpr int ROWS = N + 4;
   static constexpr int CL = chunk_len(n, NTHR);
-  static constexpr int SMEM1 = ROWS * 32 + NTHR * 56 + 512;      // one tile + scratch
-  static constexpr int SMEM2 = 2 * ROWS * 32 + NTHR * 56 + 512;  // two tiles + scratch
+  static constexpr int SMEM1 = ROWS * 32 + scan_threads(NTHR) * 56 + 512;      // one tile + scratch
+  static constexpr int SMEM2 = 2 * ROWS * 32 + scan_threads(NTHR) * 56 + 512;  // two tiles + scratch
 };
 
 #define YK_SMEM(td, red)          \
