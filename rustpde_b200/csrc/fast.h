@@ -171,5 +171,70 @@ struct XProjectArgs {  // a1 = from_ortho_x(D_x S_x phi)/sx, a2 = from_ortho_x(S
 };
 void launch_x_project(const XProjectArgs& a, cudaStream_t s);
 
+// ---- periodic path (fast_p.cu): complex arrays are passed as Mat with ld / cols in complex units ----
+bool px_supported(int n0);
+
+struct PC2rArgs {  // c2r along x of a spectral array and of its (i k / sx) derivative
+  Mat src;         // [mk, cols] complex
+  Mat val, dx;     // [nx, cols] real
+  double isx;
+  const double2* tw;  // exp(-2 pi i k / n)
+  int n;
+};
+struct PC2rArgs3 {
+  PC2rArgs a[3];
+};
+void launch_p_c2r(const PC2rArgs3& a, int nbatch, cudaStream_t s);
+
+struct PR2cArgs {  // r2c along x + dealias cut
+  Mat src;         // [nx, cols] real
+  Mat dst;         // [mk, cols] complex
+  int cut;         // first zeroed kx
+  const double2* tw;
+  int n;
+};
+struct PR2cArgs3 {
+  PR2cArgs a[3];
+};
+void launch_p_r2c(const PR2cArgs3& a, int nbatch, cudaStream_t s);
+
+struct PHholtzArgs {  // rhs assembly + per-mode Helmholtz solve on complex rows
+  Mat chat;           // [mk, ny] convection term
+  Mat fld, out;       // [mk, my] old / new composite coefficients (may alias)
+  Mat pres, tmp, tbc, bcdiff;  // mode 0: pres; mode 1: pres, tmp [mk, my], tbc; mode 2: bcdiff
+  const double *sd, *sl, *tsd, *tsl;
+  int mode;
+  double dt, isx, isy;
+  B2Tabs b2;
+  ModeTabs m;
+  int ny;
+};
+struct PHholtzArgs3 {
+  PHholtzArgs a[3];
+};
+void launch_p_hholtz(const PHholtzArgs3& a, int nbatch, cudaStream_t s);
+
+struct PDivPoisArgs {  // divergence + per-mode Poisson solve
+  Mat ux, uy;          // [mk, my]
+  Mat div;             // [mk, ny]
+  Mat phi;             // [mk, my]
+  const double *sd, *sl;
+  double isx, isy;
+  B2Tabs b2;
+  ModeTabs m;
+  int ny;
+};
+void launch_p_divpois(const PDivPoisArgs& a, cudaStream_t s);
+
+struct PProjectArgs {  // projection + pressure update
+  Mat phi, ux, uy;     // [mk, my]
+  Mat div, pres;       // [mk, ny]
+  const double *nsd, *nsl;
+  TdmaTabs t;
+  double isx, isy, nu, inv_dt;
+  int ny;
+};
+void launch_p_project(const PProjectArgs& a, cudaStream_t s);
+
 }  // namespace fk
 }  // namespace rp

@@ -1,0 +1,307 @@
+// fast_p.cu -- specialised kernels of the periodic Navier2D::update (Fourier x Chebyshev,
+// navier.rs:384-467 + 737-765): real FFT along x on column strips, per-mode passes on complex rows.
+//
+//   pk_c2r      : x-backward, c2r (r2c.rs:283-303) of a spectral array and of its (ik/sx) derivative
+//   pk_r2c      : x-forward, r2c (r2c.rs:250-272) + dealias cut in kx (navier.rs:1022-1032)
+//   pk_hholtz   : rhs assembly (navier.rs:622-674) + per-mode Helmholtz solve (hholtz.rs:156-197)
+//   pk_divpois  : divergence (navier.rs:698-703) + per-mode Poisson solve (poisson.rs:131-149)
+//   pk_project  : projection and pressure update (navier.rs:683-721)
+// The y passes in physical space (B_y S_y, products, forward DCT-y) are the kernels of fast_y.cu.
+//
+// x kernels: a block owns 4 real columns = two packed complex FFT lanes (columns a, b of a lane travel
+// as a + i b through one complex FFT of length n).  y kernels: a block owns 2 complex rows = 4 real
+// lanes (re, im of row r0, re, im of row r0 + 1); both parts of a row share the row's eigenvalue.
+#include "fast_y.cuh"
+
+namespace rp {
+namespace fk {
+
+// ---- x kernels ---------------------------------------------------------------------------------
+template <int LOG2N>
+struct PXCfg {
+  static constexpr int N = 1 << LOG2N;
+  static constexpr int NTHR = (N / 8) < 64 ? 64 : (N / 8);
+  static constexpr int SMEM = N * 32;
+};
+
+template <int LOG2N>
+__global__ void __launch_bounds__(PXCfg<LOG2N>::NTHR, 2) pk_c2r(PC2rArgs3 a3) {
+  typedef PXCfg<LOG2N> C;
+  const PC2rArgs& a = a3.a[blockIdx.y];
+  RP_DYN_SMEM(double, td);
+  cplx* tc = (cplx*)td;
+  constexpr int n = C::N, mkr = n / 2 + 1;
+  const int c0 = blockIdx.x * 4;
+  const int ncols = a.src.cols;
+  const cplx* src = (const cplx*)a.src.p;
+  const double inv_n = 1.0 / (double)n;
+  for (int pass = 0; pass < 2; ++pass) {
+    const Mat& o = pass ? a.dx : a.val;
+    for (int it = threadIdx.x; it < mkr * 2; it += C::NTHR) {
+      const int k = it >> 1, c = it & 1;
+      const int ca = c0 + 2 * c, cb = ca + 1;
+      cplx xa = mk(0.0, 0.0), xb = mk(0.0, 0.0);
+      if (ca < ncols) xa = src[(size_t)k * a.src.ld + ca];
+      if (cb < ncols) xb = src[(size_t)k * a.src.ld + cb];
+      if (pass) {  // times i k / sx   (r2c.rs:88-99, space2.rs:247-264)
+        const double kk = (double)k * a.isx;
+        xa = mk(-kk * xa.y, kk * xa.x);
+        xb = mk(-kk * xb.y, kk * xb.x);
+      }
+      if (k == 0 || 2 * k == n) {  // c2r ignores Im of the DC and Nyquist bins
+        xa.y = 0.0;
+        xb.y = 0.0;
+      }
+      tc[cidx(k, c)] = mk(xa.x - xb.y, xa.y + xb.x);                                    // X_a + i X_b
+      if (k > 0 && 2 * k != n) tc[cidx(n - k, c)] = mk(xa.x + xb.y, -xa.y + xb.x);     // conj(X_a) + i conj(X_b)
+    }
+    __syncthreads();
+    fft<LOG2N, C::NTHR, true, false>(tc, a.tw, nullptr);
+    for (int it = threadIdx.x; it < n * 2; it += C::NTHR) {
+      const int i = it >> 1, c = it & 1;
+      const int ca = c0 + 2 * c;
+      const cplx z = tc[cidx(i, c)];
+      double* row = o.p + (size_t)i * o.ld;
+      if (ca < o.cols) row[ca] = z.x * inv_n;
+      if (ca + 1 < o.cols) row[ca + 1] = z.y * inv_n;
+    }
+    __syncthreads();
+  }
+}
+
+template <int LOG2N>
+__global__ void __launch_bounds__(PXCfg<LOG2N>::NTHR, 2) pk_r2c(PR2cArgs3 a3) {
+  typedef PXCfg<LOG2N> C;
+  const PR2cArgs& a = a3.a[blockIdx.y];
+  RP_DYN_SMEM(double, td);
+  cplx* tc = (cplx*)td;
+  constexpr int n = C::N, mkr = n / 2 + 1;
+  const int c0 = blockIdx.x * 4;
+  const int ncols = a.src.cols;
+  for (int it = threadIdx.x; it < n * 2; it += C::NTHR) {
+    const int i = it >> 1, c = it & 1;
+    const int ca = c0 + 2 * c;
+    const double* row = a.src.p + (size_t)i * a.src.ld;
+    tc[cidx(i, c)] = mk(ca < ncols ? row[ca] : 0.0, ca + 1 < ncols ? row[ca + 1] : 0.0);
+  }
+  __syncthreads();
+  fft<LOG2N, C::NTHR, false, false>(tc, a.tw, nullptr);
+  cplx* dst = (cplx*)a.dst.p;
+  for (int it = threadIdx.x; it < mkr * 2; it += C::NTHR) {
+    const int k = it >> 1, c = it & 1;
+    const int ca = c0 + 2 * c, cb = ca + 1;
+    const cplx zk = tc[cidx(k, c)], zc = tc[cidx(k == 0 ? 0 : n - k, c)];
+    const cplx zm = mk(zc.x, -zc.y);
+    const cplx s = cadd(zk, zm), d = csub(zk, zm);
+    const double h = (k < a.cut) ? 0.5 : 0.0;  // dealias: modes kx >= cut are zeroed
+    if (ca < ncols) dst[(size_t)k * a.dst.ld + ca] = mk(h * s.x, h * s.y);
+    if (cb < ncols) dst[(size_t)k * a.dst.ld + cb] = mk(h * d.y, -h * d.x);
+  }
+}
+
+// ---- y kernels on complex rows -------------------------------------------------------------------
+// lane l of the tile: row r0 + (l >> 1), part l & 1 (re / im)
+FK_DEV int prow_of(int r0, int l) { return r0 + (l >> 1); }
+// element (row, j).part of a complex array, zero outside [0, rows) x [0, cols)
+FK_DEV double ldc(const Mat& a, int r, int j, int part) {
+  const double v = a.p[((size_t)min(r, a.rows - 1) * a.ld + min(max(j, 0), a.cols - 1)) * 2 + part];
+  return (r < a.rows && j >= 0 && j < a.cols) ? v : 0.0;
+}
+// composite -> ortho along y while loading: p_j = d_j c_j + l_{j-2} c_{j-2}
+FK_DEV double ldc_stencil(const Mat& a, int r, int j, int part, const double* __restrict__ sd, const double* __restrict__ sl) {
+  const int m = a.cols;
+  const double v0 = ldc(a, r, min(j, m - 1), part), v2 = ldc(a, r, max(j - 2, 0), part);
+  const double d = (j < m) ? __ldg(&sd[min(j, m - 1)]) : 0.0;
+  const double l = (j >= 2) ? __ldg(&sl[max(j - 2, 0)]) : 0.0;
+  return fma(l, v2, d * v0);
+}
+// (i k s z).part for z = (re, im): re' = -k s im, im' = k s re
+FK_DEV double ik_part(double ks, double re, double im, int part) { return part ? ks * re : -ks * im; }
+
+template <int LOG2L>
+__global__ void __launch_bounds__(YCfg<LOG2L>::NTHR, 1) pk_hholtz(PHholtzArgs3 a3) {
+  typedef YCfg<LOG2L> C;
+  const PHholtzArgs& a = a3.a[blockIdx.y];
+  YK_SMEM(td, red0);
+  double* ti = td + C::ROWS * 4;
+  double* red = ti + C::ROWS * 4;
+  (void)red0;
+  const int r0 = blockIdx.x * 2;
+  constexpr int n = C::n, m = n - 2;
+  const int nrows = a.chat.rows;
+  if (a.mode == 1) {  // - dt/sy d/dy pres   (navier.rs:646)
+    tile_fill<C::NTHR>(td, n, [&](int j, int l) { return ldc(a.pres, prow_of(r0, l), j, l & 1); });
+    __syncthreads();
+    cheb_diff<C::NTHR, C::CL>(td, -1, td, -1, n, -a.dt * a.isy, red);
+  }
+  tile_fill<C::NTHR>(ti, m, [&](int j, int l) { return a.m.inv[(size_t)min(prow_of(r0, l), nrows - 1) * a.m.inv_ld + j]; });
+  {
+    const int tot = n * 4;
+    for (int it0 = threadIdx.x; it0 < tot; it0 += C::NTHR * 4) {
+      double v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int it = min(it0 + u * C::NTHR, tot - 1);
+        const int j = it >> 2, l = it & 3, r = prow_of(r0, l), part = l & 1;
+        double x = -a.dt * ldc(a.chat, r, j, part);                       // - dt * conv          (630, 651, 671)
+        x += ldc_stencil(a.fld, r, j, part, a.sd, a.sl);                  // + to_ortho(field)    (625, 644, 663)
+        if (a.mode == 0) {                                                // - dt/sx d/dx pres    (627)
+          const double ks = -a.dt * a.isx * (double)min(r, nrows - 1);
+          x += ik_part(ks, ldc(a.pres, r, j, 0), ldc(a.pres, r, j, 1), part);
+        } else if (a.mode == 1) {                                         // + dt * (that + tbc)  (648)
+          x = fma(a.dt, ldc_stencil(a.tmp, r, j, part, a.tsd, a.tsl) + ldc(a.tbc, r, j, part), x);
+        } else {                                                          // + dt ka lap(fieldbc) (665-668)
+          x += ldc(a.bcdiff, r, j, part);
+        }
+        v[u] = x;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int it = it0 + u * C::NTHR;
+        if (it < tot) {
+          double* w = &td[didx(it >> 2, it & 3)];
+          *w = (a.mode == 1) ? *w + v[u] : v[u];
+        }
+      }
+    }
+  }
+  __syncthreads();
+  const double mu = __ldg(&a.m.lam[min(prow_of(r0, threadIdx.x & 3), nrows - 1)]) + a.m.alpha;
+  mode_solve<C::NTHR, C::CL>(td, ti, n, a.b2, a.m, mu, red);
+  tile_drain<C::NTHR>(td, -1, m, [&](int j, int l, double v) {
+    const int r = prow_of(r0, l);
+    if (r < a.out.rows) a.out.p[((size_t)r * a.out.ld + j) * 2 + (l & 1)] = v;
+  });
+}
+
+template <int LOG2L>
+__global__ void __launch_bounds__(YCfg<LOG2L>::NTHR, 1) pk_divpois(PDivPoisArgs a) {
+  typedef YCfg<LOG2L> C;
+  YK_SMEM(td, red0);
+  double* ti = td + C::ROWS * 4;
+  double* red = ti + C::ROWS * 4;
+  (void)red0;
+  const int r0 = blockIdx.x * 2;
+  constexpr int n = C::n, m = n - 2;
+  const int nrows = a.ux.rows;
+  // div = i k / sx S_y ux + D_y S_y uy / sy   (navier.rs:698-703)
+  tile_fill<C::NTHR>(td, n, [&](int j, int l) { return ldc_stencil(a.uy, prow_of(r0, l), j, l & 1, a.sd, a.sl); });
+  tile_fill<C::NTHR>(ti, m, [&](int j, int l) { return a.m.inv[(size_t)min(prow_of(r0, l), nrows - 1) * a.m.inv_ld + j]; });
+  __syncthreads();
+  cheb_diff<C::NTHR, C::CL>(td, -1, td, -1, n, a.isy, red);
+  for (int it = threadIdx.x; it < n * 4; it += C::NTHR) {
+    const int j = it >> 2, l = it & 3, r = prow_of(r0, l), part = l & 1;
+    const double ks = a.isx * (double)min(r, nrows - 1);
+    const double re = ldc_stencil(a.ux, r, j, 0, a.sd, a.sl), im = ldc_stencil(a.ux, r, j, 1, a.sd, a.sl);
+    const double v = td[didx(j, l)] + ik_part(ks, re, im, part);
+    td[didx(j, l)] = v;
+    if (r < a.div.rows) a.div.p[((size_t)r * a.div.ld + j) * 2 + part] = v;
+  }
+  __syncthreads();
+  const double mu = __ldg(&a.m.lam[min(prow_of(r0, threadIdx.x & 3), nrows - 1)]) + a.m.alpha;
+  mode_solve<C::NTHR, C::CL>(td, ti, n, a.b2, a.m, mu, red);
+  tile_drain<C::NTHR>(td, -1, m, [&](int j, int l, double v) {
+    const int r = prow_of(r0, l);
+    if (r == 0 && j == 0) v = 0.0;  // pres[1].vhat[[0,0]] = 0   (navier.rs:714)
+    if (r < a.phi.rows) a.phi.p[((size_t)r * a.phi.ld + j) * 2 + (l & 1)] = v;
+  });
+}
+
+template <int LOG2L>
+__global__ void __launch_bounds__(YCfg<LOG2L>::NTHR, 2) pk_project(PProjectArgs a) {
+  typedef YCfg<LOG2L> C;
+  YK_SMEM(td, red);
+  const int r0 = blockIdx.x * 2;
+  constexpr int n = C::n, m = n - 2;
+  const int nrows = a.phi.rows;
+  // ux -= from_ortho_y(i k / sx S_y phi)   (navier.rs:683-695)
+  tile_fill<C::NTHR>(td, n, [&](int j, int l) {
+    const int r = prow_of(r0, l);
+    const double ks = a.isx * (double)min(r, nrows - 1);
+    return ik_part(ks, ldc_stencil(a.phi, r, j, 0, a.nsd, a.nsl), ldc_stencil(a.phi, r, j, 1, a.nsd, a.nsl), l & 1);
+  });
+  __syncthreads();
+  from_ortho<C::NTHR, C::CL>(td, -1, n, a.t, red);
+  tile_drain<C::NTHR>(td, -1, m, [&](int j, int l, double v) {
+    const int r = prow_of(r0, l);
+    if (r < a.ux.rows) a.ux.p[((size_t)r * a.ux.ld + j) * 2 + (l & 1)] -= v;
+  });
+  __syncthreads();
+  // to_ortho(phi): pressure update p += -nu div + to_ortho(phi) / dt   (navier.rs:717-721)
+  tile_fill<C::NTHR>(td, n, [&](int j, int l) { return ldc_stencil(a.phi, prow_of(r0, l), j, l & 1, a.nsd, a.nsl); });
+  __syncthreads();
+  for (int it0 = threadIdx.x; it0 < n * 4; it0 += C::NTHR * 4) {
+    double dv[4], pv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int it = min(it0 + u * C::NTHR, n * 4 - 1);
+      dv[u] = ldc(a.div, prow_of(r0, it & 3), it >> 2, it & 1);
+      pv[u] = ldc(a.pres, prow_of(r0, it & 3), it >> 2, it & 1);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int it = it0 + u * C::NTHR;
+      if (it < n * 4) {
+        const int j = it >> 2, l = it & 3, r = prow_of(r0, l);
+        if (r < a.pres.rows) a.pres.p[((size_t)r * a.pres.ld + j) * 2 + (l & 1)] = fma(-a.nu, dv[u], pv[u]) + td[didx(j, l)] * a.inv_dt;
+      }
+    }
+  }
+  __syncthreads();
+  // uy -= from_ortho_y(D_y S_y phi / sy)
+  cheb_diff<C::NTHR, C::CL>(td, -1, td, -1, n, a.isy, red);
+  from_ortho<C::NTHR, C::CL>(td, -1, n, a.t, red);
+  tile_drain<C::NTHR>(td, -1, m, [&](int j, int l, double v) {
+    const int r = prow_of(r0, l);
+    if (r < a.uy.rows) a.uy.p[((size_t)r * a.uy.ld + j) * 2 + (l & 1)] -= v;
+  });
+}
+
+// ---- launchers -----------------------------------------------------------------------------------
+#define PX_SIZES(X) X(5) X(6) X(9) X(10) X(11)
+
+bool px_supported(int n0) {
+  const int l = log2_of(n0);
+#define X(L) \
+  if (l == L) return true;
+  PX_SIZES(X)
+#undef X
+  return false;
+}
+
+#define PX_CASE(kern, L)                                                              \
+  if (l_ == L) {                                                                      \
+    typedef PXCfg<L> C;                                                               \
+    static bool init_ = false;                                                        \
+    if (!init_) {                                                                     \
+      set_smem(kern<L>, C::SMEM);                                                     \
+      init_ = true;                                                                   \
+    }                                                                                 \
+    RP_LAUNCH(kern<L>, dim3(nb_, nby_), dim3(C::NTHR), (size_t)C::SMEM, s, a);        \
+    ok_ = true;                                                                       \
+  }
+#define PX_CASE_pk_c2r(L) PX_CASE(pk_c2r, L)
+#define PX_CASE_pk_r2c(L) PX_CASE(pk_r2c, L)
+#define PX_LAUNCH(kern, ncols, nx, nby)                                            \
+  do {                                                                             \
+    const int l_ = log2_of(nx);                                                    \
+    const int nb_ = ((ncols) + 3) / 4, nby_ = (nby);                               \
+    bool ok_ = false;                                                              \
+    PX_SIZES(PX_CASE_##kern)                                                       \
+    if (!ok_) throw Error(RP_ERR_INTERNAL, #kern ": unsupported lane length");     \
+  } while (0)
+
+void launch_p_c2r(const PC2rArgs3& a, int nb, cudaStream_t s) { PX_LAUNCH(pk_c2r, a.a[0].src.cols, a.a[0].n, nb); }
+void launch_p_r2c(const PR2cArgs3& a, int nb, cudaStream_t s) { PX_LAUNCH(pk_r2c, a.a[0].src.cols, a.a[0].n, nb); }
+
+#define YK_CASE_pk_hholtz(L) YK_CASE_BODY(pk_hholtz, L, true, a)
+#define YK_CASE_pk_divpois(L) YK_CASE_BODY(pk_divpois, L, true, a)
+#define YK_CASE_pk_project(L) YK_CASE_BODY(pk_project, L, false, a)
+
+// complex rows: a block owns 2 rows -> the launch helper's "rows / 4" becomes "2 * rows / 4"
+void launch_p_hholtz(const PHholtzArgs3& a, int nb, cudaStream_t s) { YK_LAUNCH(pk_hholtz, true, 2 * a.a[0].chat.rows, a.a[0].ny, a, nb); }
+void launch_p_divpois(const PDivPoisArgs& a, cudaStream_t s) { YK_LAUNCH(pk_divpois, true, 2 * a.ux.rows, a.ny, a, 1); }
+void launch_p_project(const PProjectArgs& a, cudaStream_t s) { YK_LAUNCH(pk_project, false, 2 * a.phi.rows, a.ny, a, 1); }
+
+}  // namespace fk
+}  // namespace rp

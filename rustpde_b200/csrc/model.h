@@ -217,6 +217,7 @@ class Navier2D {
   void build_step_confined();
   void build_step_periodic();
   void build_step_confined_fast();
+  void build_step_periodic_fast();
   void add_fast(const char* name, double bytes, std::function<void()> fn);
   std::vector<std::function<void()>> fast_ops_;  // specialised kernels (fast.h), launched on `stream`
   void build_y_phase();

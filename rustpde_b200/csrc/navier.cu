@@ -175,7 +175,9 @@ void Navier2D::build_step() {
   if (!ops_.empty()) return;
   const char* nf = getenv("RUSTPDE_B200_NO_FAST");
   const bool fast_ok = !(nf && nf[0] == '1');
-  if (periodic)
+  if (periodic && fast_ok && fk::px_supported(nx) && fk::y_supported(ny))
+    build_step_periodic_fast();
+  else if (periodic)
     build_step_periodic();
   else if (fast_ok && fk::x_supported(nx) && fk::y_supported(ny))
     build_step_confined_fast();
@@ -604,6 +606,110 @@ void Navier2D::build_step_confined_fast() {
     add_fast("pressure_update", 5 * fb, [this, a]() { fk::launch_y_pres(a, stream); });
   }
   (void)my;
+}
+
+// --------------------------------------------------------------------------
+// Periodic step on the specialised kernels (fast_p.cu + the physical-space y
+// kernels of fast_y.cu): same schedule and arrays as build_step_periodic.
+// --------------------------------------------------------------------------
+void Navier2D::build_step_periodic_fast() {
+  const Base &bx = *ux->sp.b0, &byu = *ux->sp.b1, &byt = *temp->sp.b1, &byn = *pres1->sp.b1, &byo = *field->sp.b1;
+  const int mk = nx / 2 + 1;
+  const double isx = 1.0 / scale[0], isy = 1.0 / scale[1];
+  Field2* flds[3] = {ux.get(), uy.get(), temp.get()};
+  const Base* bys[3] = {&byu, &byu, &byt};
+  const double fb = 8.0 * (double)nx * (double)ny;
+  const int val_idx[3] = {0, 1, -1}, dx_idx[3] = {2, 4, 6}, dy_idx[3] = {3, 5, 7};
+  const fk::Mat none{nullptr, 0, 0, 0};
+  {  // ---- 1. x-backward (c2r): value and (ik/sx) derivative -------------------
+    fk::PC2rArgs3 a3;
+    for (int f = 0; f < 3; ++f) {
+      fk::PC2rArgs& a = a3.a[f];
+      a.src = mat_of(flds[f]->vhat), a.val = mat_of(ax_[f]), a.dx = mat_of(adx_[f]);
+      a.isx = isx;
+      a.tw = bx.fft.plan.tw;
+      a.n = nx;
+    }
+    add_fast("x_backward_c2r", 9 * fb, [this, a3]() { fk::launch_p_c2r(a3, 3, stream); });
+  }
+  {  // ---- 2. y-backward -> physical space ------------------------------------
+    fk::YBackwardArgs3 a3;
+    for (int f = 0; f < 3; ++f) {
+      fk::YBackwardArgs& a = a3.a[f];
+      a.a = mat_of(ax_[f]), a.adx = mat_of(adx_[f]);
+      a.val = val_idx[f] >= 0 ? mat_of(phys_[val_idx[f]]) : none;
+      a.dy = mat_of(phys_[dy_idx[f]]), a.dx = mat_of(phys_[dx_idx[f]]);
+      a.sd = bys[f]->d_sd.as<double>(), a.sl = bys[f]->d_sl.as<double>();
+      a.isy = isy;
+      a.t = dct_of(byo);
+    }
+    add_fast("y_backward", 14 * fb, [this, a3]() { fk::launch_y_backward(a3, 3, stream); });
+  }
+  {  // ---- 3. products + forward DCT-y + dealias-y -----------------------------
+    fk::YConvArgs3 a3;
+    for (int f = 0; f < 3; ++f) {
+      fk::YConvArgs& a = a3.a[f];
+      a.u = mat_of(phys_[0]), a.du = mat_of(phys_[dx_idx[f]]), a.v = mat_of(phys_[1]), a.dv = mat_of(phys_[dy_idx[f]]);
+      a.bcx = f == 2 ? mat_of(dxtbc_) : none;
+      a.bcy = f == 2 ? mat_of(dytbc_) : none;
+      a.out = mat_of(bconv_[f]);
+      a.cut = dealias ? (ny * 2) / 3 : ny;
+      a.t = dct_of(byo);
+    }
+    add_fast("conv_y_forward", 17 * fb, [this, a3]() { fk::launch_y_conv(a3, 3, stream); });
+  }
+  {  // ---- 4. x-forward (r2c) + dealias ------------------------------------------
+    fk::PR2cArgs3 a3;
+    for (int f = 0; f < 3; ++f) {
+      fk::PR2cArgs& a = a3.a[f];
+      a.src = mat_of(bconv_[f]), a.dst = mat_of(chat_[f]);
+      a.cut = dealias ? (mk * 2) / 3 : mk;  // navier.rs:1028 with shape[0] = nx/2+1
+      a.tw = bx.fft.plan.tw;
+      a.n = nx;
+    }
+    add_fast("x_forward_r2c", 6 * fb, [this, a3]() { fk::launch_p_r2c(a3, 3, stream); });
+  }
+  // ---- 5. rhs assembly + per-mode Helmholtz solves (hholtz.rs:156-197).  The buoyancy term of uy
+  //         reads the old temperature, so the temperature solve is a launch of its own.
+  fk::PHholtzArgs3 h3;
+  for (int f = 0; f < 3; ++f) {
+    fk::PHholtzArgs& a = h3.a[f];
+    a.chat = mat_of(chat_[f]);
+    a.fld = mat_of(flds[f]->vhat), a.out = mat_of(flds[f]->vhat);
+    a.pres = mat_of(pres0->vhat), a.tmp = mat_of(temp->vhat), a.tbc = mat_of(tbc_ortho_), a.bcdiff = mat_of(bcdiff_);
+    a.sd = bys[f]->d_sd.as<double>(), a.sl = bys[f]->d_sl.as<double>();
+    a.tsd = byt.d_sd.as<double>(), a.tsl = byt.d_sl.as<double>();
+    a.mode = f;
+    a.dt = dt, a.isx = isx, a.isy = isy;
+    a.b2 = b2_of(byo);
+    a.m = mode_of(solver[f]->ts.mode);
+    a.ny = ny;
+  }
+  add_fast("rhs_hholtz_mode_y", 10 * fb, [this, h3]() { fk::launch_p_hholtz(h3, 2, stream); });
+  {
+    fk::PHholtzArgs3 t3 = h3;
+    t3.a[0] = h3.a[2];
+    add_fast("rhs_hholtz_mode_y", 4 * fb, [this, t3]() { fk::launch_p_hholtz(t3, 1, stream); });
+  }
+  {  // ---- 6. divergence + Poisson (per-mode) -------------------------------------
+    fk::PDivPoisArgs a;
+    a.ux = mat_of(ux->vhat), a.uy = mat_of(uy->vhat), a.div = mat_of(div_), a.phi = mat_of(pres1->vhat);
+    a.sd = byu.d_sd.as<double>(), a.sl = byu.d_sl.as<double>();
+    a.isx = isx, a.isy = isy;
+    a.b2 = b2_of(byo);
+    a.m = mode_of(solver[3]->ts.mode);
+    a.ny = ny;
+    add_fast("divergence_poisson_mode_y", 5 * fb, [this, a]() { fk::launch_p_divpois(a, stream); });
+  }
+  {  // ---- 7. projection + pressure update -----------------------------------------
+    fk::PProjectArgs a;
+    a.phi = mat_of(pres1->vhat), a.ux = mat_of(ux->vhat), a.uy = mat_of(uy->vhat), a.div = mat_of(div_), a.pres = mat_of(pres0->vhat);
+    a.nsd = byn.d_sd.as<double>(), a.nsl = byn.d_sl.as<double>();
+    a.t = tdma_of(byu);
+    a.isx = isx, a.isy = isy, a.nu = nu, a.inv_dt = 1.0 / dt;
+    a.ny = ny;
+    add_fast("project_pressure_update", 8 * fb, [this, a]() { fk::launch_p_project(a, stream); });
+  }
 }
 
 void Navier2D::build_step_periodic() {

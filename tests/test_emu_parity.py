@@ -123,6 +123,33 @@ def test_navier_periodic(emu, nx, ny):
     assert max(derr) < 1e-9, (derr, dn, do)
 
 
+@pytest.mark.parametrize("nx,ny", [(32, 33), (64, 65), (32, 65)])
+def test_navier_periodic_specialised_kernels(emu, nx, ny):
+    """Sizes served by the specialised periodic kernels (fast_p.cu): pow2 r2c/c2r along x, pow2 DCT along y."""
+    import rustpde_b200 as R
+    assert R.Navier2D.new_periodic(nx, ny, 1e5, 1.0, 0.01, 1.0, lib=emu).kernel_path()[0]
+    err, derr, dn, do = pc.check_navier_steps(emu, True, nx, ny, 4, batch=2)
+    assert max(derr) < 1e-9, (derr, dn, do)
+
+
+def test_navier_periodic_specialised_aspect_no_dealias(emu):
+    import oracle as O
+    import rustpde_b200 as R
+    o = O.Navier2D.new_periodic(32, 33, 1e4, 0.7, 0.02, 1.5, banded=True)
+    n = R.Navier2D.new_periodic(32, 33, 1e4, 0.7, 0.02, 1.5, lib=emu)
+    o.dealias = False
+    n.dealias = False
+    assert n.kernel_path()[0]
+    for x in (n, o):
+        x.set_velocity(0.1, 2.0, 1.0)
+        x.set_temperature(0.3, 1.0, 2.0)
+    n.update(3)
+    for _ in range(3):
+        o.update()
+    err = pc.navier_field_errors(n, o)
+    assert max(err.values()) < 1e-9, err
+
+
 def test_navier_aspect_and_no_dealias(emu):
     import oracle as O
     import rustpde_b200 as R

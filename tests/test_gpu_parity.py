@@ -167,6 +167,17 @@ def test_fast_diag_parity_split(gpu, which, kx, ky, nx, ny):
     assert e1 <= tol and e2 <= tol, (e1, e2)
 
 
+@pytest.mark.parametrize("nx,ny,steps", [(32, 33, 6), (64, 65, 50), (512, 513, 20), (2048, 2049, 2)])
+def test_navier_periodic_specialised_kernels(gpu, nx, ny, steps):
+    """Specialised periodic kernels (fast_p.cu): config-3 grid 512x513 and the 2048x2049 grid.
+    Fields <= 1e-9 relative, diagnostics <= 1e-9 relative."""
+    import rustpde_b200 as R
+    assert R.Navier2D.new_periodic(nx, ny, 1e6, 1.0, 2e-3, 1.0, lib=gpu).kernel_path()[0]
+    ra, dt = (1e6, 2e-3) if nx < 1000 else (1e9, 1e-4)
+    err, derr, dn, do = pc.check_navier_steps(gpu, True, nx, ny, steps, ra=ra, dt=dt, tol=1e-9, batch=5)
+    assert max(derr) < 1e-9, (derr, dn, do)
+
+
 @pytest.mark.parametrize("nx,ny,steps", [(16, 17, 6), (24, 20, 6), (128, 129, 50), (512, 513, 5)])
 def test_navier_periodic(gpu, nx, ny, steps):
     err, derr, dn, do = pc.check_navier_steps(gpu, True, nx, ny, steps, ra=1e6, dt=2e-3, tol=1e-9, batch=5)
