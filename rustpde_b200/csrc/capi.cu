@@ -132,6 +132,7 @@ int rp_field_upload_vhat(rp_field_t* f, const double* v, size_t len) {
     need(f && v, RP_ERR_INVALID, "null argument");
     need(len == arr_len(f->f->vhat), RP_ERR_SHAPE, "vhat: size mismatch");
     f->f->vhat.upload(v, f->f->stream);
+    ++f->f->vhat_version;
     rt::sync(f->f->stream);
   });
 }

@@ -138,6 +138,7 @@ void Field2::build_transforms() {
 }
 
 void Field2::forward() {
+  ++vhat_version;
   fwd_y_.launch(stream);
   fwd_x_.launch(stream);
 }
@@ -150,6 +151,7 @@ void Field2::to_ortho() {
   to_y_.launch(stream);
 }
 void Field2::from_ortho() {
+  ++vhat_version;
   if (from_x_.valid) from_x_.launch(stream);
   from_y_.launch(stream);
 }

@@ -99,6 +99,7 @@ class Field2 {
   Arr v, vhat, ortho;  // ortho: staging for to_ortho / from_ortho / gradient results
   std::vector<double> x[2], dx[2];
   cudaStream_t stream = 0;
+  unsigned long long vhat_version = 0;  // bumped whenever vhat is rewritten from outside a Navier2D step
 
   void forward();
   void backward();
@@ -229,6 +230,7 @@ class Navier2D {
   Arr a1_, a2_;
   bool graph_dirty_ = true;
   bool use_graph_ = true;
+  unsigned long long dyp_version_ = ~0ull;  // pres0 version dyp_ was computed from
   // work arrays
   Arr ax_[3], adx_[3];           // x-backward results: value and d/dx   [nx x my]
   Arr phys_[8];                  // ux, uy, dxu, dyu, dxv, dyv, dxT, dyT   [nx x ny]

@@ -859,9 +859,12 @@ void Navier2D::update(int nsteps) {
   build_step();
   for (Field2* f : {temp.get(), ux.get(), uy.get(), pres0.get(), pres1.get(), field.get()}) f->stream = stream;
   for (auto& s : solver) s->stream = stream;
-  if (!periodic) {  // d/dy pres of the current pressure (it may have been uploaded since the last step)
+  if (!periodic && dyp_version_ != pres0->vhat_version) {
+    // d/dy pres of the current pressure: every step leaves it behind for the next one, so this is only
+    // needed at the first step and after the pressure was rewritten from outside (upload / forward)
     pres0->gradient(0, 1, scale);
     copy_arr(dyp_, pres0->ortho, stream);
+    dyp_version_ = pres0->vhat_version;
   }
 #ifndef RP_EMU
   if (use_graph_) {
