@@ -35,6 +35,7 @@ WORKLOADS = {
     "periodic512": (True, 512, 513, 1e7, 1.0, 2e-3, 1.0, True, "Navier2D::new_periodic 512x513 Ra=1e7 Pr=1 dt=2e-3"),
     "confined64": (False, 64, 64, 1e5, 1.0, 0.02, 1.0, True, "Navier2D::new 64x64 Ra=1e5 Pr=1 dt=0.02 adiabatic"),
     "periodic2048": (True, 2048, 2049, 1e9, 1.0, 1e-4, 1.0, True, "Navier2D::new_periodic 2048x2049 Ra=1e9 Pr=1 dt=1e-4"),
+    "periodic8192": (True, 8192, 8193, 1e10, 1.0, 2e-5, 1.0, True, "Navier2D::new_periodic 8192x8193 Ra=1e10 Pr=1 dt=2e-5 (one GPU, generic lane programs)"),
     "confined1024": (False, 1024, 1025, 1e8, 1.0, 2e-4, 1.0, True, "Navier2D::new confined 1024x1025 Ra=1e8 Pr=1 dt=2e-4 adiabatic"),
 }
 METRIC = "Navier2D time steps/sec at Nx(N+1) (device-timed)"

@@ -61,9 +61,20 @@ FK_DEV void prefetch_strip(const Mat& a, int c0, int nrows) {
 RP_HD constexpr int scan_threads(int nthr) { return nthr > 512 ? 512 : nthr; }
 
 // ---- tile addressing --------------------------------------------------------
-FK_DEV int prow(int i) { return i ^ ((i >> 3) & 3); }
-FK_DEV int didx(int i, int r) { return prow(i) * 4 + r; }  // as double
-FK_DEV int cidx(int i, int c) { return prow(i) * 2 + c; }  // as double2
+// LC = packed complex lanes per tile row (2: the default 4-real-lane tile; 1: long lanes whose 4-lane tile
+// would not fit shared memory).  A row is LC * 16 bytes; the swizzle spreads 8 / LC-row groups.
+template <int LC>
+FK_DEV int prow(int i) {
+  return i ^ ((i >> 3) & (8 / LC - 1));
+}
+template <int LC>
+FK_DEV int didx(int i, int r) {  // as double
+  return prow<LC>(i) * (2 * LC) + r;
+}
+template <int LC>
+FK_DEV int cidx(int i, int c) {  // as double2
+  return prow<LC>(i) * LC + c;
+}
 // layout of a lane inside a tile: natural (sn < 0: element i at row i) or
 // split(sn) (even i at row i/2, odd i at row sn - i/2), the output layout of the DCT
 FK_DEV int rowof(int sn, int i) { return sn < 0 ? i : ((i & 1) ? sn - (i >> 1) : (i >> 1)); }
@@ -134,11 +145,11 @@ FK_DEV void apply_twiddles(cplx* v, cplx w1) {
 // One in-place Stockham pass of radix R over both complex lanes of the tile.
 // L = 1 << LOG2L rows; tw[k] = exp(-2 pi i k / L).
 // MUL: the loaded values are first multiplied by mulv[row] (Bluestein filter).
-template <int LOG2L, int NTHR, int R, int NS, bool CONJ_IN, bool CONJ_OUT, bool MUL>
+template <int LC, int LOG2L, int NTHR, int R, int NS, bool CONJ_IN, bool CONJ_OUT, bool MUL>
 FK_DEV void fft_pass(cplx* tc, const cplx* __restrict__ tw, const cplx* __restrict__ mulv) {
   constexpr int L = 1 << LOG2L;
   constexpr int NB = L / R;
-  constexpr int TOT = NB * 2;
+  constexpr int TOT = NB * LC;
   constexpr int KB = (TOT + NTHR - 1) / NTHR;
   const int tid = threadIdx.x;
   cplx v[KB][R];
@@ -146,10 +157,10 @@ FK_DEV void fft_pass(cplx* tc, const cplx* __restrict__ tw, const cplx* __restri
   for (int kb = 0; kb < KB; ++kb) {
     const int b = tid + kb * NTHR;
     if (TOT % NTHR == 0 || b < TOT) {
-      const int q = b >> 1, c = b & 1;
+      const int q = b / LC, c = b % LC;
 #pragma unroll
       for (int r = 0; r < R; ++r) {
-        cplx x = tc[cidx(q + r * NB, c)];
+        cplx x = tc[cidx<LC>(q + r * NB, c)];
         if (MUL) x = cmul(x, __ldg(&mulv[q + r * NB]));
         if (CONJ_IN) x.y = -x.y;
         v[kb][r] = x;
@@ -166,14 +177,14 @@ FK_DEV void fft_pass(cplx* tc, const cplx* __restrict__ tw, const cplx* __restri
   for (int kb = 0; kb < KB; ++kb) {
     const int b = tid + kb * NTHR;
     if (TOT % NTHR == 0 || b < TOT) {
-      const int q = b >> 1, c = b & 1;
+      const int q = b / LC, c = b % LC;
       const int k = q & (NS - 1);
       const int o = (q - k) * R + k;
 #pragma unroll
       for (int r = 0; r < R; ++r) {
         cplx x = v[kb][r];
         if (CONJ_OUT) x.y = -x.y;
-        tc[cidx(o + r * NS, c)] = x;
+        tc[cidx<LC>(o + r * NS, c)] = x;
       }
     }
   }
@@ -183,19 +194,19 @@ FK_DEV void fft_pass(cplx* tc, const cplx* __restrict__ tw, const cplx* __restri
 // Complex FFT of length L = 1 << LOG2L on rows [0, L) of the tile (both complex
 // lanes), natural order in and out, radix-8 passes plus one radix-2/4 pass.
 // INV: unnormalised inverse (conjugate in / out).  MUL: input multiplied by mulv[row].
-template <int LOG2L, int NTHR, int LOG2NS, bool INV, bool MUL>
+template <int LC, int LOG2L, int NTHR, int LOG2NS, bool INV, bool MUL>
 FK_DEV void fft_rec(cplx* tc, const cplx* __restrict__ tw, const cplx* __restrict__ mulv) {
   constexpr int REM = LOG2L - LOG2NS;  // log2 of what is left
   if constexpr (REM > 0) {
     constexpr int LR = REM >= 3 ? 3 : REM;
     constexpr bool first = (LOG2NS == 0), last = (REM == LR);
-    fft_pass<LOG2L, NTHR, (1 << LR), (1 << LOG2NS), INV && first, INV && last, MUL && first>(tc, tw, mulv);
-    fft_rec<LOG2L, NTHR, LOG2NS + LR, INV, MUL>(tc, tw, mulv);
+    fft_pass<LC, LOG2L, NTHR, (1 << LR), (1 << LOG2NS), INV && first, INV && last, MUL && first>(tc, tw, mulv);
+    fft_rec<LC, LOG2L, NTHR, LOG2NS + LR, INV, MUL>(tc, tw, mulv);
   }
 }
-template <int LOG2L, int NTHR, bool INV, bool MUL>
+template <int LC, int LOG2L, int NTHR, bool INV, bool MUL>
 FK_DEV void fft(cplx* tc, const cplx* __restrict__ tw, const cplx* __restrict__ mulv) {
-  fft_rec<LOG2L, NTHR, 0, INV, MUL>(tc, tw, mulv);
+  fft_rec<LC, LOG2L, NTHR, 0, INV, MUL>(tc, tw, mulv);
 }
 
 // ---- in-place decimation-in-frequency / decimation-in-time FFT pair ----------------
@@ -237,41 +248,41 @@ FK_DEV void bfly_zero_half(cplx* v) {  // DFT-R of (v[0..R/2), 0, ..., 0)
 }
 
 // DIF stage of span S = 1 << LOG2S, radix R.  ZERO_HALF: rows >= L/2 hold zeros (not read).
-template <int LOG2L, int NTHR, int LOG2S, int R, bool ZERO_HALF>
+template <int LC, int LOG2L, int NTHR, int LOG2S, int R, bool ZERO_HALF>
 FK_DEV void dif_stage(cplx* tc, const cplx* __restrict__ tw) {
   constexpr int L = 1 << LOG2L, S = 1 << LOG2S, SR = S / R;
-  constexpr int TOT = (L / R) * 2;
+  constexpr int TOT = (L / R) * LC;
 #pragma unroll 2
   for (int b = threadIdx.x; b < TOT; b += NTHR) {
-    const int u = b >> 1, c = b & 1;
+    const int u = b / LC, c = b % LC;
     const int q = u & (SR - 1), base = (u - q) * R + q;
     cplx v[R];
 #pragma unroll
-    for (int r = 0; r < R; ++r) v[r] = (ZERO_HALF && r >= R / 2) ? mk(0.0, 0.0) : tc[cidx(base + r * SR, c)];
+    for (int r = 0; r < R; ++r) v[r] = (ZERO_HALF && r >= R / 2) ? mk(0.0, 0.0) : tc[cidx<LC>(base + r * SR, c)];
     if (ZERO_HALF)
       bfly_zero_half<R>(v);
     else
       Bfly<R>::run(v);
     if (SR > 1) apply_twiddles<R>(v, __ldg(&tw[q * (L / S)]));
 #pragma unroll
-    for (int r = 0; r < R; ++r) tc[cidx(base + r * SR, c)] = v[r];
+    for (int r = 0; r < R; ++r) tc[cidx<LC>(base + r * SR, c)] = v[r];
   }
   __syncthreads();
 }
 // inverse DIT stage (unnormalised): FIRST multiplies the loaded values by mulv[row]
 // and conjugates them, LAST conjugates the results; HALF_OUT: only rows < L/2 are stored.
-template <int LOG2L, int NTHR, int LOG2S, int R, bool FIRST, bool LAST, bool HALF_OUT>
+template <int LC, int LOG2L, int NTHR, int LOG2S, int R, bool FIRST, bool LAST, bool HALF_OUT>
 FK_DEV void dit_stage(cplx* tc, const cplx* __restrict__ tw, const cplx* __restrict__ mulv) {
   constexpr int L = 1 << LOG2L, S = 1 << LOG2S, SR = S / R;
-  constexpr int TOT = (L / R) * 2;
+  constexpr int TOT = (L / R) * LC;
 #pragma unroll 2
   for (int b = threadIdx.x; b < TOT; b += NTHR) {
-    const int u = b >> 1, c = b & 1;
+    const int u = b / LC, c = b % LC;
     const int q = u & (SR - 1), base = (u - q) * R + q;
     cplx v[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      cplx x = tc[cidx(base + r * SR, c)];
+      cplx x = tc[cidx<LC>(base + r * SR, c)];
       if (FIRST) {
         x = cmul(x, __ldg(&mulv[base + r * SR]));
         x.y = -x.y;
@@ -284,39 +295,39 @@ FK_DEV void dit_stage(cplx* tc, const cplx* __restrict__ tw, const cplx* __restr
     for (int r = 0; r < (HALF_OUT ? R / 2 : R); ++r) {
       cplx x = v[r];
       if (LAST) x.y = -x.y;
-      tc[cidx(base + r * SR, c)] = x;
+      tc[cidx<LC>(base + r * SR, c)] = x;
     }
   }
   __syncthreads();
 }
-template <int LOG2L, int NTHR, int LOG2S, bool ZERO_HALF>
+template <int LC, int LOG2L, int NTHR, int LOG2S, bool ZERO_HALF>
 FK_DEV void fft_dif_rec(cplx* tc, const cplx* __restrict__ tw) {
   if constexpr (LOG2S > 0) {
     constexpr int LR = (LOG2S % 3) ? (LOG2S % 3) : 3;
-    dif_stage<LOG2L, NTHR, LOG2S, (1 << LR), ZERO_HALF && LOG2S == LOG2L>(tc, tw);
-    fft_dif_rec<LOG2L, NTHR, LOG2S - LR, ZERO_HALF>(tc, tw);
+    dif_stage<LC, LOG2L, NTHR, LOG2S, (1 << LR), ZERO_HALF && LOG2S == LOG2L>(tc, tw);
+    fft_dif_rec<LC, LOG2L, NTHR, LOG2S - LR, ZERO_HALF>(tc, tw);
   }
 }
-template <int LOG2L, int NTHR, int LOG2S, bool HALF_OUT>
+template <int LC, int LOG2L, int NTHR, int LOG2S, bool HALF_OUT>
 FK_DEV void fft_dit_rec(cplx* tc, const cplx* __restrict__ tw, const cplx* __restrict__ mulv) {
   constexpr int LR = (LOG2S == LOG2L && (LOG2L % 3)) ? (LOG2L % 3) : 3;
   constexpr bool last = (LOG2S == LOG2L);
-  dit_stage<LOG2L, NTHR, LOG2S, (1 << LR), LOG2S == 3, last, HALF_OUT && last>(tc, tw, mulv);
+  dit_stage<LC, LOG2L, NTHR, LOG2S, (1 << LR), LOG2S == 3, last, HALF_OUT && last>(tc, tw, mulv);
   if constexpr (!last) {
     constexpr int NEXT = (LOG2S + 3 > LOG2L) ? LOG2L : LOG2S + 3;
-    fft_dit_rec<LOG2L, NTHR, NEXT, HALF_OUT>(tc, tw, mulv);
+    fft_dit_rec<LC, LOG2L, NTHR, NEXT, HALF_OUT>(tc, tw, mulv);
   }
 }
 // forward: natural order in, digit-reversed out (rows >= L/2 of the input are zero when ZERO_HALF)
-template <int LOG2L, int NTHR, bool ZERO_HALF>
+template <int LC, int LOG2L, int NTHR, bool ZERO_HALF>
 FK_DEV void fft_dif(cplx* tc, const cplx* __restrict__ tw) {
-  fft_dif_rec<LOG2L, NTHR, LOG2L, ZERO_HALF>(tc, tw);
+  fft_dif_rec<LC, LOG2L, NTHR, LOG2L, ZERO_HALF>(tc, tw);
 }
 // inverse of fft_dif (unnormalised) with the input first multiplied by mulv (digit-reversed order)
-template <int LOG2L, int NTHR, bool HALF_OUT>
+template <int LC, int LOG2L, int NTHR, bool HALF_OUT>
 FK_DEV void fft_dit_inv(cplx* tc, const cplx* __restrict__ tw, const cplx* __restrict__ mulv) {
   static_assert(LOG2L >= 3, "FFT length must be at least 8");
-  fft_dit_rec<LOG2L, NTHR, 3, HALF_OUT>(tc, tw, mulv);
+  fft_dit_rec<LC, LOG2L, NTHR, 3, HALF_OUT>(tc, tw, mulv);
 }
 
 // pre-combine of one pair (j, N-j): Chebyshev scaling of the backward transform
@@ -339,16 +350,16 @@ FK_DEV void precombine_pair(cplx a, cplx c, int j, int N, cplx sc, cplx& za, cpl
   f1.y = fma(w, dif.y, f1.y);
 }
 
-// per-complex-lane block reduction of f1 (threads with equal tid&1 share a lane)
-template <int NTHR>
+// per-complex-lane block reduction of f1 (threads with equal tid % LC share a lane)
+template <int LC, int NTHR>
 FK_DEV void reduce_f1(cplx f1, cplx* f1red) {
 #pragma unroll
-  for (int o = 2; o < 32; o <<= 1) {
+  for (int o = LC; o < 32; o <<= 1) {
     f1.x += __shfl_xor_sync(0xffffffffu, f1.x, o);
     f1.y += __shfl_xor_sync(0xffffffffu, f1.y, o);
   }
   const int tid = threadIdx.x;
-  if ((tid & 31) < 2) f1red[(tid >> 5) * 2 + (tid & 1)] = f1;
+  if ((tid & 31) < LC) f1red[(tid >> 5) * LC + (tid % LC)] = f1;
 }
 
 // recombine of one pair: X_{2k} = Z_k + Z_{N-k}, D_k = i (Z_k - Z_{N-k}); forward
@@ -363,10 +374,11 @@ FK_DEV void recombine_pair(cplx zk, cplx zm, int k, int N, cplx& xe, cplx& dk) {
 
 // Odd outputs of the DCT: prefix sum along rows N, N-1, ..., N-Ko of the tile
 // (4 real lanes); forward transform: times -1/N, last one halved when N is odd.
-template <int NTHR, int CLR, bool BWD>
+template <int LC, int NTHR, int CLR, bool BWD>
 FK_DEV void dct_odd_scan(double* td, int N, double* red) {
-  constexpr int NSC = scan_threads(NTHR), NG = NSC / 4;
-  const int tid = threadIdx.x, lane = tid & 3, g = tid >> 2;
+  constexpr int LR = 2 * LC;
+  constexpr int NSC = scan_threads(NTHR), NG = NSC / LR;
+  const int tid = threadIdx.x, lane = tid % LR, g = tid / LR;
   const bool act = tid < NSC;
   const int M = act ? (N - 1) / 2 + 1 : 0;  // Ko + 1
   const int cl = (M + NG - 1) / NG;
@@ -377,25 +389,25 @@ FK_DEV void dct_odd_scan(double* td, int N, double* red) {
   for (int u = 0; u < CLR; ++u) {
     const int t = t0 + u;
     if (t < t1) {
-      q[u] = td[didx(N - t, lane)];
+      q[u] = td[didx<LC>(N - t, lane)];
       s += q[u];
     }
   }
   // two-level carry: sums of groups of 8 chunks, then the chunks inside the group
-  double* red2 = red + NG * 4;
-  if (act) red[g * 4 + lane] = s;
+  double* red2 = red + NG * LR;
+  if (act) red[g * LR + lane] = s;
   __syncthreads();
   if (act && (g & 7) == 0) {
     double t = 0.0;
 #pragma unroll
     for (int k = 0; k < 8; ++k)
-      if (g + k < NG) t += red[(g + k) * 4 + lane];
-    red2[(g >> 3) * 4 + lane] = t;
+      if (g + k < NG) t += red[(g + k) * LR + lane];
+    red2[(g >> 3) * LR + lane] = t;
   }
   __syncthreads();
   double y = 0.0;
-  for (int gg = 0; act && gg < (g >> 3); ++gg) y += red2[gg * 4 + lane];
-  for (int gg = (g & ~7); act && gg < g; ++gg) y += red[gg * 4 + lane];
+  for (int gg = 0; act && gg < (g >> 3); ++gg) y += red2[gg * LR + lane];
+  for (int gg = (g & ~7); act && gg < g; ++gg) y += red[gg * LR + lane];
   const double ho = BWD ? 1.0 : -1.0 / (double)N;
 #pragma unroll
   for (int u = 0; u < CLR; ++u) {
@@ -404,7 +416,7 @@ FK_DEV void dct_odd_scan(double* td, int N, double* red) {
       y += q[u];
       double o = y * ho;
       if (!BWD && 2 * t + 1 == N) o *= 0.5;
-      td[didx(N - t, lane)] = o;
+      td[didx<LC>(N - t, lane)] = o;
     }
   }
   __syncthreads();
@@ -412,47 +424,47 @@ FK_DEV void dct_odd_scan(double* td, int N, double* red) {
 
 // DCT-I with the Chebyshev scaling, power-of-two N = 1 << LOG2L, in place on a
 // tile of n = N + 1 rows in natural layout.  Result in split(N) layout.
-template <int LOG2L, int NTHR, bool BWD>
+template <int LC, int LOG2L, int NTHR, bool BWD>
 FK_DEV void dct_pow2(double* td, const DctTab& T, double* red) {
   constexpr int N = 1 << LOG2L;
   constexpr int NP = N / 2 + 1;
   cplx* tc = (cplx*)td;
   cplx* f1red = (cplx*)red;
-  const int tid = threadIdx.x, c = tid & 1;
+  const int tid = threadIdx.x, c = tid % LC;
   cplx f1 = mk(0.0, 0.0);
-  for (int it = tid; it < NP * 2; it += NTHR) {
-    const int j = it >> 1, jm = N - j;
-    const cplx a = tc[cidx(j, c)], cc = tc[cidx(jm, c)];
+  for (int it = tid; it < NP * LC; it += NTHR) {
+    const int j = it / LC, jm = N - j;
+    const cplx a = tc[cidx<LC>(j, c)], cc = tc[cidx<LC>(jm, c)];
     cplx za, zb;
     precombine_pair<BWD>(a, cc, j, N, __ldg(&T.sc[j]), za, zb, f1);
-    tc[cidx(j, c)] = za;
-    if (jm != j && j != 0) tc[cidx(jm, c)] = zb;
+    tc[cidx<LC>(j, c)] = za;
+    if (jm != j && j != 0) tc[cidx<LC>(jm, c)] = zb;
   }
-  reduce_f1<NTHR>(f1, f1red);
+  reduce_f1<LC, NTHR>(f1, f1red);
   __syncthreads();
-  fft<LOG2L, NTHR, false, false>(tc, T.tw, nullptr);
+  fft<LC, LOG2L, NTHR, false, false>(tc, T.tw, nullptr);
   constexpr int Ko = (N - 1) / 2;
-  for (int it = tid; it < NP * 2; it += NTHR) {
-    const int k = it >> 1;
-    const cplx zk = tc[cidx(k, c)], zm = tc[cidx(k == 0 ? 0 : N - k, c)];
+  for (int it = tid; it < NP * LC; it += NTHR) {
+    const int k = it / LC;
+    const cplx zk = tc[cidx<LC>(k, c)], zm = tc[cidx<LC>(k == 0 ? 0 : N - k, c)];
     cplx xe, dk;
     recombine_pair<BWD>(zk, zm, k, N, xe, dk);
-    tc[cidx(k, c)] = xe;
-    if (k >= 1 && k <= Ko) tc[cidx(N - k, c)] = dk;
+    tc[cidx<LC>(k, c)] = xe;
+    if (k >= 1 && k <= Ko) tc[cidx<LC>(N - k, c)] = dk;
     if (k == 0) {
       cplx s = mk(0.0, 0.0);
-      for (int w = 0; w < NTHR / 32; ++w) s = cadd(s, f1red[w * 2 + c]);
-      tc[cidx(N, c)] = cscale(s, 2.0);
+      for (int w = 0; w < NTHR / 32; ++w) s = cadd(s, f1red[w * LC + c]);
+      tc[cidx<LC>(N, c)] = cscale(s, 2.0);
     }
   }
   __syncthreads();
-  dct_odd_scan<NTHR, (N / 2 + scan_threads(NTHR) / 4 - 1) / (scan_threads(NTHR) / 4), BWD>(td, N, red);
+  dct_odd_scan<LC, NTHR, (N / 2 + scan_threads(NTHR) / (2 * LC) - 1) / (scan_threads(NTHR) / (2 * LC)), BWD>(td, N, red);
 }
 
 // DCT-I of arbitrary N = n - 1 through Bluestein (FFT length Lb = 1 << LOG2LB >=
 // 2N - 1): reads tile A (natural layout, n rows), result in tile W (Lb rows),
 // split(N) layout.  A is left untouched.
-template <int LOG2LB, int NTHR, bool BWD>
+template <int LC, int LOG2LB, int NTHR, bool BWD>
 FK_DEV void dct_bluestein(const double* ta, double* tw_, const DctTab& T, double* red) {
   constexpr int LB = 1 << LOG2LB;
   const int N = T.n - 1;
@@ -460,37 +472,37 @@ FK_DEV void dct_bluestein(const double* ta, double* tw_, const DctTab& T, double
   const cplx* A = (const cplx*)ta;
   cplx* W = (cplx*)tw_;
   cplx* f1red = (cplx*)red;
-  const int tid = threadIdx.x, c = tid & 1;
+  const int tid = threadIdx.x, c = tid % LC;
   cplx f1 = mk(0.0, 0.0);
-  for (int it = tid; it < NP * 2; it += NTHR) {
-    const int j = it >> 1, jm = N - j;
+  for (int it = tid; it < NP * LC; it += NTHR) {
+    const int j = it / LC, jm = N - j;
     cplx za, zb;
-    precombine_pair<BWD>(A[cidx(j, c)], A[cidx(jm, c)], j, N, __ldg(&T.sc[j]), za, zb, f1);
-    W[cidx(j, c)] = cmul(za, __ldg(&T.chirp[j]));
-    if (jm != j && j != 0) W[cidx(jm, c)] = cmul(zb, __ldg(&T.chirp[jm]));
+    precombine_pair<BWD>(A[cidx<LC>(j, c)], A[cidx<LC>(jm, c)], j, N, __ldg(&T.sc[j]), za, zb, f1);
+    W[cidx<LC>(j, c)] = cmul(za, __ldg(&T.chirp[j]));
+    if (jm != j && j != 0) W[cidx<LC>(jm, c)] = cmul(zb, __ldg(&T.chirp[jm]));
   }
-  for (int it = 2 * N + tid; it < LB; it += NTHR) W[cidx(it >> 1, c)] = mk(0.0, 0.0);  // rows [N, LB/2)
-  reduce_f1<NTHR>(f1, f1red);
+  for (int it = LC * N + tid; it < (LB / 2) * LC; it += NTHR) W[cidx<LC>(it / LC, c)] = mk(0.0, 0.0);  // rows [N, LB/2)
+  reduce_f1<LC, NTHR>(f1, f1red);
   __syncthreads();
-  fft_dif<LOG2LB, NTHR, true>(W, T.tw);
-  fft_dit_inv<LOG2LB, NTHR, true>(W, T.tw, T.bhat);
+  fft_dif<LC, LOG2LB, NTHR, true>(W, T.tw);
+  fft_dit_inv<LC, LOG2LB, NTHR, true>(W, T.tw, T.bhat);
   const int Ko = (N - 1) / 2;
-  for (int it = tid; it < NP * 2; it += NTHR) {
-    const int k = it >> 1;
-    const cplx zk = cmul(W[cidx(k, c)], __ldg(&T.chirp[k]));
-    const cplx zm = (k == 0) ? zk : cmul(W[cidx(N - k, c)], __ldg(&T.chirp[N - k]));
+  for (int it = tid; it < NP * LC; it += NTHR) {
+    const int k = it / LC;
+    const cplx zk = cmul(W[cidx<LC>(k, c)], __ldg(&T.chirp[k]));
+    const cplx zm = (k == 0) ? zk : cmul(W[cidx<LC>(N - k, c)], __ldg(&T.chirp[N - k]));
     cplx xe, dk;
     recombine_pair<BWD>(zk, zm, k, N, xe, dk);
-    W[cidx(k, c)] = xe;
-    if (k >= 1 && k <= Ko) W[cidx(N - k, c)] = dk;
+    W[cidx<LC>(k, c)] = xe;
+    if (k >= 1 && k <= Ko) W[cidx<LC>(N - k, c)] = dk;
     if (k == 0) {
       cplx s = mk(0.0, 0.0);
-      for (int w = 0; w < NTHR / 32; ++w) s = cadd(s, f1red[w * 2 + c]);
-      W[cidx(N, c)] = cscale(s, 2.0);
+      for (int w = 0; w < NTHR / 32; ++w) s = cadd(s, f1red[w * LC + c]);
+      W[cidx<LC>(N, c)] = cscale(s, 2.0);
     }
   }
   __syncthreads();
-  dct_odd_scan<NTHR, (LB / 4 + scan_threads(NTHR) / 4 - 1) / (scan_threads(NTHR) / 4), BWD>(tw_, N, red);
+  dct_odd_scan<LC, NTHR, (LB / 4 + scan_threads(NTHR) / (2 * LC) - 1) / (scan_threads(NTHR) / (2 * LC)), BWD>(tw_, N, red);
 }
 
 // ---- chunked scans over the 8 parity chains of a tile ---------------------------
@@ -499,11 +511,12 @@ FK_DEV void dct_bluestein(const double* ta, double* tw_, const DctTab& T, double
 //   y_t = in(i, lane) + c1(i, lane) * y_{t-1}
 // `out(i, lane, y)` is called after every input of the block has been read, so
 // it may overwrite the tile the inputs came from (any row).
-template <int NTHR, int CL, bool FWD, class In, class C1, class Out>
+template <int LC, int NTHR, int CL, bool FWD, class In, class C1, class Out>
 FK_DEV void scan1(int n, double* red, In in, C1 c1, Out out) {
-  constexpr int NSC = scan_threads(NTHR), NG = NSC / 8;
-  const int tid = threadIdx.x, ch = tid & 7, g = tid >> 3;
-  const int lane = ch & 3, p = ch >> 2;
+  constexpr int LR = 2 * LC, NCH = 2 * LR;  // chains per tile: LR lanes x 2 parities
+  constexpr int NSC = scan_threads(NTHR), NG = NSC / NCH;
+  const int tid = threadIdx.x, ch = tid % NCH, g = tid / NCH;
+  const int lane = ch % LR, p = ch / LR;
   const int M = (tid < NSC) ? ((n - p + 1) >> 1) : 0;  // threads beyond NSC own empty chunks
   const int cl = (((n + 1) >> 1) + NG - 1) / NG;
   const int t0 = g * cl, t1 = min(t0 + cl, M);
@@ -521,11 +534,11 @@ FK_DEV void scan1(int n, double* red, In in, C1 c1, Out out) {
     }
   }
   // two-level carry: maps of groups of 8 chunks, then the chunks inside the group
-  double* red2 = red + NG * 16;
+  double* red2 = red + NG * NCH * 2;
   const bool act = tid < NSC;
   if (act) {
-    red[(g * 8 + ch) * 2] = A;
-    red[(g * 8 + ch) * 2 + 1] = b;
+    red[(g * NCH + ch) * 2] = A;
+    red[(g * NCH + ch) * 2 + 1] = b;
   }
   __syncthreads();
   if (act && (g & 7) == 0) {
@@ -533,18 +546,18 @@ FK_DEV void scan1(int n, double* red, In in, C1 c1, Out out) {
 #pragma unroll
     for (int k = 0; k < 8; ++k)
       if (g + k < NG) {
-        const double Ak = red[((g + k) * 8 + ch) * 2], bk = red[((g + k) * 8 + ch) * 2 + 1];
+        const double Ak = red[((g + k) * NCH + ch) * 2], bk = red[((g + k) * NCH + ch) * 2 + 1];
         bg = fma(Ak, bg, bk);
         Ag *= Ak;
       }
-    red2[((g >> 3) * 8 + ch) * 2] = Ag;
-    red2[((g >> 3) * 8 + ch) * 2 + 1] = bg;
+    red2[((g >> 3) * NCH + ch) * 2] = Ag;
+    red2[((g >> 3) * NCH + ch) * 2 + 1] = bg;
   }
   __syncthreads();
   double y = 0.0;
   if (act) {
-    for (int gg = 0; gg < (g >> 3); ++gg) y = fma(red2[(gg * 8 + ch) * 2], y, red2[(gg * 8 + ch) * 2 + 1]);
-    for (int gg = (g & ~7); gg < g; ++gg) y = fma(red[(gg * 8 + ch) * 2], y, red[(gg * 8 + ch) * 2 + 1]);
+    for (int gg = 0; gg < (g >> 3); ++gg) y = fma(red2[(gg * NCH + ch) * 2], y, red2[(gg * NCH + ch) * 2 + 1]);
+    for (int gg = (g & ~7); gg < g; ++gg) y = fma(red[(gg * NCH + ch) * 2], y, red[(gg * NCH + ch) * 2 + 1]);
   }
 #pragma unroll
   for (int u = 0; u < CL; ++u) {
@@ -559,11 +572,12 @@ FK_DEV void scan1(int n, double* red, In in, C1 c1, Out out) {
 }
 
 //   y_t = in(i, lane) + c1(i, lane) * y_{t-1} + c2(i, lane) * y_{t-2}
-template <int NTHR, int CL, bool FWD, class In, class C1, class C2, class Out>
+template <int LC, int NTHR, int CL, bool FWD, class In, class C1, class C2, class Out>
 FK_DEV void scan2(int n, double* red, In in, C1 c1, C2 c2, Out out) {
-  constexpr int NSC = scan_threads(NTHR), NG = NSC / 8;
-  const int tid = threadIdx.x, ch = tid & 7, g = tid >> 3;
-  const int lane = ch & 3, p = ch >> 2;
+  constexpr int LR = 2 * LC, NCH = 2 * LR;  // chains per tile: LR lanes x 2 parities
+  constexpr int NSC = scan_threads(NTHR), NG = NSC / NCH;
+  const int tid = threadIdx.x, ch = tid % NCH, g = tid / NCH;
+  const int lane = ch % LR, p = ch / LR;
   const int M = (tid < NSC) ? ((n - p + 1) >> 1) : 0;
   const int cl = (((n + 1) >> 1) + NG - 1) / NG;
   const int t0 = g * cl, t1 = min(t0 + cl, M);
@@ -587,37 +601,37 @@ FK_DEV void scan2(int n, double* red, In in, C1 c1, C2 c2, Out out) {
   }
   const bool act = tid < NSC;
   if (act) {
-    double* r = red + (g * 8 + ch) * 6;
+    double* r = red + (g * NCH + ch) * 6;
     r[0] = a1, r[1] = b1, r[2] = p1, r[3] = a2, r[4] = b2, r[5] = p2;
   }
   __syncthreads();
   // two-level carry: maps of groups of 8 chunks, then the chunks inside the group
-  double* red2 = red + NG * 48;
+  double* red2 = red + NG * NCH * 6;
   if (act && (g & 7) == 0) {
     // group map  [y1; y2] -> G [y1; y2] + h,  G = [g11 g12; g21 g22]
     double g11 = 1.0, g12 = 0.0, g21 = 0.0, g22 = 1.0, h1 = 0.0, h2 = 0.0;
 #pragma unroll
     for (int k = 0; k < 8; ++k)
       if (g + k < NG) {
-        const double* rr = red + ((g + k) * 8 + ch) * 6;
+        const double* rr = red + ((g + k) * NCH + ch) * 6;
         const double n11 = fma(rr[0], g11, rr[1] * g21), n12 = fma(rr[0], g12, rr[1] * g22);
         const double n21 = fma(rr[3], g11, rr[4] * g21), n22 = fma(rr[3], g12, rr[4] * g22);
         const double m1 = fma(rr[0], h1, fma(rr[1], h2, rr[2])), m2 = fma(rr[3], h1, fma(rr[4], h2, rr[5]));
         g11 = n11, g12 = n12, g21 = n21, g22 = n22, h1 = m1, h2 = m2;
       }
-    double* w = red2 + ((g >> 3) * 8 + ch) * 6;
+    double* w = red2 + ((g >> 3) * NCH + ch) * 6;
     w[0] = g11, w[1] = g12, w[2] = h1, w[3] = g21, w[4] = g22, w[5] = h2;
   }
   __syncthreads();
   double y1 = 0.0, y2 = 0.0;
   for (int gg = 0; act && gg < (g >> 3); ++gg) {
-    const double* rr = red2 + (gg * 8 + ch) * 6;
+    const double* rr = red2 + (gg * NCH + ch) * 6;
     const double n1 = fma(rr[0], y1, fma(rr[1], y2, rr[2]));
     const double n2 = fma(rr[3], y1, fma(rr[4], y2, rr[5]));
     y1 = n1, y2 = n2;
   }
   for (int gg = (g & ~7); act && gg < g; ++gg) {
-    const double* rr = red + (gg * 8 + ch) * 6;
+    const double* rr = red + (gg * NCH + ch) * 6;
     const double n1 = fma(rr[0], y1, fma(rr[1], y2, rr[2]));
     const double n2 = fma(rr[3], y1, fma(rr[4], y2, rr[5]));
     y1 = n1, y2 = n2;
@@ -636,57 +650,59 @@ FK_DEV void scan2(int n, double* red, In in, C1 c1, C2 c2, Out out) {
 }
 
 // chunk length bound for a lane of n elements handled by NTHR threads
-RP_HD constexpr int chunk_len(int n, int nthr) { return (((n + 1) / 2) + scan_threads(nthr) / 8 - 1) / (scan_threads(nthr) / 8); }
+RP_HD constexpr int chunk_len(int n, int nthr, int lc = 2) {
+  return (((n + 1) / 2) + scan_threads(nthr) / (4 * lc) - 1) / (scan_threads(nthr) / (4 * lc));
+}
 
 // Chebyshev derivative (ortho.rs:107-125) of the lane held in tile `src`
 // (layout sn_s, n elements), times `sc`, written to tile `dst` (layout sn_d;
 // may alias src):  b_k = sum_{p > k, p - k odd} 2 p a_p  (k >= 1), b_0 = half of that.
-template <int NTHR, int CL>
+template <int LC, int NTHR, int CL>
 FK_DEV void cheb_diff(const double* src, int sn_s, double* dst, int sn_d, int n, double sc, double* red) {
-  scan1<NTHR, CL, false>(
-      n, red, [&](int i, int l) { return (2.0 * (double)i * sc) * src[didx(rowof(sn_s, i), l)]; },
+  scan1<LC, NTHR, CL, false>(
+      n, red, [&](int i, int l) { return (2.0 * (double)i * sc) * src[didx<LC>(rowof(sn_s, i), l)]; },
       [](int, int) { return 1.0; },
       [&](int i, int l, double y) {
-        if (i >= 1) dst[didx(rowof(sn_d, i - 1), l)] = (i == 1) ? 0.5 * y : y;
-        if (i == n - 1) dst[didx(rowof(sn_d, n - 1), l)] = 0.0;
+        if (i >= 1) dst[didx<LC>(rowof(sn_d, i - 1), l)] = (i == 1) ? 0.5 * y : y;
+        if (i == n - 1) dst[didx<LC>(rowof(sn_d, n - 1), l)] = 0.0;
       });
 }
 
 // HholtzAdi half step along the tile axis (hholtz_adi.rs:108-129): B2 matvec
 // (n -> m = n-2) fused into the forward sweep, then the backward sweep
 // (fdma.rs:101-118).  In place on tile t (layout sn); result elements 0..m-1.
-template <int NTHR, int CL>
+template <int LC, int NTHR, int CL>
 FK_DEV void b2_fdma(double* t, int sn, int n, const B2Tabs& B, const FdmaTabs& F, double* red) {
   const int m = n - 2;
-  scan1<NTHR, CL, true>(
+  scan1<LC, NTHR, CL, true>(
       m, red,
       [&](int i, int l) {
-        return fma(__ldg(&B.lo[i]), t[didx(rowof(sn, i), l)],
-                   fma(__ldg(&B.di[i]), t[didx(rowof(sn, i + 2), l)],
-                       (i + 4 < n) ? __ldg(&B.up[i]) * t[didx(rowof(sn, i + 4), l)] : 0.0));
+        return fma(__ldg(&B.lo[i]), t[didx<LC>(rowof(sn, i), l)],
+                   fma(__ldg(&B.di[i]), t[didx<LC>(rowof(sn, i + 2), l)],
+                       (i + 4 < n) ? __ldg(&B.up[i]) * t[didx<LC>(rowof(sn, i + 4), l)] : 0.0));
       },
-      [&](int i, int) { return __ldg(&F.fp[i]); }, [&](int i, int l, double y) { t[didx(rowof(sn, i), l)] = y; });
-  scan2<NTHR, CL, false>(
-      m, red, [&](int i, int l) { return __ldg(&F.bs[i]) * t[didx(rowof(sn, i), l)]; },
+      [&](int i, int) { return __ldg(&F.fp[i]); }, [&](int i, int l, double y) { t[didx<LC>(rowof(sn, i), l)] = y; });
+  scan2<LC, NTHR, CL, false>(
+      m, red, [&](int i, int l) { return __ldg(&F.bs[i]) * t[didx<LC>(rowof(sn, i), l)]; },
       [&](int i, int) { return __ldg(&F.bp1[i]); }, [&](int i, int) { return __ldg(&F.bp2[i]); },
-      [&](int i, int l, double y) { t[didx(rowof(sn, i), l)] = y; });
+      [&](int i, int l, double y) { t[didx<LC>(rowof(sn, i), l)] = y; });
 }
 
 // from_ortho (composite_stencil.rs:250-276): c = S^T p, then the (S^T S) solve.
 // In place on tile t (layout sn): n ortho coefficients -> m = n-2 composite ones.
-template <int NTHR, int CL>
+template <int LC, int NTHR, int CL>
 FK_DEV void from_ortho(double* t, int sn, int n, const TdmaTabs& T, double* red) {
   const int m = n - 2;
-  scan1<NTHR, CL, true>(
+  scan1<LC, NTHR, CL, true>(
       m, red,
       [&](int i, int l) {
-        const double c = fma(__ldg(&T.sd[i]), t[didx(rowof(sn, i), l)], __ldg(&T.sl[i]) * t[didx(rowof(sn, i + 2), l)]);
+        const double c = fma(__ldg(&T.sd[i]), t[didx<LC>(rowof(sn, i), l)], __ldg(&T.sl[i]) * t[didx<LC>(rowof(sn, i + 2), l)]);
         return __ldg(&T.fs[i]) * c;
       },
-      [&](int i, int) { return __ldg(&T.fp[i]); }, [&](int i, int l, double y) { t[didx(rowof(sn, i), l)] = y; });
-  scan1<NTHR, CL, false>(
-      m, red, [&](int i, int l) { return t[didx(rowof(sn, i), l)]; }, [&](int i, int) { return __ldg(&T.bp[i]); },
-      [&](int i, int l, double y) { t[didx(rowof(sn, i), l)] = y; });
+      [&](int i, int) { return __ldg(&T.fp[i]); }, [&](int i, int l, double y) { t[didx<LC>(rowof(sn, i), l)] = y; });
+  scan1<LC, NTHR, CL, false>(
+      m, red, [&](int i, int l) { return t[didx<LC>(rowof(sn, i), l)]; }, [&](int i, int) { return __ldg(&T.bp[i]); },
+      [&](int i, int l, double y) { t[didx<LC>(rowof(sn, i), l)] = y; });
 }
 
 }  // namespace fk

@@ -17,28 +17,29 @@ namespace rp {
 namespace fk {
 
 // ---- x kernels ---------------------------------------------------------------------------------
-template <int LOG2N>
+template <int LOG2N, int LC_>
 struct PXCfg {
+  static constexpr int LC = LC_;
   static constexpr int N = 1 << LOG2N;
-  static constexpr int NTHR = (N / 8) < 64 ? 64 : (N / 8);
-  static constexpr int SMEM = N * 32;
+  static constexpr int NTHR = (N * LC / 16) < 64 ? 64 : (N * LC / 16);
+  static constexpr int SMEM = N * LC * 16;
 };
 
-template <int LOG2N>
-__global__ void __launch_bounds__(PXCfg<LOG2N>::NTHR, 2) pk_c2r(PC2rArgs3 a3) {
-  typedef PXCfg<LOG2N> C;
+template <int LOG2N, int LC>
+__global__ void __launch_bounds__(PXCfg<LOG2N, LC>::NTHR, PXCfg<LOG2N, LC>::SMEM > 110 * 1024 ? 1 : 2) pk_c2r(PC2rArgs3 a3) {
+  typedef PXCfg<LOG2N, LC> C;
   const PC2rArgs& a = a3.a[blockIdx.y];
   RP_DYN_SMEM(double, td);
   cplx* tc = (cplx*)td;
   constexpr int n = C::N, mkr = n / 2 + 1;
-  const int c0 = blockIdx.x * 4;
+  const int c0 = blockIdx.x * 2 * LC;
   const int ncols = a.src.cols;
   const cplx* src = (const cplx*)a.src.p;
   const double inv_n = 1.0 / (double)n;
   for (int pass = 0; pass < 2; ++pass) {
     const Mat& o = pass ? a.dx : a.val;
-    for (int it = threadIdx.x; it < mkr * 2; it += C::NTHR) {
-      const int k = it >> 1, c = it & 1;
+    for (int it = threadIdx.x; it < mkr * LC; it += C::NTHR) {
+      const int k = it / LC, c = it % LC;
       const int ca = c0 + 2 * c, cb = ca + 1;
       cplx xa = mk(0.0, 0.0), xb = mk(0.0, 0.0);
       if (ca < ncols) xa = src[(size_t)k * a.src.ld + ca];
@@ -52,15 +53,15 @@ __global__ void __launch_bounds__(PXCfg<LOG2N>::NTHR, 2) pk_c2r(PC2rArgs3 a3) {
         xa.y = 0.0;
         xb.y = 0.0;
       }
-      tc[cidx(k, c)] = mk(xa.x - xb.y, xa.y + xb.x);                                    // X_a + i X_b
-      if (k > 0 && 2 * k != n) tc[cidx(n - k, c)] = mk(xa.x + xb.y, -xa.y + xb.x);     // conj(X_a) + i conj(X_b)
+      tc[cidx<LC>(k, c)] = mk(xa.x - xb.y, xa.y + xb.x);                                    // X_a + i X_b
+      if (k > 0 && 2 * k != n) tc[cidx<LC>(n - k, c)] = mk(xa.x + xb.y, -xa.y + xb.x);     // conj(X_a) + i conj(X_b)
     }
     __syncthreads();
-    fft<LOG2N, C::NTHR, true, false>(tc, a.tw, nullptr);
-    for (int it = threadIdx.x; it < n * 2; it += C::NTHR) {
-      const int i = it >> 1, c = it & 1;
+    fft<LC, LOG2N, C::NTHR, true, false>(tc, a.tw, nullptr);
+    for (int it = threadIdx.x; it < n * LC; it += C::NTHR) {
+      const int i = it / LC, c = it % LC;
       const int ca = c0 + 2 * c;
-      const cplx z = tc[cidx(i, c)];
+      const cplx z = tc[cidx<LC>(i, c)];
       double* row = o.p + (size_t)i * o.ld;
       if (ca < o.cols) row[ca] = z.x * inv_n;
       if (ca + 1 < o.cols) row[ca + 1] = z.y * inv_n;
@@ -69,28 +70,28 @@ __global__ void __launch_bounds__(PXCfg<LOG2N>::NTHR, 2) pk_c2r(PC2rArgs3 a3) {
   }
 }
 
-template <int LOG2N>
-__global__ void __launch_bounds__(PXCfg<LOG2N>::NTHR, 2) pk_r2c(PR2cArgs3 a3) {
-  typedef PXCfg<LOG2N> C;
+template <int LOG2N, int LC>
+__global__ void __launch_bounds__(PXCfg<LOG2N, LC>::NTHR, PXCfg<LOG2N, LC>::SMEM > 110 * 1024 ? 1 : 2) pk_r2c(PR2cArgs3 a3) {
+  typedef PXCfg<LOG2N, LC> C;
   const PR2cArgs& a = a3.a[blockIdx.y];
   RP_DYN_SMEM(double, td);
   cplx* tc = (cplx*)td;
   constexpr int n = C::N, mkr = n / 2 + 1;
-  const int c0 = blockIdx.x * 4;
+  const int c0 = blockIdx.x * 2 * LC;
   const int ncols = a.src.cols;
-  for (int it = threadIdx.x; it < n * 2; it += C::NTHR) {
-    const int i = it >> 1, c = it & 1;
+  for (int it = threadIdx.x; it < n * LC; it += C::NTHR) {
+    const int i = it / LC, c = it % LC;
     const int ca = c0 + 2 * c;
     const double* row = a.src.p + (size_t)i * a.src.ld;
-    tc[cidx(i, c)] = mk(ca < ncols ? row[ca] : 0.0, ca + 1 < ncols ? row[ca + 1] : 0.0);
+    tc[cidx<LC>(i, c)] = mk(ca < ncols ? row[ca] : 0.0, ca + 1 < ncols ? row[ca + 1] : 0.0);
   }
   __syncthreads();
-  fft<LOG2N, C::NTHR, false, false>(tc, a.tw, nullptr);
+  fft<LC, LOG2N, C::NTHR, false, false>(tc, a.tw, nullptr);
   cplx* dst = (cplx*)a.dst.p;
-  for (int it = threadIdx.x; it < mkr * 2; it += C::NTHR) {
-    const int k = it >> 1, c = it & 1;
+  for (int it = threadIdx.x; it < mkr * LC; it += C::NTHR) {
+    const int k = it / LC, c = it % LC;
     const int ca = c0 + 2 * c, cb = ca + 1;
-    const cplx zk = tc[cidx(k, c)], zc = tc[cidx(k == 0 ? 0 : n - k, c)];
+    const cplx zk = tc[cidx<LC>(k, c)], zc = tc[cidx<LC>(k == 0 ? 0 : n - k, c)];
     const cplx zm = mk(zc.x, -zc.y);
     const cplx s = cadd(zk, zm), d = csub(zk, zm);
     const double h = (k < a.cut) ? 0.5 : 0.0;  // dealias: modes kx >= cut are zeroed
@@ -101,7 +102,7 @@ __global__ void __launch_bounds__(PXCfg<LOG2N>::NTHR, 2) pk_r2c(PR2cArgs3 a3) {
 
 // ---- y kernels on complex rows -------------------------------------------------------------------
 // lane l of the tile: row r0 + (l >> 1), part l & 1 (re / im)
-FK_DEV int prow_of(int r0, int l) { return r0 + (l >> 1); }
+FK_DEV int prow_of(int r0, int l) { return r0 + (l >> 1); }  // lanes (2r, 2r+1) = (re, im) of row r0 + r
 // element (row, j).part of a complex array, zero outside [0, rows) x [0, cols)
 FK_DEV double ldc(const Mat& a, int r, int j, int part) {
   const double v = a.p[((size_t)min(r, a.rows - 1) * a.ld + min(max(j, 0), a.cols - 1)) * 2 + part];
@@ -118,31 +119,34 @@ FK_DEV double ldc_stencil(const Mat& a, int r, int j, int part, const double* __
 // (i k s z).part for z = (re, im): re' = -k s im, im' = k s re
 FK_DEV double ik_part(double ks, double re, double im, int part) { return part ? ks * re : -ks * im; }
 
-template <int LOG2L>
-__global__ void __launch_bounds__(YCfg<LOG2L>::NTHR, 1) pk_hholtz(PHholtzArgs3 a3) {
-  typedef YCfg<LOG2L> C;
+template <int LOG2L, int LC>
+__global__ void __launch_bounds__(YCfg<LOG2L, LC>::NTHR, 1) pk_hholtz(PHholtzArgs3 a3) {
+  typedef YCfg<LOG2L, LC> C;
   const PHholtzArgs& a = a3.a[blockIdx.y];
   YK_SMEM(td, red0);
-  double* ti = td + C::ROWS * 4;
-  double* red = ti + C::ROWS * 4;
+  double* ti = td + C::TILE;
+  double* red = ti + LC * C::ROWS;
   (void)red0;
-  const int r0 = blockIdx.x * 2;
+  const int r0 = blockIdx.x * LC;
   constexpr int n = C::n, m = n - 2;
   const int nrows = a.chat.rows;
   if (a.mode == 1) {  // - dt/sy d/dy pres   (navier.rs:646)
-    tile_fill<C::NTHR>(td, n, [&](int j, int l) { return ldc(a.pres, prow_of(r0, l), j, l & 1); });
+    tile_fill<LC, C::NTHR>(td, n, [&](int j, int l) { return ldc(a.pres, prow_of(r0, l), j, l & 1); });
     __syncthreads();
-    cheb_diff<C::NTHR, C::CL>(td, -1, td, -1, n, -a.dt * a.isy, red);
+    cheb_diff<LC, C::NTHR, C::CL>(td, -1, td, -1, n, -a.dt * a.isy, red);
   }
-  tile_fill<C::NTHR>(ti, m, [&](int j, int l) { return a.m.inv[(size_t)min(prow_of(r0, l), nrows - 1) * a.m.inv_ld + j]; });
+  for (int it = threadIdx.x; it < m * LC; it += C::NTHR) {  // pivot reciprocals of the LC complex rows
+    const int l = it / m, j = it - l * m;
+    ti[l * C::ROWS + j] = a.m.inv[(size_t)min(r0 + l, nrows - 1) * a.m.inv_ld + j];
+  }
   {
-    const int tot = n * 4;
+    const int tot = n * C::LR;
     for (int it0 = threadIdx.x; it0 < tot; it0 += C::NTHR * 4) {
       double v[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int it = min(it0 + u * C::NTHR, tot - 1);
-        const int j = it >> 2, l = it & 3, r = prow_of(r0, l), part = l & 1;
+        const int j = it / C::LR, l = it % C::LR, r = prow_of(r0, l), part = l & 1;
         double x = -a.dt * ldc(a.chat, r, j, part);                       // - dt * conv          (630, 651, 671)
         x += ldc_stencil(a.fld, r, j, part, a.sd, a.sl);                  // + to_ortho(field)    (625, 644, 663)
         if (a.mode == 0) {                                                // - dt/sx d/dx pres    (627)
@@ -159,133 +163,138 @@ __global__ void __launch_bounds__(YCfg<LOG2L>::NTHR, 1) pk_hholtz(PHholtzArgs3 a
       for (int u = 0; u < 4; ++u) {
         const int it = it0 + u * C::NTHR;
         if (it < tot) {
-          double* w = &td[didx(it >> 2, it & 3)];
+          double* w = &td[didx<LC>(it / C::LR, it % C::LR)];
           *w = (a.mode == 1) ? *w + v[u] : v[u];
         }
       }
     }
   }
   __syncthreads();
-  const double mu = __ldg(&a.m.lam[min(prow_of(r0, threadIdx.x & 3), nrows - 1)]) + a.m.alpha;
-  mode_solve<C::NTHR, C::CL>(td, ti, n, a.b2, a.m, mu, red);
-  tile_drain<C::NTHR>(td, -1, m, [&](int j, int l, double v) {
+  const double mu = __ldg(&a.m.lam[min(prow_of(r0, threadIdx.x % C::LR), nrows - 1)]) + a.m.alpha;
+  mode_solve<LC, C::NTHR, C::CL, C::ROWS, 1>(td, ti, n, a.b2, a.m, mu, red);
+  tile_drain<LC, C::NTHR>(td, -1, m, [&](int j, int l, double v) {
     const int r = prow_of(r0, l);
     if (r < a.out.rows) a.out.p[((size_t)r * a.out.ld + j) * 2 + (l & 1)] = v;
   });
 }
 
-template <int LOG2L>
-__global__ void __launch_bounds__(YCfg<LOG2L>::NTHR, 1) pk_divpois(PDivPoisArgs a) {
-  typedef YCfg<LOG2L> C;
+template <int LOG2L, int LC>
+__global__ void __launch_bounds__(YCfg<LOG2L, LC>::NTHR, 1) pk_divpois(PDivPoisArgs a) {
+  typedef YCfg<LOG2L, LC> C;
   YK_SMEM(td, red0);
-  double* ti = td + C::ROWS * 4;
-  double* red = ti + C::ROWS * 4;
+  double* ti = td + C::TILE;
+  double* red = ti + LC * C::ROWS;
   (void)red0;
-  const int r0 = blockIdx.x * 2;
+  const int r0 = blockIdx.x * LC;
   constexpr int n = C::n, m = n - 2;
   const int nrows = a.ux.rows;
   // div = i k / sx S_y ux + D_y S_y uy / sy   (navier.rs:698-703)
-  tile_fill<C::NTHR>(td, n, [&](int j, int l) { return ldc_stencil(a.uy, prow_of(r0, l), j, l & 1, a.sd, a.sl); });
-  tile_fill<C::NTHR>(ti, m, [&](int j, int l) { return a.m.inv[(size_t)min(prow_of(r0, l), nrows - 1) * a.m.inv_ld + j]; });
+  tile_fill<LC, C::NTHR>(td, n, [&](int j, int l) { return ldc_stencil(a.uy, prow_of(r0, l), j, l & 1, a.sd, a.sl); });
+  for (int it = threadIdx.x; it < m * LC; it += C::NTHR) {  // pivot reciprocals of the LC complex rows
+    const int l = it / m, j = it - l * m;
+    ti[l * C::ROWS + j] = a.m.inv[(size_t)min(r0 + l, nrows - 1) * a.m.inv_ld + j];
+  }
   __syncthreads();
-  cheb_diff<C::NTHR, C::CL>(td, -1, td, -1, n, a.isy, red);
-  for (int it = threadIdx.x; it < n * 4; it += C::NTHR) {
-    const int j = it >> 2, l = it & 3, r = prow_of(r0, l), part = l & 1;
+  cheb_diff<LC, C::NTHR, C::CL>(td, -1, td, -1, n, a.isy, red);
+  for (int it = threadIdx.x; it < n * C::LR; it += C::NTHR) {
+    const int j = it / C::LR, l = it % C::LR, r = prow_of(r0, l), part = l & 1;
     const double ks = a.isx * (double)min(r, nrows - 1);
     const double re = ldc_stencil(a.ux, r, j, 0, a.sd, a.sl), im = ldc_stencil(a.ux, r, j, 1, a.sd, a.sl);
-    const double v = td[didx(j, l)] + ik_part(ks, re, im, part);
-    td[didx(j, l)] = v;
+    const double v = td[didx<LC>(j, l)] + ik_part(ks, re, im, part);
+    td[didx<LC>(j, l)] = v;
     if (r < a.div.rows) a.div.p[((size_t)r * a.div.ld + j) * 2 + part] = v;
   }
   __syncthreads();
-  const double mu = __ldg(&a.m.lam[min(prow_of(r0, threadIdx.x & 3), nrows - 1)]) + a.m.alpha;
-  mode_solve<C::NTHR, C::CL>(td, ti, n, a.b2, a.m, mu, red);
-  tile_drain<C::NTHR>(td, -1, m, [&](int j, int l, double v) {
+  const double mu = __ldg(&a.m.lam[min(prow_of(r0, threadIdx.x % C::LR), nrows - 1)]) + a.m.alpha;
+  mode_solve<LC, C::NTHR, C::CL, C::ROWS, 1>(td, ti, n, a.b2, a.m, mu, red);
+  tile_drain<LC, C::NTHR>(td, -1, m, [&](int j, int l, double v) {
     const int r = prow_of(r0, l);
     if (r == 0 && j == 0) v = 0.0;  // pres[1].vhat[[0,0]] = 0   (navier.rs:714)
     if (r < a.phi.rows) a.phi.p[((size_t)r * a.phi.ld + j) * 2 + (l & 1)] = v;
   });
 }
 
-template <int LOG2L>
-__global__ void __launch_bounds__(YCfg<LOG2L>::NTHR, 2) pk_project(PProjectArgs a) {
-  typedef YCfg<LOG2L> C;
+template <int LOG2L, int LC>
+__global__ void __launch_bounds__(YCfg<LOG2L, LC>::NTHR, YCfg<LOG2L, LC>::SMEM1 > 110 * 1024 ? 1 : 2) pk_project(PProjectArgs a) {
+  typedef YCfg<LOG2L, LC> C;
   YK_SMEM(td, red);
-  const int r0 = blockIdx.x * 2;
+  const int r0 = blockIdx.x * LC;
   constexpr int n = C::n, m = n - 2;
   const int nrows = a.phi.rows;
   // ux -= from_ortho_y(i k / sx S_y phi)   (navier.rs:683-695)
-  tile_fill<C::NTHR>(td, n, [&](int j, int l) {
+  tile_fill<LC, C::NTHR>(td, n, [&](int j, int l) {
     const int r = prow_of(r0, l);
     const double ks = a.isx * (double)min(r, nrows - 1);
     return ik_part(ks, ldc_stencil(a.phi, r, j, 0, a.nsd, a.nsl), ldc_stencil(a.phi, r, j, 1, a.nsd, a.nsl), l & 1);
   });
   __syncthreads();
-  from_ortho<C::NTHR, C::CL>(td, -1, n, a.t, red);
-  tile_drain<C::NTHR>(td, -1, m, [&](int j, int l, double v) {
+  from_ortho<LC, C::NTHR, C::CL>(td, -1, n, a.t, red);
+  tile_drain<LC, C::NTHR>(td, -1, m, [&](int j, int l, double v) {
     const int r = prow_of(r0, l);
     if (r < a.ux.rows) a.ux.p[((size_t)r * a.ux.ld + j) * 2 + (l & 1)] -= v;
   });
   __syncthreads();
   // to_ortho(phi): pressure update p += -nu div + to_ortho(phi) / dt   (navier.rs:717-721)
-  tile_fill<C::NTHR>(td, n, [&](int j, int l) { return ldc_stencil(a.phi, prow_of(r0, l), j, l & 1, a.nsd, a.nsl); });
+  tile_fill<LC, C::NTHR>(td, n, [&](int j, int l) { return ldc_stencil(a.phi, prow_of(r0, l), j, l & 1, a.nsd, a.nsl); });
   __syncthreads();
-  for (int it0 = threadIdx.x; it0 < n * 4; it0 += C::NTHR * 4) {
+  for (int it0 = threadIdx.x; it0 < n * C::LR; it0 += C::NTHR * 4) {
     double dv[4], pv[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const int it = min(it0 + u * C::NTHR, n * 4 - 1);
-      dv[u] = ldc(a.div, prow_of(r0, it & 3), it >> 2, it & 1);
-      pv[u] = ldc(a.pres, prow_of(r0, it & 3), it >> 2, it & 1);
+      const int it = min(it0 + u * C::NTHR, n * C::LR - 1);
+      dv[u] = ldc(a.div, prow_of(r0, it % C::LR), it / C::LR, it & 1);
+      pv[u] = ldc(a.pres, prow_of(r0, it % C::LR), it / C::LR, it & 1);
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int it = it0 + u * C::NTHR;
-      if (it < n * 4) {
-        const int j = it >> 2, l = it & 3, r = prow_of(r0, l);
-        if (r < a.pres.rows) a.pres.p[((size_t)r * a.pres.ld + j) * 2 + (l & 1)] = fma(-a.nu, dv[u], pv[u]) + td[didx(j, l)] * a.inv_dt;
+      if (it < n * C::LR) {
+        const int j = it / C::LR, l = it % C::LR, r = prow_of(r0, l);
+        if (r < a.pres.rows) a.pres.p[((size_t)r * a.pres.ld + j) * 2 + (l & 1)] = fma(-a.nu, dv[u], pv[u]) + td[didx<LC>(j, l)] * a.inv_dt;
       }
     }
   }
   __syncthreads();
   // uy -= from_ortho_y(D_y S_y phi / sy)
-  cheb_diff<C::NTHR, C::CL>(td, -1, td, -1, n, a.isy, red);
-  from_ortho<C::NTHR, C::CL>(td, -1, n, a.t, red);
-  tile_drain<C::NTHR>(td, -1, m, [&](int j, int l, double v) {
+  cheb_diff<LC, C::NTHR, C::CL>(td, -1, td, -1, n, a.isy, red);
+  from_ortho<LC, C::NTHR, C::CL>(td, -1, n, a.t, red);
+  tile_drain<LC, C::NTHR>(td, -1, m, [&](int j, int l, double v) {
     const int r = prow_of(r0, l);
     if (r < a.uy.rows) a.uy.p[((size_t)r * a.uy.ld + j) * 2 + (l & 1)] -= v;
   });
 }
 
 // ---- launchers -----------------------------------------------------------------------------------
-#define PX_SIZES(X) X(5) X(6) X(9) X(10) X(11)
+#define PX_SIZES(X) X(5, 2) X(6, 2) X(7, 1) X(9, 2) X(10, 2) X(11, 2) X(12, 1) X(13, 1)
 
 bool px_supported(int n0) {
   const int l = log2_of(n0);
-#define X(L) \
+#define X(L, LCV) \
   if (l == L) return true;
   PX_SIZES(X)
 #undef X
   return false;
 }
 
-#define PX_CASE(kern, L)                                                              \
+#define PX_CASE(kern, L, LCV)                                                         \
   if (l_ == L) {                                                                      \
-    typedef PXCfg<L> C;                                                               \
+    typedef PXCfg<L, LCV> C;                                                          \
+    auto kp_ = kern<L, LCV>;                                                          \
+    const int nb_ = ((ncols_) + 2 * LCV - 1) / (2 * LCV);                             \
     static bool init_ = false;                                                        \
     if (!init_) {                                                                     \
-      set_smem(kern<L>, C::SMEM);                                                     \
+      set_smem(kp_, C::SMEM);                                                         \
       init_ = true;                                                                   \
     }                                                                                 \
-    RP_LAUNCH(kern<L>, dim3(nb_, nby_), dim3(C::NTHR), (size_t)C::SMEM, s, a);        \
+    RP_LAUNCH(kp_, dim3(nb_, nby_), dim3(C::NTHR), (size_t)C::SMEM, s, a);            \
     ok_ = true;                                                                       \
   }
-#define PX_CASE_pk_c2r(L) PX_CASE(pk_c2r, L)
-#define PX_CASE_pk_r2c(L) PX_CASE(pk_r2c, L)
+#define PX_CASE_pk_c2r(L, LCV) PX_CASE(pk_c2r, L, LCV)
+#define PX_CASE_pk_r2c(L, LCV) PX_CASE(pk_r2c, L, LCV)
 #define PX_LAUNCH(kern, ncols, nx, nby)                                            \
   do {                                                                             \
     const int l_ = log2_of(nx);                                                    \
-    const int nb_ = ((ncols) + 3) / 4, nby_ = (nby);                               \
+    const int ncols_ = (ncols), nby_ = (nby);                                      \
     bool ok_ = false;                                                              \
     PX_SIZES(PX_CASE_##kern)                                                       \
     if (!ok_) throw Error(RP_ERR_INTERNAL, #kern ": unsupported lane length");     \
@@ -294,9 +303,9 @@ bool px_supported(int n0) {
 void launch_p_c2r(const PC2rArgs3& a, int nb, cudaStream_t s) { PX_LAUNCH(pk_c2r, a.a[0].src.cols, a.a[0].n, nb); }
 void launch_p_r2c(const PR2cArgs3& a, int nb, cudaStream_t s) { PX_LAUNCH(pk_r2c, a.a[0].src.cols, a.a[0].n, nb); }
 
-#define YK_CASE_pk_hholtz(L) YK_CASE_BODY(pk_hholtz, L, true, a)
-#define YK_CASE_pk_divpois(L) YK_CASE_BODY(pk_divpois, L, true, a)
-#define YK_CASE_pk_project(L) YK_CASE_BODY(pk_project, L, false, a)
+#define YK_CASE_pk_hholtz(L, LCV) YK_CASE_BODY(pk_hholtz, L, LCV, 2, a)
+#define YK_CASE_pk_divpois(L, LCV) YK_CASE_BODY(pk_divpois, L, LCV, 2, a)
+#define YK_CASE_pk_project(L, LCV) YK_CASE_BODY(pk_project, L, LCV, 0, a)
 
 // complex rows: a block owns 2 rows -> the launch helper's "rows / 4" becomes "2 * rows / 4"
 void launch_p_hholtz(const PHholtzArgs3& a, int nb, cudaStream_t s) { YK_LAUNCH(pk_hholtz, true, 2 * a.a[0].chat.rows, a.a[0].ny, a, nb); }

@@ -13,6 +13,8 @@
 namespace rp {
 namespace fk {
 
+constexpr int LC = 2;  // the x kernels of the confined path use the 4-real-lane tile
+
 template <int LOG2LB>
 struct XCfg {
   static constexpr int LB = 1 << LOG2LB;
@@ -38,7 +40,7 @@ FK_DEV void xtile_fill(double* td, int nfill, F f) {  // batched like tile_fill 
 #pragma unroll
     for (int u = 0; u < FK_FILL_U; ++u) {
       const int it = it0 + u * NTHR;
-      if (it < tot) td[didx(it >> 2, it & 3)] = v[u];
+      if (it < tot) td[didx<LC>(it >> 2, it & 3)] = v[u];
     }
   }
 }
@@ -82,9 +84,9 @@ FK_DEV void xstencil_tile(double* dst, const double* src, int n, const double* _
   for (int it = threadIdx.x; it < n * 4; it += NTHR) {
     const int l = it & 3, i = it >> 2;
     double v = 0.0;
-    if (i < m) v = __ldg(&sd[i]) * src[didx(i, l)];
-    if (i >= 2) v = fma(__ldg(&sl[i - 2]), src[didx(i - 2, l)], v);
-    dst[didx(i, l)] = v;
+    if (i < m) v = __ldg(&sd[i]) * src[didx<LC>(i, l)];
+    if (i >= 2) v = fma(__ldg(&sl[i - 2]), src[didx<LC>(i - 2, l)], v);
+    dst[didx<LC>(i, l)] = v;
   }
 }
 
@@ -108,11 +110,11 @@ __global__ void __launch_bounds__(XCfg<LOG2LB>::NTHR, 1) xk_backward(XBackwardAr
   __syncthreads();
   for (int pass = 0; pass < 2; ++pass) {
     const Mat& o = pass ? a.dx : a.val;
-    if (pass) cheb_diff<C::NTHR, C::CL>(ta, -1, ta, -1, n, a.isx, red);
-    dct_bluestein<LOG2LB, C::NTHR, true>(ta, tw, a.t, red);
+    if (pass) cheb_diff<LC, C::NTHR, C::CL>(ta, -1, ta, -1, n, a.isx, red);
+    dct_bluestein<LC, LOG2LB, C::NTHR, true>(ta, tw, a.t, red);
     for (int it = threadIdx.x; it < n * 4; it += C::NTHR) {
       const int l = it & 3, i = it >> 2;
-      if (c0 + l < o.cols) o.p[(size_t)i * o.ld + c0 + l] = tw[didx(rowof(N, i), l)];
+      if (c0 + l < o.cols) o.p[(size_t)i * o.ld + c0 + l] = tw[didx<LC>(rowof(N, i), l)];
     }
     __syncthreads();
   }
@@ -134,7 +136,7 @@ __global__ void __launch_bounds__(XCfg<LOG2LB>::NTHR, 1) xk_forward(XForwardArgs
     if (nxt < (int)(gridDim.x * gridDim.y)) prefetch_strip<C::NTHR, false>(a3.a[nxt / gridDim.x].conv, (nxt % gridDim.x) * 4, n);
   }
   __syncthreads();
-  dct_bluestein<LOG2LB, C::NTHR, false>(ta, tw, a.t, red);
+  dct_bluestein<LC, LOG2LB, C::NTHR, false>(ta, tw, a.t, red);
   // rhs assembly in the split(N) layout of W.  Every global array is read once per element:
   // S_y is applied while loading (columns j, j-2), S_x on the shared-memory copy in A.
   const int mxr = n - 2;
@@ -147,8 +149,8 @@ __global__ void __launch_bounds__(XCfg<LOG2LB>::NTHR, 1) xk_forward(XForwardArgs
   };
   auto sx_at = [&](int i, int l, const double* __restrict__ xsd, const double* __restrict__ xsl) {
     double v = 0.0;
-    if (i < mxr) v = __ldg(&xsd[i]) * ta[didx(i, l)];
-    if (i >= 2) v = fma(__ldg(&xsl[i - 2]), ta[didx(i - 2, l)], v);
+    if (i < mxr) v = __ldg(&xsd[i]) * ta[didx<LC>(i, l)];
+    if (i >= 2) v = fma(__ldg(&xsl[i - 2]), ta[didx<LC>(i - 2, l)], v);
     return v;
   };
   // - dt * dealiased conv + to_ortho(field)   (navier.rs:625, 630, 651, 671)
@@ -166,7 +168,7 @@ __global__ void __launch_bounds__(XCfg<LOG2LB>::NTHR, 1) xk_forward(XForwardArgs
       const int it = it0 + u * C::NTHR;
       if (it < n * 4) {
         const int l = it & 3, i = it >> 2;
-        double* w = &tw[didx(rowof(N, i), l)];
+        double* w = &tw[didx<LC>(rowof(N, i), l)];
         const double v = (i < a.cut) ? -a.dt * (*w) : 0.0;
         *w = v + sx_at(i, l, a.fxsd, a.fxsl) + add[u];
       }
@@ -176,10 +178,10 @@ __global__ void __launch_bounds__(XCfg<LOG2LB>::NTHR, 1) xk_forward(XForwardArgs
   if (a.mode == 0) {  // - dt/sx d/dx pres   (navier.rs:627)
     xtile_fill<C::NTHR>(ta, n, [&](int i, int l) { return ld_plain(a.pres, i, c0 + l); });
     __syncthreads();
-    cheb_diff<C::NTHR, C::CL>(ta, -1, ta, -1, n, -a.dt * a.isx, red);
+    cheb_diff<LC, C::NTHR, C::CL>(ta, -1, ta, -1, n, -a.dt * a.isx, red);
     for (int it = threadIdx.x; it < n * 4; it += C::NTHR) {
       const int l = it & 3, i = it >> 2;
-      tw[didx(rowof(N, i), l)] += ta[didx(i, l)];
+      tw[didx<LC>(rowof(N, i), l)] += ta[didx<LC>(i, l)];
     }
   } else if (a.mode == 1) {  // - dt/sy d/dy pres + dt * (that + tbc)   (navier.rs:646-648)
     xtile_fill<C::NTHR>(ta, mxr, [&](int i, int l) { return ld_sy(a.tmp, i, l, a.tysd, a.tysl); });
@@ -198,18 +200,18 @@ __global__ void __launch_bounds__(XCfg<LOG2LB>::NTHR, 1) xk_forward(XForwardArgs
         if (it < n * 4) {
           const int l = it & 3, i = it >> 2;
           const double that = sx_at(i, l, a.txsd, a.txsl) + g2[u];
-          double* w = &tw[didx(rowof(N, i), l)];
+          double* w = &tw[didx<LC>(rowof(N, i), l)];
           *w = fma(a.dt, that, fma(-a.dt, g1[u], *w));
         }
       }
     }
   }
   __syncthreads();
-  b2_fdma<C::NTHR, C::CL>(tw, N, n, a.b2, a.f, red);
+  b2_fdma<LC, C::NTHR, C::CL>(tw, N, n, a.b2, a.f, red);
   const int m = n - 2;
   for (int it = threadIdx.x; it < m * 4; it += C::NTHR) {
     const int l = it & 3, i = it >> 2;
-    if (c0 + l < ncols) a.out.p[(size_t)i * a.out.ld + c0 + l] = tw[didx(rowof(N, i), l)];
+    if (c0 + l < ncols) a.out.p[(size_t)i * a.out.ld + c0 + l] = tw[didx<LC>(rowof(N, i), l)];
   }
 }
 
@@ -227,21 +229,21 @@ __global__ void __launch_bounds__(XCfg<LOG2LB>::NTHR, 1) xk_div(XDivArgs a) {
   xstencil_tile<C::NTHR>(ta, tb, n, a.sd, a.sl);
   __syncthreads();
   xtile_fill<C::NTHR>(tb, m, [&](int i, int l) { return ld_plain(a.ey, i, c0 + l); });
-  cheb_diff<C::NTHR, C::CL>(ta, -1, ta, -1, n, a.isx, red);
+  cheb_diff<LC, C::NTHR, C::CL>(ta, -1, ta, -1, n, a.isx, red);
   for (int it = threadIdx.x; it < n * 4; it += C::NTHR) {
     const int l = it & 3, i = it >> 2;
     double e = 0.0;
-    if (i < m) e = __ldg(&a.sd[i]) * tb[didx(i, l)];
-    if (i >= 2) e = fma(__ldg(&a.sl[i - 2]), tb[didx(i - 2, l)], e);
-    const double v = ta[didx(i, l)] + e;
-    ta[didx(i, l)] = v;
+    if (i < m) e = __ldg(&a.sd[i]) * tb[didx<LC>(i, l)];
+    if (i >= 2) e = fma(__ldg(&a.sl[i - 2]), tb[didx<LC>(i - 2, l)], e);
+    const double v = ta[didx<LC>(i, l)] + e;
+    ta[didx<LC>(i, l)] = v;
     if (c0 + l < ncols) a.div.p[(size_t)i * a.div.ld + c0 + l] = v;
   }
   __syncthreads();
   for (int it = threadIdx.x; it < m * 4; it += C::NTHR) {
     const int l = it & 3, i = it >> 2;
-    const double v = fma(__ldg(&a.b2.lo[i]), ta[didx(i, l)],
-                         fma(__ldg(&a.b2.di[i]), ta[didx(i + 2, l)], (i + 4 < n) ? __ldg(&a.b2.up[i]) * ta[didx(i + 4, l)] : 0.0));
+    const double v = fma(__ldg(&a.b2.lo[i]), ta[didx<LC>(i, l)],
+                         fma(__ldg(&a.b2.di[i]), ta[didx<LC>(i + 2, l)], (i + 4 < n) ? __ldg(&a.b2.up[i]) * ta[didx<LC>(i + 4, l)] : 0.0));
     if (c0 + l < ncols) a.r1.p[(size_t)i * a.r1.ld + c0 + l] = v;
   }
 }
@@ -259,14 +261,14 @@ __global__ void __launch_bounds__(XCfg<LOG2LB>::NTHR, 1) xk_project(XProjectArgs
   __syncthreads();
   xstencil_tile<C::NTHR>(ta, tb, n, a.nsd, a.nsl);
   __syncthreads();
-  cheb_diff<C::NTHR, C::CL>(ta, -1, tb, -1, n, a.isx, red);
-  from_ortho<C::NTHR, C::CL>(tb, -1, n, a.t, red);
-  from_ortho<C::NTHR, C::CL>(ta, -1, n, a.t, red);
+  cheb_diff<LC, C::NTHR, C::CL>(ta, -1, tb, -1, n, a.isx, red);
+  from_ortho<LC, C::NTHR, C::CL>(tb, -1, n, a.t, red);
+  from_ortho<LC, C::NTHR, C::CL>(ta, -1, n, a.t, red);
   for (int it = threadIdx.x; it < m * 4; it += C::NTHR) {
     const int l = it & 3, i = it >> 2;
     if (c0 + l < ncols) {
-      a.a1.p[(size_t)i * a.a1.ld + c0 + l] = tb[didx(i, l)];
-      a.a2.p[(size_t)i * a.a2.ld + c0 + l] = ta[didx(i, l)];
+      a.a1.p[(size_t)i * a.a1.ld + c0 + l] = tb[didx<LC>(i, l)];
+      a.a2.p[(size_t)i * a.a2.ld + c0 + l] = ta[didx<LC>(i, l)];
     }
   }
 }

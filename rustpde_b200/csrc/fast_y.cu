@@ -14,47 +14,47 @@ namespace rp {
 namespace fk {
 
 // ---------------------------------------------------------------------------------
-template <int LOG2L>
-__global__ void __launch_bounds__(YCfg<LOG2L>::NTHR, 2) yk_backward(YBackwardArgs3 a3) {
-  typedef YCfg<LOG2L> C;
+template <int LOG2L, int LC>
+__global__ void __launch_bounds__(YCfg<LOG2L, LC>::NTHR, YCfg<LOG2L, LC>::SMEM1 > 110 * 1024 ? 1 : 2) yk_backward(YBackwardArgs3 a3) {
+  typedef YCfg<LOG2L, LC> C;
   const YBackwardArgs& a = a3.a[blockIdx.y];
   YK_SMEM(td, red);
-  const int r0 = blockIdx.x * 4;
+  const int r0 = blockIdx.x * C::LR;
   constexpr int n = C::n, m = n - 2, N = C::N;
   auto fill = [&](const Mat& s) {
-    tile_fill<C::NTHR>(td, n, [&](int j, int l) { return ld_stencil(s, r0 + l, j, m, a.sd, a.sl); });
+    tile_fill<LC, C::NTHR>(td, n, [&](int j, int l) { return ld_stencil(s, r0 + l, j, m, a.sd, a.sl); });
     __syncthreads();
   };
   auto drain = [&](const Mat& o) {
-    tile_drain<C::NTHR>(td, N, n, [&](int j, int l, double v) {
+    tile_drain<LC, C::NTHR>(td, N, n, [&](int j, int l, double v) {
       if (r0 + l < o.rows) o.p[(size_t)(r0 + l) * o.ld + j] = v;
     });
   };
   fill(a.a);
   if (a.val.p) {
-    dct_pow2<LOG2L, C::NTHR, true>(td, a.t, red);
+    dct_pow2<LC, LOG2L, C::NTHR, true>(td, a.t, red);
     drain(a.val);
     __syncthreads();
     fill(a.a);
   }
-  cheb_diff<C::NTHR, C::CL>(td, -1, td, -1, n, a.isy, red);
-  dct_pow2<LOG2L, C::NTHR, true>(td, a.t, red);
+  cheb_diff<LC, C::NTHR, C::CL>(td, -1, td, -1, n, a.isy, red);
+  dct_pow2<LC, LOG2L, C::NTHR, true>(td, a.t, red);
   drain(a.dy);
   __syncthreads();
   fill(a.adx);
-  dct_pow2<LOG2L, C::NTHR, true>(td, a.t, red);
+  dct_pow2<LC, LOG2L, C::NTHR, true>(td, a.t, red);
   drain(a.dx);
 }
 
-template <int LOG2L>
-__global__ void __launch_bounds__(YCfg<LOG2L>::NTHR, 2) yk_conv(YConvArgs3 a3) {
-  typedef YCfg<LOG2L> C;
+template <int LOG2L, int LC>
+__global__ void __launch_bounds__(YCfg<LOG2L, LC>::NTHR, YCfg<LOG2L, LC>::SMEM1 > 110 * 1024 ? 1 : 2) yk_conv(YConvArgs3 a3) {
+  typedef YCfg<LOG2L, LC> C;
   const YConvArgs& a = a3.a[blockIdx.y];
   YK_SMEM(td, red);
-  const int r0 = blockIdx.x * 4;
+  const int r0 = blockIdx.x * C::LR;
   constexpr int n = C::n, N = C::N;
   const bool has_bc = a.bcx.p != nullptr;
-  tile_fill<C::NTHR>(td, n, [&](int j, int l) {
+  tile_fill<LC, C::NTHR>(td, n, [&](int j, int l) {
     const int r = min(r0 + l, a.u.rows - 1);
     double gx = a.du.p[(size_t)r * a.du.ld + j], gy = a.dv.p[(size_t)r * a.dv.ld + j];
     const double u = a.u.p[(size_t)r * a.u.ld + j], v = a.v.p[(size_t)r * a.v.ld + j];
@@ -65,104 +65,107 @@ __global__ void __launch_bounds__(YCfg<LOG2L>::NTHR, 2) yk_conv(YConvArgs3 a3) {
     return (r0 + l < a.u.rows) ? fma(u, gx, v * gy) : 0.0;
   });
   __syncthreads();
-  dct_pow2<LOG2L, C::NTHR, false>(td, a.t, red);
-  tile_drain<C::NTHR>(td, N, n, [&](int j, int l, double v) {
+  dct_pow2<LC, LOG2L, C::NTHR, false>(td, a.t, red);
+  tile_drain<LC, C::NTHR>(td, N, n, [&](int j, int l, double v) {
     if (r0 + l < a.out.rows) a.out.p[(size_t)(r0 + l) * a.out.ld + j] = (j < a.cut) ? v : 0.0;
   });
 }
 
-template <int LOG2L>
-__global__ void __launch_bounds__(YCfg<LOG2L>::NTHR, 2) yk_adi(YAdiArgs3 a3) {
-  typedef YCfg<LOG2L> C;
+template <int LOG2L, int LC>
+__global__ void __launch_bounds__(YCfg<LOG2L, LC>::NTHR, YCfg<LOG2L, LC>::SMEM1 > 110 * 1024 ? 1 : 2) yk_adi(YAdiArgs3 a3) {
+  typedef YCfg<LOG2L, LC> C;
   const YAdiArgs& a = a3.a[blockIdx.y];
   YK_SMEM(td, red);
-  const int r0 = blockIdx.x * 4;
+  const int r0 = blockIdx.x * C::LR;
   constexpr int n = C::n, m = n - 2;
-  tile_fill<C::NTHR>(td, n, [&](int j, int l) { return ld_row(a.w, r0 + l, j); });
+  tile_fill<LC, C::NTHR>(td, n, [&](int j, int l) { return ld_row(a.w, r0 + l, j); });
   __syncthreads();
-  b2_fdma<C::NTHR, C::CL>(td, -1, n, a.b2, a.f, red);
-  tile_drain<C::NTHR>(td, -1, m, [&](int j, int l, double v) {
+  b2_fdma<LC, C::NTHR, C::CL>(td, -1, n, a.b2, a.f, red);
+  tile_drain<LC, C::NTHR>(td, -1, m, [&](int j, int l, double v) {
     if (r0 + l < a.out.rows) a.out.p[(size_t)(r0 + l) * a.out.ld + j] = v;
   });
   if (a.mode == 0) return;
   // ortho coefficients p_j = d_j x_j + l_{j-2} x_{j-2} of the new velocity component
   auto pj = [&](int j, int l) {
     double v = 0.0;
-    if (j < m) v = __ldg(&a.sd[j]) * td[didx(j, l)];
-    if (j >= 2) v = fma(__ldg(&a.sl[j - 2]), td[didx(j - 2, l)], v);
+    if (j < m) v = __ldg(&a.sd[j]) * td[didx<LC>(j, l)];
+    if (j >= 2) v = fma(__ldg(&a.sl[j - 2]), td[didx<LC>(j - 2, l)], v);
     return v;
   };
   if (a.mode == 1) {
-    for (int it = threadIdx.x; it < n * 4; it += C::NTHR) {
-      const int l = it & 3, j = it >> 2;
+    for (int it = threadIdx.x; it < n * C::LR; it += C::NTHR) {
+      const int l = it % C::LR, j = it / C::LR;
       if (r0 + l < a.aux.rows) a.aux.p[(size_t)(r0 + l) * a.aux.ld + j] = pj(j, l);
     }
     return;
   }
   __syncthreads();
-  scan1<C::NTHR, C::CL, false>(
+  scan1<LC, C::NTHR, C::CL, false>(
       n, red, [&](int i, int l) { return (2.0 * (double)i * a.isy) * pj(i, l); }, [](int, int) { return 1.0; },
       [&](int i, int l, double y) {
-        if (i >= 1) td[didx(i - 1, l)] = (i == 1) ? 0.5 * y : y;
-        if (i == n - 1) td[didx(n - 1, l)] = 0.0;
+        if (i >= 1) td[didx<LC>(i - 1, l)] = (i == 1) ? 0.5 * y : y;
+        if (i == n - 1) td[didx<LC>(n - 1, l)] = 0.0;
       });
-  tile_drain<C::NTHR>(td, -1, n, [&](int j, int l, double v) {
+  tile_drain<LC, C::NTHR>(td, -1, n, [&](int j, int l, double v) {
     if (r0 + l < a.aux.rows) a.aux.p[(size_t)(r0 + l) * a.aux.ld + j] = v;
   });
 }
 
-template <int LOG2L>
-__global__ void __launch_bounds__(YCfg<LOG2L>::NTHR, 1) yk_mode(YModeArgs a) {
-  typedef YCfg<LOG2L> C;
+template <int LOG2L, int LC>
+__global__ void __launch_bounds__(YCfg<LOG2L, LC>::NTHR, 1) yk_mode(YModeArgs a) {
+  typedef YCfg<LOG2L, LC> C;
   YK_SMEM(td, red0);
-  double* ti = td + C::ROWS * 4;
-  double* red = ti + C::ROWS * 4;
+  double* ti = td + C::TILE;
+  double* red = ti + C::LR * C::ROWS;
   (void)red0;
-  const int r0 = blockIdx.x * 4;
+  const int r0 = blockIdx.x * C::LR;
   constexpr int n = C::n, m = n - 2;
-  tile_fill<C::NTHR>(td, n, [&](int j, int l) { return ld_row(a.g, r0 + l, j); });
-  tile_fill<C::NTHR>(ti, m, [&](int j, int l) { return a.m.inv[(size_t)min(r0 + l, a.g.rows - 1) * a.m.inv_ld + j]; });
+  tile_fill<LC, C::NTHR>(td, n, [&](int j, int l) { return ld_row(a.g, r0 + l, j); });
+  for (int it = threadIdx.x; it < m * C::LR; it += C::NTHR) {  // pivot reciprocals of the LR rows (coalesced along j)
+    const int l = it / m, j = it - l * m;
+    ti[l * C::ROWS + j] = a.m.inv[(size_t)min(r0 + l, a.g.rows - 1) * a.m.inv_ld + j];
+  }
   __syncthreads();
-  const double mu = __ldg(&a.m.lam[min(r0 + (int)(threadIdx.x & 3), a.g.rows - 1)]) + a.m.alpha;
-  mode_solve<C::NTHR, C::CL>(td, ti, n, a.b2, a.m, mu, red);
-  tile_drain<C::NTHR>(td, -1, m, [&](int j, int l, double v) {
+  const double mu = __ldg(&a.m.lam[min(r0 + (int)(threadIdx.x % C::LR), a.g.rows - 1)]) + a.m.alpha;
+  mode_solve<LC, C::NTHR, C::CL, C::ROWS, 0>(td, ti, n, a.b2, a.m, mu, red);
+  tile_drain<LC, C::NTHR>(td, -1, m, [&](int j, int l, double v) {
     if (r0 + l < a.h.rows) a.h.p[(size_t)(r0 + l) * a.h.ld + j] = v;
   });
 }
 
-template <int LOG2L>
-__global__ void __launch_bounds__(YCfg<LOG2L>::NTHR, 2) yk_project(YProjectArgs a) {
-  typedef YCfg<LOG2L> C;
+template <int LOG2L, int LC>
+__global__ void __launch_bounds__(YCfg<LOG2L, LC>::NTHR, YCfg<LOG2L, LC>::SMEM1 > 110 * 1024 ? 1 : 2) yk_project(YProjectArgs a) {
+  typedef YCfg<LOG2L, LC> C;
   YK_SMEM(td, red);
-  const int r0 = blockIdx.x * 4;
+  const int r0 = blockIdx.x * C::LR;
   constexpr int n = C::n, m = n - 2;
   // ux -= from_ortho_y(S_y a1)
-  tile_fill<C::NTHR>(td, n, [&](int j, int l) { return ld_stencil(a.a1, r0 + l, j, m, a.nsd, a.nsl); });
+  tile_fill<LC, C::NTHR>(td, n, [&](int j, int l) { return ld_stencil(a.a1, r0 + l, j, m, a.nsd, a.nsl); });
   __syncthreads();
-  from_ortho<C::NTHR, C::CL>(td, -1, n, a.t, red);
-  tile_drain<C::NTHR>(td, -1, m, [&](int j, int l, double v) {
+  from_ortho<LC, C::NTHR, C::CL>(td, -1, n, a.t, red);
+  tile_drain<LC, C::NTHR>(td, -1, m, [&](int j, int l, double v) {
     if (r0 + l < a.ux.rows) a.ux.p[(size_t)(r0 + l) * a.ux.ld + j] -= v;
   });
   __syncthreads();
   // uy -= from_ortho_y(D_y S_y a2 / sy)
-  tile_fill<C::NTHR>(td, n, [&](int j, int l) { return ld_stencil(a.a2, r0 + l, j, m, a.nsd, a.nsl); });
+  tile_fill<LC, C::NTHR>(td, n, [&](int j, int l) { return ld_stencil(a.a2, r0 + l, j, m, a.nsd, a.nsl); });
   __syncthreads();
-  cheb_diff<C::NTHR, C::CL>(td, -1, td, -1, n, a.isy, red);
-  from_ortho<C::NTHR, C::CL>(td, -1, n, a.t, red);
-  tile_drain<C::NTHR>(td, -1, m, [&](int j, int l, double v) {
+  cheb_diff<LC, C::NTHR, C::CL>(td, -1, td, -1, n, a.isy, red);
+  from_ortho<LC, C::NTHR, C::CL>(td, -1, n, a.t, red);
+  tile_drain<LC, C::NTHR>(td, -1, m, [&](int j, int l, double v) {
     if (r0 + l < a.uy.rows) a.uy.p[(size_t)(r0 + l) * a.uy.ld + j] -= v;
   });
 }
 
-template <int LOG2L>
-__global__ void __launch_bounds__(YCfg<LOG2L>::NTHR, 2) yk_pres(YPresArgs a) {
-  typedef YCfg<LOG2L> C;
+template <int LOG2L, int LC>
+__global__ void __launch_bounds__(YCfg<LOG2L, LC>::NTHR, YCfg<LOG2L, LC>::SMEM1 > 110 * 1024 ? 1 : 2) yk_pres(YPresArgs a) {
+  typedef YCfg<LOG2L, LC> C;
   YK_SMEM(td, red);
-  const int r0 = blockIdx.x * 4;
+  const int r0 = blockIdx.x * C::LR;
   constexpr int n = C::n, m = n - 2;
   const int mx = a.phi.rows;
   // to_ortho(phi): S_x across lanes (rows i, i-2 of phi), S_y along the lane
-  tile_fill<C::NTHR>(td, n, [&](int j, int l) {
+  tile_fill<LC, C::NTHR>(td, n, [&](int j, int l) {
     const int i = min(r0 + l, a.pres.rows - 1);
     const double s0 = ld_stencil(a.phi, min(i, mx - 1), j, m, a.ysd, a.ysl);
     const double s2 = ld_stencil(a.phi, max(i - 2, 0), j, m, a.ysd, a.ysl);
@@ -172,12 +175,12 @@ __global__ void __launch_bounds__(YCfg<LOG2L>::NTHR, 2) yk_pres(YPresArgs a) {
     return (r0 + l < a.pres.rows) ? p : 0.0;
   });
   __syncthreads();
-  tile_drain<C::NTHR>(td, -1, n, [&](int j, int l, double v) {
+  tile_drain<LC, C::NTHR>(td, -1, n, [&](int j, int l, double v) {
     if (r0 + l < a.pres.rows) a.pres.p[(size_t)(r0 + l) * a.pres.ld + j] = v;
   });
   __syncthreads();
-  cheb_diff<C::NTHR, C::CL>(td, -1, td, -1, n, a.isy, red);
-  tile_drain<C::NTHR>(td, -1, n, [&](int j, int l, double v) {
+  cheb_diff<LC, C::NTHR, C::CL>(td, -1, td, -1, n, a.isy, red);
+  tile_drain<LC, C::NTHR>(td, -1, n, [&](int j, int l, double v) {
     if (r0 + l < a.dyp.rows) a.dyp.p[(size_t)(r0 + l) * a.dyp.ld + j] = v;
   });
 }
@@ -187,19 +190,19 @@ __global__ void __launch_bounds__(YCfg<LOG2L>::NTHR, 2) yk_pres(YPresArgs a) {
 // ---------------------------------------------------------------------------------
 bool y_supported(int n1) {
   const int l = log2_of(n1 - 1);
-#define X(L) \
+#define X(L, LCV) \
   if (l == L) return true;
   YK_SIZES(X)
 #undef X
   return false;
 }
 
-#define YK_CASE_yk_backward(L) YK_CASE_BODY(yk_backward, L, false, a)
-#define YK_CASE_yk_conv(L) YK_CASE_BODY(yk_conv, L, false, a)
-#define YK_CASE_yk_adi(L) YK_CASE_BODY(yk_adi, L, false, a)
-#define YK_CASE_yk_mode(L) YK_CASE_BODY(yk_mode, L, true, a)
-#define YK_CASE_yk_project(L) YK_CASE_BODY(yk_project, L, false, a)
-#define YK_CASE_yk_pres(L) YK_CASE_BODY(yk_pres, L, false, a)
+#define YK_CASE_yk_backward(L, LCV) YK_CASE_BODY(yk_backward, L, LCV, 0, a)
+#define YK_CASE_yk_conv(L, LCV) YK_CASE_BODY(yk_conv, L, LCV, 0, a)
+#define YK_CASE_yk_adi(L, LCV) YK_CASE_BODY(yk_adi, L, LCV, 0, a)
+#define YK_CASE_yk_mode(L, LCV) YK_CASE_BODY(yk_mode, L, LCV, 1, a)
+#define YK_CASE_yk_project(L, LCV) YK_CASE_BODY(yk_project, L, LCV, 0, a)
+#define YK_CASE_yk_pres(L, LCV) YK_CASE_BODY(yk_pres, L, LCV, 0, a)
 
 void launch_y_backward(const YBackwardArgs3& a, int nb, cudaStream_t s) { YK_LAUNCH(yk_backward, false, a.a[0].a.rows, a.a[0].t.n, a, nb); }
 void launch_y_conv(const YConvArgs3& a, int nb, cudaStream_t s) { YK_LAUNCH(yk_conv, false, a.a[0].u.rows, a.a[0].t.n, a, nb); }

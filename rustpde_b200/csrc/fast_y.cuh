@@ -6,47 +6,52 @@
 namespace rp {
 namespace fk {
 
-template <int LOG2L>
+template <int LOG2L, int LC_ = 2>
 struct YCfg {
+  static constexpr int LC = LC_, LR = 2 * LC_;  // complex / real lanes per tile
   static constexpr int N = 1 << LOG2L;
   static constexpr int n = N + 1;
-  static constexpr int NTHR = (N / 4) < 64 ? 64 : (N / 4);
-  static constexpr int ROWS = N + 4;
-  static constexpr int CL = chunk_len(n, NTHR);
-  static constexpr int SMEM1 = ROWS * 32 + scan_threads(NTHR) * 56 + 512;      // one tile + scratch
-  static constexpr int SMEM2 = 2 * ROWS * 32 + scan_threads(NTHR) * 56 + 512;  // two tiles + scratch
+  static constexpr int NTHR = (N * LC / 8) < 64 ? 64 : (N * LC / 8);
+  static constexpr int ROWS = N + 8;
+  static constexpr int TILE = ROWS * LR;  // doubles per tile
+  static constexpr int CL = chunk_len(n, NTHR, LC);
+  static constexpr int SMEM1 = TILE * 8 + scan_threads(NTHR) * 56 + 512;      // one tile + scratch
+  static constexpr int SMEM2 = (TILE + LR * ROWS) * 8 + scan_threads(NTHR) * 56 + 512;  // tile + pivot rows + scratch
+  static constexpr int SMEMC = (TILE + LC * ROWS) * 8 + scan_threads(NTHR) * 56 + 512;  // same on complex rows
 };
 
 #define YK_SMEM(td, red)          \
   RP_DYN_SMEM(double, td);        \
-  double* red = td + C::ROWS * 4
+  double* red = td + C::TILE
 
 // tile(j, lane) = f(j, lane) for j < nfill.  Loads are issued in batches of FK_FILL_U
 // per thread before the first store, so that enough global requests are in flight.
 #define FK_FILL_U 8
-template <int NTHR, class F>
+template <int LC, int NTHR, class F>
 FK_DEV void tile_fill(double* td, int nfill, F f) {
-  const int tot = nfill * 4;
+  constexpr int LR = 2 * LC;
+  const int tot = nfill * LR;
   for (int it0 = threadIdx.x; it0 < tot; it0 += NTHR * FK_FILL_U) {
     double v[FK_FILL_U];
 #pragma unroll
     for (int u = 0; u < FK_FILL_U; ++u) {
       const int it = min(it0 + u * NTHR, tot - 1);  // clamped: the loads stay unconditional
-      v[u] = f(it >> 2, it & 3);
+      v[u] = f(it / LR, it % LR);
     }
 #pragma unroll
     for (int u = 0; u < FK_FILL_U; ++u) {
       const int it = it0 + u * NTHR;
-      if (it < tot) td[didx(it >> 2, it & 3)] = v[u];
+      if (it < tot) td[didx<LC>(it / LR, it % LR)] = v[u];
     }
   }
 }
 // g(j, lane, value of natural element j) for j < nout
-template <int NTHR, class G>
+template <int LC, int NTHR, class G>
 FK_DEV void tile_drain(const double* td, int sn, int nout, G g) {
-  for (int it = threadIdx.x; it < nout * 4; it += NTHR) {
-    const int lane = it & 3, j = it >> 2;
-    g(j, lane, td[didx(rowof(sn, j), lane)]);
+  constexpr int LR = 2 * LC;
+  for (int it = threadIdx.x; it < nout * LR; it += NTHR) {
+    const int lane = it % LR, j = it / LR;
+    g(j, lane, td[didx<LC>(rowof(sn, j), lane)]);
   }
 }
 
@@ -74,34 +79,37 @@ FK_DEV double ld_row(const Mat& a, int r, int j) {
 // tile td holds g (n entries, natural layout), tile ti the swept pivot reciprocals 1/dia'_i of the lane
 // (set-up data); everything else of the sweep is recomputed from the raw bands.  `mu` = lam + alpha of
 // the calling thread's lane (threadIdx.x & 3).  Result: m = n - 2 entries in td.
-template <int NTHR, int CL>
+// `ti` holds one plain array of ROWS reciprocals per *row* of the tile; lane l reads row l >> CSHIFT
+// (CSHIFT = 0: 2 LC real rows; CSHIFT = 1: re/im lanes of LC complex rows share their row's array).
+template <int LC, int NTHR, int CL, int ROWS, int CSHIFT>
 FK_DEV void mode_solve(double* td, const double* ti, int n, const B2Tabs& B, const ModeTabs& M, double mu, double* red) {
   const int m = n - 2;
+  auto inv = [&](int i, int l) { return ti[(l >> CSHIFT) * ROWS + i]; };
   // forward: x_i -= l_{i-2} x_{i-2},  l_j = low_j / dia'_j   (fdma.rs:104-107 on the swept system)
   auto lw = [&](int i, int l) {  // low'_{i-2}
-    return fma(mu, __ldg(&M.c_low[i - 2]), __ldg(&M.a_low[i - 2])) * ti[didx(i - 2, l)];
+    return fma(mu, __ldg(&M.c_low[i - 2]), __ldg(&M.a_low[i - 2])) * inv(i - 2, l);
   };
-  scan1<NTHR, CL, true>(
+  scan1<LC, NTHR, CL, true>(
       m, red,
       [&](int i, int l) {
-        return fma(__ldg(&B.lo[i]), td[didx(i, l)],
-                   fma(__ldg(&B.di[i]), td[didx(i + 2, l)], (i + 4 < n) ? __ldg(&B.up[i]) * td[didx(i + 4, l)] : 0.0));
+        return fma(__ldg(&B.lo[i]), td[didx<LC>(i, l)],
+                   fma(__ldg(&B.di[i]), td[didx<LC>(i + 2, l)], (i + 4 < n) ? __ldg(&B.up[i]) * td[didx<LC>(i + 4, l)] : 0.0));
       },
-      [&](int i, int l) { return i >= 2 ? -lw(i, l) : 0.0; }, [&](int i, int l, double y) { td[didx(i, l)] = y; });
+      [&](int i, int l) { return i >= 2 ? -lw(i, l) : 0.0; }, [&](int i, int l, double y) { td[didx<LC>(i, l)] = y; });
   // backward: x_i = (x_i - up1'_i x_{i+2} - up2_i x_{i+4}) / dia'_i   (fdma.rs:108-117)
-  scan2<NTHR, CL, false>(
-      m, red, [&](int i, int l) { return ti[didx(i, l)] * td[didx(i, l)]; },
+  scan2<LC, NTHR, CL, false>(
+      m, red, [&](int i, int l) { return inv(i, l) * td[didx<LC>(i, l)]; },
       [&](int i, int l) {
         if (i >= m - 2) return 0.0;
         double u1 = fma(mu, __ldg(&M.c_up1[i]), __ldg(&M.a_up1[i]));
         if (i >= 2) u1 = fma(-lw(i, l), fma(mu, __ldg(&M.c_up2[i - 2]), __ldg(&M.a_up2[i - 2])), u1);
-        return -u1 * ti[didx(i, l)];
+        return -u1 * inv(i, l);
       },
       [&](int i, int l) {
         if (i >= m - 4) return 0.0;
-        return -fma(mu, __ldg(&M.c_up2[i]), __ldg(&M.a_up2[i])) * ti[didx(i, l)];
+        return -fma(mu, __ldg(&M.c_up2[i]), __ldg(&M.a_up2[i])) * inv(i, l);
       },
-      [&](int i, int l, double y) { td[didx(i, l)] = y; });
+      [&](int i, int l, double y) { td[didx<LC>(i, l)] = y; });
 }
 
 // ---- launch helpers -----------------------------------------------------------------
@@ -111,7 +119,8 @@ static int log2_of(int v) {
   return ((1 << l) == v) ? l : -1;
 }
 
-#define YK_SIZES(X) X(5) X(6) X(9) X(10) X(11)
+// (log2 lane length, complex lanes per tile): long lanes use the 2-real-lane tile
+#define YK_SIZES(X) X(5, 2) X(6, 2) X(7, 1) X(9, 2) X(10, 2) X(11, 2) X(12, 1) X(13, 1)
 
 template <class K>
 static void set_smem(K kern, int bytes) {
@@ -127,22 +136,24 @@ static void set_smem(K kern, int bytes) {
   do {                                                                                                \
     const int nby_ = (nby);                                                                           \
     const int l_ = log2_of((ny)-1);                                                                   \
-    const int nb_ = ((nrows) + 3) / 4;                                                                \
+    const int nrows_ = (nrows);                                                                       \
     bool ok_ = false;                                                                                 \
     YK_SIZES(YK_CASE_##kern)                                                                          \
     if (!ok_) throw Error(RP_ERR_INTERNAL, #kern ": unsupported lane length");                        \
   } while (0)
 
-#define YK_CASE_BODY(kern, L, two_tiles, args)                                                \
+#define YK_CASE_BODY(kern, L, LCV, smem_sel, args)                                           \
   if (l_ == L) {                                                                              \
-    typedef YCfg<L> C;                                                                        \
-    const int sm_ = (two_tiles) ? C::SMEM2 : C::SMEM1;                                        \
+    typedef YCfg<L, LCV> C;                                                                   \
+    const int nb_ = ((nrows_) + C::LR - 1) / C::LR;                                           \
+    const int sm_ = (smem_sel) == 2 ? C::SMEMC : ((smem_sel) == 1 ? C::SMEM2 : C::SMEM1);     \
+    auto kp_ = kern<L, LCV>;                                                                  \
     static bool init_ = false;                                                                \
     if (!init_) {                                                                             \
-      set_smem(kern<L>, sm_);                                                                 \
+      set_smem(kp_, sm_);                                                                     \
       init_ = true;                                                                           \
     }                                                                                         \
-    RP_LAUNCH(kern<L>, dim3(nb_, nby_), dim3(C::NTHR), (size_t)sm_, s, args);                       \
+    RP_LAUNCH(kp_, dim3(nb_, nby_), dim3(C::NTHR), (size_t)sm_, s, args);                     \
     ok_ = true;                                                                               \
   }
 

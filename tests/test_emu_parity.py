@@ -92,7 +92,8 @@ def test_navier_confined(emu, nx, ny, adiabatic):
     assert max(derr) < 1e-9, (derr, dn, do)
 
 
-@pytest.mark.parametrize("nx,ny,adiabatic,own_eig", [(32, 33, True, False), (24, 33, False, True), (64, 65, True, True), (30, 65, True, False)])
+@pytest.mark.parametrize("nx,ny,adiabatic,own_eig", [(32, 33, True, False), (24, 33, False, True), (64, 65, True, True), (30, 65, True, False),
+                                                     (32, 129, True, True)])  # 2-lane y tiles
 def test_navier_confined_specialised_kernels(emu, nx, ny, adiabatic, own_eig):
     """Sizes served by the specialised x/y kernels (fast_x.cu / fast_y.cu): Bluestein DCT along x,
     power-of-two DCT along y; own_eig also exercises the parity-split GEMMs."""
@@ -123,7 +124,7 @@ def test_navier_periodic(emu, nx, ny):
     assert max(derr) < 1e-9, (derr, dn, do)
 
 
-@pytest.mark.parametrize("nx,ny", [(32, 33), (64, 65), (32, 65)])
+@pytest.mark.parametrize("nx,ny", [(32, 33), (64, 65), (32, 65), (128, 129), (32, 129), (128, 33)])  # 129 / 128: 2-lane tiles
 def test_navier_periodic_specialised_kernels(emu, nx, ny):
     """Sizes served by the specialised periodic kernels (fast_p.cu): pow2 r2c/c2r along x, pow2 DCT along y."""
     import rustpde_b200 as R

@@ -167,7 +167,10 @@ def test_fast_diag_parity_split(gpu, which, kx, ky, nx, ny):
     assert e1 <= tol and e2 <= tol, (e1, e2)
 
 
-@pytest.mark.parametrize("nx,ny,steps", [(32, 33, 6), (64, 65, 50), (512, 513, 20), (2048, 2049, 2)])
+@pytest.mark.parametrize("nx,ny,steps", [(32, 33, 6), (64, 65, 50), (512, 513, 20), (2048, 2049, 2),
+                                         (128, 129, 10),     # 2-lane tiles on both axes (small instantiation)
+                                         (8192, 65, 3),      # config-5 lane length along x (r2c 8192, 2-lane tile)
+                                         (64, 8193, 3)])     # config-5 lane length along y (DCT-I 8193, 2-lane tile)
 def test_navier_periodic_specialised_kernels(gpu, nx, ny, steps):
     """Specialised periodic kernels (fast_p.cu): config-3 grid 512x513 and the 2048x2049 grid.
     Fields <= 1e-9 relative, diagnostics <= 1e-9 relative."""
