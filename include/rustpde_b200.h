@@ -125,6 +125,16 @@ int rp_navier_field(rp_navier_t* h, int which, rp_field_t** out);              /
 int rp_navier_export_eig(rp_navier_t* h, double* lam, double* q, double* p);   /* pressure Poisson set-up data */
 int rp_navier_launches_per_step(rp_navier_t* h, int* n);
 int rp_navier_set_graph(rp_navier_t* h, int on);                               /* CUDA-graph replay of update() (default on) */
+/* Slab decomposition of the periodic step over the Fourier modes kx (one process per GPU; the caller owns the
+   exchange buffers -- DEVICE pointers, dense row-major, interleaved complex -- and performs the all-to-all between
+   the phases; rustpde_b200/slab.py is the driver).  The object's own state arrays hold the rows [k0, k0+mkl).
+     phase1: out6[f]   = B_y S_y u_f,  out6[3+f] = B_y D_y S_y u_f / sy   f = ux, uy, temp   each [mkl, ny] complex
+     phase2: in6[.]    = the same six arrays after the exchange, [nx/2+1, nyl] complex (columns j0..j0+nyl of physical y);
+             work      = 8 * nx * nyl doubles;  out3[f] = r2c(u . grad f) with the kx dealias cut, [nx/2+1, nyl] complex
+     phase3: in3[f]    = out3[f] after the exchange, [mkl, ny] complex; forward DCT-y, rhs, solves, projection; time += dt */
+int rp_navier_slab_phase1(rp_navier_t* h, int k0, int mkl, double* const* out6);
+int rp_navier_slab_phase2(rp_navier_t* h, int j0, int nyl, const double* const* in6, double* work, double* const* out3);
+int rp_navier_slab_phase3(rp_navier_t* h, int k0, int mkl, const double* const* in3);
 /* which kernels serve update(): specialised = 1 -> hand-specialised x/y pass kernels (else generic lane programs);
    split_gemm = 1 -> pressure Poisson runs the even/odd parity-split GEMM pairs (exactly checkerboard set-up data) */
 int rp_navier_kernel_path(rp_navier_t* h, int* specialised, int* split_gemm);

@@ -68,6 +68,9 @@ _SIGS = {
     "rp_navier_launches_per_step": [vp, c_int_p],
     "rp_navier_set_graph": [vp, C.c_int],
     "rp_navier_kernel_path": [vp, c_int_p, c_int_p],
+    "rp_navier_slab_phase1": [vp, C.c_int, C.c_int, C.POINTER(C.c_void_p)],
+    "rp_navier_slab_phase2": [vp, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_void_p, C.POINTER(C.c_void_p)],
+    "rp_navier_slab_phase3": [vp, C.c_int, C.c_int, C.POINTER(C.c_void_p)],
     "rp_navier_profile": [vp, C.c_int, c_double_p, C.c_size_t, c_int_p],
     "rp_navier_op_info": [vp, C.c_int, C.c_char_p, C.c_size_t, c_double_p, c_double_p],
 }

@@ -356,6 +356,24 @@ int rp_navier_export_eig(rp_navier_t* h, double* lam, double* q, double* p) {
 }
 int rp_navier_launches_per_step(rp_navier_t* h, int* n) { NAV_GUARD(if (n) *n = N.launches_per_step()); }
 int rp_navier_set_graph(rp_navier_t* h, int on) { NAV_GUARD(N.set_graph(on != 0)); }
+int rp_navier_slab_phase1(rp_navier_t* h, int k0, int mkl, double* const* out6) {
+  NAV_GUARD({
+    need(out6 != nullptr && mkl > 0 && k0 >= 0 && k0 + mkl <= N.nx / 2 + 1, RP_ERR_INVALID, "slab_phase1: bad row range");
+    N.slab_phase1(k0, mkl, out6);
+  });
+}
+int rp_navier_slab_phase2(rp_navier_t* h, int j0, int nyl, const double* const* in6, double* work, double* const* out3) {
+  NAV_GUARD({
+    need(in6 && work && out3 && nyl > 0 && j0 >= 0 && j0 + nyl <= N.ny, RP_ERR_INVALID, "slab_phase2: bad column range");
+    N.slab_phase2(j0, nyl, in6, work, out3);
+  });
+}
+int rp_navier_slab_phase3(rp_navier_t* h, int k0, int mkl, const double* const* in3) {
+  NAV_GUARD({
+    need(in3 != nullptr && mkl > 0 && k0 >= 0 && k0 + mkl <= N.nx / 2 + 1, RP_ERR_INVALID, "slab_phase3: bad row range");
+    N.slab_phase3(k0, mkl, in3);
+  });
+}
 int rp_navier_kernel_path(rp_navier_t* h, int* specialised, int* split_gemm) {
   NAV_GUARD({
     if (specialised) *specialised = N.uses_specialised_kernels() ? 1 : 0;

@@ -187,7 +187,8 @@ struct PC2rArgs3 {
 void launch_p_c2r(const PC2rArgs3& a, int nbatch, cudaStream_t s);
 
 struct PR2cArgs {  // r2c along x + dealias cut
-  Mat src;         // [nx, cols] real
+  Mat src;         // [nx, cols] real; ignored when u.p is set
+  Mat u, du, v, dv, bcx, bcy;  // optional: transform u * (du + bcx) + v * (dv + bcy) instead of src (conv_term.rs:41)
   Mat dst;         // [mk, cols] complex
   int cut;         // first zeroed kx
   const double2* tw;
@@ -206,8 +207,9 @@ struct PHholtzArgs {  // rhs assembly + per-mode Helmholtz solve on complex rows
   int mode;
   double dt, isx, isy;
   B2Tabs b2;
-  ModeTabs m;
+  ModeTabs m;  // lam / inv already offset to the first row of the slab
   int ny;
+  int k0;      // global kx of row 0 (slab decomposition over kx; 0 on one GPU)
 };
 struct PHholtzArgs3 {
   PHholtzArgs a[3];
@@ -223,6 +225,7 @@ struct PDivPoisArgs {  // divergence + per-mode Poisson solve
   B2Tabs b2;
   ModeTabs m;
   int ny;
+  int k0;
 };
 void launch_p_divpois(const PDivPoisArgs& a, cudaStream_t s);
 
@@ -233,8 +236,33 @@ struct PProjectArgs {  // projection + pressure update
   TdmaTabs t;
   double isx, isy, nu, inv_dt;
   int ny;
+  int k0;
 };
 void launch_p_project(const PProjectArgs& a, cudaStream_t s);
+
+// slab decomposition over kx: the y transforms run on complex rows of the kx slab, before (backward) and
+// after (forward) the x transform on y slabs -- the operators commute
+struct PYBackArgs {  // B_y S_y and B_y D_y S_y / sy of complex rows
+  Mat src;           // [rows, my] complex composite coefficients
+  Mat val, dy;       // [rows, ny] complex
+  const double *sd, *sl;
+  double isy;
+  DctTab t;
+};
+struct PYBackArgs3 {
+  PYBackArgs a[3];
+};
+void launch_p_ybackward(const PYBackArgs3& a, int nbatch, cudaStream_t s);
+
+struct PYFwdArgs {  // forward DCT-y of complex rows + dealias cut in y
+  Mat src, dst;     // [rows, ny] complex
+  int cut;
+  DctTab t;
+};
+struct PYFwdArgs3 {
+  PYFwdArgs a[3];
+};
+void launch_p_yforward(const PYFwdArgs3& a, int nbatch, cudaStream_t s);
 
 }  // namespace fk
 }  // namespace rp

@@ -38,6 +38,7 @@ __global__ void __launch_bounds__(PXCfg<LOG2N, LC>::NTHR, PXCfg<LOG2N, LC>::SMEM
   const double inv_n = 1.0 / (double)n;
   for (int pass = 0; pass < 2; ++pass) {
     const Mat& o = pass ? a.dx : a.val;
+    if (o.p == nullptr) continue;  // block-uniform
     for (int it = threadIdx.x; it < mkr * LC; it += C::NTHR) {
       const int k = it / LC, c = it % LC;
       const int ca = c0 + 2 * c, cb = ca + 1;
@@ -78,12 +79,27 @@ __global__ void __launch_bounds__(PXCfg<LOG2N, LC>::NTHR, PXCfg<LOG2N, LC>::SMEM
   cplx* tc = (cplx*)td;
   constexpr int n = C::N, mkr = n / 2 + 1;
   const int c0 = blockIdx.x * 2 * LC;
-  const int ncols = a.src.cols;
+  const int ncols = a.dst.cols;
   for (int it = threadIdx.x; it < n * LC; it += C::NTHR) {
     const int i = it / LC, c = it % LC;
     const int ca = c0 + 2 * c;
-    const double* row = a.src.p + (size_t)i * a.src.ld;
-    tc[cidx<LC>(i, c)] = mk(ca < ncols ? row[ca] : 0.0, ca + 1 < ncols ? row[ca + 1] : 0.0);
+    double va = 0.0, vb = 0.0;
+    if (a.u.p) {  // physical-space products (conv_term.rs:41) fused into the load
+      auto prod = [&](int cc) {
+        const size_t o = (size_t)i;
+        double gx = a.du.p[o * a.du.ld + cc], gy = a.dv.p[o * a.dv.ld + cc];
+        if (a.bcx.p) gx += a.bcx.p[o * a.bcx.ld + cc];
+        if (a.bcy.p) gy += a.bcy.p[o * a.bcy.ld + cc];
+        return fma(a.u.p[o * a.u.ld + cc], gx, a.v.p[o * a.v.ld + cc] * gy);
+      };
+      if (ca < ncols) va = prod(ca);
+      if (ca + 1 < ncols) vb = prod(ca + 1);
+    } else {
+      const double* row = a.src.p + (size_t)i * a.src.ld;
+      if (ca < ncols) va = row[ca];
+      if (ca + 1 < ncols) vb = row[ca + 1];
+    }
+    tc[cidx<LC>(i, c)] = mk(va, vb);
   }
   __syncthreads();
   fft<LC, LOG2N, C::NTHR, false, false>(tc, a.tw, nullptr);
@@ -150,7 +166,7 @@ __global__ void __launch_bounds__(YCfg<LOG2L, LC>::NTHR, 1) pk_hholtz(PHholtzArg
         double x = -a.dt * ldc(a.chat, r, j, part);                       // - dt * conv          (630, 651, 671)
         x += ldc_stencil(a.fld, r, j, part, a.sd, a.sl);                  // + to_ortho(field)    (625, 644, 663)
         if (a.mode == 0) {                                                // - dt/sx d/dx pres    (627)
-          const double ks = -a.dt * a.isx * (double)min(r, nrows - 1);
+          const double ks = -a.dt * a.isx * (double)(a.k0 + min(r, nrows - 1));
           x += ik_part(ks, ldc(a.pres, r, j, 0), ldc(a.pres, r, j, 1), part);
         } else if (a.mode == 1) {                                         // + dt * (that + tbc)  (648)
           x = fma(a.dt, ldc_stencil(a.tmp, r, j, part, a.tsd, a.tsl) + ldc(a.tbc, r, j, part), x);
@@ -198,7 +214,7 @@ __global__ void __launch_bounds__(YCfg<LOG2L, LC>::NTHR, 1) pk_divpois(PDivPoisA
   cheb_diff<LC, C::NTHR, C::CL>(td, -1, td, -1, n, a.isy, red);
   for (int it = threadIdx.x; it < n * C::LR; it += C::NTHR) {
     const int j = it / C::LR, l = it % C::LR, r = prow_of(r0, l), part = l & 1;
-    const double ks = a.isx * (double)min(r, nrows - 1);
+    const double ks = a.isx * (double)(a.k0 + min(r, nrows - 1));
     const double re = ldc_stencil(a.ux, r, j, 0, a.sd, a.sl), im = ldc_stencil(a.ux, r, j, 1, a.sd, a.sl);
     const double v = td[didx<LC>(j, l)] + ik_part(ks, re, im, part);
     td[didx<LC>(j, l)] = v;
@@ -209,7 +225,7 @@ __global__ void __launch_bounds__(YCfg<LOG2L, LC>::NTHR, 1) pk_divpois(PDivPoisA
   mode_solve<LC, C::NTHR, C::CL, C::ROWS, 1>(td, ti, n, a.b2, a.m, mu, red);
   tile_drain<LC, C::NTHR>(td, -1, m, [&](int j, int l, double v) {
     const int r = prow_of(r0, l);
-    if (r == 0 && j == 0) v = 0.0;  // pres[1].vhat[[0,0]] = 0   (navier.rs:714)
+    if (a.k0 + r == 0 && j == 0) v = 0.0;  // pres[1].vhat[[0,0]] = 0   (navier.rs:714)
     if (r < a.phi.rows) a.phi.p[((size_t)r * a.phi.ld + j) * 2 + (l & 1)] = v;
   });
 }
@@ -224,7 +240,7 @@ __global__ void __launch_bounds__(YCfg<LOG2L, LC>::NTHR, YCfg<LOG2L, LC>::SMEM1 
   // ux -= from_ortho_y(i k / sx S_y phi)   (navier.rs:683-695)
   tile_fill<LC, C::NTHR>(td, n, [&](int j, int l) {
     const int r = prow_of(r0, l);
-    const double ks = a.isx * (double)min(r, nrows - 1);
+    const double ks = a.isx * (double)(a.k0 + min(r, nrows - 1));
     return ik_part(ks, ldc_stencil(a.phi, r, j, 0, a.nsd, a.nsl), ldc_stencil(a.phi, r, j, 1, a.nsd, a.nsl), l & 1);
   });
   __syncthreads();
@@ -261,6 +277,52 @@ __global__ void __launch_bounds__(YCfg<LOG2L, LC>::NTHR, YCfg<LOG2L, LC>::SMEM1 
   tile_drain<LC, C::NTHR>(td, -1, m, [&](int j, int l, double v) {
     const int r = prow_of(r0, l);
     if (r < a.uy.rows) a.uy.p[((size_t)r * a.uy.ld + j) * 2 + (l & 1)] -= v;
+  });
+}
+
+// ---- y transforms on complex rows (slab decomposition over kx) ------------------------------------------
+template <int LOG2L, int LC>
+__global__ void __launch_bounds__(YCfg<LOG2L, LC>::NTHR, YCfg<LOG2L, LC>::SMEM1 > 110 * 1024 ? 1 : 2) pk_ybackward(PYBackArgs3 a3) {
+  typedef YCfg<LOG2L, LC> C;
+  const PYBackArgs& a = a3.a[blockIdx.y];
+  YK_SMEM(td, red);
+  const int r0 = blockIdx.x * LC;
+  constexpr int n = C::n, N = C::N;
+  auto fill = [&]() {
+    tile_fill<LC, C::NTHR>(td, n, [&](int j, int l) { return ldc_stencil(a.src, prow_of(r0, l), j, l & 1, a.sd, a.sl); });
+    __syncthreads();
+  };
+  auto drain = [&](const Mat& o) {
+    tile_drain<LC, C::NTHR>(td, N, n, [&](int j, int l, double v) {
+      const int r = prow_of(r0, l);
+      if (r < o.rows) o.p[((size_t)r * o.ld + j) * 2 + (l & 1)] = v;
+    });
+  };
+  fill();
+  if (a.val.p) {
+    dct_pow2<LC, LOG2L, C::NTHR, true>(td, a.t, red);
+    drain(a.val);
+    __syncthreads();
+    fill();
+  }
+  cheb_diff<LC, C::NTHR, C::CL>(td, -1, td, -1, n, a.isy, red);
+  dct_pow2<LC, LOG2L, C::NTHR, true>(td, a.t, red);
+  drain(a.dy);
+}
+
+template <int LOG2L, int LC>
+__global__ void __launch_bounds__(YCfg<LOG2L, LC>::NTHR, YCfg<LOG2L, LC>::SMEM1 > 110 * 1024 ? 1 : 2) pk_yforward(PYFwdArgs3 a3) {
+  typedef YCfg<LOG2L, LC> C;
+  const PYFwdArgs& a = a3.a[blockIdx.y];
+  YK_SMEM(td, red);
+  const int r0 = blockIdx.x * LC;
+  constexpr int n = C::n, N = C::N;
+  tile_fill<LC, C::NTHR>(td, n, [&](int j, int l) { return ldc(a.src, prow_of(r0, l), j, l & 1); });
+  __syncthreads();
+  dct_pow2<LC, LOG2L, C::NTHR, false>(td, a.t, red);
+  tile_drain<LC, C::NTHR>(td, N, n, [&](int j, int l, double v) {
+    const int r = prow_of(r0, l);
+    if (r < a.dst.rows) a.dst.p[((size_t)r * a.dst.ld + j) * 2 + (l & 1)] = (j < a.cut) ? v : 0.0;
   });
 }
 
@@ -301,7 +363,7 @@ bool px_supported(int n0) {
   } while (0)
 
 void launch_p_c2r(const PC2rArgs3& a, int nb, cudaStream_t s) { PX_LAUNCH(pk_c2r, a.a[0].src.cols, a.a[0].n, nb); }
-void launch_p_r2c(const PR2cArgs3& a, int nb, cudaStream_t s) { PX_LAUNCH(pk_r2c, a.a[0].src.cols, a.a[0].n, nb); }
+void launch_p_r2c(const PR2cArgs3& a, int nb, cudaStream_t s) { PX_LAUNCH(pk_r2c, a.a[0].dst.cols, a.a[0].n, nb); }
 
 #define YK_CASE_pk_hholtz(L, LCV) YK_CASE_BODY(pk_hholtz, L, LCV, 2, a)
 #define YK_CASE_pk_divpois(L, LCV) YK_CASE_BODY(pk_divpois, L, LCV, 2, a)
@@ -310,6 +372,10 @@ void launch_p_r2c(const PR2cArgs3& a, int nb, cudaStream_t s) { PX_LAUNCH(pk_r2c
 // complex rows: a block owns 2 rows -> the launch helper's "rows / 4" becomes "2 * rows / 4"
 void launch_p_hholtz(const PHholtzArgs3& a, int nb, cudaStream_t s) { YK_LAUNCH(pk_hholtz, true, 2 * a.a[0].chat.rows, a.a[0].ny, a, nb); }
 void launch_p_divpois(const PDivPoisArgs& a, cudaStream_t s) { YK_LAUNCH(pk_divpois, true, 2 * a.ux.rows, a.ny, a, 1); }
+#define YK_CASE_pk_ybackward(L, LCV) YK_CASE_BODY(pk_ybackward, L, LCV, 0, a)
+#define YK_CASE_pk_yforward(L, LCV) YK_CASE_BODY(pk_yforward, L, LCV, 0, a)
+void launch_p_ybackward(const PYBackArgs3& a, int nb, cudaStream_t s) { YK_LAUNCH(pk_ybackward, false, 2 * a.a[0].src.rows, a.a[0].t.n, a, nb); }
+void launch_p_yforward(const PYFwdArgs3& a, int nb, cudaStream_t s) { YK_LAUNCH(pk_yforward, false, 2 * a.a[0].src.rows, a.a[0].t.n, a, nb); }
 void launch_p_project(const PProjectArgs& a, cudaStream_t s) { YK_LAUNCH(pk_project, false, 2 * a.phi.rows, a.ny, a, 1); }
 
 }  // namespace fk

@@ -663,6 +663,7 @@ void Navier2D::build_step_periodic_fast() {
     for (int f = 0; f < 3; ++f) {
       fk::PR2cArgs& a = a3.a[f];
       a.src = mat_of(bconv_[f]), a.dst = mat_of(chat_[f]);
+      a.u = a.du = a.v = a.dv = a.bcx = a.bcy = none;
       a.cut = dealias ? (mk * 2) / 3 : mk;  // navier.rs:1028 with shape[0] = nx/2+1
       a.tw = bx.fft.plan.tw;
       a.n = nx;
@@ -684,6 +685,7 @@ void Navier2D::build_step_periodic_fast() {
     a.b2 = b2_of(byo);
     a.m = mode_of(solver[f]->ts.mode);
     a.ny = ny;
+    a.k0 = 0;
   }
   add_fast("rhs_hholtz_mode_y", 10 * fb, [this, h3]() { fk::launch_p_hholtz(h3, 2, stream); });
   {
@@ -699,6 +701,7 @@ void Navier2D::build_step_periodic_fast() {
     a.b2 = b2_of(byo);
     a.m = mode_of(solver[3]->ts.mode);
     a.ny = ny;
+    a.k0 = 0;
     add_fast("divergence_poisson_mode_y", 5 * fb, [this, a]() { fk::launch_p_divpois(a, stream); });
   }
   {  // ---- 7. projection + pressure update -----------------------------------------
@@ -708,8 +711,153 @@ void Navier2D::build_step_periodic_fast() {
     a.t = tdma_of(byu);
     a.isx = isx, a.isy = isy, a.nu = nu, a.inv_dt = 1.0 / dt;
     a.ny = ny;
+    a.k0 = 0;
     add_fast("project_pressure_update", 8 * fb, [this, a]() { fk::launch_p_project(a, stream); });
   }
+}
+
+// --------------------------------------------------------------------------
+// Slab decomposition of the periodic step over the Fourier modes kx.
+// Every per-mode operation (y transforms, stencils, rhs assembly, Helmholtz /
+// Poisson solves, projection) is local to a row slab [k0, k0 + mkl) of the
+// spectral arrays; the x FFT and the physical-space products are local to a
+// column slab [j0, j0 + nyl) of physical y.  One step = phase 1 (kx slab) ->
+// all-to-all of 6 arrays -> phase 2 (y slab) -> all-to-all of 3 arrays ->
+// phase 3 (kx slab).  The y transform is applied before the x transform in
+// the backward direction (the reference does x first, space2.rs:346-356; the
+// operators commute).  State arrays are the row slabs of this object's own
+// arrays; the exchange buffers belong to the caller.
+// --------------------------------------------------------------------------
+static fk::Mat row_slab(const Arr& a, int k0, int rows) {
+  return fk::Mat{a.d() + (size_t)k0 * a.ld * (a.cplx ? 2 : 1), a.ld, rows, a.cols};
+}
+static fk::Mat dense(double* p, int rows, int cols) { return fk::Mat{p, cols, rows, cols}; }
+
+void Navier2D::slab_phase1(int k0, int mkl, double* const out[6]) {
+  if (!periodic || !fk::px_supported(nx) || !fk::y_supported(ny)) throw Error(RP_ERR_INVALID, "slab phases need the specialised periodic kernels");
+  const Base &byu = *ux->sp.b1, &byt = *temp->sp.b1, &byo = *field->sp.b1;
+  Field2* flds[3] = {ux.get(), uy.get(), temp.get()};
+  const Base* bys[3] = {&byu, &byu, &byt};
+  fk::PYBackArgs3 a3;
+  for (int f = 0; f < 3; ++f) {
+    fk::PYBackArgs& a = a3.a[f];
+    a.src = row_slab(flds[f]->vhat, k0, mkl);
+    a.val = dense(out[f], mkl, ny);
+    a.dy = dense(out[3 + f], mkl, ny);
+    a.sd = bys[f]->d_sd.as<double>(), a.sl = bys[f]->d_sl.as<double>();
+    a.isy = 1.0 / scale[1];
+    a.t = dct_of(byo);
+  }
+  fk::launch_p_ybackward(a3, 3, stream);
+}
+
+void Navier2D::slab_phase2(int j0, int nyl, const double* const in[6], double* work, double* const out[3]) {
+  if (!periodic || !fk::px_supported(nx)) throw Error(RP_ERR_INVALID, "slab phases need the specialised periodic kernels");
+  const Base& bx = *ux->sp.b0;
+  const int mk = nx / 2 + 1;
+  const int dx_idx[3] = {2, 4, 6}, dy_idx[3] = {3, 5, 7};
+  const fk::Mat none{nullptr, 0, 0, 0};
+  auto phys = [&](int i) { return dense(work + (size_t)i * nx * nyl, nx, nyl); };
+  fk::PC2rArgs3 c3;
+  for (int f = 0; f < 3; ++f) {  // value and (ik/sx) derivative of ux, uy, T
+    fk::PC2rArgs& a = c3.a[f];
+    a.src = dense(const_cast<double*>(in[f]), mk, nyl);
+    a.val = f < 2 ? phys(f) : none;
+    a.dx = phys(dx_idx[f]);
+    a.isx = 1.0 / scale[0];
+    a.tw = bx.fft.plan.tw;
+    a.n = nx;
+  }
+  fk::launch_p_c2r(c3, 3, stream);
+  for (int f = 0; f < 3; ++f) {  // d/dy of ux, uy, T
+    fk::PC2rArgs& a = c3.a[f];
+    a.src = dense(const_cast<double*>(in[3 + f]), mk, nyl);
+    a.val = phys(dy_idx[f]);
+    a.dx = none;
+  }
+  fk::launch_p_c2r(c3, 3, stream);
+  fk::PR2cArgs3 r3;
+  for (int f = 0; f < 3; ++f) {  // products + r2c + dealias in kx
+    fk::PR2cArgs& a = r3.a[f];
+    a.src = none;
+    a.u = phys(0), a.du = phys(dx_idx[f]), a.v = phys(1), a.dv = phys(dy_idx[f]);
+    a.bcx = f == 2 ? fk::Mat{dxtbc_.d() + j0, dxtbc_.ld, nx, nyl} : none;
+    a.bcy = f == 2 ? fk::Mat{dytbc_.d() + j0, dytbc_.ld, nx, nyl} : none;
+    a.dst = dense(out[f], mk, nyl);
+    a.cut = dealias ? (mk * 2) / 3 : mk;
+    a.tw = bx.fft.plan.tw;
+    a.n = nx;
+  }
+  fk::launch_p_r2c(r3, 3, stream);
+}
+
+void Navier2D::slab_phase3(int k0, int mkl, const double* const in[3]) {
+  if (!periodic || !fk::px_supported(nx) || !fk::y_supported(ny)) throw Error(RP_ERR_INVALID, "slab phases need the specialised periodic kernels");
+  const Base &byu = *ux->sp.b1, &byt = *temp->sp.b1, &byn = *pres1->sp.b1, &byo = *field->sp.b1;
+  const double isx = 1.0 / scale[0], isy = 1.0 / scale[1];
+  Field2* flds[3] = {ux.get(), uy.get(), temp.get()};
+  const Base* bys[3] = {&byu, &byu, &byt};
+  fk::PYFwdArgs3 y3;
+  for (int f = 0; f < 3; ++f) {  // forward DCT-y + dealias in y -> chat_f rows
+    fk::PYFwdArgs& a = y3.a[f];
+    a.src = dense(const_cast<double*>(in[f]), mkl, ny);
+    a.dst = row_slab(chat_[f], k0, mkl);
+    a.cut = dealias ? (ny * 2) / 3 : ny;
+    a.t = dct_of(byo);
+  }
+  fk::launch_p_yforward(y3, 3, stream);
+  auto slab_mode = [&](const FdmaModeDev& md) {
+    fk::ModeTabs t = mode_of(md);
+    t.lam += k0;
+    t.inv += (size_t)k0 * md.inv_ld;
+    return t;
+  };
+  fk::PHholtzArgs3 h3;
+  for (int f = 0; f < 3; ++f) {
+    fk::PHholtzArgs& a = h3.a[f];
+    a.chat = row_slab(chat_[f], k0, mkl);
+    a.fld = row_slab(flds[f]->vhat, k0, mkl), a.out = a.fld;
+    a.pres = row_slab(pres0->vhat, k0, mkl), a.tmp = row_slab(temp->vhat, k0, mkl);
+    a.tbc = row_slab(tbc_ortho_, k0, mkl), a.bcdiff = row_slab(bcdiff_, k0, mkl);
+    a.sd = bys[f]->d_sd.as<double>(), a.sl = bys[f]->d_sl.as<double>();
+    a.tsd = byt.d_sd.as<double>(), a.tsl = byt.d_sl.as<double>();
+    a.mode = f;
+    a.dt = dt, a.isx = isx, a.isy = isy;
+    a.b2 = b2_of(byo);
+    a.m = slab_mode(solver[f]->ts.mode);
+    a.ny = ny;
+    a.k0 = k0;
+  }
+  fk::launch_p_hholtz(h3, 2, stream);
+  {
+    fk::PHholtzArgs3 t3 = h3;
+    t3.a[0] = h3.a[2];
+    fk::launch_p_hholtz(t3, 1, stream);
+  }
+  {
+    fk::PDivPoisArgs a;
+    a.ux = row_slab(ux->vhat, k0, mkl), a.uy = row_slab(uy->vhat, k0, mkl);
+    a.div = row_slab(div_, k0, mkl), a.phi = row_slab(pres1->vhat, k0, mkl);
+    a.sd = byu.d_sd.as<double>(), a.sl = byu.d_sl.as<double>();
+    a.isx = isx, a.isy = isy;
+    a.b2 = b2_of(byo);
+    a.m = slab_mode(solver[3]->ts.mode);
+    a.ny = ny;
+    a.k0 = k0;
+    fk::launch_p_divpois(a, stream);
+  }
+  {
+    fk::PProjectArgs a;
+    a.phi = row_slab(pres1->vhat, k0, mkl), a.ux = row_slab(ux->vhat, k0, mkl), a.uy = row_slab(uy->vhat, k0, mkl);
+    a.div = row_slab(div_, k0, mkl), a.pres = row_slab(pres0->vhat, k0, mkl);
+    a.nsd = byn.d_sd.as<double>(), a.nsl = byn.d_sl.as<double>();
+    a.t = tdma_of(byu);
+    a.isx = isx, a.isy = isy, a.nu = nu, a.inv_dt = 1.0 / dt;
+    a.ny = ny;
+    a.k0 = k0;
+    fk::launch_p_project(a, stream);
+  }
+  time += dt;
 }
 
 void Navier2D::build_step_periodic() {

@@ -1,0 +1,126 @@
+"""Slab-decomposed periodic Navier2D over the GPUs of one node (BASELINE config 5).
+
+One process per GPU (torch.distributed, NCCL over NVLink; gloo with the CPU emulation in the tests).
+The spectral arrays `[nx/2+1, .]` are split over the Fourier modes kx (row slabs): every per-mode
+operation -- y transforms, stencils, rhs assembly, the per-mode Helmholtz / Poisson solves
+(hholtz.rs:156-197, poisson.rs:131-149), projection -- is local to a rank.  The x FFT and the
+physical-space products (conv_term.rs:41) need full x lines, so they run on column slabs of physical
+y; the two layouts are connected by an all-to-all:
+
+    phase 1 (kx slab)   B_y S_y and B_y D_y S_y of ux, uy, temp                   rp_navier_slab_phase1
+    all-to-all          6 complex arrays  [mk_loc, ny] -> [mk, ny_loc]
+    phase 2 (y slab)    c2r along x, products, r2c along x + dealias              rp_navier_slab_phase2
+    all-to-all          3 complex arrays  [mk, ny_loc] -> [mk_loc, ny]
+    phase 3 (kx slab)   forward DCT-y + dealias, rhs, solves, projection          rp_navier_slab_phase3
+
+The y transform is applied before the x transform in the backward direction (the reference does x
+first, space2.rs:346-356; the operators commute, the results differ by rounding only).
+
+Every rank holds a full `Navier2D` (set-up, initial conditions and diagnostics reuse the single-GPU
+code; 21 GB at 8192x8193) but steps only its own rows; `gather_state()` makes the full arrays
+consistent again on every rank before diagnostics are evaluated.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def split(n, parts):
+    """Sizes and offsets of `parts` nearly equal consecutive chunks of range(n) (remainder to the first ranks)."""
+    base, rem = divmod(n, parts)
+    sizes = [base + (1 if p < rem else 0) for p in range(parts)]
+    offs = [sum(sizes[:p]) for p in range(parts)]
+    return sizes, offs
+
+
+class Navier2DSlab:
+    def __init__(self, nav, group=None):
+        if not nav.periodic:
+            raise ValueError("the slab decomposition is defined for Navier2D.new_periodic (Fourier x Chebyshev)")
+        self.nav = nav
+        self.lib = nav._lib
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.nx, self.ny = nav.nx, nav.ny
+        self.mk = self.nx // 2 + 1
+        self.ksz, self.koff = split(self.mk, self.world)
+        self.jsz, self.joff = split(self.ny, self.world)
+        if min(self.ksz) < 1 or min(self.jsz) < 1:
+            raise ValueError("more ranks than Fourier modes / grid columns")
+        self.k0, self.mkl = self.koff[self.rank], self.ksz[self.rank]
+        self.j0, self.nyl = self.joff[self.rank], self.jsz[self.rank]
+        dev = "cpu" if self.lib.emulated else torch.device("cuda", torch.cuda.current_device())
+        f64 = dict(dtype=torch.float64, device=dev)
+        mk, ny, nx, mkl, nyl = self.mk, self.ny, self.nx, self.mkl, self.nyl
+        # exchange buffers (interleaved complex = trailing dimension 2)
+        self.s1 = [torch.zeros(mkl * ny * 2, **f64) for _ in range(6)]    # phase-1 output   [mkl, ny]
+        self.x_in = [torch.zeros(mk * nyl * 2, **f64) for _ in range(6)]  # after exchange   [mk, nyl]
+        self.x_out = [torch.zeros(mk * nyl * 2, **f64) for _ in range(3)]  # phase-2 output  [mk, nyl]
+        self.s3 = [torch.zeros(mkl * ny * 2, **f64) for _ in range(3)]    # phase-3 input    [mkl, ny]
+        self.pack = torch.zeros(mkl * ny * 2, **f64)                      # send / receive staging
+        self.work = torch.zeros(8 * nx * nyl, **f64)
+        self._p = lambda ts: (C.c_void_p * len(ts))(*[t.data_ptr() for t in ts])
+        # NVLink egress of this rank per step: 6 arrays rows->cols, 3 arrays cols->rows (16 B per complex element)
+        self.bytes_exchanged_per_step = 16 * (6 * mkl * (ny - nyl) + 3 * nyl * (mk - mkl))
+
+    # -- exchanges ---------------------------------------------------------------------------------
+    def _rows_to_cols(self, src, dst):
+        """[mkl, ny] complex on every rank -> [mk, nyl]: column blocks are packed, row blocks arrive in rank order."""
+        if self.world == 1:
+            dst.copy_(src)
+            return
+        s = src.view(self.mkl, self.ny, 2)
+        send_split, off = [], 0
+        for q in range(self.world):
+            cnt = self.mkl * self.jsz[q] * 2
+            self.pack[off:off + cnt].view(self.mkl, self.jsz[q], 2).copy_(s[:, self.joff[q]:self.joff[q] + self.jsz[q], :])
+            send_split.append(cnt)
+            off += cnt
+        recv_split = [self.ksz[q] * self.nyl * 2 for q in range(self.world)]
+        dist.all_to_all_single(dst, self.pack, recv_split, send_split, group=self.group)
+
+    def _cols_to_rows(self, src, dst):
+        """[mk, nyl] complex -> [mkl, ny]: row blocks leave as they are, column blocks are unpacked on arrival."""
+        if self.world == 1:
+            dst.copy_(src)
+            return
+        send_split = [self.ksz[q] * self.nyl * 2 for q in range(self.world)]
+        recv_split = [self.mkl * self.jsz[q] * 2 for q in range(self.world)]
+        dist.all_to_all_single(self.pack, src, recv_split, send_split, group=self.group)
+        d = dst.view(self.mkl, self.ny, 2)
+        off = 0
+        for q in range(self.world):
+            cnt = recv_split[q]
+            d[:, self.joff[q]:self.joff[q] + self.jsz[q], :].copy_(self.pack[off:off + cnt].view(self.mkl, self.jsz[q], 2))
+            off += cnt
+
+    # -- time stepping -------------------------------------------------------------------------------
+    def update(self, nsteps=1):
+        lib, h = self.lib, self.nav._h
+        for _ in range(int(nsteps)):
+            lib.call("rp_navier_slab_phase1", h, self.k0, self.mkl, self._p(self.s1))
+            for a in range(6):
+                self._rows_to_cols(self.s1[a], self.x_in[a])
+            lib.call("rp_navier_slab_phase2", h, self.j0, self.nyl, self._p(self.x_in), C.c_void_p(self.work.data_ptr()), self._p(self.x_out))
+            for a in range(3):
+                self._cols_to_rows(self.x_out[a], self.s3[a])
+            lib.call("rp_navier_slab_phase3", h, self.k0, self.mkl, self._p(self.s3))
+
+    def sync(self):
+        self.nav.sync()
+        if not self.lib.emulated:
+            torch.cuda.synchronize()
+
+    def gather_state(self):
+        """Make temp / ux / uy / pres vhat of the full per-rank model consistent (each rank owns rows [k0, k0+mkl))."""
+        self.sync()
+        if self.world == 1:
+            return
+        for f in (self.nav.temp, self.nav.ux, self.nav.uy, self.nav.pres[0], self.nav.pres[1]):
+            mine = np.ascontiguousarray(f.vhat[self.k0:self.k0 + self.mkl])
+            parts = [None] * self.world
+            dist.all_gather_object(parts, mine, group=self.group)
+            f.vhat = np.concatenate(parts, axis=0)
