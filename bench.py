@@ -175,7 +175,7 @@ def run_ours(args, wl, rank, world, local_rank):
     if periodic and (world > 1 or args.parallel == "slab") and args.parallel != "replicas":
         # strong scaling: ONE problem, slab-decomposed over the Fourier modes kx, NCCL all-to-all transposes
         from rustpde_b200.slab import Navier2DSlab
-        slab = Navier2DSlab(nav)
+        slab = Navier2DSlab(nav, transport=args.transport)
     stepper = slab if slab is not None else nav
     stepper.update(W)
     stepper.sync()
@@ -211,7 +211,7 @@ def run_ours(args, wl, rank, world, local_rank):
                 "metric": METRIC, "value": steps_per_s, "unit": "steps/s", "n_gpus": world, "steps": args.steps, "warmup": W,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic (set_velocity(0.2,1,1)+set_temperature(0.2,1,1), no RNG)",
-                "config": {"workload": desc, "parallelism": "kx slabs x%d, 9 all-to-all transposes per step (NCCL)" % world,
+                "config": {"workload": desc, "parallelism": "kx slabs x%d, 9 transposes per step, %s" % (world, "fused into the kernels over NVLink peer memory (CUDA IPC)" if slab.transport == "p2p" else "NCCL all_to_all"),
                            "l2": "working set >> 126 MB L2, no flush needed", "cuda_graph": False, "setup_s": round(t_setup, 2),
                            "div_norm_after": div, "nvlink_egress_bytes_per_rank_per_step": slab.bytes_exchanged_per_step},
                 "clocks": clocks, "e2e": None, "gpu_launches": launches * args.steps, "roofline": None, "cpu_baseline": None,
@@ -340,6 +340,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="confined2048", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--transport", default="p2p", choices=["p2p", "collective"],
+                    help="slab mode: fused transposes over NVLink peer memory (p2p) or NCCL all_to_all (collective)")
     ap.add_argument("--parallel", default="auto", choices=["auto", "replicas", "slab"],
                     help="N > 1: independent replicas (confined path) or one slab-decomposed problem (periodic path)")
     args = ap.parse_args()

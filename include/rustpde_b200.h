@@ -135,6 +135,20 @@ int rp_navier_set_graph(rp_navier_t* h, int on);                               /
 int rp_navier_slab_phase1(rp_navier_t* h, int k0, int mkl, double* const* out6);
 int rp_navier_slab_phase2(rp_navier_t* h, int j0, int nyl, const double* const* in6, double* work, double* const* out3);
 int rp_navier_slab_phase3(rp_navier_t* h, int k0, int mkl, const double* const* in3);
+/* Fused transposes over NVLink peer memory: instead of dense outputs + all-to-all, the phase-1 / phase-2 kernels
+   store every element straight into the buffer of the rank that owns it (buffers mapped with CUDA IPC).
+     joff[world+1] / koff[world+1]: first physical-y column / Fourier mode owned by each rank;
+     peers[a * world + q]: device address of array a (phase 1: the six in6 arrays, phase 2: the three in3 arrays)
+     on rank q, as mapped into THIS process.  The caller separates the phases with a cross-rank barrier. */
+int rp_navier_slab_phase1_p2p(rp_navier_t* h, int k0, int mkl, int world, const int* joff, double* const* peers);
+int rp_navier_slab_phase2_p2p(rp_navier_t* h, int j0, int nyl, const double* const* in6, double* work, int world,
+                              const int* koff, double* const* peers);
+/* device memory shared between the processes of one node (cudaMalloc + cudaIpc*MemHandle) */
+int rp_dev_alloc(size_t bytes, void** out);
+int rp_dev_free(void* p);
+int rp_ipc_export(void* p, unsigned char handle[64]);
+int rp_ipc_open(const unsigned char handle[64], void** out);
+int rp_ipc_close(void* p);
 /* which kernels serve update(): specialised = 1 -> hand-specialised x/y pass kernels (else generic lane programs);
    split_gemm = 1 -> pressure Poisson runs the even/odd parity-split GEMM pairs (exactly checkerboard set-up data) */
 int rp_navier_kernel_path(rp_navier_t* h, int* specialised, int* split_gemm);

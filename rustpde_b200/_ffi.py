@@ -71,6 +71,13 @@ _SIGS = {
     "rp_navier_slab_phase1": [vp, C.c_int, C.c_int, C.POINTER(C.c_void_p)],
     "rp_navier_slab_phase2": [vp, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_void_p, C.POINTER(C.c_void_p)],
     "rp_navier_slab_phase3": [vp, C.c_int, C.c_int, C.POINTER(C.c_void_p)],
+    "rp_navier_slab_phase1_p2p": [vp, C.c_int, C.c_int, C.c_int, c_int_p, C.POINTER(C.c_void_p)],
+    "rp_navier_slab_phase2_p2p": [vp, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_void_p, C.c_int, c_int_p, C.POINTER(C.c_void_p)],
+    "rp_dev_alloc": [C.c_size_t, vpp],
+    "rp_dev_free": [vp],
+    "rp_ipc_export": [vp, C.c_char_p],
+    "rp_ipc_open": [C.c_char_p, vpp],
+    "rp_ipc_close": [vp],
     "rp_navier_profile": [vp, C.c_int, c_double_p, C.c_size_t, c_int_p],
     "rp_navier_op_info": [vp, C.c_int, C.c_char_p, C.c_size_t, c_double_p, c_double_p],
 }

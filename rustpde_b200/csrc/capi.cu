@@ -368,6 +368,62 @@ int rp_navier_slab_phase2(rp_navier_t* h, int j0, int nyl, const double* const* 
     N.slab_phase2(j0, nyl, in6, work, out3);
   });
 }
+int rp_navier_slab_phase1_p2p(rp_navier_t* h, int k0, int mkl, int world, const int* joff, double* const* peers) {
+  NAV_GUARD({
+    need(world >= 1 && world <= 8 && joff && peers && mkl > 0 && k0 >= 0 && k0 + mkl <= N.nx / 2 + 1, RP_ERR_INVALID, "slab_phase1_p2p: bad arguments");
+    N.slab_phase1(k0, mkl, nullptr, world, joff, peers);
+  });
+}
+int rp_navier_slab_phase2_p2p(rp_navier_t* h, int j0, int nyl, const double* const* in6, double* work, int world, const int* koff,
+                              double* const* peers) {
+  NAV_GUARD({
+    need(world >= 1 && world <= 8 && koff && peers && in6 && work && nyl > 0 && j0 >= 0 && j0 + nyl <= N.ny, RP_ERR_INVALID, "slab_phase2_p2p: bad arguments");
+    N.slab_phase2(j0, nyl, in6, work, nullptr, world, koff, peers);
+  });
+}
+int rp_dev_alloc(size_t bytes, void** out) {
+  return guard([&] {
+    need(out != nullptr, RP_ERR_INVALID, "null out pointer");
+    *out = rt::dmalloc(bytes);
+  });
+}
+int rp_dev_free(void* p) {
+  return guard([&] { rt::dfree(p); });
+}
+int rp_ipc_export(void* p, unsigned char handle[64]) {
+  return guard([&] {
+    need(p && handle, RP_ERR_INVALID, "null argument");
+#ifndef RP_EMU
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    cudaIpcMemHandle_t hd;
+    RP_CUDA_CHECK(cudaIpcGetMemHandle(&hd, p));
+    memcpy(handle, &hd, 64);
+#else
+    throw rp::Error(RP_ERR_INVALID, "CUDA IPC is not available in the emulation");
+#endif
+  });
+}
+int rp_ipc_open(const unsigned char handle[64], void** out) {
+  return guard([&] {
+    need(out && handle, RP_ERR_INVALID, "null argument");
+#ifndef RP_EMU
+    cudaIpcMemHandle_t hd;
+    memcpy(&hd, handle, 64);
+    RP_CUDA_CHECK(cudaIpcOpenMemHandle(out, hd, cudaIpcMemLazyEnablePeerAccess));
+#else
+    throw rp::Error(RP_ERR_INVALID, "CUDA IPC is not available in the emulation");
+#endif
+  });
+}
+int rp_ipc_close(void* p) {
+  return guard([&] {
+#ifndef RP_EMU
+    if (p) RP_CUDA_CHECK(cudaIpcCloseMemHandle(p));
+#else
+    (void)p;
+#endif
+  });
+}
 int rp_navier_slab_phase3(rp_navier_t* h, int k0, int mkl, const double* const* in3) {
   NAV_GUARD({
     need(in3 != nullptr && mkl > 0 && k0 >= 0 && k0 + mkl <= N.nx / 2 + 1, RP_ERR_INVALID, "slab_phase3: bad row range");

@@ -171,6 +171,14 @@ struct XProjectArgs {  // a1 = from_ortho_x(D_x S_x phi)/sx, a2 = from_ortho_x(S
 };
 void launch_x_project(const XProjectArgs& a, cudaStream_t s);
 
+// Destination of a fused transpose: part q (a peer GPU's buffer, mapped through CUDA IPC, or a local one) owns
+// the global indices [beg[q], beg[q+1]) along the scattered axis.  nparts == 0: no scatter (dense output).
+struct Scatter {
+  double* ptr[8];
+  int beg[9];
+  int nparts;
+};
+
 // ---- periodic path (fast_p.cu): complex arrays are passed as Mat with ld / cols in complex units ----
 bool px_supported(int n0);
 
@@ -193,6 +201,10 @@ struct PR2cArgs {  // r2c along x + dealias cut
   int cut;         // first zeroed kx
   const double2* tw;
   int n;
+  // fused transpose (slab decomposition): row k goes to the peer that owns it, into its [rows_q, ny] array at
+  // columns j0 + c (NVLink stores from inside the kernel instead of a separate all-to-all)
+  Scatter sdst;
+  int j0, ny;
 };
 struct PR2cArgs3 {
   PR2cArgs a[3];
@@ -248,6 +260,9 @@ struct PYBackArgs {  // B_y S_y and B_y D_y S_y / sy of complex rows
   const double *sd, *sl;
   double isy;
   DctTab t;
+  // fused transpose: column j goes to the peer that owns it, into its [mk, ny_q] array at row k0 + r
+  Scatter sval, sdy;
+  int k0;
 };
 struct PYBackArgs3 {
   PYBackArgs a[3];

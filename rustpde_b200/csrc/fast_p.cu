@@ -16,6 +16,13 @@
 namespace rp {
 namespace fk {
 
+// rank that owns global index i of a scattered axis
+FK_DEV int owner_of(const Scatter& sc, int i) {
+  int q = 0;
+  while (q + 1 < sc.nparts && i >= sc.beg[q + 1]) ++q;
+  return q;
+}
+
 // ---- x kernels ---------------------------------------------------------------------------------
 template <int LOG2N, int LC_>
 struct PXCfg {
@@ -111,8 +118,15 @@ __global__ void __launch_bounds__(PXCfg<LOG2N, LC>::NTHR, PXCfg<LOG2N, LC>::SMEM
     const cplx zm = mk(zc.x, -zc.y);
     const cplx s = cadd(zk, zm), d = csub(zk, zm);
     const double h = (k < a.cut) ? 0.5 : 0.0;  // dealias: modes kx >= cut are zeroed
-    if (ca < ncols) dst[(size_t)k * a.dst.ld + ca] = mk(h * s.x, h * s.y);
-    if (cb < ncols) dst[(size_t)k * a.dst.ld + cb] = mk(h * d.y, -h * d.x);
+    cplx* row;
+    if (a.sdst.nparts > 0) {  // fused transpose: row k lives on the rank that owns mode k
+      const int q = owner_of(a.sdst, k);
+      row = (cplx*)a.sdst.ptr[q] + (size_t)(k - a.sdst.beg[q]) * a.ny + a.j0;
+    } else {
+      row = dst + (size_t)k * a.dst.ld;
+    }
+    if (ca < ncols) row[ca] = mk(h * s.x, h * s.y);
+    if (cb < ncols) row[cb] = mk(h * d.y, -h * d.x);
   }
 }
 
@@ -292,22 +306,28 @@ __global__ void __launch_bounds__(YCfg<LOG2L, LC>::NTHR, YCfg<LOG2L, LC>::SMEM1 
     tile_fill<LC, C::NTHR>(td, n, [&](int j, int l) { return ldc_stencil(a.src, prow_of(r0, l), j, l & 1, a.sd, a.sl); });
     __syncthreads();
   };
-  auto drain = [&](const Mat& o) {
+  auto drain = [&](const Mat& o, const Scatter& sc) {
     tile_drain<LC, C::NTHR>(td, N, n, [&](int j, int l, double v) {
       const int r = prow_of(r0, l);
-      if (r < o.rows) o.p[((size_t)r * o.ld + j) * 2 + (l & 1)] = v;
+      if (r >= o.rows) return;
+      if (sc.nparts > 0) {  // fused transpose: column j lives on the rank that owns it
+        const int q = owner_of(sc, j);
+        sc.ptr[q][((size_t)(a.k0 + r) * (sc.beg[q + 1] - sc.beg[q]) + (j - sc.beg[q])) * 2 + (l & 1)] = v;
+      } else {
+        o.p[((size_t)r * o.ld + j) * 2 + (l & 1)] = v;
+      }
     });
   };
   fill();
   if (a.val.p) {
     dct_pow2<LC, LOG2L, C::NTHR, true>(td, a.t, red);
-    drain(a.val);
+    drain(a.val, a.sval);
     __syncthreads();
     fill();
   }
   cheb_diff<LC, C::NTHR, C::CL>(td, -1, td, -1, n, a.isy, red);
   dct_pow2<LC, LOG2L, C::NTHR, true>(td, a.t, red);
-  drain(a.dy);
+  drain(a.dy, a.sdy);
 }
 
 template <int LOG2L, int LC>

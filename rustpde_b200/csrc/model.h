@@ -209,8 +209,10 @@ class Navier2D {
   }
   void profile(int reps, std::vector<double>& ms);
   // slab decomposition over kx (periodic path; rustpde_b200/slab.py drives the phases and owns the exchange buffers)
-  void slab_phase1(int k0, int mkl, double* const out[6]);
-  void slab_phase2(int j0, int nyl, const double* const in[6], double* work, double* const out[3]);
+  // world > 0: fused transposes -- the outputs are scattered straight into the peers' buffers (peers[a * world + q])
+  void slab_phase1(int k0, int mkl, double* const out[6], int world = 0, const int* joff = nullptr, double* const* peers = nullptr);
+  void slab_phase2(int j0, int nyl, const double* const in[6], double* work, double* const out[3], int world = 0,
+                   const int* koff = nullptr, double* const* peers = nullptr);
   void slab_phase3(int k0, int mkl, const double* const in[3]);
   void set_graph(bool on) {
     use_graph_ = on;

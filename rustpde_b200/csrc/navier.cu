@@ -664,6 +664,7 @@ void Navier2D::build_step_periodic_fast() {
       fk::PR2cArgs& a = a3.a[f];
       a.src = mat_of(bconv_[f]), a.dst = mat_of(chat_[f]);
       a.u = a.du = a.v = a.dv = a.bcx = a.bcy = none;
+      a.sdst.nparts = 0, a.j0 = 0, a.ny = ny;
       a.cut = dealias ? (mk * 2) / 3 : mk;  // navier.rs:1028 with shape[0] = nx/2+1
       a.tw = bx.fft.plan.tw;
       a.n = nx;
@@ -733,7 +734,18 @@ static fk::Mat row_slab(const Arr& a, int k0, int rows) {
 }
 static fk::Mat dense(double* p, int rows, int cols) { return fk::Mat{p, cols, rows, cols}; }
 
-void Navier2D::slab_phase1(int k0, int mkl, double* const out[6]) {
+static fk::Scatter scatter_of(int world, const int* beg, double* const* peers) {
+  fk::Scatter sc;
+  sc.nparts = 0;
+  if (world <= 0 || !beg || !peers) return sc;
+  if (world > 8) throw Error(RP_ERR_INVALID, "at most 8 peers");
+  sc.nparts = world;
+  for (int q = 0; q < world; ++q) sc.ptr[q] = peers[q], sc.beg[q] = beg[q];
+  sc.beg[world] = beg[world];
+  return sc;
+}
+
+void Navier2D::slab_phase1(int k0, int mkl, double* const out[6], int world, const int* joff, double* const* peers) {
   if (!periodic || !fk::px_supported(nx) || !fk::y_supported(ny)) throw Error(RP_ERR_INVALID, "slab phases need the specialised periodic kernels");
   const Base &byu = *ux->sp.b1, &byt = *temp->sp.b1, &byo = *field->sp.b1;
   Field2* flds[3] = {ux.get(), uy.get(), temp.get()};
@@ -742,8 +754,12 @@ void Navier2D::slab_phase1(int k0, int mkl, double* const out[6]) {
   for (int f = 0; f < 3; ++f) {
     fk::PYBackArgs& a = a3.a[f];
     a.src = row_slab(flds[f]->vhat, k0, mkl);
-    a.val = dense(out[f], mkl, ny);
-    a.dy = dense(out[3 + f], mkl, ny);
+    a.val = dense(out ? out[f] : nullptr, mkl, ny);
+    a.dy = dense(out ? out[3 + f] : nullptr, mkl, ny);
+    if (!out) a.val.p = a.dy.p = ux->vhat.d();  // non-null marker: the outputs go to the peers
+    a.sval = scatter_of(world, joff, peers ? peers + (size_t)f * world : nullptr);
+    a.sdy = scatter_of(world, joff, peers ? peers + (size_t)(3 + f) * world : nullptr);
+    a.k0 = k0;
     a.sd = bys[f]->d_sd.as<double>(), a.sl = bys[f]->d_sl.as<double>();
     a.isy = 1.0 / scale[1];
     a.t = dct_of(byo);
@@ -751,7 +767,8 @@ void Navier2D::slab_phase1(int k0, int mkl, double* const out[6]) {
   fk::launch_p_ybackward(a3, 3, stream);
 }
 
-void Navier2D::slab_phase2(int j0, int nyl, const double* const in[6], double* work, double* const out[3]) {
+void Navier2D::slab_phase2(int j0, int nyl, const double* const in[6], double* work, double* const out[3], int world,
+                           const int* koff, double* const* peers) {
   if (!periodic || !fk::px_supported(nx)) throw Error(RP_ERR_INVALID, "slab phases need the specialised periodic kernels");
   const Base& bx = *ux->sp.b0;
   const int mk = nx / 2 + 1;
@@ -783,10 +800,12 @@ void Navier2D::slab_phase2(int j0, int nyl, const double* const in[6], double* w
     a.u = phys(0), a.du = phys(dx_idx[f]), a.v = phys(1), a.dv = phys(dy_idx[f]);
     a.bcx = f == 2 ? fk::Mat{dxtbc_.d() + j0, dxtbc_.ld, nx, nyl} : none;
     a.bcy = f == 2 ? fk::Mat{dytbc_.d() + j0, dytbc_.ld, nx, nyl} : none;
-    a.dst = dense(out[f], mk, nyl);
+    a.dst = dense(out ? out[f] : nullptr, mk, nyl);
     a.cut = dealias ? (mk * 2) / 3 : mk;
     a.tw = bx.fft.plan.tw;
     a.n = nx;
+    a.sdst = scatter_of(world, koff, peers ? peers + (size_t)f * world : nullptr);
+    a.j0 = j0, a.ny = ny;
   }
   fk::launch_p_r2c(r3, 3, stream);
 }

@@ -36,7 +36,12 @@ def split(n, parts):
 
 
 class Navier2DSlab:
-    def __init__(self, nav, group=None):
+    """transport = "collective": dense phase outputs + all_to_all_single (NCCL / gloo).
+    transport = "p2p": fused transposes -- the phase-1 / phase-2 kernels store every element straight into the
+    buffer of the rank that owns it over NVLink peer memory (buffers shared with CUDA IPC); the phases are
+    separated by a stream-ordered one-element all-reduce instead of nine all-to-alls and their pack copies."""
+
+    def __init__(self, nav, group=None, transport="collective"):
         if not nav.periodic:
             raise ValueError("the slab decomposition is defined for Navier2D.new_periodic (Fourier x Chebyshev)")
         self.nav = nav
@@ -63,6 +68,9 @@ class Navier2DSlab:
         self.pack = torch.zeros(mkl * ny * 2, **f64)                      # send / receive staging
         self.work = torch.zeros(8 * nx * nyl, **f64)
         self._p = lambda ts: (C.c_void_p * len(ts))(*[t.data_ptr() for t in ts])
+        self.transport = transport if self.world > 1 else "collective"
+        if self.transport == "p2p":
+            self._setup_p2p(f64)
         # NVLink egress of this rank per step: 6 arrays rows->cols, 3 arrays cols->rows (16 B per complex element)
         self.bytes_exchanged_per_step = 16 * (6 * mkl * (ny - nyl) + 3 * nyl * (mk - mkl))
 
@@ -97,9 +105,62 @@ class Navier2DSlab:
             d[:, self.joff[q]:self.joff[q] + self.jsz[q], :].copy_(self.pack[off:off + cnt].view(self.mkl, self.jsz[q], 2))
             off += cnt
 
+    # -- fused transposes over peer memory ---------------------------------------------------------
+    def _setup_p2p(self, f64):
+        lib, W = self.lib, self.world
+        mk, ny = self.mk, self.ny
+        nbytes = lambda q: 16 * (6 * mk * self.jsz[q] + 3 * self.ksz[q] * ny)
+        base = C.c_void_p()
+        lib.call("rp_dev_alloc", nbytes(self.rank), C.byref(base))
+        handle = C.create_string_buffer(64)
+        lib.call("rp_ipc_export", base, handle)
+        handles = [None] * W
+        dist.all_gather_object(handles, handle.raw, group=self.group)
+        self._peer_base, self._opened = [], []
+        for q in range(W):
+            if q == self.rank:
+                self._peer_base.append(base.value)
+            else:
+                ptr = C.c_void_p()
+                lib.call("rp_ipc_open", C.create_string_buffer(handles[q], 64), C.byref(ptr))
+                self._peer_base.append(ptr.value)
+                self._opened.append(ptr)
+        self._own = base
+        xin = lambda q, a: self._peer_base[q] + 16 * a * mk * self.jsz[q]
+        s3 = lambda q, f: self._peer_base[q] + 16 * (6 * mk * self.jsz[q] + f * self.ksz[q] * ny)
+        self._peers1 = (C.c_void_p * (6 * W))(*[xin(q, a) for a in range(6) for q in range(W)])
+        self._peers2 = (C.c_void_p * (3 * W))(*[s3(q, f) for f in range(3) for q in range(W)])
+        self._in6 = (C.c_void_p * 6)(*[xin(self.rank, a) for a in range(6)])
+        self._in3 = (C.c_void_p * 3)(*[s3(self.rank, f) for f in range(3)])
+        self._joff = (C.c_int * (W + 1))(*(self.joff + [ny]))
+        self._koff = (C.c_int * (W + 1))(*(self.koff + [mk]))
+        self._flag = torch.zeros(1, **f64)
+        dist.barrier(group=self.group)
+
+    def _fence(self):
+        # stream-ordered: completes on this rank only after every rank's preceding kernels have finished
+        dist.all_reduce(self._flag, group=self.group)
+
+    def close(self):
+        if getattr(self, "_own", None) is not None:
+            self.sync()
+            dist.barrier(group=self.group)
+            for p in self._opened:
+                self.lib.call("rp_ipc_close", p)
+            self.lib.call("rp_dev_free", self._own)
+            self._own = None
+
     # -- time stepping -------------------------------------------------------------------------------
     def update(self, nsteps=1):
         lib, h = self.lib, self.nav._h
+        if self.transport == "p2p":
+            for _ in range(int(nsteps)):
+                lib.call("rp_navier_slab_phase1_p2p", h, self.k0, self.mkl, self.world, self._joff, self._peers1)
+                self._fence()
+                lib.call("rp_navier_slab_phase2_p2p", h, self.j0, self.nyl, self._in6, C.c_void_p(self.work.data_ptr()), self.world, self._koff, self._peers2)
+                self._fence()
+                lib.call("rp_navier_slab_phase3", h, self.k0, self.mkl, self._in3)
+            return
         for _ in range(int(nsteps)):
             lib.call("rp_navier_slab_phase1", h, self.k0, self.mkl, self._p(self.s1))
             for a in range(6):

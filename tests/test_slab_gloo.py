@@ -65,3 +65,37 @@ def test_split():
     assert split(4097, 8) == ([513] + [512] * 7, [0, 513, 1025, 1537, 2049, 2561, 3073, 3585])
     assert split(8193, 8)[0] == [1025] + [1024] * 7
     assert sum(split(17, 3)[0]) == 17 and split(17, 3)[1] == [0, 6, 12]
+
+
+@pytest.mark.parametrize("world,nx,ny", [(2, 32, 33), (3, 32, 33), (3, 128, 129)])
+def test_fused_transposes_virtual_ranks(emu, world, nx, ny):
+    """The fused-transpose entry points (rp_navier_slab_phase{1,2}_p2p) with the peers played by buffers of ONE
+    process: every virtual rank scatters into every other rank's buffer exactly like the NVLink stores do."""
+    import ctypes as C
+    import torch
+    import parity_cases as pc
+    from rustpde_b200.slab import split
+
+    n, o = pc.make_navier_pair(emu, True, nx, ny, 1e5, 1.0, 0.01)
+    mk = nx // 2 + 1
+    ksz, koff = split(mk, world)
+    jsz, joff = split(ny, world)
+    xin = [[torch.zeros(mk * jsz[q] * 2, dtype=torch.float64) for _ in range(6)] for q in range(world)]
+    s3 = [[torch.zeros(ksz[q] * ny * 2, dtype=torch.float64) for _ in range(3)] for q in range(world)]
+    work = [torch.zeros(8 * nx * jsz[q], dtype=torch.float64) for q in range(world)]
+    peers1 = (C.c_void_p * (6 * world))(*[xin[q][a].data_ptr() for a in range(6) for q in range(world)])
+    peers2 = (C.c_void_p * (3 * world))(*[s3[q][f].data_ptr() for f in range(3) for q in range(world)])
+    cj = (C.c_int * (world + 1))(*(joff + [ny]))
+    ck = (C.c_int * (world + 1))(*(koff + [mk]))
+    for _ in range(3):
+        for p in range(world):
+            emu.call("rp_navier_slab_phase1_p2p", n._h, koff[p], ksz[p], world, cj, peers1)
+        for p in range(world):
+            in6 = (C.c_void_p * 6)(*[t.data_ptr() for t in xin[p]])
+            emu.call("rp_navier_slab_phase2_p2p", n._h, joff[p], jsz[p], in6, C.c_void_p(work[p].data_ptr()), world, ck, peers2)
+        for p in range(world):
+            in3 = (C.c_void_p * 3)(*[t.data_ptr() for t in s3[p]])
+            emu.call("rp_navier_slab_phase3", n._h, koff[p], ksz[p], in3)
+        o.update()
+    err = pc.navier_field_errors(n, o)
+    assert max(err.values()) <= 1e-10, err

@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, nx, ny, steps, out):
+def _worker(rank, world, port, nx, ny, steps, transport, out):
     for p in (ROOT, os.path.join(ROOT, "tests")):
         if p not in sys.path:
             sys.path.insert(0, p)
@@ -27,26 +27,29 @@ def _worker(rank, world, port, nx, ny, steps, out):
 
         lib = _ffi.product_lib(rank)
         n, o = pc.make_navier_pair(lib, True, nx, ny, 1e6, 1.0, 2e-3)
-        s = Navier2DSlab(n)
+        s = Navier2DSlab(n, transport=transport)
+        assert s.transport == transport
         s.update(steps)
         s.gather_state()
         for _ in range(steps):
             o.update()
         err = pc.navier_field_errors(n, o)
         out[rank] = (max(err.values()) <= 1e-9, err)
+        s.close()
     finally:
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("transport", ["collective", "p2p"])
 @pytest.mark.parametrize("nx,ny,steps", [(64, 65, 10), (512, 513, 5), (2048, 129, 3)])
-def test_slab_periodic_nccl(nx, ny, steps):
+def test_slab_periodic_nccl(nx, ny, steps, transport):
     import torch
     import torch.multiprocessing as mp
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     mgr = mp.Manager()
     out = mgr.dict()
-    mp.spawn(_worker, args=(2, 29650 + nx % 89, nx, ny, steps, out), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, 29650 + nx % 89 + (7 if transport == "p2p" else 0), nx, ny, steps, transport, out), nprocs=2, join=True)
     for r in range(2):
         ok, err = out[r]
         assert ok, (r, err)
