@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(YCfg<LOG2L, LC>::NTHR, 1) pk_hholtz(PHholtzArg
   }
   for (int it = threadIdx.x; it < m * LC; it += C::NTHR) {  // pivot reciprocals of the LC complex rows
     const int l = it / m, j = it - l * m;
-    ti[l * C::ROWS + j] = a.m.inv[(size_t)min(r0 + l, nrows - 1) * a.m.inv_ld + j];
+    ti[j * LC + l] = a.m.inv[(size_t)min(r0 + l, nrows - 1) * a.m.inv_ld + j];
   }
   {
     const int tot = n * C::LR;
@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(YCfg<LOG2L, LC>::NTHR, 1) pk_divpois(PDivPoisA
   tile_fill<LC, C::NTHR>(td, n, [&](int j, int l) { return ldc_stencil(a.uy, prow_of(r0, l), j, l & 1, a.sd, a.sl); });
   for (int it = threadIdx.x; it < m * LC; it += C::NTHR) {  // pivot reciprocals of the LC complex rows
     const int l = it / m, j = it - l * m;
-    ti[l * C::ROWS + j] = a.m.inv[(size_t)min(r0 + l, nrows - 1) * a.m.inv_ld + j];
+    ti[j * LC + l] = a.m.inv[(size_t)min(r0 + l, nrows - 1) * a.m.inv_ld + j];
   }
   __syncthreads();
   cheb_diff<LC, C::NTHR, C::CL>(td, -1, td, -1, n, a.isy, red);

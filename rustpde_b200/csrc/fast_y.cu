@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(YCfg<LOG2L, LC>::NTHR, 1) yk_mode(YModeArgs a)
   tile_fill<LC, C::NTHR>(td, n, [&](int j, int l) { return ld_row(a.g, r0 + l, j); });
   for (int it = threadIdx.x; it < m * C::LR; it += C::NTHR) {  // pivot reciprocals of the LR rows (coalesced along j)
     const int l = it / m, j = it - l * m;
-    ti[l * C::ROWS + j] = a.m.inv[(size_t)min(r0 + l, a.g.rows - 1) * a.m.inv_ld + j];
+    ti[j * C::LR + l] = a.m.inv[(size_t)min(r0 + l, a.g.rows - 1) * a.m.inv_ld + j];
   }
   __syncthreads();
   const double mu = __ldg(&a.m.lam[min(r0 + (int)(threadIdx.x % C::LR), a.g.rows - 1)]) + a.m.alpha;

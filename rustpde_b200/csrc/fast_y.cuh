@@ -79,12 +79,14 @@ FK_DEV double ld_row(const Mat& a, int r, int j) {
 // tile td holds g (n entries, natural layout), tile ti the swept pivot reciprocals 1/dia'_i of the lane
 // (set-up data); everything else of the sweep is recomputed from the raw bands.  `mu` = lam + alpha of
 // the calling thread's lane (threadIdx.x & 3).  Result: m = n - 2 entries in td.
-// `ti` holds one plain array of ROWS reciprocals per *row* of the tile; lane l reads row l >> CSHIFT
-// (CSHIFT = 0: 2 LC real rows; CSHIFT = 1: re/im lanes of LC complex rows share their row's array).
+// `ti` holds the reciprocals of the NR = (2 LC) >> CSHIFT rows of the tile, row fastest: ti[i * NR + row];
+// lane l reads row l >> CSHIFT (CSHIFT = 0: 2 LC real rows; CSHIFT = 1: re/im lanes of LC complex rows share
+// their row's values).
 template <int LC, int NTHR, int CL, int ROWS, int CSHIFT>
 FK_DEV void mode_solve(double* td, const double* ti, int n, const B2Tabs& B, const ModeTabs& M, double mu, double* red) {
   const int m = n - 2;
-  auto inv = [&](int i, int l) { return ti[(l >> CSHIFT) * ROWS + i]; };
+  constexpr int NR = (2 * LC) >> CSHIFT;
+  auto inv = [&](int i, int l) { return ti[i * NR + (l >> CSHIFT)]; };
   // forward: x_i -= l_{i-2} x_{i-2},  l_j = low_j / dia'_j   (fdma.rs:104-107 on the swept system)
   auto lw = [&](int i, int l) {  // low'_{i-2}
     return fma(mu, __ldg(&M.c_low[i - 2]), __ldg(&M.a_low[i - 2])) * inv(i - 2, l);
