@@ -33,9 +33,8 @@ struct PXCfg {
 };
 
 template <int LOG2N, int LC>
-__global__ void __launch_bounds__(PXCfg<LOG2N, LC>::NTHR, PXCfg<LOG2N, LC>::SMEM > 110 * 1024 ? 1 : 2) pk_c2r(PC2rArgs3 a3) {
+FK_DEV void pk_c2r_body(const PC2rArgs& a, const PC2rArgs3& a3) {
   typedef PXCfg<LOG2N, LC> C;
-  const PC2rArgs& a = a3.a[blockIdx.y];
   RP_DYN_SMEM(double, td);
   cplx* tc = (cplx*)td;
   constexpr int n = C::N, mkr = n / 2 + 1;
@@ -77,11 +76,21 @@ __global__ void __launch_bounds__(PXCfg<LOG2N, LC>::NTHR, PXCfg<LOG2N, LC>::SMEM
     __syncthreads();
   }
 }
+// blockIdx.y selects the field; the branch is block-uniform and keeps every argument a direct constant-bank
+// operand (a dynamically indexed `a3.a[blockIdx.y]` costs an LDC per access)
+template <int LOG2N, int LC>
+__global__ void __launch_bounds__(PXCfg<LOG2N, LC>::NTHR, PXCfg<LOG2N, LC>::SMEM > 110 * 1024 ? 1 : 2) pk_c2r(PC2rArgs3 a3) {
+  if (blockIdx.y == 0)
+    pk_c2r_body<LOG2N, LC>(a3.a[0], a3);
+  else if (blockIdx.y == 1)
+    pk_c2r_body<LOG2N, LC>(a3.a[1], a3);
+  else
+    pk_c2r_body<LOG2N, LC>(a3.a[2], a3);
+}
 
 template <int LOG2N, int LC>
-__global__ void __launch_bounds__(PXCfg<LOG2N, LC>::NTHR, PXCfg<LOG2N, LC>::SMEM > 110 * 1024 ? 1 : 2) pk_r2c(PR2cArgs3 a3) {
+FK_DEV void pk_r2c_body(const PR2cArgs& a, const PR2cArgs3& a3) {
   typedef PXCfg<LOG2N, LC> C;
-  const PR2cArgs& a = a3.a[blockIdx.y];
   RP_DYN_SMEM(double, td);
   cplx* tc = (cplx*)td;
   constexpr int n = C::N, mkr = n / 2 + 1;
@@ -129,6 +138,17 @@ __global__ void __launch_bounds__(PXCfg<LOG2N, LC>::NTHR, PXCfg<LOG2N, LC>::SMEM
     if (cb < ncols) row[cb] = mk(h * d.y, -h * d.x);
   }
 }
+// blockIdx.y selects the field; the branch is block-uniform and keeps every argument a direct constant-bank
+// operand (a dynamically indexed `a3.a[blockIdx.y]` costs an LDC per access)
+template <int LOG2N, int LC>
+__global__ void __launch_bounds__(PXCfg<LOG2N, LC>::NTHR, PXCfg<LOG2N, LC>::SMEM > 110 * 1024 ? 1 : 2) pk_r2c(PR2cArgs3 a3) {
+  if (blockIdx.y == 0)
+    pk_r2c_body<LOG2N, LC>(a3.a[0], a3);
+  else if (blockIdx.y == 1)
+    pk_r2c_body<LOG2N, LC>(a3.a[1], a3);
+  else
+    pk_r2c_body<LOG2N, LC>(a3.a[2], a3);
+}
 
 // ---- y kernels on complex rows -------------------------------------------------------------------
 // lane l of the tile: row r0 + (l >> 1), part l & 1 (re / im)
@@ -150,9 +170,8 @@ FK_DEV double ldc_stencil(const Mat& a, int r, int j, int part, const double* __
 FK_DEV double ik_part(double ks, double re, double im, int part) { return part ? ks * re : -ks * im; }
 
 template <int LOG2L, int LC>
-__global__ void __launch_bounds__(YCfg<LOG2L, LC>::NTHR, 1) pk_hholtz(PHholtzArgs3 a3) {
+FK_DEV void pk_hholtz_body(const PHholtzArgs& a, const PHholtzArgs3& a3) {
   typedef YCfg<LOG2L, LC> C;
-  const PHholtzArgs& a = a3.a[blockIdx.y];
   YK_SMEM(td, red0);
   double* ti = td + C::TILE;
   double* red = ti + LC * C::ROWS;
@@ -206,6 +225,17 @@ __global__ void __launch_bounds__(YCfg<LOG2L, LC>::NTHR, 1) pk_hholtz(PHholtzArg
     const int r = prow_of(r0, l);
     if (r < a.out.rows) a.out.p[((size_t)r * a.out.ld + j) * 2 + (l & 1)] = v;
   });
+}
+// blockIdx.y selects the field; the branch is block-uniform and keeps every argument a direct constant-bank
+// operand (a dynamically indexed `a3.a[blockIdx.y]` costs an LDC per access)
+template <int LOG2L, int LC>
+__global__ void __launch_bounds__(YCfg<LOG2L, LC>::NTHR, 1) pk_hholtz(PHholtzArgs3 a3) {
+  if (blockIdx.y == 0)
+    pk_hholtz_body<LOG2L, LC>(a3.a[0], a3);
+  else if (blockIdx.y == 1)
+    pk_hholtz_body<LOG2L, LC>(a3.a[1], a3);
+  else
+    pk_hholtz_body<LOG2L, LC>(a3.a[2], a3);
 }
 
 template <int LOG2L, int LC>
@@ -296,9 +326,8 @@ __global__ void __launch_bounds__(YCfg<LOG2L, LC>::NTHR, YCfg<LOG2L, LC>::SMEM1 
 
 // ---- y transforms on complex rows (slab decomposition over kx) ------------------------------------------
 template <int LOG2L, int LC>
-__global__ void __launch_bounds__(YCfg<LOG2L, LC>::NTHR, YCfg<LOG2L, LC>::SMEM1 > 110 * 1024 ? 1 : 2) pk_ybackward(PYBackArgs3 a3) {
+FK_DEV void pk_ybackward_body(const PYBackArgs& a, const PYBackArgs3& a3) {
   typedef YCfg<LOG2L, LC> C;
-  const PYBackArgs& a = a3.a[blockIdx.y];
   YK_SMEM(td, red);
   const int r0 = blockIdx.x * LC;
   constexpr int n = C::n, N = C::N;
@@ -329,11 +358,21 @@ __global__ void __launch_bounds__(YCfg<LOG2L, LC>::NTHR, YCfg<LOG2L, LC>::SMEM1 
   dct_pow2<LC, LOG2L, C::NTHR, true>(td, a.t, red);
   drain(a.dy, a.sdy);
 }
+// blockIdx.y selects the field; the branch is block-uniform and keeps every argument a direct constant-bank
+// operand (a dynamically indexed `a3.a[blockIdx.y]` costs an LDC per access)
+template <int LOG2L, int LC>
+__global__ void __launch_bounds__(YCfg<LOG2L, LC>::NTHR, YCfg<LOG2L, LC>::SMEM1 > 110 * 1024 ? 1 : 2) pk_ybackward(PYBackArgs3 a3) {
+  if (blockIdx.y == 0)
+    pk_ybackward_body<LOG2L, LC>(a3.a[0], a3);
+  else if (blockIdx.y == 1)
+    pk_ybackward_body<LOG2L, LC>(a3.a[1], a3);
+  else
+    pk_ybackward_body<LOG2L, LC>(a3.a[2], a3);
+}
 
 template <int LOG2L, int LC>
-__global__ void __launch_bounds__(YCfg<LOG2L, LC>::NTHR, YCfg<LOG2L, LC>::SMEM1 > 110 * 1024 ? 1 : 2) pk_yforward(PYFwdArgs3 a3) {
+FK_DEV void pk_yforward_body(const PYFwdArgs& a, const PYFwdArgs3& a3) {
   typedef YCfg<LOG2L, LC> C;
-  const PYFwdArgs& a = a3.a[blockIdx.y];
   YK_SMEM(td, red);
   const int r0 = blockIdx.x * LC;
   constexpr int n = C::n, N = C::N;
@@ -344,6 +383,17 @@ __global__ void __launch_bounds__(YCfg<LOG2L, LC>::NTHR, YCfg<LOG2L, LC>::SMEM1 
     const int r = prow_of(r0, l);
     if (r < a.dst.rows) a.dst.p[((size_t)r * a.dst.ld + j) * 2 + (l & 1)] = (j < a.cut) ? v : 0.0;
   });
+}
+// blockIdx.y selects the field; the branch is block-uniform and keeps every argument a direct constant-bank
+// operand (a dynamically indexed `a3.a[blockIdx.y]` costs an LDC per access)
+template <int LOG2L, int LC>
+__global__ void __launch_bounds__(YCfg<LOG2L, LC>::NTHR, YCfg<LOG2L, LC>::SMEM1 > 110 * 1024 ? 1 : 2) pk_yforward(PYFwdArgs3 a3) {
+  if (blockIdx.y == 0)
+    pk_yforward_body<LOG2L, LC>(a3.a[0], a3);
+  else if (blockIdx.y == 1)
+    pk_yforward_body<LOG2L, LC>(a3.a[1], a3);
+  else
+    pk_yforward_body<LOG2L, LC>(a3.a[2], a3);
 }
 
 // ---- launchers -----------------------------------------------------------------------------------

@@ -99,10 +99,9 @@ FK_DEV void xstencil_tile(double* dst, const double* src, int n, const double* _
 
 // ---------------------------------------------------------------------------------
 template <int LOG2LB, int LC>
-__global__ void __launch_bounds__(XCfg<LOG2LB, LC>::NTHR, XCfg<LOG2LB, LC>::MINB) xk_backward(XBackwardArgs3 a3) {
+FK_DEV void xk_backward_body(const XBackwardArgs& a, const XBackwardArgs3& a3) {
   typedef XCfg<LOG2LB, LC> C;
   constexpr int LR = C::LR;
-  const XBackwardArgs& a = a3.a[blockIdx.y];
   RP_DYN_SMEM(double, ta);
   double* tw = ta + C::AROWS * LR;
   double* red = tw + C::LB * LR;
@@ -127,12 +126,22 @@ __global__ void __launch_bounds__(XCfg<LOG2LB, LC>::NTHR, XCfg<LOG2LB, LC>::MINB
     __syncthreads();
   }
 }
+// blockIdx.y selects the field; the branch is block-uniform and keeps every argument a direct constant-bank
+// operand (a dynamically indexed `a3.a[blockIdx.y]` costs an LDC per access)
+template <int LOG2LB, int LC>
+__global__ void __launch_bounds__(XCfg<LOG2LB, LC>::NTHR, XCfg<LOG2LB, LC>::MINB) xk_backward(XBackwardArgs3 a3) {
+  if (blockIdx.y == 0)
+    xk_backward_body<LOG2LB, LC>(a3.a[0], a3);
+  else if (blockIdx.y == 1)
+    xk_backward_body<LOG2LB, LC>(a3.a[1], a3);
+  else
+    xk_backward_body<LOG2LB, LC>(a3.a[2], a3);
+}
 
 template <int LOG2LB, int LC>
-__global__ void __launch_bounds__(XCfg<LOG2LB, LC>::NTHR, XCfg<LOG2LB, LC>::MINB) xk_forward(XForwardArgs3 a3) {
+FK_DEV void xk_forward_body(const XForwardArgs& a, const XForwardArgs3& a3) {
   typedef XCfg<LOG2LB, LC> C;
   constexpr int LR = C::LR;
-  const XForwardArgs& a = a3.a[blockIdx.y];
   RP_DYN_SMEM(double, ta);
   double* tw = ta + C::AROWS * LR;
   double* red = tw + C::LB * LR;
@@ -222,6 +231,17 @@ __global__ void __launch_bounds__(XCfg<LOG2LB, LC>::NTHR, XCfg<LOG2LB, LC>::MINB
     const int l = it % LR, i = it / LR;
     if (c0 + l < ncols) a.out.p[(size_t)i * a.out.ld + c0 + l] = tw[didx<LC>(rowof(N, i), l)];
   }
+}
+// blockIdx.y selects the field; the branch is block-uniform and keeps every argument a direct constant-bank
+// operand (a dynamically indexed `a3.a[blockIdx.y]` costs an LDC per access)
+template <int LOG2LB, int LC>
+__global__ void __launch_bounds__(XCfg<LOG2LB, LC>::NTHR, XCfg<LOG2LB, LC>::MINB) xk_forward(XForwardArgs3 a3) {
+  if (blockIdx.y == 0)
+    xk_forward_body<LOG2LB, LC>(a3.a[0], a3);
+  else if (blockIdx.y == 1)
+    xk_forward_body<LOG2LB, LC>(a3.a[1], a3);
+  else
+    xk_forward_body<LOG2LB, LC>(a3.a[2], a3);
 }
 
 template <int LOG2LB, int LC>

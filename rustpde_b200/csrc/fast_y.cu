@@ -15,9 +15,8 @@ namespace fk {
 
 // ---------------------------------------------------------------------------------
 template <int LOG2L, int LC>
-__global__ void __launch_bounds__(YCfg<LOG2L, LC>::NTHR, YCfg<LOG2L, LC>::SMEM1 > 110 * 1024 ? 1 : 2) yk_backward(YBackwardArgs3 a3) {
+FK_DEV void yk_backward_body(const YBackwardArgs& a, const YBackwardArgs3& a3) {
   typedef YCfg<LOG2L, LC> C;
-  const YBackwardArgs& a = a3.a[blockIdx.y];
   YK_SMEM(td, red);
   const int r0 = blockIdx.x * C::LR;
   constexpr int n = C::n, m = n - 2, N = C::N;
@@ -45,11 +44,21 @@ __global__ void __launch_bounds__(YCfg<LOG2L, LC>::NTHR, YCfg<LOG2L, LC>::SMEM1 
   dct_pow2<LC, LOG2L, C::NTHR, true>(td, a.t, red);
   drain(a.dx);
 }
+// blockIdx.y selects the field; the branch is block-uniform and keeps every argument a direct constant-bank
+// operand (a dynamically indexed `a3.a[blockIdx.y]` costs an LDC per access)
+template <int LOG2L, int LC>
+__global__ void __launch_bounds__(YCfg<LOG2L, LC>::NTHR, YCfg<LOG2L, LC>::SMEM1 > 110 * 1024 ? 1 : 2) yk_backward(YBackwardArgs3 a3) {
+  if (blockIdx.y == 0)
+    yk_backward_body<LOG2L, LC>(a3.a[0], a3);
+  else if (blockIdx.y == 1)
+    yk_backward_body<LOG2L, LC>(a3.a[1], a3);
+  else
+    yk_backward_body<LOG2L, LC>(a3.a[2], a3);
+}
 
 template <int LOG2L, int LC>
-__global__ void __launch_bounds__(YCfg<LOG2L, LC>::NTHR, YCfg<LOG2L, LC>::SMEM1 > 110 * 1024 ? 1 : 2) yk_conv(YConvArgs3 a3) {
+FK_DEV void yk_conv_body(const YConvArgs& a, const YConvArgs3& a3) {
   typedef YCfg<LOG2L, LC> C;
-  const YConvArgs& a = a3.a[blockIdx.y];
   YK_SMEM(td, red);
   const int r0 = blockIdx.x * C::LR;
   constexpr int n = C::n, N = C::N;
@@ -70,11 +79,21 @@ __global__ void __launch_bounds__(YCfg<LOG2L, LC>::NTHR, YCfg<LOG2L, LC>::SMEM1 
     if (r0 + l < a.out.rows) a.out.p[(size_t)(r0 + l) * a.out.ld + j] = (j < a.cut) ? v : 0.0;
   });
 }
+// blockIdx.y selects the field; the branch is block-uniform and keeps every argument a direct constant-bank
+// operand (a dynamically indexed `a3.a[blockIdx.y]` costs an LDC per access)
+template <int LOG2L, int LC>
+__global__ void __launch_bounds__(YCfg<LOG2L, LC>::NTHR, YCfg<LOG2L, LC>::SMEM1 > 110 * 1024 ? 1 : 2) yk_conv(YConvArgs3 a3) {
+  if (blockIdx.y == 0)
+    yk_conv_body<LOG2L, LC>(a3.a[0], a3);
+  else if (blockIdx.y == 1)
+    yk_conv_body<LOG2L, LC>(a3.a[1], a3);
+  else
+    yk_conv_body<LOG2L, LC>(a3.a[2], a3);
+}
 
 template <int LOG2L, int LC>
-__global__ void __launch_bounds__(YCfg<LOG2L, LC>::NTHR, YCfg<LOG2L, LC>::SMEM1 > 110 * 1024 ? 1 : 2) yk_adi(YAdiArgs3 a3) {
+FK_DEV void yk_adi_body(const YAdiArgs& a, const YAdiArgs3& a3) {
   typedef YCfg<LOG2L, LC> C;
-  const YAdiArgs& a = a3.a[blockIdx.y];
   YK_SMEM(td, red);
   const int r0 = blockIdx.x * C::LR;
   constexpr int n = C::n, m = n - 2;
@@ -109,6 +128,17 @@ __global__ void __launch_bounds__(YCfg<LOG2L, LC>::NTHR, YCfg<LOG2L, LC>::SMEM1 
   tile_drain<LC, C::NTHR>(td, -1, n, [&](int j, int l, double v) {
     if (r0 + l < a.aux.rows) a.aux.p[(size_t)(r0 + l) * a.aux.ld + j] = v;
   });
+}
+// blockIdx.y selects the field; the branch is block-uniform and keeps every argument a direct constant-bank
+// operand (a dynamically indexed `a3.a[blockIdx.y]` costs an LDC per access)
+template <int LOG2L, int LC>
+__global__ void __launch_bounds__(YCfg<LOG2L, LC>::NTHR, YCfg<LOG2L, LC>::SMEM1 > 110 * 1024 ? 1 : 2) yk_adi(YAdiArgs3 a3) {
+  if (blockIdx.y == 0)
+    yk_adi_body<LOG2L, LC>(a3.a[0], a3);
+  else if (blockIdx.y == 1)
+    yk_adi_body<LOG2L, LC>(a3.a[1], a3);
+  else
+    yk_adi_body<LOG2L, LC>(a3.a[2], a3);
 }
 
 template <int LOG2L, int LC>
