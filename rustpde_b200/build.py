@@ -37,6 +37,29 @@ def _deps():
     return out
 
 
+def _includes(path, seen):
+    """Transitive closure of the quoted #includes of `path` inside csrc/."""
+    import re
+
+    if path in seen or not os.path.exists(path):
+        return
+    seen.add(path)
+    for m in re.finditer(r'#include\s+"([^"]+)"', open(path).read()):
+        _includes(os.path.join(os.path.dirname(path), m.group(1)), seen)
+        _includes(os.path.join(CSRC, m.group(1)), seen)
+
+
+def _stale(src_path, obj, extra=()):
+    """True when `obj` is older than the source or any header it includes (per-file incremental build)."""
+    if not os.path.exists(obj):
+        return True
+    deps = set()
+    _includes(src_path, deps)
+    deps.update(extra)
+    t = os.path.getmtime(obj)
+    return any(os.path.getmtime(p) > t for p in deps if os.path.exists(p))
+
+
 def needs_build():
     if not os.path.exists(LIB):
         return True
@@ -52,6 +75,8 @@ def build(force=False, verbose=False):
 
     def compile_one(src):
         obj = os.path.join(OBJ, src.replace(".cu", ".o"))
+        if not force and not verbose and not _stale(os.path.join(CSRC, src), obj):
+            return obj
         cmd = [nvcc] + NVCC_FLAGS + os.environ.get("RUSTPDE_B200_NVCC_EXTRA", "").split() + ["-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")

@@ -318,6 +318,51 @@ FK_DEV void fft_dit_rec(cplx* tc, const cplx* __restrict__ tw, const cplx* __res
     fft_dit_rec<LC, LOG2L, NTHR, NEXT, HALF_OUT>(tc, tw, mulv);
   }
 }
+// Last DIF stage (span 8), pointwise filter, first inverse DIT stage (span 8) in one pass: both stages
+// work on the same 8 consecutive rows without twiddles, so the values stay in registers (one barrier and
+// one shared-memory round trip less per convolution; same arithmetic as the separate stages).
+template <int LC, int LOG2L, int NTHR>
+FK_DEV void dif_dit_mid(cplx* tc, const cplx* __restrict__ mulv) {
+  constexpr int L = 1 << LOG2L;
+  constexpr int TOT = (L / 8) * LC;
+#pragma unroll 1
+  for (int b = threadIdx.x; b < TOT; b += NTHR) {
+    const int u = b / LC, c = b % LC;
+    cplx v[8], m[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) m[r] = __ldg(&mulv[u * 8 + r]);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) v[r] = tc[cidx<LC>(u * 8 + r, c)];
+    Bfly<8>::run(v);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      v[r] = cmul(v[r], m[r]);
+      v[r].y = -v[r].y;
+    }
+    Bfly<8>::run(v);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) tc[cidx<LC>(u * 8 + r, c)] = v[r];
+  }
+  __syncthreads();
+}
+// DIF stages down to span 64 (the span-8 stage is fused into dif_dit_mid)
+template <int LC, int LOG2L, int NTHR, int LOG2S, bool ZERO_HALF>
+FK_DEV void fft_dif_rec_hi(cplx* tc, const cplx* __restrict__ tw) {
+  if constexpr (LOG2S > 3) {
+    constexpr int LR = (LOG2S % 3) ? (LOG2S % 3) : 3;
+    dif_stage<LC, LOG2L, NTHR, LOG2S, (1 << LR), ZERO_HALF && LOG2S == LOG2L>(tc, tw);
+    fft_dif_rec_hi<LC, LOG2L, NTHR, LOG2S - LR, ZERO_HALF>(tc, tw);
+  }
+}
+// circular convolution with the filter whose digit-reversed spectrum is mulv: rows >= L/2 of the input are
+// zero, only rows < L/2 of the result are produced (the Bluestein use)
+template <int LC, int LOG2L, int NTHR>
+FK_DEV void fft_convolve_half(cplx* tc, const cplx* __restrict__ tw, const cplx* __restrict__ mulv) {
+  static_assert(LOG2L >= 6, "fused middle stage needs at least two stages");
+  fft_dif_rec_hi<LC, LOG2L, NTHR, LOG2L, true>(tc, tw);
+  dif_dit_mid<LC, LOG2L, NTHR>(tc, mulv);
+  fft_dit_rec<LC, LOG2L, NTHR, 6, true>(tc, tw, mulv);
+}
 // forward: natural order in, digit-reversed out (rows >= L/2 of the input are zero when ZERO_HALF)
 template <int LC, int LOG2L, int NTHR, bool ZERO_HALF>
 FK_DEV void fft_dif(cplx* tc, const cplx* __restrict__ tw) {
@@ -422,6 +467,57 @@ FK_DEV void dct_odd_scan(double* td, int N, double* red) {
   __syncthreads();
 }
 
+// two-lane form of dct_odd_scan: a thread sums both real lanes of a complex lane (half the chunk length,
+// 16-byte accesses); carries: warp-level inclusive scan, then the warp totals through shared memory
+template <int LC, int NTHR, int CLR, bool BWD>
+FK_DEV void dct_odd_scan_v(cplx* tc, int N, double* red_) {
+  constexpr int NSC = scan_threads(NTHR), NG = NSC / LC;
+  static_assert(NSC % 32 == 0 && 32 % LC == 0, "scan threads");
+  cplx* red = (cplx*)red_;
+  const int tid = threadIdx.x, c = tid % LC, g = tid / LC;
+  const bool act = tid < NSC;
+  const int M = act ? (N - 1) / 2 + 1 : 0;  // Ko + 1
+  const int cl = ((N - 1) / 2 + 1 + NG - 1) / NG;
+  const int t0 = g * cl, t1 = min(t0 + cl, M);
+  cplx q[CLR];
+  cplx s = mk(0.0, 0.0);
+#pragma unroll
+  for (int u = 0; u < CLR; ++u) {
+    const int t = t0 + u;
+    if (t < t1) {
+      q[u] = tc[cidx<LC>(N - t, c)];
+      s = cadd(s, q[u]);
+    }
+  }
+  // inclusive scan of the chunk sums over the threads of the warp that share the lane
+  cplx inc = s;
+#pragma unroll
+  for (int o = LC; o < 32; o <<= 1) {
+    const double ux = __shfl_up_sync(0xffffffffu, inc.x, o), uy = __shfl_up_sync(0xffffffffu, inc.y, o);
+    if ((tid & 31) >= o) inc = mk(inc.x + ux, inc.y + uy);
+  }
+  if (act && (tid & 31) >= 32 - LC) red[(tid >> 5) * LC + c] = inc;  // warp totals
+  __syncthreads();
+  cplx y;  // exclusive prefix inside the warp
+  {
+    const double ux = __shfl_up_sync(0xffffffffu, inc.x, LC), uy = __shfl_up_sync(0xffffffffu, inc.y, LC);
+    y = ((tid & 31) >= LC) ? mk(ux, uy) : mk(0.0, 0.0);
+  }
+  for (int w = 0; act && w < (tid >> 5); ++w) y = cadd(y, red[w * LC + c]);
+  const double ho = BWD ? 1.0 : -1.0 / (double)N;
+#pragma unroll
+  for (int u = 0; u < CLR; ++u) {
+    const int t = t0 + u;
+    if (t < t1) {
+      y = cadd(y, q[u]);
+      cplx o = cscale(y, ho);
+      if (!BWD && 2 * t + 1 == N) o = cscale(o, 0.5);
+      tc[cidx<LC>(N - t, c)] = o;
+    }
+  }
+  __syncthreads();
+}
+
 // DCT-I with the Chebyshev scaling, power-of-two N = 1 << LOG2L, in place on a
 // tile of n = N + 1 rows in natural layout.  Result in split(N) layout.
 template <int LC, int LOG2L, int NTHR, bool BWD>
@@ -458,7 +554,7 @@ FK_DEV void dct_pow2(double* td, const DctTab& T, double* red) {
     }
   }
   __syncthreads();
-  dct_odd_scan<LC, NTHR, (N / 2 + scan_threads(NTHR) / (2 * LC) - 1) / (scan_threads(NTHR) / (2 * LC)), BWD>(td, N, red);
+  dct_odd_scan_v<LC, NTHR, (N / 2 + scan_threads(NTHR) / LC - 1) / (scan_threads(NTHR) / LC), BWD>(tc, N, red);
 }
 
 // DCT-I of arbitrary N = n - 1 through Bluestein (FFT length Lb = 1 << LOG2LB >=
@@ -484,8 +580,7 @@ FK_DEV void dct_bluestein(const double* ta, double* tw_, const DctTab& T, double
   for (int it = LC * N + tid; it < (LB / 2) * LC; it += NTHR) W[cidx<LC>(it / LC, c)] = mk(0.0, 0.0);  // rows [N, LB/2)
   reduce_f1<LC, NTHR>(f1, f1red);
   __syncthreads();
-  fft_dif<LC, LOG2LB, NTHR, true>(W, T.tw);
-  fft_dit_inv<LC, LOG2LB, NTHR, true>(W, T.tw, T.bhat);
+  fft_convolve_half<LC, LOG2LB, NTHR>(W, T.tw, T.bhat);
   const int Ko = (N - 1) / 2;
   for (int it = tid; it < NP * LC; it += NTHR) {
     const int k = it / LC;
@@ -502,7 +597,7 @@ FK_DEV void dct_bluestein(const double* ta, double* tw_, const DctTab& T, double
     }
   }
   __syncthreads();
-  dct_odd_scan<LC, NTHR, (LB / 4 + scan_threads(NTHR) / (2 * LC) - 1) / (scan_threads(NTHR) / (2 * LC)), BWD>(tw_, N, red);
+  dct_odd_scan_v<LC, NTHR, (LB / 4 + scan_threads(NTHR) / LC - 1) / (scan_threads(NTHR) / LC), BWD>(W, N, red);
 }
 
 // ---- chunked scans over the 8 parity chains of a tile ---------------------------
@@ -703,6 +798,261 @@ FK_DEV void from_ortho(double* t, int sn, int n, const TdmaTabs& T, double* red)
   scan1<LC, NTHR, CL, false>(
       m, red, [&](int i, int l) { return t[didx<LC>(rowof(sn, i), l)]; }, [&](int i, int) { return __ldg(&T.bp[i]); },
       [&](int i, int l, double y) { t[didx<LC>(rowof(sn, i), l)] = y; });
+}
+
+
+// =====================================================================================
+// Two-lane ("v") forms of the building blocks: a thread works on one packed complex
+// lane = two real lanes at a time (16-byte shared-memory and global accesses, one
+// coefficient load per pair of lanes).  Same arithmetic per lane as the scalar forms.
+// =====================================================================================
+FK_DEV cplx lmul(cplx a, cplx b) { return mk(a.x * b.x, a.y * b.y); }  // lane-wise product
+FK_DEV cplx lfma(cplx a, cplx b, cplx c) { return mk(fma(a.x, b.x, c.x), fma(a.y, b.y, c.y)); }
+FK_DEV cplx sfma(double s, cplx b, cplx c) { return mk(fma(s, b.x, c.x), fma(s, b.y, c.y)); }
+// recurrence coefficients are either shared by the two lanes (double) or per lane (cplx)
+FK_DEV cplx kfma(double k, cplx y, cplx q) { return sfma(k, y, q); }
+FK_DEV cplx kfma(cplx k, cplx y, cplx q) { return lfma(k, y, q); }
+FK_DEV cplx kmul(double k, cplx a) { return cscale(a, k); }
+FK_DEV cplx kmul(cplx k, cplx a) { return lmul(k, a); }
+
+// chunk length bound of a two-lane scan run by `nsc` threads
+RP_HD constexpr int chunk_len_v(int n, int nsc, int lc = 2) { return (((n + 1) / 2) + nsc / (2 * lc) - 1) / (nsc / (2 * lc)); }
+// bytes of scratch of scan1v / scan2v with nsc threads (two carry levels)
+RP_HD constexpr int scan1v_bytes(int nsc) { return nsc * 32 + (nsc / 8 + 8) * 32; }
+RP_HD constexpr int scan2v_bytes(int nsc) { return nsc * 96 + (nsc / 8 + 8) * 96; }
+
+//   y_t = in(i, c) + c1(i, c) * y_{t-1}   on both real lanes of complex lane c (see scan1)
+template <int LC, int NTHR, int NSC, int CL, bool FWD, class In, class C1, class Out>
+FK_DEV void scan1v(int n, double* red_, In in, C1 c1, Out out) {
+  constexpr int NCH = 2 * LC;  // chains per tile: LC complex lanes x 2 parities
+  constexpr int NG = NSC / NCH;
+  static_assert(NSC <= NTHR && NSC % NCH == 0, "scan threads");
+  cplx* red = (cplx*)red_;
+  const int tid = threadIdx.x, ch = tid % NCH, g = tid / NCH;
+  const int c = ch % LC, p = ch / LC;
+  const bool act = tid < NSC;
+  const int M = act ? ((n - p + 1) >> 1) : 0;  // threads beyond NSC own empty chunks
+  const int cl = (((n + 1) >> 1) + NG - 1) / NG;
+  const int t0 = g * cl, t1 = min(t0 + cl, M);
+  cplx q[CL];
+  cplx A = mk(1.0, 1.0), b = mk(0.0, 0.0);
+#pragma unroll
+  for (int u = 0; u < CL; ++u) {
+    const int t = t0 + u;
+    if (t < t1) {
+      const int i = 2 * (FWD ? t : M - 1 - t) + p;
+      q[u] = in(i, c);
+      const auto k = c1(i, c);
+      b = kfma(k, b, q[u]);
+      A = kmul(k, A);
+    }
+  }
+  cplx* red2 = red + NG * NCH * 2;
+  if (act) {
+    red[(g * NCH + ch) * 2] = A;
+    red[(g * NCH + ch) * 2 + 1] = b;
+  }
+  __syncthreads();
+  if (act && (g & 7) == 0) {
+    cplx Ag = mk(1.0, 1.0), bg = mk(0.0, 0.0);
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (g + k < NG) {
+        const cplx Ak = red[((g + k) * NCH + ch) * 2], bk = red[((g + k) * NCH + ch) * 2 + 1];
+        bg = lfma(Ak, bg, bk);
+        Ag = lmul(Ag, Ak);
+      }
+    red2[((g >> 3) * NCH + ch) * 2] = Ag;
+    red2[((g >> 3) * NCH + ch) * 2 + 1] = bg;
+  }
+  __syncthreads();
+  cplx y = mk(0.0, 0.0);
+  if (act) {
+    for (int gg = 0; gg < (g >> 3); ++gg) y = lfma(red2[(gg * NCH + ch) * 2], y, red2[(gg * NCH + ch) * 2 + 1]);
+    for (int gg = (g & ~7); gg < g; ++gg) y = lfma(red[(gg * NCH + ch) * 2], y, red[(gg * NCH + ch) * 2 + 1]);
+  }
+#pragma unroll
+  for (int u = 0; u < CL; ++u) {
+    const int t = t0 + u;
+    if (t < t1) {
+      const int i = 2 * (FWD ? t : M - 1 - t) + p;
+      y = kfma(c1(i, c), y, q[u]);
+      out(i, c, y);
+    }
+  }
+  __syncthreads();
+}
+
+//   y_t = in(i, c) + c1(i, c) * y_{t-1} + c2(i, c) * y_{t-2}   (see scan2)
+// CACHE = false: in(i, c) is evaluated again in the second walk instead of being kept in registers --
+// only valid when out(i, c, .) of a thread touches nothing but what in(i, c) of the same thread read.
+template <int LC, int NTHR, int NSC, int CL, bool FWD, bool CACHE, class In, class C1, class C2, class Out>
+FK_DEV void scan2v(int n, double* red_, In in, C1 c1, C2 c2, Out out) {
+  constexpr int NCH = 2 * LC;
+  constexpr int NG = NSC / NCH;
+  static_assert(NSC <= NTHR && NSC % NCH == 0, "scan threads");
+  cplx* red = (cplx*)red_;
+  const int tid = threadIdx.x, ch = tid % NCH, g = tid / NCH;
+  const int c = ch % LC, p = ch / LC;
+  const bool act = tid < NSC;
+  const int M = act ? ((n - p + 1) >> 1) : 0;
+  const int cl = (((n + 1) >> 1) + NG - 1) / NG;
+  const int t0 = g * cl, t1 = min(t0 + cl, M);
+  cplx q[CACHE ? CL : 1];
+  const cplx one = mk(1.0, 1.0), zero = mk(0.0, 0.0);
+  // particular solution and the two homogeneous ones, states (y_{t-1}, y_{t-2})
+  cplx p1 = zero, p2 = zero, a1 = one, a2 = zero, b1 = zero, b2 = one;
+#pragma unroll
+  for (int u = 0; u < CL; ++u) {
+    const int t = t0 + u;
+    if (t < t1) {
+      const int i = 2 * (FWD ? t : M - 1 - t) + p;
+      const cplx qu = in(i, c);
+      if (CACHE) q[u] = qu;
+      const auto k1 = c1(i, c);
+      const auto k2 = c2(i, c);
+      const cplx pn = kfma(k1, p1, kfma(k2, p2, qu));
+      const cplx an = kfma(k1, a1, kmul(k2, a2));
+      const cplx bn = kfma(k1, b1, kmul(k2, b2));
+      p2 = p1, p1 = pn;
+      a2 = a1, a1 = an;
+      b2 = b1, b1 = bn;
+    }
+  }
+  if (act) {
+    cplx* r = red + (g * NCH + ch) * 6;
+    r[0] = a1, r[1] = b1, r[2] = p1, r[3] = a2, r[4] = b2, r[5] = p2;
+  }
+  __syncthreads();
+  cplx* red2 = red + NG * NCH * 6;
+  if (act && (g & 7) == 0) {
+    cplx g11 = one, g12 = zero, g21 = zero, g22 = one, h1 = zero, h2 = zero;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (g + k < NG) {
+        const cplx* rr = red + ((g + k) * NCH + ch) * 6;
+        const cplx n11 = lfma(rr[0], g11, lmul(rr[1], g21)), n12 = lfma(rr[0], g12, lmul(rr[1], g22));
+        const cplx n21 = lfma(rr[3], g11, lmul(rr[4], g21)), n22 = lfma(rr[3], g12, lmul(rr[4], g22));
+        const cplx m1 = lfma(rr[0], h1, lfma(rr[1], h2, rr[2])), m2 = lfma(rr[3], h1, lfma(rr[4], h2, rr[5]));
+        g11 = n11, g12 = n12, g21 = n21, g22 = n22, h1 = m1, h2 = m2;
+      }
+    cplx* w = red2 + ((g >> 3) * NCH + ch) * 6;
+    w[0] = g11, w[1] = g12, w[2] = h1, w[3] = g21, w[4] = g22, w[5] = h2;
+  }
+  __syncthreads();
+  cplx y1 = zero, y2 = zero;
+  for (int gg = 0; act && gg < (g >> 3); ++gg) {
+    const cplx* rr = red2 + (gg * NCH + ch) * 6;
+    const cplx n1 = lfma(rr[0], y1, lfma(rr[1], y2, rr[2]));
+    const cplx n2 = lfma(rr[3], y1, lfma(rr[4], y2, rr[5]));
+    y1 = n1, y2 = n2;
+  }
+  for (int gg = (g & ~7); act && gg < g; ++gg) {
+    const cplx* rr = red + (gg * NCH + ch) * 6;
+    const cplx n1 = lfma(rr[0], y1, lfma(rr[1], y2, rr[2]));
+    const cplx n2 = lfma(rr[3], y1, lfma(rr[4], y2, rr[5]));
+    y1 = n1, y2 = n2;
+  }
+#pragma unroll
+  for (int u = 0; u < CL; ++u) {
+    const int t = t0 + u;
+    if (t < t1) {
+      const int i = 2 * (FWD ? t : M - 1 - t) + p;
+      const cplx qu = CACHE ? q[u] : in(i, c);
+      const cplx yn = kfma(c1(i, c), y1, kfma(c2(i, c), y2, qu));
+      y2 = y1, y1 = yn;
+      out(i, c, yn);
+    }
+  }
+  __syncthreads();
+}
+
+// Chebyshev derivative (see cheb_diff), tiles viewed as cplx[rows][LC]
+template <int LC, int NTHR, int NMAX>
+FK_DEV void cheb_diff_v(const cplx* src, int sn_s, cplx* dst, int sn_d, int n, double sc, double* red) {
+  constexpr int NSC = scan_threads(NTHR);
+  scan1v<LC, NTHR, NSC, chunk_len_v(NMAX, NSC, LC), false>(
+      n, red, [&](int i, int c) { return cscale(src[cidx<LC>(rowof(sn_s, i), c)], 2.0 * (double)i * sc); },
+      [](int, int) { return 1.0; },
+      [&](int i, int c, cplx y) {
+        if (i >= 1) dst[cidx<LC>(rowof(sn_d, i - 1), c)] = (i == 1) ? cscale(y, 0.5) : y;
+        if (i == n - 1) dst[cidx<LC>(rowof(sn_d, n - 1), c)] = mk(0.0, 0.0);
+      });
+}
+
+// HholtzAdi half step (see b2_fdma).  NSC2 threads run the second-order sweep; its scratch `red2`
+// needs scan2v_bytes(NSC2) bytes, `red` scan1v_bytes(scan_threads(NTHR)).
+template <int LC, int NTHR, int NMAX, int NSC2>
+FK_DEV void b2_fdma_v(cplx* t, int sn, int n, const B2Tabs& B, const FdmaTabs& F, double* red, double* red2) {
+  const int m = n - 2;
+  constexpr int NSC = scan_threads(NTHR);
+  scan1v<LC, NTHR, NSC, chunk_len_v(NMAX, NSC, LC), true>(
+      m, red,
+      [&](int i, int c) {
+        const cplx up = (i + 4 < n) ? cscale(t[cidx<LC>(rowof(sn, i + 4), c)], __ldg(&B.up[i])) : mk(0.0, 0.0);
+        return sfma(__ldg(&B.lo[i]), t[cidx<LC>(rowof(sn, i), c)], sfma(__ldg(&B.di[i]), t[cidx<LC>(rowof(sn, i + 2), c)], up));
+      },
+      [&](int i, int) { return __ldg(&F.fp[i]); }, [&](int i, int c, cplx y) { t[cidx<LC>(rowof(sn, i), c)] = y; });
+  scan2v<LC, NTHR, NSC2, chunk_len_v(NMAX, NSC2, LC), false, false>(
+      m, red2, [&](int i, int c) { return cscale(t[cidx<LC>(rowof(sn, i), c)], __ldg(&F.bs[i])); },
+      [&](int i, int) { return __ldg(&F.bp1[i]); }, [&](int i, int) { return __ldg(&F.bp2[i]); },
+      [&](int i, int c, cplx y) { t[cidx<LC>(rowof(sn, i), c)] = y; });
+}
+
+// from_ortho (see above), two-lane form
+template <int LC, int NTHR, int NMAX>
+FK_DEV void from_ortho_v(cplx* t, int sn, int n, const TdmaTabs& T, double* red) {
+  const int m = n - 2;
+  constexpr int NSC = scan_threads(NTHR);
+  constexpr int CL = chunk_len_v(NMAX, NSC, LC);
+  scan1v<LC, NTHR, NSC, CL, true>(
+      m, red,
+      [&](int i, int c) {
+        const cplx v = sfma(__ldg(&T.sd[i]), t[cidx<LC>(rowof(sn, i), c)], cscale(t[cidx<LC>(rowof(sn, i + 2), c)], __ldg(&T.sl[i])));
+        return cscale(v, __ldg(&T.fs[i]));
+      },
+      [&](int i, int) { return __ldg(&T.fp[i]); }, [&](int i, int c, cplx y) { t[cidx<LC>(rowof(sn, i), c)] = y; });
+  scan1v<LC, NTHR, NSC, CL, false>(
+      m, red, [&](int i, int c) { return t[cidx<LC>(rowof(sn, i), c)]; }, [&](int i, int) { return __ldg(&T.bp[i]); },
+      [&](int i, int c, cplx y) { t[cidx<LC>(rowof(sn, i), c)] = y; });
+}
+
+// ---- 16-byte global accesses of a pitched real matrix (two adjacent columns = one complex lane) ----------
+// (a[i][col], a[i][col + 1]), zero outside the matrix; col even, a.p 16-byte aligned, a.ld even
+FK_DEV cplx ld2(const Mat& a, int i, int col) {
+  const int cc = (col < a.cols) ? col : 0;  // keeps the access inside the row pitch
+  const cplx v = *(const cplx*)(a.p + (size_t)min(i, a.rows - 1) * a.ld + cc);
+  const bool r = i < a.rows;
+  return mk((r && col < a.cols) ? v.x : 0.0, (r && col + 1 < a.cols) ? v.y : 0.0);
+}
+FK_DEV void st2(const Mat& o, int i, int col, cplx v) {
+  double* q = o.p + (size_t)i * o.ld + col;
+  if (col + 1 < o.cols)
+    *(cplx*)q = v;
+  else if (col < o.cols)
+    *q = v.x;
+}
+// composite -> ortho stencil across columns applied while loading: out_j = d_j a[i][j] + l_{j-2} a[i][j-2],
+// j = col, col + 1; (yd, yl) are the coefficient pairs prepared by stencil_pair() (zero where out of range)
+struct StencilPair {
+  cplx d, l;
+  int c0, c2;
+};
+FK_DEV StencilPair stencil_pair(int cols, int col, const double* __restrict__ sd, const double* __restrict__ sl) {
+  StencilPair s;
+  s.d = mk(col < cols ? __ldg(&sd[col]) : 0.0, col + 1 < cols ? __ldg(&sd[col + 1]) : 0.0);
+  s.l = mk((col >= 2 && col - 2 < cols) ? __ldg(&sl[col - 2]) : 0.0, (col >= 2 && col - 1 < cols) ? __ldg(&sl[col - 1]) : 0.0);
+  s.c0 = col < cols ? col : 0;
+  s.c2 = (col >= 2 && col - 2 < cols) ? col - 2 : 0;
+  return s;
+}
+FK_DEV cplx ld2_stencil(const Mat& f, int i, const StencilPair& s) {  // i < f.rows
+  const double* row = f.p + (size_t)i * f.ld;
+  const cplx v0 = *(const cplx*)(row + s.c0), v2 = *(const cplx*)(row + s.c2);
+  // selects, not products with zero: the padding columns of the pitch are never initialised
+  const double a0 = s.d.x != 0.0 ? v0.x : 0.0, a1 = s.d.y != 0.0 ? v0.y : 0.0;
+  const double b0 = s.l.x != 0.0 ? v2.x : 0.0, b1 = s.l.y != 0.0 ? v2.y : 0.0;
+  return mk(fma(s.l.x, b0, s.d.x * a0), fma(s.l.y, b1, s.d.y * a1));
 }
 
 }  // namespace fk

@@ -20,6 +20,29 @@ SOURCES = ["kernels.cu", "fast_x.cu", "fast_y.cu", "fast_p.cu", "tables.cu", "pr
 FLAGS = ["-std=c++17", "-O2", "-g", "-fPIC", "-DRP_EMU", "-I", HERE, "-I", CSRC, "-fvisibility=hidden", "-Wall", "-Wno-unused-function", "-Wno-unknown-pragmas"]
 
 
+def _includes(path, seen):
+    """Transitive closure of the quoted #includes of `path` inside csrc/."""
+    import re
+
+    if path in seen or not os.path.exists(path):
+        return
+    seen.add(path)
+    for m in re.finditer(r'#include\s+"([^"]+)"', open(path).read()):
+        _includes(os.path.join(os.path.dirname(path), m.group(1)), seen)
+        _includes(os.path.join(CSRC, m.group(1)), seen)
+
+
+def _stale(src_path, obj, extra=()):
+    """True when `obj` is older than the source or any header it includes (per-file incremental build)."""
+    if not os.path.exists(obj):
+        return True
+    deps = set()
+    _includes(src_path, deps)
+    deps.update(extra)
+    t = os.path.getmtime(obj)
+    return any(os.path.getmtime(p) > t for p in deps if os.path.exists(p))
+
+
 def needs_build():
     if not os.path.exists(LIB):
         return True
@@ -36,6 +59,8 @@ def build(force=False):
 
     def compile_one(src):
         obj = os.path.join(OUT, src.replace(".cu", ".o"))
+        if not force and not _stale(os.path.join(CSRC, src), obj, [os.path.join(HERE, "cuemu.h")]):
+            return obj
         cmd = ["g++"] + FLAGS + ["-x", "c++", "-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
