@@ -114,6 +114,13 @@ int rp_navier_set_tempbc_ortho(rp_navier_t* h, const double* that_bc, size_t len
 int rp_navier_set_dealias(rp_navier_t* h, int on);                             /* pub dealias */
 int rp_navier_update(rp_navier_t* h, int nsteps);                              /* Integrate::update, 737-765 (x nsteps, asynchronous) */
 int rp_navier_sync(rp_navier_t* h);
+/* Double-buffered upload of the pub `vhat` arrays of temp, ux, uy, pres[0] (navier.rs:153-160; what `read()`
+ * 963-981 assigns): stage_state queues the host-to-device copies on a copy stream and returns (the host buffers
+ * must stay valid -- and should be page-locked -- until the commit); commit_staged makes the compute stream wait
+ * for them and moves the staged state into place.  The copies of the next state overlap update() of the current one. */
+int rp_navier_stage_state(rp_navier_t* h, const double* temp, size_t len_temp, const double* ux, size_t len_ux,
+                          const double* uy, size_t len_uy, const double* pres, size_t len_pres);
+int rp_navier_commit_staged(rp_navier_t* h);
 int rp_navier_get_time(rp_navier_t* h, double* time);                          /* get_time */
 int rp_navier_get_dt(rp_navier_t* h, double* dt);                              /* get_dt */
 int rp_navier_reset_time(rp_navier_t* h);                                      /* 951-953 */

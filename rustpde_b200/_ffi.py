@@ -57,6 +57,8 @@ _SIGS = {
     "rp_navier_set_tempbc_ortho": [vp, c_double_p, C.c_size_t],
     "rp_navier_set_dealias": [vp, C.c_int],
     "rp_navier_update": [vp, C.c_int],
+    "rp_navier_stage_state": [vp, c_double_p, C.c_size_t, c_double_p, C.c_size_t, c_double_p, C.c_size_t, c_double_p, C.c_size_t],
+    "rp_navier_commit_staged": [vp],
     "rp_navier_sync": [vp],
     "rp_navier_get_time": [vp, c_double_p],
     "rp_navier_get_dt": [vp, c_double_p],

@@ -383,6 +383,28 @@ class Navier2D:
     def sync(self):
         self._lib.call("rp_navier_sync", self._h)
 
+    def stage_state(self, temp, ux, uy, pres):
+        """Queue the upload of a complete state (the `vhat` arrays of temp, ux, uy, pres[0] as flat float64
+        buffers: numpy arrays or (address, n_doubles) pairs of page-locked memory) on the copy stream; returns
+        at once.  The buffers must stay alive until commit_staged()."""
+        args = []
+        keep = []
+        for a in (temp, ux, uy, pres):
+            if isinstance(a, tuple):
+                ptr, n = a
+            else:
+                a = np.ascontiguousarray(a)
+                keep.append(a)
+                ptr, n = a.ctypes.data, a.view(np.float64).size
+            args += [C.cast(ptr, _ffi.c_double_p), C.c_size_t(n)]
+        self._staged_keep = keep
+        self._lib.call("rp_navier_stage_state", self._h, *args)
+
+    def commit_staged(self):
+        """Make the compute stream wait for the staged upload and move it into place (see stage_state)."""
+        self._lib.call("rp_navier_commit_staged", self._h)
+        self._staged_keep = None
+
     def get_time(self):
         return self.time
 

@@ -331,6 +331,23 @@ int rp_navier_update(rp_navier_t* h, int nsteps) {
     N.update(nsteps);
   });
 }
+int rp_navier_stage_state(rp_navier_t* h, const double* temp, size_t len_temp, const double* ux, size_t len_ux,
+                          const double* uy, size_t len_uy, const double* pres, size_t len_pres) {
+  return guard([&] {
+    need(h && temp && ux && uy && pres, RP_ERR_INVALID, "null argument");
+    Navier2D& n = *h->n;
+    need(len_temp == arr_len(n.temp->vhat) && len_ux == arr_len(n.ux->vhat) && len_uy == arr_len(n.uy->vhat) &&
+             len_pres == arr_len(n.pres0->vhat),
+         RP_ERR_SHAPE, "stage_state: size mismatch");
+    n.stage_state(temp, ux, uy, pres);
+  });
+}
+int rp_navier_commit_staged(rp_navier_t* h) {
+  return guard([&] {
+    need(h, RP_ERR_INVALID, "null handle");
+    h->n->commit_staged();
+  });
+}
 int rp_navier_sync(rp_navier_t* h) { NAV_GUARD(N.sync()); }
 int rp_navier_get_time(rp_navier_t* h, double* t) { NAV_GUARD(if (t) *t = N.time); }
 int rp_navier_get_dt(rp_navier_t* h, double* dt) { NAV_GUARD(if (dt) *dt = N.dt); }

@@ -218,6 +218,13 @@ class Navier2D {
     use_graph_ = on;
     graph_dirty_ = true;
   }
+  // Double-buffered state upload (host buffers in the vhat layouts of temp, ux, uy, pres[0]): stage_state() queues
+  // the host-to-device copies on a copy stream of its own and returns; commit_staged() makes the compute stream
+  // wait for them and moves the staged state into place (device-to-device).  The copies of the next state
+  // therefore overlap the update() of the current one.  Host buffers must stay valid (and should be pinned)
+  // until the commit.
+  void stage_state(const double* t, const double* u, const double* v, const double* p);
+  void commit_staged();
 
  private:
   void build_step();
@@ -255,6 +262,12 @@ class Navier2D {
   void run_op(const StepOp& op);
   int launches_per_step_ = 0;
   DevBuf red_;
+  Arr stage_[4];
+  bool staged_ = false;
+#ifndef RP_EMU
+  cudaStream_t copy_stream_ = nullptr;
+  cudaEvent_t ev_staged_ = nullptr, ev_consumed_ = nullptr;
+#endif
 #ifndef RP_EMU
   cudaGraphExec_t graph_ = nullptr;
   bool graph_ok_ = false;

@@ -92,7 +92,54 @@ Navier2D::Navier2D(int nx_, int ny_, double ra_, double pr_, double dt_, double 
 Navier2D::~Navier2D() {
 #ifndef RP_EMU
   if (graph_) cudaGraphExecDestroy(graph_);
+  if (copy_stream_) {
+    cudaStreamSynchronize(copy_stream_);
+    cudaStreamDestroy(copy_stream_);
+    cudaEventDestroy(ev_staged_);
+    cudaEventDestroy(ev_consumed_);
+  }
 #endif
+}
+
+void Navier2D::stage_state(const double* t, const double* u, const double* v, const double* p) {
+  Field2* dst[4] = {temp.get(), ux.get(), uy.get(), pres0.get()};
+  const double* src[4] = {t, u, v, p};
+  cudaStream_t cs = stream;
+#ifndef RP_EMU
+  if (!copy_stream_) {
+    RP_CUDA_CHECK(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
+    RP_CUDA_CHECK(cudaEventCreateWithFlags(&ev_staged_, cudaEventDisableTiming));
+    RP_CUDA_CHECK(cudaEventCreateWithFlags(&ev_consumed_, cudaEventDisableTiming));
+  } else {
+    // the staging arrays may still be read by the previous commit
+    RP_CUDA_CHECK(cudaStreamWaitEvent(copy_stream_, ev_consumed_, 0));
+  }
+  cs = copy_stream_;
+#endif
+  for (int i = 0; i < 4; ++i) {
+    if (!stage_[i].buf.p) stage_[i].alloc(dst[i]->vhat.rows, dst[i]->vhat.cols, dst[i]->vhat.cplx);
+    stage_[i].upload(src[i], cs);
+  }
+#ifndef RP_EMU
+  RP_CUDA_CHECK(cudaEventRecord(ev_staged_, copy_stream_));
+#endif
+  staged_ = true;
+}
+
+void Navier2D::commit_staged() {
+  if (!staged_) throw Error(RP_ERR_INVALID, "commit_staged: no staged state");
+  Field2* dst[4] = {temp.get(), ux.get(), uy.get(), pres0.get()};
+#ifndef RP_EMU
+  RP_CUDA_CHECK(cudaStreamWaitEvent(stream, ev_staged_, 0));
+#endif
+  for (int i = 0; i < 4; ++i) {
+    rt::d2d(dst[i]->vhat.buf.p, stage_[i].buf.p, stage_[i].buf.bytes, stream);
+    ++dst[i]->vhat_version;
+  }
+#ifndef RP_EMU
+  RP_CUDA_CHECK(cudaEventRecord(ev_consumed_, stream));
+#endif
+  staged_ = false;
 }
 
 Field2* Navier2D::field_by_index(int which) {

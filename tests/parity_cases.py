@@ -193,3 +193,40 @@ def check_navier_steps(lib, periodic, nx, ny, nsteps, ra=1e5, pr=1.0, dt=0.01, a
     derr = [abs(a - b) / max(abs(b), 1e-300) for a, b in zip(dn, do)]
     assert abs(n.time - o.time) < 1e-12
     return err, derr, dn, do
+
+
+def check_staged_upload(lib, periodic, nx, ny, steps=3):
+    """stage_state + commit_staged must be the same as assigning the four vhat arrays (bit for bit), also when the
+    next upload is queued while the current step is still running."""
+    import rustpde_b200 as R
+
+    def make():
+        n = (R.Navier2D.new_periodic(nx, ny, 1e5, 1.0, 0.01, 1.0, lib=lib) if periodic
+             else R.Navier2D.new(nx, ny, 1e5, 1.0, 0.01, 1.0, True, lib=lib))
+        n.set_velocity(0.2, 1.0, 1.0)
+        n.set_temperature(0.2, 1.0, 1.0)
+        return n
+
+    src = make()
+    states = []
+    for _ in range(steps):
+        src.update(2)
+        states.append([np.array(f.vhat) for f in (src.temp, src.ux, src.uy, src.pres[0])])
+    a, b = make(), make()
+    outs_a, outs_b = [], []
+    for st in states:  # plain assignment
+        a.temp.vhat, a.ux.vhat, a.uy.vhat = st[0], st[1], st[2]
+        a.pres[0].vhat = st[3]
+        a.update(1)
+        outs_a.append([np.array(f.vhat) for f in (a.temp, a.ux, a.uy, a.pres[0])])
+    b.stage_state(*states[0])
+    for k in range(len(states)):  # double-buffered: upload k+1 is queued behind update k
+        b.commit_staged()
+        b.update(1)
+        if k + 1 < len(states):
+            b.stage_state(*states[k + 1])
+        outs_b.append([np.array(f.vhat) for f in (b.temp, b.ux, b.uy, b.pres[0])])
+    for oa, ob in zip(outs_a, outs_b):
+        for x, y in zip(oa, ob):
+            assert np.array_equal(x, y)
+    return True

@@ -177,3 +177,15 @@ def test_shape_errors(emu):
         R.HholtzAdi(f, [1.0, 1.0]).solve(np.zeros((9, 9)))
     with pytest.raises(R.RustpdeError):
         f.from_ortho(np.zeros((6, 7)))
+
+
+@pytest.mark.parametrize("periodic,nx,ny", [(False, 32, 33), (True, 32, 33)])
+def test_staged_state_upload(emu, periodic, nx, ny):
+    assert pc.check_staged_upload(emu, periodic, nx, ny)
+
+
+def test_commit_without_stage_fails(emu):
+    import rustpde_b200 as R
+    n = R.Navier2D.new(16, 17, 1e4, 1.0, 0.01, 1.0, True, lib=emu)
+    with pytest.raises(R.RustpdeError):
+        n.commit_staged()

@@ -232,3 +232,10 @@ def test_full_size_properties(gpu):
     o = f.to_ortho()
     f.from_ortho(o)
     assert pc.rel(f.vhat, 2.0 * c1 - 3.0 * c2) < 1e-9
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("periodic,nx,ny", [(False, 64, 65), (True, 64, 65), (False, 1024, 1025)])
+def test_staged_state_upload(gpu, periodic, nx, ny):
+    """rp_navier_stage_state / commit_staged (copy stream, overlaps update()) == plain vhat uploads, bit for bit."""
+    assert pc.check_staged_upload(gpu, periodic, nx, ny)
