@@ -11,19 +11,29 @@ namespace rp {
 // (512, 1): without the explicit min-blocks ptxas squeezed the whole call tree into 32 registers
 __global__ void __launch_bounds__(512, 1) lane_vm_kernel(const Program* __restrict__ progs) { lane_vm_body(progs); }
 
+// block tile 128 x BN x 16 (BN = 64: 4 x 2 warps of 32 x 32; BN = 56: 8 x 1 warps of 16 x 56), 3-stage cp.async
+// pipeline; shared tiles: A [m][k] (row stride GLDK), B [k][n] (row stride BN + 4), both padded so that the DMMA
+// fragment loads are conflict-free
+enum { GBM = 128, GBK = 16, GLDK = GBK + 4, GSTAGES = 3 };
+enum { GA_STAGE = GBM * GLDK };
+template <int WN, int NJ>
+struct GemmCfg {
+  static constexpr int WM = 8 / WN;          // warps along m
+  static constexpr int NI = GBM / (8 * WM);  // m8 fragments per warp
+  static constexpr int BN = WN * NJ * 8, LDN = BN + 4;
+  static constexpr int B_STAGE = GBK * LDN;
+  static constexpr int SMEM = GSTAGES * (GA_STAGE + B_STAGE) * (int)sizeof(double);
+};
+template <int WN, int NJ>
 __global__ void __launch_bounds__(256, 2) dgemm_dmma_kernel(GemmArgs g0, GemmArgs g1);
-// block tile 128 x 64 x 16, 3-stage cp.async pipeline; shared tiles: A [m][k] (row stride GLDK),
-// B [k][n] (row stride GLDN), both padded so that the DMMA fragment loads are conflict-free
-enum { GBM = 128, GBN = 64, GBK = 16, GLDK = GBK + 4, GLDN = GBN + 4, GSTAGES = 3 };
-enum { GA_STAGE = GBM * GLDK, GB_STAGE = GBK * GLDN };
-static const int kGemmSmem = GSTAGES * (GA_STAGE + GB_STAGE) * (int)sizeof(double);
 
 void init_kernels() {
 #ifndef RP_EMU
   static bool done = false;
   if (done) return;
   RP_CUDA_CHECK(cudaFuncSetAttribute(lane_vm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RP_MAX_SMEM));
-  RP_CUDA_CHECK(cudaFuncSetAttribute(dgemm_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
+  RP_CUDA_CHECK(cudaFuncSetAttribute(dgemm_dmma_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<2, 4>::SMEM));
+  RP_CUDA_CHECK(cudaFuncSetAttribute(dgemm_dmma_kernel<1, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<1, 7>::SMEM));
   done = true;
 #endif
 }
@@ -75,30 +85,33 @@ RP_DEV void cp_async_wait() {
 #endif
 }
 
+template <int WN, int NJ>
 __global__ void __launch_bounds__(256, 2) dgemm_dmma_kernel(GemmArgs g0, GemmArgs g1) {
+  typedef GemmCfg<WN, NJ> C;
+  constexpr int NI = C::NI, BN = C::BN, LDN = C::LDN;
   const GemmArgs& g = blockIdx.z ? g1 : g0;
   if ((int)(blockIdx.y * GBM) >= g.M) return;
   RP_DYN_SMEM(double, sm);
   double* As = sm;                        // [GSTAGES][GBM][GLDK]
-  double* Bs = sm + GSTAGES * GA_STAGE;   // [GSTAGES][GBK][GLDN]
+  double* Bs = sm + GSTAGES * GA_STAGE;   // [GSTAGES][GBK][LDN]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int m0 = blockIdx.y * GBM, n0 = blockIdx.x * GBN;
-  const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
+  const int m0 = blockIdx.y * GBM, n0 = blockIdx.x * BN;
+  const int wm = (warp / WN) * (8 * NI), wn = (warp % WN) * (8 * NJ);
   const int lr = lane >> 2, lc = lane & 3;
   // number of 8-column blocks of this warp that hold valid columns (ragged last tile)
   int jmax = (g.N - n0 - wn + 7) >> 3;
-  jmax = jmax < 0 ? 0 : (jmax > 4 ? 4 : jmax);
-  double acc[4][4][2];
+  jmax = jmax < 0 ? 0 : (jmax > NJ ? NJ : jmax);
+  double acc[NI][NJ][2];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < NI; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int j = 0; j < NJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
   const int nk = (g.K + GBK - 1) / GBK;
   auto issue = [&](int kt) {
     if (kt < nk) {
       const int st = kt % GSTAGES, k0 = kt * GBK;
       double* a = As + st * GA_STAGE;
-      double* b = Bs + st * GB_STAGE;
+      double* b = Bs + st * C::B_STAGE;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {  // A: 128 rows x 8 chunks
         const int ch = tid + q * 256, row = ch >> 3, kc = (ch & 7) * 2;
@@ -108,14 +121,18 @@ __global__ void __launch_bounds__(256, 2) dgemm_dmma_kernel(GemmArgs g0, GemmArg
         const double* src = bytes ? g.A + (size_t)gm * g.lda + gk : g.A;
         cp_async16(a + row * GLDK + kc, src, bytes);
       }
+      constexpr int BCH = BN / 2, BTOT = GBK * BCH;  // B: 16 rows x BN / 2 chunks
 #pragma unroll
-      for (int q = 0; q < 2; ++q) {  // B: 16 rows x 32 chunks
-        const int ch = tid + q * 256, row = ch >> 5, nc = (ch & 31) * 2;
-        const int gk = k0 + row, gn = n0 + nc;
-        int bytes = (gk < g.K) ? (g.N - gn) * 8 : 0;
-        bytes = bytes < 0 ? 0 : (bytes > 16 ? 16 : bytes);
-        const double* src = bytes ? g.B + (size_t)(g.b_r0 + (long long)gk * g.b_rs) * g.ldb + gn : g.B;
-        cp_async16(b + row * GLDN + nc, src, bytes);
+      for (int q = 0; q < (BTOT + 255) / 256; ++q) {
+        const int ch = tid + q * 256;
+        if (BTOT % 256 == 0 || ch < BTOT) {
+          const int row = ch / BCH, nc = (ch % BCH) * 2;
+          const int gk = k0 + row, gn = n0 + nc;
+          int bytes = (gk < g.K) ? (g.N - gn) * 8 : 0;
+          bytes = bytes < 0 ? 0 : (bytes > 16 ? 16 : bytes);
+          const double* src = bytes ? g.B + (size_t)(g.b_r0 + (long long)gk * g.b_rs) * g.ldb + gn : g.B;
+          cp_async16(b + row * LDN + nc, src, bytes);
+        }
       }
     }
     cp_async_commit();
@@ -127,31 +144,31 @@ __global__ void __launch_bounds__(256, 2) dgemm_dmma_kernel(GemmArgs g0, GemmArg
     __syncthreads();
     issue(kt + GSTAGES - 1);
     const double* a = As + (kt % GSTAGES) * GA_STAGE;
-    const double* b = Bs + (kt % GSTAGES) * GB_STAGE;
+    const double* b = Bs + (kt % GSTAGES) * C::B_STAGE;
     if (jmax > 0) {
 #pragma unroll
       for (int kk = 0; kk < GBK; kk += 4) {
-        double af[4], bf[4];
+        double af[NI], bf[NJ];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) af[i] = a[(wm + 8 * i + lr) * GLDK + kk + lc];
+        for (int i = 0; i < NI; ++i) af[i] = a[(wm + 8 * i + lr) * GLDK + kk + lc];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) bf[j] = b[(kk + lc) * GLDN + wn + 8 * j + lr];
+        for (int j = 0; j < NJ; ++j) bf[j] = b[(kk + lc) * LDN + wn + 8 * j + lr];
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+        for (int j = 0; j < NJ; ++j)
           if (j < jmax) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+            for (int i = 0; i < NI; ++i) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
           }
       }
     }
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < NI; ++i) {
     const int gm = m0 + wm + 8 * i + lr;
     if (gm >= g.M) continue;
     double* crow = g.C + (size_t)(g.c_r0 + (long long)gm * g.c_rs) * g.ldc;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < NJ; ++j) {
       const int gn = n0 + wn + 8 * j + 2 * lc;
       if (gn < g.N) crow[gn] = acc[i][j][0];
       if (gn + 1 < g.N) crow[gn + 1] = acc[i][j][1];
@@ -159,19 +176,55 @@ __global__ void __launch_bounds__(256, 2) dgemm_dmma_kernel(GemmArgs g0, GemmArg
   }
 }
 
+// Tile width: 64 columns, or 56 when that needs less time in units of (waves of 2 blocks per SM) x (tile width) --
+// e.g. the two 1023 x 1023 x 2047 products of the parity-split solve at 2048 x 2049 are 2 x 8 x 37 = 592 tiles of
+// 128 x 56 = exactly two waves on 148 SMs, against 512 tiles = 1.73 -> 2 waves of 128 x 64.
+static int gemm_sm_count() {
+#ifndef RP_EMU
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return n;
+#else
+  return 1;
+#endif
+}
+static int gemm_tile_width(int M, int N, int nz) {
+  static const char* e = getenv("RUSTPDE_B200_GEMM_BN");
+  if (e) return atoi(e) == 56 ? 56 : 64;
+  const long long slots = 2LL * gemm_sm_count();
+  const long long mt = (M + GBM - 1) / GBM;
+  const long long t64 = mt * ((N + 63) / 64) * nz, t56 = mt * ((N + 55) / 56) * nz;
+  const long long c64 = ((t64 + slots - 1) / slots) * 64, c56 = ((t56 + slots - 1) / slots) * 56;
+  // (a grid that fits one wave keeps the 64-wide tile: its blocks do not all share an SM, and the 4 x 2 warp layout
+  // needs fewer fragment loads per DMMA)
+  return (t64 > slots && c56 * 21 < c64 * 20) ? 56 : 64;
+}
+
+static const int kSmem56 = GemmCfg<1, 7>::SMEM, kSmem64 = GemmCfg<2, 4>::SMEM;
 void launch_dgemm(const GemmArgs& g, cudaStream_t s) {
   if (g.M <= 0 || g.N <= 0) return;
-  const int smem = kGemmSmem;
   init_kernels();
-  dim3 grid((g.N + GBN - 1) / GBN, (g.M + GBM - 1) / GBM);
-  RP_LAUNCH(dgemm_dmma_kernel, grid, dim3(256), (size_t)smem, s, g, g);
+  const int bn = gemm_tile_width(g.M, g.N, 1);
+  dim3 grid((g.N + bn - 1) / bn, (g.M + GBM - 1) / GBM);
+  if (bn == 56)
+    RP_LAUNCH((dgemm_dmma_kernel<1, 7>), grid, dim3(256), (size_t)kSmem56, s, g, g);
+  else
+    RP_LAUNCH((dgemm_dmma_kernel<2, 4>), grid, dim3(256), (size_t)kSmem64, s, g, g);
 }
 void launch_dgemm2(const GemmArgs& g0, const GemmArgs& g1, cudaStream_t s) {
   if (g0.N <= 0 || g0.M <= 0) return;
   init_kernels();
   const int mmax = std::max(g0.M, g1.M);
-  dim3 grid((g0.N + GBN - 1) / GBN, (mmax + GBM - 1) / GBM, 2);
-  RP_LAUNCH(dgemm_dmma_kernel, grid, dim3(256), (size_t)kGemmSmem, s, g0, g1);
+  const int bn = gemm_tile_width(mmax, g0.N, 2);
+  dim3 grid((g0.N + bn - 1) / bn, (mmax + GBM - 1) / GBM, 2);
+  if (bn == 56)
+    RP_LAUNCH((dgemm_dmma_kernel<1, 7>), grid, dim3(256), (size_t)kSmem56, s, g0, g1);
+  else
+    RP_LAUNCH((dgemm_dmma_kernel<2, 4>), grid, dim3(256), (size_t)kSmem64, s, g0, g1);
 }
 
 // ===========================================================================
