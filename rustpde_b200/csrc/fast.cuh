@@ -20,6 +20,8 @@
 // chunk maps are chained through a small shared array, and the chunk is
 // re-walked with its carry-in.
 #pragma once
+#include <utility>
+
 #include "fast.h"
 
 namespace rp {
@@ -600,12 +602,38 @@ FK_DEV void dct_bluestein(const double* ta, double* tw_, const DctTab& T, double
   dct_odd_scan_v<LC, NTHR, (LB / 4 + scan_threads(NTHR) / LC - 1) / (scan_threads(NTHR) / LC), BWD>(W, N, red);
 }
 
+// ---- chunk-major ("permuted") coefficient tables -------------------------------------------------
+// In a chunked scan the threads of a warp work on elements that are a whole chunk apart, so a load of
+// coefficient[i] touches one 128-byte line per chunk group -- the tables, not the data, then dominate the L1
+// traffic of the banded solves.  A permuted table stores the coefficients of scan element (group g, step u,
+// parity p) at slot (u * NG + g) * 2 + p: the slots a warp reads in one step are contiguous.  Functors of the
+// scans may take the slot as a third argument (host side: fk::perm_table, fast.h).
+template <class F, class... A>
+struct fk_takes {
+  template <class G>
+  static auto test(int) -> decltype(std::declval<G>()(std::declval<A>()...), char());
+  template <class G>
+  static long test(...);
+  static constexpr bool value = sizeof(test<F>(0)) == 1;
+};
+template <class F>
+FK_DEV auto fcall(F& f, int i, int l, int slot) {
+  if constexpr (fk_takes<F, int, int, int>::value)
+    return f(i, l, slot);
+  else
+    return f(i, l);
+}
+
 // ---- chunked scans over the 8 parity chains of a tile ---------------------------
 // Dependency order t = 0..M-1 of the chain of parity p; element m = FWD ? t : M-1-t,
 // natural index i = 2m + p.
 //   y_t = in(i, lane) + c1(i, lane) * y_{t-1}
 // `out(i, lane, y)` is called after every input of the block has been read, so
 // it may overwrite the tile the inputs came from (any row).
+// The inputs and coefficients of a chunk are fetched by branch-free loops (clamped indices) before the serial
+// chain starts: all loads of a (sub-)batch are in flight together, instead of one exposed L2 round trip per chunk
+// element (the coefficient tables do not stay in the small L1 left beside the tiles).
+#define FK_SCAN_SB 8  // sub-batch of the loops that re-fetch coefficients
 template <int LC, int NTHR, int CL, bool FWD, class In, class C1, class Out>
 FK_DEV void scan1(int n, double* red, In in, C1 c1, Out out) {
   constexpr int LR = 2 * LC, NCH = 2 * LR;  // chains per tile: LR lanes x 2 parities
@@ -615,17 +643,28 @@ FK_DEV void scan1(int n, double* red, In in, C1 c1, Out out) {
   const int M = (tid < NSC) ? ((n - p + 1) >> 1) : 0;  // threads beyond NSC own empty chunks
   const int cl = (((n + 1) >> 1) + NG - 1) / NG;
   const int t0 = g * cl, t1 = min(t0 + cl, M);
+  auto idx = [&](int t) { return 2 * (FWD ? t : M - 1 - t) + p; };
+  constexpr int SB = FK_SCAN_SB;
   double q[CL];
   double A = 1.0, b = 0.0;
+  if (M > 0) {
 #pragma unroll
-  for (int u = 0; u < CL; ++u) {
-    const int t = t0 + u;
-    if (t < t1) {
-      const int i = 2 * (FWD ? t : M - 1 - t) + p;
-      q[u] = in(i, lane);
-      const double k = c1(i, lane);
-      b = fma(k, b, q[u]);
-      A *= k;
+    for (int u0 = 0; u0 < CL; u0 += SB) {
+      double k[SB];
+#pragma unroll
+      for (int v = 0; v < SB; ++v)
+        if (u0 + v < CL) {
+          const int i = idx(min(t0 + u0 + v, M - 1));
+          const int sl = ((u0 + v) * NG + g) * 2 + p;
+          q[u0 + v] = fcall(in, i, lane, sl);
+          k[v] = fcall(c1, i, lane, sl);
+        }
+#pragma unroll
+      for (int v = 0; v < SB; ++v)
+        if (u0 + v < CL && t0 + u0 + v < t1) {
+          b = fma(k[v], b, q[u0 + v]);
+          A *= k[v];
+        }
     }
   }
   // two-level carry: maps of groups of 8 chunks, then the chunks inside the group
@@ -639,9 +678,9 @@ FK_DEV void scan1(int n, double* red, In in, C1 c1, Out out) {
   if (act && (g & 7) == 0) {
     double Ag = 1.0, bg = 0.0;
 #pragma unroll
-    for (int k = 0; k < 8; ++k)
-      if (g + k < NG) {
-        const double Ak = red[((g + k) * NCH + ch) * 2], bk = red[((g + k) * NCH + ch) * 2 + 1];
+    for (int kk = 0; kk < 8; ++kk)
+      if (g + kk < NG) {
+        const double Ak = red[((g + kk) * NCH + ch) * 2], bk = red[((g + kk) * NCH + ch) * 2 + 1];
         bg = fma(Ak, bg, bk);
         Ag *= Ak;
       }
@@ -654,44 +693,63 @@ FK_DEV void scan1(int n, double* red, In in, C1 c1, Out out) {
     for (int gg = 0; gg < (g >> 3); ++gg) y = fma(red2[(gg * NCH + ch) * 2], y, red2[(gg * NCH + ch) * 2 + 1]);
     for (int gg = (g & ~7); gg < g; ++gg) y = fma(red[(gg * NCH + ch) * 2], y, red[(gg * NCH + ch) * 2 + 1]);
   }
+  if (M > 0) {
 #pragma unroll
-  for (int u = 0; u < CL; ++u) {
-    const int t = t0 + u;
-    if (t < t1) {
-      const int i = 2 * (FWD ? t : M - 1 - t) + p;
-      y = fma(c1(i, lane), y, q[u]);
-      out(i, lane, y);
+    for (int u0 = 0; u0 < CL; u0 += SB) {
+      double k[SB];
+#pragma unroll
+      for (int v = 0; v < SB; ++v)
+        if (u0 + v < CL) k[v] = fcall(c1, idx(min(t0 + u0 + v, M - 1)), lane, ((u0 + v) * NG + g) * 2 + p);
+#pragma unroll
+      for (int v = 0; v < SB; ++v)
+        if (u0 + v < CL && t0 + u0 + v < t1) {
+          y = fma(k[v], y, q[u0 + v]);
+          out(idx(t0 + u0 + v), lane, y);
+        }
     }
   }
   __syncthreads();
 }
 
 //   y_t = in(i, lane) + c1(i, lane) * y_{t-1} + c2(i, lane) * y_{t-2}
+// in(i, lane) is evaluated again in the second walk (no register copy of the chunk): out(i, lane, .) of a
+// thread may only overwrite what in(i, lane) of the same thread read -- true for every use (element-wise in place).
 template <int LC, int NTHR, int CL, bool FWD, class In, class C1, class C2, class Out>
 FK_DEV void scan2(int n, double* red, In in, C1 c1, C2 c2, Out out) {
   constexpr int LR = 2 * LC, NCH = 2 * LR;  // chains per tile: LR lanes x 2 parities
   constexpr int NSC = scan_threads(NTHR), NG = NSC / NCH;
+  constexpr int SB = FK_SCAN_SB;
   const int tid = threadIdx.x, ch = tid % NCH, g = tid / NCH;
   const int lane = ch % LR, p = ch / LR;
   const int M = (tid < NSC) ? ((n - p + 1) >> 1) : 0;
   const int cl = (((n + 1) >> 1) + NG - 1) / NG;
   const int t0 = g * cl, t1 = min(t0 + cl, M);
-  double q[CL];
+  auto idx = [&](int t) { return 2 * (FWD ? t : M - 1 - t) + p; };
   // particular solution and the two homogeneous ones, states (y_{t-1}, y_{t-2})
   double p1 = 0.0, p2 = 0.0, a1 = 1.0, a2 = 0.0, b1 = 0.0, b2 = 1.0;
+  if (M > 0) {
 #pragma unroll
-  for (int u = 0; u < CL; ++u) {
-    const int t = t0 + u;
-    if (t < t1) {
-      const int i = 2 * (FWD ? t : M - 1 - t) + p;
-      q[u] = in(i, lane);
-      const double k1 = c1(i, lane), k2 = c2(i, lane);
-      const double pn = fma(k1, p1, fma(k2, p2, q[u]));
-      const double an = fma(k1, a1, k2 * a2);
-      const double bn = fma(k1, b1, k2 * b2);
-      p2 = p1, p1 = pn;
-      a2 = a1, a1 = an;
-      b2 = b1, b1 = bn;
+    for (int u0 = 0; u0 < CL; u0 += SB) {
+      double q[SB], k1[SB], k2[SB];
+#pragma unroll
+      for (int v = 0; v < SB; ++v)
+        if (u0 + v < CL) {
+          const int i = idx(min(t0 + u0 + v, M - 1));
+          const int sl = ((u0 + v) * NG + g) * 2 + p;
+          q[v] = fcall(in, i, lane, sl);
+          k1[v] = fcall(c1, i, lane, sl);
+          k2[v] = fcall(c2, i, lane, sl);
+        }
+#pragma unroll
+      for (int v = 0; v < SB; ++v)
+        if (u0 + v < CL && t0 + u0 + v < t1) {
+          const double pn = fma(k1[v], p1, fma(k2[v], p2, q[v]));
+          const double an = fma(k1[v], a1, k2[v] * a2);
+          const double bn = fma(k1[v], b1, k2[v] * b2);
+          p2 = p1, p1 = pn;
+          a2 = a1, a1 = an;
+          b2 = b1, b1 = bn;
+        }
     }
   }
   const bool act = tid < NSC;
@@ -731,14 +789,26 @@ FK_DEV void scan2(int n, double* red, In in, C1 c1, C2 c2, Out out) {
     const double n2 = fma(rr[3], y1, fma(rr[4], y2, rr[5]));
     y1 = n1, y2 = n2;
   }
+  if (M > 0) {
 #pragma unroll
-  for (int u = 0; u < CL; ++u) {
-    const int t = t0 + u;
-    if (t < t1) {
-      const int i = 2 * (FWD ? t : M - 1 - t) + p;
-      const double yn = fma(c1(i, lane), y1, fma(c2(i, lane), y2, q[u]));
-      y2 = y1, y1 = yn;
-      out(i, lane, yn);
+    for (int u0 = 0; u0 < CL; u0 += SB) {
+      double q[SB], k1[SB], k2[SB];  // in() again: valid because out(i, .) only overwrites what in(i, .) read
+#pragma unroll
+      for (int v = 0; v < SB; ++v)
+        if (u0 + v < CL) {
+          const int i = idx(min(t0 + u0 + v, M - 1));
+          const int sl = ((u0 + v) * NG + g) * 2 + p;
+          q[v] = fcall(in, i, lane, sl);
+          k1[v] = fcall(c1, i, lane, sl);
+          k2[v] = fcall(c2, i, lane, sl);
+        }
+#pragma unroll
+      for (int v = 0; v < SB; ++v)
+        if (u0 + v < CL && t0 + u0 + v < t1) {
+          const double yn = fma(k1[v], y1, fma(k2[v], y2, q[v]));
+          y2 = y1, y1 = yn;
+          out(idx(t0 + u0 + v), lane, yn);
+        }
     }
   }
   __syncthreads();
@@ -783,23 +853,46 @@ FK_DEV void b2_fdma(double* t, int sn, int n, const B2Tabs& B, const FdmaTabs& F
       [&](int i, int l, double y) { t[didx<LC>(rowof(sn, i), l)] = y; });
 }
 
+// b2_fdma with chunk-major packed coefficient tables (fast.h perm_table): pt1[slot] = {lo, di, up, fp} in the
+// order of the forward sweep, pt2[slot] = {bs, bp1, bp2, -} in the order of the backward sweep
+template <int LC, int NTHR, int CL>
+FK_DEV void b2_fdma_perm(double* t, int sn, int n, const double* __restrict__ pt1, const double* __restrict__ pt2, double* red) {
+  const int m = n - 2;
+  const double2* P1 = (const double2*)pt1;
+  const double2* P2 = (const double2*)pt2;
+  scan1<LC, NTHR, CL, true>(
+      m, red,
+      [&](int i, int l, int s) {
+        const double2 a = __ldg(&P1[2 * s]), b = __ldg(&P1[2 * s + 1]);  // lo, di | up, fp
+        return fma(a.x, t[didx<LC>(rowof(sn, i), l)],
+                   fma(a.y, t[didx<LC>(rowof(sn, i + 2), l)], (i + 4 < n) ? b.x * t[didx<LC>(rowof(sn, i + 4), l)] : 0.0));
+      },
+      [&](int, int, int s) { return __ldg(&P1[2 * s + 1]).y; }, [&](int i, int l, double y) { t[didx<LC>(rowof(sn, i), l)] = y; });
+  scan2<LC, NTHR, CL, false>(
+      m, red, [&](int i, int l, int s) { return __ldg(&P2[2 * s]).x * t[didx<LC>(rowof(sn, i), l)]; },
+      [&](int, int, int s) { return __ldg(&P2[2 * s]).y; }, [&](int, int, int s) { return __ldg(&P2[2 * s + 1]).x; },
+      [&](int i, int l, double y) { t[didx<LC>(rowof(sn, i), l)] = y; });
+}
+
 // from_ortho (composite_stencil.rs:250-276): c = S^T p, then the (S^T S) solve.
 // In place on tile t (layout sn): n ortho coefficients -> m = n-2 composite ones.
 template <int LC, int NTHR, int CL>
 FK_DEV void from_ortho(double* t, int sn, int n, const TdmaTabs& T, double* red) {
   const int m = n - 2;
+  const double2* PF = (const double2*)T.pf;  // slot: sd, sl | fs, fp   (chunk-major packed, fast.h)
+  const double* PB = T.pb;
   scan1<LC, NTHR, CL, true>(
       m, red,
-      [&](int i, int l) {
-        const double c = fma(__ldg(&T.sd[i]), t[didx<LC>(rowof(sn, i), l)], __ldg(&T.sl[i]) * t[didx<LC>(rowof(sn, i + 2), l)]);
-        return __ldg(&T.fs[i]) * c;
+      [&](int i, int l, int s) {
+        const double2 a = __ldg(&PF[2 * s]);
+        const double c = fma(a.x, t[didx<LC>(rowof(sn, i), l)], a.y * t[didx<LC>(rowof(sn, i + 2), l)]);
+        return __ldg(&PF[2 * s + 1]).x * c;
       },
-      [&](int i, int) { return __ldg(&T.fp[i]); }, [&](int i, int l, double y) { t[didx<LC>(rowof(sn, i), l)] = y; });
+      [&](int, int, int s) { return __ldg(&PF[2 * s + 1]).y; }, [&](int i, int l, double y) { t[didx<LC>(rowof(sn, i), l)] = y; });
   scan1<LC, NTHR, CL, false>(
-      m, red, [&](int i, int l) { return t[didx<LC>(rowof(sn, i), l)]; }, [&](int i, int) { return __ldg(&T.bp[i]); },
+      m, red, [&](int i, int l) { return t[didx<LC>(rowof(sn, i), l)]; }, [&](int, int, int s) { return __ldg(&PB[s]); },
       [&](int i, int l, double y) { t[didx<LC>(rowof(sn, i), l)] = y; });
 }
-
 
 // =====================================================================================
 // Two-lane ("v") forms of the building blocks: a thread works on one packed complex
@@ -834,17 +927,29 @@ FK_DEV void scan1v(int n, double* red_, In in, C1 c1, Out out) {
   const int M = act ? ((n - p + 1) >> 1) : 0;  // threads beyond NSC own empty chunks
   const int cl = (((n + 1) >> 1) + NG - 1) / NG;
   const int t0 = g * cl, t1 = min(t0 + cl, M);
+  auto idx = [&](int t) { return 2 * (FWD ? t : M - 1 - t) + p; };
+  typedef decltype(fcall(c1, 0, 0, 0)) K;
+  constexpr int SB = FK_SCAN_SB;
   cplx q[CL];
   cplx A = mk(1.0, 1.0), b = mk(0.0, 0.0);
+  if (M > 0) {
 #pragma unroll
-  for (int u = 0; u < CL; ++u) {
-    const int t = t0 + u;
-    if (t < t1) {
-      const int i = 2 * (FWD ? t : M - 1 - t) + p;
-      q[u] = in(i, c);
-      const auto k = c1(i, c);
-      b = kfma(k, b, q[u]);
-      A = kmul(k, A);
+    for (int u0 = 0; u0 < CL; u0 += SB) {  // branch-free fetch of a sub-batch (see scan1), then its part of the chain
+      K k[SB];
+#pragma unroll
+      for (int v = 0; v < SB; ++v)
+        if (u0 + v < CL) {
+          const int i = idx(min(t0 + u0 + v, M - 1));
+          const int sl = ((u0 + v) * NG + g) * 2 + p;
+          q[u0 + v] = fcall(in, i, c, sl);
+          k[v] = fcall(c1, i, c, sl);
+        }
+#pragma unroll
+      for (int v = 0; v < SB; ++v)
+        if (u0 + v < CL && t0 + u0 + v < t1) {
+          b = kfma(k[v], b, q[u0 + v]);
+          A = kmul(k[v], A);
+        }
     }
   }
   cplx* red2 = red + NG * NCH * 2;
@@ -871,13 +976,19 @@ FK_DEV void scan1v(int n, double* red_, In in, C1 c1, Out out) {
     for (int gg = 0; gg < (g >> 3); ++gg) y = lfma(red2[(gg * NCH + ch) * 2], y, red2[(gg * NCH + ch) * 2 + 1]);
     for (int gg = (g & ~7); gg < g; ++gg) y = lfma(red[(gg * NCH + ch) * 2], y, red[(gg * NCH + ch) * 2 + 1]);
   }
+  if (M > 0) {
 #pragma unroll
-  for (int u = 0; u < CL; ++u) {
-    const int t = t0 + u;
-    if (t < t1) {
-      const int i = 2 * (FWD ? t : M - 1 - t) + p;
-      y = kfma(c1(i, c), y, q[u]);
-      out(i, c, y);
+    for (int u0 = 0; u0 < CL; u0 += SB) {
+      K k[SB];
+#pragma unroll
+      for (int v = 0; v < SB; ++v)
+        if (u0 + v < CL) k[v] = fcall(c1, idx(min(t0 + u0 + v, M - 1)), c, ((u0 + v) * NG + g) * 2 + p);
+#pragma unroll
+      for (int v = 0; v < SB; ++v)
+        if (u0 + v < CL && t0 + u0 + v < t1) {
+          y = kfma(k[v], y, q[u0 + v]);
+          out(idx(t0 + u0 + v), c, y);
+        }
     }
   }
   __syncthreads();
@@ -898,25 +1009,40 @@ FK_DEV void scan2v(int n, double* red_, In in, C1 c1, C2 c2, Out out) {
   const int M = act ? ((n - p + 1) >> 1) : 0;
   const int cl = (((n + 1) >> 1) + NG - 1) / NG;
   const int t0 = g * cl, t1 = min(t0 + cl, M);
+  auto idx = [&](int t) { return 2 * (FWD ? t : M - 1 - t) + p; };
+  typedef decltype(fcall(c1, 0, 0, 0)) K1;
+  typedef decltype(fcall(c2, 0, 0, 0)) K2;
+  constexpr int SB = FK_SCAN_SB;
   cplx q[CACHE ? CL : 1];
   const cplx one = mk(1.0, 1.0), zero = mk(0.0, 0.0);
   // particular solution and the two homogeneous ones, states (y_{t-1}, y_{t-2})
   cplx p1 = zero, p2 = zero, a1 = one, a2 = zero, b1 = zero, b2 = one;
+  if (M > 0) {
 #pragma unroll
-  for (int u = 0; u < CL; ++u) {
-    const int t = t0 + u;
-    if (t < t1) {
-      const int i = 2 * (FWD ? t : M - 1 - t) + p;
-      const cplx qu = in(i, c);
-      if (CACHE) q[u] = qu;
-      const auto k1 = c1(i, c);
-      const auto k2 = c2(i, c);
-      const cplx pn = kfma(k1, p1, kfma(k2, p2, qu));
-      const cplx an = kfma(k1, a1, kmul(k2, a2));
-      const cplx bn = kfma(k1, b1, kmul(k2, b2));
-      p2 = p1, p1 = pn;
-      a2 = a1, a1 = an;
-      b2 = b1, b1 = bn;
+    for (int u0 = 0; u0 < CL; u0 += SB) {  // branch-free fetch of a sub-batch, then its part of the chain
+      cplx qq[SB];
+      K1 k1[SB];
+      K2 k2[SB];
+#pragma unroll
+      for (int v = 0; v < SB; ++v)
+        if (u0 + v < CL) {
+          const int i = idx(min(t0 + u0 + v, M - 1));
+          const int sl = ((u0 + v) * NG + g) * 2 + p;
+          qq[v] = fcall(in, i, c, sl);
+          if (CACHE) q[u0 + v] = qq[v];
+          k1[v] = fcall(c1, i, c, sl);
+          k2[v] = fcall(c2, i, c, sl);
+        }
+#pragma unroll
+      for (int v = 0; v < SB; ++v)
+        if (u0 + v < CL && t0 + u0 + v < t1) {
+          const cplx pn = kfma(k1[v], p1, kfma(k2[v], p2, qq[v]));
+          const cplx an = kfma(k1[v], a1, kmul(k2[v], a2));
+          const cplx bn = kfma(k1[v], b1, kmul(k2[v], b2));
+          p2 = p1, p1 = pn;
+          a2 = a1, a1 = an;
+          b2 = b1, b1 = bn;
+        }
     }
   }
   if (act) {
@@ -953,15 +1079,28 @@ FK_DEV void scan2v(int n, double* red_, In in, C1 c1, C2 c2, Out out) {
     const cplx n2 = lfma(rr[3], y1, lfma(rr[4], y2, rr[5]));
     y1 = n1, y2 = n2;
   }
+  if (M > 0) {
 #pragma unroll
-  for (int u = 0; u < CL; ++u) {
-    const int t = t0 + u;
-    if (t < t1) {
-      const int i = 2 * (FWD ? t : M - 1 - t) + p;
-      const cplx qu = CACHE ? q[u] : in(i, c);
-      const cplx yn = kfma(c1(i, c), y1, kfma(c2(i, c), y2, qu));
-      y2 = y1, y1 = yn;
-      out(i, c, yn);
+    for (int u0 = 0; u0 < CL; u0 += SB) {
+      cplx qq[SB];
+      K1 k1[SB];
+      K2 k2[SB];
+#pragma unroll
+      for (int v = 0; v < SB; ++v)
+        if (u0 + v < CL) {
+          const int i = idx(min(t0 + u0 + v, M - 1));
+          const int sl = ((u0 + v) * NG + g) * 2 + p;
+          qq[v] = CACHE ? q[u0 + v] : fcall(in, i, c, sl);
+          k1[v] = fcall(c1, i, c, sl);
+          k2[v] = fcall(c2, i, c, sl);
+        }
+#pragma unroll
+      for (int v = 0; v < SB; ++v)
+        if (u0 + v < CL && t0 + u0 + v < t1) {
+          const cplx yn = kfma(k1[v], y1, kfma(k2[v], y2, qq[v]));
+          y2 = y1, y1 = yn;
+          out(idx(t0 + u0 + v), c, yn);
+        }
     }
   }
   __syncthreads();
@@ -983,19 +1122,23 @@ FK_DEV void cheb_diff_v(const cplx* src, int sn_s, cplx* dst, int sn_d, int n, d
 // HholtzAdi half step (see b2_fdma).  NSC2 threads run the second-order sweep; its scratch `red2`
 // needs scan2v_bytes(NSC2) bytes, `red` scan1v_bytes(scan_threads(NTHR)).
 template <int LC, int NTHR, int NMAX, int NSC2>
-FK_DEV void b2_fdma_v(cplx* t, int sn, int n, const B2Tabs& B, const FdmaTabs& F, double* red, double* red2) {
+FK_DEV void b2_fdma_v(cplx* t, int sn, int n, const double* __restrict__ pt1, const double* __restrict__ pt2, double* red,
+                      double* red2) {
   const int m = n - 2;
   constexpr int NSC = scan_threads(NTHR);
+  const double2* P1 = (const double2*)pt1;  // slot: lo, di | up, fp   (chunk-major packed, fast.h)
+  const double2* P2 = (const double2*)pt2;  // slot: bs, bp1 | bp2, -
   scan1v<LC, NTHR, NSC, chunk_len_v(NMAX, NSC, LC), true>(
       m, red,
-      [&](int i, int c) {
-        const cplx up = (i + 4 < n) ? cscale(t[cidx<LC>(rowof(sn, i + 4), c)], __ldg(&B.up[i])) : mk(0.0, 0.0);
-        return sfma(__ldg(&B.lo[i]), t[cidx<LC>(rowof(sn, i), c)], sfma(__ldg(&B.di[i]), t[cidx<LC>(rowof(sn, i + 2), c)], up));
+      [&](int i, int c, int s) {
+        const double2 a = __ldg(&P1[2 * s]), b = __ldg(&P1[2 * s + 1]);
+        const cplx up = (i + 4 < n) ? cscale(t[cidx<LC>(rowof(sn, i + 4), c)], b.x) : mk(0.0, 0.0);
+        return sfma(a.x, t[cidx<LC>(rowof(sn, i), c)], sfma(a.y, t[cidx<LC>(rowof(sn, i + 2), c)], up));
       },
-      [&](int i, int) { return __ldg(&F.fp[i]); }, [&](int i, int c, cplx y) { t[cidx<LC>(rowof(sn, i), c)] = y; });
+      [&](int, int, int s) { return __ldg(&P1[2 * s + 1]).y; }, [&](int i, int c, cplx y) { t[cidx<LC>(rowof(sn, i), c)] = y; });
   scan2v<LC, NTHR, NSC2, chunk_len_v(NMAX, NSC2, LC), false, false>(
-      m, red2, [&](int i, int c) { return cscale(t[cidx<LC>(rowof(sn, i), c)], __ldg(&F.bs[i])); },
-      [&](int i, int) { return __ldg(&F.bp1[i]); }, [&](int i, int) { return __ldg(&F.bp2[i]); },
+      m, red2, [&](int i, int c, int s) { return cscale(t[cidx<LC>(rowof(sn, i), c)], __ldg(&P2[2 * s]).x); },
+      [&](int, int, int s) { return __ldg(&P2[2 * s]).y; }, [&](int, int, int s) { return __ldg(&P2[2 * s + 1]).x; },
       [&](int i, int c, cplx y) { t[cidx<LC>(rowof(sn, i), c)] = y; });
 }
 
@@ -1005,15 +1148,18 @@ FK_DEV void from_ortho_v(cplx* t, int sn, int n, const TdmaTabs& T, double* red)
   const int m = n - 2;
   constexpr int NSC = scan_threads(NTHR);
   constexpr int CL = chunk_len_v(NMAX, NSC, LC);
+  const double2* PF = (const double2*)T.pf;  // slot: sd, sl | fs, fp
+  const double* PB = T.pb;
   scan1v<LC, NTHR, NSC, CL, true>(
       m, red,
-      [&](int i, int c) {
-        const cplx v = sfma(__ldg(&T.sd[i]), t[cidx<LC>(rowof(sn, i), c)], cscale(t[cidx<LC>(rowof(sn, i + 2), c)], __ldg(&T.sl[i])));
-        return cscale(v, __ldg(&T.fs[i]));
+      [&](int i, int c, int s) {
+        const double2 a = __ldg(&PF[2 * s]);
+        const cplx v = sfma(a.x, t[cidx<LC>(rowof(sn, i), c)], cscale(t[cidx<LC>(rowof(sn, i + 2), c)], a.y));
+        return cscale(v, __ldg(&PF[2 * s + 1]).x);
       },
-      [&](int i, int) { return __ldg(&T.fp[i]); }, [&](int i, int c, cplx y) { t[cidx<LC>(rowof(sn, i), c)] = y; });
+      [&](int, int, int s) { return __ldg(&PF[2 * s + 1]).y; }, [&](int i, int c, cplx y) { t[cidx<LC>(rowof(sn, i), c)] = y; });
   scan1v<LC, NTHR, NSC, CL, false>(
-      m, red, [&](int i, int c) { return t[cidx<LC>(rowof(sn, i), c)]; }, [&](int i, int) { return __ldg(&T.bp[i]); },
+      m, red, [&](int i, int c) { return t[cidx<LC>(rowof(sn, i), c)]; }, [&](int, int, int s) { return __ldg(&PB[s]); },
       [&](int i, int c, cplx y) { t[cidx<LC>(rowof(sn, i), c)] = y; });
 }
 

@@ -6,6 +6,8 @@
 // FFT), x lanes of any n0 whose Bluestein length 2^k >= 2 (n0 - 1) - 1 is
 // instantiated.  Everything else stays on the generic lane programs.
 #pragma once
+#include <vector>
+
 #include "lane_prog.h"
 
 namespace rp {
@@ -32,6 +34,7 @@ struct B2Tabs {  // B2 preconditioner rows (matvec.rs:172-193)
 };
 struct TdmaTabs {  // from_ortho: S^T then the pre-factored (S^T S) solve
   const double *sd, *sl, *fs, *fp, *bp;
+  const double *pf, *pb;  // chunk-major packed copies (perm_table): forward {sd, sl, fs, fp} (W = 4), backward {bp} (W = 1)
 };
 struct ModeTabs {  // per-lane A + (lam + alpha) C (fdma_tensor.rs:219-227)
   const double *a_low, *a_up1, *a_up2, *c_low, *c_up1, *c_up2;
@@ -39,10 +42,30 @@ struct ModeTabs {  // per-lane A + (lam + alpha) C (fdma_tensor.rs:219-227)
   double alpha;
   const double* inv;  // swept pivot reciprocals, [lanes][inv_ld]
   long long inv_ld;
+  // chunk-major packed copies (perm_table): forward sweep {b2 lo, di, up, a_low[i-2], c_low[i-2], -} (W = 6),
+  // backward sweep {a_up1, c_up1, a_up2, c_up2, a_up2[i-2], c_up2[i-2], a_low[i-2], c_low[i-2]} (W = 8)
+  const double *pf, *pb;
 };
 
 bool y_supported(int n1);
 bool x_supported(int n0);
+
+// ---- chunk-major coefficient tables of the chunked scans (fast.cuh) ------------------------------
+// A scan over m elements is cut into NG chunks per parity chain of cl = ceil(ceil(m / 2) / NG) elements; element
+// (group g, step u, parity p) is natural index i = 2 t + p (forward) or 2 (M_p - 1 - t) + p (backward), t = g cl + u,
+// M_p = (m - p + 1) / 2.  perm_table() packs W coefficients per element at slot (u NG + g) 2 + p, so that the
+// slots a warp reads in one step of its chunks are contiguous in memory:
+//   out[slot * W + k] = src[k][i + shift[k]]   (0 where i + shift[k] is outside [0, len[k]) or t >= M_p)
+// the kernels fetch a whole compile-time chunk bound `rows` of slots per group unconditionally, so the tables are
+// sized by it (rows >= cl)
+struct ScanShape {
+  int ng, rows;
+};
+ScanShape y_scan_shape(int n1);   // scalar scans of the y kernels for lanes of n1 points (ng = 0: unsupported)
+ScanShape x_scan_shape(int n0);   // two-lane first-order scans of the x kernels for lanes of n0 points
+ScanShape x_scan2_shape(int n0);  // two-lane second-order scan of xk_forward
+std::vector<double> perm_table(int m, bool fwd, ScanShape sh, int W, const std::vector<std::vector<double>>& src,
+                               const std::vector<int>& shift);
 
 // ---- y kernels ------------------------------------------------------------------
 struct YBackwardArgs {  // B_y S_y (value), B_y D_y S_y / sy, and B_y S_y of a second array
@@ -77,6 +100,7 @@ struct YAdiArgs {  // y half of HholtzAdi (hholtz_adi.rs:113,129) + pieces of th
   double isy;
   B2Tabs b2;
   FdmaTabs f;
+  const double *pt1, *pt2;  // chunk-major packed tables: {b2 lo, di, up, f.fp} (forward), {f.bs, bp1, bp2, 0} (backward)
   int ny;
 };
 struct YAdiArgs3 {
@@ -142,6 +166,7 @@ struct XForwardArgs {  // forward DCT-x + dealias + rhs assembly + x half of Hho
   double isx;
   B2Tabs b2;
   FdmaTabs f;
+  const double *pt1, *pt2;  // chunk-major packed tables: {b2 lo, di, up, f.fp} (forward), {f.bs, bp1, bp2, 0} (backward)
   DctTab t;
 };
 struct XForwardArgs3 {

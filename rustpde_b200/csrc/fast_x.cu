@@ -210,7 +210,7 @@ FK_DEV void xk_forward_body(const XForwardArgs& a, const XForwardArgs3& a3) {
   }
   __syncthreads();
   // the A tile is idle from here on: scratch of the second-order sweep when it is large enough
-  b2_fdma_v<2, C::NTHR, C::NMAX, C::NSC2>(tw, N, n, a.b2, a.f, red, C::NSC2 == C::NSC ? (double*)ta : red);
+  b2_fdma_v<2, C::NTHR, C::NMAX, C::NSC2>(tw, N, n, a.pt1, a.pt2, red, C::NSC2 == C::NSC ? (double*)ta : red);
   for (int i = threadIdx.x >> 1; i < mxr; i += C::NTHR / 2) st2(a.out, i, col, tw[cidx<2>(rowof(N, i), c)]);
 }
 // blockIdx.y selects the field; the branch is block-uniform and keeps every argument a direct constant-bank
@@ -291,6 +291,23 @@ static int bluestein_log2(int n0) {  // tables.cu: Lb = next_pow2(2N - 1)
   int l = 0;
   while ((1 << l) < need) ++l;
   return l;
+}
+
+ScanShape x_scan_shape(int n0) {
+  const int l = bluestein_log2(n0);
+#define X(L, LCV) \
+  if (l == L) return ScanShape{XCfg<L>::NSC / 4, chunk_len_v(XCfg<L>::NMAX, XCfg<L>::NSC, 2)};
+  XK_SIZES(X)
+#undef X
+  return ScanShape{0, 0};
+}
+ScanShape x_scan2_shape(int n0) {
+  const int l = bluestein_log2(n0);
+#define X(L, LCV) \
+  if (l == L) return ScanShape{XCfg<L>::NSC2 / 4, chunk_len_v(XCfg<L>::NMAX, XCfg<L>::NSC2, 2)};
+  XK_SIZES(X)
+#undef X
+  return ScanShape{0, 0};
 }
 
 bool x_supported(int n0) {

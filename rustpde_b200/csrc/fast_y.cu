@@ -99,7 +99,7 @@ FK_DEV void yk_adi_body(const YAdiArgs& a, const YAdiArgs3& a3) {
   constexpr int n = C::n, m = n - 2;
   tile_fill<LC, C::NTHR>(td, n, [&](int j, int l) { return ld_row(a.w, r0 + l, j); });
   __syncthreads();
-  b2_fdma<LC, C::NTHR, C::CL>(td, -1, n, a.b2, a.f, red);
+  b2_fdma_perm<LC, C::NTHR, C::CL>(td, -1, n, a.pt1, a.pt2, red);
   tile_drain<LC, C::NTHR>(td, -1, m, [&](int j, int l, double v) {
     if (r0 + l < a.out.rows) a.out.p[(size_t)(r0 + l) * a.out.ld + j] = v;
   });
@@ -218,6 +218,35 @@ __global__ void __launch_bounds__(YCfg<LOG2L, LC>::NTHR, YCfg<LOG2L, LC>::SMEM1 
 // ---------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------
+ScanShape y_scan_shape(int n1) {
+  const int l = log2_of(n1 - 1);
+#define X(L, LCV) \
+  if (l == L) return ScanShape{scan_threads(YCfg<L, LCV>::NTHR) / (4 * LCV), YCfg<L, LCV>::CL};
+  YK_SIZES(X)
+#undef X
+  return ScanShape{0, 0};
+}
+
+std::vector<double> perm_table(int m, bool fwd, ScanShape sh, int W, const std::vector<std::vector<double>>& src,
+                               const std::vector<int>& shift) {
+  const int ng = sh.ng, cl = (((m + 1) >> 1) + ng - 1) / ng;
+  if (cl > sh.rows) throw Error(RP_ERR_INTERNAL, "perm_table: chunk longer than the kernel's bound");
+  std::vector<double> out((size_t)sh.rows * ng * 2 * W, 0.0);
+  for (int u = 0; u < cl; ++u)
+    for (int g = 0; g < ng; ++g)
+      for (int p = 0; p < 2; ++p) {
+        const int Mp = (m - p + 1) >> 1, t = g * cl + u;
+        if (t >= Mp) continue;
+        const int i = 2 * (fwd ? t : Mp - 1 - t) + p;
+        const size_t slot = ((size_t)u * ng + g) * 2 + p;
+        for (int k = 0; k < (int)src.size(); ++k) {
+          const int j = i + shift[k];
+          if (j >= 0 && j < (int)src[k].size()) out[slot * W + k] = src[k][j];
+        }
+      }
+  return out;
+}
+
 bool y_supported(int n1) {
   const int l = log2_of(n1 - 1);
 #define X(L, LCV) \

@@ -86,30 +86,42 @@ template <int LC, int NTHR, int CL, int ROWS, int CSHIFT>
 FK_DEV void mode_solve(double* td, const double* ti, int n, const B2Tabs& B, const ModeTabs& M, double mu, double* red) {
   const int m = n - 2;
   constexpr int NR = (2 * LC) >> CSHIFT;
+  (void)B;
   auto inv = [&](int i, int l) { return ti[i * NR + (l >> CSHIFT)]; };
+  // the raw bands come from the chunk-major packed tables (one contiguous run per warp and step)
+  const double2* PF = (const double2*)M.pf;  // slot: lo, di | up, a_low[i-2] | c_low[i-2], -
+  const double2* PB = (const double2*)M.pb;  // slot: a_up1, c_up1 | a_up2, c_up2 | a_up2[i-2], c_up2[i-2] | a_low[i-2], c_low[i-2]
   // forward: x_i -= l_{i-2} x_{i-2},  l_j = low_j / dia'_j   (fdma.rs:104-107 on the swept system)
-  auto lw = [&](int i, int l) {  // low'_{i-2}
-    return fma(mu, __ldg(&M.c_low[i - 2]), __ldg(&M.a_low[i - 2])) * inv(i - 2, l);
-  };
   scan1<LC, NTHR, CL, true>(
       m, red,
-      [&](int i, int l) {
-        return fma(__ldg(&B.lo[i]), td[didx<LC>(i, l)],
-                   fma(__ldg(&B.di[i]), td[didx<LC>(i + 2, l)], (i + 4 < n) ? __ldg(&B.up[i]) * td[didx<LC>(i + 4, l)] : 0.0));
+      [&](int i, int l, int s) {
+        const double2 a = __ldg(&PF[3 * s]), b = __ldg(&PF[3 * s + 1]);
+        return fma(a.x, td[didx<LC>(i, l)], fma(a.y, td[didx<LC>(i + 2, l)], (i + 4 < n) ? b.x * td[didx<LC>(i + 4, l)] : 0.0));
       },
-      [&](int i, int l) { return i >= 2 ? -lw(i, l) : 0.0; }, [&](int i, int l, double y) { td[didx<LC>(i, l)] = y; });
+      [&](int i, int l, int s) {
+        if (i < 2) return 0.0;
+        const double alow = __ldg(&PF[3 * s + 1]).y, clow = __ldg(&PF[3 * s + 2]).x;
+        return -fma(mu, clow, alow) * inv(i - 2, l);
+      },
+      [&](int i, int l, double y) { td[didx<LC>(i, l)] = y; });
   // backward: x_i = (x_i - up1'_i x_{i+2} - up2_i x_{i+4}) / dia'_i   (fdma.rs:108-117)
   scan2<LC, NTHR, CL, false>(
       m, red, [&](int i, int l) { return inv(i, l) * td[didx<LC>(i, l)]; },
-      [&](int i, int l) {
+      [&](int i, int l, int s) {
         if (i >= m - 2) return 0.0;
-        double u1 = fma(mu, __ldg(&M.c_up1[i]), __ldg(&M.a_up1[i]));
-        if (i >= 2) u1 = fma(-lw(i, l), fma(mu, __ldg(&M.c_up2[i - 2]), __ldg(&M.a_up2[i - 2])), u1);
+        const double2 u1p = __ldg(&PB[4 * s]);
+        double u1 = fma(mu, u1p.y, u1p.x);
+        if (i >= 2) {
+          const double2 u2m = __ldg(&PB[4 * s + 2]), lo = __ldg(&PB[4 * s + 3]);
+          const double lw = fma(mu, lo.y, lo.x) * inv(i - 2, l);
+          u1 = fma(-lw, fma(mu, u2m.y, u2m.x), u1);
+        }
         return -u1 * inv(i, l);
       },
-      [&](int i, int l) {
+      [&](int i, int l, int s) {
         if (i >= m - 4) return 0.0;
-        return -fma(mu, __ldg(&M.c_up2[i]), __ldg(&M.a_up2[i])) * inv(i, l);
+        const double2 u2 = __ldg(&PB[4 * s + 1]);
+        return -fma(mu, u2.y, u2.x) * inv(i, l);
       },
       [&](int i, int l, double y) { td[didx<LC>(i, l)] = y; });
 }

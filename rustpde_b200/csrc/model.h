@@ -264,6 +264,11 @@ class Navier2D {
   DevBuf red_;
   Arr stage_[4];
   bool staged_ = false;
+  std::vector<DevBuf> perm_;  // chunk-major coefficient tables of the specialised kernels (fast.h perm_table)
+  std::map<const void*, std::pair<const double*, const double*>> perm_mode_;
+  std::map<std::pair<const void*, int>, std::pair<const double*, const double*>> perm_tdma_;
+  fk::ModeTabs mode_of(const FdmaModeDev& m);
+  fk::TdmaTabs tdma_of(const Base& b, int n, fk::ScanShape ng);
 #ifndef RP_EMU
   cudaStream_t copy_stream_ = nullptr;
   cudaEvent_t ev_staged_ = nullptr, ev_consumed_ = nullptr;

@@ -476,11 +476,32 @@ static fk::B2Tabs b2_of(const Base& b) {
 static fk::FdmaTabs fdma_of(const FdmaDev& f) {
   return fk::FdmaTabs{f.fp.as<double>(), f.bs.as<double>(), f.bp1.as<double>(), f.bp2.as<double>()};
 }
-static fk::TdmaTabs tdma_of(const Base& b) {
-  return fk::TdmaTabs{b.d_sd.as<double>(), b.d_sl.as<double>(), b.d_tfs.as<double>(), b.d_tfp.as<double>(),
-                      b.d_tbp.as<double>()};
+// host copy of a device table of doubles
+static std::vector<double> host_of(const DevBuf& b) {
+  std::vector<double> v(b.bytes / sizeof(double));
+  if (!v.empty()) {
+    rt::d2h(v.data(), b.p, b.bytes, 0);
+    rt::sync(0);
+  }
+  return v;
 }
-static fk::ModeTabs mode_of(const FdmaModeDev& m) {
+// from_ortho tables of base b for lanes of n points; ng = chunk groups of the kernel's first-order scans
+fk::TdmaTabs Navier2D::tdma_of(const Base& b, int n, fk::ScanShape ng) {
+  fk::TdmaTabs t{b.d_sd.as<double>(), b.d_sl.as<double>(), b.d_tfs.as<double>(), b.d_tfp.as<double>(), b.d_tbp.as<double>(),
+                 nullptr, nullptr};
+  const auto key = std::make_pair((const void*)&b, ng.ng * 1024 + ng.rows);
+  auto it = perm_tdma_.find(key);
+  if (it == perm_tdma_.end()) {
+    const int m = n - 2;
+    perm_.push_back(upload(fk::perm_table(m, true, ng, 4, {host_of(b.d_sd), host_of(b.d_sl), host_of(b.d_tfs), host_of(b.d_tfp)}, {0, 0, 0, 0})));
+    const double* pf = perm_.back().as<double>();
+    perm_.push_back(upload(fk::perm_table(m, false, ng, 1, {host_of(b.d_tbp)}, {0})));
+    it = perm_tdma_.emplace(key, std::make_pair(pf, perm_.back().as<double>())).first;
+  }
+  t.pf = it->second.first, t.pb = it->second.second;
+  return t;
+}
+fk::ModeTabs Navier2D::mode_of(const FdmaModeDev& m) {
   fk::ModeTabs t;
   t.a_low = m.a_low.as<double>(), t.a_up1 = m.a_up1.as<double>(), t.a_up2 = m.a_up2.as<double>();
   t.c_low = m.c_low.as<double>(), t.c_up1 = m.c_up1.as<double>(), t.c_up2 = m.c_up2.as<double>();
@@ -488,6 +509,20 @@ static fk::ModeTabs mode_of(const FdmaModeDev& m) {
   t.alpha = m.alpha;
   t.inv = m.inv.as<double>();
   t.inv_ld = m.inv_ld;
+  auto it = perm_mode_.find(&m);
+  if (it == perm_mode_.end()) {  // chunk-major packed copies of the raw bands (fast.h perm_table)
+    const Base& byo = *field->sp.b1;
+    const fk::ScanShape ng = fk::y_scan_shape(ny);
+    const int mm = ny - 2;
+    const std::vector<double> al = host_of(m.a_low), cl = host_of(m.c_low), au1 = host_of(m.a_up1), cu1 = host_of(m.c_up1),
+                              au2 = host_of(m.a_up2), cu2 = host_of(m.c_up2);
+    perm_.push_back(upload(fk::perm_table(mm, true, ng, 6, {host_of(byo.d_b2lo), host_of(byo.d_b2di), host_of(byo.d_b2up), al, cl},
+                                          {0, 0, 0, -2, -2})));
+    const double* pf = perm_.back().as<double>();
+    perm_.push_back(upload(fk::perm_table(mm, false, ng, 8, {au1, cu1, au2, cu2, au2, cu2, al, cl}, {0, 0, 0, 0, -2, -2, -2, -2})));
+    it = perm_mode_.emplace(&m, std::make_pair(pf, perm_.back().as<double>())).first;
+  }
+  t.pf = it->second.first, t.pb = it->second.second;
   return t;
 }
 
@@ -577,6 +612,15 @@ void Navier2D::build_step_confined_fast() {
       a.isx = isx;
       a.b2 = b2_of(bxo);
       a.f = fdma_of(solver[f]->adi[0].fdma);
+      {  // chunk-major packed copies of the sweep coefficients (fast.h perm_table)
+        const FdmaDev& fd = solver[f]->adi[0].fdma;
+        const int m = nx - 2;
+        perm_.push_back(upload(fk::perm_table(m, true, fk::x_scan_shape(nx), 4,
+                                              {host_of(bxo.d_b2lo), host_of(bxo.d_b2di), host_of(bxo.d_b2up), host_of(fd.fp)}, {0, 0, 0, 0})));
+        a.pt1 = perm_.back().as<double>();
+        perm_.push_back(upload(fk::perm_table(m, false, fk::x_scan2_shape(nx), 4, {host_of(fd.bs), host_of(fd.bp1), host_of(fd.bp2)}, {0, 0, 0})));
+        a.pt2 = perm_.back().as<double>();
+      }
       a.t = dct_of(bxo);
     }
     add_fast("x_forward_rhs_adi_x", 14 * fb, [this, a3]() { fk::launch_x_forward(a3, 3, stream); });
@@ -594,6 +638,16 @@ void Navier2D::build_step_confined_fast() {
       a.isy = isy;
       a.b2 = b2_of(byo);
       a.f = fdma_of(solver[f]->adi[1].fdma);
+      {  // chunk-major packed copies of the sweep coefficients (fast.h perm_table)
+        const FdmaDev& fd = solver[f]->adi[1].fdma;
+        const fk::ScanShape ng = fk::y_scan_shape(ny);
+        const int m = ny - 2;
+        perm_.push_back(upload(fk::perm_table(m, true, ng, 4, {host_of(byo.d_b2lo), host_of(byo.d_b2di), host_of(byo.d_b2up), host_of(fd.fp)},
+                                              {0, 0, 0, 0})));
+        a.pt1 = perm_.back().as<double>();
+        perm_.push_back(upload(fk::perm_table(m, false, ng, 4, {host_of(fd.bs), host_of(fd.bp1), host_of(fd.bp2)}, {0, 0, 0})));
+        a.pt2 = perm_.back().as<double>();
+      }
       a.ny = ny;
     }
     add_fast("adi_y", 8 * fb, [this, a3]() { fk::launch_y_adi(a3, 3, stream); });
@@ -628,7 +682,7 @@ void Navier2D::build_step_confined_fast() {
     fk::XProjectArgs a;
     a.phi = mat_of(pres1->vhat), a.a1 = mat_of(a1_), a.a2 = mat_of(a2_);
     a.nsd = bxn.d_sd.as<double>(), a.nsl = bxn.d_sl.as<double>();
-    a.t = tdma_of(bxu);
+    a.t = tdma_of(bxu, nx, fk::x_scan_shape(nx));
     a.isx = isx;
     a.nx = nx;
     add_fast("project_x", 3 * fb, [this, a]() { fk::launch_x_project(a, stream); });
@@ -637,7 +691,7 @@ void Navier2D::build_step_confined_fast() {
     fk::YProjectArgs a;
     a.a1 = mat_of(a1_), a.a2 = mat_of(a2_), a.ux = mat_of(ux->vhat), a.uy = mat_of(uy->vhat);
     a.nsd = byn.d_sd.as<double>(), a.nsl = byn.d_sl.as<double>();
-    a.t = tdma_of(byu);
+    a.t = tdma_of(byu, ny, fk::y_scan_shape(ny));
     a.isy = isy;
     a.ny = ny;
     add_fast("project_y", 6 * fb, [this, a]() { fk::launch_y_project(a, stream); });
@@ -756,7 +810,7 @@ void Navier2D::build_step_periodic_fast() {
     fk::PProjectArgs a;
     a.phi = mat_of(pres1->vhat), a.ux = mat_of(ux->vhat), a.uy = mat_of(uy->vhat), a.div = mat_of(div_), a.pres = mat_of(pres0->vhat);
     a.nsd = byn.d_sd.as<double>(), a.nsl = byn.d_sl.as<double>();
-    a.t = tdma_of(byu);
+    a.t = tdma_of(byu, ny, fk::y_scan_shape(ny));
     a.isx = isx, a.isy = isy, a.nu = nu, a.inv_dt = 1.0 / dt;
     a.ny = ny;
     a.k0 = 0;
@@ -917,7 +971,7 @@ void Navier2D::slab_phase3(int k0, int mkl, const double* const in[3]) {
     a.phi = row_slab(pres1->vhat, k0, mkl), a.ux = row_slab(ux->vhat, k0, mkl), a.uy = row_slab(uy->vhat, k0, mkl);
     a.div = row_slab(div_, k0, mkl), a.pres = row_slab(pres0->vhat, k0, mkl);
     a.nsd = byn.d_sd.as<double>(), a.nsl = byn.d_sl.as<double>();
-    a.t = tdma_of(byu);
+    a.t = tdma_of(byu, ny, fk::y_scan_shape(ny));
     a.isx = isx, a.isy = isy, a.nu = nu, a.inv_dt = 1.0 / dt;
     a.ny = ny;
     a.k0 = k0;
