@@ -145,7 +145,7 @@ FK_DEV void apply_twiddles(cplx* v, cplx w1) {
 }
 
 // One in-place Stockham pass of radix R over both complex lanes of the tile.
-// L = 1 << LOG2L rows; tw[k] = exp(-2 pi i k / L).
+// L = 1 << LOG2L rows; tw = per-span compact twiddles: tw[S/2 - 1 + q] = exp(-2 pi i q / S) (tables.cu).
 // MUL: the loaded values are first multiplied by mulv[row] (Bluestein filter).
 template <int LC, int LOG2L, int NTHR, int R, int NS, bool CONJ_IN, bool CONJ_OUT, bool MUL>
 FK_DEV void fft_pass(cplx* tc, const cplx* __restrict__ tw, const cplx* __restrict__ mulv) {
@@ -169,7 +169,7 @@ FK_DEV void fft_pass(cplx* tc, const cplx* __restrict__ tw, const cplx* __restri
       }
       if (NS > 1) {
         const int k = q & (NS - 1);
-        apply_twiddles<R>(v[kb], __ldg(&tw[k * (L / (NS * R))]));
+        apply_twiddles<R>(v[kb], __ldg(&tw[NS * R / 2 - 1 + k]));  // compact table: exp(-2 pi i k / (NS R))
       }
       Bfly<R>::run(v[kb]);
     }
@@ -265,7 +265,7 @@ FK_DEV void dif_stage(cplx* tc, const cplx* __restrict__ tw) {
       bfly_zero_half<R>(v);
     else
       Bfly<R>::run(v);
-    if (SR > 1) apply_twiddles<R>(v, __ldg(&tw[q * (L / S)]));
+    if (SR > 1) apply_twiddles<R>(v, __ldg(&tw[S / 2 - 1 + q]));
 #pragma unroll
     for (int r = 0; r < R; ++r) tc[cidx<LC>(base + r * SR, c)] = v[r];
   }
@@ -291,7 +291,7 @@ FK_DEV void dit_stage(cplx* tc, const cplx* __restrict__ tw, const cplx* __restr
       }
       v[r] = x;
     }
-    if (SR > 1) apply_twiddles<R>(v, __ldg(&tw[q * (L / S)]));
+    if (SR > 1) apply_twiddles<R>(v, __ldg(&tw[S / 2 - 1 + q]));
     Bfly<R>::run(v);
 #pragma unroll
     for (int r = 0; r < (HALF_OUT ? R / 2 : R); ++r) {
@@ -332,7 +332,7 @@ FK_DEV void dif_dit_mid(cplx* tc, const cplx* __restrict__ mulv) {
     const int u = b / LC, c = b % LC;
     cplx v[8], m[8];
 #pragma unroll
-    for (int r = 0; r < 8; ++r) m[r] = __ldg(&mulv[u * 8 + r]);
+    for (int r = 0; r < 8; ++r) m[r] = __ldg(&mulv[r * (L / 8) + u]);  // filter table stored [r][u]
 #pragma unroll
     for (int r = 0; r < 8; ++r) v[r] = tc[cidx<LC>(u * 8 + r, c)];
     Bfly<8>::run(v);

@@ -22,9 +22,9 @@ struct Mat {  // pitched real matrix in global memory
 struct DctTab {
   int n;                 // lane length, N = n - 1
   const double2* sc;     // (sin, cos)(pi j / N), j = 0..N/2
-  const double2* tw;     // exp(-2 pi i k / L), L = N (pow2) or Lb (Bluestein)
+  const double2* tw;     // per-span compact twiddles tw[S/2 - 1 + q] = exp(-2 pi i q / S), S <= N (pow2) or Lb (Bluestein)
   const double2* chirp;  // Bluestein: exp(-i pi j^2 / N), j < N
-  const double2* bhat;   // Bluestein: FFT_Lb(wrapped conj chirp) / Lb, in the digit-reversed order of fft_dif (fast.cuh)
+  const double2* bhat;   // Bluestein: FFT_Lb(wrapped conj chirp) / Lb, digit-reversed order of fft_dif, transposed [8][Lb/8] (fast.cuh dif_dit_mid)
 };
 struct FdmaTabs {  // pre-swept banded solve (tables.h FdmaDev)
   const double *fp, *bs, *bp1, *bp2;
@@ -211,7 +211,7 @@ struct PC2rArgs {  // c2r along x of a spectral array and of its (i k / sx) deri
   Mat src;         // [mk, cols] complex
   Mat val, dx;     // [nx, cols] real
   double isx;
-  const double2* tw;  // exp(-2 pi i k / n)
+  const double2* tw;  // per-span compact twiddles of length n (see DctTab)
   int n;
 };
 struct PC2rArgs3 {

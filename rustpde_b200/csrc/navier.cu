@@ -465,7 +465,7 @@ static fk::DctTab dct_of(const Base& b) {
   fk::DctTab t;
   t.n = b.n;
   t.sc = b.d_sc.as<double2>();
-  t.tw = b.fft.plan.tw;
+  t.tw = b.fft.twc.as<double2>();
   t.chirp = b.fft.plan.chirp;
   t.bhat = b.fft.bhat_dr.as<double2>();
   return t;
@@ -728,7 +728,7 @@ void Navier2D::build_step_periodic_fast() {
       fk::PC2rArgs& a = a3.a[f];
       a.src = mat_of(flds[f]->vhat), a.val = mat_of(ax_[f]), a.dx = mat_of(adx_[f]);
       a.isx = isx;
-      a.tw = bx.fft.plan.tw;
+      a.tw = bx.fft.twc.as<double2>();
       a.n = nx;
     }
     add_fast("x_backward_c2r", 9 * fb, [this, a3]() { fk::launch_p_c2r(a3, 3, stream); });
@@ -767,7 +767,7 @@ void Navier2D::build_step_periodic_fast() {
       a.u = a.du = a.v = a.dv = a.bcx = a.bcy = none;
       a.sdst.nparts = 0, a.j0 = 0, a.ny = ny;
       a.cut = dealias ? (mk * 2) / 3 : mk;  // navier.rs:1028 with shape[0] = nx/2+1
-      a.tw = bx.fft.plan.tw;
+      a.tw = bx.fft.twc.as<double2>();
       a.n = nx;
     }
     add_fast("x_forward_r2c", 6 * fb, [this, a3]() { fk::launch_p_r2c(a3, 3, stream); });
@@ -883,7 +883,7 @@ void Navier2D::slab_phase2(int j0, int nyl, const double* const in[6], double* w
     a.val = f < 2 ? phys(f) : none;
     a.dx = phys(dx_idx[f]);
     a.isx = 1.0 / scale[0];
-    a.tw = bx.fft.plan.tw;
+    a.tw = bx.fft.twc.as<double2>();
     a.n = nx;
   }
   fk::launch_p_c2r(c3, 3, stream);
@@ -903,7 +903,7 @@ void Navier2D::slab_phase2(int j0, int nyl, const double* const in[6], double* w
     a.bcy = f == 2 ? fk::Mat{dytbc_.d() + j0, dytbc_.ld, nx, nyl} : none;
     a.dst = dense(out ? out[f] : nullptr, mk, nyl);
     a.cut = dealias ? (mk * 2) / 3 : mk;
-    a.tw = bx.fft.plan.tw;
+    a.tw = bx.fft.twc.as<double2>();
     a.n = nx;
     a.sdst = scatter_of(world, koff, peers ? peers + (size_t)f * world : nullptr);
     a.j0 = j0, a.ny = ny;

@@ -58,6 +58,16 @@ void build_fft_tables(int L, FftTables& out) {
   }
   out.tw = upload(tw);
   P.tw = out.tw.as<double2>();
+  {  // per-span compact copy for the specialised kernels: twc[S/2 - 1 + q] = exp(-2 pi i q / S), q < S/2, S = 2, 4, .., Lt
+     // (a stage of span S reads consecutive entries instead of every (Lt/S)-th one of the full table)
+    std::vector<double2> twc(Lt > 1 ? Lt - 1 : 1);
+    for (int S = 2; S <= Lt; S <<= 1)
+      for (int q = 0; q < S / 2; ++q) {
+        lc_t w = unit_root(q, S);
+        twc[S / 2 - 1 + q] = make_double2((double)w.real(), (double)w.imag());
+      }
+    out.twc = upload(twc);
+  }
   P.chirp = nullptr;
   P.bhat = nullptr;
   if (!P.pow2) {
@@ -95,7 +105,12 @@ void build_fft_tables(int L, FftTables& out) {
       }
       bdr[pos] = bhat[k];
     }
-    out.bhat_dr = upload(bdr);
+    // the fused middle stage of the convolution (fast.cuh dif_dit_mid) reads rows 8u .. 8u+7 per thread: stored
+    // transposed ([r][u]) the 16-byte loads of a warp are contiguous
+    std::vector<double2> bdt(P.Lb);
+    for (int u = 0; u < P.Lb / 8; ++u)
+      for (int r = 0; r < 8; ++r) bdt[(size_t)r * (P.Lb / 8) + u] = bdr[(size_t)u * 8 + r];
+    out.bhat_dr = upload(bdt);
     P.chirp = out.chirp.as<double2>();
     P.bhat = out.bhat.as<double2>();
   }

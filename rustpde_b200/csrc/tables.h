@@ -76,7 +76,8 @@ struct Diags {
 struct FftTables {
   FftPlan plan;  // pointers into the buffers below
   DevBuf tw, chirp, bhat;
-  DevBuf bhat_dr;  // bhat in the digit-reversed order of the in-place DIF FFT (fast.cuh fft_dif)
+  DevBuf twc;      // per-span compact twiddles (tables.cu build_fft_tables)
+  DevBuf bhat_dr;  // bhat in the digit-reversed order of the in-place DIF FFT, transposed [8][Lb/8] (fast.cuh dif_dit_mid)
   int fft_len() const { return plan.pow2 ? plan.L : plan.Lb; }
 };
 void build_fft_tables(int L, FftTables& out);
