@@ -8,10 +8,14 @@ Our arm: one process per GPU.  A "step" is one Navier2D.update() (navier.rs:737-
 synthetic initial fields (set_velocity/set_temperature, no RNG).  At N=1 the workload is the
 configuration the metric is quoted on that fits one GPU: confined 2048x2049, Ra=1e9.  For
 N>1 the ranks run independent replicas of that workload ("replicas only", weak scaling --
-DESIGN.md section e; the slab-decomposed periodic path is not built yet).  Timing: W>=3
-warm-up steps, then exactly K steps between CUDA events on the launching stream with a
-barrier + synchronize on both sides, max over ranks.  The working set (>2 GB) is far
-larger than L2, so no L2 flush is needed between steps.
+DESIGN.md section 6); `--workload periodic8192` (or any periodic workload) at N>1 runs ONE
+problem slab-decomposed over the Fourier modes instead (strong scaling, fused NVLink
+transposes).  Timing: W>=3 warm-up steps, then exactly K steps between CUDA events on the
+launching stream with a barrier + synchronize on both sides, max over ranks.  The working
+set (>2 GB) is far larger than L2, so no L2 flush is needed between steps.  `e2e` is the
+same metric through the C ABI with HOST buffers: every step uploads the whole state from
+pinned host memory (double-buffered on a copy stream, rp_navier_stage_state) and reads
+|div|_2 back.
 
 Reference arm (--impl reference): the reference is pure Rust and cannot be built in this
 image, so this times the CPU restatement (oracle/, numpy/scipy with all host threads) of

@@ -28,6 +28,9 @@ extern "C" {
     fn rp_navier_set_velocity(h: *mut rp_navier_t, amp: c_double, m: c_double, n: c_double) -> c_int;
     fn rp_navier_set_temperature(h: *mut rp_navier_t, amp: c_double, m: c_double, n: c_double) -> c_int;
     fn rp_navier_update(h: *mut rp_navier_t, nsteps: c_int) -> c_int;
+    fn rp_navier_stage_state(h: *mut rp_navier_t, temp: *const c_double, n_temp: usize, ux: *const c_double, n_ux: usize,
+                             uy: *const c_double, n_uy: usize, pres: *const c_double, n_pres: usize) -> c_int;
+    fn rp_navier_commit_staged(h: *mut rp_navier_t) -> c_int;
     fn rp_navier_get_time(h: *mut rp_navier_t, t: *mut c_double) -> c_int;
     fn rp_navier_get_dt(h: *mut rp_navier_t, dt: *mut c_double) -> c_int;
     fn rp_navier_eval(h: *mut rp_navier_t, nu: *mut c_double, nuvol: *mut c_double, re: *mut c_double,
@@ -135,6 +138,22 @@ impl Navier2D {
 impl Drop for Navier2D {
     fn drop(&mut self) {
         unsafe { rp_navier_destroy(self.h) };
+    }
+}
+
+impl Navier2D {
+    /// Queue the upload of a full state (the `vhat` buffers of temp, ux, uy, pres[0], row-major as in the
+    /// reference's `Array2`) on the copy stream; it overlaps the kernels of the step in flight.  The slices must
+    /// outlive the matching `commit_staged` (page-locked memory keeps the copy asynchronous).
+    pub fn stage_state(&mut self, temp: &[f64], ux: &[f64], uy: &[f64], pres: &[f64]) {
+        unsafe {
+            check(rp_navier_stage_state(self.h, temp.as_ptr(), temp.len(), ux.as_ptr(), ux.len(), uy.as_ptr(), uy.len(),
+                                        pres.as_ptr(), pres.len()))
+        }
+    }
+    /// Make the compute stream wait for the staged upload and move it into place.
+    pub fn commit_staged(&mut self) {
+        unsafe { check(rp_navier_commit_staged(self.h)) }
     }
 }
 

@@ -134,8 +134,18 @@ struct YPresArgs {  // p += -nu div + to_ortho(phi)/dt (navier.rs:717-721); dyp 
   const double *ysd, *ysl;  // Neumann stencil along y
   double inv_dt, nu, isy;
   int ny;
+  int only_dyp;  // 1: leave pres as it is and only refresh dyp = D_y pres / sy (after pres was rewritten from outside)
 };
 void launch_y_pres(const YPresArgs& a, cudaStream_t s);
+
+struct YDivPrepArgs {  // y parts of the divergence of (ux, uy) (navier.rs:698-703): vx = S_y ux, ey = D_y S_y uy / sy
+  Mat ux, uy;          // [mx, my]
+  Mat vx, ey;          // [mx, ny]
+  const double *sd, *sl;
+  double isy;
+  int ny;
+};
+void launch_y_divprep(const YDivPrepArgs& a, cudaStream_t s);
 
 // ---- x kernels ------------------------------------------------------------------
 struct XBackwardArgs {  // B_x S_x u^ and B_x D_x S_x u^ / sx

@@ -195,6 +195,15 @@ __global__ void __launch_bounds__(YCfg<LOG2L, LC>::NTHR, YCfg<LOG2L, LC>::SMEM1 
   constexpr int n = C::n, m = n - 2;
   const int mx = a.phi.rows;
   // to_ortho(phi): S_x across lanes (rows i, i-2 of phi), S_y along the lane
+  if (a.only_dyp) {  // block-uniform
+    tile_fill<LC, C::NTHR>(td, n, [&](int j, int l) { return ld_row(a.pres, r0 + l, j); });
+    __syncthreads();
+    cheb_diff<LC, C::NTHR, C::CL>(td, -1, td, -1, n, a.isy, red);
+    tile_drain<LC, C::NTHR>(td, -1, n, [&](int j, int l, double v) {
+      if (r0 + l < a.dyp.rows) a.dyp.p[(size_t)(r0 + l) * a.dyp.ld + j] = v;
+    });
+    return;
+  }
   tile_fill<LC, C::NTHR>(td, n, [&](int j, int l) {
     const int i = min(r0 + l, a.pres.rows - 1);
     const double s0 = ld_stencil(a.phi, min(i, mx - 1), j, m, a.ysd, a.ysl);
@@ -212,6 +221,24 @@ __global__ void __launch_bounds__(YCfg<LOG2L, LC>::NTHR, YCfg<LOG2L, LC>::SMEM1 
   cheb_diff<LC, C::NTHR, C::CL>(td, -1, td, -1, n, a.isy, red);
   tile_drain<LC, C::NTHR>(td, -1, n, [&](int j, int l, double v) {
     if (r0 + l < a.dyp.rows) a.dyp.p[(size_t)(r0 + l) * a.dyp.ld + j] = v;
+  });
+}
+
+// blockIdx.y = 0: vx = S_y ux;  1: ey = D_y S_y uy / sy   (the y parts of the divergence, for the diagnostics)
+template <int LOG2L, int LC>
+__global__ void __launch_bounds__(YCfg<LOG2L, LC>::NTHR, YCfg<LOG2L, LC>::SMEM1 > 110 * 1024 ? 1 : 2) yk_divprep(YDivPrepArgs a) {
+  typedef YCfg<LOG2L, LC> C;
+  YK_SMEM(td, red);
+  const int r0 = blockIdx.x * C::LR;
+  constexpr int n = C::n, m = n - 2;
+  const bool second = blockIdx.y != 0;
+  const Mat& src = second ? a.uy : a.ux;
+  const Mat& dst = second ? a.ey : a.vx;
+  tile_fill<LC, C::NTHR>(td, n, [&](int j, int l) { return ld_stencil(src, r0 + l, j, m, a.sd, a.sl); });
+  __syncthreads();
+  if (second) cheb_diff<LC, C::NTHR, C::CL>(td, -1, td, -1, n, a.isy, red);
+  tile_drain<LC, C::NTHR>(td, -1, n, [&](int j, int l, double v) {
+    if (r0 + l < dst.rows) dst.p[(size_t)(r0 + l) * dst.ld + j] = v;
   });
 }
 
@@ -262,6 +289,7 @@ bool y_supported(int n1) {
 #define YK_CASE_yk_mode(L, LCV) YK_CASE_BODY(yk_mode, L, LCV, 1, a)
 #define YK_CASE_yk_project(L, LCV) YK_CASE_BODY(yk_project, L, LCV, 0, a)
 #define YK_CASE_yk_pres(L, LCV) YK_CASE_BODY(yk_pres, L, LCV, 0, a)
+#define YK_CASE_yk_divprep(L, LCV) YK_CASE_BODY(yk_divprep, L, LCV, 0, a)
 
 void launch_y_backward(const YBackwardArgs3& a, int nb, cudaStream_t s) { YK_LAUNCH(yk_backward, false, a.a[0].a.rows, a.a[0].t.n, a, nb); }
 void launch_y_conv(const YConvArgs3& a, int nb, cudaStream_t s) { YK_LAUNCH(yk_conv, false, a.a[0].u.rows, a.a[0].t.n, a, nb); }
@@ -269,6 +297,7 @@ void launch_y_adi(const YAdiArgs3& a, int nb, cudaStream_t s) { YK_LAUNCH(yk_adi
 void launch_y_mode(const YModeArgs& a, cudaStream_t s) { YK_LAUNCH(yk_mode, true, a.g.rows, a.ny, a, 1); }
 void launch_y_project(const YProjectArgs& a, cudaStream_t s) { YK_LAUNCH(yk_project, false, a.a1.rows, a.ny, a, 1); }
 void launch_y_pres(const YPresArgs& a, cudaStream_t s) { YK_LAUNCH(yk_pres, false, a.pres.rows, a.ny, a, 1); }
+void launch_y_divprep(const YDivPrepArgs& a, cudaStream_t s) { YK_LAUNCH(yk_divprep, false, a.ux.rows, a.ny, a, 2); }
 
 }  // namespace fk
 }  // namespace rp

@@ -264,6 +264,7 @@ class Navier2D {
   DevBuf red_;
   Arr stage_[4];
   bool staged_ = false;
+  std::function<void()> fast_dyp_, fast_div_;  // specialised refresh of d/dy pres and divergence of (ux, uy), when available
   std::vector<DevBuf> perm_;  // chunk-major coefficient tables of the specialised kernels (fast.h perm_table)
   std::map<const void*, std::pair<const double*, const double*>> perm_mode_;
   std::map<std::pair<const void*, int>, std::pair<const double*, const double*>> perm_tdma_;

@@ -704,7 +704,27 @@ void Navier2D::build_step_confined_fast() {
     a.ysd = byn.d_sd.as<double>(), a.ysl = byn.d_sl.as<double>();
     a.inv_dt = 1.0 / dt, a.nu = nu, a.isy = isy;
     a.ny = ny;
+    a.only_dyp = 0;
     add_fast("pressure_update", 5 * fb, [this, a]() { fk::launch_y_pres(a, stream); });
+    // the same kernel refreshes d/dy pres after the pressure was rewritten from outside (update())
+    fk::YPresArgs r = a;
+    r.only_dyp = 1;
+    fast_dyp_ = [this, r]() { fk::launch_y_pres(r, stream); };
+    // |div u| of the current velocity for exit() (navier.rs:855-879): y parts, then the divergence kernel of the step
+    fk::YDivPrepArgs dp;
+    dp.ux = mat_of(ux->vhat), dp.uy = mat_of(uy->vhat), dp.vx = mat_of(vx_), dp.ey = mat_of(ey_);
+    dp.sd = byu.d_sd.as<double>(), dp.sl = byu.d_sl.as<double>();
+    dp.isy = isy, dp.ny = ny;
+    fk::XDivArgs xd;
+    xd.vx = mat_of(vx_), xd.ey = mat_of(ey_), xd.div = mat_of(div_), xd.r1 = mat_of(r1_);
+    xd.sd = bxu.d_sd.as<double>(), xd.sl = bxu.d_sl.as<double>();
+    xd.isx = isx;
+    xd.b2 = b2_of(bxo);
+    xd.nx = nx;
+    fast_div_ = [this, dp, xd]() {
+      fk::launch_y_divprep(dp, stream);
+      fk::launch_x_div(xd, stream);
+    };
   }
   (void)my;
 }
@@ -1130,8 +1150,12 @@ void Navier2D::update(int nsteps) {
   if (!periodic && dyp_version_ != pres0->vhat_version) {
     // d/dy pres of the current pressure: every step leaves it behind for the next one, so this is only
     // needed at the first step and after the pressure was rewritten from outside (upload / forward)
-    pres0->gradient(0, 1, scale);
-    copy_arr(dyp_, pres0->ortho, stream);
+    if (fast_dyp_) {
+      fast_dyp_();
+    } else {
+      pres0->gradient(0, 1, scale);
+      copy_arr(dyp_, pres0->ortho, stream);
+    }
     dyp_version_ = pres0->vhat_version;
   }
 #ifndef RP_EMU
@@ -1174,6 +1198,16 @@ void Navier2D::update(int nsteps) {
 // Diagnostics (src/navier/functions.rs, navier.rs:855-879)
 // --------------------------------------------------------------------------
 double Navier2D::div_norm() {
+  build_step();
+  if (fast_div_) {  // specialised kernels: vx_, ey_, div_, r1_ are scratch between steps
+    fast_div_();
+    rt::dzero(red_.p, 8, stream);
+    launch_wsum(div_.d(), nullptr, div_.ld, div_.rows, div_.cols, nullptr, nullptr, 3, red_.as<double>(), stream);
+    double r = 0.0;
+    rt::d2h(&r, red_.p, 8, stream);
+    rt::sync(stream);
+    return std::sqrt(r);
+  }
   ux->gradient(1, 0, scale);
   uy->gradient(0, 1, scale);
   const int rc = ux->cplx ? 2 : 1;
