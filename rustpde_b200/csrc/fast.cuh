@@ -47,15 +47,28 @@ FK_DEV void prefetch_l2(const void* p) {
   (void)p;
 #endif
 }
-// rows [0, nrows) of the 4-column strip of `a` starting at column c0 (and, with HALO, the two columns before it)
-template <int NTHR, bool HALO>
-FK_DEV void prefetch_strip(const Mat& a, int c0, int nrows) {
-  if (a.p == nullptr || c0 >= a.cols) return;
-  for (int i = threadIdx.x; i < nrows; i += NTHR) {
-    const double* row = a.p + (size_t)i * a.ld;
-    prefetch_l2(row + c0);
-    if (HALO && c0 >= 2) prefetch_l2(row + c0 - 2);
-  }
+// ---- asynchronous global -> shared copies (LDGSTS) ---------------------------------------------
+// 16-byte chunk; only the first `bytes` (0, 8 or 16) are read, the rest is zero-filled
+FK_DEV void cp_async16(void* smem_dst, const double* gsrc, int bytes) {
+#ifdef RP_EMU
+  double* d = (double*)smem_dst;
+  d[0] = bytes >= 8 ? gsrc[0] : 0.0;
+  d[1] = bytes >= 16 ? gsrc[1] : 0.0;
+#else
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(bytes) : "memory");
+#endif
+}
+FK_DEV void cp_async_commit() {
+#ifndef RP_EMU
+  asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+template <int N>  // wait until at most N of the most recent groups are still in flight
+FK_DEV void cp_async_wait() {
+#ifndef RP_EMU
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+#endif
 }
 
 // at most 512 threads of a block take part in the scans (bounds the scratch array); the rest only
@@ -271,10 +284,10 @@ FK_DEV void dif_stage(cplx* tc, const cplx* __restrict__ tw) {
   }
   __syncthreads();
 }
-// inverse DIT stage (unnormalised): FIRST multiplies the loaded values by mulv[row]
-// and conjugates them, LAST conjugates the results; HALF_OUT: only rows < L/2 are stored.
-template <int LC, int LOG2L, int NTHR, int LOG2S, int R, bool FIRST, bool LAST, bool HALF_OUT>
-FK_DEV void dit_stage(cplx* tc, const cplx* __restrict__ tw, const cplx* __restrict__ mulv) {
+// inverse DIT stage (unnormalised) of span S >= 64 (the span-8 stage is fused into dif_dit_mid, which also
+// conjugates the input); LAST conjugates the results; HALF_OUT: only rows < L/2 are stored.
+template <int LC, int LOG2L, int NTHR, int LOG2S, int R, bool LAST, bool HALF_OUT>
+FK_DEV void dit_stage(cplx* tc, const cplx* __restrict__ tw) {
   constexpr int L = 1 << LOG2L, S = 1 << LOG2S, SR = S / R;
   constexpr int TOT = (L / R) * LC;
 #pragma unroll 2
@@ -283,14 +296,7 @@ FK_DEV void dit_stage(cplx* tc, const cplx* __restrict__ tw, const cplx* __restr
     const int q = u & (SR - 1), base = (u - q) * R + q;
     cplx v[R];
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-      cplx x = tc[cidx<LC>(base + r * SR, c)];
-      if (FIRST) {
-        x = cmul(x, __ldg(&mulv[base + r * SR]));
-        x.y = -x.y;
-      }
-      v[r] = x;
-    }
+    for (int r = 0; r < R; ++r) v[r] = tc[cidx<LC>(base + r * SR, c)];
     if (SR > 1) apply_twiddles<R>(v, __ldg(&tw[S / 2 - 1 + q]));
     Bfly<R>::run(v);
 #pragma unroll
@@ -302,22 +308,15 @@ FK_DEV void dit_stage(cplx* tc, const cplx* __restrict__ tw, const cplx* __restr
   }
   __syncthreads();
 }
-template <int LC, int LOG2L, int NTHR, int LOG2S, bool ZERO_HALF>
-FK_DEV void fft_dif_rec(cplx* tc, const cplx* __restrict__ tw) {
-  if constexpr (LOG2S > 0) {
-    constexpr int LR = (LOG2S % 3) ? (LOG2S % 3) : 3;
-    dif_stage<LC, LOG2L, NTHR, LOG2S, (1 << LR), ZERO_HALF && LOG2S == LOG2L>(tc, tw);
-    fft_dif_rec<LC, LOG2L, NTHR, LOG2S - LR, ZERO_HALF>(tc, tw);
-  }
-}
 template <int LC, int LOG2L, int NTHR, int LOG2S, bool HALF_OUT>
-FK_DEV void fft_dit_rec(cplx* tc, const cplx* __restrict__ tw, const cplx* __restrict__ mulv) {
+FK_DEV void fft_dit_rec(cplx* tc, const cplx* __restrict__ tw) {
+  static_assert(LOG2S >= 6, "the span-8 stage belongs to dif_dit_mid");
   constexpr int LR = (LOG2S == LOG2L && (LOG2L % 3)) ? (LOG2L % 3) : 3;
   constexpr bool last = (LOG2S == LOG2L);
-  dit_stage<LC, LOG2L, NTHR, LOG2S, (1 << LR), LOG2S == 3, last, HALF_OUT && last>(tc, tw, mulv);
+  dit_stage<LC, LOG2L, NTHR, LOG2S, (1 << LR), last, HALF_OUT && last>(tc, tw);
   if constexpr (!last) {
     constexpr int NEXT = (LOG2S + 3 > LOG2L) ? LOG2L : LOG2S + 3;
-    fft_dit_rec<LC, LOG2L, NTHR, NEXT, HALF_OUT>(tc, tw, mulv);
+    fft_dit_rec<LC, LOG2L, NTHR, NEXT, HALF_OUT>(tc, tw);
   }
 }
 // Last DIF stage (span 8), pointwise filter, first inverse DIT stage (span 8) in one pass: both stages
@@ -363,20 +362,8 @@ FK_DEV void fft_convolve_half(cplx* tc, const cplx* __restrict__ tw, const cplx*
   static_assert(LOG2L >= 6, "fused middle stage needs at least two stages");
   fft_dif_rec_hi<LC, LOG2L, NTHR, LOG2L, true>(tc, tw);
   dif_dit_mid<LC, LOG2L, NTHR>(tc, mulv);
-  fft_dit_rec<LC, LOG2L, NTHR, 6, true>(tc, tw, mulv);
+  fft_dit_rec<LC, LOG2L, NTHR, 6, true>(tc, tw);
 }
-// forward: natural order in, digit-reversed out (rows >= L/2 of the input are zero when ZERO_HALF)
-template <int LC, int LOG2L, int NTHR, bool ZERO_HALF>
-FK_DEV void fft_dif(cplx* tc, const cplx* __restrict__ tw) {
-  fft_dif_rec<LC, LOG2L, NTHR, LOG2L, ZERO_HALF>(tc, tw);
-}
-// inverse of fft_dif (unnormalised) with the input first multiplied by mulv (digit-reversed order)
-template <int LC, int LOG2L, int NTHR, bool HALF_OUT>
-FK_DEV void fft_dit_inv(cplx* tc, const cplx* __restrict__ tw, const cplx* __restrict__ mulv) {
-  static_assert(LOG2L >= 3, "FFT length must be at least 8");
-  fft_dit_rec<LC, LOG2L, NTHR, 3, HALF_OUT>(tc, tw, mulv);
-}
-
 // pre-combine of one pair (j, N-j): Chebyshev scaling of the backward transform
 // (ortho.rs:398-404), reduction of the length-2N even DFT to a length-N real DFT.
 template <bool BWD>
@@ -419,58 +406,9 @@ FK_DEV void recombine_pair(cplx zk, cplx zm, int k, int N, cplx& xe, cplx& dk) {
   dk = mk(-(zk.y - zm.y), zk.x - zm.x);
 }
 
-// Odd outputs of the DCT: prefix sum along rows N, N-1, ..., N-Ko of the tile
-// (4 real lanes); forward transform: times -1/N, last one halved when N is odd.
-template <int LC, int NTHR, int CLR, bool BWD>
-FK_DEV void dct_odd_scan(double* td, int N, double* red) {
-  constexpr int LR = 2 * LC;
-  constexpr int NSC = scan_threads(NTHR), NG = NSC / LR;
-  const int tid = threadIdx.x, lane = tid % LR, g = tid / LR;
-  const bool act = tid < NSC;
-  const int M = act ? (N - 1) / 2 + 1 : 0;  // Ko + 1
-  const int cl = (M + NG - 1) / NG;
-  const int t0 = g * cl, t1 = min(t0 + cl, M);
-  double q[CLR];
-  double s = 0.0;
-#pragma unroll
-  for (int u = 0; u < CLR; ++u) {
-    const int t = t0 + u;
-    if (t < t1) {
-      q[u] = td[didx<LC>(N - t, lane)];
-      s += q[u];
-    }
-  }
-  // two-level carry: sums of groups of 8 chunks, then the chunks inside the group
-  double* red2 = red + NG * LR;
-  if (act) red[g * LR + lane] = s;
-  __syncthreads();
-  if (act && (g & 7) == 0) {
-    double t = 0.0;
-#pragma unroll
-    for (int k = 0; k < 8; ++k)
-      if (g + k < NG) t += red[(g + k) * LR + lane];
-    red2[(g >> 3) * LR + lane] = t;
-  }
-  __syncthreads();
-  double y = 0.0;
-  for (int gg = 0; act && gg < (g >> 3); ++gg) y += red2[gg * LR + lane];
-  for (int gg = (g & ~7); act && gg < g; ++gg) y += red[gg * LR + lane];
-  const double ho = BWD ? 1.0 : -1.0 / (double)N;
-#pragma unroll
-  for (int u = 0; u < CLR; ++u) {
-    const int t = t0 + u;
-    if (t < t1) {
-      y += q[u];
-      double o = y * ho;
-      if (!BWD && 2 * t + 1 == N) o *= 0.5;
-      td[didx<LC>(N - t, lane)] = o;
-    }
-  }
-  __syncthreads();
-}
-
-// two-lane form of dct_odd_scan: a thread sums both real lanes of a complex lane (half the chunk length,
-// 16-byte accesses); carries: warp-level inclusive scan, then the warp totals through shared memory
+// Odd outputs of the DCT: prefix sum along rows N, N-1, ..., N-Ko of the tile; forward transform: times -1/N,
+// last one halved when N is odd.  A thread sums both real lanes of a complex lane (16-byte accesses); carries:
+// warp-level inclusive scan, then the warp totals through shared memory
 template <int LC, int NTHR, int CLR, bool BWD>
 FK_DEV void dct_odd_scan_v(cplx* tc, int N, double* red_) {
   constexpr int NSC = scan_threads(NTHR), NG = NSC / LC;
@@ -562,8 +500,10 @@ FK_DEV void dct_pow2(double* td, const DctTab& T, double* red) {
 // DCT-I of arbitrary N = n - 1 through Bluestein (FFT length Lb = 1 << LOG2LB >=
 // 2N - 1): reads tile A (natural layout, n rows), result in tile W (Lb rows),
 // split(N) layout.  A is left untouched.
-template <int LC, int LOG2LB, int NTHR, bool BWD>
-FK_DEV void dct_bluestein(const double* ta, double* tw_, const DctTab& T, double* red) {
+// `after_pre()` runs (all threads) once tile A has been consumed, i.e. under the FFT stages: the caller may start
+// asynchronous copies into A there.
+template <int LC, int LOG2LB, int NTHR, bool BWD, class Hook>
+FK_DEV void dct_bluestein(const double* ta, double* tw_, const DctTab& T, double* red, Hook after_pre) {
   constexpr int LB = 1 << LOG2LB;
   const int N = T.n - 1;
   const int NP = N / 2 + 1;
@@ -582,6 +522,7 @@ FK_DEV void dct_bluestein(const double* ta, double* tw_, const DctTab& T, double
   for (int it = LC * N + tid; it < (LB / 2) * LC; it += NTHR) W[cidx<LC>(it / LC, c)] = mk(0.0, 0.0);  // rows [N, LB/2)
   reduce_f1<LC, NTHR>(f1, f1red);
   __syncthreads();
+  after_pre();
   fft_convolve_half<LC, LOG2LB, NTHR>(W, T.tw, T.bhat);
   const int Ko = (N - 1) / 2;
   for (int it = tid; it < NP * LC; it += NTHR) {
@@ -600,6 +541,10 @@ FK_DEV void dct_bluestein(const double* ta, double* tw_, const DctTab& T, double
   }
   __syncthreads();
   dct_odd_scan_v<LC, NTHR, (LB / 4 + scan_threads(NTHR) / LC - 1) / (scan_threads(NTHR) / LC), BWD>(W, N, red);
+}
+template <int LC, int LOG2LB, int NTHR, bool BWD>
+FK_DEV void dct_bluestein(const double* ta, double* tw_, const DctTab& T, double* red) {
+  dct_bluestein<LC, LOG2LB, NTHR, BWD>(ta, tw_, T, red, [] {});
 }
 
 // ---- chunk-major ("permuted") coefficient tables -------------------------------------------------
@@ -833,28 +778,10 @@ FK_DEV void cheb_diff(const double* src, int sn_s, double* dst, int sn_d, int n,
       });
 }
 
-// HholtzAdi half step along the tile axis (hholtz_adi.rs:108-129): B2 matvec
-// (n -> m = n-2) fused into the forward sweep, then the backward sweep
-// (fdma.rs:101-118).  In place on tile t (layout sn); result elements 0..m-1.
-template <int LC, int NTHR, int CL>
-FK_DEV void b2_fdma(double* t, int sn, int n, const B2Tabs& B, const FdmaTabs& F, double* red) {
-  const int m = n - 2;
-  scan1<LC, NTHR, CL, true>(
-      m, red,
-      [&](int i, int l) {
-        return fma(__ldg(&B.lo[i]), t[didx<LC>(rowof(sn, i), l)],
-                   fma(__ldg(&B.di[i]), t[didx<LC>(rowof(sn, i + 2), l)],
-                       (i + 4 < n) ? __ldg(&B.up[i]) * t[didx<LC>(rowof(sn, i + 4), l)] : 0.0));
-      },
-      [&](int i, int) { return __ldg(&F.fp[i]); }, [&](int i, int l, double y) { t[didx<LC>(rowof(sn, i), l)] = y; });
-  scan2<LC, NTHR, CL, false>(
-      m, red, [&](int i, int l) { return __ldg(&F.bs[i]) * t[didx<LC>(rowof(sn, i), l)]; },
-      [&](int i, int) { return __ldg(&F.bp1[i]); }, [&](int i, int) { return __ldg(&F.bp2[i]); },
-      [&](int i, int l, double y) { t[didx<LC>(rowof(sn, i), l)] = y; });
-}
-
-// b2_fdma with chunk-major packed coefficient tables (fast.h perm_table): pt1[slot] = {lo, di, up, fp} in the
-// order of the forward sweep, pt2[slot] = {bs, bp1, bp2, -} in the order of the backward sweep
+// HholtzAdi half step along the tile axis (hholtz_adi.rs:108-129): B2 matvec (n -> m = n-2) fused into the forward
+// sweep, then the backward sweep (fdma.rs:101-118).  In place on tile t (layout sn); result elements 0..m-1.
+// Coefficients from the chunk-major packed tables (fast.h perm_table): pt1[slot] = {lo, di, up, fp} in the order
+// of the forward sweep, pt2[slot] = {bs, bp1, bp2, -} in the order of the backward sweep
 template <int LC, int NTHR, int CL>
 FK_DEV void b2_fdma_perm(double* t, int sn, int n, const double* __restrict__ pt1, const double* __restrict__ pt2, double* red) {
   const int m = n - 2;

@@ -115,6 +115,37 @@ __global__ void __launch_bounds__(XCfg<LOG2LB>::NTHR, XCfg<LOG2LB>::MINB) xk_bac
     xk_backward_body<LOG2LB>(a3.a[2], a3);
 }
 
+// Asynchronous staging of a 4-column strip (cp.async, 16 bytes per thread and row): dst[i][c] = (f[i][col], f[i][col+1])
+// for i < nrows, zero outside the matrix.  One commit group per call.
+template <int NTHR>
+FK_DEV void xstage(cplx* dst, const Mat& f, int nrows, int col) {
+  const int c = threadIdx.x & 1;
+  const int nb = (col + 1 < f.cols) ? 16 : (col < f.cols ? 8 : 0);
+  const double* base = f.p + (nb ? col : 0);
+  for (int i = threadIdx.x >> 1; i < nrows; i += NTHR / 2) {
+    const bool r = i < f.rows;
+    cp_async16(&dst[cidx<2>(i, c)], base + (size_t)(r ? i : 0) * f.ld, r ? nb : 0);
+  }
+  cp_async_commit();
+}
+// composite -> ortho stencil across the columns of a staged strip, in place: t(col) = d(col) t(col) + l(col-2) t(col-2).
+// Columns c0-2, c0-1 belong to the neighbouring strip and come from global memory (an L2 hit: that strip is being
+// worked on by the neighbouring block); columns c0, c0+1 for the second lane pair come from the first one by shuffle.
+template <int NTHR>
+FK_DEV void xstencil_cols(cplx* t, const Mat& f, int nrows, int col, const StencilPair& sp) {
+  const int c = threadIdx.x & 1;
+  const bool left = c == 0 && col >= 2 && col - 2 < f.cols;
+  for (int i0 = 0; i0 < nrows; i0 += NTHR / 2) {
+    const int i = i0 + (threadIdx.x >> 1);
+    const bool ok = i < nrows && i < f.rows;
+    const cplx v0 = ok ? t[cidx<2>(i, c)] : mk(0.0, 0.0);
+    cplx v2 = mk(__shfl_up_sync(0xffffffffu, v0.x, 1), __shfl_up_sync(0xffffffffu, v0.y, 1));
+    if (c == 0) v2 = (left && ok) ? *(const cplx*)(f.p + (size_t)i * f.ld + col - 2) : mk(0.0, 0.0);
+    if (left && col - 1 >= f.cols) v2.y = 0.0;
+    if (i < nrows) t[cidx<2>(i, c)] = mk(fma(sp.l.x, v2.x, sp.d.x * v0.x), fma(sp.l.y, v2.y, sp.d.y * v0.y));
+  }
+}
+
 template <int LOG2LB>
 FK_DEV void xk_forward_body(const XForwardArgs& a, const XForwardArgs3& a3) {
   typedef XCfg<LOG2LB> C;
@@ -122,42 +153,38 @@ FK_DEV void xk_forward_body(const XForwardArgs& a, const XForwardArgs3& a3) {
   RP_DYN_SMEM(double, ta_);
   cplx* ta = (cplx*)ta_;
   cplx* tw = ta + C::AROWS * 2;
+  cplx* tu = tw + (C::LB / 2) * 2;  // rows [LB/2, LB) of W: idle once the inverse transform is done
   double* red = (double*)(tw + C::LB * 2);
   const int c0 = blockIdx.x * LR, col = c0 + 2 * (threadIdx.x & 1), c = threadIdx.x & 1;
   const int n = a.t.n, N = n - 1;
   const int mxr = n - 2;
   xfill<C::NTHR>(ta, n, [&](int i) { return ld2(a.conv, i, col); });
-  // everything the later phases of this block read -> L2, and the first strip of the block that runs on
-  // this SM next
-  xprefetch<C::NTHR, true>(a.fld, c0, mxr);
-  if (a.mode == 0) {
-    xprefetch<C::NTHR, false>(a.pres, c0, n);
-  } else if (a.mode == 1) {
-    xprefetch<C::NTHR, true>(a.tmp, c0, mxr);
-    xprefetch<C::NTHR, false>(a.dyp, c0, n);
-    xprefetch<C::NTHR, false>(a.tbc, c0, n);
-  } else {
-    xprefetch<C::NTHR, false>(a.bcdiff, c0, n);
-  }
-  {
+  {  // first strip of the block that runs on this SM next -> L2
     const int nxt = blockIdx.y * gridDim.x + blockIdx.x + a3.next_wave;
     if (nxt < (int)(gridDim.x * gridDim.y)) xprefetch<C::NTHR, false>(a3.a[nxt / gridDim.x].conv, (nxt % gridDim.x) * LR, n);
   }
   __syncthreads();
-  dct_bluestein<2, LOG2LB, C::NTHR, false>((const double*)ta, (double*)tw, a.t, red);
-  // rhs assembly in the split(N) layout of W.  Every global array is read once per element:
-  // S_y is applied while loading (columns j, j-2), S_x on the shared-memory copy in A.
-  auto sx_at = [&](int i, const double* __restrict__ xsd, const double* __restrict__ xsl) {
+  // The strips of the later phases are staged asynchronously (cp.async) into tiles that are idle at the time: the
+  // old field into A under the FFT stages, pres / temp into the upper half of W under the rhs assembly.
+  dct_bluestein<2, LOG2LB, C::NTHR, false>((const double*)ta, (double*)tw, a.t, red, [&] { xstage<C::NTHR>(ta, a.fld, mxr, col); });
+  if (a.mode == 0)
+    xstage<C::NTHR>(tu, a.pres, n, col);
+  else if (a.mode == 1)
+    xstage<C::NTHR>(tu, a.tmp, mxr, col);
+  else
+    cp_async_commit();  // (keeps the group count uniform)
+  cp_async_wait<1>();   // the old field has landed
+  __syncthreads();
+  // rhs assembly in the split(N) layout of W.  Every global array is read once per element: S_y across the
+  // columns of the staged strip, S_x along it.
+  auto sx_at = [&](const cplx* t, int i, const double* __restrict__ xsd, const double* __restrict__ xsl) {
     cplx v = mk(0.0, 0.0);
-    if (i < mxr) v = cscale(ta[cidx<2>(i, c)], __ldg(&xsd[i]));
-    if (i >= 2) v = sfma(__ldg(&xsl[i - 2]), ta[cidx<2>(i - 2, c)], v);
+    if (i < mxr) v = cscale(t[cidx<2>(i, c)], __ldg(&xsd[i]));
+    if (i >= 2) v = sfma(__ldg(&xsl[i - 2]), t[cidx<2>(i - 2, c)], v);
     return v;
   };
   // - dt * dealiased conv + to_ortho(field)   (navier.rs:625, 630, 651, 671)
-  {
-    const StencilPair sp = stencil_pair(a.fld.cols, col, a.fysd, a.fysl);
-    xfill<C::NTHR>(ta, mxr, [&](int i) { return ld2_stencil(a.fld, i, sp); });
-  }
+  xstencil_cols<C::NTHR>(ta, a.fld, mxr, col, stencil_pair(a.fld.cols, col, a.fysd, a.fysl));
   __syncthreads();
   for (int i0 = threadIdx.x >> 1; i0 < n; i0 += (C::NTHR / 2) * 4) {
     cplx add[4];
@@ -170,24 +197,20 @@ FK_DEV void xk_forward_body(const XForwardArgs& a, const XForwardArgs3& a3) {
       if (i < n) {
         cplx* w = &tw[cidx<2>(rowof(N, i), c)];
         const cplx v = (i < a.cut) ? cscale(*w, -a.dt) : mk(0.0, 0.0);
-        *w = cadd(cadd(v, sx_at(i, a.fxsd, a.fxsl)), add[u]);
+        *w = cadd(cadd(v, sx_at(ta, i, a.fxsd, a.fxsl)), add[u]);
       }
     }
   }
+  cp_async_wait<0>();
   __syncthreads();
   if (a.mode == 0) {  // - dt/sx d/dx pres   (navier.rs:627)
-    xfill<C::NTHR>(ta, n, [&](int i) { return ld2(a.pres, i, col); });
-    __syncthreads();
-    cheb_diff_v<2, C::NTHR, C::NMAX>(ta, -1, ta, -1, n, -a.dt * a.isx, red);
+    cheb_diff_v<2, C::NTHR, C::NMAX>(tu, -1, tu, -1, n, -a.dt * a.isx, red);
     for (int i = threadIdx.x >> 1; i < n; i += C::NTHR / 2) {
       cplx* w = &tw[cidx<2>(rowof(N, i), c)];
-      *w = cadd(*w, ta[cidx<2>(i, c)]);
+      *w = cadd(*w, tu[cidx<2>(i, c)]);
     }
   } else if (a.mode == 1) {  // - dt/sy d/dy pres + dt * (that + tbc)   (navier.rs:646-648)
-    {
-      const StencilPair sp = stencil_pair(a.tmp.cols, col, a.tysd, a.tysl);
-      xfill<C::NTHR>(ta, mxr, [&](int i) { return ld2_stencil(a.tmp, i, sp); });
-    }
+    xstencil_cols<C::NTHR>(tu, a.tmp, mxr, col, stencil_pair(a.tmp.cols, col, a.tysd, a.tysl));
     __syncthreads();
     for (int i0 = threadIdx.x >> 1; i0 < n; i0 += (C::NTHR / 2) * 4) {
       cplx g1[4], g2[4];
@@ -201,7 +224,7 @@ FK_DEV void xk_forward_body(const XForwardArgs& a, const XForwardArgs3& a3) {
       for (int u = 0; u < 4; ++u) {
         const int i = i0 + u * (C::NTHR / 2);
         if (i < n) {
-          const cplx that = cadd(sx_at(i, a.txsd, a.txsl), g2[u]);
+          const cplx that = cadd(sx_at(tu, i, a.txsd, a.txsl), g2[u]);
           cplx* w = &tw[cidx<2>(rowof(N, i), c)];
           *w = sfma(a.dt, that, sfma(-a.dt, g1[u], *w));
         }
