@@ -103,6 +103,16 @@ def test_navier_confined_specialised_kernels(emu, nx, ny, adiabatic, own_eig):
     assert max(derr) < 1e-9, (derr, dn, do)
 
 
+@pytest.mark.parametrize("nx,ny", [(530, 129), (1030, 33)])
+def test_navier_confined_specialised_kernels_partial_lanes(emu, nx, ny):
+    """x lanes much shorter than the instantiated Bluestein length (2048 / 4096): the chunk-major coefficient tables
+    have fewer rows of slots than the kernels' compile-time chunk bound, the staged strips are partly empty."""
+    import rustpde_b200 as R
+    assert R.Navier2D.new(nx, ny, 1e5, 1.0, 0.01, 1.0, True, lib=emu).kernel_path()[0]
+    err, derr, dn, do = pc.check_navier_steps(emu, False, nx, ny, 2, tol=1e-9, batch=2)
+    assert max(derr) < 1e-9, (derr, dn, do)
+
+
 def test_lane_program_and_specialised_kernels_agree(emu, monkeypatch):
     """The generic lane programs and the specialised kernels implement the same step."""
     import rustpde_b200 as R
