@@ -112,9 +112,21 @@ FK_DEV void yk_adi_body(const YAdiArgs& a, const YAdiArgs3& a3) {
     return v;
   };
   if (a.mode == 1) {
-    for (int it = threadIdx.x; it < n * C::LR; it += C::NTHR) {
-      const int l = it % C::LR, j = it / C::LR;
-      if (r0 + l < a.aux.rows) a.aux.p[(size_t)(r0 + l) * a.aux.ld + j] = pj(j, l);
+    // batches of 8: the stencil coefficients come from L2, one exposed round trip per element otherwise
+    constexpr int U = 8, TOT = n * C::LR;
+    for (int it0 = threadIdx.x; it0 < TOT; it0 += C::NTHR * U) {
+      double v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int it = min(it0 + u * C::NTHR, TOT - 1);
+        v[u] = pj(it / C::LR, it % C::LR);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int it = it0 + u * C::NTHR;
+        const int l = it % C::LR, j = it / C::LR;
+        if (it < TOT && r0 + l < a.aux.rows) a.aux.p[(size_t)(r0 + l) * a.aux.ld + j] = v[u];
+      }
     }
     return;
   }
