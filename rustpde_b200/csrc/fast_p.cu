@@ -289,9 +289,9 @@ __global__ void __launch_bounds__(YCfg<LOG2L, LC>::NTHR, YCfg<LOG2L, LC>::SMEM1 
   });
   __syncthreads();
   from_ortho<LC, C::NTHR, C::CL>(td, -1, n, a.t, red);
-  tile_drain<LC, C::NTHR>(td, -1, m, [&](int j, int l, double v) {
+  tile_drain_sub<LC, C::NTHR>(td, -1, m, [&](int j, int l) -> double* {
     const int r = prow_of(r0, l);
-    if (r < a.ux.rows) a.ux.p[((size_t)r * a.ux.ld + j) * 2 + (l & 1)] -= v;
+    return (r < a.ux.rows) ? a.ux.p + ((size_t)r * a.ux.ld + j) * 2 + (l & 1) : nullptr;
   });
   __syncthreads();
   // to_ortho(phi): pressure update p += -nu div + to_ortho(phi) / dt   (navier.rs:717-721)
@@ -318,9 +318,9 @@ __global__ void __launch_bounds__(YCfg<LOG2L, LC>::NTHR, YCfg<LOG2L, LC>::SMEM1 
   // uy -= from_ortho_y(D_y S_y phi / sy)
   cheb_diff<LC, C::NTHR, C::CL>(td, -1, td, -1, n, a.isy, red);
   from_ortho<LC, C::NTHR, C::CL>(td, -1, n, a.t, red);
-  tile_drain<LC, C::NTHR>(td, -1, m, [&](int j, int l, double v) {
+  tile_drain_sub<LC, C::NTHR>(td, -1, m, [&](int j, int l) -> double* {
     const int r = prow_of(r0, l);
-    if (r < a.uy.rows) a.uy.p[((size_t)r * a.uy.ld + j) * 2 + (l & 1)] -= v;
+    return (r < a.uy.rows) ? a.uy.p + ((size_t)r * a.uy.ld + j) * 2 + (l & 1) : nullptr;
   });
 }
 

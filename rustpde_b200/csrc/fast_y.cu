@@ -185,8 +185,8 @@ __global__ void __launch_bounds__(YCfg<LOG2L, LC>::NTHR, YCfg<LOG2L, LC>::SMEM1 
   tile_fill<LC, C::NTHR>(td, n, [&](int j, int l) { return ld_stencil(a.a1, r0 + l, j, m, a.nsd, a.nsl); });
   __syncthreads();
   from_ortho<LC, C::NTHR, C::CL>(td, -1, n, a.t, red);
-  tile_drain<LC, C::NTHR>(td, -1, m, [&](int j, int l, double v) {
-    if (r0 + l < a.ux.rows) a.ux.p[(size_t)(r0 + l) * a.ux.ld + j] -= v;
+  tile_drain_sub<LC, C::NTHR>(td, -1, m, [&](int j, int l) -> double* {
+    return (r0 + l < a.ux.rows) ? a.ux.p + (size_t)(r0 + l) * a.ux.ld + j : nullptr;
   });
   __syncthreads();
   // uy -= from_ortho_y(D_y S_y a2 / sy)
@@ -194,8 +194,8 @@ __global__ void __launch_bounds__(YCfg<LOG2L, LC>::NTHR, YCfg<LOG2L, LC>::SMEM1 
   __syncthreads();
   cheb_diff<LC, C::NTHR, C::CL>(td, -1, td, -1, n, a.isy, red);
   from_ortho<LC, C::NTHR, C::CL>(td, -1, n, a.t, red);
-  tile_drain<LC, C::NTHR>(td, -1, m, [&](int j, int l, double v) {
-    if (r0 + l < a.uy.rows) a.uy.p[(size_t)(r0 + l) * a.uy.ld + j] -= v;
+  tile_drain_sub<LC, C::NTHR>(td, -1, m, [&](int j, int l) -> double* {
+    return (r0 + l < a.uy.rows) ? a.uy.p + (size_t)(r0 + l) * a.uy.ld + j : nullptr;
   });
 }
 

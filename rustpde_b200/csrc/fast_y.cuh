@@ -55,6 +55,29 @@ FK_DEV void tile_drain(const double* td, int sn, int nout, G g) {
   }
 }
 
+// *addr(j, lane) -= tile(j, lane) for j < nout (addr returns nullptr for lanes outside the matrix).  The old values
+// of a batch are all requested before the first store: a plain `-=` loop exposes one DRAM round trip per element.
+template <int LC, int NTHR, class A>
+FK_DEV void tile_drain_sub(const double* td, int sn, int nout, A addr) {
+  constexpr int LR = 2 * LC, U = FK_FILL_U;
+  const int tot = nout * LR;
+  for (int it0 = threadIdx.x; it0 < tot; it0 += NTHR * U) {
+    double* p[U];
+    double old[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int it = it0 + u * NTHR;
+      p[u] = it < tot ? addr(it / LR, it % LR) : nullptr;
+      old[u] = p[u] ? *p[u] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int it = it0 + u * NTHR;
+      if (p[u]) *p[u] = old[u] - td[didx<LC>(rowof(sn, it / LR), it % LR)];
+    }
+  }
+}
+
 // composite -> ortho stencil applied while loading row r of `a` (m = n-2 columns):
 // p_j = d_j c_j + l_{j-2} c_{j-2}   (composite_stencil.rs:207-229)
 // All loads are unconditional (clamped indices, zero weights) so that the compiler
