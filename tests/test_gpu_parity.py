@@ -239,3 +239,14 @@ def test_full_size_properties(gpu):
 def test_staged_state_upload(gpu, periodic, nx, ny):
     """rp_navier_stage_state / commit_staged (copy stream, overlaps update()) == plain vhat uploads, bit for bit."""
     assert pc.check_staged_upload(gpu, periodic, nx, ny)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nx,ny", [(530, 129), (1030, 33)])
+def test_navier_confined_partial_lanes(gpu, nx, ny):
+    """x lanes much shorter than the instantiated Bluestein length (2048 / 4096 rows): chunk-major coefficient tables
+    with fewer rows of slots than the kernels' chunk bound, partly empty staged strips.  Diagnostics <= 1e-9 relative."""
+    import rustpde_b200 as R
+    assert R.Navier2D.new(nx, ny, 1e5, 1.0, 0.01, 1.0, True, lib=gpu).kernel_path()[0]
+    err, derr, dn, do = pc.check_navier_steps(gpu, False, nx, ny, 2, tol=1e-9, batch=2)
+    assert max(derr) < 1e-9, (derr, dn, do)
