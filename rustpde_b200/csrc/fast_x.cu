@@ -8,6 +8,10 @@
 //                 (navier.rs:622-674) + x half of HholtzAdi (hholtz_adi.rs:108,128)
 //   xk_div      : divergence (navier.rs:698-703) + B2_x of the Poisson rhs
 //   xk_project  : x part of u -= from_ortho(grad phi) (navier.rs:683-695)
+//
+// Column strips are strided in memory (one 32-byte sector per row), so every array is read exactly once per
+// element, 16 bytes per thread; xk_forward stages the strips of its later phases asynchronously (cp.async) into
+// tiles that are idle at the time (xstage / xstencil_cols).
 #include "fast.cuh"
 
 namespace rp {
