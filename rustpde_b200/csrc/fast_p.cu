@@ -397,7 +397,7 @@ __global__ void __launch_bounds__(YCfg<LOG2L, LC>::NTHR, YCfg<LOG2L, LC>::SMEM1 
 }
 
 // ---- launchers -----------------------------------------------------------------------------------
-#define PX_SIZES(X) X(5, 2) X(6, 2) X(7, 1) X(9, 2) X(10, 2) X(11, 2) X(12, 1) X(13, 1)
+#define PX_SIZES(X) X(5, 2) X(6, 2) X(7, 1) X(8, 2) X(9, 2) X(10, 2) X(11, 2) X(12, 1) X(13, 1)
 
 bool px_supported(int n0) {
   const int l = log2_of(n0);

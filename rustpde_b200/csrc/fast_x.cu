@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(XCfg<LOG2LB>::NTHR, XCfg<LOG2LB>::MINB) xk_pro
 // launchers
 // ---------------------------------------------------------------------------------
 // log2 Bluestein length (complex lanes per tile: always 2)
-#define XK_SIZES(X) X(6, 2) X(7, 2) X(11, 2) X(12, 2)
+#define XK_SIZES(X) X(6, 2) X(7, 2) X(8, 2) X(9, 2) X(10, 2) X(11, 2) X(12, 2)
 
 static int bluestein_log2(int n0) {  // tables.cu: Lb = next_pow2(2N - 1)
   const int need = 2 * (n0 - 1) - 1;

@@ -157,7 +157,7 @@ static int log2_of(int v) {
 }
 
 // (log2 lane length, complex lanes per tile): long lanes use the 2-real-lane tile
-#define YK_SIZES(X) X(5, 2) X(6, 2) X(7, 1) X(9, 2) X(10, 2) X(11, 2) X(12, 1) X(13, 1)
+#define YK_SIZES(X) X(5, 2) X(6, 2) X(7, 1) X(8, 2) X(9, 2) X(10, 2) X(11, 2) X(12, 1) X(13, 1)
 
 template <class K>
 static void set_smem(K kern, int bytes) {

@@ -103,7 +103,7 @@ def test_navier_confined_specialised_kernels(emu, nx, ny, adiabatic, own_eig):
     assert max(derr) < 1e-9, (derr, dn, do)
 
 
-@pytest.mark.parametrize("nx,ny", [(530, 129), (1030, 33)])
+@pytest.mark.parametrize("nx,ny", [(530, 129), (1030, 33), (300, 257), (200, 65)])
 def test_navier_confined_specialised_kernels_partial_lanes(emu, nx, ny):
     """x lanes much shorter than the instantiated Bluestein length (2048 / 4096): the chunk-major coefficient tables
     have fewer rows of slots than the kernels' compile-time chunk bound, the staged strips are partly empty."""

@@ -242,11 +242,20 @@ def test_staged_state_upload(gpu, periodic, nx, ny):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("nx,ny", [(530, 129), (1030, 33)])
+@pytest.mark.parametrize("nx,ny", [(530, 129), (1030, 33), (300, 257), (200, 65)])
 def test_navier_confined_partial_lanes(gpu, nx, ny):
     """x lanes much shorter than the instantiated Bluestein length (2048 / 4096 rows): chunk-major coefficient tables
     with fewer rows of slots than the kernels' chunk bound, partly empty staged strips.  Diagnostics <= 1e-9 relative."""
     import rustpde_b200 as R
     assert R.Navier2D.new(nx, ny, 1e5, 1.0, 0.01, 1.0, True, lib=gpu).kernel_path()[0]
     err, derr, dn, do = pc.check_navier_steps(gpu, False, nx, ny, 2, tol=1e-9, batch=2)
+    assert max(derr) < 1e-9, (derr, dn, do)
+
+
+@pytest.mark.gpu
+def test_navier_periodic_256(gpu):
+    """r2c length 256 / y lanes of 257 points (instantiations added last): specialised kernels, diagnostics <= 1e-9."""
+    import rustpde_b200 as R
+    assert R.Navier2D.new_periodic(256, 257, 1e5, 1.0, 0.01, 1.0, lib=gpu).kernel_path()[0]
+    err, derr, dn, do = pc.check_navier_steps(gpu, True, 256, 257, 2, tol=1e-9, batch=2)
     assert max(derr) < 1e-9, (derr, dn, do)
