@@ -73,6 +73,9 @@ int rp_field_upload_v(rp_field_t* f, const double* v, size_t len);      /* pub v
 int rp_field_download_v(rp_field_t* f, double* v, size_t len);
 int rp_field_upload_vhat(rp_field_t* f, const double* vhat, size_t len);/* pub vhat */
 int rp_field_download_vhat(rp_field_t* f, double* vhat, size_t len);
+/* rows [row0, row0+nrows) of the pub vhat (a kx slab of the spectral array, dense host block) */
+int rp_field_upload_vhat_rows(rp_field_t* f, int row0, int nrows, const double* vhat, size_t len);
+int rp_field_download_vhat_rows(rp_field_t* f, int row0, int nrows, double* vhat, size_t len);
 int rp_field_forward(rp_field_t* f);                                    /* field.rs:103-105 */
 int rp_field_backward(rp_field_t* f);                                   /* field.rs:108-110 */
 int rp_field_to_ortho(rp_field_t* f, double* out, size_t len);          /* field.rs:113-115 */
@@ -94,6 +97,9 @@ int rp_hholtz_create_with_eig(rp_field_t* f, double cx, double cy, double alpha,
 int rp_poisson_create_with_eig(rp_field_t* f, double cx, double cy, const double* lam, const double* q, const double* p,
                                rp_solver_t** out);
 int rp_solver_eig_size(rp_solver_t* s, int* m, int* has_matrices);
+/* The exported eigenvalues are those of inv(Cx) Ax in the reference order (descending, utils.rs:80-94) BEFORE the
+ * Poisson singularity shift (poisson.rs:80-83); *_create_with_eig expects the same and applies the shift itself,
+ * so create_with_eig(export_eig()) reproduces the solver exactly. */
 int rp_solver_export_eig(rp_solver_t* s, double* lam, double* q, double* p);
 /* Solve::solve(&self, input, output, axis) ; input [n0,n1] ortho, output composite */
 int rp_solver_solve(rp_solver_t* s, const double* in, size_t in_len, double* out, size_t out_len, int is_complex);
@@ -121,6 +127,17 @@ int rp_navier_sync(rp_navier_t* h);
 int rp_navier_stage_state(rp_navier_t* h, const double* temp, size_t len_temp, const double* ux, size_t len_ux,
                           const double* uy, size_t len_uy, const double* pres, size_t len_pres);
 int rp_navier_commit_staged(rp_navier_t* h);
+/* Asynchronous download of the same four pub `vhat` arrays (what `write()` 975-1013 stores): the state is
+ * snapshotted on the compute stream and copied to the (page-locked) host buffers on a second copy stream, so the
+ * copies overlap the following update()s; fetch_wait blocks until the buffers are complete. */
+int rp_navier_fetch_state(rp_navier_t* h, double* temp, size_t len_temp, double* ux, size_t len_ux, double* uy, size_t len_uy,
+                          double* pres, size_t len_pres);
+int rp_navier_fetch_wait(rp_navier_t* h);
+/* Integrate::exit (855-862) without a host sync per step: div_async queues |div u|_2 of the current state and its
+ * copy to a page-locked slot; div_poll returns the most recent value that has arrived (ready = 0: none yet;
+ * wait != 0 blocks for the outstanding request).  integrate() then sees a NaN one check late. */
+int rp_navier_div_async(rp_navier_t* h);
+int rp_navier_div_poll(rp_navier_t* h, int wait, double* div_norm, int* ready);
 int rp_navier_get_time(rp_navier_t* h, double* time);                          /* get_time */
 int rp_navier_get_dt(rp_navier_t* h, double* dt);                              /* get_dt */
 int rp_navier_reset_time(rp_navier_t* h);                                      /* 951-953 */

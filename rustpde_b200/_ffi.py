@@ -33,6 +33,8 @@ _SIGS = {
     "rp_field_download_v": [vp, c_double_p, C.c_size_t],
     "rp_field_upload_vhat": [vp, c_double_p, C.c_size_t],
     "rp_field_download_vhat": [vp, c_double_p, C.c_size_t],
+    "rp_field_upload_vhat_rows": [vp, C.c_int, C.c_int, c_double_p, C.c_size_t],
+    "rp_field_download_vhat_rows": [vp, C.c_int, C.c_int, c_double_p, C.c_size_t],
     "rp_field_forward": [vp],
     "rp_field_backward": [vp],
     "rp_field_to_ortho": [vp, c_double_p, C.c_size_t],
@@ -59,6 +61,10 @@ _SIGS = {
     "rp_navier_update": [vp, C.c_int],
     "rp_navier_stage_state": [vp, c_double_p, C.c_size_t, c_double_p, C.c_size_t, c_double_p, C.c_size_t, c_double_p, C.c_size_t],
     "rp_navier_commit_staged": [vp],
+    "rp_navier_fetch_state": [vp, c_double_p, C.c_size_t, c_double_p, C.c_size_t, c_double_p, C.c_size_t, c_double_p, C.c_size_t],
+    "rp_navier_fetch_wait": [vp],
+    "rp_navier_div_async": [vp],
+    "rp_navier_div_poll": [vp, C.c_int, c_double_p, c_int_p],
     "rp_navier_sync": [vp],
     "rp_navier_get_time": [vp, c_double_p],
     "rp_navier_get_dt": [vp, c_double_p],

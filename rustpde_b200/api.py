@@ -162,6 +162,17 @@ class Field2:
             raise RustpdeError(2, "vhat: shape mismatch %s vs %s" % (a.shape, self.shape_spectral))
         self._lib.call("rp_field_upload_vhat", self._h, _dp(flat), flat.size)
 
+    def vhat_rows(self, row0, nrows):
+        """Rows [row0, row0+nrows) of vhat (the kx slab a rank owns in the slab decomposition)."""
+        a = np.zeros((nrows, self.shape_spectral[1]), dtype=self.spectral_dtype)
+        flat = a.view(np.float64).reshape(-1)
+        self._lib.call("rp_field_download_vhat_rows", self._h, int(row0), int(nrows), _dp(flat), flat.size)
+        return a
+
+    def set_vhat_rows(self, row0, val):
+        a, flat = _as_f64(val, self.is_complex)
+        self._lib.call("rp_field_upload_vhat_rows", self._h, int(row0), int(a.shape[0]), _dp(flat), flat.size)
+
     def forward(self):  # field.rs:103-105
         self._lib.call("rp_field_forward", self._h)
 
@@ -405,6 +416,39 @@ class Navier2D:
         self._lib.call("rp_navier_commit_staged", self._h)
         self._staged_keep = None
 
+    def _state_args(self, bufs, keep):
+        args = []
+        for a in bufs:
+            if isinstance(a, tuple):
+                ptr, n = a
+            else:
+                assert a.flags["C_CONTIGUOUS"]
+                keep.append(a)
+                ptr, n = a.ctypes.data, a.view(np.float64).size
+            args += [C.cast(ptr, _ffi.c_double_p), C.c_size_t(n)]
+        return args
+
+    def fetch_state(self, temp, ux, uy, pres):
+        """Queue the download of the complete state into host buffers (numpy arrays or (address, n_doubles) pairs of
+        page-locked memory) on a second copy stream; overlaps the following update()s.  fetch_wait() completes it."""
+        keep = []
+        self._lib.call("rp_navier_fetch_state", self._h, *self._state_args((temp, ux, uy, pres), keep))
+        self._fetch_keep = keep
+
+    def fetch_wait(self):
+        self._lib.call("rp_navier_fetch_wait", self._h)
+        self._fetch_keep = None
+
+    def div_async(self):
+        """Queue |div u|_2 of the current state without waiting for it (see div_poll)."""
+        self._lib.call("rp_navier_div_async", self._h)
+
+    def div_poll(self, wait=False):
+        """Most recent |div u|_2 that has arrived from div_async(), or None."""
+        v, ready = C.c_double(), C.c_int()
+        self._lib.call("rp_navier_div_poll", self._h, int(bool(wait)), C.byref(v), C.byref(ready))
+        return v.value if ready.value else None
+
     def get_time(self):
         return self.time
 
@@ -445,6 +489,13 @@ class Navier2D:
     def exit(self):  # navier.rs:855-862: stop when |div| is NaN
         return math.isnan(self.div_norm())
 
+    def exit_async(self):
+        """exit() without a device sync: queues |div| of this step and tests the newest value that has already
+        arrived (so a NaN is seen one check late)."""
+        self.div_async()
+        d = self.div_poll(False)
+        return d is not None and math.isnan(d)
+
     def export_eig(self):
         m = self.nx - 2
         lam, q, p = np.zeros(m), np.zeros((m, m)), np.zeros((m, m))
@@ -479,9 +530,9 @@ class Navier2D:
         return out
 
 
-def integrate(pde, max_time, save_intervall=None, exit_every=1):
-    """src/lib.rs:155-187.  `exit_every` > 1 checks the NaN break criterion less
-    often (the reference checks every step, which costs a device sync)."""
+def integrate(pde, max_time, save_intervall=None, exit_every=1, async_exit=False):
+    """src/lib.rs:155-187.  `exit_every` > 1 checks the NaN break criterion less often (the reference checks every
+    step, which costs a device sync); `async_exit` uses exit_async() (no sync, NaN seen one check late)."""
     timestep = 0
     eps_dt = pde.get_dt() * 1e-4
     while True:
@@ -497,7 +548,7 @@ def integrate(pde, max_time, save_intervall=None, exit_every=1):
         if timestep >= MAX_TIMESTEP:
             print("timestep limit reached: %r" % timestep)
             break
-        if timestep % exit_every == 0 and pde.exit():
+        if timestep % exit_every == 0 and (pde.exit_async() if async_exit else pde.exit()):
             print("break criteria triggered")
             break
     return timestep

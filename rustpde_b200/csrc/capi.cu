@@ -144,6 +144,28 @@ int rp_field_download_vhat(rp_field_t* f, double* v, size_t len) {
     rt::sync(f->f->stream);
   });
 }
+// rows [row0, row0 + nrows) of vhat <-> a dense host block (the slab a rank owns in the kx decomposition)
+static void vhat_rows(rp_field_t* f, int row0, int nrows, double* host, size_t len, bool up) {
+  need(f && host, RP_ERR_INVALID, "null argument");
+  Arr& a = f->f->vhat;
+  need(row0 >= 0 && nrows > 0 && row0 + nrows <= a.rows, RP_ERR_INVALID, "vhat_rows: bad row range");
+  need(len == (size_t)nrows * a.cols * (a.cplx ? 2 : 1), RP_ERR_SHAPE, "vhat_rows: size mismatch");
+  const size_t w = (size_t)a.cols * a.elem_bytes(), pitch = (size_t)a.ld * a.elem_bytes();
+  char* d = (char*)a.buf.p + (size_t)row0 * pitch;
+  if (up) {
+    rt::h2d_2d(d, pitch, host, w, w, nrows, f->f->stream);
+    ++f->f->vhat_version;
+  } else {
+    rt::d2h_2d(host, w, d, pitch, w, nrows, f->f->stream);
+  }
+  rt::sync(f->f->stream);
+}
+int rp_field_upload_vhat_rows(rp_field_t* f, int row0, int nrows, const double* vhat, size_t len) {
+  return guard([&] { vhat_rows(f, row0, nrows, const_cast<double*>(vhat), len, true); });
+}
+int rp_field_download_vhat_rows(rp_field_t* f, int row0, int nrows, double* vhat, size_t len) {
+  return guard([&] { vhat_rows(f, row0, nrows, vhat, len, false); });
+}
 int rp_field_forward(rp_field_t* f) {
   return guard([&] {
     need(f, RP_ERR_INVALID, "null field");
@@ -193,7 +215,7 @@ int rp_field_average(rp_field_t* f, double* out) {
 int rp_field_average_axis(rp_field_t* f, int axis, double* out, size_t len) {
   return guard([&] {
     need(f && out, RP_ERR_INVALID, "null argument");
-    need(axis == 0, RP_ERR_INVALID, "average_axis: only axis 0 is on the Navier2D path");
+    need(axis == 0, RP_ERR_INVALID, "average_axis: only axis 0 is on the Navier2D path (functions.rs:33)");
     need(len == (size_t)f->f->n1, RP_ERR_SHAPE, "average_axis: output size mismatch");
     std::vector<double> v;
     f->f->average_axis0(v);
@@ -346,6 +368,25 @@ int rp_navier_commit_staged(rp_navier_t* h) {
   return guard([&] {
     need(h, RP_ERR_INVALID, "null handle");
     h->n->commit_staged();
+  });
+}
+int rp_navier_fetch_state(rp_navier_t* h, double* temp, size_t len_temp, double* ux, size_t len_ux, double* uy, size_t len_uy,
+                          double* pres, size_t len_pres) {
+  return guard([&] {
+    need(h && temp && ux && uy && pres, RP_ERR_INVALID, "null argument");
+    Navier2D& n = *h->n;
+    need(len_temp == arr_len(n.temp->vhat) && len_ux == arr_len(n.ux->vhat) && len_uy == arr_len(n.uy->vhat) &&
+             len_pres == arr_len(n.pres0->vhat),
+         RP_ERR_SHAPE, "fetch_state: size mismatch");
+    n.fetch_state(temp, ux, uy, pres);
+  });
+}
+int rp_navier_fetch_wait(rp_navier_t* h) { NAV_GUARD(N.fetch_wait()); }
+int rp_navier_div_async(rp_navier_t* h) { NAV_GUARD(N.div_async()); }
+int rp_navier_div_poll(rp_navier_t* h, int wait, double* div_norm, int* ready) {
+  NAV_GUARD({
+    const bool ok = N.div_poll(div_norm, wait != 0);
+    if (ready) *ready = ok ? 1 : 0;
   });
 }
 int rp_navier_sync(rp_navier_t* h) { NAV_GUARD(N.sync()); }

@@ -50,6 +50,23 @@ struct ModeTabs {  // per-lane A + (lam + alpha) C (fdma_tensor.rs:219-227)
 bool y_supported(int n1);
 bool x_supported(int n0);
 
+// true the first time it is called for `mask` on the current CUDA device (kernel attributes such as the dynamic
+// shared-memory limit are per device, not per process)
+inline bool first_use_on_device(unsigned long long& mask) {
+#ifndef RP_EMU
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (mask & bit) return false;
+  mask |= bit;
+  return true;
+#else
+  if (mask) return false;
+  mask = 1;
+  return true;
+#endif
+}
+
 // ---- chunk-major coefficient tables of the chunked scans (fast.cuh) ------------------------------
 // A scan over m elements is cut into NG chunks per parity chain of cl = ceil(ceil(m / 2) / NG) elements; element
 // (group g, step u, parity p) is natural index i = 2 t + p (forward) or 2 (M_p - 1 - t) + p (backward), t = g cl + u,

@@ -413,10 +413,9 @@ bool px_supported(int n0) {
     typedef PXCfg<L, LCV> C;                                                          \
     auto kp_ = kern<L, LCV>;                                                          \
     const int nb_ = ((ncols_) + 2 * LCV - 1) / (2 * LCV);                             \
-    static bool init_ = false;                                                        \
-    if (!init_) {                                                                     \
+    static unsigned long long init_ = 0; /* one bit per device */                                                        \
+    if (first_use_on_device(init_)) {                                                                     \
       set_smem(kp_, C::SMEM);                                                         \
-      init_ = true;                                                                   \
     }                                                                                 \
     RP_LAUNCH(kp_, dim3(nb_, nby_), dim3(C::NTHR), (size_t)C::SMEM, s, a);            \
     ok_ = true;                                                                       \

@@ -365,10 +365,9 @@ static void set_smem(K kern, int bytes) {
     auto kp_ = kern<L>;                                                          \
     const int sm_ = (smem_expr);                                                 \
     const int nb_ = ((ncols_) + C::LR - 1) / C::LR;                              \
-    static bool init_ = false;                                                   \
-    if (!init_) {                                                                \
+    static unsigned long long init_ = 0; /* one bit per device */                                                   \
+    if (first_use_on_device(init_)) {                                                                \
       set_smem(kp_, sm_);                                                        \
-      init_ = true;                                                              \
     }                                                                            \
     RP_LAUNCH(kp_, dim3(nb_, nby_), dim3(C::NTHR), (size_t)sm_, s, a);           \
     ok_ = true;                                                                  \

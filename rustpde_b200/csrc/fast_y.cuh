@@ -185,10 +185,9 @@ static void set_smem(K kern, int bytes) {
     const int nb_ = ((nrows_) + C::LR - 1) / C::LR;                                           \
     const int sm_ = (smem_sel) == 2 ? C::SMEMC : ((smem_sel) == 1 ? C::SMEM2 : C::SMEM1);     \
     auto kp_ = kern<L, LCV>;                                                                  \
-    static bool init_ = false;                                                                \
-    if (!init_) {                                                                             \
+    static unsigned long long init_ = 0; /* one bit per device */                                                                \
+    if (first_use_on_device(init_)) {                                                                             \
       set_smem(kp_, sm_);                                                                     \
-      init_ = true;                                                                           \
     }                                                                                         \
     RP_LAUNCH(kp_, dim3(nb_, nby_), dim3(C::NTHR), (size_t)sm_, s, args);                     \
     ok_ = true;                                                                               \

@@ -134,7 +134,7 @@ void Field2::build_transforms() {
   for (int j = 0; j < n1; ++j) wy[j] = dx[1][j] / ly;
   wx_ = upload(wx);
   wy_ = upload(wy);
-  red_ = DevBuf(sizeof(double) * 4);
+  red_ = DevBuf(sizeof(double) * (RP_WSUM_DOUBLES + (size_t)(RP_AVG0_ROWPARTS + 1) * n1));
 }
 
 void Field2::forward() {
@@ -196,7 +196,6 @@ void Field2::gradient(int ddx, int ddy, const double* scale) {
 }
 
 double Field2::average() {
-  rt::dzero(red_.p, 8, stream);
   launch_wsum(v.d(), nullptr, v.ld, n0, n1, wx_.as<double>(), wy_.as<double>(), 0, red_.as<double>(), stream);
   double r = 0.0;
   rt::d2h(&r, red_.p, 8, stream);
@@ -204,14 +203,14 @@ double Field2::average() {
   return r;
 }
 
+// average.rs:25-33 along axis 0, reduced on the device (fixed summation order); only n1 values come back
 void Field2::average_axis0(std::vector<double>& out) {
-  std::vector<double> h((size_t)n0 * n1);
-  v.download(h.data(), stream);
-  rt::sync(stream);
-  const double lx = std::fabs(x[0][x[0].size() - 1] - x[0][0]);
+  double* scratch = red_.as<double>() + RP_WSUM_DOUBLES;
+  double* res = scratch + (size_t)RP_AVG0_ROWPARTS * n1;
+  launch_avg_axis0(v.d(), v.ld, n0, n1, wx_.as<double>(), scratch, res, stream);
   out.assign(n1, 0.0);
-  for (int i = 0; i < n0; ++i)
-    for (int j = 0; j < n1; ++j) out[j] += h[(size_t)i * n1 + j] * dx[0][i] / lx;
+  rt::d2h(out.data(), res, sizeof(double) * n1, stream);
+  rt::sync(stream);
 }
 
 }  // namespace rp

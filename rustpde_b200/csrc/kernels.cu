@@ -29,12 +29,14 @@ __global__ void __launch_bounds__(256, 2) dgemm_dmma_kernel(GemmArgs g0, GemmArg
 
 void init_kernels() {
 #ifndef RP_EMU
-  static bool done = false;
-  if (done) return;
+  static unsigned long long done = 0;  // one bit per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (done >> (dev & 63) & 1) return;
   RP_CUDA_CHECK(cudaFuncSetAttribute(lane_vm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RP_MAX_SMEM));
   RP_CUDA_CHECK(cudaFuncSetAttribute(dgemm_dmma_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<2, 4>::SMEM));
   RP_CUDA_CHECK(cudaFuncSetAttribute(dgemm_dmma_kernel<1, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<1, 7>::SMEM));
-  done = true;
+  done |= 1ull << (dev & 63);
 #endif
 }
 
@@ -250,10 +252,13 @@ RP_DEV double block_sum(double v, double* red) {
   return tot;  // valid on thread 0
 }
 
-// out[0] += sum_ij wx[i] wy[j] g(a, b, c)[i, j];  mode selects g
+// out[0] = sum_ij wx[i] wy[j] g(a, b)[i, j];  mode selects g
 //   0: a    1: sqrt(a^2+b^2)    2: 0.5 (a^2+b^2)    3: a^2 (sum of squares, weights ignored)
+// Two stages with a fixed summation order (bitwise reproducible between runs, unlike atomicAdd): every block
+// writes its partial sum to scratch[blockIdx.x], a single block adds the partials in index order.
+enum { WSUM_MAX_BLOCKS = 592 };
 __global__ void __launch_bounds__(256) wsum_kernel(const double* a, const double* b, long long ld, int rows, int cols,
-                                                    const double* wx, const double* wy, int mode, double* out) {
+                                                    const double* wx, const double* wy, int mode, double* scratch) {
   __shared__ double red[32];
   double acc = 0.0;
   const long long total = (long long)rows * cols;
@@ -274,14 +279,50 @@ __global__ void __launch_bounds__(256) wsum_kernel(const double* a, const double
     acc = fma(w, gval, acc);
   }
   const double tot = block_sum(acc, red);
-  if (threadIdx.x == 0) atomicAdd(out, tot);
+  if (threadIdx.x == 0) scratch[blockIdx.x] = tot;
 }
+__global__ void __launch_bounds__(256) wsum_final_kernel(const double* scratch, int n, double* out) {
+  __shared__ double red[32];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) acc += scratch[i];
+  const double tot = block_sum(acc, red);
+  if (threadIdx.x == 0) out[0] = tot;
+}
+// `out` must hold 1 + WSUM_MAX_BLOCKS doubles: out[0] receives the sum, out[1..] is scratch
 void launch_wsum(const double* a, const double* b, long long ld, int rows, int cols, const double* wx, const double* wy,
                  int mode, double* out, cudaStream_t s) {
   long long total = (long long)rows * cols;
-  int blocks = (int)std::min<long long>((total + 255) / 256, 592);
+  int blocks = (int)std::min<long long>((total + 255) / 256, (long long)WSUM_MAX_BLOCKS);
   if (blocks < 1) blocks = 1;
-  RP_LAUNCH(wsum_kernel, dim3(blocks), dim3(256), (size_t)0, s, a, b, ld, rows, cols, wx, wy, mode, out);
+  RP_LAUNCH(wsum_kernel, dim3(blocks), dim3(256), (size_t)0, s, a, b, ld, rows, cols, wx, wy, mode, out + 1);
+  RP_LAUNCH(wsum_final_kernel, dim3(1), dim3(256), (size_t)0, s, (const double*)(out + 1), blocks, out);
+}
+
+// out[j] = sum_i w[i] a[i][j]  (average_axis along axis 0, average.rs:25-33).  Stage 1: block (bx, by) sums the rows
+// i = by, by + gridDim.y, ... of 256 columns into scratch[by][j]; stage 2 adds the gridDim.y partials in order.
+enum { AVG0_ROWPARTS = 32 };
+__global__ void __launch_bounds__(256) avg_axis0_kernel(const double* a, long long ld, int rows, int cols, const double* w,
+                                                         double* scratch) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= cols) return;
+  double acc = 0.0;
+  for (int i = blockIdx.y; i < rows; i += gridDim.y) acc = fma(w[i], a[(size_t)i * ld + j], acc);
+  scratch[(size_t)blockIdx.y * cols + j] = acc;
+}
+__global__ void __launch_bounds__(256) avg_axis0_final_kernel(const double* scratch, int parts, int cols, double* out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= cols) return;
+  double acc = 0.0;
+  for (int p = 0; p < parts; ++p) acc += scratch[(size_t)p * cols + j];
+  out[j] = acc;
+}
+// scratch: AVG0_ROWPARTS * cols doubles
+void launch_avg_axis0(const double* a, long long ld, int rows, int cols, const double* w, double* scratch, double* out,
+                      cudaStream_t s) {
+  const int parts = std::min<int>(AVG0_ROWPARTS, rows);
+  dim3 grid((cols + 255) / 256, parts);
+  RP_LAUNCH(avg_axis0_kernel, grid, dim3(256), (size_t)0, s, a, ld, rows, cols, w, scratch);
+  RP_LAUNCH(avg_axis0_final_kernel, dim3((cols + 255) / 256), dim3(256), (size_t)0, s, (const double*)scratch, parts, cols, out);
 }
 
 // out = (a + b*c*s1) * s0   elementwise on pitched arrays (eval_nuvol, functions.rs:60-72)

@@ -21,8 +21,14 @@ void launch_dgemm(const GemmArgs& g, cudaStream_t s);
 void launch_dgemm2(const GemmArgs& g0, const GemmArgs& g1, cudaStream_t s);  // two independent products, one launch
 
 void launch_zero_elems(double* p, int count, cudaStream_t s);
+// weighted sum with a fixed summation order; `out` holds RP_WSUM_DOUBLES doubles (out[0] = result, rest scratch)
+enum { RP_WSUM_DOUBLES = 1 + 592 };
 void launch_wsum(const double* a, const double* b, long long ld, int rows, int cols, const double* wx, const double* wy,
                  int mode, double* out, cudaStream_t s);
+// out[j] = sum_i w[i] a[i][j]; scratch holds RP_AVG0_ROWPARTS * cols doubles
+enum { RP_AVG0_ROWPARTS = 32 };
+void launch_avg_axis0(const double* a, long long ld, int rows, int cols, const double* w, double* scratch, double* out,
+                      cudaStream_t s);
 void launch_combine(double* out, const double* a, const double* b, const double* c, long long ld, int rows, int cols,
                     double s0, double s1, cudaStream_t s);
 

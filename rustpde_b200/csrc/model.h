@@ -225,6 +225,12 @@ class Navier2D {
   // until the commit.
   void stage_state(const double* t, const double* u, const double* v, const double* p);
   void commit_staged();
+  // asynchronous state download on a second copy stream (see navier.cu)
+  void fetch_state(double* t, double* u, double* v, double* p);
+  void fetch_wait();
+  // exit() without a per-step host sync
+  void div_async();
+  bool div_poll(double* out, bool wait);
 
  private:
   void build_step();
@@ -239,8 +245,16 @@ class Navier2D {
   void rebuild_bc();
   void apply_ic(Field2& f, double amp, double m, double n, bool sin_cos);
   void run_step();
+  void prepare_step();
+#ifndef RP_EMU
+  void capture_graph();
+#endif
   double div_norm();
+  void enqueue_div2();
   Arr a1_, a2_;
+  Arr snap_[4];
+  double div_last_ = 0.0;
+  bool div_have_ = false, div_pending_ = false;
   bool graph_dirty_ = true;
   bool use_graph_ = true;
   unsigned long long dyp_version_ = ~0ull;  // pres0 version dyp_ was computed from
@@ -271,8 +285,9 @@ class Navier2D {
   fk::ModeTabs mode_of(const FdmaModeDev& m);
   fk::TdmaTabs tdma_of(const Base& b, int n, fk::ScanShape ng);
 #ifndef RP_EMU
-  cudaStream_t copy_stream_ = nullptr;
-  cudaEvent_t ev_staged_ = nullptr, ev_consumed_ = nullptr;
+  cudaStream_t copy_stream_ = nullptr, fetch_stream_ = nullptr;
+  cudaEvent_t ev_staged_ = nullptr, ev_consumed_ = nullptr, ev_fetch_ready_ = nullptr, ev_fetched_ = nullptr, ev_div_ = nullptr;
+  double* div_host_ = nullptr;
 #endif
 #ifndef RP_EMU
   cudaGraphExec_t graph_ = nullptr;

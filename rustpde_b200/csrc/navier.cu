@@ -78,7 +78,7 @@ Navier2D::Navier2D(int nx_, int ny_, double ra_, double pr_, double dt_, double 
   dxtbc_.alloc(nx, ny, false);
   dytbc_.alloc(nx, ny, false);
   bcdiff_.alloc(ox, ny, periodic);
-  red_ = DevBuf(64);
+  red_ = DevBuf(sizeof(double) * RP_WSUM_DOUBLES);
   // navier.rs:301 / 461: Rayleigh-Benard boundary field, T = +0.5 at y=-1, -0.5 at y=+1
   // (bc_rbc 314-332, bc_rbc_periodic 474-492): in the ortho basis only T_1(y) is present.
   std::vector<double> tb((size_t)ox * ny * (periodic ? 2 : 1), 0.0);
@@ -97,6 +97,16 @@ Navier2D::~Navier2D() {
     cudaStreamDestroy(copy_stream_);
     cudaEventDestroy(ev_staged_);
     cudaEventDestroy(ev_consumed_);
+  }
+  if (fetch_stream_) {
+    cudaStreamSynchronize(fetch_stream_);
+    cudaStreamDestroy(fetch_stream_);
+    cudaEventDestroy(ev_fetch_ready_);
+    cudaEventDestroy(ev_fetched_);
+  }
+  if (div_host_) {
+    cudaEventDestroy(ev_div_);
+    cudaFreeHost(div_host_);
   }
 #endif
 }
@@ -140,6 +150,42 @@ void Navier2D::commit_staged() {
   RP_CUDA_CHECK(cudaEventRecord(ev_consumed_, stream));
 #endif
   staged_ = false;
+}
+
+// Asynchronous download of the state (the vhat arrays of temp, ux, uy, pres[0]) into caller-owned host buffers on a
+// second copy stream: the snapshot is taken device-to-device on the compute stream (so later update()s may overwrite
+// the live arrays), the device-to-host copies then overlap those updates.  fetch_wait() blocks until they landed.
+void Navier2D::fetch_state(double* t, double* u, double* v, double* p) {
+  Field2* src[4] = {temp.get(), ux.get(), uy.get(), pres0.get()};
+  double* dst[4] = {t, u, v, p};
+  cudaStream_t cs = stream;
+#ifndef RP_EMU
+  if (!fetch_stream_) {
+    RP_CUDA_CHECK(cudaStreamCreateWithFlags(&fetch_stream_, cudaStreamNonBlocking));
+    RP_CUDA_CHECK(cudaEventCreateWithFlags(&ev_fetch_ready_, cudaEventDisableTiming));
+    RP_CUDA_CHECK(cudaEventCreateWithFlags(&ev_fetched_, cudaEventDisableTiming));
+  } else {
+    RP_CUDA_CHECK(cudaStreamWaitEvent(stream, ev_fetched_, 0));  // the snapshot arrays may still be read by the last fetch
+  }
+#endif
+  for (int i = 0; i < 4; ++i) {
+    if (!snap_[i].buf.p) snap_[i].alloc(src[i]->vhat.rows, src[i]->vhat.cols, src[i]->vhat.cplx);
+    rt::d2d(snap_[i].buf.p, src[i]->vhat.buf.p, snap_[i].buf.bytes, stream);
+  }
+#ifndef RP_EMU
+  RP_CUDA_CHECK(cudaEventRecord(ev_fetch_ready_, stream));
+  RP_CUDA_CHECK(cudaStreamWaitEvent(fetch_stream_, ev_fetch_ready_, 0));
+  cs = fetch_stream_;
+#endif
+  for (int i = 0; i < 4; ++i) snap_[i].download(dst[i], cs);
+#ifndef RP_EMU
+  RP_CUDA_CHECK(cudaEventRecord(ev_fetched_, fetch_stream_));
+#endif
+}
+void Navier2D::fetch_wait() {
+#ifndef RP_EMU
+  if (fetch_stream_) RP_CUDA_CHECK(cudaStreamSynchronize(fetch_stream_));
+#endif
 }
 
 Field2* Navier2D::field_by_index(int which) {
@@ -231,6 +277,18 @@ void Navier2D::build_step() {
   else
     build_step_confined();
   launches_per_step_ = (int)ops_.size();
+  if (fast_ok && fast_ops_.empty() && (long long)nx * ny >= 256 * 256 && !getenv("RUSTPDE_B200_QUIET")) {
+    // a performance cliff worth a line: the specialised kernels cover y lanes of 2^k + 1 points, confined x lanes whose
+    // period n-1 is NOT a power of two (Bluestein; 2^k + 1 points have no chirp tables) and periodic x lanes of 2^k points
+    static bool warned = false;
+    if (!warned) {
+      warned = true;
+      fprintf(stderr,
+              "[rustpde_b200] Navier2D %dx%d %s runs on the generic lane programs (several times slower): the specialised kernels "
+              "need ny = 2^k + 1 and %s\n",
+              nx, ny, periodic ? "periodic" : "confined", periodic ? "nx = 2^k" : "nx - 1 not a power of two (e.g. nx = 2^k)");
+    }
+  }
   if (getenv("RUSTPDE_B200_VERBOSE"))
     fprintf(stderr, "[rustpde_b200] Navier2D %dx%d %s: %s kernels, %d launches/step\n", nx, ny,
             periodic ? "periodic" : "confined", fast_ops_.empty() ? "lane-program" : "specialised", launches_per_step_);
@@ -1112,8 +1170,7 @@ void Navier2D::run_step() {
 // Per-launch device times of one update(), averaged over `reps` eager steps
 // (CUDA events on the launching stream).  Advances the solution by `reps` steps.
 void Navier2D::profile(int reps, std::vector<double>& ms) {
-  build_step();
-  for (auto& s : solver) s->stream = stream;
+  prepare_step();
   ms.assign(ops_.size(), 0.0);
 #ifndef RP_EMU
   std::vector<cudaEvent_t> ev(ops_.size() + 1);
@@ -1143,13 +1200,14 @@ void Navier2D::profile(int reps, std::vector<double>& ms) {
 #endif
 }
 
-void Navier2D::update(int nsteps) {
+// Everything a step needs before its first launch: the launch list, the streams of the member objects, and
+// d/dy pres of the *current* pressure (every step leaves it behind for the next one, so the refresh only runs at
+// the first step and after the pressure was rewritten from outside: upload / commit_staged / forward / from_ortho).
+void Navier2D::prepare_step() {
   build_step();
   for (Field2* f : {temp.get(), ux.get(), uy.get(), pres0.get(), pres1.get(), field.get()}) f->stream = stream;
   for (auto& s : solver) s->stream = stream;
   if (!periodic && dyp_version_ != pres0->vhat_version) {
-    // d/dy pres of the current pressure: every step leaves it behind for the next one, so this is only
-    // needed at the first step and after the pressure was rewritten from outside (upload / forward)
     if (fast_dyp_) {
       fast_dyp_();
     } else {
@@ -1158,29 +1216,63 @@ void Navier2D::update(int nsteps) {
     }
     dyp_version_ = pres0->vhat_version;
   }
+}
+
+#ifndef RP_EMU
+// Captures one step into graph_.  On any failure the capture is ended, the capture stream destroyed and the
+// object's streams restored before the error is rethrown (graph_dirty_ stays set), so the object stays usable.
+void Navier2D::capture_graph() {
+  if (graph_) {
+    cudaGraphExecDestroy(graph_);
+    graph_ = nullptr;
+  }
+  cudaStream_t cs = nullptr;
+  RP_CUDA_CHECK(cudaStreamCreate(&cs));
+  const cudaStream_t saved = stream;
+  auto restore = [&]() {
+    stream = saved;
+    for (auto& s : solver) s->stream = saved;
+    for (Field2* f : {temp.get(), ux.get(), uy.get(), pres0.get(), pres1.get(), field.get()}) f->stream = saved;
+  };
+  cudaGraph_t g = nullptr;
+  bool capturing = false;
+  try {
+    stream = cs;
+    for (auto& s : solver) s->stream = cs;
+    RP_CUDA_CHECK(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+    capturing = true;
+    run_step();
+    capturing = false;
+    RP_CUDA_CHECK(cudaStreamEndCapture(cs, &g));
+    RP_CUDA_CHECK(cudaGraphInstantiate(&graph_, g, 0));
+  } catch (...) {
+    if (capturing) {
+      cudaGraph_t dead = nullptr;
+      cudaStreamEndCapture(cs, &dead);  // invalidates the capture; `dead` is null on failure
+      if (dead) cudaGraphDestroy(dead);
+    }
+    if (g) cudaGraphDestroy(g);
+    if (graph_) {
+      cudaGraphExecDestroy(graph_);
+      graph_ = nullptr;
+    }
+    cudaGetLastError();
+    restore();
+    cudaStreamDestroy(cs);
+    throw;
+  }
+  cudaGraphDestroy(g);
+  restore();
+  cudaStreamDestroy(cs);
+  graph_dirty_ = false;
+}
+#endif
+
+void Navier2D::update(int nsteps) {
+  prepare_step();
 #ifndef RP_EMU
   if (use_graph_) {
-    if (!graph_ || graph_dirty_) {
-      if (graph_) {
-        cudaGraphExecDestroy(graph_);
-        graph_ = nullptr;
-      }
-      cudaStream_t cs;
-      RP_CUDA_CHECK(cudaStreamCreate(&cs));
-      cudaStream_t saved = stream;
-      stream = cs;
-      for (auto& s : solver) s->stream = cs;
-      cudaGraph_t g = nullptr;
-      RP_CUDA_CHECK(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
-      run_step();
-      RP_CUDA_CHECK(cudaStreamEndCapture(cs, &g));
-      RP_CUDA_CHECK(cudaGraphInstantiate(&graph_, g, 0));
-      cudaGraphDestroy(g);
-      stream = saved;
-      for (auto& s : solver) s->stream = saved;
-      cudaStreamDestroy(cs);
-      graph_dirty_ = false;
-    }
+    if (!graph_ || graph_dirty_) capture_graph();
     for (int i = 0; i < nsteps; ++i) {
       RP_CUDA_CHECK(cudaGraphLaunch(graph_, stream));
       time += dt;
@@ -1197,28 +1289,72 @@ void Navier2D::update(int nsteps) {
 // --------------------------------------------------------------------------
 // Diagnostics (src/navier/functions.rs, navier.rs:855-879)
 // --------------------------------------------------------------------------
-double Navier2D::div_norm() {
+// queues |div u|^2 of the current velocity into red_[0] on `stream` (no host sync)
+void Navier2D::enqueue_div2() {
   build_step();
   if (fast_div_) {  // specialised kernels: vx_, ey_, div_, r1_ are scratch between steps
     fast_div_();
-    rt::dzero(red_.p, 8, stream);
     launch_wsum(div_.d(), nullptr, div_.ld, div_.rows, div_.cols, nullptr, nullptr, 3, red_.as<double>(), stream);
-    double r = 0.0;
-    rt::d2h(&r, red_.p, 8, stream);
-    rt::sync(stream);
-    return std::sqrt(r);
+    return;
   }
+  for (Field2* f : {ux.get(), uy.get()}) f->stream = stream;
   ux->gradient(1, 0, scale);
   uy->gradient(0, 1, scale);
   const int rc = ux->cplx ? 2 : 1;
   Arr& o = ux->ortho;
   launch_combine(o.d(), o.d(), uy->ortho.d(), nullptr, o.ld * rc, o.rows, o.cols * rc, 1.0, 1.0, stream);
-  rt::dzero(red_.p, 8, stream);
   launch_wsum(o.d(), nullptr, o.ld * rc, o.rows, o.cols * rc, nullptr, nullptr, 3, red_.as<double>(), stream);
+}
+
+double Navier2D::div_norm() {
+  enqueue_div2();
   double r = 0.0;
   rt::d2h(&r, red_.p, 8, stream);
   rt::sync(stream);
   return std::sqrt(r);
+}
+
+// exit() without a host sync per step (navier.rs:855-862): div_async() queues |div u|^2 of the current state and its
+// copy into a page-locked slot; div_poll() reports the most recent value that has arrived.  integrate() therefore
+// sees a NaN one check late instead of stalling the stream every step.
+void Navier2D::div_async() {
+#ifndef RP_EMU
+  if (!div_host_) {
+    RP_CUDA_CHECK(cudaMallocHost((void**)&div_host_, 2 * sizeof(double)));
+    div_host_[0] = div_host_[1] = 0.0;
+    RP_CUDA_CHECK(cudaEventCreateWithFlags(&ev_div_, cudaEventDisableTiming));
+  } else if (div_pending_) {
+    RP_CUDA_CHECK(cudaEventSynchronize(ev_div_));  // the slot is still in flight: at most one outstanding request
+    div_last_ = std::sqrt(div_host_[0]);
+    div_have_ = true;
+  }
+  enqueue_div2();
+  rt::d2h(div_host_, red_.p, 8, stream);
+  RP_CUDA_CHECK(cudaEventRecord(ev_div_, stream));
+  div_pending_ = true;
+#else
+  div_last_ = div_norm();
+  div_have_ = true;
+#endif
+}
+// returns true when a value is available (out = |div u|_2 of the most recently completed request)
+bool Navier2D::div_poll(double* out, bool wait) {
+#ifndef RP_EMU
+  if (div_pending_) {
+    cudaError_t e = wait ? cudaEventSynchronize(ev_div_) : cudaEventQuery(ev_div_);
+    if (e == cudaSuccess) {
+      div_last_ = std::sqrt(div_host_[0]);
+      div_have_ = true;
+      div_pending_ = false;
+    } else if (e != cudaErrorNotReady) {
+      RP_CUDA_CHECK(e);
+    }
+  }
+#else
+  (void)wait;
+#endif
+  if (out && div_have_) *out = div_last_;
+  return div_have_;
 }
 
 void Navier2D::eval(double* o_nu, double* o_nuvol, double* o_re, double* o_div, double* o_ekin) {
@@ -1259,7 +1395,6 @@ void Navier2D::eval(double* o_nu, double* o_nuvol, double* o_re, double* o_div, 
     uy->backward();
     for (int mode = 1; mode <= 2; ++mode) {
       if ((mode == 1 && !o_re) || (mode == 2 && !o_ekin)) continue;
-      rt::dzero(red_.p, 8, stream);
       // averaging weights of `field` (unscaled coords; the ratio dx/L is scale invariant)
       launch_wsum(ux->v.d(), uy->v.d(), ux->v.ld, nx, ny, F.weights_x(), F.weights_y(), mode, red_.as<double>(), stream);
       double r = 0.0;

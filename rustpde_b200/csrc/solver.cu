@@ -126,11 +126,11 @@ Solver2::Solver2(int kind_, const Space2& sp_, double cx, double cy, double alph
     rt::sync(0);
   }
   {
-    const std::vector<double>& l0 = lam_export_.empty() ? ts.lam : lam_export_;  // reference order: descending
-    if (kind == SOLVER_POISSON && std::fabs(l0[0]) < 1e-10) {                   // poisson.rs:80-83
+    // lam_export_: reference order (descending), before the singularity shift -- what export_eig() returns and
+    // what *_create_with_eig expects, so the round trip never shifts twice
+    if (lam_export_.empty()) lam_export_ = ts.lam;
+    if (kind == SOLVER_POISSON && std::fabs(lam_export_[0]) < 1e-10)  // poisson.rs:80-83
       for (auto& l : ts.lam) l -= 1e-10;
-      for (auto& l : lam_export_) l -= 1e-10;
-    }
   }
   Diags Ay = combine(b1.A, sign * cy, b1.A, 0.0);
   build_fdma_mode_dev(Ay, b1.C, ts.lam, al, ts.mode);
@@ -138,8 +138,7 @@ Solver2::Solver2(int kind_, const Space2& sp_, double cx, double cy, double alph
 
 void Solver2::export_eig(double* lam, double* q, double* p) const {
   if (kind == SOLVER_HHOLTZ_ADI) throw Error(RP_ERR_INVALID, "HholtzAdi has no eigen set-up data");
-  const std::vector<double>& l0 = lam_export_.empty() ? ts.lam : lam_export_;
-  if (lam) std::copy(l0.begin(), l0.end(), lam);
+  if (lam) std::copy(lam_export_.begin(), lam_export_.end(), lam);
   if (!ts.x_diag) {
     if (q) std::copy(hq_.begin(), hq_.end(), q);
     if (p) std::copy(hp_.begin(), hp_.end(), p);

@@ -25,6 +25,37 @@ def rel(a, b):
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
 
 
+def band_rel(a, b, nb=4):
+    """Banded error metric: the array is cut into nb x nb blocks of mode bands (spectral coefficients span 15 decades,
+    so a global max-norm cannot see the high modes); per band max|a-b| / max(max|b| of the band, floor) with
+    floor = 1e-13 * global max|b| (bands that hold only rounding noise are compared against the noise level, not
+    against themselves).  Returns the worst band."""
+    a, b = np.asarray(a), np.asarray(b)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    gmax = max(np.abs(b).max(), 1e-300)
+    worst = 0.0
+    r_edges = np.linspace(0, a.shape[0], nb + 1).astype(int)
+    c_edges = np.linspace(0, a.shape[1], nb + 1).astype(int) if a.ndim > 1 else np.array([0, 1])
+    for i in range(nb):
+        for j in range(len(c_edges) - 1):
+            sl = (slice(r_edges[i], r_edges[i + 1]), slice(c_edges[j], c_edges[j + 1])) if a.ndim > 1 else (slice(r_edges[i], r_edges[i + 1]),)
+            bb = b[sl]
+            if bb.size == 0:
+                continue
+            ref = max(np.abs(bb).max(), 1e-13 * gmax)
+            worst = max(worst, float(np.abs(a[sl] - bb).max() / ref))
+    return worst
+
+
+def oracle_lam_unshifted(ts):
+    """Eigenvalues of the oracle's FdmaTensor before the Poisson singularity shift (poisson.rs:80-83): the C ABI takes
+    and returns unshifted eigenvalues (rustpde_b200.h, rp_solver_export_eig)."""
+    lam = ts.lam[0].copy()
+    if abs(lam[0] + 1e-10) < 1e-10:
+        lam = lam + 1e-10
+    return lam
+
+
 def smooth_field(x, y):
     """SURVEY 8d per-kernel input: sin(3x~+0.3) cos(2y~) + 0.1 x~ y~^2 on normalised coords."""
     xs = (x - x[0]) / (x[-1] - x[0])
@@ -85,11 +116,8 @@ def check_tensor_shared_eig(lib, which, kx, ky, nx, ny, c=(1.0, 0.8), alpha=2.0,
     f, of = make_fields(lib, kx, nx, ky, ny)
     if which == "poisson":
         osol = O.Poisson(of, c, banded=True)
-        lam = osol.solver.lam[0].copy()
-        # hand the device the pre-shift eigenvalues; it applies poisson.rs:80-83 itself
-        if abs(lam[0] + 1e-10) < 1e-10:
-            lam = lam + 1e-10
-        sol = R.Poisson(f, c, eig=(lam, osol.solver.bwd[0], osol.solver.fwd[0]))
+        # the device takes the pre-shift eigenvalues and applies poisson.rs:80-83 itself
+        sol = R.Poisson(f, c, eig=(oracle_lam_unshifted(osol.solver), osol.solver.bwd[0], osol.solver.fwd[0]))
     else:
         osol = O.Hholtz(of, c, alpha=alpha, banded=True)
         sol = R.Hholtz(f, c, alpha=alpha, eig=(osol.solver.lam[0], osol.solver.bwd[0], osol.solver.fwd[0]))
@@ -118,7 +146,8 @@ def check_tensor_own_eig(lib, which, kx, ky, nx, ny, c=(1.0, 0.8), alpha=2.0, se
     assert np.all(np.diff(lam) <= 0), "eigenvalues not sorted descending (utils.rs:80-94)"
     lam_ref = np.sort(osol.solver.lam[0])[::-1]
     assert np.abs(lam - lam_ref).max() <= 1e-6 * max(1.0, np.abs(lam_ref).max()), "eigenvalues differ from dgeev on the full matrix"
-    osol.solver.lam[0], osol.solver.bwd[0], osol.solver.fwd[0] = lam, q, p
+    lam_used = lam - 1e-10 if (which == "poisson" and abs(lam[0]) < 1e-10) else lam  # poisson.rs:80-83
+    osol.solver.lam[0], osol.solver.bwd[0], osol.solver.fwd[0] = lam_used, q, p
     b = rng.uniform(-1, 1, (nx, ny))
     ref = osol.solve(b)
     e1 = rel(sol.solve(b), ref)
@@ -145,16 +174,12 @@ def make_navier_pair(lib, periodic, nx, ny, ra, pr, dt, aspect=1.0, adiabatic=Tr
         n = R.Navier2D.new_periodic(nx, ny, ra, pr, dt, aspect, lib=lib)
     elif own_eig:
         n = R.Navier2D.new(nx, ny, ra, pr, dt, aspect, adiabatic, lib=lib)
-        lam, q, p = n.export_eig()  # lam already carries the poisson.rs:80-83 shift
-        o = O.Navier2D.new(nx, ny, ra, pr, dt, aspect, adiabatic, banded=True, eig_data=(lam, q, p))
-        o.solver[3].solver.lam[0] = lam.copy()
+        # exported eigenvalues are unshifted; the oracle's Poisson applies poisson.rs:80-83 itself, like the device
+        o = O.Navier2D.new(nx, ny, ra, pr, dt, aspect, adiabatic, banded=True, eig_data=n.export_eig())
     else:
         o = O.Navier2D.new(nx, ny, ra, pr, dt, aspect, adiabatic, banded=True)
         ts = o.solver[3].solver
-        lam = ts.lam[0].copy()
-        if abs(lam[0] + 1e-10) < 1e-10:
-            lam = lam + 1e-10
-        n = R.Navier2D.new(nx, ny, ra, pr, dt, aspect, adiabatic, eig=(lam, ts.bwd[0], ts.fwd[0]), lib=lib)
+        n = R.Navier2D.new(nx, ny, ra, pr, dt, aspect, adiabatic, eig=(oracle_lam_unshifted(ts), ts.bwd[0], ts.fwd[0]), lib=lib)
     if ics:
         for x in (n, o):
             x.set_velocity(0.2, 1.0, 1.0)
@@ -162,12 +187,13 @@ def make_navier_pair(lib, periodic, nx, ny, ra, pr, dt, aspect=1.0, adiabatic=Tr
     return n, o
 
 
-def navier_field_errors(n, o):
+def navier_field_errors(n, o, metric=None):
+    metric = metric or rel
     return {
-        "temp": rel(n.temp.vhat, o.temp.vhat),
-        "ux": rel(n.ux.vhat, o.ux.vhat),
-        "uy": rel(n.uy.vhat, o.uy.vhat),
-        "pres": rel(n.pres[0].vhat, o.pres[0].vhat) if np.abs(o.pres[0].vhat).max() > 0 else 0.0,
+        "temp": metric(n.temp.vhat, o.temp.vhat),
+        "ux": metric(n.ux.vhat, o.ux.vhat),
+        "uy": metric(n.uy.vhat, o.uy.vhat),
+        "pres": metric(n.pres[0].vhat, o.pres[0].vhat) if np.abs(o.pres[0].vhat).max() > 0 else 0.0,
     }
 
 
@@ -229,4 +255,67 @@ def check_staged_upload(lib, periodic, nx, ny, steps=3):
     for oa, ob in zip(outs_a, outs_b):
         for x, y in zip(oa, ob):
             assert np.array_equal(x, y)
+    return True
+
+
+def check_host_api_additions(lib, periodic, nx, ny):
+    """Round-2 ABI additions against their blocking counterparts: profile() after an outside pressure write ==
+    update(), eig export/import round trip, fetch_state == vhat, div_async/poll == div_norm,
+    vhat row slabs, device-side average_axis versus the oracle."""
+    import rustpde_b200 as R
+
+    def make(eig=None):
+        n = (R.Navier2D.new_periodic(nx, ny, 1e5, 1.0, 0.01, 1.0, lib=lib) if periodic
+             else R.Navier2D.new(nx, ny, 1e5, 1.0, 0.01, 1.0, True, eig=eig, lib=lib))
+        n.set_velocity(0.2, 1.0, 1.0)
+        n.set_temperature(0.2, 1.0, 1.0)
+        return n
+
+    a = make()
+    a.update(3)
+    state = [np.array(f.vhat) for f in (a.temp, a.ux, a.uy, a.pres[0])]
+    # 1. profile(k) must advance exactly like update(k), also right after the pressure was written from outside
+    b, c = make(), make()
+    for n in (b, c):
+        n.temp.vhat, n.ux.vhat, n.uy.vhat = state[0], state[1], state[2]
+        n.pres[0].vhat = state[3]
+    b.update(2)
+    c.profile(2)
+    for fb, fc in ((b.temp, c.temp), (b.ux, c.ux), (b.uy, c.uy), (b.pres[0], c.pres[0])):
+        assert np.array_equal(fb.vhat, fc.vhat)
+    assert abs(b.time - c.time) < 1e-14
+    # 2. create_with_eig(export_eig()) reproduces the solver bit for bit (no double shift)
+    if not periodic:
+        d = make(eig=a.export_eig())
+        d.update(3)
+        for fa, fd in ((a.temp, d.temp), (a.ux, d.ux), (a.uy, d.uy), (a.pres[0], d.pres[0])):
+            assert np.array_equal(fa.vhat, fd.vhat)
+        lam = a.export_eig()[0]
+        assert np.array_equal(lam, d.export_eig()[0])
+    # 3. fetch_state (async, snapshot semantics): queued before further updates, must hold the state at the call
+    bufs = [np.zeros_like(s) for s in state]
+    a.fetch_state(*bufs)
+    a.update(2)
+    a.fetch_wait()
+    for s, g in zip(state, bufs):
+        assert np.array_equal(s, g)
+    # 4. div_async / div_poll
+    dn = b.div_norm()
+    b.div_async()
+    got = b.div_poll(wait=True)
+    assert got == dn, (got, dn)
+    assert not b.exit_async()
+    # 5. row slabs of vhat
+    full = np.array(b.ux.vhat)
+    r0, nr = 1, min(5, full.shape[0] - 1)
+    assert np.array_equal(b.ux.vhat_rows(r0, nr), full[r0:r0 + nr])
+    b.ux.set_vhat_rows(r0, 2.0 * full[r0:r0 + nr])
+    full[r0:r0 + nr] *= 2.0
+    assert np.array_equal(np.array(b.ux.vhat), full)
+    # 6. device-side average_axis(0) and average() versus the oracle (average.rs:25-57)
+    f, of = make_fields(lib, "fourier_r2c" if periodic else "cheb_dirichlet", nx, "cheb_dirichlet", ny)
+    v = smooth_field(of.x[0][:nx], of.x[1])
+    f.v, of.v = v, v.copy()
+    assert rel(f.average_axis(0), of.average_axis(0)) <= 1e-13
+    assert abs(f.average() - of.average()) <= 1e-13 * max(1.0, abs(of.average()))
     return True

@@ -199,3 +199,21 @@ def test_commit_without_stage_fails(emu):
     n = R.Navier2D.new(16, 17, 1e4, 1.0, 0.01, 1.0, True, lib=emu)
     with pytest.raises(R.RustpdeError):
         n.commit_staged()
+
+
+@pytest.mark.parametrize("periodic,nx,ny", [(False, 24, 33), (True, 32, 33), (False, 20, 20)])
+def test_host_api_additions(emu, periodic, nx, ny):
+    """profile() == update() after an outside pressure write, eig round trip, fetch_state, div_async, row slabs,
+    device-side averages (deterministic two-stage reductions)."""
+    assert pc.check_host_api_additions(emu, periodic, nx, ny)
+
+
+def test_band_rel_metric():
+    """The banded metric must see an error confined to the small high modes that the global max-norm misses."""
+    rng = np.random.default_rng(0)
+    b = rng.uniform(-1, 1, (64, 64)) * np.logspace(0, -12, 64)[None, :]
+    a = b.copy()
+    a[:, 48:] *= 1.5
+    assert pc.rel(a, b) < 1e-9
+    assert pc.band_rel(a, b) > 0.1
+    assert pc.band_rel(b, b) == 0.0
