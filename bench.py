@@ -5,22 +5,36 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 Our arm: one process per GPU.  A "step" is one Navier2D.update() (navier.rs:737-765) on
-synthetic initial fields (set_velocity/set_temperature, no RNG).  At N=1 the workload is the
-configuration the metric is quoted on that fits one GPU: confined 2048x2049, Ra=1e9.  For
-N>1 the ranks run independent replicas of that workload ("replicas only", weak scaling --
-DESIGN.md section 6); `--workload periodic8192` (or any periodic workload) at N>1 runs ONE
-problem slab-decomposed over the Fourier modes instead (strong scaling, fused NVLink
-transposes).  Timing: W>=3 warm-up steps, then exactly K steps between CUDA events on the
-launching stream with a barrier + synchronize on both sides, max over ranks.  The working
-set (>2 GB) is far larger than L2, so no L2 flush is needed between steps.  `e2e` is the
-same metric through the C ABI with HOST buffers: every step uploads the whole state from
-pinned host memory (double-buffered on a copy stream, rp_navier_stage_state) and reads
-|div|_2 back.
+synthetic initial fields (set_velocity/set_temperature, no RNG).
+
+* N = 1: the configuration the metric is quoted on that fits one GPU -- confined 2048x2049,
+  Ra=1e9 (BASELINE.json configs[3]).
+* N > 1: BASELINE.json configs[4], `new_periodic` 8192x8193, ONE problem slab-decomposed over
+  the Fourier modes kx: strong scaling, transposes fused into the kernels over
+  NVLink peer memory.  In the same run every rank first advances the SAME problem on the
+  single-GPU CUDA-graph path: that gives `speedup_vs_1gpu` (so the curve does not depend on a
+  different workload at N=1) and the on-box parity check -- after `parity_steps` steps the
+  rows a rank owns must equal the single-GPU result to <= 1e-10 relative (max and banded).
+  `--parallel replicas` runs N independent copies of the N=1 workload instead (weak scaling).
+* `--workload hholtz1024`: BASELINE.json configs[1], 64 back-to-back `Hholtz::solve` calls of
+  examples/hholtz_2d.rs scaled to 1024x1025 (one step = one solve).
+
+Timing: W>=3 warm-up steps, then exactly K steps between CUDA events on the launching stream
+with a barrier + synchronize on both sides, max over ranks.  The working set (>2 GB) is far
+larger than L2, so no L2 flush is needed between steps.
+
+`e2e` (streaming) is the same metric through the C ABI with HOST buffers: every step uploads
+the whole state from pinned host memory (double-buffered on a copy stream,
+rp_navier_stage_state), runs update(1), downloads the whole new state to pinned host memory on
+a second copy stream (rp_navier_fetch_state) and reads |div|_2 back (what Integrate::exit
+needs, lib.rs:182).  `e2e_resident` is what a user of integrate() sees when the state stays on
+the device: update(1) + exit() per step, 8 bytes back.
 
 Reference arm (--impl reference): the reference is pure Rust and cannot be built in this
-image, so this times the CPU restatement (oracle/, numpy/scipy with all host threads) of
-the same update() on the same configuration; each requested step is one full update, and
-the number of steps actually run is bounded so the arm ends within a few minutes.
+image, so this times the CPU restatement of the same update() on the same configuration (the
+C++ lane-parallel twin oracle/_build/liboracle_cpu.so when it was built, else the numpy/scipy
+restatement), OPENBLAS_NUM_THREADS=1 as the reference's README asks, thread count stated; the
+number of steps actually run is bounded so the arm ends within a few minutes.
 """
 import argparse
 import json
@@ -29,6 +43,10 @@ import subprocess
 import sys
 import threading
 import time
+
+# the reference asks for single-threaded BLAS beside its own lane parallelism (README.md:10-16, src/lib.rs:8-14);
+# must be set before numpy/scipy load OpenBLAS
+os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -41,8 +59,11 @@ WORKLOADS = {
     "periodic2048": (True, 2048, 2049, 1e9, 1.0, 1e-4, 1.0, True, "Navier2D::new_periodic 2048x2049 Ra=1e9 Pr=1 dt=1e-4"),
     "periodic8192": (True, 8192, 8193, 1e10, 1.0, 2e-5, 1.0, True, "Navier2D::new_periodic 8192x8193 Ra=1e10 Pr=1 dt=2e-5"),
     "confined1024": (False, 1024, 1025, 1e8, 1.0, 2e-4, 1.0, True, "Navier2D::new confined 1024x1025 Ra=1e8 Pr=1 dt=2e-4 adiabatic"),
+    "hholtz1024": (False, 1024, 1025, 0.0, 0.0, 0.0, 1.0, True, "Hholtz::new2 cd x cd 1024x1025 c=[1,1] alpha=10 (examples/hholtz_2d.rs), 64 batched solves"),
 }
 METRIC = "Navier2D time steps/sec at Nx(N+1) (device-timed)"
+DATA = "synthetic (set_velocity(0.2,1,1)+set_temperature(0.2,1,1), no RNG)"
+NVLINK_PEAK_GBS = 900.0  # per direction per GPU (NVLink 5, B200_PROFILING.md)
 
 
 def measured_peaks():
@@ -54,6 +75,14 @@ def measured_peaks():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def config_of(args, wl, world, **extra):
+    """Same keys in both arms (the driver compares the dicts)."""
+    cfg = {"workload": wl[8], "workload_name": args.workload, "grid": [wl[1], wl[2]],
+           "parallelism": extra.pop("parallelism", "1 GPU"), "l2": "working set >> 126 MB L2, no flush needed"}
+    cfg.update(extra)
+    return cfg
 
 
 class ClockSampler:
@@ -69,10 +98,14 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
+            # wait for the first sample so that short timed regions are covered too
+            t0 = time.time()
+            while not self.rows and time.time() - t0 < 2.0:
+                time.sleep(0.01)
         except Exception:
             self.proc = None
 
@@ -83,7 +116,7 @@ class ClockSampler:
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.12)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -108,6 +141,22 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+# ------------------------------------------------------------------------------------------------
+# CPU restatement (reference arm and cpu_baseline leg)
+# ------------------------------------------------------------------------------------------------
+def cpu_twin():
+    """The C++ lane-parallel restatement (oracle/cpu_twin), if it was built; None otherwise."""
+    try:
+        from oracle import cpu_twin as T
+        return T if T.available() else None
+    except Exception:
+        return None
+
+
+def host_threads():
+    return os.cpu_count() or 1
+
+
 def make_oracle(wl, eig=None):
     import oracle as O
     periodic, nx, ny, ra, pr, dt, aspect, adiabatic, _ = wl
@@ -120,12 +169,22 @@ def make_oracle(wl, eig=None):
     return o
 
 
-def time_oracle(wl, want_steps, warmup, budget_s, eig=None):
-    """Time the CPU restatement; returns (steps_per_s, steps_run, description)."""
-    o = make_oracle(wl, eig)
+def time_cpu(wl, want_steps, warmup, budget_s, eig=None):
+    """Time the CPU restatement of update(); returns (steps_per_s, description, threads, kind)."""
+    T = cpu_twin()
+    if T is not None:
+        o = T.make_navier(wl, eig)
+        kind_desc = "C++ lane-parallel restatement (oracle/cpu_twin, %d threads, OPENBLAS_NUM_THREADS=%s)" % (T.threads(), os.environ.get("OPENBLAS_NUM_THREADS"))
+        threads = T.threads()
+    else:
+        o = make_oracle(wl, eig)
+        kind_desc = "numpy/scipy restatement (scipy.fft workers = all cores, OPENBLAS_NUM_THREADS=%s)" % os.environ.get("OPENBLAS_NUM_THREADS")
+        threads = host_threads()
     t0 = time.perf_counter()
     o.update()
     t1 = time.perf_counter() - t0
+    if t1 > 0.5 * budget_s:  # one step already eats the budget: report it (first-touch cost included, said so)
+        return 1.0 / t1, "1 full update() step (the first call, page-touch cost included) of the %s (of %d requested)" % (kind_desc, want_steps), threads
     nwarm = max(0, min(warmup - 1, int(0.15 * budget_s / max(t1, 1e-9))))
     for _ in range(nwarm):
         o.update()
@@ -134,23 +193,286 @@ def time_oracle(wl, want_steps, warmup, budget_s, eig=None):
     for _ in range(nrun):
         o.update()
     dt = time.perf_counter() - t0
-    return nrun / dt, nrun, "%d full update() steps of the numpy/scipy restatement (of %d requested; %d warm-up)" % (nrun, want_steps, nwarm + 1)
+    return nrun / dt, "%d full update() steps of the %s (of %d requested; %d warm-up)" % (nrun, kind_desc, want_steps, nwarm + 1), threads
 
 
-def run_reference(args, wl, rank):
+def time_cpu_hholtz(nsolves, budget_s):
+    import numpy as np
+    import oracle as O
+    nx, ny = 1024, 1025
+    f = O.Field2(O.Space2(O.cheb_dirichlet(nx), O.cheb_dirichlet(ny)))
+    x, y = f.x
+    f.v = np.cos(np.pi / 2 * x)[:, None] * np.cos(np.pi / 2 * y)[None, :]
+    f.forward()
+    h = O.Hholtz.new2(f, [1.0, 1.0], 10.0, banded=True)
+    rhs = f.to_ortho()
+    t0 = time.perf_counter()
+    h.solve(rhs)
+    t1 = time.perf_counter() - t0
+    nrun = max(1, min(nsolves, int(budget_s / max(t1, 1e-9))))
+    t0 = time.perf_counter()
+    for _ in range(nrun):
+        h.solve(rhs)
+    dt = time.perf_counter() - t0
+    return nrun / dt, "%d Hholtz::solve calls of the numpy/scipy restatement (of %d requested)" % (nrun, nsolves), host_threads()
+
+
+def run_reference(args, wl, rank, world):
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
-    val, nrun, sample = time_oracle(wl, args.steps, args.warmup, budget_s=150.0)
+    if args.workload == "hholtz1024":
+        val, sample, threads = time_cpu_hholtz(args.steps, 120.0)
+    else:
+        val, sample, threads = time_cpu(wl, args.steps, args.warmup, budget_s=150.0)
+    slab = wl[0] and world > 1 and args.parallel != "replicas"
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": "steps/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 / val, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic (set_velocity(0.2,1,1)+set_temperature(0.2,1,1), no RNG)",
-        "config": {"workload": wl[8], "note": "CPU restatement of rustpde (oracle/), not the rustpde binary: no Rust toolchain in this image"},
-        "cpu_baseline": {"value": val, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "warmup": args.warmup, "ms_per_step": 1e3 / val, "higher_is_better": True, "scaling": "strong" if slab else "weak",
+        "vs_baseline": None, "dtype": "f64", "data": DATA,
+        "config": config_of(args, wl, world, parallelism="host CPU, %d threads" % threads,
+                            note="CPU restatement of rustpde (oracle/), not the rustpde binary: no Rust toolchain in this image"),
+        "cpu_baseline": {"value": val, "unit": "steps/s", "cores": threads, "kind": "port", "sample": sample,
+                         "openblas_num_threads": os.environ.get("OPENBLAS_NUM_THREADS")},
         "e2e": {"value": val, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def dgemm_peak(torch):
+    """cuBLAS DGEMM 4096^3, TFLOP/s (the FP64 tensor denominator, measured in this run)."""
+    a = torch.randn(4096, 4096, device="cuda", dtype=torch.float64)
+    b = torch.randn(4096, 4096, device="cuda", dtype=torch.float64)
+    torch.matmul(a, b)
+    torch.cuda.synchronize()
+    best = 1e9
+    for _ in range(3):
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        torch.matmul(a, b)
+        s1.record()
+        torch.cuda.synchronize()
+        best = min(best, s0.elapsed_time(s1))
+    return 2 * 4096 ** 3 / (best * 1e-3) / 1e12
+
+
+def pinned_state(torch, np, fields, rows=None):
+    """Page-locked host copies of the vhat arrays (or of the row slab `rows` = (r0, nr))."""
+    out = []
+    for f in fields:
+        a = f.vhat if rows is None else f.vhat_rows(*rows)
+        t = torch.empty(a.view(np.float64).size, dtype=torch.float64).pin_memory()
+        t.numpy()[:] = a.view(np.float64).reshape(-1)
+        out.append(t)
+    return out
+
+
+def run_slab(args, wl, rank, world, local_rank, torch, dist, lib, R, _ffi, np):
+    """Strong scaling of ONE periodic problem, slab-decomposed over kx."""
+    from rustpde_b200.slab import Navier2DSlab
+    periodic, nx, ny, ra, pr, dt, aspect, adiabatic, desc = wl
+    t_setup = time.perf_counter()
+    nav = R.Navier2D.new_periodic(nx, ny, ra, pr, dt, aspect, lib=lib)
+    slab = Navier2DSlab(nav, transport=args.transport)
+    t_setup = time.perf_counter() - t_setup
+    W = max(3, args.warmup)
+    k0, mkl = slab.k0, slab.mkl
+    fields = lambda: (nav.temp, nav.ux, nav.uy, nav.pres[0])
+
+    def reset():
+        nav.set_velocity(0.2, 1.0, 1.0)
+        nav.set_temperature(0.2, 1.0, 1.0)
+        z = np.zeros(nav.pres[0].shape_spectral, dtype=np.complex128)
+        nav.pres[0].vhat = z
+        nav.pres[1].vhat = np.zeros(nav.pres[1].shape_spectral, dtype=np.complex128)
+        nav.reset_time()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed_ms(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn(steps)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if dist is not None:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    # ---- 1. the same problem on ONE GPU (every rank, independently): parity reference + 1-GPU time
+    pk = args.parity_steps
+    reset()
+    nav.update(pk)
+    nav.sync()
+    ref_rows = [f.vhat_rows(k0, mkl) for f in fields()]
+    n1 = max(3, min(args.steps, 10))
+    nav.update(2)
+    ms_1gpu = timed_ms(nav.update, n1) / n1
+    # ---- 2. parity of the slab path: own rows after pk steps versus the single-GPU rows
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from parity_cases import band_rel, rel
+    reset()
+    slab.update(pk)
+    slab.sync()
+    errs = []
+    for f, r in zip(fields(), ref_rows):
+        mine = f.vhat_rows(k0, mkl)
+        scale = max(np.abs(r).max(), 1e-300)
+        errs.append((float(np.abs(mine - r).max()), float(scale), band_rel(mine, r) if np.abs(r).max() > 0 else 0.0))
+    # global max-norm relative error: max over ranks of |a-b|, over max over ranks of |b|
+    t = torch.tensor([[e[0] for e in errs], [e[1] for e in errs], [e[2] for e in errs]], device="cuda", dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    t = t.cpu().numpy()
+    rel_err = float((t[0] / t[1]).max())
+    band_err = float(t[2].max())
+    parity = {"steps": pk, "max_rel_err": rel_err, "max_band_rel_err": band_err, "tol": 1e-10, "band_tol": 1e-8,
+              "against": "single-GPU CUDA-graph path of the same problem, same initial state, rows owned by each rank",
+              "ok": bool(rel_err <= 1e-10 and band_err <= 1e-8)}
+    del ref_rows
+    # ---- 3. timed slab steps
+    slab.update(W)
+    slab.sync()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms = timed_ms(slab.update, args.steps)
+    clocks = sampler.stop()
+    steps_per_s = args.steps / (ms * 1e-3)
+    # ---- 4. end to end with HOST buffers: each rank uploads / downloads the rows it owns
+    pin_in = pinned_state(torch, np, fields(), rows=(k0, mkl))
+    pin_out = [torch.empty_like(p).pin_memory() for p in pin_in]
+    handles = [f._h for f in fields()]
+    ne2e = max(3, min(args.steps, 10))
+
+    def e2e_step():
+        for h, p in zip(handles, pin_in):
+            lib.call("rp_field_upload_vhat_rows", h, k0, mkl, _ffi.C.cast(p.data_ptr(), _ffi.c_double_p), p.numel())
+        slab.update(1)
+        for h, p in zip(handles, pin_out):
+            lib.call("rp_field_download_vhat_rows", h, k0, mkl, _ffi.C.cast(p.data_ptr(), _ffi.c_double_p), p.numel())
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(ne2e):
+        e2e_step()
+    barrier()
+    te = time.perf_counter() - t0
+    if dist is not None:
+        tt = torch.tensor([te], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        te = float(tt.item())
+    io_bytes = sum(p.numel() * 8 for p in pin_in)
+    e2e = {"value": ne2e / te, "unit": "steps/s", "h2d_bytes_per_step": io_bytes * world, "d2h_bytes_per_step": io_bytes * world,
+           "steps": ne2e, "note": "per step and rank: the kx rows it owns of temp/ux/uy/pres vhat from pinned host memory "
+                                  "(rp_field_upload_vhat_rows), one slab update, the same rows back (rp_field_download_vhat_rows); "
+                                  "blocking copies, bytes summed over the ranks"}
+    hbm_peak, src = measured_peaks()
+    contract_bytes = 408.0 * nx * ny  # SURVEY 8(d): periodic step = 51 field sweeps of 8 Np bytes
+    ach = contract_bytes / world / (ms / args.steps * 1e-3) / 1e9
+    nv = slab.bytes_exchanged_per_step / (ms / args.steps * 1e-3) / 1e9
+    roof = {"bound": "hbm", "kernel": "whole slab step (per rank)", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+            "traffic": None, "peak_source": src, "algorithmic_bytes_per_step_per_rank": contract_bytes / world,
+            "nvlink": {"egress_bytes_per_rank_per_step": slab.bytes_exchanged_per_step, "achieved_GBps": nv, "peak_GBps": NVLINK_PEAK_GBS,
+                       "frac": nv / NVLINK_PEAK_GBS, "note": "egress / whole step time: the transposes are fused into the producing kernels"},
+            "limiter": "per-rank kernels at 1/N of the lanes (latency-bound pass kernels, DESIGN.md 6) plus %d cross-rank fences per step" % slab.fences_per_step}
+    div = None
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": steps_per_s, "unit": "steps/s", "n_gpus": world, "steps": args.steps, "warmup": W,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": DATA,
+            "config": config_of(args, wl, world, parallelism="kx slabs x%d, 9 transposes per step, %s" % (
+                world, "fused into the kernels over NVLink peer memory (CUDA IPC)" if slab.transport == "p2p" else "NCCL all_to_all"),
+                cuda_graph=False, setup_s=round(t_setup, 2), comm_nranks=world, transport=slab.transport),
+            "speedup_vs_1gpu": ms_1gpu / (ms / args.steps), "ms_per_step_1gpu": ms_1gpu,
+            "steps_per_s_1gpu": 1e3 / ms_1gpu, "slab_parity": parity,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": slab.launches_per_step * args.steps, "roofline": roof, "cpu_baseline": None,
+        }
+        print(json.dumps(line), flush=True)
+    slab.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    if not parity["ok"]:
+        raise SystemExit("slab parity check failed: %r" % (parity,))
+
+
+def run_hholtz(args, wl, rank, world, local_rank, torch, lib, R, _ffi, np):
+    """BASELINE.json configs[1]: batched Hholtz solves (examples/hholtz_2d.rs:7-31 at 1024x1025)."""
+    import math
+    nx, ny = wl[1], wl[2]
+    f = R.Field2(R.Space2(R.cheb_dirichlet(nx), R.cheb_dirichlet(ny)), lib=lib)
+    x, y = f.x
+    n = math.pi / 2.0
+    alpha = 1e-1
+    v = np.cos(n * x)[:, None] * np.cos(n * y)[None, :]
+    f.v = v
+    f.forward()
+    t_setup = time.perf_counter()
+    h = R.Hholtz.new2(f, [1.0, 1.0], 1.0 / alpha)
+    t_setup = time.perf_counter() - t_setup
+    rhs = f.to_ortho()
+    sol = h.solve(rhs)          # also stages rhs on the device
+    f.vhat = sol
+    f.backward()
+    err = float(np.abs(f.v - alpha / (1.0 + alpha * n * n * 2.0) * v).max())
+    W = max(3, args.warmup)
+    K = args.steps
+    h.solve_resident(W)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    h.solve_resident(K)
+    e1.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    # e2e: host rhs in, host solution out, per solve
+    ne = max(3, min(K, 16))
+    h.solve(rhs)
+    t0 = time.perf_counter()
+    for _ in range(ne):
+        h.solve(rhs)
+    te = time.perf_counter() - t0
+    m = nx - 2
+    flops = 2 * 2.0 * m * m * (ny - 2)  # SURVEY 8(d): two GEMMs, unsplit count ("effective")
+    peak = dgemm_peak(torch)
+    ach = flops / (ms / K * 1e-3) / 1e12
+    info = h.path_info()
+    roof = {"bound": "tensor", "kernel": "fast-diagonalisation GEMM pair (dgemm_dmma_kernel)", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+            "frac": ach / peak, "traffic": None, "peak_source": "cuBLAS DGEMM 4096^3 measured in this run (f64)",
+            "note": "effective rate on the unsplit flop count 4 M^2 Ny over the whole solve; the parity-split GEMMs execute half of it",
+            "executed_TFLOPs": ach / (2.0 if info.get("split_gemm") else 1.0)}
+    cpu = None
+    if not args.no_cpu_baseline:
+        val, sample, threads = time_cpu_hholtz(8, 15.0)
+        cpu = {"value": val, "unit": "steps/s", "cores": threads, "kind": "port", "sample": sample}
+    line = {
+        "metric": METRIC, "value": K / (ms * 1e-3), "unit": "steps/s", "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": ms / K,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic (rhs = to_ortho(forward(cos(pi x/2) cos(pi y/2))), examples/hholtz_2d.rs)",
+        "config": config_of(args, wl, world, step="one Hholtz::solve (device-resident rhs)", setup_s=round(t_setup, 2),
+                            analytic_max_abs_err=err, kernel_path=info),
+        "clocks": clocks,
+        "e2e": {"value": ne / te, "unit": "steps/s", "h2d_bytes_per_step": rhs.size * 8, "d2h_bytes_per_step": sol.size * 8, "steps": ne,
+                "note": "rp_solver_solve with host rhs and host solution (pageable numpy buffers)"},
+        "gpu_launches": info.get("launches", 4) * K, "roofline": roof, "cpu_baseline": cpu,
+    }
+    assert err < 1e-3, err  # the reference's own tolerance for this example
     print(json.dumps(line), flush=True)
 
 
@@ -169,20 +491,24 @@ def run_ours(args, wl, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     lib = _ffi.product_lib(local_rank)
     periodic, nx, ny, ra, pr, dt, aspect, adiabatic, desc = wl
+    if args.workload == "hholtz1024":
+        if rank == 0:
+            run_hholtz(args, wl, rank, world, local_rank, torch, lib, R, _ffi, np)
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+    if periodic and (world > 1 or args.parallel == "slab") and args.parallel != "replicas":
+        return run_slab(args, wl, rank, world, local_rank, torch, dist, lib, R, _ffi, np)
+
     t_setup = time.perf_counter()
     nav = R.Navier2D.new_periodic(nx, ny, ra, pr, dt, aspect, lib=lib) if periodic else R.Navier2D.new(nx, ny, ra, pr, dt, aspect, adiabatic, lib=lib)
     nav.set_velocity(0.2, 1.0, 1.0)
     nav.set_temperature(0.2, 1.0, 1.0)
     t_setup = time.perf_counter() - t_setup
     W = max(3, args.warmup)
-    slab = None
-    if periodic and (world > 1 or args.parallel == "slab") and args.parallel != "replicas":
-        # strong scaling: ONE problem, slab-decomposed over the Fourier modes kx, NCCL all-to-all transposes
-        from rustpde_b200.slab import Navier2DSlab
-        slab = Navier2DSlab(nav, transport=args.transport)
-    stepper = slab if slab is not None else nav
-    stepper.update(W)
-    stepper.sync()
+    nav.update(W)
+    nav.sync()
 
     def barrier():
         torch.cuda.synchronize()
@@ -195,7 +521,7 @@ def run_ours(args, wl, rank, world, local_rank):
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    stepper.update(args.steps)
+    nav.update(args.steps)
     e1.record()
     barrier()
     clocks = sampler.stop()
@@ -204,62 +530,53 @@ def run_ours(args, wl, rank, world, local_rank):
         t = torch.tensor([ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    steps_per_s = (1 if slab is not None else world) * args.steps / (ms * 1e-3)
-    launches = nav.launches_per_step() if slab is None else 9  # our kernels per slab step (+ torch pack copies, NCCL)
-    if slab is not None:
-        slab.gather_state()
+    steps_per_s = world * args.steps / (ms * 1e-3)
+    launches = nav.launches_per_step()
     div = nav.div_norm()
-    if slab is not None:
-        if rank == 0:
-            line = {
-                "metric": METRIC, "value": steps_per_s, "unit": "steps/s", "n_gpus": world, "steps": args.steps, "warmup": W,
-                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-                "data": "synthetic (set_velocity(0.2,1,1)+set_temperature(0.2,1,1), no RNG)",
-                "config": {"workload": desc, "parallelism": "kx slabs x%d, 9 transposes per step, %s" % (world, "fused into the kernels over NVLink peer memory (CUDA IPC)" if slab.transport == "p2p" else "NCCL all_to_all"),
-                           "l2": "working set >> 126 MB L2, no flush needed", "cuda_graph": False, "setup_s": round(t_setup, 2),
-                           "div_norm_after": div, "nvlink_egress_bytes_per_rank_per_step": slab.bytes_exchanged_per_step},
-                "clocks": clocks, "e2e": None, "gpu_launches": launches * args.steps, "roofline": None, "cpu_baseline": None,
-            }
-            print(json.dumps(line), flush=True)
-        if dist is not None:
-            dist.destroy_process_group()
-        return
 
-    # ---- e2e: HOST buffers through the C ABI; H2D of the state + D2H of the step's metric inside the timed region
+    # ---- e2e: HOST buffers through the C ABI; H2D of the state, D2H of the new state and of |div| inside the timed region
     fields = [nav.temp, nav.ux, nav.uy, nav.pres[0]]
-    pinned = []
-    for f in fields:
-        a = f.vhat
-        t = torch.empty(a.view(np.float64).size, dtype=torch.float64).pin_memory()
-        t.numpy()[:] = a.view(np.float64).reshape(-1)
-        pinned.append(t)
+    pinned = pinned_state(torch, np, fields)
+    pinned_out = [torch.empty_like(p).pin_memory() for p in pinned]
     h2d = sum(t.numel() * 8 for t in pinned)
     ne2e = max(3, min(args.steps, 20))
+    ptrs = lambda ts: [(t.data_ptr(), t.numel()) for t in ts]
+
+    def stage():
+        nav.stage_state(*ptrs(pinned))
 
     def e2e_step_serial():
         for f, t in zip(fields, pinned):
             lib.call("rp_field_upload_vhat", f._h, _ffi.C.cast(t.data_ptr(), _ffi.c_double_p), t.numel())
         nav.update(1)
+        for f, t in zip(fields, pinned_out):
+            lib.call("rp_field_download_vhat", f._h, _ffi.C.cast(t.data_ptr(), _ffi.c_double_p), t.numel())
         return nav.div_norm()  # reference: integrate() calls exit() -> |div| on the host every step (lib.rs:182)
 
-    def stage():
-        nav.stage_state(*[(t.data_ptr(), t.numel()) for t in pinned])
-
-    def e2e_step():
-        # double-buffered: the state uploaded during the previous step is moved into place, update(1) is queued,
-        # the upload of the next step's inputs is queued on the copy stream (it overlaps this step's kernels),
-        # then |div|_2 of this step comes back to the host
+    def e2e_step_streaming():
+        # the state uploaded during the previous step is moved into place, update(1) is queued, the new state is
+        # snapshotted and downloaded on the second copy stream, the upload of the next step's inputs is queued on
+        # the first one (both overlap the kernels), then |div|_2 of this step comes back to the host
         nav.commit_staged()
         nav.update(1)
+        nav.fetch_state(*ptrs(pinned_out))
         stage()
         return nav.div_norm()
 
-    def timed(step):
+    def e2e_step_resident():
+        nav.update(1)
+        return nav.exit()
+
+    def timed(step, fin=None):
         step()
+        if fin:
+            fin()
         barrier()
         t0 = time.perf_counter()
         for _ in range(ne2e):
             step()
+        if fin:
+            fin()
         torch.cuda.synchronize()
         te = time.perf_counter() - t0
         if dist is not None:
@@ -270,19 +587,23 @@ def run_ours(args, wl, rank, world, local_rank):
 
     te_serial = timed(e2e_step_serial)
     stage()
-    te = timed(e2e_step)
-    e2e = {"value": world * ne2e / te, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
+    te = timed(e2e_step_streaming, nav.fetch_wait)
+    nav.commit_staged()
+    te_res = timed(e2e_step_resident)
+    e2e = {"value": world * ne2e / te, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": h2d + 8,
            "steps": ne2e, "serial_value": world * ne2e / te_serial,
-           "note": "per step: temp/ux/uy/pres vhat from pinned host memory (rp_navier_stage_state on a copy stream, "
-                   "overlapping the previous step's kernels; rp_navier_commit_staged), update(1), |div|_2 back to the host; "
-                   "serial_value = the same without the overlap (rp_field_upload_vhat x4, update, |div|)"}
+           "note": "streaming: per step temp/ux/uy/pres vhat from pinned host memory (rp_navier_stage_state on a copy stream, overlapping "
+                   "the previous step's kernels; rp_navier_commit_staged), update(1), the whole new state back to pinned host memory "
+                   "(rp_navier_fetch_state on a second copy stream) and |div|_2 to the host; serial_value = the same with blocking "
+                   "rp_field_upload_vhat / download_vhat x4"}
+    e2e_resident = {"value": world * ne2e / te_res, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 8, "steps": ne2e,
+                    "note": "state resident on the device: update(1) + exit() (|div|_2 to the host) per step -- what integrate() costs"}
 
     # ---- roofline of the dominant kernel (per-launch CUDA-event times of eagerly launched steps)
     roof = None
     if rank == 0:
         prof = nav.profile(5)
         tot = sum(o["ms"] for o in prof)
-        # group launches of the same kernel program
         groups = {}
         for o in prof:
             g = groups.setdefault(o["name"], {"ms": 0.0, "bytes": 0.0, "flops": 0.0, "n": 0})
@@ -290,8 +611,7 @@ def run_ours(args, wl, rank, world, local_rank):
             g["bytes"] += o["bytes"]
             g["flops"] += o["flops"]
             g["n"] += 1
-        top = max(groups.items(), key=lambda kv: kv[1]["ms"])
-        name, g = top
+        name, g = max(groups.items(), key=lambda kv: kv[1]["ms"])
         hbm_peak, src = measured_peaks()
         traffic = None
         tj = os.path.join(ROOT, "profiles", "traffic.json")
@@ -301,23 +621,10 @@ def run_ours(args, wl, rank, world, local_rank):
                 traffic = json.load(open(tj)).get(args.workload, {}).get(name)
             except Exception:
                 traffic = None
+        fp64_peak = dgemm_peak(torch)
         if g["flops"] > 0:
-            # FP64 tensor (DMMA) bound: measure the denominator here with cuBLAS DGEMM
-            a = torch.randn(4096, 4096, device="cuda", dtype=torch.float64)
-            bmat = torch.randn(4096, 4096, device="cuda", dtype=torch.float64)
-            torch.matmul(a, bmat)
-            torch.cuda.synchronize()
-            best = 1e9
-            for _ in range(3):
-                s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                s0.record()
-                torch.matmul(a, bmat)
-                s1.record()
-                torch.cuda.synchronize()
-                best = min(best, s0.elapsed_time(s1))
-            peak = 2 * 4096 ** 3 / (best * 1e-3) / 1e12
             ach = g["flops"] / (g["ms"] * 1e-3) / 1e12
-            roof = {"bound": "tensor", "kernel": name, "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+            roof = {"bound": "tensor", "kernel": name, "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach / fp64_peak,
                     "traffic": traffic, "peak_source": "cuBLAS DGEMM 4096^3 measured in this run (f64)",
                     "share_of_step": g["ms"] / tot}
         else:
@@ -325,32 +632,34 @@ def run_ours(args, wl, rank, world, local_rank):
             roof = {"bound": "hbm", "kernel": name, "launches_per_step": g["n"], "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
                     "frac": ach / hbm_peak, "traffic": traffic, "peak_source": src, "share_of_step": g["ms"] / tot,
                     "algorithmic_bytes_per_launch": g["bytes"] / g["n"]}
+        roof["fp64_dgemm_peak_TFLOPs"] = fp64_peak
+        step_bytes = sum(o["bytes"] for o in prof)
+        roof["whole_step"] = {"algorithmic_bytes": step_bytes, "GBps": step_bytes / (ms / args.steps * 1e-3) / 1e9,
+                              "frac_hbm": step_bytes / (ms / args.steps * 1e-3) / 1e9 / hbm_peak,
+                              "contract_bytes": (408.0 if periodic else 560.0) * nx * ny + (0 if periodic else 16.0 * (nx - 2) ** 2)}
         roof["per_kernel"] = [{"kernel": k, "launches": v["n"], "ms": round(v["ms"], 4),
                                "GBps": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1) if v["ms"] > 0 else None,
+                               "frac_hbm": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9 / hbm_peak, 4) if v["ms"] > 0 and v["flops"] == 0 else None,
                                "TFLOPs": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 2) if v["flops"] > 0 else None}
                               for k, v in sorted(groups.items(), key=lambda kv: -kv[1]["ms"])]
 
     # ---- CPU baseline beside it (rank 0, N = 1): bounded sample of the same workload
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        eig = None if periodic else nav.export_eig()
-        if eig is not None:
-            lam = eig[0].copy()
-            if abs(lam[0] + 1e-10) < 1e-10:
-                lam = lam + 1e-10  # un-shift: the oracle's Poisson applies poisson.rs:80-83 itself
-            eig = (lam, eig[1], eig[2])
-        val, nrun, sample = time_oracle(wl, 4, 1, budget_s=20.0, eig=eig)
-        cpu = {"value": val, "unit": "steps/s", "cores": os.cpu_count() or 1, "kind": "port", "sample": sample}
+        eig = None if periodic else nav.export_eig()  # unshifted; the oracle's Poisson applies poisson.rs:80-83 itself
+        val, sample, threads = time_cpu(wl, 8, 1, budget_s=25.0, eig=eig)
+        cpu = {"value": val, "unit": "steps/s", "cores": threads, "kind": "port", "sample": sample,
+               "openblas_num_threads": os.environ.get("OPENBLAS_NUM_THREADS")}
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": steps_per_s, "unit": "steps/s", "n_gpus": world, "steps": args.steps, "warmup": W,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic (set_velocity(0.2,1,1)+set_temperature(0.2,1,1), no RNG)",
-            "config": {"workload": desc, "parallelism": "replicas x%d" % world if world > 1 else "1 GPU",
-                       "l2": "working set > 2 GB >> 126 MB L2, no flush needed", "cuda_graph": True,
-                       "setup_s": round(t_setup, 2), "div_norm_after": div},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches * args.steps, "roofline": roof, "cpu_baseline": cpu,
+            "data": DATA,
+            "config": config_of(args, wl, world, parallelism="replicas x%d" % world if world > 1 else "1 GPU", cuda_graph=True,
+                                setup_s=round(t_setup, 2), div_norm_after=div, kernel_path=list(nav.kernel_path())),
+            "clocks": clocks, "e2e": e2e, "e2e_resident": e2e_resident, "gpu_launches": launches * args.steps, "roofline": roof,
+            "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
     if dist is not None:
@@ -360,22 +669,29 @@ def run_ours(args, wl, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="confined2048", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--transport", default="p2p", choices=["p2p", "collective"],
                     help="slab mode: fused transposes over NVLink peer memory (p2p) or NCCL all_to_all (collective)")
     ap.add_argument("--parallel", default="auto", choices=["auto", "replicas", "slab"],
-                    help="N > 1: independent replicas (confined path) or one slab-decomposed problem (periodic path)")
+                    help="N > 1: one slab-decomposed periodic problem (default) or independent replicas of the N = 1 workload")
+    ap.add_argument("--parity-steps", type=int, default=3, help="slab mode: steps of the on-box parity check against the 1-GPU path")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    ngpus = max(args.gpus, world)
+    if args.workload is None:
+        # N = 1: the configuration the metric is quoted on (confined 2048x2049); N > 1: the slab-decomposed 8192x8193 problem
+        args.workload = "confined2048" if (ngpus == 1 or args.parallel == "replicas") else "periodic8192"
+    if args.steps is None:
+        args.steps = {"periodic8192": 30, "hholtz1024": 64}.get(args.workload, 200)
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
-        run_reference(args, wl, rank)
+        run_reference(args, wl, rank, world)
         return
     if world == 1 and args.gpus > 1:
         # launched without torchrun: re-exec under torch.distributed.run

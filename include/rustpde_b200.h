@@ -103,6 +103,12 @@ int rp_solver_eig_size(rp_solver_t* s, int* m, int* has_matrices);
 int rp_solver_export_eig(rp_solver_t* s, double* lam, double* q, double* p);
 /* Solve::solve(&self, input, output, axis) ; input [n0,n1] ortho, output composite */
 int rp_solver_solve(rp_solver_t* s, const double* in, size_t in_len, double* out, size_t out_len, int is_complex);
+/* Measurement aids (no reference counterpart): repeat the solve `reps` times on the rhs staged by the last
+ * rp_solver_solve (device-resident, asynchronous; rp_solver_sync waits), and report which kernels serve real-data
+ * solves (specialised = 1: hand-specialised x/y kernels + DMMA GEMMs, else generic lane programs). */
+int rp_solver_solve_resident(rp_solver_t* s, int reps, int is_complex);
+int rp_solver_sync(rp_solver_t* s);
+int rp_solver_path(rp_solver_t* s, int* specialised, int* split_gemm, int* launches);
 int rp_solver_destroy(rp_solver_t* s);
 
 /* ---- Navier2D (src/navier/navier.rs) -------------------------------------- */

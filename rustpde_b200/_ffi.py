@@ -50,6 +50,9 @@ _SIGS = {
     "rp_solver_eig_size": [vp, c_int_p, c_int_p],
     "rp_solver_export_eig": [vp, c_double_p, c_double_p, c_double_p],
     "rp_solver_solve": [vp, c_double_p, C.c_size_t, c_double_p, C.c_size_t, C.c_int],
+    "rp_solver_solve_resident": [vp, C.c_int, C.c_int],
+    "rp_solver_sync": [vp],
+    "rp_solver_path": [vp, c_int_p, c_int_p, c_int_p],
     "rp_solver_destroy": [vp],
     "rp_navier_create": [C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, vpp],
     "rp_navier_create_with_eig": [C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, c_double_p, c_double_p, c_double_p, vpp],

@@ -239,6 +239,18 @@ class _Solver:
             output[...] = out
         return out
 
+    def solve_resident(self, reps=1, complex_data=False):
+        """Repeat the last solve `reps` times on the device-resident rhs (asynchronous; measurement aid)."""
+        self._lib.call("rp_solver_solve_resident", self._h, int(reps), int(bool(complex_data)))
+
+    def sync(self):
+        self._lib.call("rp_solver_sync", self._h)
+
+    def path_info(self):
+        a, b, c = C.c_int(), C.c_int(), C.c_int()
+        self._lib.call("rp_solver_path", self._h, C.byref(a), C.byref(b), C.byref(c))
+        return {"specialised": bool(a.value), "split_gemm": bool(b.value), "launches": c.value}
+
     def export_eig(self):
         m, has = C.c_int(), C.c_int()
         self._lib.call("rp_solver_eig_size", self._h, C.byref(m), C.byref(has))

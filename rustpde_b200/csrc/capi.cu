@@ -286,6 +286,30 @@ int rp_solver_solve(rp_solver_t* s, const double* in, size_t in_len, double* out
     rt::sync(S.stream);
   });
 }
+int rp_solver_solve_resident(rp_solver_t* s, int reps, int is_complex) {
+  return guard([&] {
+    need(s && reps >= 0, RP_ERR_INVALID, "bad argument");
+    Solver2& S = *s->s;
+    const bool cd = is_complex != 0;
+    const bool lanes_c = cd || S.x_fourier;
+    need((lanes_c ? S.in_c : S.in_r).buf.p != nullptr, RP_ERR_INVALID, "solve_resident: call rp_solver_solve once first (stages the rhs)");
+    for (int i = 0; i < reps; ++i) S.solve(cd);
+  });
+}
+int rp_solver_sync(rp_solver_t* s) {
+  return guard([&] {
+    need(s, RP_ERR_INVALID, "null solver");
+    rt::sync(s->s->stream);
+  });
+}
+int rp_solver_path(rp_solver_t* s, int* specialised, int* split_gemm, int* launches) {
+  return guard([&] {
+    need(s, RP_ERR_INVALID, "null solver");
+    if (specialised) *specialised = s->s->fast_path() ? 1 : 0;
+    if (split_gemm) *split_gemm = s->s->ts.split ? 1 : 0;
+    if (launches) *launches = s->s->launches_per_solve(false);
+  });
+}
 int rp_solver_destroy(rp_solver_t* s) {
   return guard([&] {
     if (!s) return;

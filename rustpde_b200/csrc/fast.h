@@ -223,6 +223,14 @@ struct XProjectArgs {  // a1 = from_ortho_x(D_x S_x phi)/sx, a2 = from_ortho_x(S
 };
 void launch_x_project(const XProjectArgs& a, cudaStream_t s);
 
+struct XAdiArgs {  // x half of a stand-alone HholtzAdi::solve: out = Fdma_x(B2_x in)
+  Mat in;          // [nx, cols]
+  Mat out;         // [mx, cols]
+  const double *pt1, *pt2;  // chunk-major packed tables: {b2 lo, di, up, f.fp} (forward), {f.bs, bp1, bp2, 0} (backward)
+  int nx;
+};
+void launch_x_adi(const XAdiArgs& a, cudaStream_t s);
+
 // Destination of a fused transpose: part q (a peer GPU's buffer, mapped through CUDA IPC, or a local one) owns
 // the global indices [beg[q], beg[q+1]) along the scattered axis.  nparts == 0: no scatter (dense output).
 struct Scatter {

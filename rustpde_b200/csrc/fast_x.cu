@@ -307,6 +307,23 @@ __global__ void __launch_bounds__(XCfg<LOG2LB>::NTHR, XCfg<LOG2LB>::MINB) xk_pro
   }
 }
 
+// x half of a stand-alone HholtzAdi::solve (hholtz_adi.rs:108,128): B2_x matvec + Fdma_x along the strided lanes
+template <int LOG2LB>
+__global__ void __launch_bounds__(XCfg<LOG2LB>::NTHR, XCfg<LOG2LB>::MINB) xk_adi(XAdiArgs a) {
+  typedef XCfg<LOG2LB> C;
+  constexpr int LR = C::LR;
+  RP_DYN_SMEM(double, ta_);
+  cplx* ta = (cplx*)ta_;
+  cplx* tb = ta + C::AROWS * 2;  // scratch of the second-order sweep (idle second tile)
+  double* red = (double*)(tb + C::AROWS * 2);
+  const int c0 = blockIdx.x * LR, col = c0 + 2 * (threadIdx.x & 1), c = threadIdx.x & 1;
+  const int n = a.nx, m = n - 2;
+  xfill<C::NTHR>(ta, n, [&](int i) { return ld2(a.in, i, col); });
+  __syncthreads();
+  b2_fdma_v<2, C::NTHR, C::NMAX, C::NSC2>(ta, -1, n, a.pt1, a.pt2, red, C::NSC2 == C::NSC ? (double*)tb : red);
+  for (int i = threadIdx.x >> 1; i < m; i += C::NTHR / 2) st2(a.out, i, col, ta[cidx<2>(i, c)]);
+}
+
 // ---------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------
@@ -376,6 +393,7 @@ static void set_smem(K kern, int bytes) {
 #define XK_CASE_xk_forward(L, LCV) XK_CASE_BODY(xk_forward, L, LCV, C::SMEM_AW)
 #define XK_CASE_xk_div(L, LCV) XK_CASE_BODY(xk_div, L, LCV, C::SMEM_AA)
 #define XK_CASE_xk_project(L, LCV) XK_CASE_BODY(xk_project, L, LCV, C::SMEM_AA)
+#define XK_CASE_xk_adi(L, LCV) XK_CASE_BODY(xk_adi, L, LCV, C::SMEM_AA)
 
 #define XK_LAUNCH(kern, ncols, nx, nby)                                            \
   do {                                                                             \
@@ -412,6 +430,7 @@ void launch_x_forward(const XForwardArgs3& a_, int nb, cudaStream_t s) {
 }
 void launch_x_div(const XDivArgs& a, cudaStream_t s) { XK_LAUNCH(xk_div, a.vx.cols, a.nx, 1); }
 void launch_x_project(const XProjectArgs& a, cudaStream_t s) { XK_LAUNCH(xk_project, a.phi.cols, a.nx, 1); }
+void launch_x_adi(const XAdiArgs& a, cudaStream_t s) { XK_LAUNCH(xk_adi, a.in.cols, a.nx, 1); }
 
 }  // namespace fk
 }  // namespace rp

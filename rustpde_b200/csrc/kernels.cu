@@ -345,4 +345,23 @@ void launch_combine(double* out, const double* a, const double* b, const double*
   RP_LAUNCH(combine_kernel, dim3(blocks), dim3(256), (size_t)0, s, out, a, b, c, ld, rows, cols, s0, s1);
 }
 
+// out[r][j] = lo[r] in[r][j] + di[r] in[r+2][j] + up[r] in[r+4][j], r < m = n - 2: the B2 preconditioner along x
+// (matvec.rs:172-193) of a stand-alone Hholtz / Poisson solve; elementwise in j, so plain coalesced rows
+__global__ void __launch_bounds__(256) b2x_kernel(const double* in, long long ldi, double* out, long long ldo, int n, int cols,
+                                                   const double* lo, const double* di, const double* up) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int m = n - 2;
+  if (j >= cols) return;
+  for (int r = blockIdx.y; r < m; r += gridDim.y) {
+    double v = lo[r] * in[(size_t)r * ldi + j] + di[r] * in[(size_t)(r + 2) * ldi + j];
+    if (r + 4 < n) v = fma(up[r], in[(size_t)(r + 4) * ldi + j], v);
+    out[(size_t)r * ldo + j] = v;
+  }
+}
+void launch_b2x(const double* in, long long ldi, double* out, long long ldo, int n, int cols, const double* lo, const double* di,
+                const double* up, cudaStream_t s) {
+  dim3 grid((cols + 255) / 256, std::min(n - 2, 1024));
+  RP_LAUNCH(b2x_kernel, grid, dim3(256), (size_t)0, s, in, ldi, out, ldo, n, cols, lo, di, up);
+}
+
 }  // namespace rp

@@ -165,12 +165,23 @@ class Solver2 {
   void emit_y(ProgBuilder& pb, int r, int rinv, Lay lay, bool complex_lanes) const;  // bandmv_y + solve_y
   void gemm_fwd(const Arr& in, Arr& out, int ncols_real) const;
   void gemm_bwd(const Arr& in, Arr& out, int ncols_real) const;
+  // per-mode tables of the specialised y kernels (fast.h ModeTabs) incl. the chunk-major packed copies; cached
+  fk::ModeTabs mode_tabs();
+  // true when solve(false) (real data) runs on the specialised kernels: HholtzAdi = xk_adi + yk_adi; Hholtz / Poisson
+  // with Chebyshev x = b2x + DMMA GEMM + yk_mode + DMMA GEMM (else: generic lane programs)
+  bool fast_path() const;
+  int launches_per_solve(bool complex_data) const;
 
  private:
   Arr t1_[2], t2_[2], t3_[2];
   Built px_[2], py_[2];
   std::vector<double> hq_, hp_, lam_export_;
   void build_programs(bool complex_data);
+  void solve_fast();
+  std::vector<DevBuf> perm_;  // chunk-major coefficient tables (fast.h perm_table)
+  bool have_mode_tabs_ = false, have_adi_tabs_ = false;
+  fk::ModeTabs mode_tabs_;
+  const double *adi_pt_[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
 };
 
 // Navier2D (src/navier/navier.rs:153-195)
@@ -282,7 +293,6 @@ class Navier2D {
   std::vector<DevBuf> perm_;  // chunk-major coefficient tables of the specialised kernels (fast.h perm_table)
   std::map<const void*, std::pair<const double*, const double*>> perm_mode_;
   std::map<std::pair<const void*, int>, std::pair<const double*, const double*>> perm_tdma_;
-  fk::ModeTabs mode_of(const FdmaModeDev& m);
   fk::TdmaTabs tdma_of(const Base& b, int n, fk::ScanShape ng);
 #ifndef RP_EMU
   cudaStream_t copy_stream_ = nullptr, fetch_stream_ = nullptr;

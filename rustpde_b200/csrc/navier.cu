@@ -559,31 +559,6 @@ fk::TdmaTabs Navier2D::tdma_of(const Base& b, int n, fk::ScanShape ng) {
   t.pf = it->second.first, t.pb = it->second.second;
   return t;
 }
-fk::ModeTabs Navier2D::mode_of(const FdmaModeDev& m) {
-  fk::ModeTabs t;
-  t.a_low = m.a_low.as<double>(), t.a_up1 = m.a_up1.as<double>(), t.a_up2 = m.a_up2.as<double>();
-  t.c_low = m.c_low.as<double>(), t.c_up1 = m.c_up1.as<double>(), t.c_up2 = m.c_up2.as<double>();
-  t.lam = m.lam.as<double>();
-  t.alpha = m.alpha;
-  t.inv = m.inv.as<double>();
-  t.inv_ld = m.inv_ld;
-  auto it = perm_mode_.find(&m);
-  if (it == perm_mode_.end()) {  // chunk-major packed copies of the raw bands (fast.h perm_table)
-    const Base& byo = *field->sp.b1;
-    const fk::ScanShape ng = fk::y_scan_shape(ny);
-    const int mm = ny - 2;
-    const std::vector<double> al = host_of(m.a_low), cl = host_of(m.c_low), au1 = host_of(m.a_up1), cu1 = host_of(m.c_up1),
-                              au2 = host_of(m.a_up2), cu2 = host_of(m.c_up2);
-    perm_.push_back(upload(fk::perm_table(mm, true, ng, 6, {host_of(byo.d_b2lo), host_of(byo.d_b2di), host_of(byo.d_b2up), al, cl},
-                                          {0, 0, 0, -2, -2})));
-    const double* pf = perm_.back().as<double>();
-    perm_.push_back(upload(fk::perm_table(mm, false, ng, 8, {au1, cu1, au2, cu2, au2, cu2, al, cl}, {0, 0, 0, 0, -2, -2, -2, -2})));
-    it = perm_mode_.emplace(&m, std::make_pair(pf, perm_.back().as<double>())).first;
-  }
-  t.pf = it->second.first, t.pb = it->second.second;
-  return t;
-}
-
 void Navier2D::build_step_confined_fast() {
   const Base &bxu = *ux->sp.b0, &byu = *ux->sp.b1;
   const Base &bxt = *temp->sp.b0, &byt = *temp->sp.b1;
@@ -727,7 +702,7 @@ void Navier2D::build_step_confined_fast() {
     fk::YModeArgs a;
     a.g = mat_of(g_), a.h = mat_of(h_);
     a.b2 = b2_of(byo);
-    a.m = mode_of(solver[3]->ts.mode);
+    a.m = solver[3]->mode_tabs();
     a.ny = ny;
     add_fast("poisson_mode_y", 3 * fb, [this, a]() { fk::launch_y_mode(a, stream); });
   }
@@ -863,7 +838,7 @@ void Navier2D::build_step_periodic_fast() {
     a.mode = f;
     a.dt = dt, a.isx = isx, a.isy = isy;
     a.b2 = b2_of(byo);
-    a.m = mode_of(solver[f]->ts.mode);
+    a.m = solver[f]->mode_tabs();
     a.ny = ny;
     a.k0 = 0;
   }
@@ -879,7 +854,7 @@ void Navier2D::build_step_periodic_fast() {
     a.sd = byu.d_sd.as<double>(), a.sl = byu.d_sl.as<double>();
     a.isx = isx, a.isy = isy;
     a.b2 = b2_of(byo);
-    a.m = mode_of(solver[3]->ts.mode);
+    a.m = solver[3]->mode_tabs();
     a.ny = ny;
     a.k0 = 0;
     add_fast("divergence_poisson_mode_y", 5 * fb, [this, a]() { fk::launch_p_divpois(a, stream); });
@@ -1004,10 +979,10 @@ void Navier2D::slab_phase3(int k0, int mkl, const double* const in[3]) {
     a.t = dct_of(byo);
   }
   fk::launch_p_yforward(y3, 3, stream);
-  auto slab_mode = [&](const FdmaModeDev& md) {
-    fk::ModeTabs t = mode_of(md);
+  auto slab_mode = [&](Solver2& sv) {
+    fk::ModeTabs t = sv.mode_tabs();
     t.lam += k0;
-    t.inv += (size_t)k0 * md.inv_ld;
+    t.inv += (size_t)k0 * sv.ts.mode.inv_ld;
     return t;
   };
   fk::PHholtzArgs3 h3;
@@ -1022,7 +997,7 @@ void Navier2D::slab_phase3(int k0, int mkl, const double* const in[3]) {
     a.mode = f;
     a.dt = dt, a.isx = isx, a.isy = isy;
     a.b2 = b2_of(byo);
-    a.m = slab_mode(solver[f]->ts.mode);
+    a.m = slab_mode(*solver[f]);
     a.ny = ny;
     a.k0 = k0;
   }
@@ -1039,7 +1014,7 @@ void Navier2D::slab_phase3(int k0, int mkl, const double* const in[3]) {
     a.sd = byu.d_sd.as<double>(), a.sl = byu.d_sl.as<double>();
     a.isx = isx, a.isy = isy;
     a.b2 = b2_of(byo);
-    a.m = slab_mode(solver[3]->ts.mode);
+    a.m = slab_mode(*solver[3]);
     a.ny = ny;
     a.k0 = k0;
     fk::launch_p_divpois(a, stream);

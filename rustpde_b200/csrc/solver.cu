@@ -230,7 +230,125 @@ void Solver2::build_programs(bool cd) {
   }
 }
 
+// host copy of a device table of doubles
+static std::vector<double> host_of(const DevBuf& b) {
+  std::vector<double> v(b.bytes / sizeof(double));
+  if (!v.empty()) {
+    rt::d2h(v.data(), b.p, b.bytes, 0);
+    rt::sync(0);
+  }
+  return v;
+}
+
+fk::ModeTabs Solver2::mode_tabs() {
+  if (have_mode_tabs_) return mode_tabs_;
+  const FdmaModeDev& m = ts.mode;
+  fk::ModeTabs t;
+  t.a_low = m.a_low.as<double>(), t.a_up1 = m.a_up1.as<double>(), t.a_up2 = m.a_up2.as<double>();
+  t.c_low = m.c_low.as<double>(), t.c_up1 = m.c_up1.as<double>(), t.c_up2 = m.c_up2.as<double>();
+  t.lam = m.lam.as<double>();
+  t.alpha = m.alpha;
+  t.inv = m.inv.as<double>();
+  t.inv_ld = m.inv_ld;
+  t.pf = t.pb = nullptr;
+  const fk::ScanShape ng = fk::y_scan_shape(n1);
+  if (ng.ng > 0) {  // chunk-major packed copies of the raw bands (fast.h perm_table)
+    const Base& by = *sp.b1;  // the B2 rows depend on n only
+    const int mm = n1 - 2;
+    const std::vector<double> al = host_of(m.a_low), cl = host_of(m.c_low), au1 = host_of(m.a_up1), cu1 = host_of(m.c_up1),
+                              au2 = host_of(m.a_up2), cu2 = host_of(m.c_up2);
+    perm_.push_back(upload(fk::perm_table(mm, true, ng, 6, {host_of(by.d_b2lo), host_of(by.d_b2di), host_of(by.d_b2up), al, cl},
+                                          {0, 0, 0, -2, -2})));
+    t.pf = perm_.back().as<double>();
+    perm_.push_back(upload(fk::perm_table(mm, false, ng, 8, {au1, cu1, au2, cu2, au2, cu2, al, cl}, {0, 0, 0, 0, -2, -2, -2, -2})));
+    t.pb = perm_.back().as<double>();
+  }
+  mode_tabs_ = t;
+  have_mode_tabs_ = true;
+  return t;
+}
+
+bool Solver2::fast_path() const {
+  static const char* nf = getenv("RUSTPDE_B200_NO_FAST");
+  if (nf && nf[0] == '1') return false;
+  if (x_fourier || !fk::y_supported(n1)) return false;
+  if (kind == SOLVER_HHOLTZ_ADI) return fk::x_supported(n0);
+  return true;  // Chebyshev x: the x pass is the elementwise B2 matvec, any n0
+}
+
+int Solver2::launches_per_solve(bool cd) const {
+  if (!cd && fast_path()) return kind == SOLVER_HHOLTZ_ADI ? 2 : 4;
+  const bool use_gemm = (kind != SOLVER_HHOLTZ_ADI) && !x_fourier;
+  return (x_fourier ? 0 : 1) + 1 + (use_gemm ? 2 : 0);
+}
+
+static fk::Mat mat_of(const Arr& a) { return fk::Mat{a.d(), a.ld, a.rows, a.cols}; }
+
+// Real data on the specialised kernels (same arithmetic as the fused Navier2D passes): the stand-alone
+// HholtzAdi / Hholtz / Poisson::solve of config 2 (examples/hholtz_2d.rs) no longer goes through the lane programs.
+void Solver2::solve_fast() {
+  if (!in_r.buf.p) {
+    in_r.alloc(n0, n1, false);
+    out_r.alloc(m0, m1, false);
+  }
+  Arr &t1 = t1_[0], &t2 = t2_[0], &t3 = t3_[0];
+  if (!t1.buf.p) {
+    t1.alloc(m0, n1, false);
+    t2.alloc(m0, n1, false);
+    t3.alloc(m0, m1, false);
+  }
+  const Base &b0 = *sp.b0, &b1 = *sp.b1;
+  if (kind == SOLVER_HHOLTZ_ADI) {
+    if (!have_adi_tabs_) {
+      const fk::ScanShape sx1 = fk::x_scan_shape(n0), sx2 = fk::x_scan2_shape(n0), sy = fk::y_scan_shape(n1);
+      const Base* bs[2] = {&b0, &b1};
+      for (int ax = 0; ax < 2; ++ax) {
+        const FdmaDev& fd = adi[ax].fdma;
+        const Base& b = *bs[ax];
+        const int m = (ax == 0 ? n0 : n1) - 2;
+        perm_.push_back(upload(fk::perm_table(m, true, ax == 0 ? sx1 : sy, 4,
+                                              {host_of(b.d_b2lo), host_of(b.d_b2di), host_of(b.d_b2up), host_of(fd.fp)}, {0, 0, 0, 0})));
+        adi_pt_[ax][0] = perm_.back().as<double>();
+        perm_.push_back(upload(fk::perm_table(m, false, ax == 0 ? sx2 : sy, 4, {host_of(fd.bs), host_of(fd.bp1), host_of(fd.bp2)}, {0, 0, 0})));
+        adi_pt_[ax][1] = perm_.back().as<double>();
+      }
+      have_adi_tabs_ = true;
+    }
+    fk::XAdiArgs xa;
+    xa.in = mat_of(in_r), xa.out = mat_of(t1);
+    xa.pt1 = adi_pt_[0][0], xa.pt2 = adi_pt_[0][1];
+    xa.nx = n0;
+    fk::launch_x_adi(xa, stream);
+    fk::YAdiArgs3 y3;
+    fk::YAdiArgs& ya = y3.a[0];
+    ya.w = mat_of(t1), ya.out = mat_of(out_r), ya.aux = fk::Mat{nullptr, 0, 0, 0};
+    ya.mode = 0;
+    ya.sd = ya.sl = nullptr;
+    ya.isy = 1.0;
+    ya.b2 = fk::B2Tabs{b1.d_b2lo.as<double>(), b1.d_b2di.as<double>(), b1.d_b2up.as<double>()};
+    ya.f = fk::FdmaTabs{adi[1].fdma.fp.as<double>(), adi[1].fdma.bs.as<double>(), adi[1].fdma.bp1.as<double>(), adi[1].fdma.bp2.as<double>()};
+    ya.pt1 = adi_pt_[1][0], ya.pt2 = adi_pt_[1][1];
+    ya.ny = n1;
+    y3.a[1] = y3.a[2] = ya;
+    fk::launch_y_adi(y3, 1, stream);
+    return;
+  }
+  launch_b2x(in_r.d(), in_r.ld, t1.d(), t1.ld, n0, n1, b0.d_b2lo.as<double>(), b0.d_b2di.as<double>(), b0.d_b2up.as<double>(), stream);
+  gemm_fwd(t1, t2, n1);
+  fk::YModeArgs ma;
+  ma.g = mat_of(t2), ma.h = mat_of(t3);
+  ma.b2 = fk::B2Tabs{b1.d_b2lo.as<double>(), b1.d_b2di.as<double>(), b1.d_b2up.as<double>()};
+  ma.m = mode_tabs();
+  ma.ny = n1;
+  fk::launch_y_mode(ma, stream);
+  gemm_bwd(t3, out_r, m1);
+}
+
 void Solver2::solve(bool cd) {
+  if (!cd && fast_path()) {
+    solve_fast();
+    return;
+  }
   build_programs(cd);
   const int q = cd ? 1 : 0;
   const bool lanes_c = cd || x_fourier;

@@ -71,6 +71,10 @@ class Navier2DSlab:
         self.transport = transport if self.world > 1 else "collective"
         if self.transport == "p2p":
             self._setup_p2p(f64)
+        # our kernels per slab step: phase 1 one launch (3 fields), phase 2 three (c2r value + d/dx, c2r d/dy, products + r2c),
+        # phase 3 five (forward DCT-y, Helmholtz x2 + x1, divergence + Poisson, projection)
+        self.launches_per_step = 9
+        self.fences_per_step = 2 if self.transport == "p2p" else 0
         # NVLink egress of this rank per step: 6 arrays rows->cols, 3 arrays cols->rows (16 B per complex element)
         self.bytes_exchanged_per_step = 16 * (6 * mkl * (ny - nyl) + 3 * nyl * (mk - mkl))
 
@@ -176,12 +180,23 @@ class Navier2DSlab:
             torch.cuda.synchronize()
 
     def gather_state(self):
-        """Make temp / ux / uy / pres vhat of the full per-rank model consistent (each rank owns rows [k0, k0+mkl))."""
+        """Make temp / ux / uy / pres vhat of the full per-rank model consistent (each rank owns rows [k0, k0+mkl)).
+        The row slabs travel as tensors through all_gather (NCCL on GPUs, gloo in the CPU tests), padded to the
+        largest slab."""
         self.sync()
         if self.world == 1:
             return
+        dev = "cpu" if self.lib.emulated else torch.device("cuda", torch.cuda.current_device())
+        kmax = max(self.ksz)
         for f in (self.nav.temp, self.nav.ux, self.nav.uy, self.nav.pres[0], self.nav.pres[1]):
-            mine = np.ascontiguousarray(f.vhat[self.k0:self.k0 + self.mkl])
-            parts = [None] * self.world
-            dist.all_gather_object(parts, mine, group=self.group)
-            f.vhat = np.concatenate(parts, axis=0)
+            ncol = f.shape_spectral[1]
+            mine = torch.zeros(kmax, ncol, 2, dtype=torch.float64, device=dev)
+            rows = f.vhat_rows(self.k0, self.mkl)
+            mine[: self.mkl].copy_(torch.from_numpy(rows.view(np.float64).reshape(self.mkl, ncol, 2)))
+            parts = [torch.empty_like(mine) for _ in range(self.world)]
+            dist.all_gather(parts, mine, group=self.group)
+            for q in range(self.world):
+                if q == self.rank:
+                    continue
+                blk = parts[q][: self.ksz[q]].cpu().numpy().reshape(self.ksz[q], ncol * 2).view(np.complex128)
+                f.set_vhat_rows(self.koff[q], blk)

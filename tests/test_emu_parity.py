@@ -30,6 +30,30 @@ def test_hholtz_adi(emu, nx, ny):
     pc.check_adi(emu, nx, ny)
 
 
+@pytest.mark.parametrize("nx,ny", [(24, 33), (40, 65), (18, 33), (130, 33)])
+def test_standalone_solvers_on_specialised_kernels(emu, nx, ny):
+    """Stand-alone HholtzAdi / Hholtz / Poisson::solve (real data) run on the specialised kernels when the shape
+    qualifies (xk_adi + yk_adi; b2x + DMMA GEMM + yk_mode + DMMA GEMM) and agree with the lane programs."""
+    import rustpde_b200 as R
+    f = R.Field2(R.Space2(R.cheb_dirichlet(nx), R.cheb_dirichlet(ny)), lib=emu)
+    assert R.HholtzAdi(f, [0.3, 0.7]).path_info()["specialised"]
+    assert R.Hholtz(f, [1.0, 0.8], 2.0).path_info() == {"specialised": True, "split_gemm": True, "launches": 4}
+    pc.check_adi(emu, nx, ny)
+    for which, kx in (("hholtz", "cheb_dirichlet"), ("poisson", "cheb_neumann")):
+        e1, e2 = pc.check_tensor_own_eig(emu, which, kx, kx, nx, ny)
+        assert e1 <= pc.TOL and e2 <= pc.TOL, (which, e1, e2)
+        e1, e2, sol, _ = pc.check_tensor_shared_eig(emu, which, kx, kx, nx, ny)
+        assert e1 <= pc.TOL and e2 <= pc.TOL, (which, e1, e2)
+    # resident repeats leave the result unchanged
+    rng = np.random.default_rng(3)
+    h = R.Hholtz(f, [1.0, 1.0], 10.0)
+    b = rng.uniform(-1, 1, (nx, ny))
+    x1 = h.solve(b)
+    h.solve_resident(3)
+    h.sync()
+    assert np.array_equal(x1, h.solve(b))
+
+
 def test_hholtz_adi_kat(emu):  # hholtz_adi.rs:176-207 through the device path
     import rustpde_b200 as R
     f = R.Field2(R.Space2(R.cheb_dirichlet(7), R.cheb_dirichlet(7)), lib=emu)
