@@ -262,6 +262,30 @@ FK_DEV void bfly_zero_half(cplx* v) {  // DFT-R of (v[0..R/2), 0, ..., 0)
   }
 }
 
+// ---- group barriers ----------------------------------------------------------------------------------------
+// Every stage of span S <= 512 rows of the in-place DIF / DIT pair touches only rows of one 512-row sub-block, and with
+// the butterfly mapping b = tid + k NTHR (2 complex lanes per row, radix 8) all butterflies of the sub-blocks
+// {tid / 128 + k NTHR / 128} belong to the 128 threads tid / 128.  Those stages therefore only need a barrier over
+// that 4-warp group (named barrier 1 + tid / 128): the groups drift apart, so the shared-memory phase of one
+// group overlaps the FP64 phase of another instead of the whole block alternating between the two pipes.
+// Development switch (RUSTPDE_B200_KFLAGS, read once per process by the launchers): bit 0 = block-wide barriers
+// everywhere (the round-1 behaviour), for A/B measurements.
+#ifndef RP_EMU
+static __constant__ int fk_kflags_c = 0;
+#endif
+template <int LC, int NTHR, int LOG2S>
+FK_DEV void stage_sync() {
+#ifndef RP_EMU
+  if constexpr (LC == 2 && NTHR > 128 && NTHR % 128 == 0 && LOG2S <= 9) {
+    if (!(fk_kflags_c & 1)) {
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + (int)(threadIdx.x >> 7)) : "memory");
+      return;
+    }
+  }
+#endif
+  __syncthreads();
+}
+
 // DIF stage of span S = 1 << LOG2S, radix R.  ZERO_HALF: rows >= L/2 hold zeros (not read).
 template <int LC, int LOG2L, int NTHR, int LOG2S, int R, bool ZERO_HALF>
 FK_DEV void dif_stage(cplx* tc, const cplx* __restrict__ tw) {
@@ -282,7 +306,7 @@ FK_DEV void dif_stage(cplx* tc, const cplx* __restrict__ tw) {
 #pragma unroll
     for (int r = 0; r < R; ++r) tc[cidx<LC>(base + r * SR, c)] = v[r];
   }
-  __syncthreads();
+  stage_sync<LC, NTHR, LOG2S>();  // the next stage (span S / R) stays inside this stage's blocks
 }
 // inverse DIT stage (unnormalised) of span S >= 64 (the span-8 stage is fused into dif_dit_mid, which also
 // conjugates the input); LAST conjugates the results; HALF_OUT: only rows < L/2 are stored.
@@ -306,7 +330,8 @@ FK_DEV void dit_stage(cplx* tc, const cplx* __restrict__ tw) {
       tc[cidx<LC>(base + r * SR, c)] = x;
     }
   }
-  __syncthreads();
+  // the next DIT stage has span 8 S (or this was the last one): group-level only if that still fits a sub-block
+  stage_sync<LC, NTHR, (LAST ? 31 : LOG2S + 3)>();
 }
 template <int LC, int LOG2L, int NTHR, int LOG2S, bool HALF_OUT>
 FK_DEV void fft_dit_rec(cplx* tc, const cplx* __restrict__ tw) {
@@ -344,7 +369,7 @@ FK_DEV void dif_dit_mid(cplx* tc, const cplx* __restrict__ mulv) {
 #pragma unroll
     for (int r = 0; r < 8; ++r) tc[cidx<LC>(u * 8 + r, c)] = v[r];
   }
-  __syncthreads();
+  stage_sync<LC, NTHR, 6>();  // next: the DIT stage of span 64
 }
 // DIF stages down to span 64 (the span-8 stage is fused into dif_dit_mid)
 template <int LC, int LOG2L, int NTHR, int LOG2S, bool ZERO_HALF>

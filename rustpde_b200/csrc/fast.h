@@ -49,6 +49,7 @@ struct ModeTabs {  // per-lane A + (lam + alpha) C (fdma_tensor.rs:219-227)
 
 bool y_supported(int n1);
 bool x_supported(int n0);
+void apply_kflags();  // development switches (RUSTPDE_B200_KFLAGS) -> device constants; call outside stream capture
 
 // true the first time it is called for `mask` on the current CUDA device (kernel attributes such as the dynamic
 // shared-memory limit are per device, not per process)

@@ -405,6 +405,16 @@ static void set_smem(K kern, int bytes) {
     if (!ok_) throw Error(RP_ERR_INTERNAL, #kern ": unsupported lane length");     \
   } while (0)
 
+// RUSTPDE_B200_KFLAGS -> the development switches of this translation unit's kernels (fast.cuh fk_kflags_c)
+void apply_kflags() {
+#ifndef RP_EMU
+  static unsigned long long done = 0;
+  if (!first_use_on_device(done)) return;
+  const char* e = getenv("RUSTPDE_B200_KFLAGS");
+  const int v = e ? atoi(e) : 0;
+  RP_CUDA_CHECK(cudaMemcpyToSymbol(fk_kflags_c, &v, sizeof(int)));
+#endif
+}
 static int sm_count() {
 #ifndef RP_EMU
   static int n = 0;

@@ -266,6 +266,7 @@ void Navier2D::set_temperature(double amp, double m, double n) {  // navier.rs:9
 // --------------------------------------------------------------------------
 void Navier2D::build_step() {
   if (!ops_.empty()) return;
+  fk::apply_kflags();
   const char* nf = getenv("RUSTPDE_B200_NO_FAST");
   const bool fast_ok = !(nf && nf[0] == '1');
   if (periodic && fast_ok && fk::px_supported(nx) && fk::y_supported(ny))

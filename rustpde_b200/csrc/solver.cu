@@ -287,6 +287,7 @@ static fk::Mat mat_of(const Arr& a) { return fk::Mat{a.d(), a.ld, a.rows, a.cols
 // Real data on the specialised kernels (same arithmetic as the fused Navier2D passes): the stand-alone
 // HholtzAdi / Hholtz / Poisson::solve of config 2 (examples/hholtz_2d.rs) no longer goes through the lane programs.
 void Solver2::solve_fast() {
+  fk::apply_kflags();
   if (!in_r.buf.p) {
     in_r.alloc(n0, n1, false);
     out_r.alloc(m0, m1, false);

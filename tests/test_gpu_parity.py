@@ -202,6 +202,61 @@ def test_navier_1000_steps_nu_ke(gpu):
     assert abs(n.time - o.time) < 1e-9
 
 
+@pytest.mark.parametrize("name,specialised", [("confined128", (True, True)), ("periodic512", (True, False))])
+def test_navier_1000_steps_golden_specialised_kernels(gpu, name, specialised):
+    """north_star end-to-end on the kernels the benchmark times: 1000 steps on grids served by the specialised x/y
+    kernels (confined 128x129 incl. the parity-split DMMA GEMMs; periodic 512x513 = BASELINE config 3, Ra=1e7,
+    dt=2e-3) against the committed oracle fixtures: Nu, Nuvol, Re and kinetic energy within 1e-8 at steps 250 ... 1000,
+    final spectral coefficients within 1e-8 of the field maximum."""
+    n, worst = pc.check_navier_golden(gpu, name, tol_obs=1e-8, tol_field=1e-8)
+    assert n.kernel_path() == specialised, n.kernel_path()
+    print(name, worst)
+
+
+def test_navier_confined_2048_20_steps(gpu):
+    """The benchmark configuration itself (2048x2049, Ra=1e9, dt=1e-4), 20 steps against the oracle fed with the
+    library's exported (lam, Q, P): fields <= 1e-9 (max-norm) and <= 1e-6 banded, Nu / Nuvol / Re / |div| / Ekin <= 1e-9."""
+    err, derr, dn, do = pc.check_navier_steps(gpu, False, 2048, 2049, 20, ra=1e9, dt=1e-4, tol=1e-9, batch=20, own_eig=True)
+    assert max(derr) < 1e-9, (derr, dn, do)
+
+
+def test_navier_no_dealias_specialised_kernels(gpu):
+    """pub dealias = false (navier.rs:188): the 2/3 cuts fused into yk_conv / xk_forward / pk_r2c are switched off."""
+    import oracle as O, rustpde_b200 as R
+    for periodic, nx, ny in ((False, 64, 65), (True, 64, 65)):
+        n, o = pc.make_navier_pair(gpu, periodic, nx, ny, 1e5, 1.0, 0.01, ics=False, own_eig=not periodic)
+        n.dealias = False
+        o.dealias = False
+        for x in (n, o):
+            x.set_velocity(0.2, 1.0, 1.0)
+            x.set_temperature(0.2, 1.0, 1.0)
+        assert n.kernel_path()[0]
+        n.update(10)
+        for _ in range(10):
+            o.update()
+        err = pc.navier_field_errors(n, o)
+        assert max(err.values()) <= 1e-9, err
+        # and the cut really matters at this resolution
+        n2, _ = pc.make_navier_pair(gpu, periodic, nx, ny, 1e5, 1.0, 0.01, own_eig=not periodic)
+        n2.update(10)
+        assert pc.rel(n2.temp.vhat, n.temp.vhat) > 1e-12
+
+
+@pytest.mark.parametrize("nx,ny", [(1024, 1025), (2048, 2049)])
+def test_standalone_solvers_specialised_kernels(gpu, nx, ny):
+    """Config 2 and the config-4 grid: stand-alone HholtzAdi / Hholtz / Poisson::solve on the specialised kernels
+    (xk_adi + yk_adi; b2x + parity-split DMMA GEMM + yk_mode + GEMM), real data.  HholtzAdi <= 1e-10; fast
+    diagonalisation with the oracle consuming the exported (lam, Q, P): <= max(1e-10, 20 x GEMM summation-order floor)."""
+    import rustpde_b200 as R, oracle as O
+    f = R.Field2(R.Space2(R.cheb_dirichlet(nx), R.cheb_dirichlet(ny)), lib=gpu)
+    assert R.HholtzAdi(f, [0.3, 0.7]).path_info()["specialised"]
+    pc.check_adi(gpu, nx, ny, tol=1e-10)
+    if nx > 1024:
+        return  # the oracle's dense 2046^2 set-up is exercised through Navier2D at this size
+    e1, e2 = pc.check_tensor_own_eig(gpu, "hholtz", "cheb_dirichlet", "cheb_dirichlet", nx, ny)
+    assert e1 <= 1e-8 and e2 <= 1e-8, (e1, e2)
+
+
 def test_graph_and_eager_agree(gpu):
     import rustpde_b200 as R
     outs = []
