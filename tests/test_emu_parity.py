@@ -237,7 +237,7 @@ def test_band_rel_metric():
     rng = np.random.default_rng(0)
     b = rng.uniform(-1, 1, (64, 64)) * np.logspace(0, -12, 64)[None, :]
     a = b.copy()
-    a[:, 48:] *= 1.5
-    assert pc.rel(a, b) < 1e-9
+    a[:, 32:] *= 1.5  # coefficients of relative size 1e-6 and below: invisible to the global max-norm at 1e-6
+    assert pc.rel(a, b) < 1e-6
     assert pc.band_rel(a, b) > 0.1
     assert pc.band_rel(b, b) == 0.0
