@@ -144,6 +144,12 @@ int rp_navier_fetch_wait(rp_navier_t* h);
  * wait != 0 blocks for the outstanding request).  integrate() then sees a NaN one check late. */
 int rp_navier_div_async(rp_navier_t* h);
 int rp_navier_div_poll(rp_navier_t* h, int wait, double* div_norm, int* ready);
+/* write (975-1013) / read (963-972): checkpoint and restart with the reference's group / dataset layout
+ * (temp, ux, uy, pres: v, vhat | vhat_re + vhat_im; x, dx, y, dy; time, ra, pr, nu, kappa) in the RPSNAP1 container
+ * (csrc/snapshot.cu; rustpde_b200/snapshot.py converts to / from HDF5 where h5py exists).  read keeps the
+ * truncate / keep-the-rest "broadcast" of field/read.rs:113-122 when the stored shape differs. */
+int rp_navier_write_snapshot(rp_navier_t* h, const char* path);
+int rp_navier_read_snapshot(rp_navier_t* h, const char* path);
 int rp_navier_get_time(rp_navier_t* h, double* time);                          /* get_time */
 int rp_navier_get_dt(rp_navier_t* h, double* dt);                              /* get_dt */
 int rp_navier_reset_time(rp_navier_t* h);                                      /* 951-953 */

@@ -68,6 +68,8 @@ _SIGS = {
     "rp_navier_fetch_wait": [vp],
     "rp_navier_div_async": [vp],
     "rp_navier_div_poll": [vp, C.c_int, c_double_p, c_int_p],
+    "rp_navier_write_snapshot": [vp, C.c_char_p],
+    "rp_navier_read_snapshot": [vp, C.c_char_p],
     "rp_navier_sync": [vp],
     "rp_navier_get_time": [vp, c_double_p],
     "rp_navier_get_dt": [vp, c_double_p],

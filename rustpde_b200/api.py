@@ -489,10 +489,30 @@ class Navier2D:
     def div_norm(self):
         return self.eval(False, False, False, True, False)[3]
 
-    def callback(self):  # navier.rs:775-853 (diagnostics; HDF5 output is out of scope)
-        nu, nuvol, re, div, _ = self.eval(True, True, True, True, False)
+    def write(self, filename):  # navier.rs:975-981: errors are printed and swallowed
+        try:
+            self._lib.call("rp_navier_write_snapshot", self._h, str(filename).encode())
+            print(" ==> %r" % str(filename))
+        except RustpdeError:
+            print("Error while writing file %r." % str(filename))
+
+    def read(self, filename):  # navier.rs:963-972
+        self._lib.call("rp_navier_read_snapshot", self._h, str(filename).encode())
+        print(" <== %r" % str(filename))
+
+    def callback(self, data_dir="data"):  # navier.rs:775-853
+        import os
         t = self.time
+        os.makedirs(data_dir, exist_ok=True)
+        # "data/flow{:0>8.2}.h5" in the reference; same stem, the RPSNAP1 container (rustpde_b200/snapshot.py)
+        fname = os.path.join(data_dir, "flow%s.rpsnap" % ("%.2f" % t).rjust(8, "0"))
+        dt_save = self.write_intervall
+        if dt_save is None or (t % dt_save) < self.dt / 2.0 or (t % dt_save) > dt_save - self.dt / 2.0:
+            self.write(fname)
+        nu, nuvol, re, div, _ = self.eval(True, True, True, True, False)
         print("time = %4.2f      |div| = %4.2e     Nu = %5.3e     Nuv = %5.3e    Re = %5.3e" % (t, div, nu, nuvol, re))
+        with open(os.path.join(data_dir, "info.txt"), "a") as f:  # navier.rs:843-852
+            f.write("%r %r %r %r\n" % (t, nu, nuvol, re))
         self.diagnostics["time"].append(t)
         self.diagnostics["Nu"].append(nu)
         self.diagnostics["Nuvol"].append(nuvol)

@@ -413,6 +413,18 @@ int rp_navier_div_poll(rp_navier_t* h, int wait, double* div_norm, int* ready) {
     if (ready) *ready = ok ? 1 : 0;
   });
 }
+int rp_navier_write_snapshot(rp_navier_t* h, const char* path) {
+  NAV_GUARD({
+    need(path != nullptr, RP_ERR_INVALID, "null path");
+    N.write_snapshot(path);
+  });
+}
+int rp_navier_read_snapshot(rp_navier_t* h, const char* path) {
+  NAV_GUARD({
+    need(path != nullptr, RP_ERR_INVALID, "null path");
+    N.read_snapshot(path);
+  });
+}
 int rp_navier_sync(rp_navier_t* h) { NAV_GUARD(N.sync()); }
 int rp_navier_get_time(rp_navier_t* h, double* t) { NAV_GUARD(if (t) *t = N.time); }
 int rp_navier_get_dt(rp_navier_t* h, double* dt) { NAV_GUARD(if (dt) *dt = N.dt); }

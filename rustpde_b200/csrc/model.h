@@ -239,6 +239,9 @@ class Navier2D {
   // asynchronous state download on a second copy stream (see navier.cu)
   void fetch_state(double* t, double* u, double* v, double* p);
   void fetch_wait();
+  // checkpoint / restart in the reference's group / dataset layout (snapshot.cu)
+  void write_snapshot(const char* path);
+  void read_snapshot(const char* path);
   // exit() without a per-step host sync
   void div_async();
   bool div_poll(double* out, bool wait);
@@ -257,6 +260,7 @@ class Navier2D {
   void apply_ic(Field2& f, double amp, double m, double n, bool sin_cos);
   void run_step();
   void prepare_step();
+  void copy_bc_to_field();  // field.vhat = ortho coefficients of the boundary-condition field
 #ifndef RP_EMU
   void capture_graph();
 #endif

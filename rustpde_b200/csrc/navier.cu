@@ -212,6 +212,8 @@ void Navier2D::set_tempbc_ortho(const double* that_bc) {
   rebuild_bc();
 }
 
+void Navier2D::copy_bc_to_field() { copy_arr(field->vhat, tbc_ortho_, stream); }
+
 // Time-invariant pieces of the boundary field (navier.rs:547-550, 665-668)
 void Navier2D::rebuild_bc() {
   Field2& f = *field;

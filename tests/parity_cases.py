@@ -26,10 +26,10 @@ def rel(a, b):
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
 
 
-def band_rel(a, b, nb=4):
+def band_rel(a, b, nb=4, floor=1e-8):
     """Banded error metric: the array is cut into nb x nb blocks of mode bands (spectral coefficients span 15 decades,
     so a global max-norm cannot see the high modes); per band max|a-b| / max(max|b| of the band, floor) with
-    floor = 1e-8 * global max|b| (rounding noise of a transform is relative to the LARGEST coefficient that went
+    floor = `floor` (default 1e-8) * global max|b| (rounding noise of a transform is relative to the LARGEST coefficient that went
     through it, so bands far below the floor are compared against the floor, not against themselves).  Returns the
     worst band; tolerance 1e-6 then means: every band down to 1e-8 of the peak is right to 6 digits, and nothing
     anywhere is off by more than 1e-14 of the peak."""
@@ -45,7 +45,7 @@ def band_rel(a, b, nb=4):
             bb = b[sl]
             if bb.size == 0:
                 continue
-            ref = max(np.abs(bb).max(), 1e-8 * gmax)
+            ref = max(np.abs(bb).max(), floor * gmax)
             worst = max(worst, float(np.abs(a[sl] - bb).max() / ref))
     return worst
 

@@ -62,3 +62,27 @@ def test_package_never_references_oracle_or_emulator():
                 txt = open(os.path.join(dirpath, fn)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt, fn
                 assert "librustpde_b200_emu" not in txt, fn
+
+
+def test_rust_shim_binds_every_declared_function():
+    """rust/src/lib.rs cannot be compiled here (no Rust toolchain); at least its extern "C" block must declare exactly
+    the functions of the header, with the same number of arguments."""
+    src = open(os.path.join(ROOT, "rust", "src", "lib.rs")).read()
+    block = src[src.index('extern "C" {'):]
+    block = block[: block.index("\n}\n")]
+    rust = dict((m.group(1), m.group(2)) for m in re.finditer(r"fn (rp_[a-z0-9_]+)\s*\((.*?)\)\s*(?:->|;)", block, flags=re.S))
+    assert sorted(rust) == declared_functions()
+    hdr = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    for name, rargs in rust.items():
+        cargs = re.search(r"\b%s\s*\((.*?)\)\s*;" % name, hdr, flags=re.S).group(1).strip()
+        nc = 0 if cargs in ("", "void") else cargs.count(",") + 1
+        nr = 0 if not rargs.strip() else rargs.count(":")
+        assert nc == nr, (name, cargs, rargs)
+    # every public item of the reference surface named in SURVEY 8(b) is present
+    for item in ("pub fn chebyshev", "pub fn cheb_dirichlet", "pub fn cheb_neumann", "pub fn cheb_dirichlet_bc", "pub fn cheb_neumann_bc",
+                 "pub fn fourier_r2c", "pub struct Space2", "pub struct Field2", "pub fn forward(&mut self)", "pub fn backward(&mut self)",
+                 "pub fn to_ortho(&self)", "pub fn from_ortho", "pub fn gradient(&self", "pub struct Hholtz", "pub fn new2",
+                 "pub struct HholtzAdi", "pub struct Poisson", "pub trait Solve", "pub enum SolverField", "pub struct Navier2D",
+                 "pub fn new_periodic", "pub fn set_velocity", "pub fn set_temperature", "pub trait Integrate", "pub fn integrate",
+                 "pub fn read(&mut self", "pub fn write(&mut self", "pub fn reset_time", "pub fn eval_nu", "pub fn eval_nuvol", "pub fn eval_re"):
+        assert item in src, item

@@ -257,6 +257,19 @@ def test_standalone_solvers_specialised_kernels(gpu, nx, ny):
     assert e1 <= 1e-8 and e2 <= 1e-8, (e1, e2)
 
 
+@pytest.mark.parametrize("periodic,nx,ny", [(False, 128, 129), (True, 128, 129)])
+def test_snapshot_roundtrip_gpu(gpu, tmp_path, periodic, nx, ny):
+    """write() / read() (navier.rs:956-1014) on the device: dataset layout, bit-exact restart, broadcast on another grid."""
+    from test_snapshot import check_snapshot_roundtrip
+    assert check_snapshot_roundtrip(gpu, periodic, nx, ny, tmp_path)
+
+
+def test_host_api_additions_gpu(gpu):
+    """fetch_state / div_async / vhat row slabs / device averages / profile() == update() on the real streams."""
+    assert pc.check_host_api_additions(gpu, False, 128, 129)
+    assert pc.check_host_api_additions(gpu, True, 128, 129)
+
+
 def test_graph_and_eager_agree(gpu):
     import rustpde_b200 as R
     outs = []
