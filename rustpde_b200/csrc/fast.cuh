@@ -604,10 +604,10 @@ FK_DEV auto fcall(F& f, int i, int l, int slot) {
 // chain starts: all loads of a (sub-)batch are in flight together, instead of one exposed L2 round trip per chunk
 // element (the coefficient tables do not stay in the small L1 left beside the tiles).
 #define FK_SCAN_SB 8  // sub-batch of the loops that re-fetch coefficients
-template <int LC, int NTHR, int CL, bool FWD, class In, class C1, class Out>
-FK_DEV void scan1(int n, double* red, In in, C1 c1, Out out) {
+template <int LC, int NTHR, int CL, bool FWD, int NSC, class In, class C1, class Out>
+FK_DEV void scan1n(int n, double* red, In in, C1 c1, Out out) {
   constexpr int LR = 2 * LC, NCH = 2 * LR;  // chains per tile: LR lanes x 2 parities
-  constexpr int NSC = scan_threads(NTHR), NG = NSC / NCH;
+  constexpr int NG = NSC / NCH;
   const int tid = threadIdx.x, ch = tid % NCH, g = tid / NCH;
   const int lane = ch % LR, p = ch / LR;
   const int M = (tid < NSC) ? ((n - p + 1) >> 1) : 0;  // threads beyond NSC own empty chunks
@@ -681,13 +681,18 @@ FK_DEV void scan1(int n, double* red, In in, C1 c1, Out out) {
   __syncthreads();
 }
 
+template <int LC, int NTHR, int CL, bool FWD, class In, class C1, class Out>
+FK_DEV void scan1(int n, double* red, In in, C1 c1, Out out) {
+  scan1n<LC, NTHR, CL, FWD, scan_threads(NTHR)>(n, red, in, c1, out);
+}
+
 //   y_t = in(i, lane) + c1(i, lane) * y_{t-1} + c2(i, lane) * y_{t-2}
 // in(i, lane) is evaluated again in the second walk (no register copy of the chunk): out(i, lane, .) of a
 // thread may only overwrite what in(i, lane) of the same thread read -- true for every use (element-wise in place).
-template <int LC, int NTHR, int CL, bool FWD, class In, class C1, class C2, class Out>
-FK_DEV void scan2(int n, double* red, In in, C1 c1, C2 c2, Out out) {
+template <int LC, int NTHR, int CL, bool FWD, int NSC, class In, class C1, class C2, class Out>
+FK_DEV void scan2n(int n, double* red, In in, C1 c1, C2 c2, Out out) {
   constexpr int LR = 2 * LC, NCH = 2 * LR;  // chains per tile: LR lanes x 2 parities
-  constexpr int NSC = scan_threads(NTHR), NG = NSC / NCH;
+  constexpr int NG = NSC / NCH;
   constexpr int SB = FK_SCAN_SB;
   const int tid = threadIdx.x, ch = tid % NCH, g = tid / NCH;
   const int lane = ch % LR, p = ch / LR;
@@ -782,6 +787,11 @@ FK_DEV void scan2(int n, double* red, In in, C1 c1, C2 c2, Out out) {
     }
   }
   __syncthreads();
+}
+
+template <int LC, int NTHR, int CL, bool FWD, class In, class C1, class C2, class Out>
+FK_DEV void scan2(int n, double* red, In in, C1 c1, C2 c2, Out out) {
+  scan2n<LC, NTHR, CL, FWD, scan_threads(NTHR)>(n, red, in, c1, c2, out);
 }
 
 // chunk length bound for a lane of n elements handled by NTHR threads

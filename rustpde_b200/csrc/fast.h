@@ -213,6 +213,7 @@ struct XDivArgs {  // div = D_x S_x vx / sx + S_x ey ; r1 = B2_x div
   int nx;
 };
 void launch_x_div(const XDivArgs& a, cudaStream_t s);
+void launch_xs_div(const XDivArgs& a, cudaStream_t s);  // the same pass as a streaming column scan (fast_xs.cu)
 
 struct XProjectArgs {  // a1 = from_ortho_x(D_x S_x phi)/sx, a2 = from_ortho_x(S_x phi)
   Mat phi;             // [mx, my]
@@ -223,6 +224,56 @@ struct XProjectArgs {  // a1 = from_ortho_x(D_x S_x phi)/sx, a2 = from_ortho_x(S
   int nx;
 };
 void launch_x_project(const XProjectArgs& a, cudaStream_t s);
+
+struct XFdctArgs {  // out = scale * cut_x(F_x conv): forward DCT-x + dealias (navier.rs:1028) + the -dt of navier.rs:630
+  Mat conv;          // [nx, ny] after the y-forward transform
+  Mat out;           // [nx, ny]
+  int cut;           // first zeroed x mode
+  double scale;
+  DctTab t;
+};
+struct XFdctArgs3 {
+  XFdctArgs a[3];
+  int next_wave;
+};
+void launch_x_fdct(const XFdctArgs3& a, int nbatch, cudaStream_t s);
+
+// ---- streaming column scans along x (fast_xs.cu): no tile, a block owns 8 adjacent columns ----
+bool xs_supported(int n0);
+ScanShape xs_scan_shape();  // scan shape of every chunk-major table these kernels read
+struct XsRhsAdiArgs {  // rhs assembly (navier.rs:622-674) + x half of HholtzAdi (hholtz_adi.rs:108,128)
+  Mat chat;            // [nx, ny]: -dt * dealiased convection term (XFdctArgs.out)
+  Mat rhs;             // [nx, ny] scratch (may alias chat)
+  Mat out;             // [mx, ny]
+  Mat fld;             // [mx, my] old composite coefficients: + S_x S_y fld
+  const double *fxsd, *fxsl, *fysd, *fysl;
+  int mode;            // 0: + dxp ; 1: - dt dyp + dt (S_x S_y tmp + tbc) ; 2: + bcdiff
+  Mat dxp, dyp, tmp, tbc, bcdiff;
+  const double *txsd, *txsl, *tysd, *tysl;
+  double dt;
+  const double *pt1, *pt2;  // chunk-major packed tables (xs_scan_shape): {b2 lo, di, up, f.fp}, {f.bs, bp1, bp2, 0}
+  int nx;
+};
+struct XsRhsAdiArgs3 {
+  XsRhsAdiArgs a[3];
+};
+void launch_xs_rhs_adi(const XsRhsAdiArgs3& a, int nbatch, cudaStream_t s);
+struct XsProjectArgs {  // a1 = from_ortho_x(D_x S_x phi)/sx, a2 = from_ortho_x(S_x phi)
+  Mat phi;              // [mx, my]
+  Mat p, d;             // [nx, my] scratch
+  Mat a1, a2;           // [mx, my]
+  const double *nsd, *nsl;
+  TdmaTabs t;           // pf / pb in xs_scan_shape
+  double isx;
+  int nx;
+};
+void launch_xs_project(const XsProjectArgs& a, cudaStream_t s);
+struct XsDiffArgs {  // dst = sc * D_x src along x
+  Mat src, dst;      // [nx, cols]
+  double sc;
+  int nx;
+};
+void launch_xs_dxp(const XsDiffArgs& a, cudaStream_t s);
 
 struct XAdiArgs {  // x half of a stand-alone HholtzAdi::solve: out = Fdma_x(B2_x in)
   Mat in;          // [nx, cols]

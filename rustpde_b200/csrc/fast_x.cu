@@ -252,6 +252,37 @@ __global__ void __launch_bounds__(XCfg<LOG2LB>::NTHR, XCfg<LOG2LB>::MINB) xk_for
     xk_forward_body<LOG2LB>(a3.a[2], a3);
 }
 
+// forward DCT-x + dealias cut + scale only: the rhs assembly and the x sweeps run as streaming column scans (fast_xs.cu)
+template <int LOG2LB>
+FK_DEV void xk_fdct_body(const XFdctArgs& a, const XFdctArgs3& a3) {
+  typedef XCfg<LOG2LB> C;
+  constexpr int LR = C::LR;
+  RP_DYN_SMEM(double, ta_);
+  cplx* ta = (cplx*)ta_;
+  cplx* tw = ta + C::AROWS * 2;
+  double* red = (double*)(tw + C::LB * 2);
+  const int c0 = blockIdx.x * LR, col = c0 + 2 * (threadIdx.x & 1), c = threadIdx.x & 1;
+  const int n = a.t.n, N = n - 1;
+  xfill<C::NTHR>(ta, n, [&](int i) { return ld2(a.conv, i, col); });
+  {  // first strip of the block that runs on this SM next -> L2
+    const int nxt = blockIdx.y * gridDim.x + blockIdx.x + a3.next_wave;
+    if (nxt < (int)(gridDim.x * gridDim.y)) xprefetch<C::NTHR, false>(a3.a[nxt / gridDim.x].conv, (nxt % gridDim.x) * LR, n);
+  }
+  __syncthreads();
+  dct_bluestein<2, LOG2LB, C::NTHR, false>((const double*)ta, (double*)tw, a.t, red);
+  for (int i = threadIdx.x >> 1; i < n; i += C::NTHR / 2)
+    st2(a.out, i, col, (i < a.cut) ? cscale(tw[cidx<2>(rowof(N, i), c)], a.scale) : mk(0.0, 0.0));
+}
+template <int LOG2LB>
+__global__ void __launch_bounds__(XCfg<LOG2LB>::NTHR, XCfg<LOG2LB>::MINB) xk_fdct(XFdctArgs3 a3) {
+  if (blockIdx.y == 0)
+    xk_fdct_body<LOG2LB>(a3.a[0], a3);
+  else if (blockIdx.y == 1)
+    xk_fdct_body<LOG2LB>(a3.a[1], a3);
+  else
+    xk_fdct_body<LOG2LB>(a3.a[2], a3);
+}
+
 template <int LOG2LB>
 __global__ void __launch_bounds__(XCfg<LOG2LB>::NTHR, XCfg<LOG2LB>::MINB) xk_div(XDivArgs a) {
   typedef XCfg<LOG2LB> C;
@@ -394,6 +425,7 @@ static void set_smem(K kern, int bytes) {
 #define XK_CASE_xk_div(L, LCV) XK_CASE_BODY(xk_div, L, LCV, C::SMEM_AA)
 #define XK_CASE_xk_project(L, LCV) XK_CASE_BODY(xk_project, L, LCV, C::SMEM_AA)
 #define XK_CASE_xk_adi(L, LCV) XK_CASE_BODY(xk_adi, L, LCV, C::SMEM_AA)
+#define XK_CASE_xk_fdct(L, LCV) XK_CASE_BODY(xk_fdct, L, LCV, C::SMEM_AW)
 
 #define XK_LAUNCH(kern, ncols, nx, nby)                                            \
   do {                                                                             \
@@ -437,6 +469,11 @@ void launch_x_forward(const XForwardArgs3& a_, int nb, cudaStream_t s) {
   XForwardArgs3 a = a_;
   a.next_wave = sm_count();
   XK_LAUNCH(xk_forward, a.a[0].conv.cols, a.a[0].t.n, nb);
+}
+void launch_x_fdct(const XFdctArgs3& a_, int nb, cudaStream_t s) {
+  XFdctArgs3 a = a_;
+  a.next_wave = sm_count();
+  XK_LAUNCH(xk_fdct, a.a[0].conv.cols, a.a[0].t.n, nb);
 }
 void launch_x_div(const XDivArgs& a, cudaStream_t s) { XK_LAUNCH(xk_div, a.vx.cols, a.nx, 1); }
 void launch_x_project(const XProjectArgs& a, cudaStream_t s) { XK_LAUNCH(xk_project, a.phi.cols, a.nx, 1); }

@@ -280,6 +280,7 @@ class Navier2D {
   Arr chat_[3];                  // conv after x-forward (periodic: complex (mk x ny))
   Arr w_[3];                     // after x-part of the implicit solve     [mx x ny]
   Arr vx_, ey_, div_, r1_, g_, h_, dyp_;
+  Arr dxp_, xs_p_, xs_d_;        // -dt/sx d/dx pres; scratch of the column-scan projection  (confined, fast_xs.cu)
   Arr tbc_ortho_, dxtbc_, dytbc_, bcdiff_;
   std::vector<Built> step_;      // programs of one update() in launch order
   struct StepOp {

@@ -78,6 +78,11 @@ Navier2D::Navier2D(int nx_, int ny_, double ra_, double pr_, double dt_, double 
   dxtbc_.alloc(nx, ny, false);
   dytbc_.alloc(nx, ny, false);
   bcdiff_.alloc(ox, ny, periodic);
+  if (!periodic) {
+    dxp_.alloc(nx, ny, false);
+    xs_p_.alloc(nx, my, false);
+    xs_d_.alloc(nx, my, false);
+  }
   red_ = DevBuf(sizeof(double) * RP_WSUM_DOUBLES);
   // navier.rs:301 / 461: Rayleigh-Benard boundary field, T = +0.5 at y=-1, -0.5 at y=+1
   // (bc_rbc 314-332, bc_rbc_periodic 474-492): in the ortho basis only T_1(y) is present.
@@ -626,7 +631,47 @@ void Navier2D::build_step_confined_fast() {
     add_fast("conv_y_forward", 17 * fb, [this, a3]() { fk::launch_y_conv(a3, 3, stream); });
   }
   // ---- 4. x-forward + dealias + rhs assembly + x half of HholtzAdi ---------
-  {
+  const char* nxs = getenv("RUSTPDE_B200_NO_XS");
+  const bool use_xs = fk::xs_supported(nx) && !(nxs && nxs[0] == '1');
+  if (use_xs) {
+    // forward DCT-x (tile kernel) -> chat = -dt * cut(F_x conv); then rhs assembly + B2_x + Fdma_x as streaming column scans
+    fk::XFdctArgs3 d3;
+    fk::XsRhsAdiArgs3 a3;
+    for (int f = 0; f < 3; ++f) {
+      fk::XFdctArgs& d = d3.a[f];
+      d.conv = mat_of(bconv_[f]);
+      d.out = mat_of(chat_[f]);
+      d.cut = dealias ? (nx * 2) / 3 : nx;  // navier.rs:1028
+      d.scale = -dt;
+      d.t = dct_of(bxo);
+      fk::XsRhsAdiArgs& a = a3.a[f];
+      a.chat = mat_of(chat_[f]);
+      a.rhs = mat_of(chat_[f]);  // in place
+      a.out = mat_of(w_[f]);
+      a.fld = mat_of(flds[f]->vhat);
+      a.fxsd = bxs[f]->d_sd.as<double>(), a.fxsl = bxs[f]->d_sl.as<double>();
+      a.fysd = bys[f]->d_sd.as<double>(), a.fysl = bys[f]->d_sl.as<double>();
+      a.mode = f;
+      a.dxp = mat_of(dxp_);
+      a.dyp = mat_of(dyp_);
+      a.tmp = mat_of(temp->vhat);
+      a.tbc = mat_of(tbc_ortho_);
+      a.bcdiff = mat_of(bcdiff_);
+      a.txsd = bxt.d_sd.as<double>(), a.txsl = bxt.d_sl.as<double>();
+      a.tysd = byt.d_sd.as<double>(), a.tysl = byt.d_sl.as<double>();
+      a.dt = dt;
+      a.nx = nx;
+      const FdmaDev& fd = solver[f]->adi[0].fdma;
+      const int m = nx - 2;
+      const fk::ScanShape sh = fk::xs_scan_shape();
+      perm_.push_back(upload(fk::perm_table(m, true, sh, 4, {host_of(bxo.d_b2lo), host_of(bxo.d_b2di), host_of(bxo.d_b2up), host_of(fd.fp)}, {0, 0, 0, 0})));
+      a.pt1 = perm_.back().as<double>();
+      perm_.push_back(upload(fk::perm_table(m, false, sh, 4, {host_of(fd.bs), host_of(fd.bp1), host_of(fd.bp2)}, {0, 0, 0})));
+      a.pt2 = perm_.back().as<double>();
+    }
+    add_fast("x_forward_dct", 6 * fb, [this, d3]() { fk::launch_x_fdct(d3, 3, stream); });
+    add_fast("rhs_adi_x", 14 * fb, [this, a3]() { fk::launch_xs_rhs_adi(a3, 3, stream); });
+  } else {
     fk::XForwardArgs3 a3;
     for (int f = 0; f < 3; ++f) {
       fk::XForwardArgs& a = a3.a[f];
@@ -696,7 +741,10 @@ void Navier2D::build_step_confined_fast() {
     a.isx = isx;
     a.b2 = b2_of(bxo);
     a.nx = nx;
-    add_fast("divergence_b2x", 4 * fb, [this, a]() { fk::launch_x_div(a, stream); });
+    if (use_xs)
+      add_fast("divergence_b2x", 4 * fb, [this, a]() { fk::launch_xs_div(a, stream); });
+    else
+      add_fast("divergence_b2x", 4 * fb, [this, a]() { fk::launch_x_div(a, stream); });
   }
   // ---- 7-9. fast diagonalisation: P., per-mode Fdma_y, Q. (poisson.rs:131-149)
   ops_.push_back(StepOp{1, 0});
@@ -714,7 +762,16 @@ void Navier2D::build_step_confined_fast() {
   ops_.push_back(StepOp{3, 0});  // pres[1].vhat[[0,0]] = 0   (navier.rs:714)
   opinfo_.push_back(OpInfo{"zero_mode00", 8.0, 0.0});
   // ---- 10-11. projection (navier.rs:683-695) --------------------------------
-  {
+  if (use_xs) {
+    fk::XsProjectArgs a;
+    a.phi = mat_of(pres1->vhat), a.a1 = mat_of(a1_), a.a2 = mat_of(a2_);
+    a.p = mat_of(xs_p_), a.d = mat_of(xs_d_);
+    a.nsd = bxn.d_sd.as<double>(), a.nsl = bxn.d_sl.as<double>();
+    a.t = tdma_of(bxu, nx, fk::xs_scan_shape());
+    a.isx = isx;
+    a.nx = nx;
+    add_fast("project_x", 3 * fb, [this, a]() { fk::launch_xs_project(a, stream); });
+  } else {
     fk::XProjectArgs a;
     a.phi = mat_of(pres1->vhat), a.a1 = mat_of(a1_), a.a2 = mat_of(a2_);
     a.nsd = bxn.d_sd.as<double>(), a.nsl = bxn.d_sl.as<double>();
@@ -742,10 +799,19 @@ void Navier2D::build_step_confined_fast() {
     a.ny = ny;
     a.only_dyp = 0;
     add_fast("pressure_update", 5 * fb, [this, a]() { fk::launch_y_pres(a, stream); });
-    // the same kernel refreshes d/dy pres after the pressure was rewritten from outside (update())
+    // - dt/sx d/dx pres of the next step's ux rhs (navier.rs:627), as a column scan
+    fk::XsDiffArgs dx;
+    dx.src = mat_of(pres0->vhat), dx.dst = mat_of(dxp_);
+    dx.sc = -dt * isx;
+    dx.nx = nx;
+    if (use_xs) add_fast("pressure_dx", 2 * fb, [this, dx]() { fk::launch_xs_dxp(dx, stream); });
+    // the same kernels refresh the pressure gradients after the pressure was rewritten from outside (update())
     fk::YPresArgs r = a;
     r.only_dyp = 1;
-    fast_dyp_ = [this, r]() { fk::launch_y_pres(r, stream); };
+    fast_dyp_ = [this, r, dx, use_xs]() {
+      fk::launch_y_pres(r, stream);
+      if (use_xs) fk::launch_xs_dxp(dx, stream);
+    };
     // |div u| of the current velocity for exit() (navier.rs:855-879): y parts, then the divergence kernel of the step
     fk::YDivPrepArgs dp;
     dp.ux = mat_of(ux->vhat), dp.uy = mat_of(uy->vhat), dp.vx = mat_of(vx_), dp.ey = mat_of(ey_);
@@ -757,9 +823,12 @@ void Navier2D::build_step_confined_fast() {
     xd.isx = isx;
     xd.b2 = b2_of(bxo);
     xd.nx = nx;
-    fast_div_ = [this, dp, xd]() {
+    fast_div_ = [this, dp, xd, use_xs]() {
       fk::launch_y_divprep(dp, stream);
-      fk::launch_x_div(xd, stream);
+      if (use_xs)
+        fk::launch_xs_div(xd, stream);
+      else
+        fk::launch_x_div(xd, stream);
     };
   }
   (void)my;
