@@ -124,6 +124,10 @@ int rp_navier_set_velocity(rp_navier_t* h, double amp, double m, double n);    /
 int rp_navier_set_temperature(rp_navier_t* h, double amp, double m, double n); /* 934-936 */
 int rp_navier_set_tempbc_ortho(rp_navier_t* h, const double* that_bc, size_t len); /* set_temp_bc, 517-519 (ortho coefficients) */
 int rp_navier_set_dealias(rp_navier_t* h, int on);                             /* pub dealias */
+/* pub solid = Some([mask, value]) (navier.rs:191, solid_masks.rs:34-175): volume penalisation -1/eta * mask * (u - value),
+ * eta = 1e-2 (navier.rs:552-608); both [nx, ny] on the physical grid, value may be NULL (zeros), mask NULL switches it off.
+ * Before the first update(); specialised kernels only. */
+int rp_navier_set_solid(rp_navier_t* h, const double* mask, const double* value, size_t len);
 int rp_navier_update(rp_navier_t* h, int nsteps);                              /* Integrate::update, 737-765 (x nsteps, asynchronous) */
 int rp_navier_sync(rp_navier_t* h);
 /* Double-buffered upload of the pub `vhat` arrays of temp, ux, uy, pres[0] (navier.rs:153-160; what `read()`

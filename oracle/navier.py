@@ -139,6 +139,8 @@ class Navier2D:
         self.ra, self.pr, self.dt = ra, pr, dt
         self.time = 0.0
         self.dealias = True
+        self.solid = None        # [mask, value] (navier.rs:191, solid_masks.rs)
+        self.statistics = None   # navier.rs:195
         self.diagnostics = {"time": [], "Nu": [], "Nuvol": [], "Re": []}
         # navier.rs:502-514 _scale
         for f in (self.temp, self.ux, self.uy, self.pres[0]):
@@ -184,6 +186,10 @@ class Navier2D:
     def reset_time(self):
         self.time = 0.0
 
+    def new_work_field(self):
+        """Field2::new(&navier.field.space) (statistics.rs:60-65)."""
+        return Field2(self.field.space)
+
     # ---- convection, navier.rs:538-616 -----------------------------------
     def _finish_conv(self, conv):
         self.field.v = conv
@@ -198,16 +204,28 @@ class Navier2D:
         if self.fieldbc is not None:
             conv = conv + conv_term(self.fieldbc, self.field, ux, [1, 0], self.scale)
             conv = conv + conv_term(self.fieldbc, self.field, uy, [0, 1], self.scale)
+        if self.solid is not None:  # navier.rs:552-560: volume penalisation, eta = 1e-2
+            eta = 1e-2
+            self.temp.backward()
+            if self.fieldbc is None:
+                damp = -1.0 / eta * self.solid[0] * (self.temp.v - self.solid[1])
+            else:
+                damp = -1.0 / eta * self.solid[0] * (self.temp.v + self.fieldbc.v - self.solid[1])
+            conv = conv - damp
         return self._finish_conv(conv)
 
     def conv_ux(self, ux, uy):
         conv = conv_term(self.ux, self.field, ux, [1, 0], self.scale)
         conv = conv + conv_term(self.ux, self.field, uy, [0, 1], self.scale)
+        if self.solid is not None:  # navier.rs:580-584
+            conv = conv - (-1.0 / 1e-2 * self.solid[0] * ux)
         return self._finish_conv(conv)
 
     def conv_uy(self, ux, uy):
         conv = conv_term(self.uy, self.field, ux, [1, 0], self.scale)
         conv = conv + conv_term(self.uy, self.field, uy, [0, 1], self.scale)
+        if self.solid is not None:  # navier.rs:604-608
+            conv = conv - (-1.0 / 1e-2 * self.solid[0] * uy)
         return self._finish_conv(conv)
 
     # ---- implicit solves, navier.rs:622-674 ------------------------------

@@ -100,6 +100,7 @@ extern "C" {
     fn rp_navier_set_temperature(h: *mut rp_navier_t, amp: c_double, m: c_double, n: c_double) -> c_int;
     fn rp_navier_set_tempbc_ortho(h: *mut rp_navier_t, that_bc: *const c_double, len: usize) -> c_int;
     fn rp_navier_set_dealias(h: *mut rp_navier_t, on: c_int) -> c_int;
+    fn rp_navier_set_solid(h: *mut rp_navier_t, mask: *const c_double, value: *const c_double, len: usize) -> c_int;
     fn rp_navier_update(h: *mut rp_navier_t, nsteps: c_int) -> c_int;
     fn rp_navier_sync(h: *mut rp_navier_t) -> c_int;
     fn rp_navier_stage_state(h: *mut rp_navier_t, temp: *const c_double, n_temp: usize, ux: *const c_double, n_ux: usize,
@@ -708,6 +709,17 @@ impl<T: SpectralScalar> Navier2D<T> {
     }
     pub fn dealias(&self) -> bool {
         self.dealias
+    }
+    /// pub `solid = Some([mask, value])` (navier.rs:191): volume penalisation masks on the physical grid
+    /// (solid_masks.rs:34-175); before the first `update()`
+    pub fn set_solid(&mut self, solid: Option<&[Array2<f64>; 2]>) {
+        match solid {
+            Some(s) => {
+                let (m, v) = (s[0].as_standard_layout(), s[1].as_standard_layout());
+                unsafe { check(rp_navier_set_solid(self.h, m.as_ptr(), v.as_ptr(), m.len())) }
+            }
+            None => unsafe { check(rp_navier_set_solid(self.h, std::ptr::null(), std::ptr::null(), 0)) },
+        }
     }
     /// `reset_time()` (navier.rs:951-953)
     pub fn reset_time(&mut self) {

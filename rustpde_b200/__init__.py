@@ -22,8 +22,16 @@ from .api import (  # noqa: F401
     fourier_r2c,
     integrate,
 )
+from .solid_masks import (  # noqa: F401
+    Statistics,
+    solid_cylinder_inner,
+    solid_porosity,
+    solid_porosity_interpolate,
+    solid_roughness_sinusoid,
+)
 
 __all__ = [
     "Base", "Field2", "Hholtz", "HholtzAdi", "Navier2D", "Poisson", "RustpdeError", "Space2",
     "cheb_dirichlet", "cheb_dirichlet_bc", "cheb_neumann", "cheb_neumann_bc", "chebyshev", "fourier_r2c", "integrate",
+    "Statistics", "solid_cylinder_inner", "solid_porosity", "solid_porosity_interpolate", "solid_roughness_sinusoid",
 ]

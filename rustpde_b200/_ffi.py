@@ -61,6 +61,7 @@ _SIGS = {
     "rp_navier_set_temperature": [vp, C.c_double, C.c_double, C.c_double],
     "rp_navier_set_tempbc_ortho": [vp, c_double_p, C.c_size_t],
     "rp_navier_set_dealias": [vp, C.c_int],
+    "rp_navier_set_solid": [vp, c_double_p, c_double_p, C.c_size_t],
     "rp_navier_update": [vp, C.c_int],
     "rp_navier_stage_state": [vp, c_double_p, C.c_size_t, c_double_p, C.c_size_t, c_double_p, C.c_size_t, c_double_p, C.c_size_t],
     "rp_navier_commit_staged": [vp],

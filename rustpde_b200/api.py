@@ -347,7 +347,7 @@ class Navier2D:
         s.field = flds[5]
         s.diagnostics = {"time": [], "Nu": [], "Nuvol": [], "Re": []}
         s.write_intervall = None
-        s.solid = None
+        s._solid = None
         s.statistics = None
         s._dealias = True
         return s
@@ -391,6 +391,33 @@ class Navier2D:
     def set_temp_bc_ortho(self, that_bc):  # set_temp_bc, navier.rs:517-519 (ortho coefficients)
         a, flat = _as_f64(that_bc, self.periodic)
         self._lib.call("rp_navier_set_tempbc_ortho", self._h, _dp(flat), flat.size)
+
+    @property
+    def solid(self):
+        return self._solid
+
+    @solid.setter
+    def solid(self, mask_value):
+        """navier.solid = Some([mask, value]) (navier.rs:191; generators: rustpde_b200.solid_masks)."""
+        if mask_value is None:
+            self._lib.call("rp_navier_set_solid", self._h, None, None, 0)
+            self._solid = None
+            return
+        mask, value = (np.ascontiguousarray(a, dtype=np.float64) for a in mask_value)
+        if mask.shape != (self.nx, self.ny) or value.shape != mask.shape:
+            raise RustpdeError(2, "solid: mask / value must be [nx, ny]")
+        self._lib.call("rp_navier_set_solid", self._h, _dp(mask.reshape(-1)), _dp(value.reshape(-1)), mask.size)
+        self._solid = [mask, value]
+
+    def new_work_field(self):
+        """Field2::new(&navier.field.space) (statistics.rs:60-65)."""
+        return Field2(self.field.space, lib=self._lib)
+
+    def tempbc_ortho(self):
+        """fieldbc.to_ortho(): the Rayleigh-Benard boundary field of navier.rs:314-332 / 474-492 (only T_1(y) is present)."""
+        a = np.zeros(self.field.shape_spectral, dtype=self.field.spectral_dtype)
+        a[0, 1] = -0.5 * self.nx if self.periodic else -0.5  # the r2c forward transform is unnormalised
+        return a
 
     def reset_time(self):  # navier.rs:951-953
         self._lib.call("rp_navier_reset_time", self._h)
@@ -509,6 +536,12 @@ class Navier2D:
         dt_save = self.write_intervall
         if dt_save is None or (t % dt_save) < self.dt / 2.0 or (t % dt_save) > dt_save - self.dt / 2.0:
             self.write(fname)
+        st = self.statistics
+        if st is not None:  # navier.rs:795-815
+            if (t % st.save_stat) < self.dt / 2.0 or (t % st.save_stat) > st.save_stat - self.dt / 2.0:
+                st.update(self.temp.to_ortho() + self.tempbc_ortho(), self.ux.to_ortho(), self.uy.to_ortho(), t)
+            if (t % st.write_stat) < self.dt / 2.0 or (t % st.write_stat) > st.write_stat - self.dt / 2.0:
+                st.write(os.path.join(data_dir, "statistics.rpsnap"))
         nu, nuvol, re, div, _ = self.eval(True, True, True, True, False)
         print("time = %4.2f      |div| = %4.2e     Nu = %5.3e     Nuv = %5.3e    Re = %5.3e" % (t, div, nu, nuvol, re))
         with open(os.path.join(data_dir, "info.txt"), "a") as f:  # navier.rs:843-852

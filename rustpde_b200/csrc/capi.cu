@@ -365,6 +365,12 @@ int rp_navier_set_tempbc_ortho(rp_navier_t* h, const double* tb, size_t len) {
     N.set_tempbc_ortho(tb);
   });
 }
+int rp_navier_set_solid(rp_navier_t* h, const double* mask, const double* value, size_t len) {
+  NAV_GUARD({
+    need(mask == nullptr || len == (size_t)N.nx * N.ny, RP_ERR_SHAPE, "set_solid: size mismatch");
+    N.set_solid(mask, value);
+  });
+}
 int rp_navier_set_dealias(rp_navier_t* h, int on) {
   NAV_GUARD({
     need(N.launches_per_step() == 0, RP_ERR_INVALID, "set_dealias must be called before the first update()");

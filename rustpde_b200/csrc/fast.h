@@ -100,6 +100,9 @@ void launch_y_backward(const YBackwardArgs3& a, int nbatch, cudaStream_t s);  //
 
 struct YConvArgs {  // out = cut_y(F_y(u * (du + bcx) + v * (dv + bcy)))   (conv_term.rs:41)
   Mat u, du, v, dv, bcx, bcy;  // bcx/bcy.p may be null
+  // solid-mask volume penalisation (navier.rs:552-560, 580-584, 604-608): + ieta * mask * (w + wbc - sval); mask.p may be null
+  Mat mask, sval, w, wbc;      // w: the field's own physical value; wbc: physical boundary field (temperature) or null
+  double ieta;
   Mat out;
   int cut;  // first zeroed y mode (navier.rs:1029), >= ny: none
   DctTab t;

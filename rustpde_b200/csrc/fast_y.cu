@@ -62,7 +62,7 @@ FK_DEV void yk_conv_body(const YConvArgs& a, const YConvArgs3& a3) {
   YK_SMEM(td, red);
   const int r0 = blockIdx.x * C::LR;
   constexpr int n = C::n, N = C::N;
-  const bool has_bc = a.bcx.p != nullptr;
+  const bool has_bc = a.bcx.p != nullptr, has_solid = a.mask.p != nullptr;
   tile_fill<LC, C::NTHR>(td, n, [&](int j, int l) {
     const int r = min(r0 + l, a.u.rows - 1);
     double gx = a.du.p[(size_t)r * a.du.ld + j], gy = a.dv.p[(size_t)r * a.dv.ld + j];
@@ -71,7 +71,13 @@ FK_DEV void yk_conv_body(const YConvArgs& a, const YConvArgs3& a3) {
       gx += a.bcx.p[(size_t)r * a.bcx.ld + j];
       gy += a.bcy.p[(size_t)r * a.bcy.ld + j];
     }
-    return (r0 + l < a.u.rows) ? fma(u, gx, v * gy) : 0.0;
+    double c = fma(u, gx, v * gy);
+    if (has_solid) {  // conv -= -1/eta * mask * (w [+ wbc] - value)
+      double w = a.w.p[(size_t)r * a.w.ld + j];
+      if (a.wbc.p) w += a.wbc.p[(size_t)r * a.wbc.ld + j];
+      c = fma(a.ieta * a.mask.p[(size_t)r * a.mask.ld + j], w - a.sval.p[(size_t)r * a.sval.ld + j], c);
+    }
+    return (r0 + l < a.u.rows) ? c : 0.0;
   });
   __syncthreads();
   dct_pow2<LC, LOG2L, C::NTHR, false>(td, a.t, red);

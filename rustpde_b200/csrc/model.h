@@ -201,6 +201,7 @@ class Navier2D {
   void set_velocity(double amp, double m, double n);
   void set_temperature(double amp, double m, double n);
   void set_tempbc_ortho(const double* that_bc);  // ortho coefficients of the BC field (o0 x o1 [x2])
+  void set_solid(const double* mask, const double* value);  // [nx, ny] each; mask == nullptr: none
   void update(int nsteps);
   void eval(double* nu, double* nuvol, double* re, double* div_norm, double* ekin);
   void sync();
@@ -280,6 +281,10 @@ class Navier2D {
   Arr chat_[3];                  // conv after x-forward (periodic: complex (mk x ny))
   Arr w_[3];                     // after x-part of the implicit solve     [mx x ny]
   Arr vx_, ey_, div_, r1_, g_, h_, dyp_;
+  Arr solid_mask_, solid_val_, phys_t_, tbc_phys_, zero_phys_;  // solid-mask penalisation (navier.rs:552-608)
+  bool has_solid_ = false;
+  void set_solid_args(fk::YConvArgs& a, int f);
+  const Arr& zero_phys();
   Arr dxp_, xs_p_, xs_d_;        // -dt/sx d/dx pres; scratch of the column-scan projection  (confined, fast_xs.cu)
   Arr tbc_ortho_, dxtbc_, dytbc_, bcdiff_;
   std::vector<Built> step_;      // programs of one update() in launch order

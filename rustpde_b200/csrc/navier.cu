@@ -217,6 +217,49 @@ void Navier2D::set_tempbc_ortho(const double* that_bc) {
   rebuild_bc();
 }
 
+// navier.solid = Some([mask, value]) (navier.rs:191; solid_masks.rs): must be set before the first update()
+void Navier2D::set_solid(const double* mask, const double* value) {
+  if (!ops_.empty()) throw Error(RP_ERR_INVALID, "set_solid must be called before the first update()");
+  has_solid_ = mask != nullptr;
+  if (!has_solid_) return;
+  if (!solid_mask_.buf.p) {
+    solid_mask_.alloc(nx, ny, false);
+    solid_val_.alloc(nx, ny, false);
+    phys_t_.alloc(nx, ny, false);
+    tbc_phys_.alloc(nx, ny, false);
+  }
+  solid_mask_.upload(mask, stream);
+  if (value)
+    solid_val_.upload(value, stream);
+  else
+    solid_val_.zero(stream);
+  // physical boundary field (fieldbc.v): backward of its ortho coefficients through the work field
+  field->stream = stream;
+  copy_bc_to_field();
+  field->backward();
+  copy_arr(tbc_phys_, field->v, stream);
+  rt::sync(stream);
+}
+// penalisation term of field f (0 ux, 1 uy, 2 temp) in the fused product kernel
+void Navier2D::set_solid_args(fk::YConvArgs& a, int f) {
+  const fk::Mat none{nullptr, 0, 0, 0};
+  a.mask = a.sval = a.w = a.wbc = none;
+  a.ieta = 1.0 / 1e-2;  // eta = 1e-2 (navier.rs:553)
+  if (!has_solid_) return;
+  auto m = [](const Arr& x) { return fk::Mat{x.d(), x.ld, x.rows, x.cols}; };
+  a.mask = m(solid_mask_);
+  a.sval = f == 2 ? m(solid_val_) : m(zero_phys());
+  a.w = f == 0 ? m(phys_[0]) : (f == 1 ? m(phys_[1]) : m(phys_t_));
+  if (f == 2) a.wbc = m(tbc_phys_);
+}
+const Arr& Navier2D::zero_phys() {
+  if (!zero_phys_.buf.p) {
+    zero_phys_.alloc(nx, ny, false);
+    zero_phys_.zero(stream);
+  }
+  return zero_phys_;
+}
+
 void Navier2D::copy_bc_to_field() { copy_arr(field->vhat, tbc_ortho_, stream); }
 
 // Time-invariant pieces of the boundary field (navier.rs:547-550, 665-668)
@@ -274,6 +317,8 @@ void Navier2D::set_temperature(double amp, double m, double n) {  // navier.rs:9
 void Navier2D::build_step() {
   if (!ops_.empty()) return;
   fk::apply_kflags();
+  if (has_solid_ && !(fk::y_supported(ny) && (periodic ? fk::px_supported(nx) : fk::x_supported(nx))))
+    throw Error(RP_ERR_INVALID, "solid masks are implemented on the specialised kernels only (ny = 2^k + 1, see rp_navier_kernel_path)");
   const char* nf = getenv("RUSTPDE_B200_NO_FAST");
   const bool fast_ok = !(nf && nf[0] == '1');
   if (periodic && fast_ok && fk::px_supported(nx) && fk::y_supported(ny))
@@ -603,7 +648,7 @@ void Navier2D::build_step_confined_fast() {
       fk::YBackwardArgs& a = a3.a[f];
       a.a = mat_of(ax_[f]);
       a.adx = mat_of(adx_[f]);
-      a.val = val_idx[f] >= 0 ? mat_of(phys_[val_idx[f]]) : fk::Mat{nullptr, 0, 0, 0};
+      a.val = val_idx[f] >= 0 ? mat_of(phys_[val_idx[f]]) : (has_solid_ ? mat_of(phys_t_) : fk::Mat{nullptr, 0, 0, 0});
       a.dy = mat_of(phys_[dy_idx[f]]);
       a.dx = mat_of(phys_[dx_idx[f]]);
       a.sd = bys[f]->d_sd.as<double>();
@@ -624,6 +669,7 @@ void Navier2D::build_step_confined_fast() {
       a.dv = mat_of(phys_[dy_idx[f]]);
       a.bcx = f == 2 ? mat_of(dxtbc_) : fk::Mat{nullptr, 0, 0, 0};
       a.bcy = f == 2 ? mat_of(dytbc_) : fk::Mat{nullptr, 0, 0, 0};
+      set_solid_args(a, f);
       a.out = mat_of(bconv_[f]);
       a.cut = dealias ? (ny * 2) / 3 : ny;  // navier.rs:1029
       a.t = dct_of(byo);
@@ -631,8 +677,10 @@ void Navier2D::build_step_confined_fast() {
     add_fast("conv_y_forward", 17 * fb, [this, a3]() { fk::launch_y_conv(a3, 3, stream); });
   }
   // ---- 4. x-forward + dealias + rhs assembly + x half of HholtzAdi ---------
-  const char* nxs = getenv("RUSTPDE_B200_NO_XS");
-  const bool use_xs = fk::xs_supported(nx) && !(nxs && nxs[0] == '1');
+  // RUSTPDE_B200_XS=1: rhs assembly / x sweeps / divergence / projection as streaming column scans (fast_xs.cu) instead
+  // of the tile kernels -- measured equal within 2 % at 2048 x 2049, so the tile kernels stay the default
+  const char* nxs = getenv("RUSTPDE_B200_XS");
+  const bool use_xs = fk::xs_supported(nx) && nxs && nxs[0] == '1';
   if (use_xs) {
     // forward DCT-x (tile kernel) -> chat = -dt * cut(F_x conv); then rhs assembly + B2_x + Fdma_x as streaming column scans
     fk::XFdctArgs3 d3;
@@ -863,7 +911,7 @@ void Navier2D::build_step_periodic_fast() {
     for (int f = 0; f < 3; ++f) {
       fk::YBackwardArgs& a = a3.a[f];
       a.a = mat_of(ax_[f]), a.adx = mat_of(adx_[f]);
-      a.val = val_idx[f] >= 0 ? mat_of(phys_[val_idx[f]]) : none;
+      a.val = val_idx[f] >= 0 ? mat_of(phys_[val_idx[f]]) : (has_solid_ ? mat_of(phys_t_) : none);
       a.dy = mat_of(phys_[dy_idx[f]]), a.dx = mat_of(phys_[dx_idx[f]]);
       a.sd = bys[f]->d_sd.as<double>(), a.sl = bys[f]->d_sl.as<double>();
       a.isy = isy;
@@ -878,6 +926,7 @@ void Navier2D::build_step_periodic_fast() {
       a.u = mat_of(phys_[0]), a.du = mat_of(phys_[dx_idx[f]]), a.v = mat_of(phys_[1]), a.dv = mat_of(phys_[dy_idx[f]]);
       a.bcx = f == 2 ? mat_of(dxtbc_) : none;
       a.bcy = f == 2 ? mat_of(dytbc_) : none;
+      set_solid_args(a, f);
       a.out = mat_of(bconv_[f]);
       a.cut = dealias ? (ny * 2) / 3 : ny;
       a.t = dct_of(byo);
@@ -996,6 +1045,7 @@ void Navier2D::slab_phase1(int k0, int mkl, double* const out[6], int world, con
 void Navier2D::slab_phase2(int j0, int nyl, const double* const in[6], double* work, double* const out[3], int world,
                            const int* koff, double* const* peers) {
   if (!periodic || !fk::px_supported(nx)) throw Error(RP_ERR_INVALID, "slab phases need the specialised periodic kernels");
+  if (has_solid_) throw Error(RP_ERR_INVALID, "solid masks are not supported by the slab-decomposed step");
   const Base& bx = *ux->sp.b0;
   const int mk = nx / 2 + 1;
   const int dx_idx[3] = {2, 4, 6}, dy_idx[3] = {3, 5, 7};

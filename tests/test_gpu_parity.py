@@ -270,6 +270,34 @@ def test_host_api_additions_gpu(gpu):
     assert pc.check_host_api_additions(gpu, True, 128, 129)
 
 
+@pytest.mark.parametrize("periodic,nx,ny", [(False, 128, 129), (True, 128, 129)])
+def test_solid_masks_gpu(gpu, periodic, nx, ny):
+    """Volume penalisation (navier.rs:552-608) fused into the product kernel: fields <= 1e-9 against the oracle."""
+    from test_solid_stats import check_solid
+    check_solid(gpu, periodic, nx, ny, steps=10)
+
+
+def test_statistics_gpu(gpu, tmp_path):
+    from test_solid_stats import check_statistics
+    assert check_statistics(gpu, False, 128, 129, tmp_path)
+
+
+def test_navier_confined_column_scan_kernels(gpu, monkeypatch):
+    """RUSTPDE_B200_XS=1: the x-direction sweeps as streaming column scans (fast_xs.cu) -- same results as the tile
+    kernels to rounding, fields <= 1e-9 against the oracle."""
+    import rustpde_b200 as R
+    monkeypatch.setenv("RUSTPDE_B200_XS", "1")
+    for nx, ny, steps in ((64, 65, 20), (530, 129, 3), (2048, 2049, 2)):
+        ra, dt = (1e5, 0.01) if nx < 1000 else (1e9, 1e-4)
+        n = R.Navier2D.new(nx, ny, ra, 1.0, dt, 1.0, True, lib=gpu)
+        n.set_velocity(0.2, 1.0, 1.0)
+        n.set_temperature(0.2, 1.0, 1.0)
+        n.update(1)
+        assert n.launches_per_step() == 15  # 13 + the split forward DCT + d/dx pres
+        err, derr, dn, do = pc.check_navier_steps(gpu, False, nx, ny, steps, ra=ra, dt=dt, tol=1e-9, batch=2, own_eig=True)
+        assert max(derr) < 1e-9, (derr, dn, do)
+
+
 def test_graph_and_eager_agree(gpu):
     import rustpde_b200 as R
     outs = []
