@@ -77,12 +77,19 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def config_of(args, wl, world, **extra):
-    """Same keys in both arms (the driver compares the dicts)."""
-    cfg = {"workload": wl[8], "workload_name": args.workload, "grid": [wl[1], wl[2]],
-           "parallelism": extra.pop("parallelism", "1 GPU"), "l2": "working set >> 126 MB L2, no flush needed"}
-    cfg.update(extra)
-    return cfg
+def parallelism_of(args, wl, world):
+    if world <= 1 and args.parallel != "slab":
+        return "1 GPU"
+    if wl[0] and args.parallel != "replicas":
+        return "kx slabs x%d, 9 transposes per step, %s" % (
+            world, "fused into the kernels over NVLink peer memory (CUDA IPC)" if args.transport == "p2p" and world > 1 else "NCCL all_to_all")
+    return "replicas x%d" % world
+
+
+def config_of(args, wl, world):
+    """Identical in both arms (the driver compares the dicts); run-specific facts go to the top-level `run_info`."""
+    return {"workload": wl[8], "workload_name": args.workload, "grid": [wl[1], wl[2]], "parallelism": parallelism_of(args, wl, world),
+            "l2": "working set >> 126 MB L2, no flush needed"}
 
 
 class ClockSampler:
@@ -229,8 +236,8 @@ def run_reference(args, wl, rank, world):
         "impl": "reference", "metric": METRIC, "value": val, "unit": "steps/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 / val, "higher_is_better": True, "scaling": "strong" if slab else "weak",
         "vs_baseline": None, "dtype": "f64", "data": DATA,
-        "config": config_of(args, wl, world, parallelism="host CPU, %d threads" % threads,
-                            note="CPU restatement of rustpde (oracle/), not the rustpde binary: no Rust toolchain in this image"),
+        "config": config_of(args, wl, world),
+        "run_info": {"host_threads": threads, "note": "CPU restatement of rustpde (oracle/), not the rustpde binary: no Rust toolchain in this image"},
         "cpu_baseline": {"value": val, "unit": "steps/s", "cores": threads, "kind": "port", "sample": sample,
                          "openblas_num_threads": os.environ.get("OPENBLAS_NUM_THREADS")},
         "e2e": {"value": val, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -396,9 +403,8 @@ def run_slab(args, wl, rank, world, local_rank, torch, dist, lib, R, _ffi, np):
             "metric": METRIC, "value": steps_per_s, "unit": "steps/s", "n_gpus": world, "steps": args.steps, "warmup": W,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": DATA,
-            "config": config_of(args, wl, world, parallelism="kx slabs x%d, 9 transposes per step, %s" % (
-                world, "fused into the kernels over NVLink peer memory (CUDA IPC)" if slab.transport == "p2p" else "NCCL all_to_all"),
-                cuda_graph=False, setup_s=round(t_setup, 2), comm_nranks=world, transport=slab.transport),
+            "config": config_of(args, wl, world),
+            "run_info": {"cuda_graph": False, "setup_s": round(t_setup, 2), "comm_nranks": world, "transport": slab.transport},
             "speedup_vs_1gpu": ms_1gpu / (ms / args.steps), "ms_per_step_1gpu": ms_1gpu,
             "steps_per_s_1gpu": 1e3 / ms_1gpu, "slab_parity": parity,
             "clocks": clocks, "e2e": e2e, "gpu_launches": slab.launches_per_step * args.steps, "roofline": roof, "cpu_baseline": None,
@@ -468,8 +474,8 @@ def run_hholtz(args, wl, rank, world, local_rank, torch, lib, R, _ffi, np):
         "metric": METRIC, "value": K / (ms * 1e-3), "unit": "steps/s", "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": ms / K,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic (rhs = to_ortho(forward(cos(pi x/2) cos(pi y/2))), examples/hholtz_2d.rs)",
-        "config": config_of(args, wl, world, step="one Hholtz::solve (device-resident rhs)", setup_s=round(t_setup, 2),
-                            analytic_max_abs_err=err, kernel_path=info),
+        "config": config_of(args, wl, world),
+        "run_info": {"step": "one Hholtz::solve (device-resident rhs)", "setup_s": round(t_setup, 2), "analytic_max_abs_err": err, "kernel_path": info},
         "clocks": clocks,
         "e2e": {"value": ne / te, "unit": "steps/s", "h2d_bytes_per_step": rhs.size * 8, "d2h_bytes_per_step": sol.size * 8, "steps": ne,
                 "note": "rp_solver_solve with host rhs and host solution (pageable numpy buffers)"},
@@ -661,8 +667,8 @@ def run_ours(args, wl, rank, world, local_rank):
             "metric": METRIC, "value": steps_per_s, "unit": "steps/s", "n_gpus": world, "steps": args.steps, "warmup": W,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": DATA,
-            "config": config_of(args, wl, world, parallelism="replicas x%d" % world if world > 1 else "1 GPU", cuda_graph=True,
-                                setup_s=round(t_setup, 2), div_norm_after=div, kernel_path=list(nav.kernel_path())),
+            "config": config_of(args, wl, world),
+            "run_info": {"cuda_graph": True, "setup_s": round(t_setup, 2), "div_norm_after": div, "kernel_path": list(nav.kernel_path())},
             "clocks": clocks, "e2e": e2e, "e2e_resident": e2e_resident, "gpu_launches": launches * args.steps, "roofline": roof,
             "cpu_baseline": cpu,
         }
