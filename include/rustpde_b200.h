@@ -53,6 +53,7 @@ enum { RP_FIELD_TEMP = 0, RP_FIELD_UX = 1, RP_FIELD_UY = 2, RP_FIELD_PRES = 3, R
 typedef struct rp_field rp_field_t;
 typedef struct rp_solver rp_solver_t;
 typedef struct rp_navier rp_navier_t;
+typedef struct rp_adjoint rp_adjoint_t;
 
 /* ---- library ----------------------------------------------------------- */
 int rp_init(int device);                 /* selects the CUDA device, sets kernel attributes */
@@ -197,6 +198,25 @@ int rp_navier_kernel_path(rp_navier_t* h, int* specialised, int* split_gemm);
  * the name / algorithmic bytes / flops of launch i. */
 int rp_navier_profile(rp_navier_t* h, int reps, double* ms, size_t cap, int* nops);
 int rp_navier_op_info(rp_navier_t* h, int i, char* name, size_t name_len, double* bytes, double* flops);
+
+/* ---- Navier2DAdjoint (src/navier/navier_adjoint.rs:128-1068) --------------------- */
+/* Navier2DAdjoint::new (197) / new_periodic (361): steady-state adjoint descent; every update() runs one update() of an
+ * inner Navier2D (dt_navier = 1e-2), three Hholtz smoother solves and one pressure Poisson solve.  Fields start at zero. */
+int rp_adjoint_create(int nx, int ny, double ra, double pr, double dt, double aspect, int adiabatic, int periodic, rp_adjoint_t** out);
+int rp_adjoint_destroy(rp_adjoint_t* h);
+int rp_adjoint_set_velocity(rp_adjoint_t* h, double amp, double m, double n);     /* 994-999 */
+int rp_adjoint_set_temperature(rp_adjoint_t* h, double amp, double m, double n);  /* 1001-1003 */
+int rp_adjoint_update(rp_adjoint_t* h, int nsteps);                               /* Integrate::update, 778-805 */
+int rp_adjoint_get_time(rp_adjoint_t* h, double* time);
+int rp_adjoint_reset_time(rp_adjoint_t* h);                                       /* 1006-1009 */
+int rp_adjoint_eval(rp_adjoint_t* h, double* nu, double* nuvol, double* re, double* div_norm); /* 952-992; any pointer may be NULL */
+/* |.|_2 of the smoothed residual fields ux[1], uy[1], temp[1] (what exit() sums, 903-906) and of the unsmoothed ones (868-870) */
+int rp_adjoint_residuals(rp_adjoint_t* h, double smooth[3], double unsmooth[3]);
+int rp_adjoint_exit(rp_adjoint_t* h, int* stop);                                  /* 892-910: NaN or residual < 1e-8 */
+/* borrowed handles: fields 0 temp, 1 ux, 2 uy, 3 pres, 4 pseudo pressure, 5 / 6 / 7 residual temp / ux / uy;
+ * solvers 0 smoother of ux and uy, 1 smoother of temp, 2 pressure Poisson, 3 the inner Navier2D's Poisson (for export_eig) */
+int rp_adjoint_field(rp_adjoint_t* h, int which, rp_field_t** out);
+int rp_adjoint_solver(rp_adjoint_t* h, int which, rp_solver_t** out);
 
 #ifdef __cplusplus
 }

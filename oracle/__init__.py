@@ -50,4 +50,5 @@ from .solver import (  # noqa: F401
     inv,
 )
 from .navier import Navier2D, integrate  # noqa: F401
+from .navier_adjoint import Navier2DAdjoint  # noqa: F401
 from .solid_masks import Statistics, solid_cylinder_inner, solid_porosity, solid_roughness_sinusoid  # noqa: F401

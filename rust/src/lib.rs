@@ -49,6 +49,10 @@ pub struct rp_solver_t {
 pub struct rp_navier_t {
     _private: [u8; 0],
 }
+#[repr(C)]
+pub struct rp_adjoint_t {
+    _private: [u8; 0],
+}
 
 // One line per function of include/rustpde_b200.h (checked by tests/test_cabi.py).
 extern "C" {
@@ -138,6 +142,19 @@ extern "C" {
     fn rp_navier_profile(h: *mut rp_navier_t, reps: c_int, ms: *mut c_double, cap: usize, nops: *mut c_int) -> c_int;
     fn rp_navier_op_info(h: *mut rp_navier_t, i: c_int, name: *mut c_char, name_len: usize, bytes: *mut c_double,
                          flops: *mut c_double) -> c_int;
+    fn rp_adjoint_create(nx: c_int, ny: c_int, ra: c_double, pr: c_double, dt: c_double, aspect: c_double, adiabatic: c_int,
+                         periodic: c_int, out: *mut *mut rp_adjoint_t) -> c_int;
+    fn rp_adjoint_destroy(h: *mut rp_adjoint_t) -> c_int;
+    fn rp_adjoint_set_velocity(h: *mut rp_adjoint_t, amp: c_double, m: c_double, n: c_double) -> c_int;
+    fn rp_adjoint_set_temperature(h: *mut rp_adjoint_t, amp: c_double, m: c_double, n: c_double) -> c_int;
+    fn rp_adjoint_update(h: *mut rp_adjoint_t, nsteps: c_int) -> c_int;
+    fn rp_adjoint_get_time(h: *mut rp_adjoint_t, time: *mut c_double) -> c_int;
+    fn rp_adjoint_reset_time(h: *mut rp_adjoint_t) -> c_int;
+    fn rp_adjoint_eval(h: *mut rp_adjoint_t, nu: *mut c_double, nuvol: *mut c_double, re: *mut c_double, div: *mut c_double) -> c_int;
+    fn rp_adjoint_residuals(h: *mut rp_adjoint_t, smooth: *mut c_double, unsmooth: *mut c_double) -> c_int;
+    fn rp_adjoint_exit(h: *mut rp_adjoint_t, stop: *mut c_int) -> c_int;
+    fn rp_adjoint_field(h: *mut rp_adjoint_t, which: c_int, out: *mut *mut rp_field_t) -> c_int;
+    fn rp_adjoint_solver(h: *mut rp_adjoint_t, which: c_int, out: *mut *mut rp_solver_t) -> c_int;
     fn rp_navier_write_snapshot(h: *mut rp_navier_t, path: *const c_char) -> c_int;
     fn rp_navier_read_snapshot(h: *mut rp_navier_t, path: *const c_char) -> c_int;
 }
@@ -890,6 +907,132 @@ impl<T: SpectralScalar> Integrate for Navier2D<T> {
             return ready != 0 && d.is_nan();
         }
         self.div_norm().is_nan()
+    }
+}
+
+/// `Navier2DAdjoint` (src/navier/navier_adjoint.rs:128-176): steady-state adjoint descent on the device.
+/// `temp`, `ux`, `uy` are `[adjoint field, Navier-Stokes residual]` like in the reference.
+pub struct Navier2DAdjoint<T: SpectralScalar> {
+    h: *mut rp_adjoint_t,
+    pub temp: [Field2<T>; 2],
+    pub ux: [Field2<T>; 2],
+    pub uy: [Field2<T>; 2],
+    pub pres: [Field2<T>; 2],
+    pub ra: f64,
+    pub pr: f64,
+    pub time: f64,
+    pub dt: f64,
+    pub dt_navier: f64,
+    pub diagnostics: HashMap<String, Vec<f64>>,
+}
+impl<T: SpectralScalar> Navier2DAdjoint<T> {
+    fn make(nx: usize, ny: usize, ra: f64, pr: f64, dt: f64, aspect: f64, adiabatic: bool, periodic: bool) -> Self {
+        ensure_init();
+        let mut h = std::ptr::null_mut();
+        unsafe { check(rp_adjoint_create(nx as c_int, ny as c_int, ra, pr, dt, aspect, adiabatic as c_int, periodic as c_int, &mut h)) };
+        let bx = |k: BaseKind| Base { kind: if periodic { BaseKind::FourierR2c } else { k }, n: nx };
+        let sp_u = Space2::new(&bx(BaseKind::ChebDirichlet), &cheb_dirichlet(ny));
+        let sp_t = Space2::new(&bx(if adiabatic { BaseKind::ChebNeumann } else { BaseKind::ChebDirichlet }), &cheb_dirichlet(ny));
+        let spaces = [sp_t, sp_u, sp_u, Space2::new(&bx(BaseKind::Chebyshev), &chebyshev(ny)),
+                      Space2::new(&bx(BaseKind::ChebNeumann), &cheb_neumann(ny)), sp_t, sp_u, sp_u];
+        let view = |i: usize| {
+            let mut f = std::ptr::null_mut();
+            unsafe { check(rp_adjoint_field(h, i as c_int, &mut f)) };
+            Field2::<T>::from_handle(f, false, spaces[i])
+        };
+        let mut diagnostics = HashMap::new();
+        for k in ["time", "Nu", "Nuvol", "Re"] {
+            diagnostics.insert(k.to_string(), Vec::new());
+        }
+        Navier2DAdjoint { h, temp: [view(0), view(5)], ux: [view(1), view(6)], uy: [view(2), view(7)], pres: [view(3), view(4)],
+                          ra, pr, time: 0.0, dt, dt_navier: 1e-2, diagnostics }
+    }
+    pub fn set_velocity(&mut self, amp: f64, m: f64, n: f64) {
+        unsafe { check(rp_adjoint_set_velocity(self.h, amp, m, n)) }
+    }
+    pub fn set_temperature(&mut self, amp: f64, m: f64, n: f64) {
+        unsafe { check(rp_adjoint_set_temperature(self.h, amp, m, n)) }
+    }
+    pub fn reset_time(&mut self) {
+        unsafe { check(rp_adjoint_reset_time(self.h)) };
+        self.time = 0.0;
+    }
+    /// (Nu, Nuvol, Re, |div|) -- `eval_nu`, `eval_nuvol`, `eval_re` (navier_adjoint.rs:952-992)
+    pub fn eval(&mut self) -> (f64, f64, f64, f64) {
+        let (mut a, mut b, mut c, mut d) = (0.0, 0.0, 0.0, 0.0);
+        unsafe { check(rp_adjoint_eval(self.h, &mut a, &mut b, &mut c, &mut d)) };
+        (a, b, c, d)
+    }
+    pub fn eval_nu(&mut self) -> f64 {
+        self.eval().0
+    }
+    pub fn eval_nuvol(&mut self) -> f64 {
+        self.eval().1
+    }
+    pub fn eval_re(&mut self) -> f64 {
+        self.eval().2
+    }
+    /// |.|_2 of the smoothed and of the unsmoothed residual fields (ux, uy, temp)
+    pub fn residuals(&mut self) -> ([f64; 3], [f64; 3]) {
+        let (mut s, mut u) = ([0.0; 3], [0.0; 3]);
+        unsafe { check(rp_adjoint_residuals(self.h, s.as_mut_ptr(), u.as_mut_ptr())) };
+        (s, u)
+    }
+    /// Eigen set-up data of solver `which` (0 smoother ux|uy, 1 smoother temp, 2 pressure, 3 inner Navier2D pressure)
+    pub fn export_eig(&self, which: usize) -> Option<EigData> {
+        let mut s = std::ptr::null_mut();
+        unsafe { check(rp_adjoint_solver(self.h, which as c_int, &mut s)) };
+        let borrowed = std::mem::ManuallyDrop::new(SolverHandle { h: s });
+        borrowed.export_eig()
+    }
+}
+impl Navier2DAdjoint<f64> {
+    /// `Navier2DAdjoint::new(nx, ny, ra, pr, dt, aspect, adiabatic)` (navier_adjoint.rs:197)
+    pub fn new(nx: usize, ny: usize, ra: f64, pr: f64, dt: f64, aspect: f64, adiabatic: bool) -> Self {
+        Self::make(nx, ny, ra, pr, dt, aspect, adiabatic, false)
+    }
+}
+impl Navier2DAdjoint<Complex<f64>> {
+    /// `Navier2DAdjoint::new_periodic(nx, ny, ra, pr, dt, aspect)` (navier_adjoint.rs:361)
+    pub fn new_periodic(nx: usize, ny: usize, ra: f64, pr: f64, dt: f64, aspect: f64) -> Self {
+        Self::make(nx, ny, ra, pr, dt, aspect, true, true)
+    }
+}
+impl<T: SpectralScalar> Drop for Navier2DAdjoint<T> {
+    fn drop(&mut self) {
+        unsafe { rp_adjoint_destroy(self.h) };
+    }
+}
+impl<T: SpectralScalar> Integrate for Navier2DAdjoint<T> {
+    fn update(&mut self) {
+        unsafe { check(rp_adjoint_update(self.h, 1)) };
+        self.time += self.dt;
+    }
+    fn get_time(&self) -> f64 {
+        let mut t = 0.0;
+        unsafe { check(rp_adjoint_get_time(self.h, &mut t)) };
+        t
+    }
+    fn get_dt(&self) -> f64 {
+        self.dt
+    }
+    fn callback(&mut self) {
+        let (nu, nuvol, re, div) = self.eval();
+        let t = self.get_time();
+        println!("time = {:4.2}      |div| = {:4.2e}     Nu = {:5.3e}     Nuv = {:5.3e}    Re = {:5.3e}", t, div, nu, nuvol, re);
+        let (s, _) = self.residuals();
+        println!("|U| = {:10.2e}", s[0]);
+        println!("|V| = {:10.2e}", s[1]);
+        println!("|T| = {:10.2e}", s[2]);
+        for (k, x) in [("time", t), ("Nu", nu), ("Nuvol", nuvol), ("Re", re)] {
+            self.diagnostics.get_mut(k).unwrap().push(x);
+        }
+    }
+    /// NaN divergence or residual below 1e-8 (navier_adjoint.rs:892-910)
+    fn exit(&mut self) -> bool {
+        let mut stop = 0 as c_int;
+        unsafe { check(rp_adjoint_exit(self.h, &mut stop)) };
+        stop != 0
     }
 }
 

@@ -11,6 +11,7 @@ from .api import (  # noqa: F401
     Hholtz,
     HholtzAdi,
     Navier2D,
+    Navier2DAdjoint,
     Poisson,
     RustpdeError,
     Space2,
@@ -31,7 +32,7 @@ from .solid_masks import (  # noqa: F401
 )
 
 __all__ = [
-    "Base", "Field2", "Hholtz", "HholtzAdi", "Navier2D", "Poisson", "RustpdeError", "Space2",
+    "Base", "Field2", "Hholtz", "HholtzAdi", "Navier2D", "Navier2DAdjoint", "Poisson", "RustpdeError", "Space2",
     "cheb_dirichlet", "cheb_dirichlet_bc", "cheb_neumann", "cheb_neumann_bc", "chebyshev", "fourier_r2c", "integrate",
     "Statistics", "solid_cylinder_inner", "solid_porosity", "solid_porosity_interpolate", "solid_roughness_sinusoid",
 ]

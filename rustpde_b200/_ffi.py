@@ -92,6 +92,18 @@ _SIGS = {
     "rp_ipc_export": [vp, C.c_char_p],
     "rp_ipc_open": [C.c_char_p, vpp],
     "rp_ipc_close": [vp],
+    "rp_adjoint_create": [C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, vpp],
+    "rp_adjoint_destroy": [vp],
+    "rp_adjoint_set_velocity": [vp, C.c_double, C.c_double, C.c_double],
+    "rp_adjoint_set_temperature": [vp, C.c_double, C.c_double, C.c_double],
+    "rp_adjoint_update": [vp, C.c_int],
+    "rp_adjoint_get_time": [vp, c_double_p],
+    "rp_adjoint_reset_time": [vp],
+    "rp_adjoint_eval": [vp, c_double_p, c_double_p, c_double_p, c_double_p],
+    "rp_adjoint_residuals": [vp, c_double_p, c_double_p],
+    "rp_adjoint_exit": [vp, c_int_p],
+    "rp_adjoint_field": [vp, C.c_int, vpp],
+    "rp_adjoint_solver": [vp, C.c_int, vpp],
     "rp_navier_profile": [vp, C.c_int, c_double_p, C.c_size_t, c_int_p],
     "rp_navier_op_info": [vp, C.c_int, C.c_char_p, C.c_size_t, c_double_p, c_double_p],
 }

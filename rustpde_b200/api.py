@@ -595,6 +595,131 @@ class Navier2D:
         return out
 
 
+class _BorrowedSolver(_Solver):
+    def __init__(self, lib, handle):
+        self._lib = lib
+        self._h = handle
+
+    def __del__(self):
+        pass
+
+
+class Navier2DAdjoint:
+    """src/navier/navier_adjoint.rs:128-176.  Use Navier2DAdjoint.new(...) / .new_periodic(...)."""
+
+    def __init__(self):
+        raise TypeError("use Navier2DAdjoint.new(...) or Navier2DAdjoint.new_periodic(...)")
+
+    @classmethod
+    def _make(cls, nx, ny, ra, pr, dt, aspect, adiabatic, periodic, lib):
+        s = object.__new__(cls)
+        s._lib = lib or _ffi.product_lib()
+        s._h = C.c_void_p()
+        s._lib.call("rp_adjoint_create", nx, ny, ra, pr, dt, aspect, int(adiabatic), int(periodic), C.byref(s._h))
+        s.nx, s.ny, s.ra, s.pr, s.dt, s.periodic = nx, ny, ra, pr, dt, bool(periodic)
+        s.dt_navier = 1e-2
+        kx = fourier_r2c if periodic else None
+        sp_u = Space2((kx or cheb_dirichlet)(nx), cheb_dirichlet(ny))
+        sp_t = Space2((kx or (cheb_neumann if adiabatic else cheb_dirichlet))(nx), cheb_dirichlet(ny))
+        spaces = [sp_t, sp_u, sp_u, Space2((kx or chebyshev)(nx), chebyshev(ny)), Space2((kx or cheb_neumann)(nx), cheb_neumann(ny)), sp_t, sp_u, sp_u]
+        flds = []
+        for i in range(8):
+            fh = C.c_void_p()
+            s._lib.call("rp_adjoint_field", s._h, i, C.byref(fh))
+            flds.append(Field2(spaces[i], lib=s._lib, _handle=fh, _owner=s))
+        # [adjoint field, Navier-Stokes residual]
+        s.temp, s.ux, s.uy = [flds[0], flds[5]], [flds[1], flds[6]], [flds[2], flds[7]]
+        s.pres = [flds[3], flds[4]]
+        s.diagnostics = {"time": [], "Nu": [], "Nuvol": [], "Re": []}
+        s.write_intervall = None
+        return s
+
+    @classmethod
+    def new(cls, nx, ny, ra, pr, dt, aspect, adiabatic, lib=None):  # navier_adjoint.rs:197
+        return cls._make(nx, ny, ra, pr, dt, aspect, adiabatic, False, lib)
+
+    @classmethod
+    def new_periodic(cls, nx, ny, ra, pr, dt, aspect, lib=None):  # navier_adjoint.rs:361
+        return cls._make(nx, ny, ra, pr, dt, aspect, True, True, lib)
+
+    def __del__(self):
+        try:
+            if self._h:
+                self._lib.c.rp_adjoint_destroy(self._h)
+        except Exception:
+            pass
+
+    def set_velocity(self, amp, m, n):
+        self._lib.call("rp_adjoint_set_velocity", self._h, float(amp), float(m), float(n))
+
+    def set_temperature(self, amp, m, n):
+        self._lib.call("rp_adjoint_set_temperature", self._h, float(amp), float(m), float(n))
+
+    def reset_time(self):
+        self._lib.call("rp_adjoint_reset_time", self._h)
+
+    @property
+    def time(self):
+        t = C.c_double()
+        self._lib.call("rp_adjoint_get_time", self._h, C.byref(t))
+        return t.value
+
+    def update(self, nsteps=1):
+        self._lib.call("rp_adjoint_update", self._h, int(nsteps))
+
+    def get_time(self):
+        return self.time
+
+    def get_dt(self):
+        return self.dt
+
+    def eval(self):
+        v = [C.c_double() for _ in range(4)]
+        self._lib.call("rp_adjoint_eval", self._h, *[C.byref(x) for x in v])
+        return [x.value for x in v]  # Nu, Nuvol, Re, |div|
+
+    def eval_nu(self):
+        return self.eval()[0]
+
+    def eval_nuvol(self):
+        return self.eval()[1]
+
+    def eval_re(self):
+        return self.eval()[2]
+
+    def div_norm(self):
+        return self.eval()[3]
+
+    def residuals(self):
+        sm, un = (C.c_double * 3)(), (C.c_double * 3)()
+        self._lib.call("rp_adjoint_residuals", self._h, sm, un)
+        return list(sm), list(un)
+
+    def exit(self):  # navier_adjoint.rs:892-910
+        stop = C.c_int()
+        self._lib.call("rp_adjoint_exit", self._h, C.byref(stop))
+        return bool(stop.value)
+
+    def callback(self):  # navier_adjoint.rs:815-890 (diagnostics part)
+        nu, nuvol, re, div = self.eval()
+        t = self.time
+        print("time = %4.2f      |div| = %4.2e     Nu = %5.3e     Nuv = %5.3e    Re = %5.3e" % (t, div, nu, nuvol, re))
+        sm, _ = self.residuals()
+        print("|U| = %10.2e\n|V| = %10.2e\n|T| = %10.2e" % tuple(sm))
+        for k, v in (("time", t), ("Nu", nu), ("Nuvol", nuvol), ("Re", re)):
+            self.diagnostics[k].append(v)
+
+    def export_eig(self):
+        """Eigen set-up data of the four fast-diagonalisation solvers (confined): smoother of ux / uy, smoother of temp,
+        pressure Poisson, the inner Navier2D's pressure Poisson -- what the oracle consumes in the parity tests."""
+        out = {}
+        for i, key in enumerate(("smooth_u", "smooth_t", "pres", "navier_pres")):
+            sh = C.c_void_p()
+            self._lib.call("rp_adjoint_solver", self._h, i, C.byref(sh))
+            out[key] = _BorrowedSolver(self._lib, sh).export_eig()
+        return out
+
+
 def integrate(pde, max_time, save_intervall=None, exit_every=1, async_exit=False):
     """src/lib.rs:155-187.  `exit_every` > 1 checks the NaN break criterion less often (the reference checks every
     step, which costs a device sync); `async_exit` uses exit_async() (no sync, NaN seen one check late)."""

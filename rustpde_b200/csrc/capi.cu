@@ -18,6 +18,11 @@ struct rp_navier {
   Navier2D* n;
   rp_field views[6];
 };
+struct rp_adjoint {
+  Navier2DAdjoint* a;
+  rp_field views[8];
+  rp_solver solvers[4];
+};
 
 static thread_local std::string g_last_error;
 
@@ -555,6 +560,70 @@ int rp_navier_op_info(rp_navier_t* h, int i, char* name, size_t name_len, double
     }
     if (bytes) *bytes = info[i].bytes;
     if (flops) *flops = info[i].flops;
+  });
+}
+
+// ---- Navier2DAdjoint ---------------------------------------------------------
+int rp_adjoint_create(int nx, int ny, double ra, double pr, double dt, double aspect, int adiabatic, int periodic, rp_adjoint_t** out) {
+  return guard([&] {
+    need(out != nullptr, RP_ERR_INVALID, "null out pointer");
+    need(nx >= 8 && ny >= 8, RP_ERR_INVALID, "grid too small");
+    need(ra > 0 && pr > 0 && dt > 0 && aspect > 0, RP_ERR_INVALID, "ra, pr, dt, aspect must be positive");
+    init_kernels();
+    auto* h = new rp_adjoint;
+    h->a = new Navier2DAdjoint(nx, ny, ra, pr, dt, aspect, adiabatic != 0, periodic != 0);
+    for (int i = 0; i < 8; ++i) h->views[i] = rp_field{h->a->field_by_index(i), false};
+    for (int i = 0; i < 4; ++i) h->solvers[i] = rp_solver{h->a->solver_by_index(i)};
+    *out = h;
+  });
+}
+int rp_adjoint_destroy(rp_adjoint_t* h) {
+  return guard([&] {
+    if (!h) return;
+    delete h->a;
+    delete h;
+  });
+}
+#define ADJ_GUARD(...)                       \
+  return guard([&] {                         \
+    need(h, RP_ERR_INVALID, "null handle");  \
+    Navier2DAdjoint& A = *h->a;              \
+    (void)A;                                 \
+    __VA_ARGS__;                             \
+  })
+int rp_adjoint_set_velocity(rp_adjoint_t* h, double amp, double m, double n) { ADJ_GUARD(A.set_velocity(amp, m, n)); }
+int rp_adjoint_set_temperature(rp_adjoint_t* h, double amp, double m, double n) { ADJ_GUARD(A.set_temperature(amp, m, n)); }
+int rp_adjoint_update(rp_adjoint_t* h, int nsteps) {
+  ADJ_GUARD({
+    need(nsteps >= 0, RP_ERR_INVALID, "nsteps < 0");
+    A.update(nsteps);
+  });
+}
+int rp_adjoint_get_time(rp_adjoint_t* h, double* t) { ADJ_GUARD(if (t) *t = A.time); }
+int rp_adjoint_reset_time(rp_adjoint_t* h) {
+  ADJ_GUARD({
+    A.time = 0.0;
+    A.navier->time = 0.0;
+  });
+}
+int rp_adjoint_eval(rp_adjoint_t* h, double* nu, double* nuvol, double* re, double* div_norm) { ADJ_GUARD(A.eval(nu, nuvol, re, div_norm)); }
+int rp_adjoint_residuals(rp_adjoint_t* h, double smooth[3], double unsmooth[3]) { ADJ_GUARD(A.residuals(smooth, unsmooth)); }
+int rp_adjoint_exit(rp_adjoint_t* h, int* stop) {
+  ADJ_GUARD({
+    const bool e = A.exit();
+    if (stop) *stop = e ? 1 : 0;
+  });
+}
+int rp_adjoint_field(rp_adjoint_t* h, int which, rp_field_t** out) {
+  ADJ_GUARD({
+    need(out && which >= 0 && which < 8, RP_ERR_INVALID, "bad field index");
+    *out = &h->views[which];
+  });
+}
+int rp_adjoint_solver(rp_adjoint_t* h, int which, rp_solver_t** out) {
+  ADJ_GUARD({
+    need(out && which >= 0 && which < 4, RP_ERR_INVALID, "bad solver index");
+    *out = &h->solvers[which];
   });
 }
 

@@ -345,6 +345,22 @@ void launch_combine(double* out, const double* a, const double* b, const double*
   RP_LAUNCH(combine_kernel, dim3(blocks), dim3(256), (size_t)0, s, out, a, b, c, ld, rows, cols, s0, s1);
 }
 
+// dealias (navier.rs:1022-1032): zero rows >= cut_row and columns >= cut_col of a spectral array (rc doubles per element)
+__global__ void dealias_kernel(double* p, long long ld, int rows, int cols, int rc, int cut_row, int cut_col) {
+  const long long total = (long long)rows * cols;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(idx / cols), j = (int)(idx % cols);
+    if (i >= cut_row || j >= cut_col)
+      for (int k = 0; k < rc; ++k) p[((size_t)i * ld + j) * rc + k] = 0.0;
+  }
+}
+void launch_dealias(double* p, long long ld, int rows, int cols, int rc, int cut_row, int cut_col, cudaStream_t s) {
+  long long total = (long long)rows * cols;
+  int blocks = (int)std::min<long long>((total + 255) / 256, 1184);
+  if (blocks < 1) blocks = 1;
+  RP_LAUNCH(dealias_kernel, dim3(blocks), dim3(256), (size_t)0, s, p, ld, rows, cols, rc, cut_row, cut_col);
+}
+
 // out[r][j] = lo[r] in[r][j] + di[r] in[r+2][j] + up[r] in[r+4][j], r < m = n - 2: the B2 preconditioner along x
 // (matvec.rs:172-193) of a stand-alone Hholtz / Poisson solve; elementwise in j, so plain coalesced rows
 __global__ void __launch_bounds__(256) b2x_kernel(const double* in, long long ldi, double* out, long long ldo, int n, int cols,

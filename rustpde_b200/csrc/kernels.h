@@ -32,6 +32,7 @@ void launch_avg_axis0(const double* a, long long ld, int rows, int cols, const d
 void launch_combine(double* out, const double* a, const double* b, const double* c, long long ld, int rows, int cols,
                     double s0, double s1, cudaStream_t s);
 
+void launch_dealias(double* p, long long ld, int rows, int cols, int rc, int cut_row, int cut_col, cudaStream_t s);
 void launch_b2x(const double* in, long long ldi, double* out, long long ldo, int n, int cols, const double* lo, const double* di,
                 const double* up, cudaStream_t s);
 

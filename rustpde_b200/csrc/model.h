@@ -159,6 +159,7 @@ class Solver2 {
   // generic entry: in_/out_ are solver-owned staging arrays
   Arr in_r, out_r, in_c, out_c;
   void solve(bool complex_data);
+  void solve_dev(const Arr& in, Arr& out, bool complex_data);  // device arrays in the solver's shapes, no host copies
   void export_eig(double* lam, double* q, double* p) const;
   // building blocks used by Navier2D's fused programs
   void emit_x(ProgBuilder& pb, int r, Lay lay) const;        // bandmv_x (+ fdma_x for ADI)
@@ -207,6 +208,8 @@ class Navier2D {
   void sync();
   Field2* field_by_index(int which);
   int launches_per_step() const { return launches_per_step_; }
+  const Arr& tempbc_ortho() const { return tbc_ortho_; }
+  void apply_ic(Field2& f, double amp, double m, double n, bool sin_cos);
   bool uses_specialised_kernels() {
     build_step();
     return !fast_ops_.empty();
@@ -258,7 +261,6 @@ class Navier2D {
   void build_y_phase();
   void add_prog(ProgBuilder& pb, const char* name);
   void rebuild_bc();
-  void apply_ic(Field2& f, double amp, double m, double n, bool sin_cos);
   void run_step();
   void prepare_step();
   void copy_bc_to_field();  // field.vhat = ortho coefficients of the boundary-condition field
@@ -313,6 +315,41 @@ class Navier2D {
   cudaGraphExec_t graph_ = nullptr;
   bool graph_ok_ = false;
 #endif
+};
+
+// Navier2DAdjoint (src/navier/navier_adjoint.rs:128-176)
+class Navier2DAdjoint {
+ public:
+  Navier2DAdjoint(int nx, int ny, double ra, double pr, double dt, double aspect, bool adiabatic, bool periodic);
+  ~Navier2DAdjoint();
+  int nx, ny;
+  bool periodic;
+  double ra, pr, nu, ka, dt, dt_navier, time = 0.0, scale[2], res_tol = 1e-8;
+  bool dealias = true;
+  std::unique_ptr<Navier2D> navier;
+  std::unique_ptr<Field2> temp[2], ux[2], uy[2], pres[2], field;  // [adjoint field, Navier-Stokes residual]
+  std::unique_ptr<Solver2> solver_pres, smoother[3];
+  cudaStream_t stream = 0;
+  void set_velocity(double amp, double m, double n);
+  void set_temperature(double amp, double m, double n);
+  void update(int nsteps);
+  void eval(double* nu, double* nuvol, double* re, double* div_norm);
+  void residuals(double smooth[3], double unsmooth[3]);
+  bool exit();
+  Field2* field_by_index(int which);    // 0 temp, 1 ux, 2 uy, 3 pres, 4 pseudo pressure, 5..7 residual temp / ux / uy
+  Solver2* solver_by_index(int which);  // 0 smoother ux|uy, 1 smoother temp, 2 pressure Poisson, 3 inner Navier2D's Poisson
+
+ private:
+  void conv_term(Field2& f, const Arr& u, int d0, int d1);
+  void finish_conv();
+  void conv_u(int comp);
+  void solve_u(int comp);
+  void solve_temp();
+  void divergence_to_rhs();
+  void update_residual();
+  double norm_l2(const Arr& a);
+  Arr rhs_, unsm_[3], phys_[3], conv_, bcv_, old_;
+  DevBuf red_;
 };
 
 // LAPACK access for the set-up eigendecomposition (src/solver/utils.rs:66-106)

@@ -345,6 +345,20 @@ void Solver2::solve_fast() {
   gemm_bwd(t3, out_r, m1);
 }
 
+void Solver2::solve_dev(const Arr& in, Arr& out, bool cd) {
+  const bool lanes_c = cd || x_fourier;
+  Arr& ain = lanes_c ? in_c : in_r;
+  Arr& aout = lanes_c ? out_c : out_r;
+  if (!ain.buf.p) {
+    ain.alloc(n0, n1, lanes_c);
+    aout.alloc(m0, m1, lanes_c);
+  }
+  if (in.buf.bytes != ain.buf.bytes || out.buf.bytes != aout.buf.bytes) throw Error(RP_ERR_SHAPE, "Dimension mismatch in solver input");
+  rt::d2d(ain.buf.p, in.buf.p, ain.buf.bytes, stream);
+  solve(cd);
+  rt::d2d(out.buf.p, aout.buf.p, aout.buf.bytes, stream);
+}
+
 void Solver2::solve(bool cd) {
   if (!cd && fast_path()) {
     solve_fast();

@@ -298,6 +298,14 @@ def test_navier_confined_column_scan_kernels(gpu, monkeypatch):
         assert max(derr) < 1e-9, (derr, dn, do)
 
 
+@pytest.mark.parametrize("periodic,nx,ny,steps", [(False, 128, 129, 5), (True, 128, 129, 5), (False, 512, 513, 2)])
+def test_adjoint_gpu(gpu, periodic, nx, ny, steps):
+    """Navier2DAdjoint (navier_adjoint.rs:128-1068): adjoint and residual fields <= 1e-9 relative against the oracle fed with
+    the library's exported eigen set-up data; three Hholtz smoothers = six parity-split DMMA GEMMs per confined step."""
+    from test_adjoint import check_adjoint
+    print(check_adjoint(gpu, periodic, nx, ny, steps=steps, tol=1e-9))
+
+
 def test_graph_and_eager_agree(gpu):
     import rustpde_b200 as R
     outs = []
