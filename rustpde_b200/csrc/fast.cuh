@@ -59,6 +59,15 @@ FK_DEV void cp_async16(void* smem_dst, const double* gsrc, int bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(bytes) : "memory");
 #endif
 }
+// 8-byte asynchronous copy (one double)
+FK_DEV void cp_async8(void* smem_dst, const double* gsrc) {
+#ifdef RP_EMU
+  *(double*)smem_dst = *gsrc;
+#else
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+#endif
+}
 FK_DEV void cp_async_commit() {
 #ifndef RP_EMU
   asm volatile("cp.async.commit_group;" ::: "memory");

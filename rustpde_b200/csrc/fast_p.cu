@@ -169,6 +169,9 @@ FK_DEV double ldc_stencil(const Mat& a, int r, int j, int part, const double* __
 // (i k s z).part for z = (re, im): re' = -k s im, im' = k s re
 FK_DEV double ik_part(double ks, double re, double im, int part) { return part ? ks * re : -ks * im; }
 
+#ifndef PK_FILL_U
+#define PK_FILL_U 8  // loads of the rhs assembly kept in flight per thread (elements per batch)
+#endif
 template <int LOG2L, int LC>
 FK_DEV void pk_hholtz_body(const PHholtzArgs& a, const PHholtzArgs3& a3) {
   typedef YCfg<LOG2L, LC> C;
@@ -179,22 +182,20 @@ FK_DEV void pk_hholtz_body(const PHholtzArgs& a, const PHholtzArgs3& a3) {
   const int r0 = blockIdx.x * LC;
   constexpr int n = C::n, m = n - 2;
   const int nrows = a.chat.rows;
+  stage_pivots<LC, C::NTHRS>(ti, a.m.inv, a.m.inv_ld, r0, nrows, m);  // pivot reciprocals of the LC complex rows, asynchronous
   if (a.mode == 1) {  // - dt/sy d/dy pres   (navier.rs:646)
-    tile_fill<LC, C::NTHR>(td, n, [&](int j, int l) { return ldc(a.pres, prow_of(r0, l), j, l & 1); });
+    tile_fill<LC, C::NTHRS>(td, n, [&](int j, int l) { return ldc(a.pres, prow_of(r0, l), j, l & 1); });
     __syncthreads();
-    cheb_diff<LC, C::NTHR, C::CL>(td, -1, td, -1, n, -a.dt * a.isy, red);
-  }
-  for (int it = threadIdx.x; it < m * LC; it += C::NTHR) {  // pivot reciprocals of the LC complex rows
-    const int l = it / m, j = it - l * m;
-    ti[j * LC + l] = a.m.inv[(size_t)min(r0 + l, nrows - 1) * a.m.inv_ld + j];
+    cheb_diff<LC, C::NTHRS, C::CL>(td, -1, td, -1, n, -a.dt * a.isy, red);
   }
   {
     const int tot = n * C::LR;
-    for (int it0 = threadIdx.x; it0 < tot; it0 += C::NTHR * 4) {
-      double v[4];
+    constexpr int FU = PK_FILL_U;
+    for (int it0 = threadIdx.x; it0 < tot; it0 += C::NTHRS * FU) {
+      double v[FU];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int it = min(it0 + u * C::NTHR, tot - 1);
+      for (int u = 0; u < FU; ++u) {
+        const int it = min(it0 + u * C::NTHRS, tot - 1);
         const int j = it / C::LR, l = it % C::LR, r = prow_of(r0, l), part = l & 1;
         double x = -a.dt * ldc(a.chat, r, j, part);                       // - dt * conv          (630, 651, 671)
         x += ldc_stencil(a.fld, r, j, part, a.sd, a.sl);                  // + to_ortho(field)    (625, 644, 663)
@@ -209,8 +210,8 @@ FK_DEV void pk_hholtz_body(const PHholtzArgs& a, const PHholtzArgs3& a3) {
         v[u] = x;
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int it = it0 + u * C::NTHR;
+      for (int u = 0; u < FU; ++u) {
+        const int it = it0 + u * C::NTHRS;
         if (it < tot) {
           double* w = &td[didx<LC>(it / C::LR, it % C::LR)];
           *w = (a.mode == 1) ? *w + v[u] : v[u];
@@ -218,10 +219,11 @@ FK_DEV void pk_hholtz_body(const PHholtzArgs& a, const PHholtzArgs3& a3) {
       }
     }
   }
+  cp_async_wait<0>();
   __syncthreads();
   const double mu = __ldg(&a.m.lam[min(prow_of(r0, threadIdx.x % C::LR), nrows - 1)]) + a.m.alpha;
-  mode_solve<LC, C::NTHR, C::CL, C::ROWS, 1>(td, ti, n, a.b2, a.m, mu, red);
-  tile_drain<LC, C::NTHR>(td, -1, m, [&](int j, int l, double v) {
+  mode_solve<LC, C::NTHRS, C::CL, C::ROWS, 1>(td, ti, n, a.b2, a.m, mu, red);
+  tile_drain<LC, C::NTHRS>(td, -1, m, [&](int j, int l, double v) {
     const int r = prow_of(r0, l);
     if (r < a.out.rows) a.out.p[((size_t)r * a.out.ld + j) * 2 + (l & 1)] = v;
   });
@@ -229,7 +231,7 @@ FK_DEV void pk_hholtz_body(const PHholtzArgs& a, const PHholtzArgs3& a3) {
 // blockIdx.y selects the field; the branch is block-uniform and keeps every argument a direct constant-bank
 // operand (a dynamically indexed `a3.a[blockIdx.y]` costs an LDC per access)
 template <int LOG2L, int LC>
-__global__ void __launch_bounds__(YCfg<LOG2L, LC>::NTHR, 1) pk_hholtz(PHholtzArgs3 a3) {
+__global__ void __launch_bounds__(YCfg<LOG2L, LC>::NTHRS, 1) pk_hholtz(PHholtzArgs3 a3) {
   if (blockIdx.y == 0)
     pk_hholtz_body<LOG2L, LC>(a3.a[0], a3);
   else if (blockIdx.y == 1)
@@ -239,7 +241,7 @@ __global__ void __launch_bounds__(YCfg<LOG2L, LC>::NTHR, 1) pk_hholtz(PHholtzArg
 }
 
 template <int LOG2L, int LC>
-__global__ void __launch_bounds__(YCfg<LOG2L, LC>::NTHR, 1) pk_divpois(PDivPoisArgs a) {
+__global__ void __launch_bounds__(YCfg<LOG2L, LC>::NTHRS, 1) pk_divpois(PDivPoisArgs a) {
   typedef YCfg<LOG2L, LC> C;
   YK_SMEM(td, red0);
   double* ti = td + C::TILE;
@@ -249,14 +251,12 @@ __global__ void __launch_bounds__(YCfg<LOG2L, LC>::NTHR, 1) pk_divpois(PDivPoisA
   constexpr int n = C::n, m = n - 2;
   const int nrows = a.ux.rows;
   // div = i k / sx S_y ux + D_y S_y uy / sy   (navier.rs:698-703)
-  tile_fill<LC, C::NTHR>(td, n, [&](int j, int l) { return ldc_stencil(a.uy, prow_of(r0, l), j, l & 1, a.sd, a.sl); });
-  for (int it = threadIdx.x; it < m * LC; it += C::NTHR) {  // pivot reciprocals of the LC complex rows
-    const int l = it / m, j = it - l * m;
-    ti[j * LC + l] = a.m.inv[(size_t)min(r0 + l, nrows - 1) * a.m.inv_ld + j];
-  }
+  stage_pivots<LC, C::NTHRS>(ti, a.m.inv, a.m.inv_ld, r0, nrows, m);  // pivot reciprocals of the LC complex rows, asynchronous
+  tile_fill<LC, C::NTHRS>(td, n, [&](int j, int l) { return ldc_stencil(a.uy, prow_of(r0, l), j, l & 1, a.sd, a.sl); });
+  cp_async_wait<0>();
   __syncthreads();
-  cheb_diff<LC, C::NTHR, C::CL>(td, -1, td, -1, n, a.isy, red);
-  for (int it = threadIdx.x; it < n * C::LR; it += C::NTHR) {
+  cheb_diff<LC, C::NTHRS, C::CL>(td, -1, td, -1, n, a.isy, red);
+  for (int it = threadIdx.x; it < n * C::LR; it += C::NTHRS) {
     const int j = it / C::LR, l = it % C::LR, r = prow_of(r0, l), part = l & 1;
     const double ks = a.isx * (double)(a.k0 + min(r, nrows - 1));
     const double re = ldc_stencil(a.ux, r, j, 0, a.sd, a.sl), im = ldc_stencil(a.ux, r, j, 1, a.sd, a.sl);
@@ -266,8 +266,8 @@ __global__ void __launch_bounds__(YCfg<LOG2L, LC>::NTHR, 1) pk_divpois(PDivPoisA
   }
   __syncthreads();
   const double mu = __ldg(&a.m.lam[min(prow_of(r0, threadIdx.x % C::LR), nrows - 1)]) + a.m.alpha;
-  mode_solve<LC, C::NTHR, C::CL, C::ROWS, 1>(td, ti, n, a.b2, a.m, mu, red);
-  tile_drain<LC, C::NTHR>(td, -1, m, [&](int j, int l, double v) {
+  mode_solve<LC, C::NTHRS, C::CL, C::ROWS, 1>(td, ti, n, a.b2, a.m, mu, red);
+  tile_drain<LC, C::NTHRS>(td, -1, m, [&](int j, int l, double v) {
     const int r = prow_of(r0, l);
     if (a.k0 + r == 0 && j == 0) v = 0.0;  // pres[1].vhat[[0,0]] = 0   (navier.rs:714)
     if (r < a.phi.rows) a.phi.p[((size_t)r * a.phi.ld + j) * 2 + (l & 1)] = v;
@@ -275,39 +275,39 @@ __global__ void __launch_bounds__(YCfg<LOG2L, LC>::NTHR, 1) pk_divpois(PDivPoisA
 }
 
 template <int LOG2L, int LC>
-__global__ void __launch_bounds__(YCfg<LOG2L, LC>::NTHR, YCfg<LOG2L, LC>::SMEM1 > 110 * 1024 ? 1 : 2) pk_project(PProjectArgs a) {
+__global__ void __launch_bounds__(YCfg<LOG2L, LC>::NTHRS, YCfg<LOG2L, LC>::SMEM1 > 110 * 1024 ? 1 : 2) pk_project(PProjectArgs a) {
   typedef YCfg<LOG2L, LC> C;
   YK_SMEM(td, red);
   const int r0 = blockIdx.x * LC;
   constexpr int n = C::n, m = n - 2;
   const int nrows = a.phi.rows;
   // ux -= from_ortho_y(i k / sx S_y phi)   (navier.rs:683-695)
-  tile_fill<LC, C::NTHR>(td, n, [&](int j, int l) {
+  tile_fill<LC, C::NTHRS>(td, n, [&](int j, int l) {
     const int r = prow_of(r0, l);
     const double ks = a.isx * (double)(a.k0 + min(r, nrows - 1));
     return ik_part(ks, ldc_stencil(a.phi, r, j, 0, a.nsd, a.nsl), ldc_stencil(a.phi, r, j, 1, a.nsd, a.nsl), l & 1);
   });
   __syncthreads();
-  from_ortho<LC, C::NTHR, C::CL>(td, -1, n, a.t, red);
-  tile_drain_sub<LC, C::NTHR>(td, -1, m, [&](int j, int l) -> double* {
+  from_ortho<LC, C::NTHRS, C::CL>(td, -1, n, a.t, red);
+  tile_drain_sub<LC, C::NTHRS>(td, -1, m, [&](int j, int l) -> double* {
     const int r = prow_of(r0, l);
     return (r < a.ux.rows) ? a.ux.p + ((size_t)r * a.ux.ld + j) * 2 + (l & 1) : nullptr;
   });
   __syncthreads();
   // to_ortho(phi): pressure update p += -nu div + to_ortho(phi) / dt   (navier.rs:717-721)
-  tile_fill<LC, C::NTHR>(td, n, [&](int j, int l) { return ldc_stencil(a.phi, prow_of(r0, l), j, l & 1, a.nsd, a.nsl); });
+  tile_fill<LC, C::NTHRS>(td, n, [&](int j, int l) { return ldc_stencil(a.phi, prow_of(r0, l), j, l & 1, a.nsd, a.nsl); });
   __syncthreads();
-  for (int it0 = threadIdx.x; it0 < n * C::LR; it0 += C::NTHR * 4) {
+  for (int it0 = threadIdx.x; it0 < n * C::LR; it0 += C::NTHRS * 4) {
     double dv[4], pv[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const int it = min(it0 + u * C::NTHR, n * C::LR - 1);
+      const int it = min(it0 + u * C::NTHRS, n * C::LR - 1);
       dv[u] = ldc(a.div, prow_of(r0, it % C::LR), it / C::LR, it & 1);
       pv[u] = ldc(a.pres, prow_of(r0, it % C::LR), it / C::LR, it & 1);
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const int it = it0 + u * C::NTHR;
+      const int it = it0 + u * C::NTHRS;
       if (it < n * C::LR) {
         const int j = it / C::LR, l = it % C::LR, r = prow_of(r0, l);
         if (r < a.pres.rows) a.pres.p[((size_t)r * a.pres.ld + j) * 2 + (l & 1)] = fma(-a.nu, dv[u], pv[u]) + td[didx<LC>(j, l)] * a.inv_dt;
@@ -316,9 +316,9 @@ __global__ void __launch_bounds__(YCfg<LOG2L, LC>::NTHR, YCfg<LOG2L, LC>::SMEM1 
   }
   __syncthreads();
   // uy -= from_ortho_y(D_y S_y phi / sy)
-  cheb_diff<LC, C::NTHR, C::CL>(td, -1, td, -1, n, a.isy, red);
-  from_ortho<LC, C::NTHR, C::CL>(td, -1, n, a.t, red);
-  tile_drain_sub<LC, C::NTHR>(td, -1, m, [&](int j, int l) -> double* {
+  cheb_diff<LC, C::NTHRS, C::CL>(td, -1, td, -1, n, a.isy, red);
+  from_ortho<LC, C::NTHRS, C::CL>(td, -1, n, a.t, red);
+  tile_drain_sub<LC, C::NTHRS>(td, -1, m, [&](int j, int l) -> double* {
     const int r = prow_of(r0, l);
     return (r < a.uy.rows) ? a.uy.p + ((size_t)r * a.uy.ld + j) * 2 + (l & 1) : nullptr;
   });
@@ -434,9 +434,9 @@ bool px_supported(int n0) {
 void launch_p_c2r(const PC2rArgs3& a, int nb, cudaStream_t s) { PX_LAUNCH(pk_c2r, a.a[0].src.cols, a.a[0].n, nb); }
 void launch_p_r2c(const PR2cArgs3& a, int nb, cudaStream_t s) { PX_LAUNCH(pk_r2c, a.a[0].dst.cols, a.a[0].n, nb); }
 
-#define YK_CASE_pk_hholtz(L, LCV) YK_CASE_BODY(pk_hholtz, L, LCV, 2, a)
-#define YK_CASE_pk_divpois(L, LCV) YK_CASE_BODY(pk_divpois, L, LCV, 2, a)
-#define YK_CASE_pk_project(L, LCV) YK_CASE_BODY(pk_project, L, LCV, 0, a)
+#define YK_CASE_pk_hholtz(L, LCV) YK_CASE_BODY_T(pk_hholtz, L, LCV, 2, a, NTHRS)
+#define YK_CASE_pk_divpois(L, LCV) YK_CASE_BODY_T(pk_divpois, L, LCV, 2, a, NTHRS)
+#define YK_CASE_pk_project(L, LCV) YK_CASE_BODY_T(pk_project, L, LCV, 0, a, NTHRS)
 
 // complex rows: a block owns 2 rows -> the launch helper's "rows / 4" becomes "2 * rows / 4"
 void launch_p_hholtz(const PHholtzArgs3& a, int nb, cudaStream_t s) { YK_LAUNCH(pk_hholtz, true, 2 * a.a[0].chat.rows, a.a[0].ny, a, nb); }

@@ -168,11 +168,9 @@ __global__ void __launch_bounds__(YCfg<LOG2L, LC>::NTHR, 1) yk_mode(YModeArgs a)
   (void)red0;
   const int r0 = blockIdx.x * C::LR;
   constexpr int n = C::n, m = n - 2;
+  stage_pivots<C::LR, C::NTHR>(ti, a.m.inv, a.m.inv_ld, r0, a.g.rows, m);  // pivot reciprocals of the LR rows, asynchronous
   tile_fill<LC, C::NTHR>(td, n, [&](int j, int l) { return ld_row(a.g, r0 + l, j); });
-  for (int it = threadIdx.x; it < m * C::LR; it += C::NTHR) {  // pivot reciprocals of the LR rows (coalesced along j)
-    const int l = it / m, j = it - l * m;
-    ti[j * C::LR + l] = a.m.inv[(size_t)min(r0 + l, a.g.rows - 1) * a.m.inv_ld + j];
-  }
+  cp_async_wait<0>();
   __syncthreads();
   const double mu = __ldg(&a.m.lam[min(r0 + (int)(threadIdx.x % C::LR), a.g.rows - 1)]) + a.m.alpha;
   mode_solve<LC, C::NTHR, C::CL, C::ROWS, 0>(td, ti, n, a.b2, a.m, mu, red);

@@ -12,6 +12,9 @@ struct YCfg {
   static constexpr int N = 1 << LOG2L;
   static constexpr int n = N + 1;
   static constexpr int NTHR = (N * LC / 8) < 64 ? 64 : (N * LC / 8);
+  // kernels without an FFT (banded sweeps only): the scans use at most 512 threads anyway, and a 1024-thread block
+  // would cap them at 64 registers (the 8193-point instantiations spilled up to 2.4 KB per thread)
+  static constexpr int NTHRS = NTHR > 512 ? 512 : NTHR;
   static constexpr int ROWS = N + 8;
   static constexpr int TILE = ROWS * LR;  // doubles per tile
   static constexpr int CL = chunk_len(n, NTHR, LC);
@@ -98,6 +101,19 @@ FK_DEV double ld_row(const Mat& a, int r, int j) {
 }
 
 
+// Swept pivot reciprocals of NR rows -> ti[j * NR + l] (row fastest), as asynchronous 8-byte copies: every element is
+// in flight at once and no register is held, so the DRAM round trip overlaps the tile fill that follows instead of
+// costing one exposed latency per loop iteration (this loop and the rhs fill were 56 % of pk_hholtz's stall samples,
+// profiles/r2_ncu_pk_hholtz_periodic2048.txt).  One commit group; the caller waits (cp_async_wait<0>) before its barrier.
+template <int NR, int NTHR>
+FK_DEV void stage_pivots(double* ti, const double* __restrict__ inv, long long inv_ld, int r0, int nrows, int m) {
+  for (int it = threadIdx.x; it < m * NR; it += NTHR) {
+    const int l = it / m, j = it - l * m;
+    cp_async8(&ti[j * NR + l], inv + (size_t)min(r0 + l, nrows - 1) * inv_ld + j);
+  }
+  cp_async_commit();
+}
+
 // Per-mode banded solve (A + mu C) x = B2 g along the tile (fdma_tensor.rs:219-227, hholtz.rs:182-190):
 // tile td holds g (n entries, natural layout), tile ti the swept pivot reciprocals 1/dia'_i of the lane
 // (set-up data); everything else of the sweep is recomputed from the raw bands.  `mu` = lam + alpha of
@@ -179,7 +195,8 @@ static void set_smem(K kern, int bytes) {
     if (!ok_) throw Error(RP_ERR_INTERNAL, #kern ": unsupported lane length");                        \
   } while (0)
 
-#define YK_CASE_BODY(kern, L, LCV, smem_sel, args)                                           \
+#define YK_CASE_BODY(kern, L, LCV, smem_sel, args) YK_CASE_BODY_T(kern, L, LCV, smem_sel, args, NTHR)
+#define YK_CASE_BODY_T(kern, L, LCV, smem_sel, args, NT)                                     \
   if (l_ == L) {                                                                              \
     typedef YCfg<L, LCV> C;                                                                   \
     const int nb_ = ((nrows_) + C::LR - 1) / C::LR;                                           \
@@ -189,7 +206,7 @@ static void set_smem(K kern, int bytes) {
     if (first_use_on_device(init_)) {                                                                             \
       set_smem(kp_, sm_);                                                                     \
     }                                                                                         \
-    RP_LAUNCH(kp_, dim3(nb_, nby_), dim3(C::NTHR), (size_t)sm_, s, args);                     \
+    RP_LAUNCH(kp_, dim3(nb_, nby_), dim3(C::NT), (size_t)sm_, s, args);                       \
     ok_ = true;                                                                               \
   }
 
