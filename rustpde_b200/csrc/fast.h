@@ -199,6 +199,7 @@ struct XForwardArgs {  // forward DCT-x + dealias + rhs assembly + x half of Hho
   FdmaTabs f;
   const double *pt1, *pt2;  // chunk-major packed tables: {b2 lo, di, up, f.fp} (forward), {f.bs, bp1, bp2, 0} (backward)
   DctTab t;
+  Mat rhs;  // p != null: stop after the rhs assembly and store the [nx, ny] ortho rhs here (the sweeps run in xw_adi)
 };
 struct XForwardArgs3 {
   XForwardArgs a[3];
@@ -285,6 +286,22 @@ struct XAdiArgs {  // x half of a stand-alone HholtzAdi::solve: out = Fdma_x(B2_
   int nx;
 };
 void launch_x_adi(const XAdiArgs& a, cudaStream_t s);
+
+// ---- warp-serial column sweeps along x (fast_xw.cu): a warp owns 16 adjacent columns, a thread one parity chain ----
+bool xw_supported(int n0);
+// row-major table of W doubles per row: out[i * W + k] = src[k][i + shift[k]] (0 outside the source)
+std::vector<double> pack_rows(int rows, int W, const std::vector<std::vector<double>>& src, const std::vector<int>& shift);
+struct XwAdiArgs {  // out = Fdma_x(B2_x in)   (hholtz_adi.rs:108,128)
+  Mat in;           // [nx, cols]
+  Mat tmp;          // [mx, cols] scratch (forward-sweep result)
+  Mat out;          // [mx, cols]
+  const double *cf, *cb;  // pack_rows tables [mx][4]: {b2 lo, di, up, f.fp}, {f.bs, bp1, bp2, 0}
+  int nx;
+};
+struct XwAdiArgs3 {
+  XwAdiArgs a[3];
+};
+void launch_xw_adi(const XwAdiArgs3& a, int nbatch, cudaStream_t s);
 
 // Destination of a fused transpose: part q (a peer GPU's buffer, mapped through CUDA IPC, or a local one) owns
 // the global indices [beg[q], beg[q+1]) along the scattered axis.  nparts == 0: no scatter (dense output).

@@ -236,6 +236,10 @@ FK_DEV void xk_forward_body(const XForwardArgs& a, const XForwardArgs3& a3) {
     }
   }
   __syncthreads();
+  if (a.rhs.p != nullptr) {  // the sweeps run as warp-serial column sweeps (fast_xw.cu)
+    for (int i = threadIdx.x >> 1; i < n; i += C::NTHR / 2) st2(a.rhs, i, col, tw[cidx<2>(rowof(N, i), c)]);
+    return;
+  }
   // the A tile is idle from here on: scratch of the second-order sweep when it is large enough
   b2_fdma_v<2, C::NTHR, C::NMAX, C::NSC2>(tw, N, n, a.pt1, a.pt2, red, C::NSC2 == C::NSC ? (double*)ta : red);
   for (int i = threadIdx.x >> 1; i < mxr; i += C::NTHR / 2) st2(a.out, i, col, tw[cidx<2>(rowof(N, i), c)]);

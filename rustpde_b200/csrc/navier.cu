@@ -681,6 +681,10 @@ void Navier2D::build_step_confined_fast() {
   // of the tile kernels -- measured equal within 2 % at 2048 x 2049, so the tile kernels stay the default
   const char* nxs = getenv("RUSTPDE_B200_XS");
   const bool use_xs = fk::xs_supported(nx) && nxs && nxs[0] == '1';
+  // RUSTPDE_B200_XW=0: keep the banded x sweeps inside the tile kernels (round-1 schedule); default: warp-serial
+  // column sweeps (fast_xw.cu)
+  const char* nxw = getenv("RUSTPDE_B200_XW");
+  const bool use_xw = !use_xs && fk::xw_supported(nx) && !(nxw && nxw[0] == '0');
   if (use_xs) {
     // forward DCT-x (tile kernel) -> chat = -dt * cut(F_x conv); then rhs assembly + B2_x + Fdma_x as streaming column scans
     fk::XFdctArgs3 d3;
@@ -751,8 +755,32 @@ void Navier2D::build_step_confined_fast() {
         a.pt2 = perm_.back().as<double>();
       }
       a.t = dct_of(bxo);
+      a.rhs = fk::Mat{nullptr, 0, 0, 0};
     }
-    add_fast("x_forward_rhs_adi_x", 14 * fb, [this, a3]() { fk::launch_x_forward(a3, 3, stream); });
+    if (use_xw) {
+      // the tile kernel stops after the rhs assembly; B2_x + Fdma_x run as warp-serial column sweeps (fast_xw.cu).
+      // Scratch: chat_ holds the [nx, ny] rhs, bconv_ (consumed by the tile kernel) the forward-sweep result
+      fk::XwAdiArgs3 w3;
+      for (int f = 0; f < 3; ++f) {
+        a3.a[f].rhs = mat_of(chat_[f]);
+        fk::XwAdiArgs& w = w3.a[f];
+        const FdmaDev& fd = solver[f]->adi[0].fdma;
+        const int m = nx - 2;
+        w.in = mat_of(chat_[f]);
+        w.tmp = mat_of(bconv_[f]);
+        w.tmp.rows = m;
+        w.out = mat_of(w_[f]);
+        perm_.push_back(upload(fk::pack_rows(m, 4, {host_of(bxo.d_b2lo), host_of(bxo.d_b2di), host_of(bxo.d_b2up), host_of(fd.fp)}, {0, 0, 0, 0})));
+        w.cf = perm_.back().as<double>();
+        perm_.push_back(upload(fk::pack_rows(m, 4, {host_of(fd.bs), host_of(fd.bp1), host_of(fd.bp2)}, {0, 0, 0})));
+        w.cb = perm_.back().as<double>();
+        w.nx = nx;
+      }
+      add_fast("x_forward_rhs", 13 * fb, [this, a3]() { fk::launch_x_forward(a3, 3, stream); });
+      add_fast("adi_x", 12 * fb, [this, w3]() { fk::launch_xw_adi(w3, 3, stream); });
+    } else {
+      add_fast("x_forward_rhs_adi_x", 14 * fb, [this, a3]() { fk::launch_x_forward(a3, 3, stream); });
+    }
   }
   // ---- 5. y half of HholtzAdi (+ pieces of the divergence) -----------------
   {

@@ -229,7 +229,8 @@ using std::min;
 #define gridDim (cuemu::gdim())
 
 static inline void __syncthreads() { cuemu::syncthreads(); }
-static inline void __syncwarp(unsigned = 0xffffffffu) {}
+// warp barrier: in the round-robin fiber model one yield lets every other thread reach the same point
+static inline void __syncwarp(unsigned = 0xffffffffu) { cuemu::yield(); }
 template <typename T>
 static inline T __shfl_sync(unsigned, T v, int src, int = 32) { return cuemu::shfl_idx(v, src); }
 template <typename T>
