@@ -193,6 +193,7 @@ struct XForwardArgs {  // forward DCT-x + dealias + rhs assembly + x half of Hho
   // mode 0: - dt/sx D_x pres ; 1: - dt dyp + dt (S_x S_y T^ + tbc) ; 2: + bcdiff
   int mode;
   Mat pres, dyp, tmp, tbc, bcdiff;
+  int tbc_rows, bcdiff_rows;  // rows >= these of tbc / bcdiff hold exact zeros and are not read
   const double *txsd, *txsl, *tysd, *tysl;
   double isx;
   B2Tabs b2;

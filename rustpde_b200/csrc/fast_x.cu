@@ -194,7 +194,7 @@ FK_DEV void xk_forward_body(const XForwardArgs& a, const XForwardArgs3& a3) {
     cplx add[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u)  // + dt ka (dxx + dyy) fieldbc (665-668)
-      add[u] = (a.mode == 2) ? ld2(a.bcdiff, min(i0 + u * (C::NTHR / 2), n - 1), col) : mk(0.0, 0.0);
+      add[u] = (a.mode == 2 && i0 + u * (C::NTHR / 2) < a.bcdiff_rows) ? ld2(a.bcdiff, min(i0 + u * (C::NTHR / 2), n - 1), col) : mk(0.0, 0.0);
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int i = i0 + u * (C::NTHR / 2);
@@ -222,7 +222,7 @@ FK_DEV void xk_forward_body(const XForwardArgs& a, const XForwardArgs3& a3) {
       for (int u = 0; u < 4; ++u) {
         const int i = min(i0 + u * (C::NTHR / 2), n - 1);
         g1[u] = ld2(a.dyp, i, col);
-        g2[u] = ld2(a.tbc, i, col);
+        g2[u] = (i < a.tbc_rows) ? ld2(a.tbc, i, col) : mk(0.0, 0.0);
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {

@@ -62,15 +62,13 @@ FK_DEV void yk_conv_body(const YConvArgs& a, const YConvArgs3& a3) {
   YK_SMEM(td, red);
   const int r0 = blockIdx.x * C::LR;
   constexpr int n = C::n, N = C::N;
-  const bool has_bc = a.bcx.p != nullptr, has_solid = a.mask.p != nullptr;
+  const bool has_bcx = a.bcx.p != nullptr, has_bcy = a.bcy.p != nullptr, has_solid = a.mask.p != nullptr;
   tile_fill<LC, C::NTHR>(td, n, [&](int j, int l) {
     const int r = min(r0 + l, a.u.rows - 1);
     double gx = a.du.p[(size_t)r * a.du.ld + j], gy = a.dv.p[(size_t)r * a.dv.ld + j];
     const double u = a.u.p[(size_t)r * a.u.ld + j], v = a.v.p[(size_t)r * a.v.ld + j];
-    if (has_bc) {
-      gx += a.bcx.p[(size_t)r * a.bcx.ld + j];
-      gy += a.bcy.p[(size_t)r * a.bcy.ld + j];
-    }
+    if (has_bcx) gx += a.bcx.p[(size_t)r * a.bcx.ld + j];  // (either may be absent: identically zero, navier.cu rebuild_bc)
+    if (has_bcy) gy += a.bcy.p[(size_t)r * a.bcy.ld + j];
     double c = fma(u, gx, v * gy);
     if (has_solid) {  // conv -= -1/eta * mask * (w [+ wbc] - value)
       double w = a.w.p[(size_t)r * a.w.ld + j];

@@ -301,6 +301,10 @@ class Navier2D {
   DevBuf red_;
   Arr stage_[4];
   bool staged_ = false;
+  // time-invariant boundary arrays: rows of tbc_ortho_ / bcdiff_ beyond these hold exact zeros (skipped by the specialised
+  // confined kernels); dxtbc_ / dytbc_ identically zero (the Rayleigh-Benard boundary field varies in y only)
+  int tbc_rows_ = 1 << 30, bcdiff_rows_ = 1 << 30;
+  bool dxtbc_zero_ = false, dytbc_zero_ = false;
   std::function<void()> fast_dyp_, fast_div_;  // specialised refresh of d/dy pres and divergence of (ux, uy), when available
   std::vector<DevBuf> perm_;  // chunk-major coefficient tables of the specialised kernels (fast.h perm_table)
   std::map<const void*, std::pair<const double*, const double*>> perm_mode_;

@@ -283,6 +283,26 @@ void Navier2D::rebuild_bc() {
   grad_to(0, 2);
   launch_combine(bcdiff_.d(), bcdiff_.d(), f.ortho.d(), nullptr, f.ortho.ld * rc, f.o0, f.o1 * rc, 1.0, dt * ka, stream);
   rt::sync(stream);
+  // how much of the time-invariant arrays is exactly zero (bc_rbc: only T_1(y) of x-mode 0 is present, so tbc has one
+  // non-zero row, its Laplacian none, and d/dx of the boundary field vanishes); the kernels skip what they need not read
+  tbc_rows_ = bcdiff_rows_ = 1 << 30;
+  dxtbc_zero_ = dytbc_zero_ = false;
+  if (!periodic) {
+    auto nz_rows = [&](const Arr& a) {
+      std::vector<double> h((size_t)a.rows * a.cols);
+      a.download(h.data(), stream);
+      rt::sync(stream);
+      int last = 0;
+      for (int i = 0; i < a.rows; ++i)
+        for (int j = 0; j < a.cols; ++j)
+          if (h[(size_t)i * a.cols + j] != 0.0) last = i + 1;
+      return last;
+    };
+    tbc_rows_ = nz_rows(tbc_ortho_);
+    bcdiff_rows_ = nz_rows(bcdiff_);
+    dxtbc_zero_ = nz_rows(dxtbc_) == 0;
+    dytbc_zero_ = nz_rows(dytbc_) == 0;
+  }
   graph_dirty_ = true;
 }
 
@@ -674,7 +694,12 @@ void Navier2D::build_step_confined_fast() {
       a.cut = dealias ? (ny * 2) / 3 : ny;  // navier.rs:1029
       a.t = dct_of(byo);
     }
-    add_fast("conv_y_forward", 17 * fb, [this, a3]() { fk::launch_y_conv(a3, 3, stream); });
+    add_fast("conv_y_forward", 17 * fb, [this, a3]() {
+      fk::YConvArgs3 b3 = a3;  // identically zero boundary gradients are not read
+      if (dxtbc_zero_) b3.a[2].bcx = fk::Mat{nullptr, 0, 0, 0};
+      if (dytbc_zero_) b3.a[2].bcy = fk::Mat{nullptr, 0, 0, 0};
+      fk::launch_y_conv(b3, 3, stream);
+    });
   }
   // ---- 4. x-forward + dealias + rhs assembly + x half of HholtzAdi ---------
   // RUSTPDE_B200_XS=1: rhs assembly / x sweeps / divergence / projection as streaming column scans (fast_xs.cu) instead
@@ -776,10 +801,18 @@ void Navier2D::build_step_confined_fast() {
         w.cb = perm_.back().as<double>();
         w.nx = nx;
       }
-      add_fast("x_forward_rhs", 13 * fb, [this, a3]() { fk::launch_x_forward(a3, 3, stream); });
+      add_fast("x_forward_rhs", 13 * fb, [this, a3]() {
+        fk::XForwardArgs3 b3 = a3;  // the zero structure of the boundary arrays is looked up at launch (graph capture) time
+        for (int f = 0; f < 3; ++f) b3.a[f].tbc_rows = tbc_rows_, b3.a[f].bcdiff_rows = bcdiff_rows_;
+        fk::launch_x_forward(b3, 3, stream);
+      });
       add_fast("adi_x", 12 * fb, [this, w3]() { fk::launch_xw_adi(w3, 3, stream); });
     } else {
-      add_fast("x_forward_rhs_adi_x", 14 * fb, [this, a3]() { fk::launch_x_forward(a3, 3, stream); });
+      add_fast("x_forward_rhs_adi_x", 14 * fb, [this, a3]() {
+        fk::XForwardArgs3 b3 = a3;
+        for (int f = 0; f < 3; ++f) b3.a[f].tbc_rows = tbc_rows_, b3.a[f].bcdiff_rows = bcdiff_rows_;
+        fk::launch_x_forward(b3, 3, stream);
+      });
     }
   }
   // ---- 5. y half of HholtzAdi (+ pieces of the divergence) -----------------

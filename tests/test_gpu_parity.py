@@ -282,6 +282,22 @@ def test_statistics_gpu(gpu, tmp_path):
     assert check_statistics(gpu, False, 128, 129, tmp_path)
 
 
+def test_navier_confined_tile_only_schedule(gpu, monkeypatch):
+    """RUSTPDE_B200_XW=0: the round-1 schedule with the ADI-x sweeps inside the tile kernel (13 launches); the default
+    (warp-serial sweeps of fast_xw.cu, 14 launches) is what every other confined test runs."""
+    import rustpde_b200 as R
+    for xw, launches in (("0", 13), ("1", 14)):
+        monkeypatch.setenv("RUSTPDE_B200_XW", xw)
+        for nx, ny, steps in ((64, 65, 10), (530, 129, 3)):
+            n = R.Navier2D.new(nx, ny, 1e5, 1.0, 0.01, 1.0, True, lib=gpu)
+            n.set_velocity(0.2, 1.0, 1.0)
+            n.set_temperature(0.2, 1.0, 1.0)
+            n.update(1)
+            assert n.launches_per_step() == launches
+            err, derr, dn, do = pc.check_navier_steps(gpu, False, nx, ny, steps, tol=1e-9, batch=2, own_eig=True)
+            assert max(derr) < 1e-9, (xw, derr, dn, do)
+
+
 def test_navier_confined_column_scan_kernels(gpu, monkeypatch):
     """RUSTPDE_B200_XS=1: the x-direction sweeps as streaming column scans (fast_xs.cu) -- same results as the tile
     kernels to rounding, fields <= 1e-9 against the oracle."""
