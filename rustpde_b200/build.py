@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_obj")
 LIB = os.path.join(HERE, "librustpde_b200.so")
-SOURCES = ["kernels.cu", "fast_x.cu", "fast_xs.cu", "fast_xw.cu", "fast_y.cu", "fast_p.cu", "tables.cu", "progbuild.cu", "field.cu", "solver.cu", "navier.cu", "snapshot.cu", "adjoint.cu", "lapack.cu", "capi.cu"]
+SOURCES = ["kernels.cu", "fast_x.cu", "fast_xs.cu", "fast_xw.cu", "fast_y.cu", "fast_p.cu", "fast_pw.cu", "tables.cu", "progbuild.cu", "field.cu", "solver.cu", "navier.cu", "snapshot.cu", "adjoint.cu", "lapack.cu", "capi.cu"]
 NVCC_FLAGS = [
     "-std=c++17",
     "-O3",

@@ -45,6 +45,9 @@ struct ModeTabs {  // per-lane A + (lam + alpha) C (fdma_tensor.rs:219-227)
   // chunk-major packed copies (perm_table): forward sweep {b2 lo, di, up, a_low[i-2], c_low[i-2], -} (W = 6),
   // backward sweep {a_up1, c_up1, a_up2, c_up2, a_up2[i-2], c_up2[i-2], a_low[i-2], c_low[i-2]} (W = 8)
   const double *pf, *pb;
+  // plain per-column copies for the warp-serial sweeps (fast_pw.cu, pack_rows): rf [m][6] = {b2 lo, di, up, a_low[i-2],
+  // c_low[i-2], 0}, rb [m][8] = {a_up1, c_up1, a_up2, c_up2, a_up2[i-2], c_up2[i-2], a_low[i-2], c_low[i-2]}
+  const double *rf, *rb;
 };
 
 bool y_supported(int n1);
@@ -355,6 +358,8 @@ struct PHholtzArgs {  // rhs assembly + per-mode Helmholtz solve on complex rows
   ModeTabs m;  // lam / inv already offset to the first row of the slab
   int ny;
   int k0;      // global kx of row 0 (slab decomposition over kx; 0 on one GPU)
+  Mat dyp;     // [mk, ny] scratch of the warp-serial kernel (mode 1: - dt/sy d/dy pres)
+  const double* rs;  // warp-serial kernel: pack_rows table [ny][4] = {sd_j, sl_{j-2}, tsd_j, tsl_{j-2}}
 };
 struct PHholtzArgs3 {
   PHholtzArgs a[3];
@@ -371,8 +376,14 @@ struct PDivPoisArgs {  // divergence + per-mode Poisson solve
   ModeTabs m;
   int ny;
   int k0;
+  const double* rs;  // warp-serial kernel: pack_rows table [ny][4] = {sd_j, sl_{j-2}, 2 j / sy, 0}
 };
 void launch_p_divpois(const PDivPoisArgs& a, cudaStream_t s);
+// the same two passes as warp-serial row sweeps (fast_pw.cu); launch_p_hholtz / launch_p_divpois pick them by row count
+// (RUSTPDE_B200_PW=0 / 1 forces the tile kernels / the row sweeps)
+bool pw_enabled(int rows, bool divpois);
+void launch_pw_hholtz(const PHholtzArgs3& a, int nbatch, cudaStream_t s);
+void launch_pw_divpois(const PDivPoisArgs& a, cudaStream_t s);
 
 struct PProjectArgs {  // projection + pressure update
   Mat phi, ux, uy;     // [mk, my]

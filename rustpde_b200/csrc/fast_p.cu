@@ -439,8 +439,14 @@ void launch_p_r2c(const PR2cArgs3& a, int nb, cudaStream_t s) { PX_LAUNCH(pk_r2c
 #define YK_CASE_pk_project(L, LCV) YK_CASE_BODY_T(pk_project, L, LCV, 0, a, NTHRS)
 
 // complex rows: a block owns 2 rows -> the launch helper's "rows / 4" becomes "2 * rows / 4"
-void launch_p_hholtz(const PHholtzArgs3& a, int nb, cudaStream_t s) { YK_LAUNCH(pk_hholtz, true, 2 * a.a[0].chat.rows, a.a[0].ny, a, nb); }
-void launch_p_divpois(const PDivPoisArgs& a, cudaStream_t s) { YK_LAUNCH(pk_divpois, true, 2 * a.ux.rows, a.ny, a, 1); }
+void launch_p_hholtz(const PHholtzArgs3& a, int nb, cudaStream_t s) {
+  if (pw_enabled(a.a[0].chat.rows, false) && a.a[0].m.rf && a.a[0].dyp.p && a.a[0].rs) return launch_pw_hholtz(a, nb, s);
+  YK_LAUNCH(pk_hholtz, true, 2 * a.a[0].chat.rows, a.a[0].ny, a, nb);
+}
+void launch_p_divpois(const PDivPoisArgs& a, cudaStream_t s) {
+  if (pw_enabled(a.ux.rows, true) && a.m.rf && a.rs) return launch_pw_divpois(a, s);
+  YK_LAUNCH(pk_divpois, true, 2 * a.ux.rows, a.ny, a, 1);
+}
 #define YK_CASE_pk_ybackward(L, LCV) YK_CASE_BODY(pk_ybackward, L, LCV, 0, a)
 #define YK_CASE_pk_yforward(L, LCV) YK_CASE_BODY(pk_yforward, L, LCV, 0, a)
 void launch_p_ybackward(const PYBackArgs3& a, int nb, cudaStream_t s) { YK_LAUNCH(pk_ybackward, false, 2 * a.a[0].src.rows, a.a[0].t.n, a, nb); }

@@ -947,6 +947,23 @@ void Navier2D::build_step_confined_fast() {
 // Periodic step on the specialised kernels (fast_p.cu + the physical-space y
 // kernels of fast_y.cu): same schedule and arrays as build_step_periodic.
 // --------------------------------------------------------------------------
+// Stencil tables of the warp-serial per-mode passes (fast_pw.cu): per column j {sd_j, sl_{j-2}, tsd_j, tsl_{j-2}} of the
+// field's own y base and of the temperature's; for the divergence {sd_j, sl_{j-2}, 2 j / sy, 0}
+void Navier2D::build_pw_tables() {
+  if (pw_rs_[0]) return;
+  const Base &byu = *ux->sp.b1, &byt = *temp->sp.b1;
+  const Base* bys[3] = {&byu, &byu, &byt};
+  const std::vector<double> tsd = host_of(byt.d_sd), tsl = host_of(byt.d_sl);
+  for (int f = 0; f < 3; ++f) {
+    perm_.push_back(upload(fk::pack_rows(ny, 4, {host_of(bys[f]->d_sd), host_of(bys[f]->d_sl), tsd, tsl}, {0, -2, 0, -2})));
+    pw_rs_[f] = perm_.back().as<double>();
+  }
+  std::vector<double> two_j(ny);
+  for (int j = 0; j < ny; ++j) two_j[j] = 2.0 * (double)j * (1.0 / scale[1]);
+  perm_.push_back(upload(fk::pack_rows(ny, 4, {host_of(byu.d_sd), host_of(byu.d_sl), two_j}, {0, -2, 0})));
+  pw_rs_[3] = perm_.back().as<double>();
+}
+
 void Navier2D::build_step_periodic_fast() {
   const Base &bx = *ux->sp.b0, &byu = *ux->sp.b1, &byt = *temp->sp.b1, &byn = *pres1->sp.b1, &byo = *field->sp.b1;
   const int mk = nx / 2 + 1;
@@ -1023,6 +1040,9 @@ void Navier2D::build_step_periodic_fast() {
     a.m = solver[f]->mode_tabs();
     a.ny = ny;
     a.k0 = 0;
+    a.dyp = mat_of(dyp_);
+    build_pw_tables();
+    a.rs = pw_rs_[f];
   }
   add_fast("rhs_hholtz_mode_y", 10 * fb, [this, h3]() { fk::launch_p_hholtz(h3, 2, stream); });
   {
@@ -1039,6 +1059,8 @@ void Navier2D::build_step_periodic_fast() {
     a.m = solver[3]->mode_tabs();
     a.ny = ny;
     a.k0 = 0;
+    build_pw_tables();
+    a.rs = pw_rs_[3];
     add_fast("divergence_poisson_mode_y", 5 * fb, [this, a]() { fk::launch_p_divpois(a, stream); });
   }
   {  // ---- 7. projection + pressure update -----------------------------------------
@@ -1183,6 +1205,9 @@ void Navier2D::slab_phase3(int k0, int mkl, const double* const in[3]) {
     a.m = slab_mode(*solver[f]);
     a.ny = ny;
     a.k0 = k0;
+    a.dyp = row_slab(dyp_, k0, mkl);
+    build_pw_tables();
+    a.rs = pw_rs_[f];
   }
   fk::launch_p_hholtz(h3, 2, stream);
   {
@@ -1200,6 +1225,8 @@ void Navier2D::slab_phase3(int k0, int mkl, const double* const in[3]) {
     a.m = slab_mode(*solver[3]);
     a.ny = ny;
     a.k0 = k0;
+    build_pw_tables();
+    a.rs = pw_rs_[3];
     fk::launch_p_divpois(a, stream);
   }
   {

@@ -250,7 +250,7 @@ fk::ModeTabs Solver2::mode_tabs() {
   t.alpha = m.alpha;
   t.inv = m.inv.as<double>();
   t.inv_ld = m.inv_ld;
-  t.pf = t.pb = nullptr;
+  t.pf = t.pb = t.rf = t.rb = nullptr;
   const fk::ScanShape ng = fk::y_scan_shape(n1);
   if (ng.ng > 0) {  // chunk-major packed copies of the raw bands (fast.h perm_table)
     const Base& by = *sp.b1;  // the B2 rows depend on n only
@@ -262,6 +262,11 @@ fk::ModeTabs Solver2::mode_tabs() {
     t.pf = perm_.back().as<double>();
     perm_.push_back(upload(fk::perm_table(mm, false, ng, 8, {au1, cu1, au2, cu2, au2, cu2, al, cl}, {0, 0, 0, 0, -2, -2, -2, -2})));
     t.pb = perm_.back().as<double>();
+    // plain per-column copies for the warp-serial sweeps (fast_pw.cu)
+    perm_.push_back(upload(fk::pack_rows(mm, 6, {host_of(by.d_b2lo), host_of(by.d_b2di), host_of(by.d_b2up), al, cl}, {0, 0, 0, -2, -2})));
+    t.rf = perm_.back().as<double>();
+    perm_.push_back(upload(fk::pack_rows(mm, 8, {au1, cu1, au2, cu2, au2, cu2, al, cl}, {0, 0, 0, 0, -2, -2, -2, -2})));
+    t.rb = perm_.back().as<double>();
   }
   mode_tabs_ = t;
   have_mode_tabs_ = true;

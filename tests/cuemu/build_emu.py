@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "rustpde_b200", "csrc")
 OUT = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT, "librustpde_b200_emu.so")
-SOURCES = ["kernels.cu", "fast_x.cu", "fast_xs.cu", "fast_xw.cu", "fast_y.cu", "fast_p.cu", "tables.cu", "progbuild.cu", "field.cu", "solver.cu", "navier.cu", "snapshot.cu", "adjoint.cu", "lapack.cu", "capi.cu"]
+SOURCES = ["kernels.cu", "fast_x.cu", "fast_xs.cu", "fast_xw.cu", "fast_y.cu", "fast_p.cu", "fast_pw.cu", "tables.cu", "progbuild.cu", "field.cu", "solver.cu", "navier.cu", "snapshot.cu", "adjoint.cu", "lapack.cu", "capi.cu"]
 FLAGS = ["-std=c++17", "-O2", "-g", "-fPIC", "-DRP_EMU", "-I", HERE, "-I", CSRC, "-fvisibility=hidden", "-Wall", "-Wno-unused-function", "-Wno-unknown-pragmas"]
 
 

@@ -264,3 +264,22 @@ def test_column_scan_kernels_agree_with_tile_kernels(emu, monkeypatch):
     monkeypatch.setenv("RUSTPDE_B200_XS", "1")
     err, derr, dn, do = pc.check_navier_steps(emu, False, 40, 33, 4, tol=1e-9, batch=2, own_eig=True)
     assert max(derr) < 1e-9
+
+
+def test_periodic_row_sweeps_agree_with_tile_kernels(emu, monkeypatch):
+    """The per-mode Helmholtz / Poisson passes of the periodic step as warp-serial row sweeps (fast_pw.cu, chosen for
+    large row counts; forced here with RUSTPDE_B200_PW=1) versus the tile kernels pk_hholtz / pk_divpois
+    (RUSTPDE_B200_PW=0): same step to rounding, ragged row counts included."""
+    import rustpde_b200 as R
+    for nx, ny in ((32, 33), (64, 65), (128, 33)):
+        outs = []
+        for pw in ("0", "1"):
+            monkeypatch.setenv("RUSTPDE_B200_PW", pw)
+            n = R.Navier2D.new_periodic(nx, ny, 1e5, 1.0, 0.01, 1.0, lib=emu)
+            assert n.kernel_path()[0]
+            n.set_velocity(0.2, 1.0, 1.0)
+            n.set_temperature(0.2, 1.0, 1.0)
+            n.update(4)
+            outs.append([np.array(f.vhat) for f in (n.temp, n.ux, n.uy, n.pres[0])])
+        for a, b in zip(*outs):
+            assert 0.0 < pc.rel(a, b) <= 1e-12  # (not bitwise equal: the two paths really are different kernels)

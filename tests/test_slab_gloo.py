@@ -11,7 +11,9 @@ import torch.multiprocessing as mp
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, nx, ny, steps, out):
+def _worker(rank, world, port, nx, ny, steps, out, pw=None):
+    if pw is not None:
+        os.environ["RUSTPDE_B200_PW"] = pw  # force the row-sweep (1) or tile (0) per-mode kernels on the slabs
     for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tests", "cuemu")):
         if p not in sys.path:
             sys.path.insert(0, p)
@@ -44,15 +46,15 @@ def _worker(rank, world, port, nx, ny, steps, out):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,nx,ny", [(2, 32, 33), (3, 32, 33), (2, 128, 129)])
-def test_slab_periodic_gloo(world, nx, ny):
+@pytest.mark.parametrize("world,nx,ny,pw", [(2, 32, 33, None), (3, 32, 33, None), (2, 128, 129, None), (3, 64, 65, "1")])
+def test_slab_periodic_gloo(world, nx, ny, pw):
     sys.path.insert(0, os.path.join(ROOT, "tests", "cuemu"))
     import build_emu  # build once in the parent so the workers do not race on the shared object
     build_emu.build()
     mgr = mp.Manager()
     out = mgr.dict()
     port = 29600 + world * 7 + (nx % 97)
-    mp.spawn(_worker, args=(world, port, nx, ny, 3, out), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, nx, ny, 3, out, pw), nprocs=world, join=True)
     assert len(out) == world
     for r in range(world):
         ok, err, diag = out[r]
