@@ -391,11 +391,13 @@ def run_slab(args, wl, rank, world, local_rank, torch, dist, lib, R, _ffi, np):
     hbm_peak, src = measured_peaks()
     contract_bytes = 408.0 * nx * ny  # periodic step = 51 field sweeps of 8 Np bytes
     ach = contract_bytes / world / (ms / args.steps * 1e-3) / 1e9
+    phases = slab.profile_step(5)  # per-phase device times of this rank (after the timed region)
     nv = slab.bytes_exchanged_per_step / (ms / args.steps * 1e-3) / 1e9
     roof = {"bound": "hbm", "kernel": "whole slab step (per rank)", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
             "traffic": None, "peak_source": src, "algorithmic_bytes_per_step_per_rank": contract_bytes / world,
             "nvlink": {"egress_bytes_per_rank_per_step": slab.bytes_exchanged_per_step, "achieved_GBps": nv, "peak_GBps": NVLINK_PEAK_GBS,
                        "frac": nv / NVLINK_PEAK_GBS, "note": "egress / whole step time: the transposes are fused into the producing kernels"},
+            "per_phase_ms_rank0": phases,
             "limiter": "per-rank kernels at 1/N of the lanes (latency-bound pass kernels, DESIGN.md 6) plus %d cross-rank fences per step" % slab.fences_per_step}
     div = None
     if rank == 0:

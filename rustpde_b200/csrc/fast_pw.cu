@@ -376,7 +376,7 @@ bool pw_enabled(int rows, bool divpois) {
   const char* e = getenv("RUSTPDE_B200_PW");  // (read at every launch: the step is a captured graph, and tests toggle it)
   if (e && e[0] == '0') return false;
   if (e && e[0] == '1') return true;
-  return rows >= (divpois ? 1280 : 448);
+  return rows >= (divpois ? 1280 : 448);  // (three fields in one launch: navier.cu)
 }
 
 template <class K>

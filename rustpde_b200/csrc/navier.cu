@@ -1044,8 +1044,20 @@ void Navier2D::build_step_periodic_fast() {
     build_pw_tables();
     a.rs = pw_rs_[f];
   }
-  add_fast("rhs_hholtz_mode_y", 10 * fb, [this, h3]() { fk::launch_p_hholtz(h3, 2, stream); });
-  {
+  if (fk::pw_enabled(mk, false)) {
+    // row sweeps (fast_pw.cu): the three fields in ONE launch -- the chains of a field are independent of the row
+    // count, so a launch of its own for the temperature would only add its latency.  The temperature solve then
+    // writes to scratch (w_[2], viewed with the pitch of temp.vhat) and is copied back, because uy reads the old field.
+    fk::PHholtzArgs3 a3 = h3;
+    a3.a[2].out = fk::Mat{w_[2].d(), temp->vhat.ld, temp->vhat.rows, temp->vhat.cols};
+    const size_t tbytes = (size_t)temp->vhat.ld * temp->vhat.rows * 16;
+    if (w_[2].buf.bytes < tbytes) throw Error(RP_ERR_INTERNAL, "periodic step: scratch smaller than temp.vhat");
+    add_fast("rhs_hholtz_mode_y", 16 * fb, [this, a3, tbytes]() {
+      fk::launch_p_hholtz(a3, 3, stream);
+      rt::d2d(temp->vhat.buf.p, w_[2].buf.p, tbytes, stream);
+    });
+  } else {
+    add_fast("rhs_hholtz_mode_y", 10 * fb, [this, h3]() { fk::launch_p_hholtz(h3, 2, stream); });
     fk::PHholtzArgs3 t3 = h3;
     t3.a[0] = h3.a[2];
     add_fast("rhs_hholtz_mode_y", 4 * fb, [this, t3]() { fk::launch_p_hholtz(t3, 1, stream); });
@@ -1209,8 +1221,13 @@ void Navier2D::slab_phase3(int k0, int mkl, const double* const in[3]) {
     build_pw_tables();
     a.rs = pw_rs_[f];
   }
-  fk::launch_p_hholtz(h3, 2, stream);
-  {
+  if (fk::pw_enabled(mkl, false)) {  // row sweeps: three fields in one launch, temperature through scratch (see build_step_periodic_fast)
+    const long long tld = temp->vhat.ld;
+    h3.a[2].out = fk::Mat{w_[2].d() + (size_t)k0 * tld * 2, tld, mkl, temp->vhat.cols};
+    fk::launch_p_hholtz(h3, 3, stream);
+    rt::d2d((char*)temp->vhat.buf.p + (size_t)k0 * tld * 16, (char*)w_[2].buf.p + (size_t)k0 * tld * 16, (size_t)mkl * tld * 16, stream);
+  } else {
+    fk::launch_p_hholtz(h3, 2, stream);
     fk::PHholtzArgs3 t3 = h3;
     t3.a[0] = h3.a[2];
     fk::launch_p_hholtz(t3, 1, stream);

@@ -73,7 +73,11 @@ class Navier2DSlab:
             self._setup_p2p(f64)
         # our kernels per slab step: phase 1 one launch (3 fields), phase 2 three (c2r value + d/dx, c2r d/dy, products + r2c),
         # phase 3 five (forward DCT-y, Helmholtz x2 + x1, divergence + Poisson, projection)
-        self.launches_per_step = 9
+        # (with the per-mode row sweeps of fast_pw.cu -- rows >= 448 unless RUSTPDE_B200_PW overrides -- the three Helmholtz
+        # solves are one launch)
+        import os
+        pw = os.environ.get("RUSTPDE_B200_PW", "")
+        self.launches_per_step = 8 if (pw[:1] == "1" or (pw[:1] != "0" and mkl >= 448)) else 9
         self.fences_per_step = 2 if self.transport == "p2p" else 0
         # NVLink egress of this rank per step: 6 arrays rows->cols, 3 arrays cols->rows (16 B per complex element)
         self.bytes_exchanged_per_step = 16 * (6 * mkl * (ny - nyl) + 3 * nyl * (mk - mkl))
@@ -173,6 +177,32 @@ class Navier2DSlab:
             for a in range(3):
                 self._cols_to_rows(self.x_out[a], self.s3[a])
             lib.call("rp_navier_slab_phase3", h, self.k0, self.mkl, self._p(self.s3))
+
+    def profile_step(self, reps=5):
+        """Device time (ms, CUDA events on the stepping stream) of the parts of one p2p slab step: phase 1, fence,
+        phase 2, fence, phase 3 -- averaged over `reps` steps.  Advances the solution like update(reps)."""
+        if self.transport != "p2p" or self.lib.emulated:
+            return None
+        lib, h = self.lib, self.nav._h
+        names = ["phase1", "fence1", "phase2", "fence2", "phase3"]
+        tot = dict.fromkeys(names, 0.0)
+        for _ in range(int(reps)):
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+            ev[0].record()
+            lib.call("rp_navier_slab_phase1_p2p", h, self.k0, self.mkl, self.world, self._joff, self._peers1)
+            ev[1].record()
+            self._fence()
+            ev[2].record()
+            lib.call("rp_navier_slab_phase2_p2p", h, self.j0, self.nyl, self._in6, C.c_void_p(self.work.data_ptr()), self.world, self._koff, self._peers2)
+            ev[3].record()
+            self._fence()
+            ev[4].record()
+            lib.call("rp_navier_slab_phase3", h, self.k0, self.mkl, self._in3)
+            ev[5].record()
+            torch.cuda.synchronize()
+            for i, n in enumerate(names):
+                tot[n] += ev[i].elapsed_time(ev[i + 1])
+        return {n: tot[n] / reps for n in names}
 
     def sync(self):
         self.nav.sync()
