@@ -306,6 +306,25 @@ struct XwAdiArgs3 {
   XwAdiArgs a[3];
 };
 void launch_xw_adi(const XwAdiArgs3& a, int nbatch, cudaStream_t s);
+struct XwDivArgs {  // div = D_x S_x vx / sx + S_x ey ; r1 = B2_x div   (one sweep, last row to first)
+  Mat vx, ey;       // [mx, ny]
+  Mat div;          // [nx, ny]
+  Mat r1;           // [mx, ny]
+  const double* tab;  // xw_div_table [nx][8]
+  int nx;
+};
+std::vector<double> xw_div_table(int n, double isx, const std::vector<double>& sd, const std::vector<double>& sl,
+                                 const std::vector<double>& lo, const std::vector<double>& di, const std::vector<double>& up);
+void launch_xw_div(const XwDivArgs& a, cudaStream_t s);
+struct XwProjectArgs {  // a1 = from_ortho_x(D_x S_x phi)/sx, a2 = from_ortho_x(S_x phi)   (two sweeps; a1 / a2 hold the intermediate)
+  Mat phi;              // [mx, my]
+  Mat a1, a2;           // [mx, my]
+  const double *t1, *t2;  // xw_project_tables [nx][8], [mx][2]
+  int nx;
+};
+void xw_project_tables(int n, double isx, const std::vector<double>& nsd, const std::vector<double>& nsl, const std::vector<double>& sd,
+                       const std::vector<double>& sl, std::vector<double>& t1, std::vector<double>& t2);
+void launch_xw_project(const XwProjectArgs& a, cudaStream_t s);
 
 // Destination of a fused transpose: part q (a peer GPU's buffer, mapped through CUDA IPC, or a local one) owns
 // the global indices [beg[q], beg[q+1]) along the scattered axis.  nparts == 0: no scatter (dense output).

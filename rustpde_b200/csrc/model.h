@@ -305,6 +305,7 @@ class Navier2D {
   // confined kernels); dxtbc_ / dytbc_ identically zero (the Rayleigh-Benard boundary field varies in y only)
   int tbc_rows_ = 1 << 30, bcdiff_rows_ = 1 << 30;
   bool dxtbc_zero_ = false, dytbc_zero_ = false;
+  fk::XwDivArgs xw_div_{};  // warp-serial divergence sweep (fast_xw.cu), when the step uses it
   std::function<void()> fast_dyp_, fast_div_;  // specialised refresh of d/dy pres and divergence of (ux, uy), when available
   std::vector<DevBuf> perm_;  // chunk-major coefficient tables of the specialised kernels (fast.h perm_table)
   const double* pw_rs_[4] = {nullptr, nullptr, nullptr, nullptr};  // stencil tables of the warp-serial periodic passes (fast_pw.cu): ux, uy, temp, divergence

@@ -710,6 +710,9 @@ void Navier2D::build_step_confined_fast() {
   // column sweeps (fast_xw.cu)
   const char* nxw = getenv("RUSTPDE_B200_XW");
   const bool use_xw = !use_xs && fk::xw_supported(nx) && !(nxw && nxw[0] == '0');
+  // RUSTPDE_B200_XW=2: divergence and projection as warp-serial sweeps too.  Parity-green but slower (one warp per
+  // strip and ~40 instructions per chain step: 0.190 / 0.233 ms against 0.083 / 0.109 ms of the tile kernels), so opt-in
+  const bool use_xw2 = use_xw && nxw && nxw[0] == '2';
   if (use_xs) {
     // forward DCT-x (tile kernel) -> chat = -dt * cut(F_x conv); then rhs assembly + B2_x + Fdma_x as streaming column scans
     fk::XFdctArgs3 d3;
@@ -850,7 +853,15 @@ void Navier2D::build_step_confined_fast() {
     a.isx = isx;
     a.b2 = b2_of(bxo);
     a.nx = nx;
-    if (use_xs)
+    if (use_xw2) {
+      perm_.push_back(upload(fk::xw_div_table(nx, isx, host_of(bxu.d_sd), host_of(bxu.d_sl), host_of(bxo.d_b2lo), host_of(bxo.d_b2di),
+                                              host_of(bxo.d_b2up))));
+      xw_div_.vx = a.vx, xw_div_.ey = a.ey, xw_div_.div = a.div, xw_div_.r1 = a.r1;
+      xw_div_.tab = perm_.back().as<double>();
+      xw_div_.nx = nx;
+      const fk::XwDivArgs w = xw_div_;
+      add_fast("divergence_b2x", 4 * fb, [this, w]() { fk::launch_xw_div(w, stream); });
+    } else if (use_xs)
       add_fast("divergence_b2x", 4 * fb, [this, a]() { fk::launch_xs_div(a, stream); });
     else
       add_fast("divergence_b2x", 4 * fb, [this, a]() { fk::launch_x_div(a, stream); });
@@ -871,7 +882,18 @@ void Navier2D::build_step_confined_fast() {
   ops_.push_back(StepOp{3, 0});  // pres[1].vhat[[0,0]] = 0   (navier.rs:714)
   opinfo_.push_back(OpInfo{"zero_mode00", 8.0, 0.0});
   // ---- 10-11. projection (navier.rs:683-695) --------------------------------
-  if (use_xs) {
+  if (use_xw2) {
+    fk::XwProjectArgs a;
+    a.phi = mat_of(pres1->vhat), a.a1 = mat_of(a1_), a.a2 = mat_of(a2_);
+    std::vector<double> t1, t2;
+    fk::xw_project_tables(nx, isx, host_of(bxn.d_sd), host_of(bxn.d_sl), host_of(bxu.d_sd), host_of(bxu.d_sl), t1, t2);
+    perm_.push_back(upload(t1));
+    a.t1 = perm_.back().as<double>();
+    perm_.push_back(upload(t2));
+    a.t2 = perm_.back().as<double>();
+    a.nx = nx;
+    add_fast("project_x", 3 * fb, [this, a]() { fk::launch_xw_project(a, stream); });
+  } else if (use_xs) {
     fk::XsProjectArgs a;
     a.phi = mat_of(pres1->vhat), a.a1 = mat_of(a1_), a.a2 = mat_of(a2_);
     a.p = mat_of(xs_p_), a.d = mat_of(xs_d_);
@@ -932,9 +954,12 @@ void Navier2D::build_step_confined_fast() {
     xd.isx = isx;
     xd.b2 = b2_of(bxo);
     xd.nx = nx;
-    fast_div_ = [this, dp, xd, use_xs]() {
+    const fk::XwDivArgs xwd = xw_div_;
+    fast_div_ = [this, dp, xd, xwd, use_xs, use_xw2]() {
       fk::launch_y_divprep(dp, stream);
-      if (use_xs)
+      if (use_xw2)
+        fk::launch_xw_div(xwd, stream);
+      else if (use_xs)
         fk::launch_xs_div(xd, stream);
       else
         fk::launch_x_div(xd, stream);

@@ -244,12 +244,13 @@ def test_band_rel_metric():
 
 
 def test_column_scan_kernels_agree_with_tile_kernels(emu, monkeypatch):
-    """The three schedules of the x-direction banded sweeps give the same step to rounding: tile kernels only
-    (RUSTPDE_B200_XW=0, 13 launches), the default (warp-serial ADI-x sweeps of fast_xw.cu, 14 launches) and the streaming
-    column scans (RUSTPDE_B200_XS=1, fast_xs.cu, 15 launches); the last one also against the oracle."""
+    """The schedules of the x-direction banded sweeps give the same step to rounding: tile kernels only
+    (RUSTPDE_B200_XW=0, 13 launches), the default (warp-serial ADI-x sweeps of fast_xw.cu, 14 launches), divergence and
+    projection as warp-serial sweeps too (RUSTPDE_B200_XW=2, 14 launches) and the streaming column scans
+    (RUSTPDE_B200_XS=1, fast_xs.cu, 15 launches); the last one also against the oracle."""
     import rustpde_b200 as R
     outs = []
-    for xw, xs in (("0", "0"), ("1", "0"), ("1", "1")):
+    for xw, xs in (("0", "0"), ("1", "0"), ("2", "0"), ("1", "1")):
         monkeypatch.setenv("RUSTPDE_B200_XW", xw)
         monkeypatch.setenv("RUSTPDE_B200_XS", xs)
         n = R.Navier2D.new(40, 33, 1e5, 1.0, 0.01, 1.0, True, lib=emu)
@@ -257,7 +258,7 @@ def test_column_scan_kernels_agree_with_tile_kernels(emu, monkeypatch):
         n.set_temperature(0.2, 1.0, 1.0)
         n.update(4)
         outs.append([np.array(f.vhat) for f in (n.temp, n.ux, n.uy, n.pres[0])] + [n.launches_per_step()])
-    assert [o[-1] for o in outs] == [13, 14, 15]
+    assert [o[-1] for o in outs] == [13, 14, 14, 15]
     for other in outs[1:]:
         for a, b in zip(outs[0][:-1], other[:-1]):
             assert pc.rel(a, b) <= 1e-12

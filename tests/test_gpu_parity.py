@@ -295,9 +295,10 @@ def test_statistics_gpu(gpu, tmp_path):
 
 def test_navier_confined_tile_only_schedule(gpu, monkeypatch):
     """RUSTPDE_B200_XW=0: the round-1 schedule with the ADI-x sweeps inside the tile kernel (13 launches); the default
-    (warp-serial sweeps of fast_xw.cu, 14 launches) is what every other confined test runs."""
+    (warp-serial ADI-x sweeps of fast_xw.cu, 14 launches) is what every other confined test runs; RUSTPDE_B200_XW=2 runs
+    the divergence and the projection as warp-serial sweeps too (xw_div, xw_project: UL order of the from_ortho solve)."""
     import rustpde_b200 as R
-    for xw, launches in (("0", 13), ("1", 14)):
+    for xw, launches in (("0", 13), ("1", 14), ("2", 14)):
         monkeypatch.setenv("RUSTPDE_B200_XW", xw)
         for nx, ny, steps in ((64, 65, 10), (530, 129, 3)):
             n = R.Navier2D.new(nx, ny, 1e5, 1.0, 0.01, 1.0, True, lib=gpu)
