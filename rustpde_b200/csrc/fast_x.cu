@@ -33,7 +33,11 @@ struct XCfg {
   // the second-order sweep of xk_forward borrows the (then idle) A tile as scratch when it is large enough
   static constexpr int NSC2 = scan2v_bytes(NSC) <= ABYTES ? NSC : NSC / 2;
   static constexpr int SMEM_AA = 2 * ABYTES + RED;
-  static constexpr int SMEM_AW = (AROWS + LB) * LR * 8 + RED;
+  // W tile: Lb rows of the Bluestein FFT, plus room for a strip of n <= Lb / 2 + 1 rows staged behind the result of a
+  // power-of-two DCT, which occupies rows [0, Lb / 2 + 4) (xk_forward)
+  static constexpr int WROWS = LB + 16;
+  static constexpr int SMEM_AW = (AROWS + WROWS) * LR * 8 + RED;
+  static_assert(SMEM_AW <= 227 * 1024, "shared memory of the x kernels");
   static constexpr int MINB = SMEM_AW > 110 * 1024 ? 1 : 2;
   static_assert(scan1v_bytes(NSC) <= RED && scan2v_bytes(NSC / 2) <= RED, "scan scratch");
 };
@@ -80,15 +84,36 @@ FK_DEV void xstencil_tile(cplx* dst, const cplx* src, int n, const double* __res
   }
 }
 
+// DCT-I along the x tile: tile A (natural layout, n rows) -> tile W (split(N) layout); A is left untouched and idle
+// from `after_pre()` on.  Odd periods N = n - 1 (n0 = 2^k, every BASELINE configuration) go through Bluestein; a
+// power-of-two period (n0 = 2^k + 1: the tables hold no chirp) is copied to W and transformed in place by the y
+// kernels' dct_pow2 -- N = Lb / 2, the same thread count and tile rows (P2 instantiations of the kernels, chosen at launch).
+template <int LOG2LB, int NTHR, bool BWD, bool P2, class Hook>
+FK_DEV void dct_x(const cplx* ta, cplx* tw, const DctTab& T, double* red, Hook after_pre) {
+  if constexpr (!P2) {
+    dct_bluestein<2, LOG2LB, NTHR, BWD>((const double*)ta, (double*)tw, T, red, after_pre);
+  } else {
+    const int c = threadIdx.x & 1;
+    for (int i = threadIdx.x >> 1; i < T.n; i += NTHR / 2) tw[cidx<2>(i, c)] = ta[cidx<2>(i, c)];
+    __syncthreads();
+    after_pre();
+    dct_pow2<2, LOG2LB - 1, NTHR, BWD>((double*)tw, T, red);
+  }
+}
+template <int LOG2LB, int NTHR, bool BWD, bool P2>
+FK_DEV void dct_x(const cplx* ta, cplx* tw, const DctTab& T, double* red) {
+  dct_x<LOG2LB, NTHR, BWD, P2>(ta, tw, T, red, [] {});
+}
+
 // ---------------------------------------------------------------------------------
-template <int LOG2LB>
+template <int LOG2LB, bool P2>
 FK_DEV void xk_backward_body(const XBackwardArgs& a, const XBackwardArgs3& a3) {
   typedef XCfg<LOG2LB> C;
   constexpr int LR = C::LR;
   RP_DYN_SMEM(double, ta_);
   cplx* ta = (cplx*)ta_;
   cplx* tw = ta + C::AROWS * 2;
-  double* red = (double*)(tw + C::LB * 2);
+  double* red = (double*)(tw + C::WROWS * 2);
   const int c0 = blockIdx.x * LR, col = c0 + 2 * (threadIdx.x & 1), c = threadIdx.x & 1;
   const int n = a.t.n, N = n - 1;
   xfill<C::NTHR>(tw, n - 2, [&](int i) { return ld2(a.src, i, col); });
@@ -102,21 +127,21 @@ FK_DEV void xk_backward_body(const XBackwardArgs& a, const XBackwardArgs3& a3) {
   for (int pass = 0; pass < 2; ++pass) {
     const Mat& o = pass ? a.dx : a.val;
     if (pass) cheb_diff_v<2, C::NTHR, C::NMAX>(ta, -1, ta, -1, n, a.isx, red);
-    dct_bluestein<2, LOG2LB, C::NTHR, true>((const double*)ta, (double*)tw, a.t, red);
+    dct_x<LOG2LB, C::NTHR, true, P2>(ta, tw, a.t, red);
     for (int i = threadIdx.x >> 1; i < n; i += C::NTHR / 2) st2(o, i, col, tw[cidx<2>(rowof(N, i), c)]);
     __syncthreads();
   }
 }
 // blockIdx.y selects the field; the branch is block-uniform and keeps every argument a direct constant-bank
 // operand (a dynamically indexed `a3.a[blockIdx.y]` costs an LDC per access)
-template <int LOG2LB>
+template <int LOG2LB, bool P2>
 __global__ void __launch_bounds__(XCfg<LOG2LB>::NTHR, XCfg<LOG2LB>::MINB) xk_backward(XBackwardArgs3 a3) {
   if (blockIdx.y == 0)
-    xk_backward_body<LOG2LB>(a3.a[0], a3);
+    xk_backward_body<LOG2LB, P2>(a3.a[0], a3);
   else if (blockIdx.y == 1)
-    xk_backward_body<LOG2LB>(a3.a[1], a3);
+    xk_backward_body<LOG2LB, P2>(a3.a[1], a3);
   else
-    xk_backward_body<LOG2LB>(a3.a[2], a3);
+    xk_backward_body<LOG2LB, P2>(a3.a[2], a3);
 }
 
 // Asynchronous staging of a 4-column strip (cp.async, 16 bytes per thread and row): dst[i][c] = (f[i][col], f[i][col+1])
@@ -150,15 +175,15 @@ FK_DEV void xstencil_cols(cplx* t, const Mat& f, int nrows, int col, const Stenc
   }
 }
 
-template <int LOG2LB>
+template <int LOG2LB, bool P2>
 FK_DEV void xk_forward_body(const XForwardArgs& a, const XForwardArgs3& a3) {
   typedef XCfg<LOG2LB> C;
   constexpr int LR = C::LR;
   RP_DYN_SMEM(double, ta_);
   cplx* ta = (cplx*)ta_;
   cplx* tw = ta + C::AROWS * 2;
-  cplx* tu = tw + (C::LB / 2) * 2;  // rows [LB/2, LB) of W: idle once the inverse transform is done
-  double* red = (double*)(tw + C::LB * 2);
+  cplx* tu = tw + C::AROWS * 2;  // rows [LB/2 + 8, ..) of W: idle once the inverse transform is done
+  double* red = (double*)(tw + C::WROWS * 2);
   const int c0 = blockIdx.x * LR, col = c0 + 2 * (threadIdx.x & 1), c = threadIdx.x & 1;
   const int n = a.t.n, N = n - 1;
   const int mxr = n - 2;
@@ -170,7 +195,7 @@ FK_DEV void xk_forward_body(const XForwardArgs& a, const XForwardArgs3& a3) {
   __syncthreads();
   // The strips of the later phases are staged asynchronously (cp.async) into tiles that are idle at the time: the
   // old field into A under the FFT stages, pres / temp into the upper half of W under the rhs assembly.
-  dct_bluestein<2, LOG2LB, C::NTHR, false>((const double*)ta, (double*)tw, a.t, red, [&] { xstage<C::NTHR>(ta, a.fld, mxr, col); });
+  dct_x<LOG2LB, C::NTHR, false, P2>(ta, tw, a.t, red, [&] { xstage<C::NTHR>(ta, a.fld, mxr, col); });
   if (a.mode == 0)
     xstage<C::NTHR>(tu, a.pres, n, col);
   else if (a.mode == 1)
@@ -246,25 +271,25 @@ FK_DEV void xk_forward_body(const XForwardArgs& a, const XForwardArgs3& a3) {
 }
 // blockIdx.y selects the field; the branch is block-uniform and keeps every argument a direct constant-bank
 // operand (a dynamically indexed `a3.a[blockIdx.y]` costs an LDC per access)
-template <int LOG2LB>
+template <int LOG2LB, bool P2>
 __global__ void __launch_bounds__(XCfg<LOG2LB>::NTHR, XCfg<LOG2LB>::MINB) xk_forward(XForwardArgs3 a3) {
   if (blockIdx.y == 0)
-    xk_forward_body<LOG2LB>(a3.a[0], a3);
+    xk_forward_body<LOG2LB, P2>(a3.a[0], a3);
   else if (blockIdx.y == 1)
-    xk_forward_body<LOG2LB>(a3.a[1], a3);
+    xk_forward_body<LOG2LB, P2>(a3.a[1], a3);
   else
-    xk_forward_body<LOG2LB>(a3.a[2], a3);
+    xk_forward_body<LOG2LB, P2>(a3.a[2], a3);
 }
 
 // forward DCT-x + dealias cut + scale only: the rhs assembly and the x sweeps run as streaming column scans (fast_xs.cu)
-template <int LOG2LB>
+template <int LOG2LB, bool P2>
 FK_DEV void xk_fdct_body(const XFdctArgs& a, const XFdctArgs3& a3) {
   typedef XCfg<LOG2LB> C;
   constexpr int LR = C::LR;
   RP_DYN_SMEM(double, ta_);
   cplx* ta = (cplx*)ta_;
   cplx* tw = ta + C::AROWS * 2;
-  double* red = (double*)(tw + C::LB * 2);
+  double* red = (double*)(tw + C::WROWS * 2);
   const int c0 = blockIdx.x * LR, col = c0 + 2 * (threadIdx.x & 1), c = threadIdx.x & 1;
   const int n = a.t.n, N = n - 1;
   xfill<C::NTHR>(ta, n, [&](int i) { return ld2(a.conv, i, col); });
@@ -273,18 +298,18 @@ FK_DEV void xk_fdct_body(const XFdctArgs& a, const XFdctArgs3& a3) {
     if (nxt < (int)(gridDim.x * gridDim.y)) xprefetch<C::NTHR, false>(a3.a[nxt / gridDim.x].conv, (nxt % gridDim.x) * LR, n);
   }
   __syncthreads();
-  dct_bluestein<2, LOG2LB, C::NTHR, false>((const double*)ta, (double*)tw, a.t, red);
+  dct_x<LOG2LB, C::NTHR, false, P2>(ta, tw, a.t, red);
   for (int i = threadIdx.x >> 1; i < n; i += C::NTHR / 2)
     st2(a.out, i, col, (i < a.cut) ? cscale(tw[cidx<2>(rowof(N, i), c)], a.scale) : mk(0.0, 0.0));
 }
-template <int LOG2LB>
+template <int LOG2LB, bool P2>
 __global__ void __launch_bounds__(XCfg<LOG2LB>::NTHR, XCfg<LOG2LB>::MINB) xk_fdct(XFdctArgs3 a3) {
   if (blockIdx.y == 0)
-    xk_fdct_body<LOG2LB>(a3.a[0], a3);
+    xk_fdct_body<LOG2LB, P2>(a3.a[0], a3);
   else if (blockIdx.y == 1)
-    xk_fdct_body<LOG2LB>(a3.a[1], a3);
+    xk_fdct_body<LOG2LB, P2>(a3.a[1], a3);
   else
-    xk_fdct_body<LOG2LB>(a3.a[2], a3);
+    xk_fdct_body<LOG2LB, P2>(a3.a[2], a3);
 }
 
 template <int LOG2LB>
@@ -391,9 +416,7 @@ ScanShape x_scan2_shape(int n0) {
 
 bool x_supported(int n0) {
   if (n0 < 8) return false;
-  const int N = n0 - 1;
-  if ((N & (N - 1)) == 0) return false;  // power-of-two period: the tables hold no chirp
-  const int l = bluestein_log2(n0);
+  const int l = bluestein_log2(n0);  // (a power-of-two period N runs dct_pow2 inside the tile of Lb = 2 N: dct_x)
 #define X(L, LCV) \
   if (l == L) return true;
   XK_SIZES(X)
@@ -424,12 +447,26 @@ static void set_smem(K kern, int bytes) {
     RP_LAUNCH(kp_, dim3(nb_, nby_), dim3(C::NTHR), (size_t)sm_, s, a);           \
     ok_ = true;                                                                  \
   }
-#define XK_CASE_xk_backward(L, LCV) XK_CASE_BODY(xk_backward, L, LCV, C::SMEM_AW)
-#define XK_CASE_xk_forward(L, LCV) XK_CASE_BODY(xk_forward, L, LCV, C::SMEM_AW)
+// kernels with a DCT: the Bluestein instantiation, or the power-of-two one when the tables hold no chirp (p2_)
+#define XK_CASE_BODY_DCT(kern, L, LCV, smem_expr)                                \
+  if (!ok_ && l_ == L) {                                                         \
+    typedef XCfg<L> C;                                                           \
+    auto kp_ = p2_ ? kern<L, true> : kern<L, false>;                             \
+    const int sm_ = (smem_expr);                                                 \
+    const int nb_ = ((ncols_) + C::LR - 1) / C::LR;                              \
+    static unsigned long long init_[2] = {0, 0}; /* one bit per device */       \
+    if (first_use_on_device(init_[p2_ ? 1 : 0])) {                               \
+      set_smem(kp_, sm_);                                                        \
+    }                                                                            \
+    RP_LAUNCH(kp_, dim3(nb_, nby_), dim3(C::NTHR), (size_t)sm_, s, a);           \
+    ok_ = true;                                                                  \
+  }
+#define XK_CASE_xk_backward(L, LCV) XK_CASE_BODY_DCT(xk_backward, L, LCV, C::SMEM_AW)
+#define XK_CASE_xk_forward(L, LCV) XK_CASE_BODY_DCT(xk_forward, L, LCV, C::SMEM_AW)
 #define XK_CASE_xk_div(L, LCV) XK_CASE_BODY(xk_div, L, LCV, C::SMEM_AA)
 #define XK_CASE_xk_project(L, LCV) XK_CASE_BODY(xk_project, L, LCV, C::SMEM_AA)
 #define XK_CASE_xk_adi(L, LCV) XK_CASE_BODY(xk_adi, L, LCV, C::SMEM_AA)
-#define XK_CASE_xk_fdct(L, LCV) XK_CASE_BODY(xk_fdct, L, LCV, C::SMEM_AW)
+#define XK_CASE_xk_fdct(L, LCV) XK_CASE_BODY_DCT(xk_fdct, L, LCV, C::SMEM_AW)
 
 #define XK_LAUNCH(kern, ncols, nx, nby)                                            \
   do {                                                                             \
@@ -467,16 +504,19 @@ static int sm_count() {
 void launch_x_backward(const XBackwardArgs3& a_, int nb, cudaStream_t s) {
   XBackwardArgs3 a = a_;
   a.next_wave = sm_count();  // the block that follows on the same SM is about one wave ahead
+  const bool p2_ = a.a[0].t.chirp == nullptr;
   XK_LAUNCH(xk_backward, a.a[0].src.cols, a.a[0].t.n, nb);
 }
 void launch_x_forward(const XForwardArgs3& a_, int nb, cudaStream_t s) {
   XForwardArgs3 a = a_;
   a.next_wave = sm_count();
+  const bool p2_ = a.a[0].t.chirp == nullptr;
   XK_LAUNCH(xk_forward, a.a[0].conv.cols, a.a[0].t.n, nb);
 }
 void launch_x_fdct(const XFdctArgs3& a_, int nb, cudaStream_t s) {
   XFdctArgs3 a = a_;
   a.next_wave = sm_count();
+  const bool p2_ = a.a[0].t.chirp == nullptr;
   XK_LAUNCH(xk_fdct, a.a[0].conv.cols, a.a[0].t.n, nb);
 }
 void launch_x_div(const XDivArgs& a, cudaStream_t s) { XK_LAUNCH(xk_div, a.vx.cols, a.nx, 1); }

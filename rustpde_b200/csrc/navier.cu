@@ -351,15 +351,15 @@ void Navier2D::build_step() {
     build_step_confined();
   launches_per_step_ = (int)ops_.size();
   if (fast_ok && fast_ops_.empty() && (long long)nx * ny >= 256 * 256 && !getenv("RUSTPDE_B200_QUIET")) {
-    // a performance cliff worth a line: the specialised kernels cover y lanes of 2^k + 1 points, confined x lanes whose
-    // period n-1 is NOT a power of two (Bluestein; 2^k + 1 points have no chirp tables) and periodic x lanes of 2^k points
+    // a performance cliff worth a line: the specialised kernels cover y lanes of 2^k + 1 points, confined x lanes of
+    // 17 .. 2049 points (Bluestein, or the power-of-two DCT when nx = 2^k + 1) and periodic x lanes of 2^k points
     static bool warned = false;
     if (!warned) {
       warned = true;
       fprintf(stderr,
               "[rustpde_b200] Navier2D %dx%d %s runs on the generic lane programs (several times slower): the specialised kernels "
               "need ny = 2^k + 1 and %s\n",
-              nx, ny, periodic ? "periodic" : "confined", periodic ? "nx = 2^k" : "nx - 1 not a power of two (e.g. nx = 2^k)");
+              nx, ny, periodic ? "periodic" : "confined", periodic ? "nx = 2^k" : "17 <= nx <= 2049");
     }
   }
   if (getenv("RUSTPDE_B200_VERBOSE"))

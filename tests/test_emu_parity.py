@@ -127,6 +127,16 @@ def test_navier_confined_specialised_kernels(emu, nx, ny, adiabatic, own_eig):
     assert max(derr) < 1e-9, (derr, dn, do)
 
 
+@pytest.mark.parametrize("nx,ny,own_eig", [(33, 33, False), (65, 65, True), (129, 33, True), (257, 33, False)])
+def test_navier_confined_pow2_period_x(emu, nx, ny, own_eig):
+    """nx = 2^k + 1 (the usual Gauss-Lobatto choice): the DCT period along x is a power of two, the x kernels run the y
+    kernels' dct_pow2 inside the Bluestein tile (fast_x.cu dct_x) -- these grids were on the lane programs before."""
+    import rustpde_b200 as R
+    assert R.Navier2D.new(nx, ny, 1e5, 1.0, 0.01, 1.0, True, lib=emu).kernel_path() == (True, True)
+    err, derr, dn, do = pc.check_navier_steps(emu, False, nx, ny, 4, tol=1e-9, batch=2, own_eig=own_eig)
+    assert max(derr) < 1e-9, (derr, dn, do)
+
+
 @pytest.mark.parametrize("nx,ny", [(530, 129), (1030, 33), (300, 257), (200, 65)])
 def test_navier_confined_specialised_kernels_partial_lanes(emu, nx, ny):
     """x lanes much shorter than the instantiated Bluestein length (2048 / 4096): the chunk-major coefficient tables

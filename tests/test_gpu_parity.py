@@ -374,6 +374,16 @@ def test_staged_state_upload(gpu, periodic, nx, ny):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("nx,ny,steps", [(33, 33, 6), (129, 129, 6), (1025, 129, 3), (2049, 65, 2)])
+def test_navier_confined_pow2_period_x(gpu, nx, ny, steps):
+    """nx = 2^k + 1: power-of-two DCT period along x inside the x kernels (fast_x.cu dct_x), up to the largest tile."""
+    import rustpde_b200 as R
+    assert R.Navier2D.new(nx, ny, 1e5, 1.0, 0.01, 1.0, True, lib=gpu).kernel_path() == (True, True)
+    err, derr, dn, do = pc.check_navier_steps(gpu, False, nx, ny, steps, tol=1e-9, batch=2, own_eig=True)
+    assert max(derr) < 1e-9, (derr, dn, do)
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("nx,ny", [(530, 129), (1030, 33), (300, 257), (200, 65)])
 def test_navier_confined_partial_lanes(gpu, nx, ny):
     """x lanes much shorter than the instantiated Bluestein length (2048 / 4096 rows): chunk-major coefficient tables
