@@ -646,6 +646,17 @@ def run_ours(args, wl, rank, world, local_rank):
                     "frac": ach / hbm_peak, "traffic": traffic, "peak_source": src, "share_of_step": g["ms"] / tot,
                     "algorithmic_bytes_per_launch": g["bytes"] / g["n"]}
         roof["fp64_dgemm_peak_TFLOPs"] = fp64_peak
+        limiter = {
+            "x_backward_dct": "FP64 instruction issue and shared-memory latency, not HBM: six 2047-point Bluestein DCTs per 4-column tile "
+                              "(two 4096-point FFTs each), one 512-thread block per SM at 128 registers (profiles/r3_ncu_xk_backward_confined2048.txt: "
+                              "FP64 pipe 31 %, DRAM 6 %)",
+            "x_forward_rhs": "as x_backward_dct: three Bluestein DCTs per tile plus the rhs assembly, one block per SM",
+            "x_forward_rhs_adi_x": "as x_backward_dct: three Bluestein DCTs per tile plus rhs assembly and ADI-x sweeps, one block per SM",
+            "y_backward": "L1 / shared-memory throughput (l1tex 83 %) and latency at two 512-thread blocks per SM (profiles/r3_ncu_yk_backward_confined2048.txt)",
+            "rhs_hholtz_mode_y": "latency of the per-mode recurrences (tile kernel) / of one warp-serial chain (row sweeps), DESIGN.md 4.4",
+        }.get(name)
+        if limiter:
+            roof["limiter"] = limiter
         step_bytes = sum(o["bytes"] for o in prof)
         roof["whole_step"] = {"algorithmic_bytes": step_bytes, "GBps": step_bytes / (ms / args.steps * 1e-3) / 1e9,
                               "frac_hbm": step_bytes / (ms / args.steps * 1e-3) / 1e9 / hbm_peak,
