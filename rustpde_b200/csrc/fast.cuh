@@ -1061,7 +1061,14 @@ FK_DEV void scan2v(int n, double* red_, In in, C1 c1, C2 c2, Out out) {
         if (u0 + v < CL) {
           const int i = idx(min(t0 + u0 + v, M - 1));
           const int sl = ((u0 + v) * NG + g) * 2 + p;
-          qq[v] = CACHE ? q[u0 + v] : fcall(in, i, c, sl);
+          // (elements past the end of the chunk belong to the next group, which is rewriting them in place during this
+          // walk: their values are never used, so they are not read either -- compute-sanitizer racecheck)
+          if (CACHE)
+            qq[v] = q[u0 + v];
+          else if (t0 + u0 + v < t1)
+            qq[v] = fcall(in, i, c, sl);
+          else
+            qq[v] = zero;
           k1[v] = fcall(c1, i, c, sl);
           k2[v] = fcall(c2, i, c, sl);
         }
