@@ -412,8 +412,16 @@ struct PProjectArgs {  // projection + pressure update
   double isx, isy, nu, inv_dt;
   int ny;
   int k0;
+  // row-sweep form (fast_pw.cu pw_project), optional: pw_project_tables of the y bases and two [mk, my] complex scratch arrays
+  const double *w1 = nullptr, *w2 = nullptr;
+  Mat z1{nullptr, 0, 0, 0}, z2{nullptr, 0, 0, 0};
 };
-void launch_p_project(const PProjectArgs& a, cudaStream_t s);
+void launch_p_project(const PProjectArgs& a, cudaStream_t s);  // picks pw_project by row count when the tables are there
+void launch_pw_project(const PProjectArgs& a, cudaStream_t s);
+void pw_project_tables(int n, double isy, const std::vector<double>& nsd, const std::vector<double>& nsl, const std::vector<double>& sd,
+                       const std::vector<double>& sl, const std::vector<double>& fs, const std::vector<double>& fp,
+                       const std::vector<double>& bp, std::vector<double>& w1, std::vector<double>& w2);
+bool pw_project_enabled(int rows);
 
 // slab decomposition over kx: the y transforms run on complex rows of the kx slab, before (backward) and
 // after (forward) the x transform on y slabs -- the operators commute

@@ -451,7 +451,10 @@ void launch_p_divpois(const PDivPoisArgs& a, cudaStream_t s) {
 #define YK_CASE_pk_yforward(L, LCV) YK_CASE_BODY(pk_yforward, L, LCV, 0, a)
 void launch_p_ybackward(const PYBackArgs3& a, int nb, cudaStream_t s) { YK_LAUNCH(pk_ybackward, false, 2 * a.a[0].src.rows, a.a[0].t.n, a, nb); }
 void launch_p_yforward(const PYFwdArgs3& a, int nb, cudaStream_t s) { YK_LAUNCH(pk_yforward, false, 2 * a.a[0].src.rows, a.a[0].t.n, a, nb); }
-void launch_p_project(const PProjectArgs& a, cudaStream_t s) { YK_LAUNCH(pk_project, false, 2 * a.phi.rows, a.ny, a, 1); }
+void launch_p_project(const PProjectArgs& a, cudaStream_t s) {
+  if (pw_project_enabled(a.phi.rows) && a.w1 && a.w2 && a.z1.p && a.z2.p) return launch_pw_project(a, s);
+  YK_LAUNCH(pk_project, false, 2 * a.phi.rows, a.ny, a, 1);
+}
 
 }  // namespace fk
 }  // namespace rp

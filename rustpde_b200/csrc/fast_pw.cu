@@ -2,6 +2,7 @@
 //
 //   pw_hholtz  : rhs assembly (navier.rs:622-674) + per-mode Helmholtz solve (hholtz.rs:156-197, fdma.rs:101-118)
 //   pw_divpois : divergence (navier.rs:698-703) + per-mode Poisson solve (poisson.rs:131-149)
+//   pw_project : projection + pressure update (navier.rs:683-721)
 //
 // The tile kernels of fast_p.cu (pk_hholtz, pk_divpois) hold a whole lane in shared memory and cut every recurrence
 // into 64 .. 128 chunks (two walks and a carry exchange per scan).  For long lanes that leaves one small block per SM
@@ -321,6 +322,162 @@ FK_DEV void pw_div_pass(const PDivPoisArgs& a, double* ring, int r0, int lane) {
   }
 }
 
+// Projection + pressure update (navier.rs:683-721) as three row sweeps, the from_ortho solves in the reference's own
+// order (S^T, then the pre-factored (S^T S) forward and backward substitution of linalg.rs:14-57):
+//   pass 1 (last column to first)  o_j = nsd_j phi_j + nsl_{j-2} phi_{j-2}   (to_ortho of the pseudo-pressure, Neumann stencil)
+//                                  p_j += -nu div_j + o_j / dt                                              (717-721)
+//                                  d_j = (j == 0 ? 1/2 : 1) sum_{k = j+1, j+3, ..} (2 k / sy) o_k           (ortho.rs:107-125)
+//                                  c_i = sd_i t_i + sl_i t_{i+2},  t = i k / sx o  |  d      -> scratch z1 (ux), z2 (uy)
+//   pass 2 (first column to last)  y_i = fs_i c_i + fp_i y_{i-2}                             in place on the scratch
+//   pass 3 (last column to first)  x_i = y_i + bp_i x_{i+2};   ux_i -= x1_i,  uy_i -= x2_i                  (683-695)
+// w1[j] = {nsd_j, nsl_{j-2}, w_j nsd_{j+1}, w_j nsl_{j-1}, sd_j, sl_j, 0, 0}, w_j = 2 (j+1) / sy;  w2[i] = {fs_i, fp_i, bp_i, 0}
+// (pw_project_tables).
+FK_DEV void pw_project_pass1(const PProjectArgs& a, double* ring, int r0, int lane) {
+  constexpr int NC = PW_CB + 2, O_T = 3 * PW_ARR, SLOT = O_T + PW_CB * 8;
+  const int n = a.ny, m = n - 2;
+  const PwLane L = pw_lane(r0, lane, a.phi.rows);
+  const int nbat = (n + PW_CB - 1) / PW_CB;
+  auto issue = [&](int b) {
+    if (b >= 0) {
+      double* s = ring + (b % PW_D) * SLOT;
+      pw_stage_c<NC>(s, a.phi, r0, b * PW_CB - 2, lane);  // columns j - 2 .. j - 1 of every j of the batch
+      pw_stage_c<PW_CB>(s + PW_ARR, a.div, r0, b * PW_CB, lane);
+      pw_stage_c<PW_CB>(s + 2 * PW_ARR, a.pres, r0, b * PW_CB, lane);
+      pw_stage_tab<8, PW_CB>(s + O_T, a.w1, n, b * PW_CB, lane);
+    }
+    cp_async_commit();
+  };
+  for (int b = 0; b < PW_K; ++b) issue(nbat - 1 - b);
+  const double ks = a.isx * (double)(a.k0 + min(L.r, a.phi.rows - 1));
+  double fown = 0.0, foth = 0.0;  // phi_j, phi_{j+1}: what the previous step read as phi_{j-2}, phi_{j-1}
+  double acc = 0.0, tprev = 0.0, dprev = 0.0;
+  for (int b = nbat - 1; b >= 0; --b) {
+    issue(b - PW_K);
+    cp_async_wait<PW_K>();
+    __syncwarp();
+    const double* s = ring + (b % PW_D) * SLOT;
+    const int so = (L.rl * PW_PC) * 2 + L.part;
+    double f2[PW_CB / 2], f1[PW_CB / 2], dv[PW_CB / 2], pv[PW_CB / 2];
+#pragma unroll
+    for (int u = 0; u < PW_CB / 2; ++u) {
+      const int c = 2 * u + L.p;
+      f2[u] = s[so + c * 2];        // phi_{j-2}
+      f1[u] = s[so + (c + 1) * 2];  // phi_{j-1}
+      dv[u] = s[PW_ARR + so + c * 2];
+      pv[u] = s[2 * PW_ARR + so + c * 2];
+    }
+#pragma unroll
+    for (int u = PW_CB / 2 - 1; u >= 0; --u) {
+      const int c = 2 * u + L.p, j = b * PW_CB + c;
+      const double2 t0 = *(const double2*)&s[O_T + c * 8], t1 = *(const double2*)&s[O_T + c * 8 + 2],
+                    t2 = *(const double2*)&s[O_T + c * 8 + 4];
+      const double o = fma(t0.y, f2[u], t0.x * fown);  // o_j
+      acc = acc + fma(t1.y, f1[u], t1.x * foth);       // + (2 (j+1) / sy) o_{j+1}
+      fown = f2[u], foth = f1[u];
+      if (L.rok && j < n) a.pres.p[((size_t)L.r * a.pres.ld + j) * 2 + L.part] = fma(-a.nu, dv[u], pv[u]) + o * a.inv_dt;
+      const double oo = __shfl_xor_sync(0xffffffffu, o, 1);  // the other part of o_j
+      const double t = L.part ? ks * oo : -ks * oo;           // (i k / sx o).part: re' = -ks im, im' = ks re
+      const double d = (j == 0) ? 0.5 * acc : acc;
+      const double c1 = fma(t2.y, tprev, t2.x * t), c2 = fma(t2.y, dprev, t2.x * d);
+      tprev = t, dprev = d;
+      if (L.rok && j < m) {
+        a.z1.p[((size_t)L.r * a.z1.ld + j) * 2 + L.part] = c1;
+        a.z2.p[((size_t)L.r * a.z2.ld + j) * 2 + L.part] = c2;
+      }
+    }
+    __syncwarp();
+  }
+}
+FK_DEV void pw_project_pass2(const PProjectArgs& a, double* ring, int r0, int lane) {
+  constexpr int O_T = 2 * PW_ARR, SLOT = O_T + PW_CB * 4;
+  const int m = a.ny - 2;
+  const PwLane L = pw_lane(r0, lane, a.phi.rows);
+  const int nbat = (m + PW_CB - 1) / PW_CB;
+  auto issue = [&](int b) {
+    if (b < nbat) {
+      double* s = ring + (b % PW_D) * SLOT;
+      pw_stage_c<PW_CB>(s, a.z1, r0, b * PW_CB, lane);
+      pw_stage_c<PW_CB>(s + PW_ARR, a.z2, r0, b * PW_CB, lane);
+      pw_stage_tab<4, PW_CB>(s + O_T, a.w2, m, b * PW_CB, lane);
+    }
+    cp_async_commit();
+  };
+  for (int b = 0; b < PW_K; ++b) issue(b);
+  double y1 = 0.0, y2 = 0.0;
+  for (int b = 0; b < nbat; ++b) {
+    issue(b + PW_K);
+    cp_async_wait<PW_K>();
+    __syncwarp();
+    const double* s = ring + (b % PW_D) * SLOT;
+    const int so = (L.rl * PW_PC) * 2 + L.part;
+    double ca[PW_CB / 2], cb[PW_CB / 2];
+    double2 ff[PW_CB / 2];
+#pragma unroll
+    for (int u = 0; u < PW_CB / 2; ++u) {
+      const int c = 2 * u + L.p;
+      ca[u] = s[so + c * 2], cb[u] = s[PW_ARR + so + c * 2];
+      ff[u] = *(const double2*)&s[O_T + c * 4];  // fs, fp
+    }
+#pragma unroll
+    for (int u = 0; u < PW_CB / 2; ++u) {
+      const int i = b * PW_CB + 2 * u + L.p;
+      y1 = fma(ff[u].y, y1, ff[u].x * ca[u]);
+      y2 = fma(ff[u].y, y2, ff[u].x * cb[u]);
+      if (L.rok && i < m) {
+        a.z1.p[((size_t)L.r * a.z1.ld + i) * 2 + L.part] = y1;
+        a.z2.p[((size_t)L.r * a.z2.ld + i) * 2 + L.part] = y2;
+      }
+    }
+    __syncwarp();
+  }
+}
+FK_DEV void pw_project_pass3(const PProjectArgs& a, double* ring, int r0, int lane) {
+  constexpr int O_T = 4 * PW_ARR, SLOT = O_T + PW_CB * 4;
+  const int m = a.ny - 2;
+  const PwLane L = pw_lane(r0, lane, a.phi.rows);
+  const int nbat = (m + PW_CB - 1) / PW_CB;
+  auto issue = [&](int b) {
+    if (b >= 0) {
+      double* s = ring + (b % PW_D) * SLOT;
+      pw_stage_c<PW_CB>(s, a.z1, r0, b * PW_CB, lane);
+      pw_stage_c<PW_CB>(s + PW_ARR, a.z2, r0, b * PW_CB, lane);
+      pw_stage_c<PW_CB>(s + 2 * PW_ARR, a.ux, r0, b * PW_CB, lane);
+      pw_stage_c<PW_CB>(s + 3 * PW_ARR, a.uy, r0, b * PW_CB, lane);
+      pw_stage_tab<4, PW_CB>(s + O_T, a.w2, m, b * PW_CB, lane);
+    }
+    cp_async_commit();
+  };
+  for (int b = 0; b < PW_K; ++b) issue(nbat - 1 - b);
+  double x1 = 0.0, x2 = 0.0;
+  for (int b = nbat - 1; b >= 0; --b) {
+    issue(b - PW_K);
+    cp_async_wait<PW_K>();
+    __syncwarp();
+    const double* s = ring + (b % PW_D) * SLOT;
+    const int so = (L.rl * PW_PC) * 2 + L.part;
+    double ya[PW_CB / 2], yb[PW_CB / 2], ua[PW_CB / 2], ub[PW_CB / 2], bp[PW_CB / 2];
+#pragma unroll
+    for (int u = 0; u < PW_CB / 2; ++u) {
+      const int c = 2 * u + L.p;
+      ya[u] = s[so + c * 2], yb[u] = s[PW_ARR + so + c * 2];
+      ua[u] = s[2 * PW_ARR + so + c * 2], ub[u] = s[3 * PW_ARR + so + c * 2];
+      bp[u] = s[O_T + c * 4 + 2];  // zero beyond the last column (staged zeros): x stays 0 until the first real one
+    }
+#pragma unroll
+    for (int u = PW_CB / 2 - 1; u >= 0; --u) {
+      const int i = b * PW_CB + 2 * u + L.p;
+      x1 = fma(bp[u], x1, ya[u]);
+      x2 = fma(bp[u], x2, yb[u]);
+      if (L.rok && i < m) {
+        a.ux.p[((size_t)L.r * a.ux.ld + i) * 2 + L.part] = ua[u] - x1;
+        a.uy.p[((size_t)L.r * a.uy.ld + i) * 2 + L.part] = ub[u] - x2;
+      }
+    }
+    __syncwarp();
+  }
+}
+constexpr int PW_PRJ_SLOT = 4 * PW_ARR + PW_CB * 4 > 3 * PW_ARR + PW_CB * 8 ? 4 * PW_ARR + PW_CB * 4 : 3 * PW_ARR + PW_CB * 8;
+constexpr int PW_PRJ_WARP = PW_D * PW_PRJ_SLOT;
 constexpr int pw_fwd_slot(int na) { return na * PW_ARR + 8 * PW_PR + PW_CB * 10 + 8; }
 constexpr int PW_BWD_SLOT = PW_ARR + 8 * PW_PR + PW_CB * 8;
 constexpr int pw_warp_doubles(int na) { return PW_D * (pw_fwd_slot(na) > PW_BWD_SLOT ? pw_fwd_slot(na) : PW_BWD_SLOT); }
@@ -367,6 +524,20 @@ __global__ void __launch_bounds__(32 * PW_WPB) pw_divpois(PDivPoisArgs a, int wa
   cp_async_wait<0>();
 }
 
+__global__ void __launch_bounds__(32 * PW_WPB) pw_project(PProjectArgs a) {
+  RP_DYN_SMEM(double, smem);
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r0 = (blockIdx.x * PW_WPB + wib) * 8;
+  double* ring = smem + wib * PW_PRJ_WARP;
+  if (r0 >= a.phi.rows) return;
+  pw_project_pass1(a, ring, r0, lane);
+  pw_pass_fence();
+  pw_project_pass2(a, ring, r0, lane);
+  pw_pass_fence();
+  pw_project_pass3(a, ring, r0, lane);
+  cp_async_wait<0>();
+}
+
 // ---------------------------------------------------------------------------------
 // Which kernel runs a per-mode pass of `rows` complex rows.  The row sweeps are bound by the latency of one chain
 // (a fixed ~0.12 us per column pair and pass, whatever the row count) until there are enough rows to fill the machine,
@@ -377,6 +548,15 @@ bool pw_enabled(int rows, bool divpois) {
   if (e && e[0] == '0') return false;
   if (e && e[0] == '1') return true;
   return rows >= (divpois ? 1280 : 448);  // (three fields in one launch: navier.cu)
+}
+bool pw_project_enabled(int rows) {  // projection + pressure update: one field, two passes
+  const char* e = getenv("RUSTPDE_B200_PW");
+  if (e && e[0] == '0') return false;
+  if (e && e[0] == '1') return true;
+  // three latency-bound passes (~0.29 us per column pair in all, whatever the row count) against ~0.15 .. 0.8 us per row
+  // of the tile kernel: measured on a B200 at 8192 x 8193 (4097 rows) 1.58 ms against 3.22 ms, at 2048 x 2049 (1025 rows)
+  // 0.298 ms against 0.152 ms
+  return rows >= 1536;
 }
 
 template <class K>
@@ -394,6 +574,36 @@ void launch_pw_hholtz(const PHholtzArgs3& a, int nb, cudaStream_t s) {
   if (first_use_on_device(init_)) pw_prepare(pw_hholtz, SMEM);
   const int nwarps = (a.a[0].chat.rows + 7) / 8;
   RP_LAUNCH(pw_hholtz, dim3((nwarps + PW_WPB - 1) / PW_WPB, nb), dim3(32 * PW_WPB), (size_t)SMEM, s, a, WD);
+}
+// Coefficient rows of pw_project: nsd / nsl = Neumann stencil of phi along y (m entries), sd / sl = Dirichlet stencil of the
+// velocity, fs / fp / bp = its pre-factored (S^T S) solve (tables.cu)
+void pw_project_tables(int n, double isy, const std::vector<double>& nsd, const std::vector<double>& nsl, const std::vector<double>& sd,
+                       const std::vector<double>& sl, const std::vector<double>& fs, const std::vector<double>& fp,
+                       const std::vector<double>& bp, std::vector<double>& w1, std::vector<double>& w2) {
+  const int m = n - 2;
+  auto at = [](const std::vector<double>& v, int i) { return (i >= 0 && i < (int)v.size()) ? v[i] : 0.0; };
+  w1.assign((size_t)n * 8, 0.0);
+  w2.assign((size_t)m * 4, 0.0);
+  for (int j = 0; j < n; ++j) {
+    double* r = &w1[(size_t)j * 8];
+    const double w = (j + 1 <= n - 1) ? 2.0 * (double)(j + 1) * isy : 0.0;
+    if (j < m) r[0] = at(nsd, j);
+    r[1] = at(nsl, j - 2);
+    if (j + 1 < m) r[2] = w * at(nsd, j + 1);
+    r[3] = w * at(nsl, j - 1);
+    if (j < m) r[4] = at(sd, j), r[5] = at(sl, j);
+  }
+  for (int i = 0; i < m; ++i) {
+    double* r = &w2[(size_t)i * 4];
+    r[0] = at(fs, i), r[1] = at(fp, i), r[2] = at(bp, i);
+  }
+}
+void launch_pw_project(const PProjectArgs& a, cudaStream_t s) {
+  constexpr int SMEM = PW_WPB * PW_PRJ_WARP * 8;
+  static unsigned long long init_ = 0;
+  if (first_use_on_device(init_)) pw_prepare(pw_project, SMEM);
+  const int nwarps = (a.phi.rows + 7) / 8;
+  RP_LAUNCH(pw_project, dim3((nwarps + PW_WPB - 1) / PW_WPB, 1), dim3(32 * PW_WPB), (size_t)SMEM, s, a);
 }
 void launch_pw_divpois(const PDivPoisArgs& a, cudaStream_t s) {
   constexpr int WD = pw_warp_doubles(2), SMEM = PW_WPB * WD * 8;

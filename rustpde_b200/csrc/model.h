@@ -309,6 +309,7 @@ class Navier2D {
   std::function<void()> fast_dyp_, fast_div_;  // specialised refresh of d/dy pres and divergence of (ux, uy), when available
   std::vector<DevBuf> perm_;  // chunk-major coefficient tables of the specialised kernels (fast.h perm_table)
   const double* pw_rs_[4] = {nullptr, nullptr, nullptr, nullptr};  // stencil tables of the warp-serial periodic passes (fast_pw.cu): ux, uy, temp, divergence
+  const double* pw_prj_[2] = {nullptr, nullptr};  // pw_project_tables (fast_pw.cu)
   void build_pw_tables();
   std::map<const void*, std::pair<const double*, const double*>> perm_mode_;
   std::map<std::pair<const void*, int>, std::pair<const double*, const double*>> perm_tdma_;

@@ -976,6 +976,16 @@ void Navier2D::build_step_confined_fast() {
 // field's own y base and of the temperature's; for the divergence {sd_j, sl_{j-2}, 2 j / sy, 0}
 void Navier2D::build_pw_tables() {
   if (pw_rs_[0]) return;
+  {  // projection + pressure update as row sweeps: Neumann stencil of phi, Dirichlet stencil of the velocity along y
+    const Base &bn = *pres1->sp.b1, &bu = *ux->sp.b1;
+    std::vector<double> t1, t2;
+    fk::pw_project_tables(ny, 1.0 / scale[1], host_of(bn.d_sd), host_of(bn.d_sl), host_of(bu.d_sd), host_of(bu.d_sl), host_of(bu.d_tfs),
+                          host_of(bu.d_tfp), host_of(bu.d_tbp), t1, t2);
+    perm_.push_back(upload(t1));
+    pw_prj_[0] = perm_.back().as<double>();
+    perm_.push_back(upload(t2));
+    pw_prj_[1] = perm_.back().as<double>();
+  }
   const Base &byu = *ux->sp.b1, &byt = *temp->sp.b1;
   const Base* bys[3] = {&byu, &byu, &byt};
   const std::vector<double> tsd = host_of(byt.d_sd), tsl = host_of(byt.d_sl);
@@ -1108,6 +1118,11 @@ void Navier2D::build_step_periodic_fast() {
     a.isx = isx, a.isy = isy, a.nu = nu, a.inv_dt = 1.0 / dt;
     a.ny = ny;
     a.k0 = 0;
+    build_pw_tables();
+    a.w1 = pw_prj_[0], a.w2 = pw_prj_[1];
+    // scratch of the row-sweep form: chat_[0], chat_[1] (consumed by the Helmholtz pass), viewed as [mk, my]
+    a.z1 = mat_of(chat_[0]), a.z2 = mat_of(chat_[1]);
+    a.z1.cols = a.z2.cols = ny - 2;
     add_fast("project_pressure_update", 8 * fb, [this, a]() { fk::launch_p_project(a, stream); });
   }
 }
@@ -1280,6 +1295,10 @@ void Navier2D::slab_phase3(int k0, int mkl, const double* const in[3]) {
     a.isx = isx, a.isy = isy, a.nu = nu, a.inv_dt = 1.0 / dt;
     a.ny = ny;
     a.k0 = k0;
+    build_pw_tables();
+    a.w1 = pw_prj_[0], a.w2 = pw_prj_[1];
+    a.z1 = row_slab(chat_[0], k0, mkl), a.z2 = row_slab(chat_[1], k0, mkl);
+    a.z1.cols = a.z2.cols = ny - 2;
     fk::launch_p_project(a, stream);
   }
   time += dt;

@@ -278,9 +278,9 @@ def test_column_scan_kernels_agree_with_tile_kernels(emu, monkeypatch):
 
 
 def test_periodic_row_sweeps_agree_with_tile_kernels(emu, monkeypatch):
-    """The per-mode Helmholtz / Poisson passes of the periodic step as warp-serial row sweeps (fast_pw.cu, chosen for
-    large row counts; forced here with RUSTPDE_B200_PW=1) versus the tile kernels pk_hholtz / pk_divpois
-    (RUSTPDE_B200_PW=0): same step to rounding, ragged row counts included."""
+    """The per-mode Helmholtz / Poisson passes and the projection + pressure update of the periodic step as warp-serial
+    row sweeps (fast_pw.cu, chosen for large row counts; forced here with RUSTPDE_B200_PW=1) versus the tile kernels
+    pk_hholtz / pk_divpois / pk_project (RUSTPDE_B200_PW=0): same step to rounding, ragged row counts included."""
     import rustpde_b200 as R
     for nx, ny in ((32, 33), (64, 65), (128, 33)):
         outs = []

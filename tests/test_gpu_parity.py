@@ -184,8 +184,9 @@ def test_navier_periodic_specialised_kernels(gpu, nx, ny, steps):
 @pytest.mark.parametrize("pw", ["0", "1"])
 @pytest.mark.parametrize("nx,ny,steps", [(32, 33, 6), (64, 65, 20), (512, 513, 10), (2048, 2049, 2), (64, 8193, 3), (8192, 65, 3)])
 def test_navier_periodic_row_sweeps_and_tile_kernels(gpu, monkeypatch, nx, ny, steps, pw):
-    """The per-mode Helmholtz / Poisson passes forced onto the warp-serial row sweeps (fast_pw.cu, RUSTPDE_B200_PW=1)
-    and onto the tile kernels (=0) at every size; by default the row count picks one (rows >= 448 / 1280)."""
+    """The per-mode Helmholtz / Poisson passes and the projection + pressure update forced onto the warp-serial row sweeps
+    (fast_pw.cu, RUSTPDE_B200_PW=1) and onto the tile kernels (=0) at every size; by default the row count picks one
+    (rows >= 448 / 1280 / 1536)."""
     monkeypatch.setenv("RUSTPDE_B200_PW", pw)
     ra, dt = (1e6, 2e-3) if nx < 1000 else (1e9, 1e-4)
     err, derr, dn, do = pc.check_navier_steps(gpu, True, nx, ny, steps, ra=ra, dt=dt, tol=1e-9, batch=5)
