@@ -5,6 +5,7 @@
 mkdir -p gpurun_out
 T=${1:-r3}
 timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -6 > gpurun_out/${T}_tests.log
+timeout 300 python __graft_entry__.py --smoke > gpurun_out/${T}_smoke.log 2>&1
 timeout 400 python bench.py > gpurun_out/${T}_bench_default.json 2> gpurun_out/${T}_bench_default.err
 timeout 400 python bench.py --impl reference --steps 4 --warmup 1 > gpurun_out/${T}_bench_reference.json 2> gpurun_out/${T}_bench_reference.err
 for w in periodic2048 periodic512 confined64 confined1024 hholtz1024; do
@@ -19,13 +20,13 @@ for k in xk_backward xk_forward xw_adi yk_backward; do
   python scripts/ncu_summary.py gpurun_out/${T}_$k.ncu-rep > gpurun_out/${T}_ncu_${k}_confined2048.txt 2>> gpurun_out/${T}_ncu_$k.log
   rm -f gpurun_out/${T}_$k.ncu-rep
 done
-for k in pw_hholtz pw_divpois; do
+for k in pw_hholtz pw_divpois pw_project; do
   RUSTPDE_B200_PW=1 timeout 300 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:$k -c 1 -f -o gpurun_out/${T}_$k \
       python scripts/ncu_step.py p 2048 2049 1 > gpurun_out/${T}_ncu_$k.log 2>&1
   python scripts/ncu_summary.py gpurun_out/${T}_$k.ncu-rep > gpurun_out/${T}_ncu_${k}_periodic2048.txt 2>> gpurun_out/${T}_ncu_$k.log
   rm -f gpurun_out/${T}_$k.ncu-rep
 done
-cat gpurun_out/${T}_tests.log
+cat gpurun_out/${T}_tests.log; tail -4 gpurun_out/${T}_smoke.log
 python - <<PY
 import json
 for f in ['bench_default','bench_reference','periodic2048','periodic512','confined64','confined1024','hholtz1024','p8192_1gpu']:
