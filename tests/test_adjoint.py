@@ -46,7 +46,8 @@ def test_adjoint(emu, periodic, nx, ny):
     check_adjoint(emu, periodic, nx, ny)
 
 
-def test_adjoint_integrate(emu):
+def test_adjoint_integrate(emu, tmp_path, monkeypatch):
+    monkeypatch.chdir(tmp_path)  # (callback() may write to ./data)
     a = R.Navier2DAdjoint.new(24, 33, 1e4, 1.0, 0.01, 1.0, True, lib=emu)
     a.set_velocity(0.2, 1.0, 1.0)
     a.set_temperature(0.2, 1.0, 1.0)

@@ -65,9 +65,11 @@ def test_snapshot_roundtrip(emu, tmp_path, periodic, nx, ny):
     assert check_snapshot_roundtrip(emu, periodic, nx, ny, tmp_path)
 
 
-def test_callback_writes_snapshot_and_info(emu, tmp_path):
+def test_callback_writes_snapshot_and_info(emu, tmp_path, monkeypatch):
+    monkeypatch.chdir(tmp_path)  # integrate() -> callback() writes to ./data like the reference (navier.rs:775-853)
     n = make(emu, False, 20, 20)
     R.integrate(n, 0.05, 0.02)
+    assert sorted(p.name for p in (tmp_path / "data").iterdir())[-1] == "info.txt"
     # callback() ran at t = 0.02 and 0.04 (src/lib.rs:165-172)
     n.callback(data_dir=str(tmp_path))
     files = sorted(p.name for p in tmp_path.iterdir())
