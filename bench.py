@@ -180,6 +180,8 @@ def time_cpu(wl, want_steps, warmup, budget_s, eig=None):
     """Time the CPU restatement of update(); returns (steps_per_s, description, threads, kind)."""
     T = cpu_twin()
     if T is not None:
+        if not os.environ.get("RUSTPDE_TWIN_THREADS"):
+            T.set_threads(host_threads())  # all host CPUs like rayon, also under torchrun (which exports OMP_NUM_THREADS=1)
         o = T.make_navier(wl, eig)
         kind_desc = "C++ lane-parallel restatement (oracle/cpu_twin, %d threads, OPENBLAS_NUM_THREADS=%s)" % (T.threads(), os.environ.get("OPENBLAS_NUM_THREADS"))
         threads = T.threads()

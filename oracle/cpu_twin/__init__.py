@@ -76,6 +76,12 @@ def threads():
     return _load().tw_set_threads(0)
 
 
+def set_threads(n):
+    """Lane-parallel threads of the twin (rayon's default in the reference = all host CPUs).  torchrun exports
+    OMP_NUM_THREADS=1 to its workers, which would otherwise leave the twin on one thread."""
+    return _load().tw_set_threads(int(n))
+
+
 class TwinNavier:
     """Navier2D::new / new_periodic + set_velocity(0.2,1,1) + set_temperature(0.2,1,1) style runs on the CPU twin."""
 
