@@ -483,10 +483,13 @@ constexpr int PW_BWD_SLOT = PW_ARR + 8 * PW_PR + PW_CB * 8;
 constexpr int pw_warp_doubles(int na) { return PW_D * (pw_fwd_slot(na) > PW_BWD_SLOT ? pw_fwd_slot(na) : PW_BWD_SLOT); }
 }  // namespace
 
-__global__ void __launch_bounds__(32 * PW_WPB) pw_hholtz(PHholtzArgs3 a3, int warp_doubles) {
+// (one warp per block here: the ring of the five-array rhs assembly is 43 KB per warp, and five one-warp blocks fit an SM
+// where two two-warp blocks do -- 2.96 -> 2.73 ms at 8192 x 8193)
+constexpr int PW_HH_WPB = 1;
+__global__ void __launch_bounds__(32 * PW_HH_WPB) pw_hholtz(PHholtzArgs3 a3, int warp_doubles) {
   RP_DYN_SMEM(double, smem);
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int r0 = (blockIdx.x * PW_WPB + wib) * 8;
+  const int r0 = (blockIdx.x * PW_HH_WPB + wib) * 8;
   double* ring = smem + wib * warp_doubles;
   // blockIdx.y selects the field; the branch is block-uniform and keeps the arguments direct constant-bank operands
   const PHholtzArgs& a = blockIdx.y == 0 ? a3.a[0] : (blockIdx.y == 1 ? a3.a[1] : a3.a[2]);
@@ -569,11 +572,11 @@ static void pw_prepare(K kern, int bytes) {
 #endif
 }
 void launch_pw_hholtz(const PHholtzArgs3& a, int nb, cudaStream_t s) {
-  constexpr int WD = pw_warp_doubles(5), SMEM = PW_WPB * WD * 8;
+  constexpr int WD = pw_warp_doubles(5), SMEM = PW_HH_WPB * WD * 8;
   static unsigned long long init_ = 0;  // one bit per device
   if (first_use_on_device(init_)) pw_prepare(pw_hholtz, SMEM);
   const int nwarps = (a.a[0].chat.rows + 7) / 8;
-  RP_LAUNCH(pw_hholtz, dim3((nwarps + PW_WPB - 1) / PW_WPB, nb), dim3(32 * PW_WPB), (size_t)SMEM, s, a, WD);
+  RP_LAUNCH(pw_hholtz, dim3((nwarps + PW_HH_WPB - 1) / PW_HH_WPB, nb), dim3(32 * PW_HH_WPB), (size_t)SMEM, s, a, WD);
 }
 // Coefficient rows of pw_project: nsd / nsl = Neumann stencil of phi along y (m entries), sd / sl = Dirichlet stencil of the
 // velocity, fs / fp / bp = its pre-factored (S^T S) solve (tables.cu)
